@@ -1,0 +1,249 @@
+"""oracle -- TEST INFRASTRUCTURE ONLY.
+
+ctypes view of ``oracle/liboracle.so``, the plain-C CPU restatement of the
+reference's generic module-lattice path (see ``oracle/oracle.h``).  Only
+``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s cpu_baseline /
+``--impl reference`` legs may import this package; nothing under
+``circl_b200/`` does.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so with the committed Makefile (gcc only)."""
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".c", ".h"))]
+    stale = (not os.path.exists(_LIB_PATH)) or any(
+        os.path.getmtime(s) > os.path.getmtime(_LIB_PATH) for s in srcs
+    )
+    if force or stale:
+        subprocess.run(["make", "-C", _HERE, "-B", "liboracle.so"], check=True, capture_output=True)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        build()
+        _lib = C.CDLL(_LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+_u8p = C.POINTER(C.c_uint8)
+_i16p = C.POINTER(C.c_int16)
+_u32p = C.POINTER(C.c_uint32)
+
+
+def _declare(L: C.CDLL) -> None:
+    L.orc_kyber_mont_reduce.restype = C.c_int16
+    L.orc_kyber_mont_reduce.argtypes = [C.c_int32]
+    L.orc_kyber_barrett_reduce.restype = C.c_int16
+    L.orc_kyber_barrett_reduce.argtypes = [C.c_int16]
+    L.orc_kyber_csubq.restype = C.c_int16
+    L.orc_kyber_csubq.argtypes = [C.c_int16]
+    L.orc_kyber_zetas.restype = _i16p
+    for name in ("orc_mlkem_ek_size", "orc_mlkem_dk_size", "orc_mlkem_ct_size"):
+        getattr(L, name).restype = C.c_size_t
+        getattr(L, name).argtypes = [C.c_int]
+    L.orc_mlkem_encaps_batch.restype = C.c_int
+    L.orc_mlkem_encaps_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                         C.c_void_p, C.c_size_t, C.c_int]
+    L.orc_kyber_ntt_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+    L.orc_kyber_mulhat_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+    L.orc_kyber_dot_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]
+    if hasattr(L, "orc_dil_ntt_batch"):
+        L.orc_dil_ntt_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_int]
+        L.orc_dil_mulhat_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_mldsa65_sign_batch.restype = C.c_int
+        L.orc_mldsa65_sign_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p,
+                                             C.c_void_p, C.c_size_t, C.c_int]
+
+
+def _buf(b) -> C.Array:
+    return (C.c_uint8 * len(b)).from_buffer_copy(bytes(b))
+
+
+def _ptr(a: np.ndarray):
+    assert a.flags["C_CONTIGUOUS"]
+    return a.ctypes.data_as(C.c_void_p)
+
+
+# ------------------------------------------------------------------ Keccak
+def keccak_f1600(state25) -> list[int]:
+    a = (C.c_uint64 * 25)(*state25)
+    lib().orc_keccak_f1600(a)
+    return list(a)
+
+
+def _hash(fn, outlen: int, data: bytes) -> bytes:
+    out = (C.c_uint8 * outlen)()
+    if fn in ("orc_sha3_256", "orc_sha3_512"):
+        getattr(lib(), fn)(out, _buf(data) if data else None, C.c_size_t(len(data)))
+    else:
+        getattr(lib(), fn)(out, C.c_size_t(outlen), _buf(data) if data else None, C.c_size_t(len(data)))
+    return bytes(out)
+
+
+def sha3_256(data: bytes) -> bytes:
+    return _hash("orc_sha3_256", 32, data)
+
+
+def sha3_512(data: bytes) -> bytes:
+    return _hash("orc_sha3_512", 64, data)
+
+
+def shake128(data: bytes, outlen: int) -> bytes:
+    return _hash("orc_shake128", outlen, data)
+
+
+def shake256(data: bytes, outlen: int) -> bytes:
+    return _hash("orc_shake256", outlen, data)
+
+
+# ------------------------------------------------------------------ Kyber polys
+def kyber_zetas() -> np.ndarray:
+    return np.ctypeslib.as_array(lib().orc_kyber_zetas(), shape=(128,)).copy()
+
+
+def _poly_unary(fn: str, p: np.ndarray) -> np.ndarray:
+    q = np.ascontiguousarray(p, dtype=np.int16).copy()
+    flat = q.reshape(-1, 256)
+    f = getattr(lib(), fn)
+    for row in flat:
+        f(_ptr(row))
+    return q
+
+
+def kyber_ntt(p):
+    q = np.ascontiguousarray(p, dtype=np.int16).copy()
+    lib().orc_kyber_ntt_batch(_ptr(q), q.size // 256, 0)
+    return q
+
+
+def kyber_invntt(p):
+    q = np.ascontiguousarray(p, dtype=np.int16).copy()
+    lib().orc_kyber_ntt_batch(_ptr(q), q.size // 256, 1)
+    return q
+
+
+def kyber_mulhat(a, b):
+    a = np.ascontiguousarray(a, dtype=np.int16)
+    b = np.ascontiguousarray(b, dtype=np.int16)
+    out = np.empty_like(a)
+    lib().orc_kyber_mulhat_batch(_ptr(out), _ptr(a), _ptr(b), a.size // 256)
+    return out
+
+
+def kyber_dot(a, b, k: int):
+    """a, b: (n, k, 256) -> (n, 256) PolyDotHat."""
+    a = np.ascontiguousarray(a, dtype=np.int16)
+    b = np.ascontiguousarray(b, dtype=np.int16)
+    n = a.size // (256 * k)
+    out = np.empty((n, 256), dtype=np.int16)
+    lib().orc_kyber_dot_batch(_ptr(out), _ptr(a), _ptr(b), k, n)
+    return out
+
+
+def kyber_barrett(p):
+    return _poly_unary("orc_kyber_barrett", p)
+
+
+def kyber_normalize(p):
+    return _poly_unary("orc_kyber_normalize", p)
+
+
+def kyber_tomont(p):
+    return _poly_unary("orc_kyber_tomont", p)
+
+
+def kyber_pack(p) -> bytes:
+    out = (C.c_uint8 * 384)()
+    lib().orc_kyber_pack(out, _ptr(np.ascontiguousarray(p, dtype=np.int16)))
+    return bytes(out)
+
+
+def kyber_unpack(buf: bytes) -> np.ndarray:
+    p = np.empty(256, dtype=np.int16)
+    lib().orc_kyber_unpack(_ptr(p), _buf(buf))
+    return p
+
+
+def kyber_compress(p, d: int) -> bytes:
+    out = (C.c_uint8 * (32 * d))()
+    lib().orc_kyber_compress(out, _ptr(np.ascontiguousarray(p, dtype=np.int16)), d)
+    return bytes(out)
+
+
+def kyber_decompress(buf: bytes, d: int) -> np.ndarray:
+    p = np.empty(256, dtype=np.int16)
+    lib().orc_kyber_decompress(_ptr(p), _buf(buf), d)
+    return p
+
+
+def kyber_derive_noise(seed: bytes, nonce: int, eta: int) -> np.ndarray:
+    p = np.empty(256, dtype=np.int16)
+    lib().orc_kyber_derive_noise(_ptr(p), _buf(seed), C.c_size_t(len(seed)), C.c_uint8(nonce), eta)
+    return p
+
+
+def kyber_derive_uniform(seed: bytes, x: int, y: int) -> np.ndarray:
+    p = np.empty(256, dtype=np.int16)
+    lib().orc_kyber_derive_uniform(_ptr(p), _buf(seed), C.c_uint8(x), C.c_uint8(y))
+    return p
+
+
+# ------------------------------------------------------------------ ML-KEM
+def mlkem_sizes(k: int):
+    L = lib()
+    return L.orc_mlkem_ek_size(k), L.orc_mlkem_dk_size(k), L.orc_mlkem_ct_size(k)
+
+
+def mlkem_keygen(k: int, seed64: bytes):
+    eksz, dksz, _ = mlkem_sizes(k)
+    ek = (C.c_uint8 * eksz)()
+    dk = (C.c_uint8 * dksz)()
+    lib().orc_mlkem_keygen(k, ek, dk, _buf(seed64))
+    return bytes(ek), bytes(dk)
+
+
+def mlkem_encaps(k: int, ek: bytes, m: bytes):
+    _, _, ctsz = mlkem_sizes(k)
+    ct = (C.c_uint8 * ctsz)()
+    ss = (C.c_uint8 * 32)()
+    rc = lib().orc_mlkem_encaps(k, ct, ss, _buf(ek), _buf(m))
+    if rc:
+        raise ValueError("kem.ErrPubKey")
+    return bytes(ct), bytes(ss)
+
+
+def mlkem_decaps(k: int, dk: bytes, ct: bytes) -> bytes:
+    ss = (C.c_uint8 * 32)()
+    rc = lib().orc_mlkem_decaps(k, ss, _buf(dk), _buf(ct))
+    if rc:
+        raise ValueError("kem.ErrPrivKey")
+    return bytes(ss)
+
+
+def mlkem_encaps_batch(k: int, ek: np.ndarray, m: np.ndarray, nthreads: int = 1):
+    """ek: (n, eksz) or (eksz,) uint8 (shared); m: (n, 32) uint8."""
+    _, _, ctsz = mlkem_sizes(k)
+    m = np.ascontiguousarray(m, dtype=np.uint8)
+    ek = np.ascontiguousarray(ek, dtype=np.uint8)
+    n = m.shape[0]
+    stride = 0 if ek.ndim == 1 else ek.shape[1]
+    ct = np.empty((n, ctsz), dtype=np.uint8)
+    ss = np.empty((n, 32), dtype=np.uint8)
+    fails = lib().orc_mlkem_encaps_batch(k, _ptr(ct), _ptr(ss), _ptr(ek), stride, _ptr(m), n, nthreads)
+    return ct, ss, fails

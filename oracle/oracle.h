@@ -1,0 +1,88 @@
+/*
+ * oracle/oracle.h -- TEST INFRASTRUCTURE ONLY.
+ *
+ * CPU restatement (plain C) of the *generic* (purego) code path of
+ * cloudflare/circl for the module-lattice hot path (ML-KEM / ML-DSA).
+ * It is the parity checker for the CUDA product in circl_b200/ and the
+ * "port" CPU baseline of bench.py.  Nothing under circl_b200/ may link,
+ * import or call this.  Only tests/, __graft_entry__.smoke() and bench.py's
+ * cpu_baseline / --impl reference legs use it.
+ *
+ * Pinning: see tests/test_oracle_*.py -- NIST ACVP vectors (FIPS 203/204),
+ * PQCgenKAT transcript hashes, the reference's embedded sampler vectors and
+ * Keccak KATs, all extracted from /root/reference by tests/golden/make_golden.py.
+ *
+ * All file:line citations are relative to the reference repository root.
+ */
+#ifndef CIRCL_B200_ORACLE_H
+#define CIRCL_B200_ORACLE_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---------------- Keccak (internal/sha3) ---------------- */
+void orc_keccak_f1600(uint64_t a[25]);                       /* keccakf.go:12 */
+typedef struct {
+  uint64_t a[25];
+  unsigned rate, pos;
+  uint8_t ds;
+  int squeezing;
+} orc_sponge;
+void orc_sponge_init(orc_sponge *s, unsigned rate, uint8_t ds); /* hashes.go:21,35; shake.go:56,74 */
+void orc_sponge_write(orc_sponge *s, const uint8_t *p, size_t n); /* sha3.go:128 */
+void orc_sponge_read(orc_sponge *s, uint8_t *out, size_t n);      /* sha3.go:163 */
+void orc_sha3_256(uint8_t out[32], const uint8_t *in, size_t n);
+void orc_sha3_512(uint8_t out[64], const uint8_t *in, size_t n);
+void orc_shake128(uint8_t *out, size_t outlen, const uint8_t *in, size_t n);
+void orc_shake256(uint8_t *out, size_t outlen, const uint8_t *in, size_t n);
+
+/* ---------------- Kyber / ML-KEM (q = 3329) ---------------- */
+#define ORC_KYBER_N 256
+#define ORC_KYBER_Q 3329
+int16_t orc_kyber_mont_reduce(int32_t x);     /* pke/kyber/internal/common/field.go:4-32 */
+int16_t orc_kyber_barrett_reduce(int16_t x);  /* field.go:45-64 */
+int16_t orc_kyber_csubq(int16_t x);           /* field.go:67-74 */
+int16_t orc_kyber_to_mont(int16_t x);         /* field.go:35-39 */
+const int16_t *orc_kyber_zetas(void);         /* ntt.go:16-29 (regenerated, not copied) */
+void orc_kyber_ntt(int16_t p[256]);           /* ntt.go:60-135 */
+void orc_kyber_invntt(int16_t p[256]);        /* ntt.go:145-193 */
+void orc_kyber_mulhat(int16_t p[256], const int16_t a[256], const int16_t b[256]); /* poly.go:63-100 */
+void orc_kyber_add(int16_t p[256], const int16_t a[256], const int16_t b[256]);
+void orc_kyber_sub(int16_t p[256], const int16_t a[256], const int16_t b[256]);
+void orc_kyber_barrett(int16_t p[256]);
+void orc_kyber_normalize(int16_t p[256]);
+void orc_kyber_tomont(int16_t p[256]);
+void orc_kyber_pack(uint8_t buf[384], const int16_t p[256]);
+void orc_kyber_unpack(int16_t p[256], const uint8_t buf[384]);
+void orc_kyber_compress(uint8_t *m, const int16_t p[256], int d);
+void orc_kyber_decompress(int16_t p[256], const uint8_t *m, int d);
+void orc_kyber_msg_decompress(int16_t p[256], const uint8_t m[32]);
+void orc_kyber_msg_compress(uint8_t m[32], const int16_t p[256]);
+void orc_kyber_derive_noise(int16_t p[256], const uint8_t *seed, size_t seedlen, uint8_t nonce, int eta);
+void orc_kyber_derive_uniform(int16_t p[256], const uint8_t seed[32], uint8_t x, uint8_t y);
+/* batched helpers (n polynomials, contiguous) used by tests / cpu baseline */
+void orc_kyber_ntt_batch(int16_t *p, size_t n, int inverse);
+void orc_kyber_mulhat_batch(int16_t *p, const int16_t *a, const int16_t *b, size_t n);
+void orc_kyber_dot_batch(int16_t *out, const int16_t *a, const int16_t *b, int k, size_t n);
+
+/* ML-KEM (k = 2,3,4).  Sizes: ek = 384k+32, dk = 768k+96, ct = 32(du*k+dv) */
+size_t orc_mlkem_ek_size(int k);
+size_t orc_mlkem_dk_size(int k);
+size_t orc_mlkem_ct_size(int k);
+/* seed = d||z (64 B).  kem/mlkem/mlkem768/kyber.go:57-78 */
+void orc_mlkem_keygen(int k, uint8_t *ek, uint8_t *dk, const uint8_t seed[64]);
+/* returns 0, or -1 if ek is not canonical (kem.ErrPubKey, cpapke.go:45-55) */
+int orc_mlkem_encaps(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *ek, const uint8_t m[32]);
+/* returns 0, or -2 if H(ek) stored in dk mismatches (kem.ErrPrivKey) */
+int orc_mlkem_decaps(int k, uint8_t ss[32], const uint8_t *dk, const uint8_t *ct);
+/* batched; ek_stride == 0 => one ek for all ops. returns number of failures */
+int orc_mlkem_encaps_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, size_t ek_stride,
+                           const uint8_t *m, size_t n, int nthreads);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

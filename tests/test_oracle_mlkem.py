@@ -1,0 +1,144 @@
+"""Pins oracle/kyber.c against every fixture the reference holds for the
+Kyber / ML-KEM path (CPU only):
+  * ACVP FIPS 203 keyGen / encaps / decaps     (kem/mlkem/acvp_test.go:12-168)
+  * PQCgenKAT transcript SHA-256               (kem/kyber/kat_test.go:19-94)
+  * embedded sampler vectors                   (pke/kyber/internal/common/sample_test.go:23-138)
+  * the algebraic self-checks                  (ntt_test.go:83, poly_test.go:92, field_test.go)
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+import oracle
+from nist_drbg import DRBG
+
+Q = 3329
+KS = {"ML-KEM-512": 2, "ML-KEM-768": 3, "ML-KEM-1024": 4}
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_acvp_encaps(mlkem_acvp, ps):
+    for t in mlkem_acvp["encap"][ps]:
+        ct, ss = oracle.mlkem_encaps(KS[ps], bytes.fromhex(t["ek"]), bytes.fromhex(t["m"]))
+        assert ct.hex().upper() == t["c"].upper(), t["tcId"]
+        assert ss.hex().upper() == t["k"].upper(), t["tcId"]
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_acvp_decaps(mlkem_acvp, ps):
+    g = mlkem_acvp["decap"][ps]
+    dk = bytes.fromhex(g["dk"])
+    for t in g["tests"]:
+        assert oracle.mlkem_decaps(KS[ps], dk, bytes.fromhex(t["c"])).hex().upper() == t["k"].upper(), t["tcId"]
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_acvp_keygen(mlkem_acvp, ps):
+    for t in mlkem_acvp["keygen"][ps]:
+        ek, dk = oracle.mlkem_keygen(KS[ps], bytes.fromhex(t["d"]) + bytes.fromhex(t["z"]))
+        assert ek.hex().upper() == t["ek"].upper(), t["tcId"]
+        assert dk.hex().upper() == t["dk"].upper(), t["tcId"]
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_pqcgenkat_hash(sampler_vectors, ps):
+    # kem/kyber/kat_test.go:42-94
+    k = KS[ps]
+    g = DRBG(bytes(range(48)))
+    f = hashlib.sha256()
+    f.update(("# %s\n\n" % ps.replace("ML-KEM-", "Kyber")).encode())
+    for i in range(100):
+        seed = g.fill(48)
+        f.update(("count = %d\n" % i).encode())
+        f.update(("seed = %s\n" % seed.hex().upper()).encode())
+        g2 = DRBG(seed)
+        kseed = g2.fill(64)
+        eseed = g2.fill(32)
+        ek, dk = oracle.mlkem_keygen(k, kseed)
+        ct, ss = oracle.mlkem_encaps(k, ek, eseed)
+        assert oracle.mlkem_decaps(k, dk, ct) == ss
+        f.update(("pk = %s\n" % ek.hex().upper()).encode())
+        f.update(("sk = %s\n" % dk.hex().upper()).encode())
+        f.update(("ct = %s\n" % ct.hex().upper()).encode())
+        f.update(("ss = %s\n\n" % ss.hex().upper()).encode())
+    assert f.hexdigest() == sampler_vectors["kat_sha256"][ps]
+
+
+def test_sampler_vectors(sampler_vectors):
+    seed = bytes(range(32))
+    assert oracle.kyber_derive_noise(seed, 37, 3).tolist() == sampler_vectors["kyber_noise3_nonce37"]
+    assert oracle.kyber_derive_noise(seed, 37, 2).tolist() == sampler_vectors["kyber_noise2_nonce37"]
+    assert oracle.kyber_derive_uniform(seed, 1, 0).tolist() == sampler_vectors["kyber_uniform_x1_y0"]
+
+
+def test_zetas_formula():
+    z = oracle.kyber_zetas()
+    assert z[:4].tolist() == [2285, 2571, 2970, 1812] and z[-1] == 1628  # ntt.go:16-29 spot values
+
+
+def test_non_canonical_ek_rejected(mlkem_acvp):
+    t = mlkem_acvp["encap"]["ML-KEM-768"][0]
+    ek = bytearray(bytes.fromhex(t["ek"]))
+    ek[0], ek[1] = 0xFF, ek[1] | 0x0F  # first coefficient = 4095 >= q
+    with pytest.raises(ValueError):
+        oracle.mlkem_encaps(3, bytes(ek), bytes.fromhex(t["m"]))
+
+
+def _rand_abs_le_q(rng, n):
+    return rng.integers(-Q, Q, size=(n, 256), dtype=np.int64).astype(np.int16)
+
+
+def test_ntt_roundtrip_and_bounds():
+    # ntt_test.go:83 TestNTT: InvNTT(NTT(p)) == p * R, bounds 7q / q
+    rng = np.random.default_rng(1)
+    p = _rand_abs_le_q(rng, 200)
+    ph = oracle.kyber_ntt(p)
+    assert np.abs(ph.astype(np.int32)).max() <= 7 * Q
+    back = oracle.kyber_invntt(oracle.kyber_barrett(ph))
+    assert np.abs(back.astype(np.int32)).max() <= Q
+    want = (p.astype(np.int64) * 65536) % Q
+    assert np.array_equal(oracle.kyber_normalize(back).astype(np.int64), want)
+
+
+def test_mulhat_is_negacyclic_product():
+    # poly_test.go:92 TestMulHat
+    rng = np.random.default_rng(2)
+    a = _rand_abs_le_q(rng, 8)
+    b = _rand_abs_le_q(rng, 8)
+    ah = oracle.kyber_tomont(oracle.kyber_ntt(a))
+    bh = oracle.kyber_tomont(oracle.kyber_ntt(b))
+    ph = oracle.kyber_barrett(oracle.kyber_mulhat(ah, bh))
+    p = oracle.kyber_normalize(oracle.kyber_invntt(ph)).astype(np.int64)
+    for i in range(8):
+        full = np.convolve(a[i].astype(np.int64), b[i].astype(np.int64))
+        full = np.concatenate([full, [0]])
+        school = (full[:256] - full[256:]) % Q
+        # tomont twice (R^2), MulHat folds in R^-1, InvNTT multiplies by R: net R^2
+        assert np.array_equal(p[i], (school * 65536 * 65536) % Q)
+
+
+def test_field_ops_exhaustive():
+    # field_test.go: barrettReduce / csubq over all int16; montReduce over a sweep
+    L = oracle.lib()
+    for x in range(-32768, 32768, 1):
+        r = L.orc_kyber_barrett_reduce(x)
+        assert 0 <= r <= Q and (r - x) % Q == 0
+    for x in range(0, 2 * Q):
+        r = L.orc_kyber_csubq(x)
+        assert 0 <= r < Q or (x >= 2 * Q)
+    for x in range(-(1 << 15) * Q, (1 << 15) * Q, 9973):
+        r = L.orc_kyber_mont_reduce(x)
+        assert -Q < r < Q and (r * 65536 - x) % Q == 0
+
+
+def test_compress_roundtrip_all_d():
+    rng = np.random.default_rng(3)
+    p = rng.integers(0, Q, size=256).astype(np.int16)
+    for d in (4, 5, 10, 11):
+        buf = oracle.kyber_compress(p, d)
+        assert len(buf) == 32 * d
+        want = ((p.astype(np.int64) << d) + Q // 2) // Q % (1 << d)
+        back = oracle.kyber_decompress(buf, d).astype(np.int64)
+        assert np.array_equal(back, ((want * Q) + (1 << (d - 1))) >> d)
+    assert oracle.kyber_unpack(oracle.kyber_pack(p)).tolist() == p.tolist()

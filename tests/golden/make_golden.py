@@ -129,6 +129,11 @@ def samplers():
     m = re.search(r"permutationOfZeroes = \[.*?\]uint64\{(.*?)\}", src, flags=re.S)
     out["keccak_f1600_of_zero"] = [int(x, 16) for x in re.findall(r"0x[0-9A-Fa-f]+", m.group(1))]
     assert len(out["keccak_f1600_of_zero"]) == 25
+    # lazy-Barrett schedule of the inverse NTT, pke/kyber/internal/common/ntt.go:38-50
+    src = open(os.path.join(REF, "pke/kyber/internal/common/ntt.go")).read()
+    m = re.search(r"InvNTTReductions = \[\.\.\.\]int\{(.*?)\n\}", src, flags=re.S)
+    body = re.sub(r"//[^\n]*", "", m.group(1))
+    out["kyber_invntt_reductions"] = [int(x) for x in re.findall(r"-?\d+", body)]
     out["kat_sha256"] = {  # kem/kyber/kat_test.go:25-33, sign/dilithium/kat_test.go:25-35
         "ML-KEM-512": re.search(r'"ML-KEM-512", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
         "ML-KEM-768": re.search(r'"ML-KEM-768", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),

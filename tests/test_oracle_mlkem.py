@@ -142,3 +142,76 @@ def test_compress_roundtrip_all_d():
         back = oracle.kyber_decompress(buf, d).astype(np.int64)
         assert np.array_equal(back, ((want * Q) + (1 << (d - 1))) >> d)
     assert oracle.kyber_unpack(oracle.kyber_pack(p)).tolist() == p.tolist()
+
+
+def test_invntt_reduction_schedule(sampler_vectors):
+    # ntt.go:38-50: the oracle states the table as (layer, period, residues); check it index by index
+    table = sampler_vectors["kyber_invntt_reductions"]
+    layers, cur = [], []
+    for v in table:
+        if v < 0:
+            layers.append(cur)
+            cur = []
+        else:
+            cur.append(v)
+    assert len(layers) == 7
+    import ctypes
+    L = oracle.lib()
+    # replay: feed a polynomial whose coefficient i is marked, use a python model of the predicate
+    def pred(l, i):
+        if l == 8:
+            return (i & 31) in (16, 17)
+        if l == 16:
+            return (i & 63) in (0, 1, 32, 33, 34, 35)
+        if l == 32:
+            return (i & 127) in (2, 3, 66, 67, 68, 69, 70, 71)
+        if l == 64:
+            return 4 <= i <= 7 or 132 <= i <= 143
+        return False
+    for n, l in enumerate((2, 4, 8, 16, 32, 64, 128)):
+        assert sorted(layers[n]) == [i for i in range(256) if pred(l, i)], l
+
+
+def test_invntt_matches_table_driven_model(sampler_vectors):
+    """Bit-exact (unnormalised) check of orc_kyber_invntt against a pure-Python
+    transcription of ntt.go:145-193 that is driven by the reference's own
+    InvNTTReductions table (tests/golden)."""
+    table = sampler_vectors["kyber_invntt_reductions"]
+    zetas = [int(z) for z in oracle.kyber_zetas()]
+
+    def s16(x):
+        x &= 0xFFFF
+        return x - 0x10000 if x & 0x8000 else x
+
+    def mont(x):
+        m = s16(x * 62209)
+        return s16(((x - m * Q) & 0xFFFFFFFF) >> 16)
+
+    def barrett(x):
+        return s16(x - s16((x * 20159) >> 26) * Q)
+
+    def invntt(p):
+        p = list(p)
+        k, r, l = 127, -1, 2
+        while l < 256:
+            for off in range(0, 256 - l, 2 * l):
+                mz = zetas[k]
+                k -= 1
+                for j in range(off, off + l):
+                    t = s16(p[j + l] - p[j])
+                    p[j] = s16(p[j] + p[j + l])
+                    p[j + l] = mont(mz * t)
+            while True:
+                r += 1
+                i = table[r]
+                if i < 0:
+                    break
+                p[i] = barrett(p[i])
+            l <<= 1
+        return [mont(1441 * x) for x in p]
+
+    rng = np.random.default_rng(7)
+    polys = _rand_abs_le_q(rng, 6)
+    got = oracle.kyber_invntt(polys)
+    for i in range(6):
+        assert got[i].tolist() == invntt(polys[i].tolist())

@@ -1,0 +1,65 @@
+"""ctypes binding of circl_b200/libcirclb200.so (the C ABI in include/circl_b200.h).
+
+The library is the product; this module only loads it.  There is no CPU
+fallback: a missing library or a missing GPU raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcirclb200.so")
+
+# every symbol include/circl_b200.h declares (checked by tests/test_abi.py)
+SYMBOLS = {
+    "cb200_init": (C.c_int, [C.c_int]),
+    "cb200_shutdown": (None, []),
+    "cb200_device_count": (C.c_int, []),
+    "cb200_last_error": (C.c_char_p, []),
+    "cb200_version": (C.c_char_p, []),
+    "cb200_set_stream": (C.c_int, [C.c_void_p]),
+    "cb200_synchronize": (C.c_int, []),
+    "cb200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "cb200_host_free": (None, [C.c_void_p]),
+    "cb200_launch_count": (C.c_uint64, []),
+    "cb200_kyber_ntt": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int]),
+    "cb200_kyber_mulhat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cb200_kyber_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "cb200_kyber_poly_op": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cb200_mlkem_encaps": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_void_p, C.c_size_t]),
+    "cb200_mlkem_public_key_size": (C.c_size_t, [C.c_int]),
+    "cb200_mlkem_ciphertext_size": (C.c_size_t, [C.c_int]),
+}
+
+_lib = None
+
+
+class Cb200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"cb200 error {code}: {msg}")
+        self.code = code
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} is missing: build it with `python -m circl_b200.build` "
+                "(nvcc, sm_100a). circl_b200 has no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SYMBOLS.items():
+            if not hasattr(L, name):
+                continue  # test_abi reports missing symbols
+            f = getattr(L, name)
+            f.restype = res
+            f.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        raise Cb200Error(rc, lib().cb200_last_error().decode())

@@ -1,0 +1,57 @@
+// circl_b200/csrc/context.h -- process-wide state behind the C ABI (one process per GPU).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <functional>
+#include <mutex>
+#include <vector>
+
+#include "launch.h"
+
+namespace cb200 {
+
+struct Ctx {
+  bool ready = false;
+  int device = -1;
+  cudaStream_t own = nullptr;   // library stream
+  cudaStream_t cur = nullptr;   // stream used for device-pointer calls (own or user supplied)
+  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // host-pointer calls: H2D -> kernels -> D2H per chunk
+  void* kyber_tw = nullptr;     // 128 x {zeta, zetaq}
+  void* dil_tw = nullptr;       // 256 x {zeta, invzeta}
+  std::atomic<uint64_t> launches{0};
+  std::mutex mu;                // serialises host-pointer calls (device scratch is shared)
+  // grow-only device scratch, one per pipeline slot
+  void* scratch[3] = {nullptr, nullptr, nullptr};
+  size_t scratch_bytes[3] = {0, 0, 0};
+  // grow-only work areas for the multi-kernel pipelines (ML-KEM / ML-DSA)
+  // slot 0..2 belong to the staging pipeline streams, slot 3 to device-pointer calls
+  void* work[4] = {nullptr, nullptr, nullptr, nullptr};
+  size_t work_bytes[4] = {0, 0, 0, 0};
+};
+
+Ctx& ctx();
+int require_ready();
+bool is_device_ptr(const void* p);
+int ensure_scratch(int slot, size_t bytes);
+int ensure_work(int slot, size_t bytes, void** out);
+inline void count_launch(uint64_t n = 1) { ctx().launches.fetch_add(n, std::memory_order_relaxed); }
+
+// One buffer of a batched call: `unit` bytes per batch element; stride 0 = shared by all elements.
+struct Buf {
+  const void* host_in = nullptr;  // copied host -> device before the kernels (may be null)
+  void* host_out = nullptr;       // copied device -> host after the kernels (may be null)
+  size_t unit = 0;
+  bool shared = false;            // whole buffer is `unit` bytes, identical for every element
+  size_t host_stride = 0;         // bytes between elements in host memory (0 = dense = unit)
+};
+
+// Runs `body(dev_ptrs, count, stream)` over the batch in chunks, overlapping the
+// host<->device copies of one chunk with the kernels of another on three streams.
+// dev_ptrs[i] is the device image of bufs[i] for the current chunk.
+int run_staged(std::vector<Buf>& bufs, size_t n, size_t chunk,
+               const std::function<int(void** dev, size_t count, size_t first, cudaStream_t st, int slot)>& body);
+
+}  // namespace cb200

@@ -1,0 +1,348 @@
+// circl_b200/csrc/kyber.cuh -- q = 3329 ring arithmetic for sm_100a.
+//
+// Replaces (bit-exactly, standard coefficient order, *generic* semantics):
+//   pke/kyber/internal/common/field.go:4-74       montReduce / barrettReduce / csubq / toMont
+//   pke/kyber/internal/common/ntt.go:60-135       nttGeneric        (asm: amd64.s:153  nttAVX2)
+//   pke/kyber/internal/common/ntt.go:145-193      invNTTGeneric     (asm: amd64.s:737  invNttAVX2)
+//   pke/kyber/internal/common/poly.go:63-100      mulHatGeneric     (asm: amd64.s:1443 mulHatAVX2)
+//
+// Work decomposition ("octet"): 8 lanes own one 256-coefficient polynomial, so a
+// warp carries 4 polynomials.  Each lane keeps 32 coefficients in registers in
+// one of two layouts:
+//   S ("strided")     r[2s+b] = coefficient 16s + 2v + b   (s = 0..15, b = 0,1)
+//                     -> layers l = 128,64,32,16 are register-local, twiddles are immediates
+//   C ("contiguous")  r[i]    = coefficient 32v + i        (i = 0..31)
+//                     -> layers l = 8,4,2 are register-local, twiddles are per-lane registers
+// One transposition S<->C through (padded, conflict-free) shared memory joins
+// the two passes; there is no cross-lane butterfly and no shuffle.
+//
+// Register format ("high-half"): a coefficient c lives in bits 31..16 of a
+// 32-bit register; bits 15..0 are zero.  int16 wrap-around of the reference is
+// then exactly the wrap-around of 32-bit adds, and
+//   montReduce(zeta*c) << 16  ==  c*zeta - m*q   with  m = int16(c*zeta*q^-1)
+// needs no final shift.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace cb200 {
+namespace kyber {
+
+constexpr int N = 256;
+constexpr int Q = 3329;
+constexpr uint32_t QINV = 62209;  // q^-1 mod 2^16, field.go:12
+
+// ---------------------------------------------------------------- twiddles
+// Zetas[i] = 17^brv7(i) * 2^16 mod q (ntt.go:5-15), regenerated at compile time.
+__host__ __device__ constexpr uint32_t brv7(uint32_t x) {
+  uint32_t r = 0;
+  for (int i = 0; i < 7; i++) r |= ((x >> i) & 1u) << (6 - i);
+  return r;
+}
+__host__ __device__ constexpr int32_t zeta_of(int i) {
+  uint32_t z = 65536u % Q, e = brv7((uint32_t)i);
+  for (uint32_t j = 0; j < e; j++) z = z * 17u % Q;
+  return (int32_t)z;
+}
+// (zeta * q^-1 mod 2^16) << 16 : multiplying the sign-extended coefficient by this
+// yields m << 16 directly.
+__host__ __device__ constexpr int32_t zetaq_of(int i) {
+  return (int32_t)((((uint32_t)zeta_of(i) * QINV) & 0xffffu) << 16);
+}
+// compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+template <int I>
+struct Zeta {
+  static constexpr int32_t z = zeta_of(I);
+  static constexpr int32_t zq = zetaq_of(I);
+};
+
+// Per-lane twiddles of the C-layout pass (index = Zetas position k), packed as
+// {zeta, zetaq} pairs in global memory by the host at init.
+struct TwPair {
+  int32_t z, zq;
+};
+
+// ---------------------------------------------------------------- field ops
+// c: sign-extended coefficient;  returns montReduce(z*c) << 16  (low half zero)
+__device__ __forceinline__ int32_t mont_mul_hi(int32_t c, int32_t z, int32_t zq) {
+  int32_t p = c * z;
+  int32_t m = (c * zq) >> 16;  // == int16(c*z*62209), field.go:12
+  return p - m * Q;            // == montReduce(p) << 16, field.go:31
+}
+// general product of two sign-extended values: montReduce(a*b) << 16
+__device__ __forceinline__ int32_t mont_prod_hi(int32_t a, int32_t b) {
+  int32_t p = a * b;
+  int32_t m = (int32_t)((uint32_t)p * (QINV << 16)) >> 16;
+  return p - m * Q;
+}
+// barrettReduce on a high-half register (field.go:45-64)
+__device__ __forceinline__ int32_t barrett_hi(int32_t x) {
+  int32_t c = x >> 16;
+  int32_t t = (c * 20159) >> 26;
+  return x - t * (Q << 16);
+}
+// csubq on a high-half register (field.go:67-74)
+__device__ __forceinline__ int32_t csubq_hi(int32_t x) {
+  x -= (Q << 16);
+  x += (x >> 31) & (Q << 16);
+  return x;
+}
+
+// ---------------------------------------------------------------- pack / unpack
+// word = two consecutive int16 coefficients (little endian)
+__device__ __forceinline__ void unpack2(uint32_t w, int32_t& lo, int32_t& hi) {
+  lo = (int32_t)(w << 16);
+  hi = (int32_t)(w & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack2(int32_t lo, int32_t hi) {
+  return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x7632);
+}
+
+// ---------------------------------------------------------------- shared-memory tile
+// One polynomial = 128 words, stored with 4 pad words after every 32 so that
+// both access patterns below are bank-conflict free; octet stride 152 words
+// (== 24 mod 32) separates the four octets of a warp.
+constexpr int kPolyWords = 152;
+__device__ __forceinline__ int phys_word(int w) { return w + ((w >> 5) << 2); }
+
+// S-layout word s of lane v  <-> logical word 8s + v
+template <int S>
+__device__ __forceinline__ int s_word(int v) {
+  return 8 * S + v + 4 * (S >> 2);
+}
+
+// ---------------------------------------------------------------- butterflies
+// Cooley-Tukey, ntt.go:129-131
+__device__ __forceinline__ void ct_bfly(int32_t& a, int32_t& b, int32_t z, int32_t zq) {
+  int32_t t = mont_mul_hi(b >> 16, z, zq);
+  b = a - t;
+  a = a + t;
+}
+// Gentleman-Sande, ntt.go:165-168
+__device__ __forceinline__ void gs_bfly(int32_t& a, int32_t& b, int32_t z, int32_t zq) {
+  int32_t t = b - a;
+  a = a + b;
+  b = mont_mul_hi(t >> 16, z, zq);
+}
+
+// Forward pass 1 on S layout: layers l = 128, 64, 32, 16.  All twiddles are
+// template constants, i.e. IMAD immediates in SASS.
+__device__ __forceinline__ void fwd_pass_S(int32_t (&r)[32]) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) ct_bfly(r[i], r[i + 16], Zeta<1>::z, Zeta<1>::zq);  // l=128, k=1
+  static_for<0, 2>([&](auto hc) {  // l=64, k = 2 + (s>>3)
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ct_bfly(r[16 * h + i], r[16 * h + i + 8], Zeta<2 + h>::z, Zeta<2 + h>::zq);
+  });
+  static_for<0, 4>([&](auto hc) {  // l=32, k = 4 + (s>>2)
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 4; i++) ct_bfly(r[8 * h + i], r[8 * h + i + 4], Zeta<4 + h>::z, Zeta<4 + h>::zq);
+  });
+  static_for<0, 8>([&](auto hc) {  // l=16, k = 8 + (s>>1)
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 2; i++) ct_bfly(r[4 * h + i], r[4 * h + i + 2], Zeta<8 + h>::z, Zeta<8 + h>::zq);
+  });
+}
+
+// Per-lane twiddle registers for the C-layout passes: lane v needs Zetas[16+2v+{0,1}],
+// Zetas[32+4v+{0..3}], Zetas[64+8v+{0..7}]  (forward) -- and the same entries,
+// walked downwards, for the inverse (ntt.go:152-160).
+struct LaneTw {
+  TwPair l8[2], l4[4], l2[8];
+};
+__device__ __forceinline__ void load_lane_tw(LaneTw& t, const TwPair* __restrict__ tab, int v) {
+#pragma unroll
+  for (int i = 0; i < 2; i++) t.l8[i] = tab[16 + 2 * v + i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) t.l4[i] = tab[32 + 4 * v + i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.l2[i] = tab[64 + 8 * v + i];
+}
+
+// Forward pass 2 on C layout: layers l = 8, 4, 2.
+__device__ __forceinline__ void fwd_pass_C(int32_t (&r)[32], const LaneTw& t) {
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) ct_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.l8[blk].z, t.l8[blk].zq);
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) ct_bfly(r[8 * blk + j], r[8 * blk + j + 4], t.l4[blk].z, t.l4[blk].zq);
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) ct_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.l2[blk].z, t.l2[blk].zq);
+}
+
+// Inverse pass A on C layout: layers l = 2, 4, 8 then the layer-3 Barrett set
+// (indices == 16,17 mod 32, ntt.go:42-43).  Zetas[k] with k = 127-(idx>>2),
+// 63-(idx>>3), 31-(idx>>4): i.e. the forward per-lane entries of lane 7-v, reversed.
+__device__ __forceinline__ void inv_pass_C(int32_t (&r)[32], const LaneTw& t) {
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) gs_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.l2[7 - blk].z, t.l2[7 - blk].zq);
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) gs_bfly(r[8 * blk + j], r[8 * blk + j + 4], t.l4[3 - blk].z, t.l4[3 - blk].zq);
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.l8[1 - blk].z, t.l8[1 - blk].zq);
+  r[16] = barrett_hi(r[16]);
+  r[17] = barrett_hi(r[17]);
+}
+
+// Inverse pass B on S layout: layers l = 16, 32, 64, 128 with the lazy Barrett
+// schedule of ntt.go:44-49 and the final multiplication by 1441 (ntt.go:187-192).
+// S layout: r[2s+b] = coefficient 16s + 2v + b.
+__device__ __forceinline__ void inv_pass_S(int32_t (&r)[32], int v) {
+  static_for<0, 8>([&](auto hc) {  // l=16: pairs (s, s+1), k = 15 - (s>>1)
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 2; i++) gs_bfly(r[4 * h + i], r[4 * h + i + 2], Zeta<15 - h>::z, Zeta<15 - h>::zq);
+  });
+  // after layer 4: idx mod 64 in {0,1} -> (s&3)==0, v==0 ; {32..35} -> (s&3)==2, v<=1
+#pragma unroll
+  for (int s = 0; s < 16; s += 4)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      if (v == 0) r[2 * s + b] = barrett_hi(r[2 * s + b]);
+      if (v <= 1) r[2 * (s + 2) + b] = barrett_hi(r[2 * (s + 2) + b]);
+    }
+  static_for<0, 4>([&](auto hc) {  // l=32: pairs (s, s+2), k = 7 - (s>>2)
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 4; i++) gs_bfly(r[8 * h + i], r[8 * h + i + 4], Zeta<7 - h>::z, Zeta<7 - h>::zq);
+  });
+  // after layer 5: idx mod 128 in {2,3} -> (s&7)==0, v==1 ; {66..71} -> (s&7)==4, v in 1..3
+#pragma unroll
+  for (int s = 0; s < 16; s += 8)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      if (v == 1) r[2 * s + b] = barrett_hi(r[2 * s + b]);
+      if (v >= 1 && v <= 3) r[2 * (s + 4) + b] = barrett_hi(r[2 * (s + 4) + b]);
+    }
+  static_for<0, 2>([&](auto hc) {  // l=64: pairs (s, s+4), k = 3 - (s>>3)
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 8; i++) gs_bfly(r[16 * h + i], r[16 * h + i + 8], Zeta<3 - h>::z, Zeta<3 - h>::zq);
+  });
+  // after layer 6: idx in {4..7} -> s==0, v in {2,3} ; {132..143} -> s==8, v in 2..7
+#pragma unroll
+  for (int b = 0; b < 2; b++) {
+    if (v == 2 || v == 3) r[b] = barrett_hi(r[b]);
+    if (v >= 2) r[16 + b] = barrett_hi(r[16 + b]);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) gs_bfly(r[i], r[i + 16], Zeta<1>::z, Zeta<1>::zq);  // l=128, k=1
+  // p[j] = montReduce(1441 * p[j])
+#pragma unroll
+  for (int i = 0; i < 32; i++) r[i] = mont_mul_hi(r[i] >> 16, 1441, (int32_t)(((1441u * QINV) & 0xffffu) << 16));
+}
+
+// ---------------------------------------------------------------- S <-> C transposition
+// `tile` points at this octet's kPolyWords-word shared-memory tile.
+__device__ __forceinline__ void store_S(uint32_t* tile, int v, const int32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++) tile[8 * s + v + 4 * (s >> 2)] = pack2(r[2 * s], r[2 * s + 1]);
+}
+__device__ __forceinline__ void load_S(const uint32_t* tile, int v, int32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++) unpack2(tile[8 * s + v + 4 * (s >> 2)], r[2 * s], r[2 * s + 1]);
+}
+__device__ __forceinline__ void store_C(uint32_t* tile, int v, const int32_t (&r)[32]) {
+  uint4* p = reinterpret_cast<uint4*>(tile + 16 * v + 4 * (v >> 1));
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+    p[c] = make_uint4(pack2(r[8 * c], r[8 * c + 1]), pack2(r[8 * c + 2], r[8 * c + 3]), pack2(r[8 * c + 4], r[8 * c + 5]),
+                      pack2(r[8 * c + 6], r[8 * c + 7]));
+}
+__device__ __forceinline__ void load_C(const uint32_t* tile, int v, int32_t (&r)[32]) {
+  const uint4* p = reinterpret_cast<const uint4*>(tile + 16 * v + 4 * (v >> 1));
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    uint4 w = p[c];
+    unpack2(w.x, r[8 * c], r[8 * c + 1]);
+    unpack2(w.y, r[8 * c + 2], r[8 * c + 3]);
+    unpack2(w.z, r[8 * c + 4], r[8 * c + 5]);
+    unpack2(w.w, r[8 * c + 6], r[8 * c + 7]);
+  }
+}
+
+// ---------------------------------------------------------------- global <-> registers
+// S layout straight from global memory: 16 x 32-bit, each octet reads one full
+// 32-byte sector per instruction.
+__device__ __forceinline__ void gload_S(const uint32_t* __restrict__ poly, int v, int32_t (&r)[32]) {
+  uint32_t w[16];
+#pragma unroll
+  for (int s = 0; s < 16; s++) w[s] = ldg_stream32(poly + 8 * s + v);
+#pragma unroll
+  for (int s = 0; s < 16; s++) unpack2(w[s], r[2 * s], r[2 * s + 1]);
+}
+__device__ __forceinline__ void gstore_S(uint32_t* __restrict__ poly, int v, const int32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++) poly[8 * s + v] = pack2(r[2 * s], r[2 * s + 1]);
+}
+// C layout: 4 x 128-bit per lane, 64 contiguous bytes per lane
+__device__ __forceinline__ void gload_C(const uint32_t* __restrict__ poly, int v, int32_t (&r)[32]) {
+  uint4 w[4];
+#pragma unroll
+  for (int c = 0; c < 4; c++) w[c] = ldg_stream128(poly + 16 * v + 4 * c);
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    unpack2(w[c].x, r[8 * c], r[8 * c + 1]);
+    unpack2(w[c].y, r[8 * c + 2], r[8 * c + 3]);
+    unpack2(w[c].z, r[8 * c + 4], r[8 * c + 5]);
+    unpack2(w[c].w, r[8 * c + 6], r[8 * c + 7]);
+  }
+}
+__device__ __forceinline__ void gstore_C(uint32_t* __restrict__ poly, int v, const int32_t (&r)[32]) {
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+    stg_stream128(poly + 16 * v + 4 * c,
+                  make_uint4(pack2(r[8 * c], r[8 * c + 1]), pack2(r[8 * c + 2], r[8 * c + 3]),
+                             pack2(r[8 * c + 4], r[8 * c + 5]), pack2(r[8 * c + 6], r[8 * c + 7])));
+}
+
+// ---------------------------------------------------------------- MulHat on C layout
+// poly.go:63-100.  p = a (*) b in Z_q[x]/(x^2 -+ zeta); quads (4j..4j+3) of lane v
+// use Zetas[64 + 8v + j] == t.l2[j].z.  acc += result (PolyDotHat, vec.go:30-37).
+__device__ __forceinline__ void mulhat_acc_C(int32_t (&acc)[32], const int32_t (&a)[32], const int32_t (&b)[32],
+                                             const LaneTw& t) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int32_t a0 = a[4 * j] >> 16, a1 = a[4 * j + 1] >> 16, a2 = a[4 * j + 2] >> 16, a3 = a[4 * j + 3] >> 16;
+    const int32_t b0 = b[4 * j] >> 16, b1 = b[4 * j + 1] >> 16, b2 = b[4 * j + 2] >> 16, b3 = b[4 * j + 3] >> 16;
+    const int32_t z = t.l2[j].z, zq = t.l2[j].zq;
+    int32_t p0 = mont_prod_hi(a1, b1);
+    p0 = mont_mul_hi(p0 >> 16, z, zq);
+    p0 += mont_prod_hi(a0, b0);
+    int32_t p1 = mont_prod_hi(a0, b1) + mont_prod_hi(a1, b0);
+    int32_t p2 = mont_prod_hi(a3, b3);
+    p2 = -mont_mul_hi(p2 >> 16, z, zq);
+    p2 += mont_prod_hi(a2, b2);
+    int32_t p3 = mont_prod_hi(a2, b3) + mont_prod_hi(a3, b2);
+    acc[4 * j] += p0;
+    acc[4 * j + 1] += p1;
+    acc[4 * j + 2] += p2;
+    acc[4 * j + 3] += p3;
+  }
+}
+
+}  // namespace kyber
+}  // namespace cb200

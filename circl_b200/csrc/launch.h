@@ -1,0 +1,23 @@
+// circl_b200/csrc/launch.h -- internal launcher prototypes (device pointers, explicit stream).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace cb200 {
+
+void set_error(const char* fmt, ...);
+
+// kyber_kernels.cu
+int launch_kyber_ntt(int16_t* d_polys, size_t n, int inverse, const void* tw, cudaStream_t st);
+int launch_kyber_dot(int16_t* d_out, const int16_t* d_a, const int16_t* d_b, int k, size_t n, const void* tw,
+                     cudaStream_t st);
+int launch_kyber_poly_op(int op, int16_t* d_out, const int16_t* d_a, const int16_t* d_b, size_t n, cudaStream_t st);
+void kyber_fill_twiddles(int32_t* out);
+
+}  // namespace cb200
+
+namespace cb200 {
+// tables.cu: twiddle tables other than Kyber's (ML-DSA); called from cb200_init
+int init_extra_tables();
+}  // namespace cb200

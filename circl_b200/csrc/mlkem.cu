@@ -1,0 +1,528 @@
+// circl_b200/csrc/mlkem.cu -- batched ML-KEM-768 / ML-KEM-1024 Encapsulate on sm_100a.
+//
+// Replaces, per operation and bit-exactly:
+//   scheme.UnmarshalBinaryPublicKey   kem/mlkem/mlkem768/kyber.go:390-396 -> :247-263
+//     cpapke.UnpackMLKEM              pke/kyber/kyber768/internal/cpapke.go:45-63 (modulus check, aT.Derive)
+//     Mat.Derive / DeriveUniform      internal/mat.go:13-29, common/sample.go:192-236 (SHAKE128 rejection)
+//   (*PublicKey).EncapsulateTo        kem/mlkem/mlkem768/kyber.go:103-137  (G = SHA3-512(m || H(ek)))
+//     (*PublicKey).EncryptTo          internal/cpapke.go:137-181
+//     DeriveNoise2                    common/sample.go:67-95 (SHAKE256 PRF + CBD_2)
+//     CompressTo                      common/poly.go:248-328
+//
+// Pipeline (all intermediates stay on the device; sub-batches are sized so that
+// A^T and the noise polynomials live in the 126 MB L2 between kernels):
+//   1. hash_kernel    one thread per op/key: h = SHA3-256(ek), (K', r) = SHA3-512(m || h)
+//   2. sample_kernel  one thread per Keccak stream: K*K SHAKE128 matrix streams per key,
+//                     2K+1 SHAKE256 noise streams per op (warps are stream-homogeneous)
+//   3. encrypt_kernel one octet (8 lanes) per op: NTT(r), A^T o r, t o r, InvNTT, +e, compress
+#include "../../include/circl_b200.h"
+#include "context.h"
+#include "keccak.cuh"
+#include "kyber.cuh"
+
+namespace cb200 {
+namespace mlkem {
+
+using kyber::N;
+using kyber::Q;
+
+template <int K>
+struct Params {
+  static constexpr int k = K;
+  static constexpr int du = (K == 4) ? 11 : 10;
+  static constexpr int dv = (K == 4) ? 5 : 4;
+  static constexpr int ek_bytes = 384 * K + 32;
+  static constexpr int ct_bytes = 32 * (du * K + dv);
+  static constexpr int n_noise = 2 * K + 1;  // r[0..K), e1[0..K), e2   (eta1 = eta2 = 2 for K = 3, 4)
+};
+
+// ------------------------------------------------------------------ 1. hashes
+// h = SHA3-256(ek) (kyber.go:258-260).  One thread per key; ek is 8-byte aligned.
+template <int K>
+__device__ __forceinline__ void sha3_256_ek(const uint8_t* ek, uint64_t (&h)[4]) {
+  constexpr int words = Params<K>::ek_bytes / 8;  // 148 / 196
+  constexpr int full = words / 17, rem = words % 17;
+  uint64_t a[25];
+  keccak::zero(a);
+  const uint8_t* p = ek;
+#pragma unroll 1
+  for (int b = 0; b < full; b++) {
+#pragma unroll
+    for (int w = 0; w < 17; w++) a[w] ^= keccak::ld64(p + 8 * w);
+    keccak::f1600(a);
+    p += 136;
+  }
+#pragma unroll
+  for (int w = 0; w < rem; w++) a[w] ^= keccak::ld64(p + 8 * w);
+  a[rem] ^= 0x06;
+  a[16] ^= 0x8000000000000000ull;
+  keccak::f1600(a);
+#pragma unroll
+  for (int i = 0; i < 4; i++) h[i] = a[i];
+}
+
+template <int K>
+__global__ void __launch_bounds__(128) hash_ek_kernel(const uint8_t* __restrict__ ek, size_t ek_stride, size_t nkeys,
+                                                      uint64_t* __restrict__ hout) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nkeys) return;
+  uint64_t h[4];
+  sha3_256_ek<K>(ek + i * ek_stride, h);
+#pragma unroll
+  for (int j = 0; j < 4; j++) hout[4 * i + j] = h[j];
+}
+
+// (K', r) = SHA3-512(m || h)  (kyber.go:126-131); ss = K' (kyber.go:136)
+__global__ void __launch_bounds__(128) g_kernel(const uint8_t* __restrict__ m, const uint64_t* __restrict__ h,
+                                                int h_shared, size_t n, uint8_t* __restrict__ ss,
+                                                uint64_t* __restrict__ r_out) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t a[25];
+  keccak::zero(a);
+  const uint64_t* hp = h + (h_shared ? 0 : 4 * i);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    a[j] = keccak::ld64(m + 32 * i + 8 * j);
+    a[4 + j] = hp[j];
+  }
+  a[8] = 0x8000000000000006ull;  // rate 72: pad bytes 64 (0x06) and 71 (0x80) share lane 8
+  keccak::f1600(a);
+  uint64_t* so = reinterpret_cast<uint64_t*>(ss + 32 * i);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    so[j] = a[j];
+    r_out[4 * i + j] = a[4 + j];
+  }
+}
+
+// ------------------------------------------------------------------ 2. samplers
+// 12-bit rejection sampling of one 168-byte SHAKE128 block (sample.go:203-233).
+// Accepted coefficients are appended to dst[ctr...]; returns the new ctr (<= 256).
+__device__ __forceinline__ int reject_block(const uint64_t (&a)[25], int16_t* __restrict__ dst, int ctr) {
+#pragma unroll
+  for (int g = 0; g < 7; g++) {
+    const uint64_t w0 = a[3 * g], w1 = a[3 * g + 1], w2 = a[3 * g + 2];
+    uint32_t t[8];
+    t[0] = (uint32_t)w0 & 0xffffff;
+    t[1] = (uint32_t)(w0 >> 24) & 0xffffff;
+    t[2] = (uint32_t)(w0 >> 48) | (((uint32_t)w1 & 0xff) << 16);
+    t[3] = (uint32_t)(w1 >> 8) & 0xffffff;
+    t[4] = (uint32_t)(w1 >> 32) & 0xffffff;
+    t[5] = (uint32_t)(w1 >> 56) | (((uint32_t)w2 & 0xffff) << 8);
+    t[6] = (uint32_t)(w2 >> 16) & 0xffffff;
+    t[7] = (uint32_t)(w2 >> 40);
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const uint32_t d1 = t[j] & 0xfff, d2 = t[j] >> 12;
+      if (d1 < (uint32_t)Q && ctr < N) dst[ctr++] = (int16_t)d1;
+      if (d2 < (uint32_t)Q && ctr < N) dst[ctr++] = (int16_t)d2;
+    }
+  }
+  return ctr;
+}
+
+// CBD_2 of 128 bytes (sample.go:80-93), written as 256 packed int16
+__device__ __forceinline__ void cbd2_store(const uint64_t (&a)[25], int16_t* __restrict__ dst) {
+  uint4* out = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int i = 0; i < 16; i++) {
+    const uint64_t t = a[i];
+    uint64_t d = (t & 0x5555555555555555ull) + ((t >> 1) & 0x5555555555555555ull);
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const int c0 = (int)((d >> (8 * j)) & 3) - (int)((d >> (8 * j + 2)) & 3);
+      const int c1 = (int)((d >> (8 * j + 4)) & 3) - (int)((d >> (8 * j + 6)) & 3);
+      w[j] = ((uint32_t)c0 & 0xffffu) | ((uint32_t)c1 << 16);
+    }
+    out[2 * i] = make_uint4(w[0], w[1], w[2], w[3]);
+    out[2 * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// Stream index space (blockDim-aligned so that warps never mix stream kinds):
+//   [0, nkeys*K*K)               matrix streams, s = (i*K + j) * nkeys + key  -> A^T[key][i][j] = XOF(rho, i, j)
+//   then n*(2K+1) noise streams, s = nonce * n + op                            -> PRF(r_op, nonce)
+template <int K>
+__global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__ ek, size_t ek_stride, size_t nkeys,
+                                                     const uint64_t* __restrict__ r, size_t n,
+                                                     int16_t* __restrict__ A, int16_t* __restrict__ noise,
+                                                     size_t mat_blocks) {
+  using P = Params<K>;
+  uint64_t a[25];
+  keccak::zero(a);
+  if (blockIdx.x < mat_blocks) {
+    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= nkeys * K * K) return;
+    const size_t key = s % nkeys;
+    const int ij = (int)(s / nkeys), i = ij / K, j = ij % K;
+    const uint8_t* rho = ek + key * ek_stride + 384 * K;
+#pragma unroll
+    for (int w = 0; w < 4; w++) a[w] = keccak::ld64(rho + 8 * w);
+    a[4] = (uint64_t)i | ((uint64_t)j << 8) | (0x1full << 16);  // aT.Derive(rho, transpose=true): x = i, y = j
+    a[20] = 0x8000000000000000ull;                               // rate 168
+    int16_t* dst = A + (key * K * K + ij) * N;
+    int ctr = 0;
+    do {
+      keccak::f1600(a);
+      ctr = reject_block(a, dst, ctr);
+    } while (ctr < N);
+  } else {
+    const size_t s = (size_t)(blockIdx.x - mat_blocks) * blockDim.x + threadIdx.x;
+    if (s >= n * P::n_noise) return;
+    const size_t op = s % n;
+    const int nonce = (int)(s / n);
+#pragma unroll
+    for (int w = 0; w < 4; w++) a[w] = r[4 * op + w];
+    a[4] = (uint64_t)nonce | (0x1full << 8);
+    a[16] = 0x8000000000000000ull;  // rate 136
+    keccak::f1600(a);
+    cbd2_store(a, noise + (op * P::n_noise + nonce) * N);
+  }
+}
+
+// ------------------------------------------------------------------ 3. K-PKE.Encrypt
+// Compress_q(x, d) for x in [0, q)  (poly.go:262-328)
+template <int D>
+__device__ __forceinline__ uint32_t compress1(uint32_t x) {
+  const uint32_t v = (x << D) + Q / 2;
+  if constexpr (D <= 5)
+    return ((v * 315u) >> 20) & ((1u << D) - 1);
+  else
+    return (__umulhi(v, 20642679u) >> 4) & ((1u << D) - 1);
+}
+
+// 32 normalised coefficients (high-half registers, C layout) -> D words of ciphertext
+template <int D>
+__device__ __forceinline__ void compress_store_C(const int32_t (&r)[32], uint32_t* __restrict__ dst) {
+  uint64_t acc = 0;
+  int bits = 0, o = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    acc |= (uint64_t)compress1<D>((uint32_t)r[i] >> 16) << bits;
+    bits += D;
+    if (bits >= 32) {
+      dst[o++] = (uint32_t)acc;
+      acc >>= 32;
+      bits -= 32;
+    }
+  }
+}
+
+// 12-bit unpack of 32 coefficients (48 bytes, 16-byte aligned) into high-half registers
+// (poly.go:123-129); returns nonzero if any coefficient is >= q (cpapke.go:45-55).
+__device__ __forceinline__ uint32_t unpack12_C(const uint8_t* __restrict__ src, int32_t (&r)[32]) {
+  const uint4* p = reinterpret_cast<const uint4*>(src);
+  uint32_t w[12];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    uint4 q4 = __ldg(p + i);
+    w[4 * i] = q4.x;
+    w[4 * i + 1] = q4.y;
+    w[4 * i + 2] = q4.z;
+    w[4 * i + 3] = q4.w;
+  }
+  uint32_t bad = 0;
+#pragma unroll
+  for (int g = 0; g < 4; g++) {  // 3 words -> 8 coefficients
+    const uint32_t a = w[3 * g], b = w[3 * g + 1], c = w[3 * g + 2];
+    uint32_t t[8];
+    t[0] = a & 0xfff;
+    t[1] = (a >> 12) & 0xfff;
+    t[2] = ((a >> 24) | (b << 8)) & 0xfff;
+    t[3] = (b >> 4) & 0xfff;
+    t[4] = (b >> 16) & 0xfff;
+    t[5] = ((b >> 28) | (c << 4)) & 0xfff;
+    t[6] = (c >> 8) & 0xfff;
+    t[7] = c >> 20;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      bad |= (t[j] >= (uint32_t)Q);
+      r[8 * g + j] = (int32_t)(t[j] << 16);
+    }
+  }
+  return bad;
+}
+
+// acc += MulHat(a, b) on C layout, with a streamed from global memory as packed words and
+// b read from this lane's private copy in shared memory (word index w*8 + v, stride kept by caller)
+__device__ __forceinline__ void mulhat_acc_words(int32_t (&acc)[32], const uint32_t (&aw)[16],
+                                                 const uint32_t* __restrict__ bpriv, const kyber::LaneTw& t) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const kyber::TwPair z = t.l2[j];  // Zetas[64 + 8v + j]
+    int32_t x0, x1, x2, x3, y0, y1, y2, y3;
+    kyber::unpack2(aw[2 * j], x0, x1);
+    kyber::unpack2(aw[2 * j + 1], x2, x3);
+    kyber::unpack2(bpriv[(2 * j) * 8], y0, y1);
+    kyber::unpack2(bpriv[(2 * j + 1) * 8], y2, y3);
+    const int32_t a0 = x0 >> 16, a1 = x1 >> 16, a2 = x2 >> 16, a3 = x3 >> 16;
+    const int32_t b0 = y0 >> 16, b1 = y1 >> 16, b2 = y2 >> 16, b3 = y3 >> 16;
+    int32_t p0 = kyber::mont_prod_hi(a1, b1);
+    p0 = kyber::mont_mul_hi(p0 >> 16, z.z, z.zq);
+    p0 += kyber::mont_prod_hi(a0, b0);
+    const int32_t p1 = kyber::mont_prod_hi(a0, b1) + kyber::mont_prod_hi(a1, b0);
+    int32_t p2 = kyber::mont_prod_hi(a3, b3);
+    p2 = -kyber::mont_mul_hi(p2 >> 16, z.z, z.zq);
+    p2 += kyber::mont_prod_hi(a2, b2);
+    const int32_t p3 = kyber::mont_prod_hi(a2, b3) + kyber::mont_prod_hi(a3, b2);
+    acc[4 * j] += p0;
+    acc[4 * j + 1] += p1;
+    acc[4 * j + 2] += p2;
+    acc[4 * j + 3] += p3;
+  }
+}
+
+__device__ __forceinline__ void load_words_C(const uint32_t* __restrict__ poly, int v, uint32_t (&w)[16]) {
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    uint4 q4 = __ldg(reinterpret_cast<const uint4*>(poly + 16 * v + 4 * c));
+    w[4 * c] = q4.x;
+    w[4 * c + 1] = q4.y;
+    w[4 * c + 2] = q4.z;
+    w[4 * c + 3] = q4.w;
+  }
+}
+
+constexpr int kEncThreads = 128;  // 16 octets = 16 operations per CTA
+
+template <int K>
+__global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
+    const uint8_t* __restrict__ ek, size_t ek_stride, const int16_t* __restrict__ A, int a_shared,
+    const int16_t* __restrict__ noise, const uint8_t* __restrict__ m, size_t n, uint8_t* __restrict__ ct,
+    uint8_t* __restrict__ ss, uint8_t* __restrict__ status, const kyber::TwPair* __restrict__ tw) {
+  using P = Params<K>;
+  using namespace kyber;
+  __shared__ __align__(16) uint32_t tiles[(kEncThreads / 8) * kPolyWords];
+  __shared__ uint32_t rh_store[(kEncThreads / 8) * K * 128];  // NTT(r), lane-private words [oct][j][w][v]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
+  const unsigned octmask = 0xffu << (8 * oct);
+  uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
+  uint32_t* rh = rh_store + (size_t)(warp * 4 + oct) * K * 128 + v;
+
+  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
+  if (base >= n) return;
+  const size_t op_raw = base + oct;
+  const bool active = op_raw < n;
+  const size_t op = active ? op_raw : n - 1;
+  const uint8_t* ekp = ek + op * ek_stride;
+  const uint32_t* Ap = reinterpret_cast<const uint32_t*>(A) + (a_shared ? 0 : op * K * K * (N / 2));
+  const uint32_t* np = reinterpret_cast<const uint32_t*>(noise) + op * P::n_noise * (N / 2);
+  uint8_t* ctp = ct + op * P::ct_bytes;
+
+  LaneTw tf, ti;
+  load_lane_tw(tf, tw, v);
+  load_lane_tw(ti, tw, 7 - v);
+  int32_t r[32];
+
+  // rh = BarrettReduce(NTT(r))   (cpapke.go:142-144)
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    gload_S(np + j * (N / 2), v, r);
+    fwd_pass_S(r);
+    store_S(tile, v, r);
+    __syncwarp();
+    load_C(tile, v, r);
+    fwd_pass_C(r, tf);
+    __syncwarp();
+#pragma unroll
+    for (int w = 0; w < 16; w++) rh[(j * 16 + w) * 8] = pack2(barrett_hi(r[2 * w]), barrett_hi(r[2 * w + 1]));
+  }
+
+  // u[i] = InvNTT(BarrettReduce(A^T[i] . rh)) + e1[i]; v = InvNTT(BarrettReduce(t . rh)) + e2 + m
+  uint32_t bad = 0;
+#pragma unroll 1
+  for (int i = 0; i <= K; i++) {
+#pragma unroll
+    for (int c = 0; c < 32; c++) r[c] = 0;
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+      uint32_t aw[16];
+      if (i < K) {
+        load_words_C(Ap + (i * K + j) * (N / 2), v, aw);
+      } else {  // row K: t-hat from the encapsulation key, PolyDotHat(&v, &pk.th, &rh) (cpapke.go:167)
+        int32_t th[32];
+        bad |= unpack12_C(ekp + 384 * j + 48 * v, th);
+#pragma unroll
+        for (int w = 0; w < 16; w++) aw[w] = pack2(th[2 * w], th[2 * w + 1]);
+      }
+      mulhat_acc_words(r, aw, rh + j * 128, tf);
+    }
+#pragma unroll
+    for (int c = 0; c < 32; c++) r[c] = barrett_hi(r[c]);
+    inv_pass_C(r, ti);
+    store_C(tile, v, r);
+    __syncwarp();
+    load_S(tile, v, r);
+    inv_pass_S(r, v);
+    __syncwarp();
+    {  // + e1[i] / + e2 (+ Decompress_q(m, 1)), S layout
+      const uint32_t* e = np + (K + i) * (N / 2);
+      const uint32_t* mw = reinterpret_cast<const uint32_t*>(m + 32 * op);
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        int32_t e0, e1;
+        unpack2(__ldg(e + 8 * s + v), e0, e1);
+        r[2 * s] += e0;
+        r[2 * s + 1] += e1;
+        if (i == K) {  // DecompressMessage, poly.go:134-147: coefficient idx = 16 s + 2 v + b <- bit idx of m
+          const uint32_t word = __ldg(mw + (s >> 1));
+          const uint32_t bits = (word >> (16 * (s & 1) + 2 * v)) & 3;
+          r[2 * s] += (bits & 1) ? ((Q + 1) / 2) << 16 : 0;
+          r[2 * s + 1] += (bits & 2) ? ((Q + 1) / 2) << 16 : 0;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; c++) r[c] = csubq_hi(barrett_hi(r[c]));  // Normalize (cpapke.go:176-177)
+    store_S(tile, v, r);
+    __syncwarp();
+    load_C(tile, v, r);
+    __syncwarp();
+    bad = __any_sync(octmask, bad) ? 1u : 0u;  // after row K this holds the modulus check of the whole key
+    if (active) {
+      if (i < K)
+        compress_store_C<P::du>(r, reinterpret_cast<uint32_t*>(ctp + i * 32 * P::du) + v * P::du);
+      else if (!bad)
+        compress_store_C<P::dv>(r, reinterpret_cast<uint32_t*>(ctp + K * 32 * P::du) + v * P::dv);
+    }
+  }
+  // kem.ErrPubKey (cpapke.go:48-54): no output for a non-canonical key
+  if (active) {
+    if (bad) {
+      uint32_t* c32 = reinterpret_cast<uint32_t*>(ctp);
+      for (int w = v; w < P::ct_bytes / 4; w += 8) c32[w] = 0;
+      reinterpret_cast<uint32_t*>(ss + 32 * op)[v] = 0;
+    }
+    if (status && v == 0) status[op] = (uint8_t)bad;
+  }
+}
+
+// ------------------------------------------------------------------ host side
+struct Work {
+  uint64_t* h;      // nkeys x 4
+  uint64_t* r;      // n x 4
+  int16_t* A;       // nkeys_sub x K*K x 256
+  int16_t* noise;   // sub x (2K+1) x 256
+};
+
+// sub-batch size: A^T + noise of one sub-batch (8 KiB / op for K=3, 12.5 KiB for K=4) stay L2-resident
+constexpr size_t kSub = 8192;
+
+template <int K>
+static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
+                         uint8_t* status, size_t n, cudaStream_t st, int slot) {
+  using P = Params<K>;
+  Ctx& c = ctx();
+  const bool shared = (ek_stride == 0);
+  const size_t nkeys = shared ? 1 : n;
+  const size_t sub = n < kSub ? n : kSub;
+  const size_t subkeys = shared ? 1 : sub;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_h = take(nkeys * 32), o_r = take(n * 32), o_A = take(subkeys * K * K * 512),
+               o_n = take(sub * P::n_noise * 512);
+  void* base = nullptr;
+  int rc = ensure_work(slot, off, &base);
+  if (rc) return rc;
+  uint64_t* h = (uint64_t*)((char*)base + o_h);
+  uint64_t* r = (uint64_t*)((char*)base + o_r);
+  int16_t* A = (int16_t*)((char*)base + o_A);
+  int16_t* noise = (int16_t*)((char*)base + o_n);
+
+  hash_ek_kernel<K><<<(unsigned)((nkeys + 127) / 128), 128, 0, st>>>(ek, ek_stride, nkeys, h);
+  g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, h, shared ? 1 : 0, n, ss, r);
+  count_launch(2);
+  for (size_t first = 0; first < n; first += sub) {
+    const size_t cnt = (n - first < sub) ? n - first : sub;
+    const size_t keys_here = shared ? (first == 0 ? 1 : 0) : cnt;  // shared key: A^T is derived once
+    const size_t mat_blocks = (keys_here * K * K + 127) / 128;
+    const size_t noise_blocks = (cnt * P::n_noise + 127) / 128;
+    sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, 0, st>>>(
+        ek + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise, mat_blocks);
+    encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
+        ek + (shared ? 0 : first * ek_stride), ek_stride, A, shared ? 1 : 0, noise, seeds + 32 * first, cnt,
+        ct + first * P::ct_bytes, ss + 32 * first, status ? status + first : nullptr,
+        (const kyber::TwPair*)c.kyber_tw);
+    count_launch(2);
+  }
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+static int encaps_any(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
+                      uint8_t* status, size_t n, cudaStream_t st, int slot) {
+  return k == 3 ? encaps_device<3>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
+                : encaps_device<4>(ek, ek_stride, seeds, ct, ss, status, n, st, slot);
+}
+
+}  // namespace mlkem
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+size_t cb200_mlkem_public_key_size(int k) { return (k >= 2 && k <= 4) ? 384u * k + 32 : 0; }
+size_t cb200_mlkem_ciphertext_size(int k) { return k == 3 ? 1088 : k == 4 ? 1568 : k == 2 ? 768 : 0; }
+
+int cb200_mlkem_encaps(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
+                       uint8_t* status, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (k != 3 && k != 4) {
+    set_error("cb200_mlkem_encaps: k must be 3 (ML-KEM-768) or 4 (ML-KEM-1024), got %d", k);
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  const size_t eksz = cb200_mlkem_public_key_size(k), ctsz = cb200_mlkem_ciphertext_size(k);
+  if (!ek || !seeds || !ct || !ss || (ek_stride != 0 && ek_stride < eksz)) {
+    set_error("cb200_mlkem_encaps: bad argument");
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(ct);
+  if (dev != is_device_ptr(ek) || dev != is_device_ptr(seeds) || dev != is_device_ptr(ss) ||
+      (status && dev != is_device_ptr(status))) {
+    set_error("cb200_mlkem_encaps: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  if (dev) {
+    if (((uintptr_t)ek | (uintptr_t)seeds | (uintptr_t)ct | (uintptr_t)ss | ek_stride) & 15) {
+      set_error("cb200_mlkem_encaps: device buffers and ek_stride must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    // status is needed to report kem.ErrPubKey; with device pointers the caller reads it asynchronously
+    return mlkem::encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, ctx().cur, 3);
+  }
+  // host pointers: stage chunks through HBM on three streams (H2D | kernels | D2H overlap)
+  std::vector<uint8_t> st_local;
+  if (!status) {
+    st_local.resize(n);
+    status = st_local.data();
+  }
+  std::vector<Buf> bufs(5);
+  bufs[0] = Buf{ek, nullptr, eksz, ek_stride == 0, ek_stride};
+  bufs[1] = Buf{seeds, nullptr, 32, false, 0};
+  bufs[2] = Buf{nullptr, ct, ctsz, false, 0};
+  bufs[3] = Buf{nullptr, ss, 32, false, 0};
+  bufs[4] = Buf{nullptr, status, 1, false, 0};
+  rc = run_staged(bufs, n, 1u << 16, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+    return mlkem::encaps_any(k, (const uint8_t*)d[0], ek_stride == 0 ? 0 : eksz, (const uint8_t*)d[1],
+                             (uint8_t*)d[2], (uint8_t*)d[3], (uint8_t*)d[4], cnt, st, slot);
+  });
+  if (rc) return rc;
+  size_t nbad = 0;
+  for (size_t i = 0; i < n; i++) nbad += status[i] != 0;
+  if (nbad) {
+    set_error("cb200_mlkem_encaps: %zu of %zu encapsulation keys are not canonical (kem.ErrPubKey)", nbad, n);
+    return CB200_ERR_PUBKEY;
+  }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,190 @@
+"""kem.Scheme mirror for ML-KEM-768 / ML-KEM-1024 over the C ABI.
+
+Mirrors the method names, argument meaning and error behaviour of
+  kem/kem.go:33-121                      (kem.Scheme, kem.Err*)
+  kem/mlkem/mlkem768/kyber.go:267-407    (scheme boilerplate)
+for the path this repository accelerates (public-key parsing + Encapsulate),
+and adds the batch entry points a per-op GPU call cannot do without
+(SURVEY.md 8(b)).  Programmer errors (wrong lengths) raise like the
+reference panics; data errors raise the kem.Err* mirror classes.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._ffi import Cb200Error, check, lib
+
+
+class KemError(Exception):
+    pass
+
+
+class ErrPubKeySize(KemError):       # kem.ErrPubKeySize, kem/kem.go:112
+    pass
+
+
+class ErrPubKey(KemError):           # kem.ErrPubKey, kem/kem.go:118 (ek not reduced mod q)
+    pass
+
+
+class ErrSeedSize(KemError):         # kem.ErrSeedSize
+    pass
+
+
+class ErrTypeMismatch(KemError):     # kem.ErrTypeMismatch
+    pass
+
+
+class PublicKey:
+    """kem.PublicKey: holds the packed encapsulation key (immutable)."""
+
+    def __init__(self, scheme: "Scheme", packed: bytes):
+        self._scheme = scheme
+        self._packed = bytes(packed)
+
+    def Scheme(self):
+        return self._scheme
+
+    def MarshalBinary(self) -> bytes:
+        return self._packed
+
+    def Equal(self, other) -> bool:
+        return isinstance(other, PublicKey) and other._scheme is self._scheme and other._packed == self._packed
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+class Scheme:
+    def __init__(self, name: str, k: int):
+        self._name, self._k = name, k
+
+    # ---- kem.Scheme size/identity methods (kyber.go:271-279) ----
+    def Name(self) -> str:
+        return self._name
+
+    def PublicKeySize(self) -> int:
+        return 384 * self._k + 32
+
+    def PrivateKeySize(self) -> int:
+        return 768 * self._k + 96
+
+    def CiphertextSize(self) -> int:
+        return {3: 1088, 4: 1568}[self._k]
+
+    def SharedKeySize(self) -> int:
+        return 32
+
+    def SeedSize(self) -> int:
+        return 64
+
+    def EncapsulationSeedSize(self) -> int:
+        return 32
+
+    # ---- keys ----
+    def UnmarshalBinaryPublicKey(self, buf: bytes) -> PublicKey:
+        """kyber.go:390-396.  Length errors are reported here; the FIPS 203 modulus
+        check (cpapke.go:45-55) is evaluated on the device when the key is first
+        used and surfaces as ErrPubKey from Encapsulate*."""
+        if len(buf) != self.PublicKeySize():
+            raise ErrPubKeySize("kem: invalid public key size")
+        return PublicKey(self, buf)
+
+    # ---- encapsulation ----
+    def EncapsulateDeterministically(self, pk: PublicKey, seed: bytes):
+        """kyber.go:359-374 (batch of one)."""
+        if not isinstance(pk, PublicKey) or pk._scheme is not self:
+            raise ErrTypeMismatch("kem: type mismatch")
+        if len(seed) != self.EncapsulationSeedSize():
+            raise ErrSeedSize("kem: invalid seed size")
+        ct, ss = self.EncapsulateBatch(pk, np.frombuffer(seed, dtype=np.uint8).reshape(1, 32))
+        return ct[0].tobytes(), ss[0].tobytes()
+
+    def EncapsulateBatch(self, pks, seeds, ct=None, ss=None):
+        """Batched EncapsulateDeterministically.
+
+        pks:   one PublicKey (shared by all ops), or an (n, PublicKeySize) uint8
+               array / CUDA tensor of packed keys (one per op; A^T and H(ek) are
+               rebuilt on the device for every op).
+        seeds: (n, 32) uint8 array or CUDA tensor.
+        Returns (ct, ss): (n, CiphertextSize), (n, 32) in the same kind of memory.
+        Raises ErrPubKey if any key is not canonical.
+        """
+        k, eksz, ctsz = self._k, self.PublicKeySize(), self.CiphertextSize()
+        torch_mode = _is_torch(seeds)
+        if torch_mode:
+            import torch
+            n = seeds.shape[0]
+            assert seeds.is_cuda and seeds.dtype == torch.uint8 and seeds.is_contiguous() and seeds.shape[1] == 32
+            if isinstance(pks, PublicKey):
+                ek = torch.frombuffer(bytearray(pks._packed), dtype=torch.uint8).to(seeds.device)
+                stride = 0
+            else:
+                ek = pks
+                assert ek.is_cuda and ek.is_contiguous() and tuple(ek.shape) == (n, eksz)
+                stride = eksz
+            ct = torch.empty((n, ctsz), dtype=torch.uint8, device=seeds.device) if ct is None else ct
+            ss = torch.empty((n, 32), dtype=torch.uint8, device=seeds.device) if ss is None else ss
+            status = torch.zeros((n,), dtype=torch.uint8, device=seeds.device)
+            check(lib().cb200_set_stream(torch.cuda.current_stream().cuda_stream))
+            check(lib().cb200_mlkem_encaps(k, ek.data_ptr(), stride, seeds.data_ptr(), ct.data_ptr(), ss.data_ptr(),
+                                           status.data_ptr(), n))
+            self._last_status = status  # read lazily: the call is asynchronous on the torch stream
+            return ct, ss
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
+        if seeds.ndim != 2 or seeds.shape[1] != 32:
+            raise ErrSeedSize("kem: invalid seed size")
+        n = seeds.shape[0]
+        if isinstance(pks, PublicKey):
+            ek = np.frombuffer(pks._packed, dtype=np.uint8)
+            stride = 0
+        else:
+            ek = np.ascontiguousarray(pks, dtype=np.uint8)
+            if ek.shape != (n, eksz):
+                raise ErrPubKeySize("kem: invalid public key size")
+            stride = eksz
+        ct = np.empty((n, ctsz), dtype=np.uint8) if ct is None else ct
+        ss = np.empty((n, 32), dtype=np.uint8) if ss is None else ss
+        status = np.zeros((n,), dtype=np.uint8)
+        try:
+            check(lib().cb200_mlkem_encaps(k, ek.ctypes.data, stride, seeds.ctypes.data, ct.ctypes.data,
+                                           ss.ctypes.data, status.ctypes.data, n))
+        except Cb200Error as e:
+            if e.code == -3:
+                err = ErrPubKey("kem: invalid public key")
+                err.status = status
+                raise err from None
+            raise
+        return ct, ss
+
+    def check_last_status(self):
+        """Device-pointer mode: synchronise and raise ErrPubKey if any op of the last batch failed."""
+        st = getattr(self, "_last_status", None)
+        if st is not None and bool(st.any().item()):
+            err = ErrPubKey("kem: invalid public key")
+            err.status = st.cpu().numpy()
+            raise err
+
+    # ---- outside the accelerated path (next rows) ----
+    def GenerateKeyPair(self):
+        raise NotImplementedError("key generation is not on the accelerated path yet (SURVEY.md 8(f) row 2)")
+
+    DeriveKeyPair = GenerateKeyPair
+
+    def Decapsulate(self, sk, ct):
+        raise NotImplementedError("decapsulation is not on the accelerated path yet (SURVEY.md 8(f) row 1)")
+
+
+_SCHEMES = {"ml-kem-768": Scheme("ML-KEM-768", 3), "ml-kem-1024": Scheme("ML-KEM-1024", 4)}
+
+
+def ByName(name: str):
+    """kem/schemes/schemes.go:70 -- case-insensitive lookup; None if unknown."""
+    return _SCHEMES.get(name.lower())
+
+
+def All():
+    return list(_SCHEMES.values())

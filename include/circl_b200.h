@@ -1,0 +1,86 @@
+/*
+ * include/circl_b200.h -- C ABI of libcirclb200.so, the B200 (sm_100a) batch
+ * polynomial-ring engine behind CIRCL's module-lattice hot path.
+ *
+ * This is the surface a cgo shim binds (see INTEGRATION.md and go/).  Plain
+ * pointers and sizes only.  Every buffer is caller-owned and never retained
+ * past the call.  A pointer may be a host pointer (pageable or pinned) or a
+ * CUDA device pointer; the library detects which (cudaPointerGetAttributes)
+ * and stages host buffers through HBM itself.  All entry points return 0 on
+ * success or a negative code; cb200_last_error() gives the message.  There is
+ * no CPU fallback: without a usable CUDA device every compute call fails.
+ *
+ * Citations are file:line in cloudflare/circl (the interface each entry point
+ * replaces).  Coefficient order is the reference's standard ("detangled")
+ * order; results are bit-identical to the reference's *Generic functions.
+ */
+#ifndef CIRCL_B200_H
+#define CIRCL_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes (mapped by the Go shim to kem.Err*, kem/kem.go:92-121) ---- */
+#define CB200_OK 0
+#define CB200_ERR_ARG (-1)          /* programmer error: the Go shim panics, as the reference does */
+#define CB200_ERR_NOT_INIT (-2)
+#define CB200_ERR_PUBKEY (-3)       /* kem.ErrPubKey: ek not reduced mod q (cpapke.go:45-55); see cb200_mlkem_encaps */
+#define CB200_ERR_SIGN_ATTEMPTS (-4)/* ML-DSA: 576 attempts exhausted (sign/mldsa/mldsa65/internal/dilithium.go:372-377) */
+/* <= -100: CUDA runtime error (-100 - cudaError_t) */
+
+/* ---- lifetime ---- */
+int cb200_init(int device);            /* binds the calling process to one GPU (one process per GPU) */
+void cb200_shutdown(void);
+int cb200_device_count(void);
+const char *cb200_last_error(void);
+const char *cb200_version(void);
+/* Use an existing CUDA stream (cudaStream_t cast to void*) for all subsequent
+ * work on device pointers; NULL (the initial state) is CUDA's legacy default
+ * stream.  Calls with device pointers are asynchronous on that stream; calls
+ * with host pointers return after the results are in the caller's buffer. */
+int cb200_set_stream(void *cuda_stream);
+int cb200_synchronize(void);
+/* Pinned host memory for large batches handed to Go via unsafe.Slice. */
+void *cb200_host_alloc(size_t bytes);
+void cb200_host_free(void *p);
+/* number of kernels launched by this library since init (bench accounting) */
+uint64_t cb200_launch_count(void);
+
+/* ---- Kyber / ML-KEM ring, q = 3329, Poly = [256]int16 ---- */
+/* (*Poly).NTT / InvNTT   pke/kyber/internal/common/generic.go:24,36; stubs_amd64.go:8-14
+ * in place over n contiguous polynomials. */
+int cb200_kyber_ntt(int16_t *polys, size_t n, int inverse);
+/* (*Poly).MulHat         generic.go:49; poly.go:63-100.  out may alias a or b. */
+int cb200_kyber_mulhat(int16_t *out, const int16_t *a, const int16_t *b, size_t n);
+/* PolyDotHat             pke/kyber/kyber768/internal/vec.go:30-37
+ * a, b: n vectors of k polynomials; out: n polynomials. */
+int cb200_kyber_dot(int16_t *out, const int16_t *a, const int16_t *b, int k, size_t n);
+/* Add, Sub, BarrettReduce, Normalize, ToMont   generic.go:7-77, poly.go:13-52 */
+#define CB200_OP_ADD 0
+#define CB200_OP_SUB 1
+#define CB200_OP_BARRETT 2
+#define CB200_OP_NORMALIZE 3
+#define CB200_OP_TOMONT 4
+int cb200_kyber_poly_op(int op, int16_t *out, const int16_t *a, const int16_t *b, size_t n);
+
+/* ---- ML-KEM ---- */
+/* scheme.UnmarshalBinaryPublicKey + EncapsulateDeterministically
+ *   kem/mlkem/mlkem768/kyber.go:390-396,359-374,103-137 (mlkem1024: same lines)
+ * k = 3 (ML-KEM-768: ek 1184, ct 1088) or 4 (ML-KEM-1024: ek 1568, ct 1568).
+ * ek_stride = 0: one ek shared by all n operations (parsed once);
+ * otherwise op i uses ek + i*ek_stride and A^T, H(ek) are rebuilt on device per op.
+ * seeds: n x 32 (the message m); ct: n x CiphertextSize; ss: n x 32.
+ * status (optional, may be NULL): n bytes, 0 = ok, 1 = kem.ErrPubKey for that op
+ * (its ct/ss are zeroed).  Returns CB200_ERR_PUBKEY if any op failed. */
+int cb200_mlkem_encaps(int k, const uint8_t *ek, size_t ek_stride, const uint8_t *seeds, uint8_t *ct, uint8_t *ss,
+                       uint8_t *status, size_t n);
+size_t cb200_mlkem_public_key_size(int k);
+size_t cb200_mlkem_ciphertext_size(int k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

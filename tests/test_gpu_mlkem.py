@@ -1,0 +1,132 @@
+"""GPU parity: batched ML-KEM-768/1024 Encapsulate vs the NIST ACVP vectors and the oracle.
+
+Reads like kem/mlkem/acvp_test.go:83-125 (UnmarshalBinaryPublicKey +
+EncapsulateDeterministically against c/k) and kem/schemes/schemes_test.go.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+KS = {"ML-KEM-768": 3, "ML-KEM-1024": 4}
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import circl_b200
+    circl_b200.init(0)
+    yield circl_b200
+    circl_b200.shutdown()
+
+
+def _h(tag, i, n):
+    return hashlib.shake_256(bytes([tag]) + i.to_bytes(8, "little")).digest(n)
+
+
+def key_pool(k, count):
+    import oracle
+    return [oracle.mlkem_keygen(k, _h(0, j, 64))[0] for j in range(count)]
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_acvp_encaps_single_calls(cb, mlkem_acvp, ps):
+    from circl_b200 import mlkem
+    scheme = mlkem.ByName(ps)
+    assert scheme is not None and scheme.Name() == ps
+    for t in mlkem_acvp["encap"][ps][:5]:
+        ek = scheme.UnmarshalBinaryPublicKey(bytes.fromhex(t["ek"]))
+        ct, ss = scheme.EncapsulateDeterministically(ek, bytes.fromhex(t["m"]))
+        assert ct.hex().upper() == t["c"].upper()
+        assert ss.hex().upper() == t["k"].upper()
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_acvp_encaps_one_batch(cb, mlkem_acvp, ps):
+    from circl_b200 import mlkem
+    scheme = mlkem.ByName(ps)
+    tests = mlkem_acvp["encap"][ps]
+    eks = np.stack([np.frombuffer(bytes.fromhex(t["ek"]), dtype=np.uint8) for t in tests])
+    ms = np.stack([np.frombuffer(bytes.fromhex(t["m"]), dtype=np.uint8) for t in tests])
+    ct, ss = scheme.EncapsulateBatch(eks, ms)
+    for i, t in enumerate(tests):
+        assert ct[i].tobytes().hex().upper() == t["c"].upper(), t["tcId"]
+        assert ss[i].tobytes().hex().upper() == t["k"].upper(), t["tcId"]
+
+
+@pytest.mark.parametrize("ps", list(KS))
+@pytest.mark.parametrize("n", [1, 7, 33, 2000])
+def test_batch_vs_oracle_per_op_keys(cb, ps, n):
+    import oracle
+    from circl_b200 import mlkem
+    k = KS[ps]
+    scheme = mlkem.ByName(ps)
+    pool = key_pool(k, min(n, 16))
+    eks = np.stack([np.frombuffer(pool[i % len(pool)], dtype=np.uint8) for i in range(n)])
+    ms = np.stack([np.frombuffer(_h(1, i, 32), dtype=np.uint8) for i in range(n)])
+    ct, ss = scheme.EncapsulateBatch(eks, ms)
+    wct, wss, fails = oracle.mlkem_encaps_batch(k, eks, ms, nthreads=8)
+    assert fails == 0
+    assert np.array_equal(ct, wct) and np.array_equal(ss, wss)
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_batch_vs_oracle_shared_key(cb, ps):
+    import oracle
+    from circl_b200 import mlkem
+    k = KS[ps]
+    scheme = mlkem.ByName(ps)
+    ek = key_pool(k, 1)[0]
+    n = 20000  # spans several L2-resident sub-batches
+    ms = np.frombuffer(hashlib.shake_256(b"seeds").digest(32 * n), dtype=np.uint8).reshape(n, 32)
+    ct, ss = scheme.EncapsulateBatch(scheme.UnmarshalBinaryPublicKey(ek), ms)
+    wct, wss, fails = oracle.mlkem_encaps_batch(k, np.frombuffer(ek, dtype=np.uint8), ms, nthreads=8)
+    assert fails == 0
+    assert np.array_equal(ct, wct) and np.array_equal(ss, wss)
+
+
+def test_non_canonical_key_is_err_pubkey(cb, mlkem_acvp):
+    from circl_b200 import mlkem
+    scheme = mlkem.ByName("ML-KEM-768")
+    tests = mlkem_acvp["encap"]["ML-KEM-768"][:4]
+    eks = np.stack([np.frombuffer(bytes.fromhex(t["ek"]), dtype=np.uint8) for t in tests]).copy()
+    eks[2, 0], eks[2, 1] = 0xFF, eks[2, 1] | 0x0F  # first coefficient of op 2 = 4095 >= q
+    ms = np.stack([np.frombuffer(bytes.fromhex(t["m"]), dtype=np.uint8) for t in tests])
+    with pytest.raises(mlkem.ErrPubKey) as ei:
+        scheme.EncapsulateBatch(eks, ms)
+    assert ei.value.status.tolist() == [0, 0, 1, 0]
+    with pytest.raises(mlkem.ErrPubKeySize):
+        scheme.UnmarshalBinaryPublicKey(b"\x00" * 10)
+    with pytest.raises(mlkem.ErrSeedSize):
+        scheme.EncapsulateDeterministically(scheme.UnmarshalBinaryPublicKey(eks[0].tobytes()), b"\x00" * 31)
+
+
+def test_device_pointers_large_batch_property(cb):
+    """2^18 ops with device-resident buffers (per-op keys from a pool of 64):
+    oracle-checked on a strided sample; every ciphertext must also decapsulate
+    (oracle) to the same shared secret on that sample."""
+    import torch
+    import oracle
+    from circl_b200 import mlkem
+    k, n = 3, 1 << 18
+    scheme = mlkem.ByName("ML-KEM-768")
+    seeds64 = [_h(0, j, 64) for j in range(64)]
+    keys = [oracle.mlkem_keygen(k, s) for s in seeds64]
+    pool = torch.from_numpy(np.stack([np.frombuffer(ek, dtype=np.uint8) for ek, _ in keys])).cuda()
+    idx = torch.arange(n, device="cuda") % 64
+    eks = pool[idx].contiguous()
+    g = torch.Generator(device="cuda").manual_seed(5)
+    ms = torch.randint(0, 256, (n, 32), generator=g, device="cuda", dtype=torch.uint8)
+    ct, ss = scheme.EncapsulateBatch(eks, ms)
+    scheme.check_last_status()
+    sample = list(range(0, n, 9973)) + [n - 1]
+    ct_h, ss_h, ms_h = ct.cpu().numpy(), ss.cpu().numpy(), ms.cpu().numpy()
+    for i in sample:
+        ek, dk = keys[i % 64]
+        wct, wss = oracle.mlkem_encaps(k, ek, ms_h[i].tobytes())
+        assert ct_h[i].tobytes() == wct and ss_h[i].tobytes() == wss
+        assert oracle.mlkem_decaps(k, dk, ct_h[i].tobytes()) == wss
+    # checksum of checksums is stable across a second run (no races in the pipeline)
+    ct2, ss2 = scheme.EncapsulateBatch(eks, ms)
+    assert torch.equal(ct, ct2) and torch.equal(ss, ss2)

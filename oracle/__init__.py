@@ -247,3 +247,115 @@ def mlkem_encaps_batch(k: int, ek: np.ndarray, m: np.ndarray, nthreads: int = 1)
     ss = np.empty((n, 32), dtype=np.uint8)
     fails = lib().orc_mlkem_encaps_batch(k, _ptr(ct), _ptr(ss), _ptr(ek), stride, _ptr(m), n, nthreads)
     return ct, ss, fails
+
+
+# ------------------------------------------------------------------ Dilithium / ML-DSA-65
+def dil_zetas():
+    L = lib()
+    L.orc_dil_zetas.restype = _u32p
+    L.orc_dil_inv_zetas.restype = _u32p
+    return (np.ctypeslib.as_array(L.orc_dil_zetas(), shape=(256,)).copy(),
+            np.ctypeslib.as_array(L.orc_dil_inv_zetas(), shape=(256,)).copy())
+
+
+def dil_ntt(p):
+    q = np.ascontiguousarray(p, dtype=np.uint32).copy()
+    lib().orc_dil_ntt_batch(_ptr(q), q.size // 256, 0)
+    return q
+
+
+def dil_invntt(p):
+    q = np.ascontiguousarray(p, dtype=np.uint32).copy()
+    lib().orc_dil_ntt_batch(_ptr(q), q.size // 256, 1)
+    return q
+
+
+def dil_mulhat(a, b):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    b = np.ascontiguousarray(b, dtype=np.uint32)
+    out = np.empty_like(a)
+    lib().orc_dil_mulhat_batch(_ptr(out), _ptr(a), _ptr(b), a.size // 256)
+    return out
+
+
+def dil_poly_op(op: int, a, b=None):
+    a = np.ascontiguousarray(a, dtype=np.uint32)
+    out = np.empty_like(a)
+    fa, fo = a.reshape(-1, 256), out.reshape(-1, 256)
+    fb = None if b is None else np.ascontiguousarray(b, dtype=np.uint32).reshape(-1, 256)
+    for i in range(fa.shape[0]):
+        lib().orc_dil_poly_op(op, _ptr(fo[i]), _ptr(fa[i]), None if fb is None else _ptr(fb[i]))
+    return out
+
+
+def dil_exceeds(p, bound: int) -> bool:
+    return bool(lib().orc_dil_exceeds(_ptr(np.ascontiguousarray(p, dtype=np.uint32)), C.c_uint32(bound)))
+
+
+def _dil_sample(fn, seed: bytes, nonce=None):
+    p = np.empty(256, dtype=np.uint32)
+    if nonce is None:
+        getattr(lib(), fn)(_ptr(p), _buf(seed))
+    else:
+        getattr(lib(), fn)(_ptr(p), _buf(seed), C.c_uint16(nonce))
+    return p
+
+
+def dil_derive_uniform(seed32, nonce):
+    return _dil_sample("orc_dil_derive_uniform", seed32, nonce)
+
+
+def dil_derive_leqeta(seed64, nonce):
+    return _dil_sample("orc_dil_derive_leqeta", seed64, nonce)
+
+
+def dil_derive_legamma1(seed64, nonce):
+    return _dil_sample("orc_dil_derive_legamma1", seed64, nonce)
+
+
+def dil_derive_ball(seed48):
+    return _dil_sample("orc_dil_derive_ball", seed48)
+
+
+def mldsa65_keygen(seed32: bytes):
+    pk = (C.c_uint8 * 1952)()
+    sk = (C.c_uint8 * 4032)()
+    lib().orc_mldsa65_keygen(pk, sk, _buf(seed32))
+    return bytes(pk), bytes(sk)
+
+
+def mldsa65_sign(sk: bytes, msg: bytes, ctx: bytes = b"", rnd: bytes = bytes(32), internal: bool = False):
+    """Returns (signature, attempts)."""
+    sig = (C.c_uint8 * 3309)()
+    L = lib()
+    L.orc_mldsa65_sign.restype = C.c_int
+    n = L.orc_mldsa65_sign(sig, _buf(sk), _buf(msg) if msg else None, C.c_size_t(len(msg)),
+                           _buf(ctx) if ctx else None, C.c_size_t(len(ctx)), _buf(rnd), int(internal))
+    if n < 0:
+        raise RuntimeError("sign: 576 attempts exhausted")
+    return bytes(sig), n
+
+
+def mldsa65_verify(pk: bytes, msg: bytes, sig: bytes, ctx: bytes = b"", internal: bool = False) -> bool:
+    L = lib()
+    L.orc_mldsa65_verify.restype = C.c_int
+    return bool(L.orc_mldsa65_verify(_buf(pk), _buf(msg) if msg else None, C.c_size_t(len(msg)),
+                                     _buf(ctx) if ctx else None, C.c_size_t(len(ctx)), _buf(sig),
+                                     C.c_size_t(len(sig)), int(internal)))
+
+
+def mldsa65_sign_batch(sk: np.ndarray, msgs: list[bytes], rnd=None, nthreads: int = 1):
+    """sk: (4032,) shared or (n, 4032); external interface, empty ctx. Returns (sigs (n,3309), total attempts)."""
+    n = len(msgs)
+    sk = np.ascontiguousarray(sk, dtype=np.uint8)
+    stride = 0 if sk.ndim == 1 else sk.shape[1]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    blob = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8)
+    sig = np.empty((n, 3309), dtype=np.uint8)
+    r = None if rnd is None else np.ascontiguousarray(rnd, dtype=np.uint8)
+    att = lib().orc_mldsa65_sign_batch(_ptr(sig), _ptr(sk), stride, _ptr(blob), _ptr(off),
+                                       None if r is None else _ptr(r), n, nthreads)
+    if att < 0:
+        raise RuntimeError("sign_batch failed")
+    return sig, att

@@ -82,6 +82,35 @@ int orc_mlkem_decaps(int k, uint8_t ss[32], const uint8_t *dk, const uint8_t *ct
 int orc_mlkem_encaps_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, size_t ek_stride,
                            const uint8_t *m, size_t n, int nthreads);
 
+/* ---------------- Dilithium / ML-DSA-65 (q = 8380417) ---------------- */
+#define ORC_MLDSA65_PK 1952
+#define ORC_MLDSA65_SK 4032
+#define ORC_MLDSA65_SIG 3309
+uint32_t orc_dil_mont_reduce_le2q(uint64_t x);        /* sign/internal/dilithium/field.go:20-24 */
+const uint32_t *orc_dil_zetas(void);                   /* ntt.go:19 (regenerated) */
+const uint32_t *orc_dil_inv_zetas(void);               /* ntt.go:66 (regenerated) */
+void orc_dil_ntt(uint32_t p[256]);                     /* ntt.go:111-184 */
+void orc_dil_invntt(uint32_t p[256]);                  /* ntt.go:191-217 */
+void orc_dil_mulhat(uint32_t p[256], const uint32_t a[256], const uint32_t b[256]); /* poly.go:88 */
+/* op: 0 add, 1 sub, 2 reduceLe2Q, 3 normalize, 4 normalizeAssumingLe2Q (poly.go:10-45) */
+void orc_dil_poly_op(int op, uint32_t *p, const uint32_t *a, const uint32_t *b);
+int orc_dil_exceeds(const uint32_t *p, uint32_t bound); /* poly.go:51-71 */
+void orc_dil_decompose(const uint32_t *p, uint32_t *p0plusq, uint32_t *p1); /* mldsa65/internal/rounding.go:13-43 */
+void orc_dil_ntt_batch(uint32_t *p, size_t n, int inverse);
+void orc_dil_mulhat_batch(uint32_t *p, const uint32_t *a, const uint32_t *b, size_t n);
+void orc_dil_derive_uniform(uint32_t p[256], const uint8_t seed[32], uint16_t nonce);   /* sample.go:92-123 */
+void orc_dil_derive_leqeta(uint32_t p[256], const uint8_t seed[64], uint16_t nonce);    /* sample.go:129-181 */
+void orc_dil_derive_legamma1(uint32_t p[256], const uint8_t seed[64], uint16_t nonce);  /* sample.go:197-209 */
+void orc_dil_derive_ball(uint32_t p[256], const uint8_t seed[48]);                      /* sample.go:299-339 */
+void orc_mldsa65_keygen(uint8_t pk[1952], uint8_t sk[4032], const uint8_t seed[32]);    /* internal/dilithium.go:181-241 */
+/* returns the number of rejection-loop attempts (>= 1), or -1 after 576 (dilithium.go:372-377) */
+int orc_mldsa65_sign(uint8_t sig[3309], const uint8_t *sk, const uint8_t *msg, size_t msglen, const uint8_t *ctx,
+                     size_t ctxlen, const uint8_t rnd[32], int internal);
+int orc_mldsa65_verify(const uint8_t pk[1952], const uint8_t *msg, size_t msglen, const uint8_t *ctx, size_t ctxlen,
+                       const uint8_t *sig, size_t siglen, int internal);
+int orc_mldsa65_sign_batch(uint8_t *sig, const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *off,
+                           const uint8_t *rnd, size_t n, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,10 @@ SYMBOLS = {
     "cb200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "cb200_host_free": (None, [C.c_void_p]),
     "cb200_launch_count": (C.c_uint64, []),
+    "cb200_profile_enable": (C.c_int, [C.c_int]),
+    "cb200_profile_kernel_count": (C.c_int, []),
+    "cb200_profile_kernel_name": (C.c_char_p, [C.c_int]),
+    "cb200_profile_read": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "cb200_kyber_ntt": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int]),
     "cb200_kyber_mulhat": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cb200_kyber_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),

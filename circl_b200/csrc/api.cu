@@ -22,6 +22,32 @@ Ctx& ctx() {
   return c;
 }
 
+static const char* kKernelNames[KID_COUNT] = {
+    "kyber_ntt", "kyber_invntt", "kyber_dot", "kyber_elementwise",
+    "mlkem_hash_ek", "mlkem_g", "mlkem_sample", "mlkem_encrypt",
+    "dil_ntt", "dil_invntt", "dil_dot", "dil_elementwise",
+    "mldsa_expand_key", "mldsa_mu_rhoprime", "mldsa_mask", "mldsa_w", "mldsa_challenge", "mldsa_response",
+    "mldsa_compact"};
+const char* kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? kKernelNames[id] : "?"; }
+
+KernelScope::KernelScope(int id_, cudaStream_t st_) : st(st_), id(id_) {
+  Ctx& c = ctx();
+  c.launches.fetch_add(1, std::memory_order_relaxed);
+  if (c.profiling) {
+    cudaEventCreate(&a);
+    cudaEventRecord(a, st);
+  }
+}
+KernelScope::~KernelScope() {
+  if (!a) return;
+  Ctx& c = ctx();
+  cudaEvent_t b;
+  cudaEventCreate(&b);
+  cudaEventRecord(b, st);
+  std::lock_guard<std::mutex> lock(c.prof_mu);
+  c.prof.push_back(ProfRec{id, a, b});
+}
+
 int require_ready() {
   if (!ctx().ready) {
     set_error("cb200: not initialised (call cb200_init; there is no CPU fallback)");
@@ -218,6 +244,38 @@ void cb200_host_free(void* p) {
 }
 
 uint64_t cb200_launch_count(void) { return ctx().launches.load(); }
+
+int cb200_profile_enable(int on) {
+  int rc = require_ready();
+  if (rc) return rc;
+  ctx().profiling = on != 0;
+  return 0;
+}
+int cb200_profile_kernel_count(void) { return KID_COUNT; }
+const char* cb200_profile_kernel_name(int id) { return kernel_name(id); }
+int cb200_profile_read(double* ms_total, uint64_t* launches, int n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  Ctx& c = ctx();
+  CB200_CUDA(cudaDeviceSynchronize());
+  std::lock_guard<std::mutex> lock(c.prof_mu);
+  for (int i = 0; i < n; i++) {
+    ms_total[i] = 0;
+    launches[i] = 0;
+  }
+  for (ProfRec& r : c.prof) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    if (r.id < n) {
+      ms_total[r.id] += ms;
+      launches[r.id] += 1;
+    }
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  c.prof.clear();
+  return 0;
+}
 
 // ---------------------------------------------------------------- Kyber ring ops
 int cb200_kyber_ntt(int16_t* polys, size_t n, int inverse) {

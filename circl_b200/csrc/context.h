@@ -13,6 +13,11 @@
 
 namespace cb200 {
 
+struct ProfRec {
+  int id;
+  cudaEvent_t a, b;
+};
+
 struct Ctx {
   bool ready = false;
   int device = -1;
@@ -22,6 +27,9 @@ struct Ctx {
   void* kyber_tw = nullptr;     // 128 x {zeta, zetaq}
   void* dil_tw = nullptr;       // 256 x {zeta, invzeta}
   std::atomic<uint64_t> launches{0};
+  bool profiling = false;
+  std::vector<ProfRec> prof;
+  std::mutex prof_mu;
   std::mutex mu;                // serialises host-pointer calls (device scratch is shared)
   // grow-only device scratch, one per pipeline slot
   void* scratch[3] = {nullptr, nullptr, nullptr};
@@ -32,7 +40,25 @@ struct Ctx {
   size_t work_bytes[4] = {0, 0, 0, 0};
 };
 
+// Kernel classes for the optional per-kernel event timing (cb200_profile_*).
+enum KernelId {
+  KID_KYBER_NTT = 0, KID_KYBER_INVNTT, KID_KYBER_DOT, KID_KYBER_EW,
+  KID_MLKEM_HASH_EK, KID_MLKEM_G, KID_MLKEM_SAMPLE, KID_MLKEM_ENCRYPT,
+  KID_DIL_NTT, KID_DIL_INVNTT, KID_DIL_DOT, KID_DIL_EW,
+  KID_MLDSA_EXPAND, KID_MLDSA_MU, KID_MLDSA_MASK, KID_MLDSA_W, KID_MLDSA_CHALLENGE, KID_MLDSA_RESPONSE,
+  KID_MLDSA_COMPACT, KID_COUNT
+};
+const char* kernel_name(int id);
+
 Ctx& ctx();
+// Brackets one kernel launch with events when profiling is on; always counts the launch.
+struct KernelScope {
+  cudaStream_t st;
+  int id;
+  cudaEvent_t a = nullptr;
+  KernelScope(int id, cudaStream_t st);
+  ~KernelScope();
+};
 int require_ready();
 bool is_device_ptr(const void* p);
 int ensure_scratch(int slot, size_t bytes);

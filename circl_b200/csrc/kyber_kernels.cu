@@ -116,12 +116,12 @@ int launch_kyber_ntt(int16_t* d_polys, size_t n, int inverse, const void* tw, cu
   using namespace kyber;
   if (n == 0) return 0;
   int grid = grid_for(n, kOctetsPerCta, 8);
+  KernelScope ks(inverse ? KID_KYBER_INVNTT : KID_KYBER_NTT, st);
   if (inverse)
     ntt_kernel<true><<<grid, kThreads, 0, st>>>((uint32_t*)d_polys, n, (const TwPair*)tw);
   else
     ntt_kernel<false><<<grid, kThreads, 0, st>>>((uint32_t*)d_polys, n, (const TwPair*)tw);
   CB200_CUDA(cudaGetLastError());
-  count_launch();
   return 0;
 }
 
@@ -130,10 +130,10 @@ int launch_kyber_dot(int16_t* d_out, const int16_t* d_a, const int16_t* d_b, int
   using namespace kyber;
   if (n == 0) return 0;
   int grid = grid_for(n, kOctetsPerCta, 8);
+  KernelScope ks(KID_KYBER_DOT, st);
   dot_kernel<<<grid, kThreads, 0, st>>>((uint32_t*)d_out, (const uint32_t*)d_a, (const uint32_t*)d_b, k, n,
                                         (const TwPair*)tw);
   CB200_CUDA(cudaGetLastError());
-  count_launch();
   return 0;
 }
 
@@ -144,6 +144,7 @@ int launch_kyber_poly_op(int op, int16_t* d_out, const int16_t* d_a, const int16
   int grid = grid_for(nvec, 256, 8);
   uint4* o = (uint4*)d_out;
   const uint4 *a = (const uint4*)d_a, *b = (const uint4*)d_b;
+  KernelScope ks(KID_KYBER_EW, st);
   switch (op) {
     case OP_ADD: ew_kernel<OP_ADD><<<grid, 256, 0, st>>>(o, a, b, nvec); break;
     case OP_SUB: ew_kernel<OP_SUB><<<grid, 256, 0, st>>>(o, a, b, nvec); break;
@@ -153,7 +154,6 @@ int launch_kyber_poly_op(int op, int16_t* d_out, const int16_t* d_a, const int16
     default: set_error("cb200_kyber_poly_op: unknown op %d", op); return -1;
   }
   CB200_CUDA(cudaGetLastError());
-  count_launch();
   return 0;
 }
 

@@ -435,21 +435,31 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
   int16_t* A = (int16_t*)((char*)base + o_A);
   int16_t* noise = (int16_t*)((char*)base + o_n);
 
-  hash_ek_kernel<K><<<(unsigned)((nkeys + 127) / 128), 128, 0, st>>>(ek, ek_stride, nkeys, h);
-  g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, h, shared ? 1 : 0, n, ss, r);
-  count_launch(2);
+  {
+    KernelScope ks(KID_MLKEM_HASH_EK, st);
+    hash_ek_kernel<K><<<(unsigned)((nkeys + 127) / 128), 128, 0, st>>>(ek, ek_stride, nkeys, h);
+  }
+  {
+    KernelScope ks(KID_MLKEM_G, st);
+    g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, h, shared ? 1 : 0, n, ss, r);
+  }
   for (size_t first = 0; first < n; first += sub) {
     const size_t cnt = (n - first < sub) ? n - first : sub;
     const size_t keys_here = shared ? (first == 0 ? 1 : 0) : cnt;  // shared key: A^T is derived once
     const size_t mat_blocks = (keys_here * K * K + 127) / 128;
     const size_t noise_blocks = (cnt * P::n_noise + 127) / 128;
-    sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, 0, st>>>(
-        ek + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise, mat_blocks);
-    encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
-        ek + (shared ? 0 : first * ek_stride), ek_stride, A, shared ? 1 : 0, noise, seeds + 32 * first, cnt,
-        ct + first * P::ct_bytes, ss + 32 * first, status ? status + first : nullptr,
-        (const kyber::TwPair*)c.kyber_tw);
-    count_launch(2);
+    {
+      KernelScope ks(KID_MLKEM_SAMPLE, st);
+      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, 0, st>>>(
+          ek + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise, mat_blocks);
+    }
+    {
+      KernelScope ks(KID_MLKEM_ENCRYPT, st);
+      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
+          ek + (shared ? 0 : first * ek_stride), ek_stride, A, shared ? 1 : 0, noise, seeds + 32 * first, cnt,
+          ct + first * P::ct_bytes, ss + 32 * first, status ? status + first : nullptr,
+          (const kyber::TwPair*)c.kyber_tw);
+    }
   }
   CB200_CUDA(cudaGetLastError());
   return 0;

@@ -48,6 +48,13 @@ void *cb200_host_alloc(size_t bytes);
 void cb200_host_free(void *p);
 /* number of kernels launched by this library since init (bench accounting) */
 uint64_t cb200_launch_count(void);
+/* Optional per-kernel-class timing with CUDA events on the launching stream
+ * (used by bench.py for the roofline line).  cb200_profile_read synchronises the
+ * device, fills ms_total[i] / launches[i] for the first n classes and clears. */
+int cb200_profile_enable(int on);
+int cb200_profile_kernel_count(void);
+const char *cb200_profile_kernel_name(int id);
+int cb200_profile_read(double *ms_total, uint64_t *launches, int n);
 
 /* ---- Kyber / ML-KEM ring, q = 3329, Poly = [256]int16 ---- */
 /* (*Poly).NTT / InvNTT   pke/kyber/internal/common/generic.go:24,36; stubs_amd64.go:8-14

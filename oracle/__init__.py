@@ -132,6 +132,12 @@ def kyber_ntt(p):
     return q
 
 
+def kyber_ntt_inplace_mt(p: np.ndarray, inverse: bool, nthreads: int) -> None:
+    """In-place multi-threaded batch NTT (bench.py cpu baseline)."""
+    assert p.dtype == np.int16 and p.flags["C_CONTIGUOUS"]
+    lib().orc_kyber_ntt_batch_mt(_ptr(p), C.c_size_t(p.size // 256), int(inverse), int(nthreads))
+
+
 def kyber_invntt(p):
     q = np.ascontiguousarray(p, dtype=np.int16).copy()
     lib().orc_kyber_ntt_batch(_ptr(q), q.size // 256, 1)

@@ -426,3 +426,23 @@ int orc_mlkem_encaps_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, s
   free(th); free(jobs);
   return fails;
 }
+
+typedef struct { int16_t *p; size_t lo, hi; int inverse; } ntt_job;
+static void *ntt_worker(void *arg) {
+  ntt_job *j = (ntt_job *)arg;
+  orc_kyber_ntt_batch(j->p + j->lo * N, j->hi - j->lo, j->inverse);
+  return NULL;
+}
+/* multi-threaded batch NTT for the CPU baseline leg of bench.py */
+void orc_kyber_ntt_batch_mt(int16_t *p, size_t n, int inverse, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n) nthreads = n ? (int)n : 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+  ntt_job *jobs = (ntt_job *)malloc(sizeof(ntt_job) * nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = (ntt_job){p, n * t / nthreads, n * (t + 1) / nthreads, inverse};
+    pthread_create(&th[t], NULL, ntt_worker, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}

@@ -65,6 +65,7 @@ void orc_kyber_derive_noise(int16_t p[256], const uint8_t *seed, size_t seedlen,
 void orc_kyber_derive_uniform(int16_t p[256], const uint8_t seed[32], uint8_t x, uint8_t y);
 /* batched helpers (n polynomials, contiguous) used by tests / cpu baseline */
 void orc_kyber_ntt_batch(int16_t *p, size_t n, int inverse);
+void orc_kyber_ntt_batch_mt(int16_t *p, size_t n, int inverse, int nthreads);
 void orc_kyber_mulhat_batch(int16_t *p, const int16_t *a, const int16_t *b, size_t n);
 void orc_kyber_dot_batch(int16_t *out, const int16_t *a, const int16_t *b, int k, size_t n);
 

@@ -91,6 +91,19 @@ int ensure_work(int slot, size_t bytes, void** out) {
   return 0;
 }
 
+int ensure_pinned(size_t bytes, void** out) {
+  Ctx& c = ctx();
+  if (c.pinned_bytes < bytes) {
+    if (c.pinned) CB200_CUDA(cudaFreeHost(c.pinned));
+    c.pinned = nullptr;
+    c.pinned_bytes = 0;
+    CB200_CUDA(cudaHostAlloc(&c.pinned, bytes, cudaHostAllocDefault));
+    c.pinned_bytes = bytes;
+  }
+  *out = c.pinned;
+  return 0;
+}
+
 int run_staged(std::vector<Buf>& bufs, size_t n, size_t chunk,
                const std::function<int(void** dev, size_t count, size_t first, cudaStream_t st, int slot)>& body) {
   Ctx& c = ctx();
@@ -208,6 +221,9 @@ void cb200_shutdown(void) {
     c.work[s] = nullptr;
     c.work_bytes[s] = 0;
   }
+  if (c.pinned) cudaFreeHost(c.pinned);
+  c.pinned = nullptr;
+  c.pinned_bytes = 0;
   if (c.kyber_tw) cudaFree(c.kyber_tw);
   if (c.dil_tw) cudaFree(c.dil_tw);
   c.kyber_tw = c.dil_tw = nullptr;

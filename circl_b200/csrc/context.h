@@ -36,6 +36,8 @@ struct Ctx {
   size_t scratch_bytes[3] = {0, 0, 0};
   // grow-only work areas for the multi-kernel pipelines (ML-KEM / ML-DSA)
   // slot 0..2 belong to the staging pipeline streams, slot 3 to device-pointer calls
+  void* pinned = nullptr;       // grow-only pinned host staging for small per-op outputs (status bytes)
+  size_t pinned_bytes = 0;
   void* work[4] = {nullptr, nullptr, nullptr, nullptr};
   size_t work_bytes[4] = {0, 0, 0, 0};
 };
@@ -63,6 +65,7 @@ int require_ready();
 bool is_device_ptr(const void* p);
 int ensure_scratch(int slot, size_t bytes);
 int ensure_work(int slot, size_t bytes, void** out);
+int ensure_pinned(size_t bytes, void** out);
 inline void count_launch(uint64_t n = 1) { ctx().launches.fetch_add(n, std::memory_order_relaxed); }
 
 // One buffer of a batched call: `unit` bytes per batch element; stride 0 = shared by all elements.

@@ -1,0 +1,296 @@
+// circl_b200/csrc/dilithium.cuh -- q = 8380417 ring arithmetic for sm_100a.
+//
+// Replaces (bit-exactly, *generic* semantics; the reference's AVX2 path equals generic here):
+//   sign/internal/dilithium/field.go:5-32     ReduceLe2Q / le2qModQ / montReduceLe2Q
+//   sign/internal/dilithium/ntt.go:111-184    nttGeneric      (asm: amd64.s:9    nttAVX2)
+//   sign/internal/dilithium/ntt.go:191-217    invNttGeneric   (asm: amd64.s:2796 invNttAVX2)
+//   sign/internal/dilithium/poly.go:10-100    mulHat / add / sub / reduce / normalize / exceeds
+//
+// Same "octet" decomposition as kyber.cuh: 8 lanes own one polynomial, 32 uint32
+// coefficients per lane, two register-local passes of 4 layers each
+//   S layout  r[2s+b] = coefficient 16s + 2v + b   -> l = 128, 64, 32, 16 (twiddles are immediates)
+//   C layout  r[i]    = coefficient 32v + i        -> l = 8, 4, 2, 1      (per-lane twiddles)
+// joined by one transposition through padded shared memory.
+#pragma once
+#include <type_traits>
+
+#include "common.cuh"
+
+namespace cb200 {
+namespace dil {
+
+constexpr int N = 256;
+constexpr uint32_t Q = 8380417u;
+constexpr uint32_t QINV = 4236238847u;  // -(q^-1) mod 2^32, params.go
+constexpr uint32_t ROVER256 = 41978u;   // (256)^-1 R^2 mod q
+
+// ---------------------------------------------------------------- twiddles (regenerated, ntt.go:3-18)
+__host__ __device__ constexpr uint32_t brv8(uint32_t x) {
+  uint32_t r = 0;
+  for (int i = 0; i < 8; i++) r |= ((x >> i) & 1u) << (7 - i);
+  return r;
+}
+__host__ __device__ constexpr uint32_t powmod(uint32_t b, uint32_t e) {
+  uint64_t r = 1, x = b;
+  while (e) {
+    if (e & 1) r = r * x % Q;
+    x = x * x % Q;
+    e >>= 1;
+  }
+  return (uint32_t)r;
+}
+__host__ __device__ constexpr uint32_t zeta_of(int i) {  // Zetas[i] = 1753^brv8(i) * 2^32 mod q
+  return (uint32_t)((uint64_t)powmod(1753, brv8((uint32_t)i)) * ((1ull << 32) % Q) % Q);
+}
+__host__ __device__ constexpr uint32_t inv_zeta_of(int i) {  // InvZetas[i] = 1753^-(256 - brv8(255-i)) * 2^32 mod q
+  return (uint32_t)((uint64_t)powmod(powmod(1753, Q - 2), 256 - brv8((uint32_t)(255 - i))) * ((1ull << 32) % Q) % Q);
+}
+template <int I>
+struct Zeta {
+  static constexpr uint32_t z = zeta_of(I);
+  static constexpr uint32_t iz = inv_zeta_of(I);
+};
+
+template <int B, int E, class F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (B < E) {
+    f(std::integral_constant<int, B>{});
+    static_for<B + 1, E>(f);
+  }
+}
+
+// ---------------------------------------------------------------- field ops
+__device__ __forceinline__ uint32_t mont_le2q(uint64_t x) {  // field.go:20-24
+  const uint32_t m = (uint32_t)x * QINV;
+  return (uint32_t)((x + (uint64_t)m * Q) >> 32);
+}
+__device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b) { return mont_le2q((uint64_t)a * b); }
+__device__ __forceinline__ uint32_t reduce_le2q(uint32_t x) {  // field.go:5-13
+  const uint32_t x1 = x >> 23, x2 = x & 0x7FFFFF;
+  return x2 + (x1 << 13) - x1;
+}
+__device__ __forceinline__ uint32_t le2q_modq(uint32_t x) {  // field.go:27-32
+  x -= Q;
+  return x + ((uint32_t)((int32_t)x >> 31) & Q);
+}
+__device__ __forceinline__ uint32_t modq(uint32_t x) { return le2q_modq(reduce_le2q(x)); }
+// exceedsGeneric on one coefficient (poly.go:51-71)
+__device__ __forceinline__ bool exceeds1(uint32_t c, uint32_t bound) {
+  int32_t x = (int32_t)((Q - 1) / 2) - (int32_t)c;
+  x ^= (x >> 31);
+  x = (int32_t)((Q - 1) / 2) - x;
+  return (uint32_t)x >= bound;
+}
+
+// ---------------------------------------------------------------- butterflies
+__device__ __forceinline__ void ct_bfly(uint32_t& a, uint32_t& b, uint32_t z) {  // ntt.go:177-180
+  const uint32_t t = mont_mul(z, b);
+  b = a + (2 * Q - t);
+  a = a + t;
+}
+__device__ __forceinline__ void gs_bfly(uint32_t& a, uint32_t& b, uint32_t z) {  // ntt.go:202-208
+  uint32_t t = a;
+  a = t + b;
+  t += 256 * Q - b;
+  b = mont_mul(z, t);
+}
+
+struct LaneTw {  // per-lane twiddles of the C-layout pass: l = 8, 4, 2, 1
+  uint32_t l8[2], l4[4], l2[8], l1[16];
+};
+// forward: Zetas[16+2v+i], [32+4v+i], [64+8v+i], [128+16v+i]
+__device__ __forceinline__ void load_lane_tw_fwd(LaneTw& t, const uint32_t* __restrict__ zetas, int v) {
+#pragma unroll
+  for (int i = 0; i < 2; i++) t.l8[i] = zetas[16 + 2 * v + i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) t.l4[i] = zetas[32 + 4 * v + i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.l2[i] = zetas[64 + 8 * v + i];
+#pragma unroll
+  for (int i = 0; i < 16; i++) t.l1[i] = zetas[128 + 16 * v + i];
+}
+// inverse (k counts up, ntt.go:191-217): l=1: InvZetas[16v+i], l=2: [128+8v+i], l=4: [192+4v+i], l=8: [224+2v+i]
+__device__ __forceinline__ void load_lane_tw_inv(LaneTw& t, const uint32_t* __restrict__ izetas, int v) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) t.l1[i] = izetas[16 * v + i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.l2[i] = izetas[128 + 8 * v + i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) t.l4[i] = izetas[192 + 4 * v + i];
+#pragma unroll
+  for (int i = 0; i < 2; i++) t.l8[i] = izetas[224 + 2 * v + i];
+}
+
+// forward pass 1, S layout: l = 128 (k=1), 64 (k=2+h), 32 (k=4+h), 16 (k=8+h)
+__device__ __forceinline__ void fwd_pass_S(uint32_t (&r)[32]) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) ct_bfly(r[i], r[i + 16], Zeta<1>::z);
+  static_for<0, 2>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ct_bfly(r[16 * h + i], r[16 * h + i + 8], Zeta<2 + h>::z);
+  });
+  static_for<0, 4>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 4; i++) ct_bfly(r[8 * h + i], r[8 * h + i + 4], Zeta<4 + h>::z);
+  });
+  static_for<0, 8>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 2; i++) ct_bfly(r[4 * h + i], r[4 * h + i + 2], Zeta<8 + h>::z);
+  });
+}
+// forward pass 2, C layout: l = 8, 4, 2, 1
+__device__ __forceinline__ void fwd_pass_C(uint32_t (&r)[32], const LaneTw& t) {
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) ct_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.l8[blk]);
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) ct_bfly(r[8 * blk + j], r[8 * blk + j + 4], t.l4[blk]);
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) ct_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.l2[blk]);
+#pragma unroll
+  for (int blk = 0; blk < 16; blk++) ct_bfly(r[2 * blk], r[2 * blk + 1], t.l1[blk]);
+}
+// inverse pass A, C layout: l = 1, 2, 4, 8
+__device__ __forceinline__ void inv_pass_C(uint32_t (&r)[32], const LaneTw& t) {
+#pragma unroll
+  for (int blk = 0; blk < 16; blk++) gs_bfly(r[2 * blk], r[2 * blk + 1], t.l1[blk]);
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) gs_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.l2[blk]);
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) gs_bfly(r[8 * blk + j], r[8 * blk + j + 4], t.l4[blk]);
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.l8[blk]);
+}
+// inverse pass B, S layout: l = 16 (k=240+h), 32 (248+h), 64 (252+h), 128 (254), then * ROver256
+__device__ __forceinline__ void inv_pass_S(uint32_t (&r)[32]) {
+  static_for<0, 8>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 2; i++) gs_bfly(r[4 * h + i], r[4 * h + i + 2], Zeta<240 + h>::iz);
+  });
+  static_for<0, 4>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 4; i++) gs_bfly(r[8 * h + i], r[8 * h + i + 4], Zeta<248 + h>::iz);
+  });
+  static_for<0, 2>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 8; i++) gs_bfly(r[16 * h + i], r[16 * h + i + 8], Zeta<252 + h>::iz);
+  });
+#pragma unroll
+  for (int i = 0; i < 16; i++) gs_bfly(r[i], r[i + 16], Zeta<254>::iz);
+#pragma unroll
+  for (int i = 0; i < 32; i++) r[i] = mont_mul(ROVER256, r[i]);
+}
+
+// ---------------------------------------------------------------- shared-memory tile (S <-> C)
+// 256 words + 4 pad words after every 32; octet stride 304 words (== 16 mod 32).
+constexpr int kPolyWords = 304;
+__device__ __forceinline__ void store_S(uint32_t* tile, int v, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++)
+    *reinterpret_cast<uint2*>(tile + 16 * s + 2 * v + 4 * (s >> 1)) = make_uint2(r[2 * s], r[2 * s + 1]);
+}
+__device__ __forceinline__ void load_S(const uint32_t* tile, int v, uint32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    const uint2 w = *reinterpret_cast<const uint2*>(tile + 16 * s + 2 * v + 4 * (s >> 1));
+    r[2 * s] = w.x;
+    r[2 * s + 1] = w.y;
+  }
+}
+__device__ __forceinline__ void store_C(uint32_t* tile, int v, const uint32_t (&r)[32]) {
+  uint4* p = reinterpret_cast<uint4*>(tile + 36 * v);
+#pragma unroll
+  for (int c = 0; c < 8; c++) p[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+}
+__device__ __forceinline__ void load_C(const uint32_t* tile, int v, uint32_t (&r)[32]) {
+  const uint4* p = reinterpret_cast<const uint4*>(tile + 36 * v);
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const uint4 w = p[c];
+    r[4 * c] = w.x;
+    r[4 * c + 1] = w.y;
+    r[4 * c + 2] = w.z;
+    r[4 * c + 3] = w.w;
+  }
+}
+
+// ---------------------------------------------------------------- global <-> registers
+__device__ __forceinline__ void gload_S(const uint32_t* __restrict__ poly, int v, uint32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    const uint2 w = *reinterpret_cast<const uint2*>(poly + 16 * s + 2 * v);
+    r[2 * s] = w.x;
+    r[2 * s + 1] = w.y;
+  }
+}
+__device__ __forceinline__ void gstore_S(uint32_t* __restrict__ poly, int v, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++) *reinterpret_cast<uint2*>(poly + 16 * s + 2 * v) = make_uint2(r[2 * s], r[2 * s + 1]);
+}
+__device__ __forceinline__ void gload_C(const uint32_t* __restrict__ poly, int v, uint32_t (&r)[32]) {
+  const uint4* p = reinterpret_cast<const uint4*>(poly + 32 * v);
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const uint4 w = p[c];
+    r[4 * c] = w.x;
+    r[4 * c + 1] = w.y;
+    r[4 * c + 2] = w.z;
+    r[4 * c + 3] = w.w;
+  }
+}
+__device__ __forceinline__ void gstore_C(uint32_t* __restrict__ poly, int v, const uint32_t (&r)[32]) {
+  uint4* p = reinterpret_cast<uint4*>(poly + 32 * v);
+#pragma unroll
+  for (int c = 0; c < 8; c++) p[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+}
+
+// Whole transforms on an octet.  fwd: in S layout -> out C layout; inv: in C layout -> out S layout.
+__device__ __forceinline__ void ntt_octet(uint32_t (&r)[32], uint32_t* tile, int v, const LaneTw& t) {
+  fwd_pass_S(r);
+  store_S(tile, v, r);
+  __syncwarp();
+  load_C(tile, v, r);
+  __syncwarp();
+  fwd_pass_C(r, t);
+}
+__device__ __forceinline__ void invntt_octet(uint32_t (&r)[32], uint32_t* tile, int v, const LaneTw& t) {
+  inv_pass_C(r, t);
+  store_C(tile, v, r);
+  __syncwarp();
+  load_S(tile, v, r);
+  __syncwarp();
+  inv_pass_S(r);
+}
+// layout changes without arithmetic
+__device__ __forceinline__ void s_to_c(uint32_t (&r)[32], uint32_t* tile, int v) {
+  store_S(tile, v, r);
+  __syncwarp();
+  load_C(tile, v, r);
+  __syncwarp();
+}
+__device__ __forceinline__ void c_to_s(uint32_t (&r)[32], uint32_t* tile, int v) {
+  store_C(tile, v, r);
+  __syncwarp();
+  load_S(tile, v, r);
+  __syncwarp();
+}
+
+}  // namespace dil
+}  // namespace cb200

@@ -18,6 +18,12 @@ void kyber_fill_twiddles(int32_t* out);
 }  // namespace cb200
 
 namespace cb200 {
+// dil_kernels.cu
+int launch_dil_ntt(uint32_t* d_polys, size_t n, int inverse, const void* tw, cudaStream_t st);
+int launch_dil_dot(uint32_t* out, const uint32_t* a, const uint32_t* b, int k, size_t n, cudaStream_t st);
+int launch_dil_poly_op(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n, cudaStream_t st);
+int launch_dil_exceeds(const uint32_t* a, uint32_t bound, size_t n, uint8_t* flags, cudaStream_t st);
+void dil_fill_twiddles(uint32_t* out);
 // tables.cu: twiddle tables other than Kyber's (ML-DSA); called from cb200_init
 int init_extra_tables();
 }  // namespace cb200

@@ -15,6 +15,8 @@
 //   2. sample_kernel  one thread per Keccak stream: K*K SHAKE128 matrix streams per key,
 //                     2K+1 SHAKE256 noise streams per op (warps are stream-homogeneous)
 //   3. encrypt_kernel one octet (8 lanes) per op: NTT(r), A^T o r, t o r, InvNTT, +e, compress
+#include <string.h>
+
 #include "../../include/circl_b200.h"
 #include "context.h"
 #include "keccak.cuh"
@@ -510,11 +512,12 @@ int cb200_mlkem_encaps(int k, const uint8_t* ek, size_t ek_stride, const uint8_t
     return mlkem::encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, ctx().cur, 3);
   }
   // host pointers: stage chunks through HBM on three streams (H2D | kernels | D2H overlap)
-  std::vector<uint8_t> st_local;
-  if (!status) {
-    st_local.resize(n);
-    status = st_local.data();
-  }
+  // per-op status always comes back (it carries kem.ErrPubKey); pinned so the D2H copy stays asynchronous
+  uint8_t* user_status = status;
+  void* pin = nullptr;
+  rc = ensure_pinned(n, &pin);
+  if (rc) return rc;
+  status = (uint8_t*)pin;
   std::vector<Buf> bufs(5);
   bufs[0] = Buf{ek, nullptr, eksz, ek_stride == 0, ek_stride};
   bufs[1] = Buf{seeds, nullptr, 32, false, 0};
@@ -528,6 +531,7 @@ int cb200_mlkem_encaps(int k, const uint8_t* ek, size_t ek_stride, const uint8_t
   if (rc) return rc;
   size_t nbad = 0;
   for (size_t i = 0; i < n; i++) nbad += status[i] != 0;
+  if (user_status) memcpy(user_status, status, n);
   if (nbad) {
     set_error("cb200_mlkem_encaps: %zu of %zu encapsulation keys are not canonical (kem.ErrPubKey)", nbad, n);
     return CB200_ERR_PUBKEY;

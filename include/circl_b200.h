@@ -73,6 +73,24 @@ int cb200_kyber_dot(int16_t *out, const int16_t *a, const int16_t *b, int k, siz
 #define CB200_OP_TOMONT 4
 int cb200_kyber_poly_op(int op, int16_t *out, const int16_t *a, const int16_t *b, size_t n);
 
+/* ---- Dilithium / ML-DSA ring, q = 8380417, Poly = [256]uint32 ---- */
+/* (*Poly).NTT / InvNTT   sign/internal/dilithium/generic.go:11,15; stubs_amd64.go:8-14; in place */
+int cb200_dil_ntt(uint32_t *polys, size_t n, int inverse);
+/* (*Poly).MulHat         sign/internal/dilithium/generic.go:19 (poly.go:88) */
+int cb200_dil_mulhat(uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n);
+/* PolyDotHat             sign/mldsa/mldsa65/internal/mat.go:52-59 (k = L polynomials per vector) */
+int cb200_dil_dot(uint32_t *out, const uint32_t *a, const uint32_t *b, int k, size_t n);
+/* Add, Sub, ReduceLe2Q, Normalize, NormalizeAssumingLe2Q, MulBy2toD   generic.go:23-89, poly.go:10-100 */
+#define CB200_DIL_OP_ADD 0
+#define CB200_DIL_OP_SUB 1
+#define CB200_DIL_OP_REDUCE_LE2Q 2
+#define CB200_DIL_OP_NORMALIZE 3
+#define CB200_DIL_OP_NORMALIZE_LE2Q 4
+#define CB200_DIL_OP_MUL_2D 5
+int cb200_dil_poly_op(int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n);
+/* (*Poly).Exceeds        poly.go:51-71 (stubs_amd64.go:32 exceedsAVX2): flags[i] = 1 iff poly i exceeds bound */
+int cb200_dil_exceeds(const uint32_t *polys, uint32_t bound, uint8_t *flags, size_t n);
+
 /* ---- ML-KEM ---- */
 /* scheme.UnmarshalBinaryPublicKey + EncapsulateDeterministically
  *   kem/mlkem/mlkem768/kyber.go:390-396,359-374,103-137 (mlkem1024: same lines)

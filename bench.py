@@ -141,7 +141,7 @@ def run_reference(args):
     import oracle
     threads = host_threads()
     wl = WORKLOADS[args.workload]
-    sample = 1 << 16
+    sample = 1 << 17
     keys = synth_keys(wl["k"], 1024, seed=2024)
     idx = np.arange(sample) % 1024
     eks = np.ascontiguousarray(keys[idx])
@@ -163,7 +163,7 @@ def run_reference(args):
         "config": {"workload": wl["desc"], "batch_per_gpu": 1 << args.batch_log2, "ek": "per-op (stride %d)" % wl["ek"],
                    "key_pool": 1024},
         "cpu_baseline": {"value": value, "unit": "encaps/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} ops per step (first 2^16 of the batch), C restatement of CIRCL's generic "
+                         "sample": f"{sample} ops per step (first 2^17 of the batch), C restatement of CIRCL's generic "
                                    "Go path incl. per-op key parse; CIRCL itself is Go and no Go toolchain exists here"},
         "e2e": {"value": value, "unit": "encaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -338,7 +338,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         import oracle
         threads = host_threads()
-        sample = 1 << 14
+        sample = 1 << 17
         eks_s = np.ascontiguousarray(eks_h.numpy()[:sample])
         seeds_s = np.ascontiguousarray(seeds_h.numpy()[:sample])
         oracle.mlkem_encaps_batch(wl["k"], eks_s[:1024], seeds_s[:1024], nthreads=threads)

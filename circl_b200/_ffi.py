@@ -38,6 +38,10 @@ SYMBOLS = {
     "cb200_dil_exceeds": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
     "cb200_mlkem_encaps": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t]),
+    "cb200_mldsa65_sign": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                     C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "cb200_mldsa65_signature_size": (C.c_size_t, []),
+    "cb200_mldsa65_private_key_size": (C.c_size_t, []),
     "cb200_mlkem_public_key_size": (C.c_size_t, [C.c_int]),
     "cb200_mlkem_ciphertext_size": (C.c_size_t, [C.c_int]),
 }

@@ -226,7 +226,8 @@ void cb200_shutdown(void) {
   c.pinned_bytes = 0;
   if (c.kyber_tw) cudaFree(c.kyber_tw);
   if (c.dil_tw) cudaFree(c.dil_tw);
-  c.kyber_tw = c.dil_tw = nullptr;
+  if (c.small) cudaFree(c.small);
+  c.kyber_tw = c.dil_tw = c.small = nullptr;
   if (c.own) cudaStreamDestroy(c.own);
   c.own = c.cur = nullptr;
   c.ready = false;

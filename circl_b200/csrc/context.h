@@ -26,6 +26,7 @@ struct Ctx {
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // host-pointer calls: H2D -> kernels -> D2H per chunk
   void* kyber_tw = nullptr;     // 128 x {zeta, zetaq}
   void* dil_tw = nullptr;       // 256 x {zeta, invzeta}
+  void* small = nullptr;        // 256-byte device buffer (ML-DSA context string)
   std::atomic<uint64_t> launches{0};
   bool profiling = false;
   std::vector<ProfRec> prof;

@@ -1,0 +1,798 @@
+// circl_b200/csrc/mldsa.cu -- batched ML-DSA-65 Sign on sm_100a.
+//
+// Replaces, per signature and bit-exactly:
+//   (*PrivateKey).Unpack        sign/mldsa/mldsa65/internal/dilithium.go:142-163  (ExpandA, NTT of s1, s2, t0)
+//   SignTo (ML-DSA.Sign_internal) sign/mldsa/mldsa65/internal/dilithium.go:340-470
+//   external framing            sign/mldsa/mldsa65/dilithium.go:56-84  (0x00 || len(ctx) || ctx || msg)
+//   samplers                    internal/sample.go:92-123 (ExpandA), :197-209 (ExpandMask), :299-339 (SampleInBall)
+//   rounding / packing          internal/rounding.go:13-67, internal/pack.go:77-95,205-252, pack.go:23-86,102-108
+//
+// The rejection loop (dilithium.go:369-467) is run in *rounds* over the list of
+// still-active signatures; every stage is a dense kernel:
+//   expand (once)  ExpandA: one thread per SHAKE128 stream; s1/s2/t0: one octet per polynomial (unpack + NTT)
+//   mu             one thread per op: mu = SHAKE256(tr || M'), rho' = SHAKE256(key || rnd || mu)
+//   per round:     mask (thread per y polynomial) -> yntt (octet) -> w (octet per row: A y, InvNTT, Decompose)
+//                  -> challenge (thread per op: c~ = H(mu || w1), SampleInBall) -> cntt (octet)
+//                  -> response (octet per output polynomial: norm checks, z packing, hints)
+//                  -> finalize (thread per op: accept -> pack c~/hints; reject -> next attempt)
+// yNonce advances by L every attempt; the first attempt passing all four checks wins; 576 attempts cap.
+#include <string.h>
+
+#include "../../include/circl_b200.h"
+#include "context.h"
+#include "dilithium.cuh"
+#include "keccak.cuh"
+
+namespace cb200 {
+namespace mldsa {
+
+using namespace dil;
+
+constexpr int K = 6, L = 5, ETA = 4, TAU = 49, BETA = TAU * ETA, OMEGA = 55, CTILDE = 48;
+constexpr uint32_t GAMMA1 = 1u << 19, GAMMA2 = 261888u, ALPHA = 2 * GAMMA2;
+constexpr int SK_BYTES = 4032, SIG_BYTES = 3309, POLY_Z = 640, POLY_W1 = 128;
+constexpr int OFF_KEY = 32, OFF_TR = 64, OFF_S1 = 128, OFF_S2 = OFF_S1 + 128 * L, OFF_T0 = OFF_S2 + 128 * K;
+constexpr int NKEYPOLY = L + K + K;  // s1h | s2h | t0h
+constexpr int MAX_ATTEMPTS = 576;
+
+struct Work {
+  uint32_t *A, *sh;        // per key: A [30][256]; sh = s1h[5] | s2h[6] | t0h[6]
+  uint64_t *mu, *rhop;     // per op: 8 words each
+  uint32_t *y, *yh, *w0;   // per op: [5][256], [5][256], [6][256]
+  uint8_t* w1p;            // per op: 768 bytes
+  uint32_t* c;             // per op: [256] challenge polynomial, then its NTT
+  uint64_t* ctilde;        // per op: 6 words
+  uint32_t *hintbits, *flags, *hintcnt, *attempt;  // per op: [48], 1, 1, 1
+  uint32_t* act[2];        // active lists
+  uint32_t* count;         // [2] list lengths (device)
+};
+
+// ------------------------------------------------------------------ key expansion
+constexpr int kExpThreads = 64;
+constexpr int kExpRow = 257;  // 256 words + 1 slack, odd stride
+
+// ExpandA (mat.go:15-23, sample.go:92-123): A[i][j] = RejNTTPoly(SHAKE128(rho || le16((i<<8)+j)))
+__global__ void __launch_bounds__(kExpThreads) expand_a_kernel(const uint8_t* __restrict__ sk, size_t sk_stride,
+                                                               size_t nkeys, uint32_t* __restrict__ A) {
+  extern __shared__ __align__(16) uint32_t rows[];
+  const size_t s0 = (size_t)blockIdx.x * blockDim.x, total = nkeys * K * L;
+  const size_t s = s0 + threadIdx.x;
+  const size_t sc = s < total ? s : total - 1;
+  const size_t key = sc % nkeys;
+  const int ij = (int)(sc / nkeys), i = ij / L, j = ij % L;
+  const uint8_t* rho = sk + key * sk_stride;
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int w = 0; w < 4; w++) a[w] = keccak::ld64(rho + 8 * w);
+  a[4] = (uint64_t)j | ((uint64_t)i << 8) | (0x1full << 16);  // nonce = (i<<8)+j, little endian
+  a[20] = 0x8000000000000000ull;                               // SHAKE128 rate 168
+  uint32_t* row = rows + threadIdx.x * kExpRow;
+  int ctr = 0;
+  do {
+    keccak::f1600(a);
+#pragma unroll
+    for (int g = 0; g < 7; g++) {  // 3 words -> 8 candidates of 3 bytes
+      const uint64_t w0 = a[3 * g], w1 = a[3 * g + 1], w2 = a[3 * g + 2];
+      uint32_t t[8];
+      t[0] = (uint32_t)w0;
+      t[1] = (uint32_t)(w0 >> 24);
+      t[2] = (uint32_t)(w0 >> 48) | ((uint32_t)w1 << 16);
+      t[3] = (uint32_t)(w1 >> 8);
+      t[4] = (uint32_t)(w1 >> 32);
+      t[5] = (uint32_t)(w1 >> 56) | ((uint32_t)w2 << 8);
+      t[6] = (uint32_t)(w2 >> 16);
+      t[7] = (uint32_t)(w2 >> 40);
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const uint32_t d = t[q] & 0x7fffff;
+        row[ctr] = d;
+        ctr += (d < Q && ctr < N);
+      }
+    }
+  } while (ctr < N);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = warp; p < kExpThreads; p += kExpThreads / 32) {
+    const size_t sp = s0 + p;
+    if (sp >= total) break;
+    uint32_t* dst = A + ((sp % nkeys) * (K * L) + sp / nkeys) * N;
+#pragma unroll
+    for (int w = 0; w < 8; w++) dst[32 * w + lane] = rows[p * kExpRow + 32 * w + lane];
+  }
+}
+
+// s1h, s2h, t0h = NTT(unpack(...)) (dilithium.go:150-162): one octet per (key, polynomial)
+__global__ void __launch_bounds__(128) expand_s_kernel(const uint8_t* __restrict__ sk, size_t sk_stride, size_t nkeys,
+                                                       uint32_t* __restrict__ sh, const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
+  uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
+  const size_t total = nkeys * NKEYPOLY;
+  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
+  if (base >= total) return;
+  const size_t u_raw = base + oct;
+  const bool active = u_raw < total;
+  const size_t u = active ? u_raw : total - 1;
+  const size_t key = u / NKEYPOLY;
+  const int p = (int)(u % NKEYPOLY);
+  const uint8_t* skp = sk + key * sk_stride;
+  uint32_t r[32];
+  if (p < L + K) {  // PolyUnpackLeqEta (internal/pack.go:49-57), eta = 4: nibbles
+    const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(skp + OFF_S1 + 128 * p + 16 * v));
+    const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+    for (int i = 0; i < 32; i++) r[i] = Q + ETA - ((w[i >> 3] >> (4 * (i & 7))) & 15);
+  } else {  // UnpackT0 (pack.go:56-86): 13-bit fields, Q + 2^12 - x
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(skp + OFF_T0 + 416 * (p - L - K) + 52 * v);
+    uint32_t w[14];
+#pragma unroll
+    for (int i = 0; i < 13; i++) w[i] = __ldg(src + i);
+    w[13] = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) {
+      const int bit = 13 * i, wi = bit >> 5, sh = bit & 31;
+      uint32_t f = w[wi] >> sh;
+      if (sh > 19) f |= w[wi + 1] << (32 - sh);
+      r[i] = Q + (1u << 12) - (f & 0x1fff);
+    }
+  }
+  c_to_s(r, tile, v);
+  LaneTw t;
+  load_lane_tw_fwd(t, zetas, v);
+  ntt_octet(r, tile, v, t);
+  if (active) gstore_C(sh + (key * NKEYPOLY + p) * N, v, r);
+}
+
+// ------------------------------------------------------------------ mu, rho'
+struct ByteSponge {  // SHAKE256 absorber for unaligned byte streams (thread-local block buffer)
+  uint64_t a[25];
+  uint64_t blk[17];
+  int pos;
+  __device__ __forceinline__ void init() {
+    keccak::zero(a);
+#pragma unroll
+    for (int i = 0; i < 17; i++) blk[i] = 0;
+    pos = 0;
+  }
+  __device__ __forceinline__ void flush() {
+#pragma unroll
+    for (int i = 0; i < 17; i++) {
+      a[i] ^= blk[i];
+      blk[i] = 0;
+    }
+    keccak::f1600(a);
+    pos = 0;
+  }
+  __device__ __forceinline__ void put(uint8_t b) {
+    blk[pos >> 3] |= (uint64_t)b << (8 * (pos & 7));
+    if (++pos == 136) flush();
+  }
+  __device__ __forceinline__ void finish() {  // SHAKE pad: 0x1f ... 0x80
+    blk[pos >> 3] ^= 0x1full << (8 * (pos & 7));
+    blk[16] ^= 0x8000000000000000ull;
+    flush();
+  }
+};
+
+__global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk, size_t sk_stride,
+                                                 const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off,
+                                                 const uint8_t* __restrict__ ctx, int ctxlen, int internal,
+                                                 const uint8_t* __restrict__ rnd, size_t n, uint64_t* __restrict__ mu,
+                                                 uint64_t* __restrict__ rhop, uint32_t* __restrict__ attempt,
+                                                 uint32_t* __restrict__ act) {
+  const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= n) return;
+  const uint8_t* skp = sk + op * sk_stride;
+  ByteSponge sp;
+  sp.init();
+  for (int i = 0; i < 64; i++) sp.put(skp[OFF_TR + i]);  // mu = H(tr || M')  (dilithium.go:354-357)
+  if (!internal) {                                         // mldsa65/dilithium.go:71-79
+    sp.put(0);
+    sp.put((uint8_t)ctxlen);
+    for (int i = 0; i < ctxlen; i++) sp.put(ctx[i]);
+  }
+  const uint64_t lo = msg_off[op], hi = msg_off[op + 1];
+  for (uint64_t i = lo; i < hi; i++) sp.put(msgs[i]);
+  sp.finish();
+  uint64_t m[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) {
+    m[i] = sp.a[i];
+    mu[8 * op + i] = m[i];
+  }
+  // rho' = H(key || rnd || mu)  (dilithium.go:360-366): 128 bytes, one block
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    a[i] = keccak::ld64(skp + OFF_KEY + 8 * i);
+    a[4 + i] = rnd ? keccak::ld64(rnd + 32 * op + 8 * i) : 0;
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) a[8 + i] = m[i];
+  a[16] = 0x800000000000001full;
+  keccak::f1600(a);
+#pragma unroll
+  for (int i = 0; i < 8; i++) rhop[8 * op + i] = a[i];
+  attempt[op] = 0;
+  act[op] = (uint32_t)op;
+}
+
+// ------------------------------------------------------------------ per-round kernels
+// y[i] = ExpandMask(rho', L*attempt + i)  (sample.go:187-209, pack.go:177-195)
+__global__ void __launch_bounds__(128) mask_kernel(const uint32_t* __restrict__ act, size_t nact,
+                                                   const uint64_t* __restrict__ rhop,
+                                                   const uint32_t* __restrict__ attempt, uint32_t* __restrict__ y) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nact * L) return;
+  const size_t op = act[s % nact];
+  const int i = (int)(s / nact);
+  const uint32_t nonce = L * attempt[op] + i;
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int w = 0; w < 8; w++) a[w] = rhop[8 * op + w];
+  a[8] = (uint64_t)(nonce & 0xffff) | (0x1full << 16);
+  a[16] = 0x8000000000000000ull;
+  uint64_t buf[86];
+#pragma unroll
+  for (int b = 0; b < 5; b++) {
+    keccak::f1600(a);
+#pragma unroll
+    for (int w = 0; w < 17; w++) buf[17 * b + w] = a[w];
+  }
+  buf[85] = 0;
+  uint4* out = reinterpret_cast<uint4*>(y + (op * L + i) * N);
+#pragma unroll 2
+  for (int p = 0; p < 64; p++) {  // 10 bytes -> 4 coefficients
+    uint32_t cf[4];
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+      const int byte = 10 * p + 5 * h, wi = byte >> 3, sh = (byte & 7) * 8;
+      uint64_t v40 = buf[wi] >> sh;
+      if (sh > 24) v40 |= buf[wi + 1] << (64 - sh);
+      uint32_t p0 = GAMMA1 - (uint32_t)(v40 & 0xfffff), p1 = GAMMA1 - (uint32_t)((v40 >> 20) & 0xfffff);
+      p0 += (uint32_t)((int32_t)p0 >> 31) & Q;
+      p1 += (uint32_t)((int32_t)p1 >> 31) & Q;
+      cf[2 * h] = p0;
+      cf[2 * h + 1] = p1;
+    }
+    out[p] = make_uint4(cf[0], cf[1], cf[2], cf[3]);
+  }
+}
+
+struct OctetCtx {
+  int lane, warp, oct, v;
+  uint32_t* tile;
+};
+__device__ __forceinline__ OctetCtx octet_ctx(uint32_t* tiles) {
+  OctetCtx o;
+  o.lane = threadIdx.x & 31;
+  o.warp = threadIdx.x >> 5;
+  o.oct = o.lane >> 3;
+  o.v = o.lane & 7;
+  o.tile = tiles + (o.warp * 4 + o.oct) * kPolyWords;
+  return o;
+}
+
+// yh = NTT(y): octet per (active op, j)
+__global__ void __launch_bounds__(128) yntt_kernel(const uint32_t* __restrict__ act, size_t nact,
+                                                   const uint32_t* __restrict__ y, uint32_t* __restrict__ yh,
+                                                   const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const OctetCtx o = octet_ctx(tiles);
+  const size_t total = nact * L, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= total) return;
+  const bool active = base + o.oct < total;
+  const size_t u = active ? base + o.oct : total - 1;
+  const size_t op = act[u % nact];
+  const int j = (int)(u / nact);
+  uint32_t r[32];
+  gload_S(y + (op * L + j) * N, o.v, r);
+  LaneTw t;
+  load_lane_tw_fwd(t, zetas, o.v);
+  ntt_octet(r, o.tile, o.v, t);
+  if (active) gstore_C(yh + (op * L + j) * N, o.v, r);
+}
+
+// decompose (rounding.go:13-43, alpha = 523776)
+__device__ __forceinline__ void decompose(uint32_t a, uint32_t& a0plusq, uint32_t& a1) {
+  a1 = (a + 127) >> 7;
+  a1 = (a1 * 1025 + (1u << 21)) >> 22;
+  a1 &= 15;
+  a0plusq = a - a1 * ALPHA;
+  a0plusq += (uint32_t)((int32_t)(a0plusq - (Q - 1) / 2) >> 31) & Q;
+}
+
+// w[i] = InvNTT(ReduceLe2Q(A[i] . yh)), NormalizeAssumingLe2Q, Decompose (dilithium.go:386-394): octet per (op, i)
+__global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
+                                                const uint32_t* __restrict__ A, const uint32_t* __restrict__ yh,
+                                                uint32_t* __restrict__ w0, uint8_t* __restrict__ w1p,
+                                                const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const OctetCtx o = octet_ctx(tiles);
+  const size_t total = nact * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= total) return;
+  const bool active = base + o.oct < total;
+  const size_t u = active ? base + o.oct : total - 1;
+  const size_t op = act[u % nact];
+  const int i = (int)(u / nact);
+  const uint32_t* Ai = A + ((key_shared ? 0 : op) * (K * L) + i * L) * N;
+  uint32_t acc[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) acc[c] = 0;
+#pragma unroll 1
+  for (int j = 0; j < L; j++) {
+    const uint4* ap = reinterpret_cast<const uint4*>(Ai + j * N + 32 * o.v);
+    const uint4* yp = reinterpret_cast<const uint4*>(yh + (op * L + j) * N + 32 * o.v);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const uint4 x = __ldg(ap + c), z = yp[c];
+      acc[4 * c] += mont_mul(x.x, z.x);
+      acc[4 * c + 1] += mont_mul(x.y, z.y);
+      acc[4 * c + 2] += mont_mul(x.z, z.z);
+      acc[4 * c + 3] += mont_mul(x.w, z.w);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c++) acc[c] = reduce_le2q(acc[c]);
+  LaneTw t;
+  load_lane_tw_inv(t, zetas + 256, o.v);
+  invntt_octet(acc, o.tile, o.v, t);  // -> S layout: acc[2s+b] = coefficient 16s + 2v + b
+  uint32_t* w0p = w0 + (op * K + i) * N;
+  uint8_t* w1b = w1p + op * (K * POLY_W1) + i * POLY_W1;
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    uint32_t lo0, hi0, lo1, hi1;
+    decompose(le2q_modq(acc[2 * s]), lo0, hi0);
+    decompose(le2q_modq(acc[2 * s + 1]), lo1, hi1);
+    if (active) {
+      *reinterpret_cast<uint2*>(w0p + 16 * s + 2 * o.v) = make_uint2(lo0, lo1);
+      w1b[8 * s + o.v] = (uint8_t)(hi0 | (hi1 << 4));  // PackLe16 (pack.go:102-108)
+    }
+  }
+}
+
+// c~ = H(mu || w1) (dilithium.go:397-401), c = SampleInBall(c~) (sample.go:299-339): thread per op
+__global__ void __launch_bounds__(128) challenge_kernel(const uint32_t* __restrict__ act, size_t nact,
+                                                        const uint64_t* __restrict__ mu, const uint8_t* __restrict__ w1p,
+                                                        uint64_t* __restrict__ ctilde, uint32_t* __restrict__ cpoly,
+                                                        uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags,
+                                                        uint32_t* __restrict__ hintcnt) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nact) return;
+  const size_t op = act[s];
+  uint64_t a[25];
+  keccak::zero(a);
+  // stream = mu (8 words) || w1 packed (96 words) = 104 words = 6 full blocks + 2 words
+  const uint64_t* w1w = reinterpret_cast<const uint64_t*>(w1p + op * (K * POLY_W1));
+#pragma unroll 1
+  for (int b = 0; b < 6; b++) {
+#pragma unroll
+    for (int w = 0; w < 17; w++) {
+      const int k = 17 * b + w;
+      a[w] ^= (k < 8) ? mu[8 * op + k] : w1w[k - 8];
+    }
+    keccak::f1600(a);
+  }
+  a[0] ^= w1w[102 - 8];
+  a[1] ^= w1w[103 - 8];
+  a[2] ^= 0x1f;
+  a[16] ^= 0x8000000000000000ull;
+  keccak::f1600(a);
+  uint64_t ct[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    ct[i] = a[i];
+    ctilde[6 * op + i] = ct[i];
+  }
+  // SampleInBall
+  keccak::zero(a);
+#pragma unroll
+  for (int i = 0; i < 6; i++) a[i] = ct[i];
+  a[6] = 0x1f;
+  a[16] = 0x8000000000000000ull;
+  keccak::f1600(a);
+  uint64_t buf[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) buf[i] = a[i];
+  uint64_t signs = buf[0];
+  int off = 8;
+  uint32_t* c = cpoly + op * N;
+  for (int i = 0; i < N; i += 4) *reinterpret_cast<uint4*>(c + i) = make_uint4(0, 0, 0, 0);
+  for (int i = N - TAU; i < N; i++) {
+    uint32_t b;
+    for (;;) {
+      if (off >= 136) {
+        keccak::f1600(a);
+#pragma unroll
+        for (int q = 0; q < 17; q++) buf[q] = a[q];
+        off = 0;
+      }
+      b = (uint32_t)(buf[off >> 3] >> (8 * (off & 7))) & 0xff;
+      off++;
+      if (b <= (uint32_t)i) break;
+    }
+    c[i] = c[b];
+    c[b] = (signs & 1) ? Q - 1 : 1;
+    signs >>= 1;
+  }
+  for (int i = 0; i < 48; i++) hintbits[48 * op + i] = 0;
+  flags[op] = 0;
+  hintcnt[op] = 0;
+}
+
+// c-hat = NTT(c): octet per active op
+__global__ void __launch_bounds__(128) cntt_kernel(const uint32_t* __restrict__ act, size_t nact,
+                                                   uint32_t* __restrict__ cpoly, const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const OctetCtx o = octet_ctx(tiles);
+  const size_t base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= nact) return;
+  const bool active = base + o.oct < nact;
+  const size_t op = act[active ? base + o.oct : nact - 1];
+  uint32_t r[32];
+  gload_S(cpoly + op * N, o.v, r);
+  LaneTw t;
+  load_lane_tw_fwd(t, zetas, o.v);
+  ntt_octet(r, o.tile, o.v, t);
+  __syncwarp();
+  if (active) gstore_C(cpoly + op * N, o.v, r);
+}
+
+// InvNTT(c-hat . x-hat) on an octet: returns S layout
+__device__ __forceinline__ void c_times(uint32_t (&r)[32], const uint32_t* __restrict__ chat,
+                                        const uint32_t* __restrict__ xhat, const OctetCtx& o, const LaneTw& ti) {
+  const uint4* cp = reinterpret_cast<const uint4*>(chat + 32 * o.v);
+  const uint4* xp = reinterpret_cast<const uint4*>(xhat + 32 * o.v);
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const uint4 x = cp[c], z = __ldg(xp + c);
+    r[4 * c] = mont_mul(x.x, z.x);
+    r[4 * c + 1] = mont_mul(x.y, z.y);
+    r[4 * c + 2] = mont_mul(x.z, z.z);
+    r[4 * c + 3] = mont_mul(x.w, z.w);
+  }
+  invntt_octet(r, o.tile, o.v, ti);
+}
+
+// makeHint (rounding.go:56-67)
+__device__ __forceinline__ uint32_t make_hint(uint32_t z0, uint32_t r1) {
+  return (z0 <= GAMMA2 || z0 > Q - GAMMA2 || (z0 == Q - GAMMA2 && r1 == 0)) ? 0u : 1u;
+}
+
+// The three norm checks + hint (dilithium.go:407-464): octet per (op, item), item < K: row i of the K-vectors
+// (w0 - c s2, c t0, hint), item >= K: polynomial j of z = y + c s1 (packed straight into the signature).
+__global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
+                                                       const uint32_t* __restrict__ sh, const uint32_t* __restrict__ cpoly,
+                                                       const uint32_t* __restrict__ y, const uint32_t* __restrict__ w0,
+                                                       const uint8_t* __restrict__ w1p, uint8_t* __restrict__ sig,
+                                                       uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags,
+                                                       uint32_t* __restrict__ hintcnt, const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const OctetCtx o = octet_ctx(tiles);
+  const unsigned octmask = 0xffu << (8 * o.oct);
+  const size_t total = nact * (K + L), base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= total) return;
+  const bool active = base + o.oct < total;
+  const size_t u = active ? base + o.oct : total - 1;
+  const size_t op = act[u % nact];
+  const int item = (int)(u / nact);
+  const uint32_t* keyp = sh + (key_shared ? 0 : op) * (NKEYPOLY * N);
+  const uint32_t* chat = cpoly + op * N;
+  LaneTw ti;
+  load_lane_tw_inv(ti, zetas + 256, o.v);
+  uint32_t r[32];
+  bool reject = false;
+  if (item < K) {
+    const int i = item;
+    c_times(r, chat, keyp + (L + i) * N, o, ti);  // c s2[i]
+    const uint32_t* w0p = w0 + (op * K + i) * N;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const uint2 a = *reinterpret_cast<const uint2*>(w0p + 16 * s + 2 * o.v);
+      r[2 * s] = modq(a.x + (2 * Q - r[2 * s]));          // w0 - c s2, Normalize
+      r[2 * s + 1] = modq(a.y + (2 * Q - r[2 * s + 1]));
+      reject |= exceeds1(r[2 * s], GAMMA2 - BETA) | exceeds1(r[2 * s + 1], GAMMA2 - BETA);
+    }
+    uint32_t u0[32];
+    c_times(u0, chat, keyp + (L + K + i) * N, o, ti);  // c t0[i]
+    const uint8_t* w1b = w1p + op * (K * POLY_W1) + i * POLY_W1;
+    uint32_t pop = 0;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const uint32_t t0 = le2q_modq(u0[2 * s]), t1 = le2q_modq(u0[2 * s + 1]);
+      reject |= exceeds1(t0, GAMMA2) | exceeds1(t1, GAMMA2);
+      const uint32_t h1byte = w1b[8 * s + o.v];
+      const uint32_t h0 = make_hint(le2q_modq(r[2 * s] + t0), h1byte & 15);
+      const uint32_t h1 = make_hint(le2q_modq(r[2 * s + 1] + t1), h1byte >> 4);
+      const uint32_t bits = h0 | (h1 << 1);
+      pop += h0 + h1;
+      if (bits && active) atomicOr(hintbits + 48 * op + 8 * i + (s >> 1), bits << (16 * (s & 1) + 2 * o.v));
+    }
+    if (pop && active) atomicAdd(hintcnt + op, pop);
+  } else {
+    const int j = item - K;
+    c_times(r, chat, keyp + j * N, o, ti);  // c s1[j]
+    const uint32_t* yp = y + (op * L + j) * N;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      const uint2 a = *reinterpret_cast<const uint2*>(yp + 16 * s + 2 * o.v);
+      r[2 * s] = modq(r[2 * s] + a.x);
+      r[2 * s + 1] = modq(r[2 * s + 1] + a.y);
+      reject |= exceeds1(r[2 * s], GAMMA1 - BETA) | exceeds1(r[2 * s + 1], GAMMA1 - BETA);
+    }
+    // PolyPackLeGamma1 (internal/pack.go:236-252): 32 coefficients -> 20 words, written speculatively
+    s_to_c(r, o.tile, o.v);
+    // signatures are 3309 bytes apart, hence byte stores
+    uint8_t* zb = sig + op * (size_t)SIG_BYTES + CTILDE + POLY_Z * j + 80 * o.v;
+    uint64_t accb = 0;
+    int bits = 0, ob = 0;
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      uint32_t p = GAMMA1 - r[c];
+      p += (uint32_t)((int32_t)p >> 31) & Q;
+      accb |= (uint64_t)(p & 0xfffff) << bits;
+      bits += 20;
+      while (bits >= 8) {
+        if (active) zb[ob] = (uint8_t)accb;
+        ob++;
+        accb >>= 8;
+        bits -= 8;
+      }
+    }
+  }
+  reject = __any_sync(octmask, reject);
+  if (reject && active && o.v == 0) atomicOr(flags + op, 1u);
+}
+
+// accept -> c~ and hints into the signature; reject -> next attempt (dilithium.go:369-377,459-469)
+__global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restrict__ act, size_t nact,
+                                                       const uint64_t* __restrict__ ctilde,
+                                                       const uint32_t* __restrict__ hintbits,
+                                                       const uint32_t* __restrict__ flags,
+                                                       const uint32_t* __restrict__ hintcnt, uint32_t* __restrict__ attempt,
+                                                       uint8_t* __restrict__ sig, uint8_t* __restrict__ status,
+                                                       uint32_t* __restrict__ next, uint32_t* __restrict__ next_count) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= nact) return;
+  const size_t op = act[s];
+  uint8_t* sg = sig + op * (size_t)SIG_BYTES;
+  if (flags[op] == 0 && hintcnt[op] <= OMEGA) {
+    for (int i = 0; i < 6; i++) {
+      const uint64_t w = ctilde[6 * op + i];
+      for (int b = 0; b < 8; b++) sg[8 * i + b] = (uint8_t)(w >> (8 * b));
+    }
+    uint8_t* hb = sg + CTILDE + L * POLY_Z;  // PackHint (internal/pack.go:77-95)
+    int off = 0;
+    for (int i = 0; i < K; i++) {
+      for (int w = 0; w < 8; w++) {
+        uint32_t m = hintbits[48 * op + 8 * i + w];
+        while (m) {
+          const int bit = __ffs(m) - 1;
+          hb[off++] = (uint8_t)(32 * w + bit);
+          m &= m - 1;
+        }
+      }
+      hb[OMEGA + i] = (uint8_t)off;
+    }
+    for (; off < OMEGA; off++) hb[off] = 0;
+    if (status) status[op] = 0;
+  } else {
+    const uint32_t at = attempt[op] + 1;
+    attempt[op] = at;
+    if (at + 1 >= MAX_ATTEMPTS) {  // "attempt >= 576" (dilithium.go:372-377): give up, flag the op
+      if (status) status[op] = 1;
+      for (int i = 0; i < SIG_BYTES; i++) sg[i] = 0;
+    } else {
+      next[atomicAdd(next_count, 1u)] = (uint32_t)op;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ host side
+static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off,
+                       const uint8_t* ctxstr, int ctxlen, const uint8_t* rnd, uint8_t* sig, uint8_t* status, size_t n,
+                       int internal, cudaStream_t st, int slot, uint64_t* attempts_out) {
+  Ctx& c = ctx();
+  const bool shared = sk_stride == 0;
+  const size_t nkeys = shared ? 1 : n;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t oA = take(nkeys * K * L * 1024), oS = take(nkeys * NKEYPOLY * 1024), oMu = take(n * 64),
+               oRh = take(n * 64), oY = take(n * L * 1024), oYh = take(n * L * 1024), oW0 = take(n * K * 1024),
+               oW1 = take(n * K * POLY_W1), oC = take(n * 1024), oCt = take(n * 48), oHb = take(n * 48 * 4),
+               oFl = take(n * 4), oHc = take(n * 4), oAt = take(n * 4), oA0 = take(n * 4), oA1 = take(n * 4),
+               oCnt = take(16);
+  void* base = nullptr;
+  int rc = ensure_work(slot, off, &base);
+  if (rc) return rc;
+  char* b = (char*)base;
+  Work w;
+  w.A = (uint32_t*)(b + oA);
+  w.sh = (uint32_t*)(b + oS);
+  w.mu = (uint64_t*)(b + oMu);
+  w.rhop = (uint64_t*)(b + oRh);
+  w.y = (uint32_t*)(b + oY);
+  w.yh = (uint32_t*)(b + oYh);
+  w.w0 = (uint32_t*)(b + oW0);
+  w.w1p = (uint8_t*)(b + oW1);
+  w.c = (uint32_t*)(b + oC);
+  w.ctilde = (uint64_t*)(b + oCt);
+  w.hintbits = (uint32_t*)(b + oHb);
+  w.flags = (uint32_t*)(b + oFl);
+  w.hintcnt = (uint32_t*)(b + oHc);
+  w.attempt = (uint32_t*)(b + oAt);
+  w.act[0] = (uint32_t*)(b + oA0);
+  w.act[1] = (uint32_t*)(b + oA1);
+  w.count = (uint32_t*)(b + oCnt);
+  const uint32_t* zetas = (const uint32_t*)c.dil_tw;
+
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    attr_set = true;
+  }
+  auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
+  {
+    KernelScope ks(KID_MLDSA_EXPAND, st);
+    expand_a_kernel<<<blocks(nkeys * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(sk, sk_stride,
+                                                                                                        nkeys, w.A);
+  }
+  {
+    KernelScope ks(KID_MLDSA_EXPAND, st);
+    expand_s_kernel<<<blocks(nkeys * NKEYPOLY, 16), 128, 0, st>>>(sk, sk_stride, nkeys, w.sh, zetas);
+  }
+  {
+    KernelScope ks(KID_MLDSA_MU, st);
+    mu_kernel<<<blocks(n, 128), 128, 0, st>>>(sk, sk_stride, msgs, msg_off, ctxstr, ctxlen, internal, rnd, n, w.mu, w.rhop,
+                                              w.attempt, w.act[0]);
+  }
+  CB200_CUDA(cudaGetLastError());
+
+  void* pin = nullptr;
+  rc = ensure_pinned(n + 64, &pin);  // the caller may be using the first n bytes for status staging
+  if (rc) return rc;
+  volatile uint32_t* h_count = (volatile uint32_t*)((char*)pin + ((n + 15) & ~(size_t)15));
+  size_t nact = n;
+  int cur = 0;
+  uint64_t total_attempts = 0;
+  for (int round = 0; nact > 0; round++) {
+    if (round >= MAX_ATTEMPTS) break;
+    total_attempts += nact;
+    const uint32_t* act = w.act[cur];
+    CB200_CUDA(cudaMemsetAsync(w.count + (cur ^ 1), 0, 4, st));
+    {
+      KernelScope ks(KID_MLDSA_MASK, st);
+      mask_kernel<<<blocks(nact * L, 128), 128, 0, st>>>(act, nact, w.rhop, w.attempt, w.y);
+    }
+    {
+      KernelScope ks(KID_MLDSA_W, st);
+      yntt_kernel<<<blocks(nact * L, 16), 128, 0, st>>>(act, nact, w.y, w.yh, zetas);
+    }
+    {
+      KernelScope ks(KID_MLDSA_W, st);
+      w_kernel<<<blocks(nact * K, 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1p, zetas);
+    }
+    {
+      KernelScope ks(KID_MLDSA_CHALLENGE, st);
+      challenge_kernel<<<blocks(nact, 128), 128, 0, st>>>(act, nact, w.mu, w.w1p, w.ctilde, w.c, w.hintbits, w.flags,
+                                                          w.hintcnt);
+    }
+    {
+      KernelScope ks(KID_MLDSA_RESPONSE, st);
+      cntt_kernel<<<blocks(nact, 16), 128, 0, st>>>(act, nact, w.c, zetas);
+    }
+    {
+      KernelScope ks(KID_MLDSA_RESPONSE, st);
+      response_kernel<<<blocks(nact * (K + L), 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1p,
+                                                                  sig, w.hintbits, w.flags, w.hintcnt, zetas);
+    }
+    {
+      KernelScope ks(KID_MLDSA_COMPACT, st);
+      finalize_kernel<<<blocks(nact, 128), 128, 0, st>>>(act, nact, w.ctilde, w.hintbits, w.flags, w.hintcnt, w.attempt,
+                                                         sig, status, w.act[cur ^ 1], w.count + (cur ^ 1));
+    }
+    CB200_CUDA(cudaMemcpyAsync((void*)h_count, w.count + (cur ^ 1), 4, cudaMemcpyDeviceToHost, st));
+    CB200_CUDA(cudaStreamSynchronize(st));
+    nact = *h_count;
+    cur ^= 1;
+  }
+  CB200_CUDA(cudaGetLastError());
+  if (attempts_out) *attempts_out = total_attempts;
+  return 0;
+}
+
+}  // namespace mldsa
+}  // namespace cb200
+
+using namespace cb200;
+
+extern "C" {
+
+int cb200_mldsa65_sign(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off,
+                       const uint8_t* context, size_t ctxlen, const uint8_t* rnd, uint8_t* sig, uint8_t* status, size_t n,
+                       int flags, uint64_t* attempts) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (!sk || !msgs || !msg_off || !sig || ctxlen > 255 || (ctxlen && !context) || (sk_stride != 0 && sk_stride < 4032)) {
+    set_error("cb200_mldsa65_sign: bad argument");  // len(ctx) > 255 is sign.ErrContextTooLong in the Go shim
+    return CB200_ERR_ARG;
+  }
+  const int internal = flags & CB200_SIGN_INTERNAL;
+  const bool dev = is_device_ptr(sig);
+  if (dev != is_device_ptr(sk) || dev != is_device_ptr(msgs) || dev != is_device_ptr(msg_off) ||
+      (rnd && dev != is_device_ptr(rnd)) || (status && dev != is_device_ptr(status))) {
+    set_error("cb200_mldsa65_sign: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  if (dev) {
+    if (((uintptr_t)sk | sk_stride | (uintptr_t)msg_off) & 15) {
+      set_error("cb200_mldsa65_sign: device sk and sk_stride must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    const uint8_t* dctx = nullptr;
+    if (ctxlen) {  // the context string is at most 255 bytes and always a host pointer: stage it
+      CB200_CUDA(cudaMemcpyAsync(ctx().small, context, ctxlen, cudaMemcpyHostToDevice, ctx().cur));
+      dctx = (const uint8_t*)ctx().small;
+    }
+    return mldsa::sign_device(sk, sk_stride, msgs, msg_off, dctx, (int)ctxlen, rnd, sig, status, n, internal, ctx().cur, 3,
+                              attempts);
+  }
+  // host pointers: one staged pass (signing is compute-heavy: ~7.4 KB of traffic per ~1e6 instructions)
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  cudaStream_t st = c.pipe[0];
+  const size_t msg_bytes = (size_t)msg_off[n];
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t nk = sk_stride ? n : 1;
+  const size_t oSk = take(nk * 4032), oMsg = take(msg_bytes + 8), oOff = take((n + 1) * 8), oRnd = take(n * 32),
+               oSig = take(n * (size_t)3309), oSt = take(n), oCtx = take(256);
+  rc = ensure_scratch(0, off);
+  if (rc) return rc;
+  char* d = (char*)c.scratch[0];
+  if (sk_stride == 0 || sk_stride == 4032)
+    CB200_CUDA(cudaMemcpyAsync(d + oSk, sk, nk * 4032, cudaMemcpyHostToDevice, st));
+  else
+    CB200_CUDA(cudaMemcpy2DAsync(d + oSk, 4032, sk, sk_stride, 4032, n, cudaMemcpyHostToDevice, st));
+  if (msg_bytes) CB200_CUDA(cudaMemcpyAsync(d + oMsg, msgs, msg_bytes, cudaMemcpyHostToDevice, st));
+  CB200_CUDA(cudaMemcpyAsync(d + oOff, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  if (rnd) CB200_CUDA(cudaMemcpyAsync(d + oRnd, rnd, n * 32, cudaMemcpyHostToDevice, st));
+  if (ctxlen) CB200_CUDA(cudaMemcpyAsync(d + oCtx, context, ctxlen, cudaMemcpyHostToDevice, st));
+  rc = mldsa::sign_device((const uint8_t*)d + oSk, sk_stride ? 4032 : 0, (const uint8_t*)d + oMsg,
+                          (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : nullptr, (int)ctxlen,
+                          rnd ? (const uint8_t*)d + oRnd : nullptr, (uint8_t*)d + oSig, (uint8_t*)d + oSt, n, internal,
+                          st, 0, attempts);
+  if (rc) return rc;
+  void* pin = nullptr;
+  rc = ensure_pinned(n + 64, &pin);
+  if (rc) return rc;
+  CB200_CUDA(cudaMemcpyAsync(sig, d + oSig, n * (size_t)3309, cudaMemcpyDeviceToHost, st));
+  CB200_CUDA(cudaMemcpyAsync(pin, d + oSt, n, cudaMemcpyDeviceToHost, st));
+  CB200_CUDA(cudaStreamSynchronize(st));
+  size_t nbad = 0;
+  const uint8_t* hs = (const uint8_t*)pin;
+  for (size_t i = 0; i < n; i++) nbad += hs[i] != 0;
+  if (status) memcpy(status, hs, n);
+  if (nbad) {
+    set_error("cb200_mldsa65_sign: %zu of %zu signatures exhausted 576 attempts", nbad, n);
+    return CB200_ERR_SIGN_ATTEMPTS;
+  }
+  return 0;
+}
+
+size_t cb200_mldsa65_signature_size(void) { return 3309; }
+size_t cb200_mldsa65_private_key_size(void) { return 4032; }
+
+}  // extern "C"

@@ -100,8 +100,9 @@ __global__ void __launch_bounds__(128) g_kernel(const uint8_t* __restrict__ m, c
 
 // ------------------------------------------------------------------ 2. samplers
 // 12-bit rejection sampling of one 168-byte SHAKE128 block (sample.go:203-233).
-// Accepted coefficients are appended to dst[ctr...]; returns the new ctr (<= 256).
-__device__ __forceinline__ int reject_block(const uint64_t (&a)[25], int16_t* __restrict__ dst, int ctr) {
+// Accepted coefficients are appended to row[ctr...] (this thread's shared-memory row);
+// returns the new ctr (<= 256).
+__device__ __forceinline__ int reject_block(const uint64_t (&a)[25], int16_t* row, int ctr) {
 #pragma unroll
   for (int g = 0; g < 7; g++) {
     const uint64_t w0 = a[3 * g], w1 = a[3 * g + 1], w2 = a[3 * g + 2];
@@ -117,8 +118,11 @@ __device__ __forceinline__ int reject_block(const uint64_t (&a)[25], int16_t* __
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const uint32_t d1 = t[j] & 0xfff, d2 = t[j] >> 12;
-      if (d1 < (uint32_t)Q && ctr < N) dst[ctr++] = (int16_t)d1;
-      if (d2 < (uint32_t)Q && ctr < N) dst[ctr++] = (int16_t)d2;
+      // rows have 2 slack entries, so the store is unconditional and only the counter is predicated
+      row[ctr] = (int16_t)d1;
+      ctr += (d1 < (uint32_t)Q && ctr < N);
+      row[ctr] = (int16_t)d2;
+      ctr += (d2 < (uint32_t)Q && ctr < N);
     }
   }
   return ctr;
@@ -143,6 +147,9 @@ __device__ __forceinline__ void cbd2_store(const uint64_t (&a)[25], int16_t* __r
   }
 }
 
+constexpr int kRowWords = 129;  // 256 int16 + 2 slack, odd word stride
+constexpr int kSampleSmem = 128 * kRowWords * 4;
+
 // Stream index space (blockDim-aligned so that warps never mix stream kinds):
 //   [0, nkeys*K*K)               matrix streams, s = (i*K + j) * nkeys + key  -> A^T[key][i][j] = XOF(rho, i, j)
 //   then n*(2K+1) noise streams, s = nonce * n + op                            -> PRF(r_op, nonce)
@@ -155,21 +162,38 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
   uint64_t a[25];
   keccak::zero(a);
   if (blockIdx.x < mat_blocks) {
-    const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nkeys * K * K) return;
-    const size_t key = s % nkeys;
-    const int ij = (int)(s / nkeys), i = ij / K, j = ij % K;
+    // Each thread rejection-samples into its own shared-memory row (129-word stride: conflict-free
+    // while the counters of a warp agree); the CTA then streams the rows out as whole 512-byte polynomials.
+    extern __shared__ __align__(16) uint32_t rows[];
+    const size_t s0 = (size_t)blockIdx.x * blockDim.x;
+    const size_t s = s0 + threadIdx.x;
+    const size_t total = nkeys * K * K;
+    const bool live = s < total;
+    const size_t sc = live ? s : total - 1;
+    const size_t key = sc % nkeys;
+    const int ij = (int)(sc / nkeys), i = ij / K, j = ij % K;
     const uint8_t* rho = ek + key * ek_stride + 384 * K;
 #pragma unroll
     for (int w = 0; w < 4; w++) a[w] = keccak::ld64(rho + 8 * w);
     a[4] = (uint64_t)i | ((uint64_t)j << 8) | (0x1full << 16);  // aT.Derive(rho, transpose=true): x = i, y = j
     a[20] = 0x8000000000000000ull;                               // rate 168
-    int16_t* dst = A + (key * K * K + ij) * N;
+    int16_t* row = reinterpret_cast<int16_t*>(rows + threadIdx.x * kRowWords);
     int ctr = 0;
     do {
       keccak::f1600(a);
-      ctr = reject_block(a, dst, ctr);
+      ctr = reject_block(a, row, ctr);
     } while (ctr < N);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int p = warp; p < (int)blockDim.x; p += blockDim.x / 32) {
+      const size_t sp = s0 + p;
+      if (sp >= total) break;
+      const size_t pkey = sp % nkeys;
+      const int pij = (int)(sp / nkeys);
+      uint32_t* dst = reinterpret_cast<uint32_t*>(A + (pkey * K * K + pij) * N);
+#pragma unroll
+      for (int w = 0; w < 4; w++) dst[32 * w + lane] = rows[p * kRowWords + 32 * w + lane];
+    }
   } else {
     const size_t s = (size_t)(blockIdx.x - mat_blocks) * blockDim.x + threadIdx.x;
     if (s >= n * P::n_noise) return;
@@ -437,6 +461,11 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
   int16_t* A = (int16_t*)((char*)base + o_A);
   int16_t* noise = (int16_t*)((char*)base + o_n);
 
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
+    attr_set = true;
+  }
   {
     KernelScope ks(KID_MLKEM_HASH_EK, st);
     hash_ek_kernel<K><<<(unsigned)((nkeys + 127) / 128), 128, 0, st>>>(ek, ek_stride, nkeys, h);
@@ -452,7 +481,7 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
     const size_t noise_blocks = (cnt * P::n_noise + 127) / 128;
     {
       KernelScope ks(KID_MLKEM_SAMPLE, st);
-      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, 0, st>>>(
+      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, st>>>(
           ek + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise, mat_blocks);
     }
     {

@@ -10,6 +10,7 @@ int init_extra_tables() {
   if (c.dil_tw) cudaFree(c.dil_tw);
   CB200_CUDA(cudaMalloc(&c.dil_tw, sizeof tw));
   CB200_CUDA(cudaMemcpy(c.dil_tw, tw, sizeof tw, cudaMemcpyHostToDevice));
+  if (!c.small) CB200_CUDA(cudaMalloc(&c.small, 256));
   return 0;
 }
 }  // namespace cb200

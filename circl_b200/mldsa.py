@@ -1,0 +1,128 @@
+"""sign.Scheme mirror for ML-DSA-65 over the C ABI.
+
+Mirrors sign/sign.go:48-119 (sign.Scheme, SignatureOpts, errors) and
+sign/mldsa/mldsa65/dilithium.go:256-366 for the path this repository accelerates
+(private-key expansion + Sign) and adds ``SignBatch``.  Wrong key types raise
+like the reference panics; an over-long context raises ErrContextTooLong.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._ffi import Cb200Error, check, lib
+
+SIGN_INTERNAL = 1
+
+
+class SignError(Exception):
+    pass
+
+
+class ErrContextTooLong(SignError):   # sign.ErrContextTooLong
+    pass
+
+
+class ErrPrivKeySize(SignError):
+    pass
+
+
+class SignatureOpts:
+    """sign.SignatureOpts (sign/sign.go:14-18)."""
+
+    def __init__(self, Context: bytes = b""):
+        self.Context = Context
+
+
+class PrivateKey:
+    def __init__(self, scheme, packed: bytes):
+        self._scheme, self._packed = scheme, bytes(packed)
+
+    def Scheme(self):
+        return self._scheme
+
+    def MarshalBinary(self) -> bytes:
+        return self._packed
+
+    def Equal(self, other) -> bool:
+        return isinstance(other, PrivateKey) and other._packed == self._packed
+
+
+class Scheme:
+    def Name(self) -> str:
+        return "ML-DSA-65"
+
+    def PublicKeySize(self) -> int:
+        return 1952
+
+    def PrivateKeySize(self) -> int:
+        return 4032
+
+    def SignatureSize(self) -> int:
+        return 3309
+
+    def SeedSize(self) -> int:
+        return 32
+
+    def SupportsContext(self) -> bool:
+        return True
+
+    def UnmarshalBinaryPrivateKey(self, buf: bytes) -> PrivateKey:
+        if len(buf) != self.PrivateKeySize():
+            raise ErrPrivKeySize("sign: invalid private key size")  # dilithium.go:346-349
+        return PrivateKey(self, buf)
+
+    def Sign(self, sk: PrivateKey, message: bytes, opts: SignatureOpts | None = None) -> bytes:
+        """sign.Scheme.Sign (dilithium.go:282-303): deterministic, batch of one."""
+        if not isinstance(sk, PrivateKey):
+            raise TypeError("sign: wrong private key type")  # the reference panics with sign.ErrTypeMismatch
+        ctx = opts.Context if opts is not None else b""
+        return self.SignBatch(sk, [message], ctx=ctx)[0].tobytes()
+
+    def SignBatch(self, sks, messages, ctx: bytes = b"", rnd=None, internal: bool = False, return_attempts=False):
+        """Batched Sign.  sks: one PrivateKey (shared, expanded once) or an (n, 4032) uint8 array
+        (expanded on the device per op).  messages: list of bytes.  rnd: None (deterministic) or
+        (n, 32) uint8.  internal=True selects ML-DSA.Sign_internal (no context framing; ACVP)."""
+        if len(ctx) > 255:
+            raise ErrContextTooLong("sign: context string too long")
+        n = len(messages)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in messages], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(messages) + b"\0" * 8, dtype=np.uint8)
+        if isinstance(sks, PrivateKey):
+            sk = np.frombuffer(sks._packed, dtype=np.uint8)
+            stride = 0
+        else:
+            sk = np.ascontiguousarray(sks, dtype=np.uint8)
+            if sk.shape != (n, 4032):
+                raise ErrPrivKeySize("sign: invalid private key size")
+            stride = 4032
+        sig = np.empty((n, 3309), dtype=np.uint8)
+        status = np.zeros((n,), dtype=np.uint8)
+        attempts = C.c_uint64(0)
+        r = None if rnd is None else np.ascontiguousarray(rnd, dtype=np.uint8)
+        cbuf = (C.c_uint8 * max(1, len(ctx))).from_buffer_copy(ctx or b"\0")
+        check(lib().cb200_mldsa65_sign(sk.ctypes.data, stride, blob.ctypes.data, off.ctypes.data,
+                                       C.cast(cbuf, C.c_void_p), len(ctx), None if r is None else r.ctypes.data,
+                                       sig.ctypes.data, status.ctypes.data, n, SIGN_INTERNAL if internal else 0,
+                                       C.cast(C.pointer(attempts), C.c_void_p)))
+        if return_attempts:
+            return sig, int(attempts.value)
+        return sig
+
+    def GenerateKey(self):
+        raise NotImplementedError("key generation is not on the accelerated path yet (SURVEY.md 8(f) row 2)")
+
+    DeriveKey = GenerateKey
+
+    def Verify(self, pk, message, signature, opts=None):
+        raise NotImplementedError("verification is not on the accelerated path yet (SURVEY.md 8(f) row 3)")
+
+
+_SCHEME = Scheme()
+
+
+def ByName(name: str):
+    """sign/schemes/schemes.go:69 -- case-insensitive lookup."""
+    return _SCHEME if name.lower() == "ml-dsa-65" else None

@@ -105,6 +105,26 @@ int cb200_mlkem_encaps(int k, const uint8_t *ek, size_t ek_stride, const uint8_t
 size_t cb200_mlkem_public_key_size(int k);
 size_t cb200_mlkem_ciphertext_size(int k);
 
+/* ---- ML-DSA-65 ---- */
+/* sign.Scheme.Sign / SignTo    sign/mldsa/mldsa65/dilithium.go:282-303,56-84  ->
+ * internal.SignTo (ML-DSA.Sign_internal)  sign/mldsa/mldsa65/internal/dilithium.go:340-470,
+ * including (*PrivateKey).Unpack (:142-163): A = ExpandA(rho), NTT(s1), NTT(s2), NTT(t0) are rebuilt on
+ * the device (once if sk_stride = 0, else per operation).
+ * sk: packed private key(s), 4032 bytes; op i uses sk + i*sk_stride (0 = one key for all).
+ * msgs: all messages back to back; message i = msgs[msg_off[i] .. msg_off[i+1]) (n+1 offsets).
+ * context/ctxlen: the FIPS 204 context string, shared by the batch (ctxlen <= 255; host pointer).
+ * rnd: n x 32 bytes of signing randomness, or NULL for deterministic signing (rnd = 0^32).
+ * sig: n x 3309 bytes.  status (optional): n bytes, 1 = the 576-attempt cap was hit (the reference
+ * panics there); attempts (optional, host pointer): total rejection-loop iterations of the batch.
+ * flags: CB200_SIGN_INTERNAL = ML-DSA.Sign_internal on the message as given (no 0x00||len||ctx framing,
+ * the ACVP interface, sign/mldsa/mldsa65/dilithium.go:87-98). */
+#define CB200_SIGN_INTERNAL 1
+int cb200_mldsa65_sign(const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *msg_off,
+                       const uint8_t *context, size_t ctxlen, const uint8_t *rnd, uint8_t *sig, uint8_t *status,
+                       size_t n, int flags, uint64_t *attempts);
+size_t cb200_mldsa65_signature_size(void);
+size_t cb200_mldsa65_private_key_size(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,86 @@
+"""GPU parity: batched ML-DSA-65 Sign vs the NIST ACVP vectors and the oracle (byte-exact).
+Reads like sign/mldsa/mldsa65/acvp_test.go:81-123 and sign/schemes/schemes_test.go."""
+import hashlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def cb():
+    import circl_b200
+    circl_b200.init(0)
+    yield circl_b200
+    circl_b200.shutdown()
+
+
+def _h(tag, i, n):
+    return hashlib.shake_256(bytes([tag]) + i.to_bytes(8, "little")).digest(n)
+
+
+def test_acvp_siggen_internal_interface(cb, mldsa65_acvp):
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName("ML-DSA-65")
+    tests = mldsa65_acvp["siggen"]
+    sks = np.stack([np.frombuffer(bytes.fromhex(t["sk"]), dtype=np.uint8) for t in tests])
+    msgs = [bytes.fromhex(t["message"]) for t in tests]       # 246 .. 6877 bytes: multi-block absorb
+    rnd = np.stack([np.frombuffer(bytes.fromhex(t["rnd"]), dtype=np.uint8) for t in tests])
+    sig = scheme.SignBatch(sks, msgs, rnd=rnd, internal=True)
+    for i, t in enumerate(tests):
+        assert sig[i].tobytes().hex().upper() == t["signature"].upper(), t["tcId"]
+
+
+@pytest.mark.parametrize("n", [1, 5, 300])
+def test_batch_vs_oracle_per_op_keys(cb, n):
+    import oracle
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName("ML-DSA-65")
+    pool = [oracle.mldsa65_keygen(_h(2, j, 32)) for j in range(min(n, 8))]
+    sks = np.stack([np.frombuffer(pool[i % len(pool)][1], dtype=np.uint8) for i in range(n)])
+    msgs = [_h(3, i, 32 + (i % 7) * 50) for i in range(n)]
+    sig, attempts = scheme.SignBatch(sks, msgs, return_attempts=True)
+    want, want_attempts = oracle.mldsa65_sign_batch(sks, msgs, nthreads=8)
+    assert np.array_equal(sig, want)
+    assert attempts == want_attempts          # same rejection-loop trajectory, attempt for attempt
+    for i in range(0, n, max(1, n // 10)):
+        assert oracle.mldsa65_verify(pool[i % len(pool)][0], msgs[i], sig[i].tobytes())
+
+
+def test_shared_key_context_and_hedged(cb):
+    import oracle
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName("ML-DSA-65")
+    pk, sk = oracle.mldsa65_keygen(_h(2, 99, 32))
+    key = scheme.UnmarshalBinaryPrivateKey(sk)
+    n = 200
+    msgs = [_h(4, i, i % 90) for i in range(n)]               # includes the empty message
+    ctx = b"circl-b200 test context"
+    rnd = np.frombuffer(hashlib.shake_256(b"rnd").digest(32 * n), dtype=np.uint8).reshape(n, 32)
+    sig = scheme.SignBatch(key, msgs, ctx=ctx, rnd=rnd)
+    for i in range(0, n, 7):
+        want, _ = oracle.mldsa65_sign(sk, msgs[i], ctx=ctx, rnd=rnd[i].tobytes())
+        assert sig[i].tobytes() == want
+        assert oracle.mldsa65_verify(pk, msgs[i], sig[i].tobytes(), ctx=ctx)
+    # single-op sign.Scheme.Sign with SignatureOpts
+    one = scheme.Sign(key, b"hello", mldsa.SignatureOpts(Context=b"ctx"))
+    assert one == oracle.mldsa65_sign(sk, b"hello", ctx=b"ctx")[0]
+    with pytest.raises(mldsa.ErrContextTooLong):
+        scheme.SignBatch(key, [b"x"], ctx=b"\0" * 256)
+    with pytest.raises(mldsa.ErrPrivKeySize):
+        scheme.UnmarshalBinaryPrivateKey(b"\0" * 100)
+
+
+def test_many_ops_property(cb):
+    """2^13 signatures, shared key: all verify (oracle) on a sample; attempts ~ 5.1 per signature."""
+    import oracle
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName("ML-DSA-65")
+    pk, sk = oracle.mldsa65_keygen(_h(2, 7, 32))
+    n = 1 << 13
+    msgs = [_h(5, i, 32) for i in range(n)]
+    sig, attempts = scheme.SignBatch(scheme.UnmarshalBinaryPrivateKey(sk), msgs, return_attempts=True)
+    assert 3.5 < attempts / n < 7.0
+    for i in range(0, n, 331):
+        assert sig[i].tobytes() == oracle.mldsa65_sign(sk, msgs[i])[0]

@@ -1,0 +1,60 @@
+"""CPU test of the N>1 host logic (world_size 2, gloo): index sharding + result gather to rank 0.
+The per-rank compute is stood in for by the oracle (this is a test of the plumbing, not of the kernels)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from circl_b200.shard import gather_rows, shard_range
+
+
+def test_shard_range_partitions_exactly():
+    for n in (0, 1, 7, 8, 1000, (1 << 20) + 3):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_range(n, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == n
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, n, q):
+    import oracle
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(123)           # every rank derives the same global inputs
+    polys = (rng.integers(0, 2 * 3329, size=(n, 256)).astype(np.int32) - 3329).astype(np.int16)
+    lo, hi = shard_range(n, rank, world)
+    local = torch.from_numpy(oracle.kyber_ntt(polys[lo:hi]))   # stand-in for the per-rank GPU shard
+    out, _ = gather_rows(local, n, dst=0)
+    dist.barrier()
+    if rank == 0:
+        q.put(bool(np.array_equal(out.numpy(), oracle.kyber_ntt(polys))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n", [10, 33])
+def test_two_rank_gather_matches_single_process(n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=5) is True

@@ -40,6 +40,8 @@ WORKLOADS = {
     "mlkem1024": dict(k=4, name="ML-KEM-1024", ek=1568, ct=1568, bytes_per_op=3200,
                       desc="ML-KEM-1024 full encaps, per-op ek, batch sharded by index"),
 }
+MLDSA = dict(name="ML-DSA-65", sk=4032, sig=3309, bytes_per_op=7373,
+             desc="ML-DSA-65 Sign 2^18 batch (q=8380417 NTT + rejection loop) on 1 B200, per-op sk, 32-byte messages")
 NTT_DESC = "2^20-batch Kyber 256-pt NTT on 1 B200, bit-exact vs common.nttGeneric"
 
 
@@ -48,10 +50,18 @@ def env_int(name, default):
 
 
 def host_threads() -> int:
+    """Hardware threads this process may use: CPU affinity, capped by the cgroup CPU quota if one is set."""
     try:
-        return len(os.sched_getaffinity(0))
+        n = len(os.sched_getaffinity(0))
     except AttributeError:
-        return os.cpu_count() or 1
+        n = os.cpu_count() or 1
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()
+        if quota != "max":
+            n = max(1, min(n, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
 
 
 def measured_peak():
@@ -75,6 +85,19 @@ def synth_keys(k: int, count: int, seed: int):
     packed = np.stack([t0 & 0xFF, (t0 >> 8) | ((t1 & 0xF) << 4), t1 >> 4], axis=-1).astype(np.uint8)
     rho = rng.integers(0, 256, size=(count, 32), dtype=np.uint8)
     return np.concatenate([packed.reshape(count, 384 * k), rho], axis=1)
+
+
+def synth_mldsa_keys(count: int, seed: int):
+    """`count` well-formed ML-DSA-65 private keys: rho, key, tr random; s1, s2 nibbles uniform in 0..8
+    (eta = 4); t0 uniform 13-bit fields.  Signing never checks t0 against s1, s2, and real t0 is
+    uniform in (-2^12, 2^12], so these exercise exactly the distribution of genuine keys."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    head = rng.integers(0, 256, size=(count, 128), dtype=np.uint8)
+    nib = rng.integers(0, 9, size=(count, 11 * 256), dtype=np.uint8)
+    s = (nib[:, 0::2] | (nib[:, 1::2] << 4)).astype(np.uint8)
+    t0 = rng.integers(0, 256, size=(count, 6 * 416), dtype=np.uint8)
+    return np.concatenate([head, s, t0], axis=1)
 
 
 def synth_seeds(n: int, seed: int):
@@ -172,6 +195,155 @@ def run_reference(args):
     return 0
 
 
+# ---------------------------------------------------------------- ML-DSA-65 (BASELINE configs[3])
+def run_mldsa(args):
+    import numpy as np
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    log2 = args.batch_log2 if args.batch_log2 != 20 else 18
+    n = 1 << log2
+    keys = synth_mldsa_keys(1024, seed=4242)
+    threads = host_threads()
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        import oracle
+        sample = 1 << 12
+        sks = np.ascontiguousarray(keys[np.arange(sample) % 1024])
+        msgs = [bytes(m) for m in synth_seeds(sample, seed=9)]
+        times = []
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            oracle.mldsa65_sign_batch(sks, msgs, nthreads=threads)
+            if step >= args.warmup:
+                times.append(time.perf_counter() - t0)
+        ms = 1e3 * sum(times) / len(times)
+        v = sample / (ms * 1e-3)
+        print(json.dumps({
+            "impl": "reference", "metric": "ML-DSA-65 sign/sec", "value": v, "unit": "sign/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "uint32", "data": "synthetic", "config": {"workload": MLDSA["desc"], "batch_per_gpu": n},
+            "cpu_baseline": {"value": v, "unit": "sign/s", "cores": threads, "kind": "port",
+                             "sample": f"{sample} signatures per step, per-op sk expansion, C restatement of CIRCL's generic path"},
+            "e2e": {"value": v, "unit": "sign/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    import circl_b200
+    from circl_b200._ffi import lib, check
+    circl_b200.init(local)
+    L = lib()
+    peak, peak_kind = measured_peak()
+    gidx = (np.arange(n, dtype=np.int64) + rank * n) % 1024
+    sk_h = torch.empty((n, 4032), dtype=torch.uint8, pin_memory=True)
+    sk_h.numpy()[:] = keys[gidx]
+    msg_h = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
+    msg_h.numpy()[:] = synth_seeds(n, seed=9 + rank)
+    off_h = torch.arange(0, 32 * (n + 1), 32, dtype=torch.int64).pin_memory()
+    sig_h = torch.empty((n, 3309), dtype=torch.uint8, pin_memory=True)
+    sk_d, msg_d, off_d = sk_h.cuda(), msg_h.cuda(), off_h.cuda()
+    sig_d = torch.empty((n, 3309), dtype=torch.uint8, device="cuda")
+    st_d = torch.zeros((n,), dtype=torch.uint8, device="cuda")
+    attempts = ctypes.c_uint64(0)
+
+    def step_device():
+        check(L.cb200_set_stream(torch.cuda.current_stream().cuda_stream))
+        check(L.cb200_mldsa65_sign(sk_d.data_ptr(), 4032, msg_d.data_ptr(), off_d.data_ptr(), None, 0, None,
+                                   sig_d.data_ptr(), st_d.data_ptr(), n, 0, ctypes.cast(ctypes.pointer(attempts), ctypes.c_void_p)))
+
+    def step_host():
+        check(L.cb200_mldsa65_sign(sk_h.data_ptr(), 4032, msg_h.data_ptr(), off_h.data_ptr(), None, 0, None,
+                                   sig_h.data_ptr(), None, n, 0, None))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    if rank == 0:
+        sampler.start()
+    l0 = circl_b200.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_device()
+    ev1.record()
+    barrier()
+    launches = circl_b200.launch_count() - l0
+    ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    att = attempts.value / n
+    assert int(st_d.sum().item()) == 0
+    step_host()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        step_host()
+    e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0) / e2e_steps)
+    same = bool(torch.equal(sig_h[:4096], sig_d[:4096].cpu()))
+    check(L.cb200_profile_enable(1))
+    step_device()
+    nk = L.cb200_profile_kernel_count()
+    ms_tot, cnt = (ctypes.c_double * nk)(), (ctypes.c_uint64 * nk)()
+    check(L.cb200_profile_read(ms_tot, cnt, nk))
+    check(L.cb200_profile_enable(0))
+    kernels = {L.cb200_profile_kernel_name(i).decode(): {"ms_total": ms_tot[i], "launches": int(cnt[i])} for i in range(nk) if cnt[i]}
+    tot = sum(v["ms_total"] for v in kernels.values())
+    dom_name = max(kernels, key=lambda k_: kernels[k_]["ms_total"])
+    # the dominant class runs once per round over the still-active signatures: all of its launches together
+    # process the whole batch, so its per-step time is the launch duration the roofline refers to
+    achieved = MLDSA["bytes_per_op"] * n / (kernels[dom_name]["ms_total"] * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                "share_of_step": kernels[dom_name]["ms_total"] / tot,
+                "note": "integer-ALU (Keccak + NTT) bound; achieved = 7373 algorithmic B/op x batch / time of this kernel "
+                        "class summed over the rounds of one step",
+                "kernels_ms_per_step": {k_: round(v["ms_total"], 3) for k_, v in kernels.items()}}
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        import oracle
+        sample = 1 << 12
+        sks = np.ascontiguousarray(sk_h.numpy()[:sample])
+        msgs = [bytes(m) for m in msg_h.numpy()[:sample]]
+        t0 = time.perf_counter()
+        want, _ = oracle.mldsa65_sign_batch(sks, msgs, nthreads=threads)
+        dt = time.perf_counter() - t0
+        cpu = {"value": sample / dt, "unit": "sign/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} signatures of the batch, all {threads} host threads, per-op sk expansion",
+               "outputs_match_gpu": bool(np.array_equal(want, sig_h.numpy()[:sample]))}
+    if rank == 0:
+        print(json.dumps({
+            "metric": "ML-DSA-65 sign/sec", "value": world * n / (ms_step * 1e-3), "unit": "sign/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "uint32", "data": "synthetic",
+            "config": {"workload": MLDSA["desc"], "batch_per_gpu": n, "sk": "per-op (stride 4032)", "key_pool": 1024,
+                       "attempts_per_signature": att, "l2": "per-op state 65 KB x batch, far larger than L2"},
+            "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "sign/s", "ms_per_step": e2e_ms,
+                    "h2d_bytes_per_step": n * (4032 + 32 + 8), "d2h_bytes_per_step": n * 3310,
+                    "host_vs_device_outputs_equal": same},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+    circl_b200.shutdown()
+    return 0
+
+
 # ---------------------------------------------------------------- our arm
 def main():
     ap = argparse.ArgumentParser()
@@ -179,13 +351,15 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="mlkem768", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="mlkem768", choices=list(WORKLOADS) + ["mldsa65"])
     ap.add_argument("--batch-log2", type=int, default=20, help="operations per GPU = 2^this")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-ntt", action="store_true", help="skip the secondary NTT measurement")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
+    if args.workload == "mldsa65":
+        return run_mldsa(args)
     if args.impl == "reference":
         return run_reference(args)
 
@@ -234,8 +408,39 @@ def main():
     ct_d = torch.empty((n, wl["ct"]), dtype=torch.uint8, device="cuda")
     ss_d = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
 
-    def step_device():
-        scheme.EncapsulateBatch(eks_d, seeds_d, ct=ct_d, ss=ss_d)
+    # N > 1: results are gathered to rank 0 in global index order (the one collective of this path,
+    # NCCL send/recv over NVLink), chunk by chunk so that the transfer of chunk c overlaps the kernels of c+1.
+    n_chunks = 8 if world > 1 else 1
+    gat_ct = gat_ss = None
+    if world > 1 and rank == 0:
+        gat_ct = torch.empty((world * n, wl["ct"]), dtype=torch.uint8, device="cuda")
+        gat_ss = torch.empty((world * n, 32), dtype=torch.uint8, device="cuda")
+
+    def gather_chunk(lo, hi):
+        ops = []
+        if rank == 0:
+            gat_ct[lo:hi].copy_(ct_d[lo:hi], non_blocking=True)
+            gat_ss[lo:hi].copy_(ss_d[lo:hi], non_blocking=True)
+            for r in range(1, world):
+                ops.append(dist.P2POp(dist.irecv, gat_ct[r * n + lo:r * n + hi], r))
+                ops.append(dist.P2POp(dist.irecv, gat_ss[r * n + lo:r * n + hi], r))
+        else:
+            ops.append(dist.P2POp(dist.isend, ct_d[lo:hi], 0))
+            ops.append(dist.P2POp(dist.isend, ss_d[lo:hi], 0))
+        return dist.batch_isend_irecv(ops)
+
+    def step_device(do_gather=True):
+        if world == 1:
+            scheme.EncapsulateBatch(eks_d, seeds_d, ct=ct_d, ss=ss_d)
+            return
+        works = []
+        for c in range(n_chunks):
+            lo, hi = c * n // n_chunks, (c + 1) * n // n_chunks
+            scheme.EncapsulateBatch(eks_d[lo:hi], seeds_d[lo:hi], ct=ct_d[lo:hi], ss=ss_d[lo:hi])
+            if do_gather:
+                works += gather_chunk(lo, hi)
+        for w in works:
+            w.wait()
 
     def step_host():
         check(L.cb200_mlkem_encaps(wl["k"], eks_h.data_ptr(), wl["ek"], seeds_h.data_ptr(), ct_h.data_ptr(),
@@ -259,6 +464,28 @@ def main():
     ms_step = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
     scheme.check_last_status()
     clocks = sampler.stop() if rank == 0 else None
+
+    # ---- N > 1: the same step without the gather, and the gather alone (reported, not the headline)
+    gather = None
+    if world > 1:
+        barrier()
+        ev0.record()
+        for _ in range(args.steps):
+            step_device(do_gather=False)
+        ev1.record()
+        barrier()
+        ms_nogather = max_over_ranks(ev0.elapsed_time(ev1) / args.steps)
+        ev0.record()
+        for w in gather_chunk(0, n):
+            w.wait()
+        ev1.record()
+        barrier()
+        ms_gather = max_over_ranks(ev0.elapsed_time(ev1))
+        gb = (world - 1) * n * (wl["ct"] + 32) / 1e9
+        gather = {"to": "rank 0", "bytes_per_step": (world - 1) * n * (wl["ct"] + 32), "chunks": n_chunks,
+                  "ms_alone": ms_gather, "rank0_ingress_GBps": gb / (ms_gather * 1e-3),
+                  "ms_per_step_without_gather": ms_nogather,
+                  "note": "value includes the gather, overlapped chunk by chunk with the kernels"}
 
     # ---- end to end through the C ABI with pinned host buffers
     for _ in range(3):
@@ -365,7 +592,7 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
             "config": {"workload": wl["desc"], "batch_per_gpu": n, "ek": "per-op (stride %d)" % wl["ek"],
                        "key_pool": 1024, "l2": "inputs+outputs 2.3 GiB per step, larger than L2",
-                       "sharding": "contiguous index ranges, no data-path collective"},
+                       "sharding": "contiguous index ranges per rank; no collective during compute, results gathered to rank 0"},
             "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "encaps/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": n * (wl["ek"] + 32), "d2h_bytes_per_step": n * (wl["ct"] + 32 + 1),
                     "host_vs_device_outputs_equal": same},
@@ -373,6 +600,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu,
             "clocks": clocks,
+            "gather": gather,
             "ntt": ntt,
         }
         print(json.dumps(line))

@@ -187,6 +187,59 @@ __device__ __forceinline__ void fwd_pass_C(int32_t (&r)[32], const LaneTw& t) {
     for (int j = 0; j < 2; j++) ct_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.l2[blk].z, t.l2[blk].zq);
 }
 
+// The same pass with the twiddles read from a shared-memory copy of the table at the
+// point of use (keeps 28 registers free -> 8 CTAs of 128 threads per SM).  `tab` must be
+// volatile-qualified by the caller's cast so the loads stay inside the polynomial loop.
+__device__ __forceinline__ TwPair tw_at(const volatile TwPair* tab, int k) {
+  const volatile int2* p = reinterpret_cast<const volatile int2*>(tab + k);
+  TwPair t;
+  t.z = p->x;
+  t.zq = p->y;
+  return t;
+}
+__device__ __forceinline__ void fwd_pass_C_smem(int32_t (&r)[32], const volatile TwPair* tab, int v) {
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++) {
+    const TwPair t = tw_at(tab, 16 + 2 * v + blk);
+#pragma unroll
+    for (int j = 0; j < 8; j++) ct_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.z, t.zq);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++) {
+    const TwPair t = tw_at(tab, 32 + 4 * v + blk);
+#pragma unroll
+    for (int j = 0; j < 4; j++) ct_bfly(r[8 * blk + j], r[8 * blk + j + 4], t.z, t.zq);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++) {
+    const TwPair t = tw_at(tab, 64 + 8 * v + blk);
+#pragma unroll
+    for (int j = 0; j < 2; j++) ct_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.z, t.zq);
+  }
+}
+__device__ __forceinline__ void inv_pass_C_smem(int32_t (&r)[32], const volatile TwPair* tab, int v) {
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++) {
+    const TwPair t = tw_at(tab, 127 - 8 * v - blk);
+#pragma unroll
+    for (int j = 0; j < 2; j++) gs_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.z, t.zq);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++) {
+    const TwPair t = tw_at(tab, 63 - 4 * v - blk);
+#pragma unroll
+    for (int j = 0; j < 4; j++) gs_bfly(r[8 * blk + j], r[8 * blk + j + 4], t.z, t.zq);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++) {
+    const TwPair t = tw_at(tab, 31 - 2 * v - blk);
+#pragma unroll
+    for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.z, t.zq);
+  }
+  r[16] = barrett_hi(r[16]);
+  r[17] = barrett_hi(r[17]);
+}
+
 // Inverse pass A on C layout: layers l = 2, 4, 8 then the layer-3 Barrett set
 // (indices == 16,17 mod 32, ntt.go:42-43).  Zetas[k] with k = 127-(idx>>2),
 // 63-(idx>>3), 31-(idx>>4): i.e. the forward per-lane entries of lane 7-v, reversed.

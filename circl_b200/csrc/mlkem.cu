@@ -274,10 +274,11 @@ __device__ __forceinline__ uint32_t unpack12_C(const uint8_t* __restrict__ src, 
 // acc += MulHat(a, b) on C layout, with a streamed from global memory as packed words and
 // b read from this lane's private copy in shared memory (word index w*8 + v, stride kept by caller)
 __device__ __forceinline__ void mulhat_acc_words(int32_t (&acc)[32], const uint32_t (&aw)[16],
-                                                 const uint32_t* __restrict__ bpriv, const kyber::LaneTw& t) {
+                                                 const uint32_t* __restrict__ bpriv, const volatile kyber::TwPair* tab,
+                                                 int v) {
 #pragma unroll
   for (int j = 0; j < 8; j++) {
-    const kyber::TwPair z = t.l2[j];  // Zetas[64 + 8v + j]
+    const kyber::TwPair z = kyber::tw_at(tab, 64 + 8 * v + j);
     int32_t x0, x1, x2, x3, y0, y1, y2, y3;
     kyber::unpack2(aw[2 * j], x0, x1);
     kyber::unpack2(aw[2 * j + 1], x2, x3);
@@ -322,11 +323,15 @@ __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
   using namespace kyber;
   __shared__ __align__(16) uint32_t tiles[(kEncThreads / 8) * kPolyWords];
   __shared__ uint32_t rh_store[(kEncThreads / 8) * K * 128];  // NTT(r), lane-private words [oct][j][w][v]
+  __shared__ __align__(16) TwPair tws[128];                    // twiddle table, read at the point of use
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
   const unsigned octmask = 0xffu << (8 * oct);
   uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
   uint32_t* rh = rh_store + (size_t)(warp * 4 + oct) * K * 128 + v;
 
+  for (int i = threadIdx.x; i < 128; i += kEncThreads) tws[i] = tw[i];
+  __syncthreads();
+  const volatile TwPair* tab = tws;
   const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
   if (base >= n) return;
   const size_t op_raw = base + oct;
@@ -337,9 +342,6 @@ __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
   const uint32_t* np = reinterpret_cast<const uint32_t*>(noise) + op * P::n_noise * (N / 2);
   uint8_t* ctp = ct + op * P::ct_bytes;
 
-  LaneTw tf, ti;
-  load_lane_tw(tf, tw, v);
-  load_lane_tw(ti, tw, 7 - v);
   int32_t r[32];
 
   // rh = BarrettReduce(NTT(r))   (cpapke.go:142-144)
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
     store_S(tile, v, r);
     __syncwarp();
     load_C(tile, v, r);
-    fwd_pass_C(r, tf);
+    fwd_pass_C_smem(r, tab, v);
     __syncwarp();
 #pragma unroll
     for (int w = 0; w < 16; w++) rh[(j * 16 + w) * 8] = pack2(barrett_hi(r[2 * w]), barrett_hi(r[2 * w + 1]));
@@ -373,11 +375,11 @@ __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
 #pragma unroll
         for (int w = 0; w < 16; w++) aw[w] = pack2(th[2 * w], th[2 * w + 1]);
       }
-      mulhat_acc_words(r, aw, rh + j * 128, tf);
+      mulhat_acc_words(r, aw, rh + j * 128, tab, v);
     }
 #pragma unroll
     for (int c = 0; c < 32; c++) r[c] = barrett_hi(r[c]);
-    inv_pass_C(r, ti);
+    inv_pass_C_smem(r, tab, v);
     store_C(tile, v, r);
     __syncwarp();
     load_S(tile, v, r);

@@ -25,4 +25,19 @@ for name, fn in (("ntt", lambda: kyber.ntt_(d)), ("invntt", lambda: kyber.inv_nt
     ms = sorted(a.elapsed_time(b) for a, b in evs)
     med = ms[len(ms) // 2]
     res[name] = {"ms_med": med, "ms_min": ms[0], "per_s": n / (med * 1e-3), "GBps_1024B": n * 1024 / (med * 1e-3) / 1e9}
+from circl_b200 import dilithium as dl
+QD = 8380417
+e = torch.randint(0, QD, (n // 2, 256), device="cuda", dtype=torch.int32)
+for name, fn in (("dil_ntt", lambda: dl.ntt_(e)), ("dil_invntt", lambda: dl.inv_ntt_(e)),
+                 ("dil_reduce", lambda: dl.reduce_le2q(e, out=e)), ("dil_mulhat", lambda: dl.mul_hat(e, e, out=e))):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+    for a, b in evs:
+        a.record(); fn(); b.record()
+    torch.cuda.synchronize()
+    ms = sorted(a.elapsed_time(b) for a, b in evs)
+    med = ms[len(ms) // 2]
+    res[name] = {"ms_med": med, "per_s": (n // 2) / (med * 1e-3), "GBps_2048B": (n // 2) * 2048 / (med * 1e-3) / 1e9}
 print(json.dumps(res, indent=1))

@@ -175,6 +175,31 @@ __device__ __forceinline__ void inv_pass_C(uint32_t (&r)[32], const LaneTw& t) {
 #pragma unroll
     for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.l8[blk]);
 }
+// inverse pass A with the twiddles read from a shared-memory copy of InvZetas at the point of use
+// (saves 30 registers in kernels that hold two polynomials)
+__device__ __forceinline__ void inv_pass_C_smem(uint32_t (&r)[32], const volatile uint32_t* iz, int v) {
+#pragma unroll
+  for (int blk = 0; blk < 16; blk++) gs_bfly(r[2 * blk], r[2 * blk + 1], iz[16 * v + blk]);
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++) {
+    const uint32_t z = iz[128 + 8 * v + blk];
+#pragma unroll
+    for (int j = 0; j < 2; j++) gs_bfly(r[4 * blk + j], r[4 * blk + j + 2], z);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++) {
+    const uint32_t z = iz[192 + 4 * v + blk];
+#pragma unroll
+    for (int j = 0; j < 4; j++) gs_bfly(r[8 * blk + j], r[8 * blk + j + 4], z);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++) {
+    const uint32_t z = iz[224 + 2 * v + blk];
+#pragma unroll
+    for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], z);
+  }
+}
+
 // inverse pass B, S layout: l = 16 (k=240+h), 32 (248+h), 64 (252+h), 128 (254), then * ROver256
 __device__ __forceinline__ void inv_pass_S(uint32_t (&r)[32]) {
   static_for<0, 8>([&](auto hc) {
@@ -272,6 +297,14 @@ __device__ __forceinline__ void ntt_octet(uint32_t (&r)[32], uint32_t* tile, int
 }
 __device__ __forceinline__ void invntt_octet(uint32_t (&r)[32], uint32_t* tile, int v, const LaneTw& t) {
   inv_pass_C(r, t);
+  store_C(tile, v, r);
+  __syncwarp();
+  load_S(tile, v, r);
+  __syncwarp();
+  inv_pass_S(r);
+}
+__device__ __forceinline__ void invntt_octet_smem(uint32_t (&r)[32], uint32_t* tile, int v, const volatile uint32_t* iz) {
+  inv_pass_C_smem(r, iz, v);
   store_C(tile, v, r);
   __syncwarp();
   load_S(tile, v, r);

@@ -40,6 +40,7 @@ struct Work {
   uint64_t *mu, *rhop;     // per op: 8 words each
   uint32_t *y, *yh, *w0;   // per op: [5][256], [5][256], [6][256]
   uint8_t* w1p;            // per op: 768 bytes
+  uint8_t* zbuf;           // per op: 5 x 640 bytes, z packed (word aligned; copied into the signature on accept)
   uint32_t* c;             // per op: [256] challenge polynomial, then its NTT
   uint64_t* ctilde;        // per op: 6 words
   uint32_t *hintbits, *flags, *hintcnt, *attempt;  // per op: [48], 1, 1, 1
@@ -443,7 +444,7 @@ __global__ void __launch_bounds__(128) cntt_kernel(const uint32_t* __restrict__ 
 
 // InvNTT(c-hat . x-hat) on an octet: returns S layout
 __device__ __forceinline__ void c_times(uint32_t (&r)[32], const uint32_t* __restrict__ chat,
-                                        const uint32_t* __restrict__ xhat, const OctetCtx& o, const LaneTw& ti) {
+                                        const uint32_t* __restrict__ xhat, const OctetCtx& o, const volatile uint32_t* iz) {
   const uint4* cp = reinterpret_cast<const uint4*>(chat + 32 * o.v);
   const uint4* xp = reinterpret_cast<const uint4*>(xhat + 32 * o.v);
 #pragma unroll
@@ -454,7 +455,7 @@ __device__ __forceinline__ void c_times(uint32_t (&r)[32], const uint32_t* __res
     r[4 * c + 2] = mont_mul(x.z, z.z);
     r[4 * c + 3] = mont_mul(x.w, z.w);
   }
-  invntt_octet(r, o.tile, o.v, ti);
+  invntt_octet_smem(r, o.tile, o.v, iz);
 }
 
 // makeHint (rounding.go:56-67)
@@ -467,10 +468,14 @@ __device__ __forceinline__ uint32_t make_hint(uint32_t z0, uint32_t r1) {
 __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
                                                        const uint32_t* __restrict__ sh, const uint32_t* __restrict__ cpoly,
                                                        const uint32_t* __restrict__ y, const uint32_t* __restrict__ w0,
-                                                       const uint8_t* __restrict__ w1p, uint8_t* __restrict__ sig,
+                                                       const uint8_t* __restrict__ w1p, uint8_t* __restrict__ zbuf,
                                                        uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags,
                                                        uint32_t* __restrict__ hintcnt, const uint32_t* __restrict__ zetas) {
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  __shared__ uint32_t izs[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) izs[i] = zetas[256 + i];
+  __syncthreads();
+  const volatile uint32_t* ti = izs;
   const OctetCtx o = octet_ctx(tiles);
   const unsigned octmask = 0xffu << (8 * o.oct);
   const size_t total = nact * (K + L), base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
@@ -481,8 +486,6 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
   const int item = (int)(u / nact);
   const uint32_t* keyp = sh + (key_shared ? 0 : op) * (NKEYPOLY * N);
   const uint32_t* chat = cpoly + op * N;
-  LaneTw ti;
-  load_lane_tw_inv(ti, zetas + 256, o.v);
   uint32_t r[32];
   bool reject = false;
   if (item < K) {
@@ -523,23 +526,23 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
       r[2 * s + 1] = modq(r[2 * s + 1] + a.y);
       reject |= exceeds1(r[2 * s], GAMMA1 - BETA) | exceeds1(r[2 * s + 1], GAMMA1 - BETA);
     }
-    // PolyPackLeGamma1 (internal/pack.go:236-252): 32 coefficients -> 20 words, written speculatively
+    // PolyPackLeGamma1 (internal/pack.go:236-252): 32 coefficients -> 20 aligned words in the staging
+    // buffer; finalize copies them into the (3309-byte strided) signature only if the attempt is accepted
     s_to_c(r, o.tile, o.v);
-    // signatures are 3309 bytes apart, hence byte stores
-    uint8_t* zb = sig + op * (size_t)SIG_BYTES + CTILDE + POLY_Z * j + 80 * o.v;
+    uint32_t* zw = reinterpret_cast<uint32_t*>(zbuf + (op * L + j) * (size_t)POLY_Z) + 20 * o.v;
     uint64_t accb = 0;
-    int bits = 0, ob = 0;
+    int bits = 0, ow = 0;
 #pragma unroll
     for (int c = 0; c < 32; c++) {
       uint32_t p = GAMMA1 - r[c];
       p += (uint32_t)((int32_t)p >> 31) & Q;
       accb |= (uint64_t)(p & 0xfffff) << bits;
       bits += 20;
-      while (bits >= 8) {
-        if (active) zb[ob] = (uint8_t)accb;
-        ob++;
-        accb >>= 8;
-        bits -= 8;
+      if (bits >= 32) {
+        if (active) zw[ow] = (uint32_t)accb;
+        ow++;
+        accb >>= 32;
+        bits -= 32;
       }
     }
   }
@@ -547,47 +550,54 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
   if (reject && active && o.v == 0) atomicOr(flags + op, 1u);
 }
 
-// accept -> c~ and hints into the signature; reject -> next attempt (dilithium.go:369-377,459-469)
+// accept -> c~, z and hints into the signature; reject -> next attempt (dilithium.go:369-377,459-469).
+// One warp per active op.
 __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restrict__ act, size_t nact,
                                                        const uint64_t* __restrict__ ctilde,
+                                                       const uint8_t* __restrict__ zbuf,
                                                        const uint32_t* __restrict__ hintbits,
                                                        const uint32_t* __restrict__ flags,
                                                        const uint32_t* __restrict__ hintcnt, uint32_t* __restrict__ attempt,
                                                        uint8_t* __restrict__ sig, uint8_t* __restrict__ status,
                                                        uint32_t* __restrict__ next, uint32_t* __restrict__ next_count) {
-  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
   if (s >= nact) return;
   const size_t op = act[s];
   uint8_t* sg = sig + op * (size_t)SIG_BYTES;
-  if (flags[op] == 0 && hintcnt[op] <= OMEGA) {
-    for (int i = 0; i < 6; i++) {
-      const uint64_t w = ctilde[6 * op + i];
-      for (int b = 0; b < 8; b++) sg[8 * i + b] = (uint8_t)(w >> (8 * b));
-    }
-    uint8_t* hb = sg + CTILDE + L * POLY_Z;  // PackHint (internal/pack.go:77-95)
-    int off = 0;
-    for (int i = 0; i < K; i++) {
-      for (int w = 0; w < 8; w++) {
-        uint32_t m = hintbits[48 * op + 8 * i + w];
-        while (m) {
-          const int bit = __ffs(m) - 1;
-          hb[off++] = (uint8_t)(32 * w + bit);
-          m &= m - 1;
+  const bool accept = flags[op] == 0 && hintcnt[op] <= OMEGA;
+  if (accept) {
+    const uint8_t* ct = reinterpret_cast<const uint8_t*>(ctilde + 6 * op);
+    for (int i = lane; i < CTILDE; i += 32) sg[i] = ct[i];
+    const uint8_t* zs = zbuf + op * (size_t)(L * POLY_Z);
+    for (int i = lane; i < L * POLY_Z; i += 32) sg[CTILDE + i] = zs[i];
+    if (lane == 0) {
+      uint8_t* hb = sg + CTILDE + L * POLY_Z;  // PackHint (internal/pack.go:77-95)
+      int off = 0;
+      for (int i = 0; i < K; i++) {
+        for (int w = 0; w < 8; w++) {
+          uint32_t m = hintbits[48 * op + 8 * i + w];
+          while (m) {
+            const int bit = __ffs(m) - 1;
+            hb[off++] = (uint8_t)(32 * w + bit);
+            m &= m - 1;
+          }
         }
+        hb[OMEGA + i] = (uint8_t)off;
       }
-      hb[OMEGA + i] = (uint8_t)off;
+      for (; off < OMEGA; off++) hb[off] = 0;
+      if (status) status[op] = 0;
     }
-    for (; off < OMEGA; off++) hb[off] = 0;
-    if (status) status[op] = 0;
   } else {
     const uint32_t at = attempt[op] + 1;
-    attempt[op] = at;
+    __syncwarp();
     if (at + 1 >= MAX_ATTEMPTS) {  // "attempt >= 576" (dilithium.go:372-377): give up, flag the op
-      if (status) status[op] = 1;
-      for (int i = 0; i < SIG_BYTES; i++) sg[i] = 0;
-    } else {
+      for (int i = lane; i < SIG_BYTES; i += 32) sg[i] = 0;
+      if (lane == 0 && status) status[op] = 1;
+    } else if (lane == 0) {
       next[atomicAdd(next_count, 1u)] = (uint32_t)op;
     }
+    if (lane == 0) attempt[op] = at;
   }
 }
 
@@ -606,7 +616,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   };
   const size_t oA = take(nkeys * K * L * 1024), oS = take(nkeys * NKEYPOLY * 1024), oMu = take(n * 64),
                oRh = take(n * 64), oY = take(n * L * 1024), oYh = take(n * L * 1024), oW0 = take(n * K * 1024),
-               oW1 = take(n * K * POLY_W1), oC = take(n * 1024), oCt = take(n * 48), oHb = take(n * 48 * 4),
+               oW1 = take(n * K * POLY_W1), oZ = take(n * L * POLY_Z), oC = take(n * 1024), oCt = take(n * 48), oHb = take(n * 48 * 4),
                oFl = take(n * 4), oHc = take(n * 4), oAt = take(n * 4), oA0 = take(n * 4), oA1 = take(n * 4),
                oCnt = take(16);
   void* base = nullptr;
@@ -622,6 +632,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   w.yh = (uint32_t*)(b + oYh);
   w.w0 = (uint32_t*)(b + oW0);
   w.w1p = (uint8_t*)(b + oW1);
+  w.zbuf = (uint8_t*)(b + oZ);
   w.c = (uint32_t*)(b + oC);
   w.ctilde = (uint64_t*)(b + oCt);
   w.hintbits = (uint32_t*)(b + oHb);
@@ -691,12 +702,12 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
       response_kernel<<<blocks(nact * (K + L), 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1p,
-                                                                  sig, w.hintbits, w.flags, w.hintcnt, zetas);
+                                                                  w.zbuf, w.hintbits, w.flags, w.hintcnt, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_COMPACT, st);
-      finalize_kernel<<<blocks(nact, 128), 128, 0, st>>>(act, nact, w.ctilde, w.hintbits, w.flags, w.hintcnt, w.attempt,
-                                                         sig, status, w.act[cur ^ 1], w.count + (cur ^ 1));
+      finalize_kernel<<<blocks(nact * 32, 128), 128, 0, st>>>(act, nact, w.ctilde, w.zbuf, w.hintbits, w.flags, w.hintcnt,
+                                                              w.attempt, sig, status, w.act[cur ^ 1], w.count + (cur ^ 1));
     }
     CB200_CUDA(cudaMemcpyAsync((void*)h_count, w.count + (cur ^ 1), 4, cudaMemcpyDeviceToHost, st));
     CB200_CUDA(cudaStreamSynchronize(st));

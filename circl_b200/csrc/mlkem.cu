@@ -75,17 +75,17 @@ __global__ void __launch_bounds__(128) hash_ek_kernel(const uint8_t* __restrict_
 }
 
 // (K', r) = SHA3-512(m || h)  (kyber.go:126-131); ss = K' (kyber.go:136)
-__global__ void __launch_bounds__(128) g_kernel(const uint8_t* __restrict__ m, const uint64_t* __restrict__ h,
-                                                int h_shared, size_t n, uint8_t* __restrict__ ss,
+__global__ void __launch_bounds__(128) g_kernel(const uint8_t* __restrict__ m, const uint8_t* __restrict__ h,
+                                                size_t h_stride, size_t n, uint8_t* __restrict__ ss,
                                                 uint64_t* __restrict__ r_out) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   uint64_t a[25];
   keccak::zero(a);
-  const uint64_t* hp = h + (h_shared ? 0 : 4 * i);
+  const uint64_t* hp = reinterpret_cast<const uint64_t*>(h + i * h_stride);
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    a[j] = keccak::ld64(m + 32 * i + 8 * j);
+    a[j] = reinterpret_cast<const uint64_t*>(m + 32 * i)[j];
     a[4 + j] = hp[j];
   }
   a[8] = 0x8000000000000006ull;  // rate 72: pad bytes 64 (0x06) and 71 (0x80) share lane 8
@@ -147,6 +147,8 @@ __device__ __forceinline__ void cbd2_store(const uint64_t (&a)[25], int16_t* __r
   }
 }
 
+// sub-batch size: A^T + noise of one sub-batch (8 KiB / op for K=3, 12.5 KiB for K=4) stay L2-resident
+constexpr size_t kSub = 8192;
 constexpr int kRowWords = 129;  // 256 int16 + 2 slack, odd word stride
 constexpr int kSampleSmem = 128 * kRowWords * 4;
 
@@ -318,7 +320,9 @@ template <int K>
 __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
     const uint8_t* __restrict__ ek, size_t ek_stride, const int16_t* __restrict__ A, int a_shared,
     const int16_t* __restrict__ noise, const uint8_t* __restrict__ m, size_t n, uint8_t* __restrict__ ct,
-    uint8_t* __restrict__ ss, uint8_t* __restrict__ status, const kyber::TwPair* __restrict__ tw) {
+    uint8_t* __restrict__ ss, uint8_t* __restrict__ status, const kyber::TwPair* __restrict__ tw, int lenient) {
+  // lenient = 1: re-encryption inside Decapsulate, where the key embedded in dk goes through
+  // PublicKey.Unpack (cpapke.go:58-63): t-hat is Normalized and there is no modulus check.
   using P = Params<K>;
   using namespace kyber;
   __shared__ __align__(16) uint32_t tiles[(kEncThreads / 8) * kPolyWords];
@@ -371,7 +375,13 @@ __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
         load_words_C(Ap + (i * K + j) * (N / 2), v, aw);
       } else {  // row K: t-hat from the encapsulation key, PolyDotHat(&v, &pk.th, &rh) (cpapke.go:167)
         int32_t th[32];
-        bad |= unpack12_C(ekp + 384 * j + 48 * v, th);
+        const uint32_t b = unpack12_C(ekp + 384 * j + 48 * v, th);
+        if (lenient) {
+#pragma unroll
+          for (int c = 0; c < 32; c++) th[c] = csubq_hi(barrett_hi(th[c]));
+        } else {
+          bad |= b;
+        }
 #pragma unroll
         for (int w = 0; w < 16; w++) aw[w] = pack2(th[2 * w], th[2 * w + 1]);
       }
@@ -421,10 +431,258 @@ __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
     if (bad) {
       uint32_t* c32 = reinterpret_cast<uint32_t*>(ctp);
       for (int w = v; w < P::ct_bytes / 4; w += 8) c32[w] = 0;
-      reinterpret_cast<uint32_t*>(ss + 32 * op)[v] = 0;
+      if (ss) reinterpret_cast<uint32_t*>(ss + 32 * op)[v] = 0;
     }
-    if (status && v == 0) status[op] = (uint8_t)bad;
+    if (status && v == 0 && !lenient) status[op] = (uint8_t)bad;
   }
+}
+
+
+// ------------------------------------------------------------------ 4. Decapsulate
+// Decompress_q(x, d) (poly.go:170-243) of 32 coefficients (C layout) from D words
+template <int D>
+__device__ __forceinline__ void decompress_C(const uint32_t* __restrict__ src, int32_t (&r)[32]) {
+  uint32_t w[D + 1];
+#pragma unroll
+  for (int i = 0; i < D; i++) w[i] = __ldg(src + i);
+  w[D] = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    const int bit = D * i, wi = bit >> 5, sh = bit & 31;
+    uint32_t t = w[wi] >> sh;
+    if (sh + D > 32) t |= w[wi + 1] << (32 - sh);
+    t &= (1u << D) - 1;
+    r[i] = (int32_t)((((1u << (D - 1)) + t * (uint32_t)Q) >> D) << 16);
+  }
+}
+
+// K-PKE.Decrypt (cpapke.go:113-130): m' = CompressMessage(v - InvNTT(s-hat . NTT(u))); one octet per op
+template <int K>
+__global__ void __launch_bounds__(kEncThreads) decrypt_kernel(const uint8_t* __restrict__ dk, size_t dk_stride,
+                                                              const uint8_t* __restrict__ ct, size_t n,
+                                                              uint8_t* __restrict__ mprime,
+                                                              const kyber::TwPair* __restrict__ tw) {
+  using P = Params<K>;
+  using namespace kyber;
+  __shared__ __align__(16) uint32_t tiles[(kEncThreads / 8) * kPolyWords];
+  __shared__ __align__(16) TwPair tws[128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
+  const unsigned octmask = 0xffu << (8 * oct);
+  uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
+  for (int i = threadIdx.x; i < 128; i += kEncThreads) tws[i] = tw[i];
+  __syncthreads();
+  const volatile TwPair* tab = tws;
+  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
+  if (base >= n) return;
+  const bool active = base + oct < n;
+  const size_t op = active ? base + oct : n - 1;
+  const uint8_t* dkp = dk + op * dk_stride;
+  const uint8_t* ctp = ct + op * P::ct_bytes;
+  int32_t acc[32], r[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) acc[c] = 0;
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    decompress_C<P::du>(reinterpret_cast<const uint32_t*>(ctp + j * 32 * P::du) + v * P::du, r);  // u[j]
+    store_C(tile, v, r);
+    __syncwarp();
+    load_S(tile, v, r);
+    __syncwarp();
+    fwd_pass_S(r);  // u.NTT()
+    store_S(tile, v, r);
+    __syncwarp();
+    load_C(tile, v, r);
+    __syncwarp();
+    fwd_pass_C_smem(r, tab, v);
+    int32_t sh[32];
+    unpack12_C(dkp + 384 * j + 48 * v, sh);  // sk.sh.Unpack + Normalize (cpapke.go:32-36)
+#pragma unroll
+    for (int q = 0; q < 8; q++) {  // PolyDotHat(&m, &sk.sh, &u): MulHat(sh[j], u[j]) (poly.go:63-100)
+      const TwPair z = tw_at(tab, 64 + 8 * v + q);
+      int32_t a[4], b[4];
+#pragma unroll
+      for (int e = 0; e < 4; e++) {
+        a[e] = csubq_hi(barrett_hi(sh[4 * q + e])) >> 16;
+        b[e] = r[4 * q + e] >> 16;
+      }
+      int32_t p0 = mont_prod_hi(a[1], b[1]);
+      p0 = mont_mul_hi(p0 >> 16, z.z, z.zq);
+      p0 += mont_prod_hi(a[0], b[0]);
+      const int32_t p1 = mont_prod_hi(a[0], b[1]) + mont_prod_hi(a[1], b[0]);
+      int32_t p2 = mont_prod_hi(a[3], b[3]);
+      p2 = -mont_mul_hi(p2 >> 16, z.z, z.zq);
+      p2 += mont_prod_hi(a[2], b[2]);
+      const int32_t p3 = mont_prod_hi(a[2], b[3]) + mont_prod_hi(a[3], b[2]);
+      acc[4 * q] += p0;
+      acc[4 * q + 1] += p1;
+      acc[4 * q + 2] += p2;
+      acc[4 * q + 3] += p3;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c++) acc[c] = barrett_hi(acc[c]);
+  inv_pass_C_smem(acc, tab, v);
+  store_C(tile, v, acc);
+  __syncwarp();
+  load_S(tile, v, acc);
+  __syncwarp();
+  inv_pass_S(acc, v);
+  // v polynomial: decompress in C layout, bring to S layout
+  decompress_C<P::dv>(reinterpret_cast<const uint32_t*>(ctp + K * 32 * P::du) + v * P::dv, r);
+  store_C(tile, v, r);
+  __syncwarp();
+  load_S(tile, v, r);
+  __syncwarp();
+  // m = Normalize(v - m); CompressMessageTo (poly.go:150-166); coefficient 16 s + 2 v + b -> bit of m'
+  uint32_t words[8];
+#pragma unroll
+  for (int w = 0; w < 8; w++) words[w] = 0;
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int32_t d = csubq_hi(barrett_hi(r[2 * s + b] - acc[2 * s + b]));
+      int32_t x = (1664 << 16) - d;        // int16 arithmetic in the high half
+      x = (x >> 31) ^ x;
+      x &= 0xffff0000;
+      x -= (832 << 16);
+      const uint32_t bit = (uint32_t)x >> 31;
+      words[s >> 1] |= bit << (16 * (s & 1) + 2 * v + b);
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    uint32_t x = words[w];
+    x |= __shfl_xor_sync(octmask, x, 1);
+    x |= __shfl_xor_sync(octmask, x, 2);
+    x |= __shfl_xor_sync(octmask, x, 4);
+    words[w] = x;
+  }
+  if (active) {
+    uint32_t mine = 0;
+#pragma unroll
+    for (int w = 0; w < 8; w++) mine = (v == w) ? words[w] : mine;
+    reinterpret_cast<uint32_t*>(mprime + 32 * op)[v] = mine;
+  }
+}
+
+// Implicit rejection (kyber.go:168-183): ss = (ct == ct2) ? K' : SHAKE256(z || ct)[:32]; also checks
+// H(ek) against the copy stored in dk (kem.ErrPrivKey, kyber.go:226-228).  One thread per op.
+template <int K>
+__global__ void __launch_bounds__(128) select_kernel(const uint8_t* __restrict__ dk, size_t dk_stride,
+                                                     const uint8_t* __restrict__ ct, const uint8_t* __restrict__ ct2,
+                                                     const uint8_t* __restrict__ kbar, const uint64_t* __restrict__ hcalc,
+                                                     size_t n, uint8_t* __restrict__ ss, uint8_t* __restrict__ status) {
+  using P = Params<K>;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* z = reinterpret_cast<const uint64_t*>(dk + i * dk_stride + 384 * K + P::ek_bytes + 32);
+  const uint64_t* hst = reinterpret_cast<const uint64_t*>(dk + i * dk_stride + 384 * K + P::ek_bytes);
+  const uint64_t* c1 = reinterpret_cast<const uint64_t*>(ct + i * P::ct_bytes);
+  const uint64_t* c2 = reinterpret_cast<const uint64_t*>(ct2 + i * P::ct_bytes);
+  constexpr int ctw = P::ct_bytes / 8, words = 4 + ctw, full = words / 17, rem = words % 17;
+  uint64_t a[25];
+  keccak::zero(a);
+  uint64_t diff = 0;
+  int k = 0;
+#pragma unroll 1
+  for (int b = 0; b < full; b++) {
+#pragma unroll
+    for (int w = 0; w < 17; w++, k++) {
+      uint64_t x;
+      if (k < 4) {
+        x = z[k];
+      } else {
+        x = c1[k - 4];
+        diff |= x ^ c2[k - 4];
+      }
+      a[w] ^= x;
+    }
+    keccak::f1600(a);
+  }
+#pragma unroll
+  for (int w = 0; w < rem; w++, k++) {
+    const uint64_t x = c1[k - 4];
+    diff |= x ^ c2[k - 4];
+    a[w] ^= x;
+  }
+  a[rem] ^= 0x1f;
+  a[16] ^= 0x8000000000000000ull;
+  keccak::f1600(a);
+  const bool hbad = (hst[0] ^ hcalc[4 * i]) | (hst[1] ^ hcalc[4 * i + 1]) | (hst[2] ^ hcalc[4 * i + 2]) |
+                    (hst[3] ^ hcalc[4 * i + 3]);
+  const uint64_t* kb = reinterpret_cast<const uint64_t*>(kbar + 32 * i);
+  uint64_t* so = reinterpret_cast<uint64_t*>(ss + 32 * i);
+#pragma unroll
+  for (int j = 0; j < 4; j++) so[j] = hbad ? 0 : (diff == 0 ? kb[j] : a[j]);
+  if (status) status[i] = hbad ? 2 : 0;
+}
+
+template <int K>
+static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct, uint8_t* ss, uint8_t* status, size_t n,
+                         cudaStream_t st, int slot) {
+  using P = Params<K>;
+  Ctx& c = ctx();
+  const size_t sub = n < kSub ? n : kSub;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_h = take(n * 32), o_r = take(n * 32), o_m = take(n * 32), o_k = take(n * 32),
+               o_ct2 = take(n * (size_t)P::ct_bytes), o_A = take(sub * K * K * 512), o_n = take(sub * P::n_noise * 512);
+  void* base = nullptr;
+  int rc = ensure_work(slot, off, &base);
+  if (rc) return rc;
+  char* b = (char*)base;
+  uint64_t* h = (uint64_t*)(b + o_h);
+  uint64_t* r = (uint64_t*)(b + o_r);
+  uint8_t* mprime = (uint8_t*)(b + o_m);
+  uint8_t* kbar = (uint8_t*)(b + o_k);
+  uint8_t* ct2 = (uint8_t*)(b + o_ct2);
+  int16_t* A = (int16_t*)(b + o_A);
+  int16_t* noise = (int16_t*)(b + o_n);
+  const uint8_t* ek = dk + 384 * K;  // dk = sk || ek || H(ek) || z (kyber.go:187-201)
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
+    attr_set = true;
+  }
+  const kyber::TwPair* tw = (const kyber::TwPair*)c.kyber_tw;
+  {
+    KernelScope ks(KID_MLKEM_ENCRYPT, st);
+    decrypt_kernel<K><<<(unsigned)((n + 15) / 16), kEncThreads, 0, st>>>(dk, dk_stride, ct, n, mprime, tw);
+  }
+  {
+    KernelScope ks(KID_MLKEM_HASH_EK, st);
+    hash_ek_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ek, dk_stride, n, h);
+  }
+  {  // (K', r') = G(m' || h) with the h stored in dk (kyber.go:160-164)
+    KernelScope ks(KID_MLKEM_G, st);
+    g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(mprime, dk + 384 * K + P::ek_bytes, dk_stride, n, kbar, r);
+  }
+  for (size_t first = 0; first < n; first += sub) {
+    const size_t cnt = (n - first < sub) ? n - first : sub;
+    const size_t mat_blocks = (cnt * K * K + 127) / 128, noise_blocks = (cnt * P::n_noise + 127) / 128;
+    {
+      KernelScope ks(KID_MLKEM_SAMPLE, st);
+      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, st>>>(
+          ek + first * dk_stride, dk_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks);
+    }
+    {
+      KernelScope ks(KID_MLKEM_ENCRYPT, st);
+      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
+          ek + first * dk_stride, dk_stride, A, 0, noise, mprime + 32 * first, cnt, ct2 + first * P::ct_bytes, nullptr,
+          nullptr, tw, 1);
+    }
+  }
+  {
+    KernelScope ks(KID_MLKEM_G, st);
+    select_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dk, dk_stride, ct, ct2, kbar, h, n, ss, status);
+  }
+  CB200_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ------------------------------------------------------------------ host side
@@ -435,8 +693,6 @@ struct Work {
   int16_t* noise;   // sub x (2K+1) x 256
 };
 
-// sub-batch size: A^T + noise of one sub-batch (8 KiB / op for K=3, 12.5 KiB for K=4) stay L2-resident
-constexpr size_t kSub = 8192;
 
 template <int K>
 static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
@@ -474,7 +730,7 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
   }
   {
     KernelScope ks(KID_MLKEM_G, st);
-    g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, h, shared ? 1 : 0, n, ss, r);
+    g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, (const uint8_t*)h, shared ? 0 : 32, n, ss, r);
   }
   for (size_t first = 0; first < n; first += sub) {
     const size_t cnt = (n - first < sub) ? n - first : sub;
@@ -491,7 +747,7 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
       encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
           ek + (shared ? 0 : first * ek_stride), ek_stride, A, shared ? 1 : 0, noise, seeds + 32 * first, cnt,
           ct + first * P::ct_bytes, ss + 32 * first, status ? status + first : nullptr,
-          (const kyber::TwPair*)c.kyber_tw);
+          (const kyber::TwPair*)c.kyber_tw, 0);
     }
   }
   CB200_CUDA(cudaGetLastError());
@@ -510,6 +766,93 @@ static int encaps_any(int k, const uint8_t* ek, size_t ek_stride, const uint8_t*
 using namespace cb200;
 
 extern "C" {
+
+size_t cb200_mlkem_private_key_size(int k) { return (k >= 2 && k <= 4) ? 768u * k + 96 : 0; }
+
+int cb200_mlkem_decaps(int k, const uint8_t* dk, size_t dk_stride, const uint8_t* ct, uint8_t* ss, uint8_t* status,
+                       size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (k != 3 && k != 4) {
+    set_error("cb200_mlkem_decaps: k must be 3 (ML-KEM-768) or 4 (ML-KEM-1024), got %d", k);
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  const size_t dksz = cb200_mlkem_private_key_size(k), ctsz = cb200_mlkem_ciphertext_size(k);
+  if (!dk || !ct || !ss || (dk_stride != 0 && dk_stride < dksz)) {
+    set_error("cb200_mlkem_decaps: bad argument");
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(ss);
+  if (dev != is_device_ptr(dk) || dev != is_device_ptr(ct) || (status && dev != is_device_ptr(status))) {
+    set_error("cb200_mlkem_decaps: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  auto run = [&](const uint8_t* d_dk, size_t stride, const uint8_t* d_ct, uint8_t* d_ss, uint8_t* d_st, size_t cnt,
+                 cudaStream_t st, int slot) {
+    return k == 3 ? mlkem::decaps_device<3>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot)
+                  : mlkem::decaps_device<4>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot);
+  };
+  if (dev) {
+    if (((uintptr_t)dk | (uintptr_t)ct | (uintptr_t)ss | dk_stride) & 15) {
+      set_error("cb200_mlkem_decaps: device buffers and dk_stride must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    if (dk_stride == 0) {
+      set_error("cb200_mlkem_decaps: a shared dk needs host pointers (device path expects one dk per op)");
+      return CB200_ERR_ARG;
+    }
+    return run(dk, dk_stride, ct, ss, status, n, ctx().cur, 3);
+  }
+  uint8_t* user_status = status;
+  void* pin = nullptr;
+  rc = ensure_pinned(n, &pin);
+  if (rc) return rc;
+  status = (uint8_t*)pin;
+  // a shared dk is replicated per op inside each staged chunk (the decapsulation pipeline is per-op)
+  std::vector<uint8_t> rep;
+  const uint8_t* dk_src = dk;
+  size_t host_stride = dk_stride;
+  const size_t chunk = 1u << 15;
+  if (dk_stride == 0) {
+    const size_t m = n < chunk ? n : chunk;
+    rep.resize(m * dksz);
+    for (size_t i = 0; i < m; i++) memcpy(rep.data() + i * dksz, dk, dksz);
+    dk_src = rep.data();
+  }
+  std::vector<Buf> bufs(4);
+  bufs[0] = Buf{dk_src, nullptr, dksz, false, dk_stride == 0 ? dksz : host_stride};
+  bufs[1] = Buf{ct, nullptr, ctsz, false, 0};
+  bufs[2] = Buf{nullptr, ss, 32, false, 0};
+  bufs[3] = Buf{nullptr, status, 1, false, 0};
+  if (dk_stride == 0) {
+    // every chunk reuses the same replicated block: run chunk by chunk with first = 0 for the dk buffer
+    for (size_t first = 0; first < n && rc == 0; first += chunk) {
+      const size_t cnt = n - first < chunk ? n - first : chunk;
+      std::vector<Buf> b2(4);
+      b2[0] = Buf{dk_src, nullptr, dksz, false, 0};
+      b2[1] = Buf{ct + first * ctsz, nullptr, ctsz, false, 0};
+      b2[2] = Buf{nullptr, ss + first * 32, 32, false, 0};
+      b2[3] = Buf{nullptr, status + first, 1, false, 0};
+      rc = run_staged(b2, cnt, cnt, [&](void** d, size_t c2, size_t, cudaStream_t st, int slot) {
+        return run((const uint8_t*)d[0], dksz, (const uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], c2, st, slot);
+      });
+    }
+  } else {
+    rc = run_staged(bufs, n, chunk, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+      return run((const uint8_t*)d[0], dksz, (const uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], cnt, st, slot);
+    });
+  }
+  if (rc) return rc;
+  size_t nbad = 0;
+  for (size_t i = 0; i < n; i++) nbad += status[i] != 0;
+  if (user_status) memcpy(user_status, status, n);
+  if (nbad) {
+    set_error("cb200_mlkem_decaps: H(ek) stored in %zu of %zu private keys does not match (kem.ErrPrivKey)", nbad, n);
+    return CB200_ERR_PRIVKEY;
+  }
+  return 0;
+}
 
 size_t cb200_mlkem_public_key_size(int k) { return (k >= 2 && k <= 4) ? 384u * k + 32 : 0; }
 size_t cb200_mlkem_ciphertext_size(int k) { return k == 3 ? 1088 : k == 4 ? 1568 : k == 2 ? 768 : 0; }

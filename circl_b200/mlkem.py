@@ -33,6 +33,18 @@ class ErrSeedSize(KemError):         # kem.ErrSeedSize
     pass
 
 
+class ErrPrivKeySize(KemError):      # kem.ErrPrivKeySize
+    pass
+
+
+class ErrPrivKey(KemError):          # kem.ErrPrivKey (H(ek) in dk mismatches, kyber.go:226-228)
+    pass
+
+
+class ErrCiphertextSize(KemError):   # kem.ErrCiphertextSize
+    pass
+
+
 class ErrTypeMismatch(KemError):     # kem.ErrTypeMismatch
     pass
 
@@ -52,6 +64,27 @@ class PublicKey:
 
     def Equal(self, other) -> bool:
         return isinstance(other, PublicKey) and other._scheme is self._scheme and other._packed == self._packed
+
+
+class PrivateKey:
+    """kem.PrivateKey: holds the packed decapsulation key (immutable)."""
+
+    def __init__(self, scheme: "Scheme", packed: bytes):
+        self._scheme = scheme
+        self._packed = bytes(packed)
+
+    def Scheme(self):
+        return self._scheme
+
+    def MarshalBinary(self) -> bytes:
+        return self._packed
+
+    def Equal(self, other) -> bool:
+        return isinstance(other, PrivateKey) and other._scheme is self._scheme and other._packed == self._packed
+
+    def Public(self) -> PublicKey:
+        k = self._scheme._k
+        return PublicKey(self._scheme, self._packed[384 * k:384 * k + 384 * k + 32])
 
 
 def _is_torch(x) -> bool:
@@ -168,15 +201,67 @@ class Scheme:
             err.status = st.cpu().numpy()
             raise err
 
-    # ---- outside the accelerated path (next rows) ----
+    # ---- outside the accelerated path ----
     def GenerateKeyPair(self):
         raise NotImplementedError("key generation is not on the accelerated path yet (SURVEY.md 8(f) row 2)")
 
     DeriveKeyPair = GenerateKeyPair
 
-    def Decapsulate(self, sk, ct):
-        raise NotImplementedError("decapsulation is not on the accelerated path yet (SURVEY.md 8(f) row 1)")
+    def UnmarshalBinaryPrivateKey(self, buf: bytes) -> PrivateKey:
+        """kyber.go:398-407.  The H(ek) consistency check of PrivateKey.Unpack (kyber.go:226-228) is
+        evaluated on the device at first use and surfaces as ErrPrivKey from Decapsulate*."""
+        if len(buf) != self.PrivateKeySize():
+            raise ErrPrivKeySize("kem: invalid private key size")
+        return PrivateKey(self, buf)
 
+    def Decapsulate(self, sk: PrivateKey, ct: bytes) -> bytes:
+        """kyber.go:376-388 (batch of one)."""
+        if not isinstance(sk, PrivateKey) or sk._scheme is not self:
+            raise ErrTypeMismatch("kem: type mismatch")
+        if len(ct) != self.CiphertextSize():
+            raise ErrCiphertextSize("kem: invalid ciphertext size")
+        return self.DecapsulateBatch(sk, np.frombuffer(ct, dtype=np.uint8).reshape(1, -1))[0].tobytes()
+
+    def DecapsulateBatch(self, sks, cts, ss=None):
+        """Batched Decapsulate.  sks: one PrivateKey (shared) or (n, PrivateKeySize) uint8 array / CUDA
+        tensor; cts: (n, CiphertextSize).  Returns (n, 32) shared secrets (implicit rejection included)."""
+        k, dksz, ctsz = self._k, self.PrivateKeySize(), self.CiphertextSize()
+        if _is_torch(cts):
+            import torch
+            n = cts.shape[0]
+            assert cts.is_cuda and cts.is_contiguous() and tuple(cts.shape) == (n, ctsz)
+            assert not isinstance(sks, PrivateKey), "device path expects one dk per op"
+            assert sks.is_cuda and sks.is_contiguous() and tuple(sks.shape) == (n, dksz)
+            ss = torch.empty((n, 32), dtype=torch.uint8, device=cts.device) if ss is None else ss
+            status = torch.zeros((n,), dtype=torch.uint8, device=cts.device)
+            check(lib().cb200_set_stream(torch.cuda.current_stream().cuda_stream))
+            check(lib().cb200_mlkem_decaps(k, sks.data_ptr(), dksz, cts.data_ptr(), ss.data_ptr(), status.data_ptr(), n))
+            self._last_status = status
+            return ss
+        cts = np.ascontiguousarray(cts, dtype=np.uint8)
+        if cts.ndim != 2 or cts.shape[1] != ctsz:
+            raise ErrCiphertextSize("kem: invalid ciphertext size")
+        n = cts.shape[0]
+        if isinstance(sks, PrivateKey):
+            dk = np.frombuffer(sks._packed, dtype=np.uint8)
+            stride = 0
+        else:
+            dk = np.ascontiguousarray(sks, dtype=np.uint8)
+            if dk.shape != (n, dksz):
+                raise ErrPrivKeySize("kem: invalid private key size")
+            stride = dksz
+        ss = np.empty((n, 32), dtype=np.uint8) if ss is None else ss
+        status = np.zeros((n,), dtype=np.uint8)
+        try:
+            check(lib().cb200_mlkem_decaps(k, dk.ctypes.data, stride, cts.ctypes.data, ss.ctypes.data,
+                                           status.ctypes.data, n))
+        except Cb200Error as e:
+            if e.code == -5:
+                err = ErrPrivKey("kem: invalid private key")
+                err.status = status
+                raise err from None
+            raise
+        return ss
 
 _SCHEMES = {"ml-kem-768": Scheme("ML-KEM-768", 3), "ml-kem-1024": Scheme("ML-KEM-1024", 4)}
 

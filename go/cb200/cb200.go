@@ -25,6 +25,7 @@ import (
 var (
 	ErrNotInit = errors.New("cb200: not initialised / no CUDA device")
 	ErrPubKey  = errors.New("cb200: encapsulation key is not canonical") // mapped to kem.ErrPubKey by callers
+	ErrPrivKey = errors.New("cb200: H(ek) stored in the decapsulation key does not match") // kem.ErrPrivKey
 )
 
 var initOnce sync.Once
@@ -46,6 +47,8 @@ func lastErr(rc C.int) error {
 		return nil
 	case C.CB200_ERR_PUBKEY:
 		return ErrPubKey
+	case C.CB200_ERR_PRIVKEY:
+		return ErrPrivKey
 	case C.CB200_ERR_NOT_INIT:
 		return ErrNotInit
 	case C.CB200_ERR_ARG:
@@ -118,6 +121,60 @@ func MLKEMEncaps(k int, ek []byte, shared bool, seeds, ct, ss []byte) error {
 	return lastErr(C.cb200_mlkem_encaps(C.int(k), (*C.uint8_t)(unsafe.Pointer(&ek[0])), stride,
 		(*C.uint8_t)(unsafe.Pointer(&seeds[0])), (*C.uint8_t)(unsafe.Pointer(&ct[0])),
 		(*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n)))
+}
+
+// MLKEMDecaps: batched UnmarshalBinaryPrivateKey + Decapsulate (implicit rejection included).
+func MLKEMDecaps(k int, dk []byte, shared bool, ct, ss []byte) error {
+	dkSize := int(C.cb200_mlkem_private_key_size(C.int(k)))
+	ctSize := int(C.cb200_mlkem_ciphertext_size(C.int(k)))
+	n := len(ct) / ctSize
+	stride := C.size_t(dkSize)
+	if shared {
+		stride = 0
+	}
+	if len(ct) != n*ctSize || len(ss) != n*32 || (shared && len(dk) != dkSize) || (!shared && len(dk) != n*dkSize) {
+		panic("cb200: dk/ct/ss have the wrong length")
+	}
+	if n == 0 {
+		return nil
+	}
+	return lastErr(C.cb200_mlkem_decaps(C.int(k), (*C.uint8_t)(unsafe.Pointer(&dk[0])), stride,
+		(*C.uint8_t)(unsafe.Pointer(&ct[0])), (*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n)))
+}
+
+// MLDSA65Sign signs len(msgs) messages.  sk holds one packed 4032-byte key (shared) or one per message.
+// rnd == nil selects deterministic signing (sign/mldsa/mldsa65/dilithium.go:57-63).  ctx must be <= 255 bytes
+// (the caller returns sign.ErrContextTooLong otherwise).  sig receives len(msgs)*3309 bytes.
+func MLDSA65Sign(sk []byte, shared bool, msgs [][]byte, ctx, rnd, sig []byte) error {
+	n := len(msgs)
+	if n == 0 {
+		return nil
+	}
+	off := make([]uint64, n+1)
+	total := 0
+	for i, m := range msgs {
+		off[i] = uint64(total)
+		total += len(m)
+	}
+	off[n] = uint64(total)
+	blob := make([]byte, total+8)
+	for i, m := range msgs {
+		copy(blob[off[i]:], m)
+	}
+	stride := C.size_t(4032)
+	if shared {
+		stride = 0
+	}
+	var pctx, prnd *C.uint8_t
+	if len(ctx) > 0 {
+		pctx = (*C.uint8_t)(unsafe.Pointer(&ctx[0]))
+	}
+	if rnd != nil {
+		prnd = (*C.uint8_t)(unsafe.Pointer(&rnd[0]))
+	}
+	return lastErr(C.cb200_mldsa65_sign((*C.uint8_t)(unsafe.Pointer(&sk[0])), stride,
+		(*C.uint8_t)(unsafe.Pointer(&blob[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])), pctx, C.size_t(len(ctx)),
+		prnd, (*C.uint8_t)(unsafe.Pointer(&sig[0])), nil, C.size_t(n), 0, nil))
 }
 
 // PinnedBytes returns a Go slice over cudaHostAlloc'd memory: large batches should live

@@ -29,6 +29,7 @@ extern "C" {
 #define CB200_ERR_NOT_INIT (-2)
 #define CB200_ERR_PUBKEY (-3)       /* kem.ErrPubKey: ek not reduced mod q (cpapke.go:45-55); see cb200_mlkem_encaps */
 #define CB200_ERR_SIGN_ATTEMPTS (-4)/* ML-DSA: 576 attempts exhausted (sign/mldsa/mldsa65/internal/dilithium.go:372-377) */
+#define CB200_ERR_PRIVKEY (-5)      /* kem.ErrPrivKey: H(ek) inside dk does not match (kem/mlkem/mlkem768/kyber.go:226-228) */
 /* <= -100: CUDA runtime error (-100 - cudaError_t) */
 
 /* ---- lifetime ---- */
@@ -102,6 +103,15 @@ int cb200_dil_exceeds(const uint32_t *polys, uint32_t bound, uint8_t *flags, siz
  * (its ct/ss are zeroed).  Returns CB200_ERR_PUBKEY if any op failed. */
 int cb200_mlkem_encaps(int k, const uint8_t *ek, size_t ek_stride, const uint8_t *seeds, uint8_t *ct, uint8_t *ss,
                        uint8_t *status, size_t n);
+/* scheme.UnmarshalBinaryPrivateKey + Decapsulate
+ *   kem/mlkem/mlkem768/kyber.go:398-407,376-388 -> PrivateKey.Unpack :203-229, DecapsulateTo :144-184
+ *   (cpapke DecryptTo cpapke.go:113-130, re-encryption EncryptTo :137-181, implicit rejection with J = SHAKE256(z || ct)).
+ * dk: packed decapsulation key(s) (2400 / 3168 bytes); op i uses dk + i*dk_stride (0 = one key, host pointers only).
+ * ct: n x CiphertextSize; ss: n x 32.  status (optional): 2 = kem.ErrPrivKey for that op (ss zeroed).
+ * Returns CB200_ERR_PRIVKEY if any op failed. */
+int cb200_mlkem_decaps(int k, const uint8_t *dk, size_t dk_stride, const uint8_t *ct, uint8_t *ss, uint8_t *status,
+                       size_t n);
+size_t cb200_mlkem_private_key_size(int k);
 size_t cb200_mlkem_public_key_size(int k);
 size_t cb200_mlkem_ciphertext_size(int k);
 

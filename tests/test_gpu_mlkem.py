@@ -130,3 +130,45 @@ def test_device_pointers_large_batch_property(cb):
     # checksum of checksums is stable across a second run (no races in the pipeline)
     ct2, ss2 = scheme.EncapsulateBatch(eks, ms)
     assert torch.equal(ct, ct2) and torch.equal(ss, ss2)
+
+
+# ---------------------------------------------------------------- Decapsulate
+@pytest.mark.parametrize("ps", list(KS))
+def test_acvp_decaps(cb, mlkem_acvp, ps):
+    # kem/mlkem/acvp_test.go:126-165 (VAL group: one dk, 10 ciphertexts incl. modified ones -> implicit rejection)
+    from circl_b200 import mlkem
+    scheme = mlkem.ByName(ps)
+    g = mlkem_acvp["decap"][ps]
+    sk = scheme.UnmarshalBinaryPrivateKey(bytes.fromhex(g["dk"]))
+    cts = np.stack([np.frombuffer(bytes.fromhex(t["c"]), dtype=np.uint8) for t in g["tests"]])
+    ss = scheme.DecapsulateBatch(sk, cts)
+    for i, t in enumerate(g["tests"]):
+        assert ss[i].tobytes().hex().upper() == t["k"].upper(), t["tcId"]
+    assert scheme.Decapsulate(sk, cts[0].tobytes()).hex().upper() == g["tests"][0]["k"].upper()
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_encaps_decaps_roundtrip_and_rejection(cb, ps):
+    import oracle
+    from circl_b200 import mlkem
+    k = KS[ps]
+    scheme = mlkem.ByName(ps)
+    n = 3000
+    keys = [oracle.mlkem_keygen(k, _h(0, j, 64)) for j in range(8)]
+    eks = np.stack([np.frombuffer(keys[i % 8][0], dtype=np.uint8) for i in range(n)])
+    dks = np.stack([np.frombuffer(keys[i % 8][1], dtype=np.uint8) for i in range(n)])
+    ms = np.stack([np.frombuffer(_h(1, i, 32), dtype=np.uint8) for i in range(n)])
+    ct, ss = scheme.EncapsulateBatch(eks, ms)
+    assert np.array_equal(scheme.DecapsulateBatch(dks, ct), ss)          # kem round trip on the GPU alone
+    bad = ct.copy()
+    bad[::3, 5] ^= 0x40                                                   # corrupt every third ciphertext
+    got = scheme.DecapsulateBatch(dks, bad)
+    for i in list(range(0, 60)) + [n - 1]:
+        assert got[i].tobytes() == oracle.mlkem_decaps(k, keys[i % 8][1], bad[i].tobytes()), i
+    assert not np.array_equal(got[0], ss[0]) and np.array_equal(got[1], ss[1])
+    # kem.ErrPrivKey: H(ek) stored in dk does not match
+    broken = dks[:4].copy()
+    broken[2, 384 * k + 384 * k + 32 + 1] ^= 1
+    with pytest.raises(mlkem.ErrPrivKey) as ei:
+        scheme.DecapsulateBatch(broken, ct[:4])
+    assert ei.value.status.tolist() == [0, 0, 2, 0]

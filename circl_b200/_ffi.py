@@ -43,6 +43,7 @@ SYMBOLS = {
     "cb200_mldsa65_signature_size": (C.c_size_t, []),
     "cb200_mldsa65_private_key_size": (C.c_size_t, []),
     "cb200_mlkem_decaps": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cb200_mlkem_keygen": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cb200_mlkem_private_key_size": (C.c_size_t, [C.c_int]),
     "cb200_mlkem_public_key_size": (C.c_size_t, [C.c_int]),
     "cb200_mlkem_ciphertext_size": (C.c_size_t, [C.c_int]),

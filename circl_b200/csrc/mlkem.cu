@@ -156,11 +156,12 @@ constexpr int kSampleSmem = 128 * kRowWords * 4;
 //   [0, nkeys*K*K)               matrix streams, s = (i*K + j) * nkeys + key  -> A^T[key][i][j] = XOF(rho, i, j)
 //   then n*(2K+1) noise streams, s = nonce * n + op                            -> PRF(r_op, nonce)
 template <int K>
-__global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__ ek, size_t ek_stride, size_t nkeys,
+__global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__ rho0, size_t ek_stride, size_t nkeys,
                                                      const uint64_t* __restrict__ r, size_t n,
                                                      int16_t* __restrict__ A, int16_t* __restrict__ noise,
-                                                     size_t mat_blocks) {
-  using P = Params<K>;
+                                                     size_t mat_blocks, int transpose, int n_noise, int r_words) {
+  // rho0 + key*ek_stride is rho of that key; transpose = 1 derives A^T (encryption), 0 derives A (key
+  // generation, mat.go:13-29); n_noise PRF streams per op, seeded by r[op*r_words .. +4)
   uint64_t a[25];
   keccak::zero(a);
   if (blockIdx.x < mat_blocks) {
@@ -174,10 +175,11 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
     const size_t sc = live ? s : total - 1;
     const size_t key = sc % nkeys;
     const int ij = (int)(sc / nkeys), i = ij / K, j = ij % K;
-    const uint8_t* rho = ek + key * ek_stride + 384 * K;
+    const uint8_t* rho = rho0 + key * ek_stride;
 #pragma unroll
     for (int w = 0; w < 4; w++) a[w] = keccak::ld64(rho + 8 * w);
-    a[4] = (uint64_t)i | ((uint64_t)j << 8) | (0x1full << 16);  // aT.Derive(rho, transpose=true): x = i, y = j
+    // m[i][j] = XOF(rho, x, y) with (x, y) = (i, j) if transpose else (j, i)
+    a[4] = (uint64_t)(transpose ? i : j) | ((uint64_t)(transpose ? j : i) << 8) | (0x1full << 16);
     a[20] = 0x8000000000000000ull;                               // rate 168
     int16_t* row = reinterpret_cast<int16_t*>(rows + threadIdx.x * kRowWords);
     int ctr = 0;
@@ -198,15 +200,15 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
     }
   } else {
     const size_t s = (size_t)(blockIdx.x - mat_blocks) * blockDim.x + threadIdx.x;
-    if (s >= n * P::n_noise) return;
+    if (s >= n * n_noise) return;
     const size_t op = s % n;
     const int nonce = (int)(s / n);
 #pragma unroll
-    for (int w = 0; w < 4; w++) a[w] = r[4 * op + w];
+    for (int w = 0; w < 4; w++) a[w] = r[r_words * op + w];
     a[4] = (uint64_t)nonce | (0x1full << 8);
     a[16] = 0x8000000000000000ull;  // rate 136
     keccak::f1600(a);
-    cbd2_store(a, noise + (op * P::n_noise + nonce) * N);
+    cbd2_store(a, noise + (op * n_noise + nonce) * N);
   }
 }
 
@@ -668,7 +670,7 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
     {
       KernelScope ks(KID_MLKEM_SAMPLE, st);
       sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, st>>>(
-          ek + first * dk_stride, dk_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks);
+          ek + 384 * K + first * dk_stride, dk_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks, 1, P::n_noise, 4);
     }
     {
       KernelScope ks(KID_MLKEM_ENCRYPT, st);
@@ -681,6 +683,189 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
     KernelScope ks(KID_MLKEM_G, st);
     select_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(dk, dk_stride, ct, ct2, kbar, h, n, ss, status);
   }
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ------------------------------------------------------------------ 5. KeyGen
+// (rho, sigma) = SHA3-512(d || byte(K))  (pke/kyber/kyber768/kyber.go:77-86, cpapke.go:72-79); one thread per op.
+// Writes rho||sigma (8 words) to rs, rho into ek/dk, z into dk.
+template <int K>
+__global__ void __launch_bounds__(128) keygen_seed_kernel(const uint8_t* __restrict__ seed, size_t n,
+                                                          uint64_t* __restrict__ rs, uint8_t* __restrict__ ek,
+                                                          uint8_t* __restrict__ dk) {
+  using P = Params<K>;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* sd = reinterpret_cast<const uint64_t*>(seed + 64 * i);
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int j = 0; j < 4; j++) a[j] = sd[j];
+  a[4] = (uint64_t)K | (0x06ull << 8);
+  a[8] = 0x8000000000000000ull;  // SHA3-512, rate 72
+  keccak::f1600(a);
+  uint64_t* ekr = reinterpret_cast<uint64_t*>(ek + i * P::ek_bytes + 384 * K);
+  uint64_t* dkr = reinterpret_cast<uint64_t*>(dk + i * (768 * K + 96) + 384 * K + 384 * K);
+  uint64_t* dkz = reinterpret_cast<uint64_t*>(dk + i * (768 * K + 96) + 384 * K + P::ek_bytes + 32);
+#pragma unroll
+  for (int j = 0; j < 8; j++) rs[8 * i + j] = a[j];
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    ekr[j] = a[j];
+    dkr[j] = a[j];
+    dkz[j] = sd[4 + j];  // z = seed[32:64] (kem/mlkem/mlkem768/kyber.go:66-67)
+  }
+}
+
+// 32 normalised coefficients (C layout, high-half registers) -> 12 words (poly.go:106-116)
+__device__ __forceinline__ void pack12_C(const int32_t (&r)[32], uint32_t (&w)[12]) {
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    uint32_t t[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) t[j] = (uint32_t)r[8 * g + j] >> 16;
+    w[3 * g] = t[0] | (t[1] << 12) | (t[2] << 24);
+    w[3 * g + 1] = (t[2] >> 8) | (t[3] << 4) | (t[4] << 16) | (t[5] << 28);
+    w[3 * g + 2] = (t[5] >> 4) | (t[6] << 8) | (t[7] << 20);
+  }
+}
+
+// K-PKE.KeyGen arithmetic (cpapke.go:83-105): s-hat = Normalize(NTT(s)), e-hat = NTT(e),
+// t-hat[i] = Normalize(ToMont(A[i] . s-hat) + e-hat[i]); packs s-hat into dk and t-hat into ek and dk.  Octet per op.
+template <int K>
+__global__ void __launch_bounds__(kEncThreads) keygen_kernel(const int16_t* __restrict__ A, const int16_t* __restrict__ noise,
+                                                             size_t n, uint8_t* __restrict__ ek, uint8_t* __restrict__ dk,
+                                                             const kyber::TwPair* __restrict__ tw) {
+  using P = Params<K>;
+  using namespace kyber;
+  __shared__ __align__(16) uint32_t tiles[(kEncThreads / 8) * kPolyWords];
+  __shared__ uint32_t sh_store[(kEncThreads / 8) * K * 128];
+  __shared__ __align__(16) TwPair tws[128];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
+  uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
+  uint32_t* shp = sh_store + (size_t)(warp * 4 + oct) * K * 128 + v;
+  for (int i = threadIdx.x; i < 128; i += kEncThreads) tws[i] = tw[i];
+  __syncthreads();
+  const volatile TwPair* tab = tws;
+  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
+  if (base >= n) return;
+  const bool active = base + oct < n;
+  const size_t op = active ? base + oct : n - 1;
+  const uint32_t* Ap = reinterpret_cast<const uint32_t*>(A) + op * K * K * (N / 2);
+  const uint32_t* np = reinterpret_cast<const uint32_t*>(noise) + op * (2 * K) * (N / 2);
+  uint8_t* ekp = ek + op * P::ek_bytes;
+  uint8_t* dkp = dk + op * (768 * K + 96);
+  int32_t r[32];
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {  // s-hat
+    gload_S(np + j * (N / 2), v, r);
+    fwd_pass_S(r);
+    store_S(tile, v, r);
+    __syncwarp();
+    load_C(tile, v, r);
+    fwd_pass_C_smem(r, tab, v);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; c++) r[c] = csubq_hi(barrett_hi(r[c]));
+#pragma unroll
+    for (int w = 0; w < 16; w++) shp[(j * 16 + w) * 8] = pack2(r[2 * w], r[2 * w + 1]);
+    uint32_t pw[12];
+    pack12_C(r, pw);
+    if (active) {
+      uint32_t* dst = reinterpret_cast<uint32_t*>(dkp + 384 * j) + 12 * v;
+#pragma unroll
+      for (int w = 0; w < 12; w++) dst[w] = pw[w];
+    }
+  }
+#pragma unroll 1
+  for (int i = 0; i < K; i++) {
+    int32_t acc[32];
+#pragma unroll
+    for (int c = 0; c < 32; c++) acc[c] = 0;
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+      uint32_t aw[16];
+      load_words_C(Ap + (i * K + j) * (N / 2), v, aw);
+      mulhat_acc_words(acc, aw, shp + j * 128, tab, v);
+    }
+    // e-hat[i] = NTT(e[i])
+    gload_S(np + (K + i) * (N / 2), v, r);
+    fwd_pass_S(r);
+    store_S(tile, v, r);
+    __syncwarp();
+    load_C(tile, v, r);
+    fwd_pass_C_smem(r, tab, v);
+    __syncwarp();
+#pragma unroll
+    for (int c = 0; c < 32; c++) {
+      const int32_t t = mont_mul_hi(acc[c] >> 16, 1353, (int32_t)(((1353u * QINV) & 0xffffu) << 16));  // ToMont
+      r[c] = csubq_hi(barrett_hi(t + r[c]));
+    }
+    uint32_t pw[12];
+    pack12_C(r, pw);
+    if (active) {
+      uint32_t* d1 = reinterpret_cast<uint32_t*>(ekp + 384 * i) + 12 * v;
+      uint32_t* d2 = reinterpret_cast<uint32_t*>(dkp + 384 * K + 384 * i) + 12 * v;
+#pragma unroll
+      for (int w = 0; w < 12; w++) {
+        d1[w] = pw[w];
+        d2[w] = pw[w];
+      }
+    }
+  }
+}
+
+template <int K>
+static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n, cudaStream_t st, int slot) {
+  using P = Params<K>;
+  Ctx& c = ctx();
+  const size_t sub = n < kSub ? n : kSub;
+  constexpr size_t dksz = 768 * K + 96;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_rs = take(n * 64), o_h = take(n * 32), o_A = take(sub * K * K * 512), o_n = take(sub * 2 * K * 512);
+  void* base = nullptr;
+  int rc = ensure_work(slot, off, &base);
+  if (rc) return rc;
+  char* b = (char*)base;
+  uint64_t* rs = (uint64_t*)(b + o_rs);
+  uint64_t* h = (uint64_t*)(b + o_h);
+  int16_t* A = (int16_t*)(b + o_A);
+  int16_t* noise = (int16_t*)(b + o_n);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
+    attr_set = true;
+  }
+  {
+    KernelScope ks(KID_MLKEM_G, st);
+    keygen_seed_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, n, rs, ek, dk);
+  }
+  for (size_t first = 0; first < n; first += sub) {
+    const size_t cnt = (n - first < sub) ? n - first : sub;
+    const size_t mat_blocks = (cnt * K * K + 127) / 128, noise_blocks = (cnt * 2 * K + 127) / 128;
+    {  // A (not transposed) from rho = rs[0..4), s/e noise from sigma = rs[4..8)
+      KernelScope ks(KID_MLKEM_SAMPLE, st);
+      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, st>>>(
+          (const uint8_t*)(rs + 8 * first), 64, cnt, rs + 8 * first + 4, cnt, A, noise, mat_blocks, 0, 2 * K, 8);
+    }
+    {
+      KernelScope ks(KID_MLKEM_ENCRYPT, st);
+      keygen_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
+          A, noise, cnt, ek + first * P::ek_bytes, dk + first * dksz, (const kyber::TwPair*)c.kyber_tw);
+    }
+  }
+  {  // H(ek) into dk (kyber.go:69-75)
+    KernelScope ks(KID_MLKEM_HASH_EK, st);
+    hash_ek_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ek, P::ek_bytes, n, h);
+  }
+  CB200_CUDA(cudaMemcpy2DAsync(dk + 384 * K + P::ek_bytes, dksz, h, 32, 32, n, cudaMemcpyDeviceToDevice, st));
   CB200_CUDA(cudaGetLastError());
   return 0;
 }
@@ -740,7 +925,8 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
     {
       KernelScope ks(KID_MLKEM_SAMPLE, st);
       sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, st>>>(
-          ek + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise, mat_blocks);
+          ek + 384 * K + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise,
+          mat_blocks, 1, P::n_noise, 4);
     }
     {
       KernelScope ks(KID_MLKEM_ENCRYPT, st);
@@ -766,6 +952,42 @@ static int encaps_any(int k, const uint8_t* ek, size_t ek_stride, const uint8_t*
 using namespace cb200;
 
 extern "C" {
+
+int cb200_mlkem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (k != 3 && k != 4) {
+    set_error("cb200_mlkem_keygen: k must be 3 (ML-KEM-768) or 4 (ML-KEM-1024), got %d", k);
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  if (!seeds || !ek || !dk) {
+    set_error("cb200_mlkem_keygen: null pointer");
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(ek);
+  if (dev != is_device_ptr(seeds) || dev != is_device_ptr(dk)) {
+    set_error("cb200_mlkem_keygen: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  auto run = [&](const uint8_t* s_, uint8_t* e_, uint8_t* d_, size_t cnt, cudaStream_t st, int slot) {
+    return k == 3 ? mlkem::keygen_device<3>(s_, e_, d_, cnt, st, slot) : mlkem::keygen_device<4>(s_, e_, d_, cnt, st, slot);
+  };
+  if (dev) {
+    if (((uintptr_t)seeds | (uintptr_t)ek | (uintptr_t)dk) & 15) {
+      set_error("cb200_mlkem_keygen: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    return run(seeds, ek, dk, n, ctx().cur, 3);
+  }
+  std::vector<Buf> bufs(3);
+  bufs[0] = Buf{seeds, nullptr, 64, false, 0};
+  bufs[1] = Buf{nullptr, ek, cb200_mlkem_public_key_size(k), false, 0};
+  bufs[2] = Buf{nullptr, dk, 768u * k + 96, false, 0};
+  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+    return run((const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
+  });
+}
 
 size_t cb200_mlkem_private_key_size(int k) { return (k >= 2 && k <= 4) ? 768u * k + 96 : 0; }
 

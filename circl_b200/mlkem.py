@@ -201,11 +201,39 @@ class Scheme:
             err.status = st.cpu().numpy()
             raise err
 
-    # ---- outside the accelerated path ----
-    def GenerateKeyPair(self):
-        raise NotImplementedError("key generation is not on the accelerated path yet (SURVEY.md 8(f) row 2)")
+    # ---- key generation ----
+    def DeriveKeyPair(self, seed: bytes):
+        """kyber.go:337-346: deterministic key pair from a 64-byte seed d || z (batch of one)."""
+        if len(seed) != self.SeedSize():
+            raise ValueError("kem: invalid seed size")  # the reference panics with kem.ErrSeedSize
+        ek, dk = self.DeriveKeyPairBatch(np.frombuffer(seed, dtype=np.uint8).reshape(1, 64))
+        return PublicKey(self, ek[0].tobytes()), PrivateKey(self, dk[0].tobytes())
 
-    DeriveKeyPair = GenerateKeyPair
+    def GenerateKeyPair(self):
+        """kyber.go:281-283: random seed from the OS, then DeriveKeyPair."""
+        import os
+        return self.DeriveKeyPair(os.urandom(self.SeedSize()))
+
+    def DeriveKeyPairBatch(self, seeds):
+        """seeds: (n, 64) uint8 array or CUDA tensor -> (ek (n, PublicKeySize), dk (n, PrivateKeySize)) packed keys."""
+        k, eksz, dksz = self._k, self.PublicKeySize(), self.PrivateKeySize()
+        if _is_torch(seeds):
+            import torch
+            n = seeds.shape[0]
+            assert seeds.is_cuda and seeds.is_contiguous() and tuple(seeds.shape) == (n, 64)
+            ek = torch.empty((n, eksz), dtype=torch.uint8, device=seeds.device)
+            dk = torch.empty((n, dksz), dtype=torch.uint8, device=seeds.device)
+            check(lib().cb200_set_stream(torch.cuda.current_stream().cuda_stream))
+            check(lib().cb200_mlkem_keygen(k, seeds.data_ptr(), ek.data_ptr(), dk.data_ptr(), n))
+            return ek, dk
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
+        if seeds.ndim != 2 or seeds.shape[1] != 64:
+            raise ValueError("kem: invalid seed size")
+        n = seeds.shape[0]
+        ek = np.empty((n, eksz), dtype=np.uint8)
+        dk = np.empty((n, dksz), dtype=np.uint8)
+        check(lib().cb200_mlkem_keygen(k, seeds.ctypes.data, ek.ctypes.data, dk.ctypes.data, n))
+        return ek, dk
 
     def UnmarshalBinaryPrivateKey(self, buf: bytes) -> PrivateKey:
         """kyber.go:398-407.  The H(ek) consistency check of PrivateKey.Unpack (kyber.go:226-228) is

@@ -111,6 +111,10 @@ int cb200_mlkem_encaps(int k, const uint8_t *ek, size_t ek_stride, const uint8_t
  * Returns CB200_ERR_PRIVKEY if any op failed. */
 int cb200_mlkem_decaps(int k, const uint8_t *dk, size_t dk_stride, const uint8_t *ct, uint8_t *ss, uint8_t *status,
                        size_t n);
+/* scheme.DeriveKeyPair   kem/mlkem/mlkem768/kyber.go:337-346 -> NewKeyFromSeed :57-78 ->
+ *   cpapke.NewKeyFromSeedMLKEM pke/kyber/kyber768/kyber.go:77-86 -> internal/cpapke.go:66-110.
+ * seeds: n x 64 (d || z); ek: n x PublicKeySize; dk: n x PrivateKeySize (packed, = MarshalBinary). */
+int cb200_mlkem_keygen(int k, const uint8_t *seeds, uint8_t *ek, uint8_t *dk, size_t n);
 size_t cb200_mlkem_private_key_size(int k);
 size_t cb200_mlkem_public_key_size(int k);
 size_t cb200_mlkem_ciphertext_size(int k);

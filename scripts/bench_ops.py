@@ -1,0 +1,59 @@
+"""Device-resident timings of the secondary entry points (CUDA events, >= 3 warm-ups, inputs > L2).
+Writes one JSON object; the headline contract lives in bench.py."""
+import json
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+import circl_b200
+from circl_b200 import dilithium as dl, kyber, mlkem
+import bench as B
+
+circl_b200.init(0)
+res = {}
+
+
+def timed(fn, steps=5, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / steps
+
+
+for name, k, log2 in (("ML-KEM-768", 3, 20), ("ML-KEM-1024", 4, 20)):
+    scheme = mlkem.ByName(name)
+    n = 1 << log2
+    g = torch.Generator(device="cuda").manual_seed(1)
+    seeds = torch.randint(0, 256, (n, 64), generator=g, device="cuda", dtype=torch.uint8)
+    ms = torch.randint(0, 256, (n, 32), generator=g, device="cuda", dtype=torch.uint8)
+    t = timed(lambda: scheme.DeriveKeyPairBatch(seeds), steps=3)
+    ek, dk = scheme.DeriveKeyPairBatch(seeds)
+    res[f"{name} keygen"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+    ct = torch.empty((n, scheme.CiphertextSize()), dtype=torch.uint8, device="cuda")
+    ss = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    t = timed(lambda: scheme.EncapsulateBatch(ek, ms, ct=ct, ss=ss))
+    res[f"{name} encaps (per-op ek)"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+    pk0 = scheme.UnmarshalBinaryPublicKey(ek[0].cpu().numpy().tobytes())
+    t = timed(lambda: scheme.EncapsulateBatch(pk0, ms, ct=ct, ss=ss))
+    res[f"{name} encaps (shared ek)"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+    scheme.EncapsulateBatch(ek, ms, ct=ct, ss=ss)
+    ss2 = torch.empty_like(ss)
+    t = timed(lambda: scheme.DecapsulateBatch(dk, ct, ss=ss2), steps=3)
+    res[f"{name} decaps"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3), "roundtrip_ok": bool(torch.equal(ss, ss2))}
+    del seeds, ms, ek, dk, ct, ss, ss2
+    torch.cuda.empty_cache()
+
+n = 1 << 19
+e = torch.randint(0, 8380417, (n, 256), device="cuda", dtype=torch.int32)
+for label, fn in (("Dilithium NTT", lambda: dl.ntt_(e)), ("Dilithium InvNTT", lambda: dl.inv_ntt_(e))):
+    t = timed(fn, steps=10)
+    res[label] = {"n": n, "ms": t, "per_s": n / (t * 1e-3), "GBps": n * 2048 / (t * 1e-3) / 1e9}
+print(json.dumps(res, indent=1))

@@ -172,3 +172,38 @@ def test_encaps_decaps_roundtrip_and_rejection(cb, ps):
     with pytest.raises(mlkem.ErrPrivKey) as ei:
         scheme.DecapsulateBatch(broken, ct[:4])
     assert ei.value.status.tolist() == [0, 0, 2, 0]
+
+
+# ---------------------------------------------------------------- KeyGen
+@pytest.mark.parametrize("ps", list(KS))
+def test_acvp_keygen(cb, mlkem_acvp, ps):
+    # kem/mlkem/acvp_test.go:41-82: seed = d || z -> ek, dk
+    from circl_b200 import mlkem
+    scheme = mlkem.ByName(ps)
+    tests = mlkem_acvp["keygen"][ps]
+    seeds = np.stack([np.frombuffer(bytes.fromhex(t["d"]) + bytes.fromhex(t["z"]), dtype=np.uint8) for t in tests])
+    ek, dk = scheme.DeriveKeyPairBatch(seeds)
+    for i, t in enumerate(tests):
+        assert ek[i].tobytes().hex().upper() == t["ek"].upper(), t["tcId"]
+        assert dk[i].tobytes().hex().upper() == t["dk"].upper(), t["tcId"]
+    pk, sk = scheme.DeriveKeyPair(seeds[0].tobytes())
+    assert pk.MarshalBinary() == ek[0].tobytes() and sk.MarshalBinary() == dk[0].tobytes()
+    assert sk.Public().Equal(pk)
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_keygen_encaps_decaps_all_on_gpu(cb, ps):
+    """kem/schemes/schemes_test.go:53 style API round trip, 10000 key pairs, nothing but the GPU path."""
+    import oracle
+    from circl_b200 import mlkem
+    k = KS[ps]
+    scheme = mlkem.ByName(ps)
+    n = 10000
+    seeds = np.frombuffer(hashlib.shake_256(b"keygen" + ps.encode()).digest(64 * n), dtype=np.uint8).reshape(n, 64)
+    ek, dk = scheme.DeriveKeyPairBatch(seeds)
+    for i in range(0, n, 997):
+        wek, wdk = oracle.mlkem_keygen(k, seeds[i].tobytes())
+        assert ek[i].tobytes() == wek and dk[i].tobytes() == wdk
+    ms = np.frombuffer(hashlib.shake_256(b"m").digest(32 * n), dtype=np.uint8).reshape(n, 32)
+    ct, ss = scheme.EncapsulateBatch(ek, ms)
+    assert np.array_equal(scheme.DecapsulateBatch(dk, ct), ss)

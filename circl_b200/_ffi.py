@@ -40,6 +40,10 @@ SYMBOLS = {
                                      C.c_void_p, C.c_size_t]),
     "cb200_mldsa65_sign": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_void_p]),
+    "cb200_mldsa65_verify": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p,
+                                       C.c_void_p, C.c_size_t, C.c_int]),
+    "cb200_mldsa65_keygen": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cb200_mldsa65_public_key_size": (C.c_size_t, []),
     "cb200_mldsa65_signature_size": (C.c_size_t, []),
     "cb200_mldsa65_private_key_size": (C.c_size_t, []),
     "cb200_mlkem_decaps": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

@@ -601,6 +601,569 @@ __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restric
   }
 }
 
+__global__ void iota_kernel(uint32_t* a, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) a[i] = (uint32_t)i;
+}
+
+// ================================================================== Verify
+// internal/dilithium.go:273-332.  pk = rho (32) || t1 (6 x 320); sig = c~ (48) || z (5 x 640) || hints (61).
+constexpr int PK_BYTES = 1952, POLY_T1 = 320;
+
+// tr = H(pk), mu = H(tr || M'), c = SampleInBall(c~), hint unpacking with the validity rules of
+// UnpackHint (internal/pack.go:113-140).  One thread per op.
+__global__ void __launch_bounds__(128) verify_prep_kernel(const uint8_t* __restrict__ pk, size_t pk_stride,
+                                                          const uint8_t* __restrict__ msgs,
+                                                          const uint64_t* __restrict__ msg_off,
+                                                          const uint8_t* __restrict__ ctxstr, int ctxlen, int internal,
+                                                          const uint8_t* __restrict__ sig, size_t n,
+                                                          uint64_t* __restrict__ mu, uint32_t* __restrict__ cpoly,
+                                                          uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags) {
+  const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= n) return;
+  const uint8_t* pkp = pk + op * pk_stride;
+  const uint8_t* sg = sig + op * (size_t)SIG_BYTES;
+  uint64_t a[25];
+  keccak::zero(a);
+  {  // tr = SHAKE256(pk, 64): 244 words = 14 full blocks + 6 words (dilithium.go:122-125)
+    const uint64_t* pw = reinterpret_cast<const uint64_t*>(pkp);
+#pragma unroll 1
+    for (int b = 0; b < 14; b++) {
+#pragma unroll
+      for (int w = 0; w < 17; w++) a[w] ^= __ldg(pw + 17 * b + w);
+      keccak::f1600(a);
+    }
+#pragma unroll
+    for (int w = 0; w < 6; w++) a[w] ^= __ldg(pw + 238 + w);
+    a[6] ^= 0x1f;
+    a[16] ^= 0x8000000000000000ull;
+    keccak::f1600(a);
+  }
+  ByteSponge sp;
+  sp.init();
+  for (int i = 0; i < 64; i++) sp.put((uint8_t)(a[i >> 3] >> (8 * (i & 7))));
+  if (!internal) {
+    sp.put(0);
+    sp.put((uint8_t)ctxlen);
+    for (int i = 0; i < ctxlen; i++) sp.put(ctxstr[i]);
+  }
+  for (uint64_t i = msg_off[op]; i < msg_off[op + 1]; i++) sp.put(msgs[i]);
+  sp.finish();
+#pragma unroll
+  for (int i = 0; i < 8; i++) mu[8 * op + i] = sp.a[i];
+  // c = SampleInBall(sig.c)
+  keccak::zero(a);
+  for (int i = 0; i < CTILDE; i++) a[i >> 3] |= (uint64_t)sg[i] << (8 * (i & 7));
+  a[6] = 0x1f;
+  a[16] = 0x8000000000000000ull;
+  keccak::f1600(a);
+  uint64_t buf[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) buf[i] = a[i];
+  uint64_t signs = buf[0];
+  int off = 8;
+  uint32_t* c = cpoly + op * N;
+  for (int i = 0; i < N; i += 4) *reinterpret_cast<uint4*>(c + i) = make_uint4(0, 0, 0, 0);
+  for (int i = N - TAU; i < N; i++) {
+    uint32_t b;
+    for (;;) {
+      if (off >= 136) {
+        keccak::f1600(a);
+#pragma unroll
+        for (int q = 0; q < 17; q++) buf[q] = a[q];
+        off = 0;
+      }
+      b = (uint32_t)(buf[off >> 3] >> (8 * (off & 7))) & 0xff;
+      off++;
+      if (b <= (uint32_t)i) break;
+    }
+    c[i] = c[b];
+    c[b] = (signs & 1) ? Q - 1 : 1;
+    signs >>= 1;
+  }
+  // UnpackHint
+  uint32_t* hb = hintbits + 48 * op;
+  for (int i = 0; i < 48; i++) hb[i] = 0;
+  const uint8_t* hp = sg + CTILDE + L * POLY_Z;
+  bool ok = true;
+  int prev = 0;
+  for (int i = 0; i < K && ok; i++) {
+    const int sop = hp[OMEGA + i];
+    if (sop < prev || sop > OMEGA) {
+      ok = false;
+      break;
+    }
+    for (int j = prev; j < sop; j++) {
+      if (j > prev && hp[j] <= hp[j - 1]) {
+        ok = false;
+        break;
+      }
+      hb[8 * i + (hp[j] >> 5)] |= 1u << (hp[j] & 31);
+    }
+    prev = sop;
+  }
+  for (int j = prev; j < OMEGA && ok; j++)
+    if (hp[j] != 0) ok = false;
+  flags[op] = ok ? 0u : 1u;
+}
+
+// zh[j] = NTT(UnpackLeGamma1(sig.z[j])), reject if z exceeds gamma1 - beta (dilithium.go:87-90): octet per (op, j)
+__global__ void __launch_bounds__(128) verify_z_kernel(const uint8_t* __restrict__ sig, size_t n, uint32_t* __restrict__ zh,
+                                                       uint32_t* __restrict__ flags, const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const OctetCtx o = octet_ctx(tiles);
+  const unsigned octmask = 0xffu << (8 * o.oct);
+  const size_t total = n * L, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= total) return;
+  const bool active = base + o.oct < total;
+  const size_t u = active ? base + o.oct : total - 1;
+  const size_t op = u % n;
+  const int j = (int)(u / n);
+  const uint8_t* zb = sig + op * (size_t)SIG_BYTES + CTILDE + POLY_Z * j + 80 * o.v;  // unaligned: byte loads
+  uint32_t r[32];
+  bool reject = false;
+#pragma unroll
+  for (int p = 0; p < 16; p++) {  // 5 bytes -> 2 coefficients (internal/pack.go:177-195)
+    const uint32_t b0 = zb[5 * p], b1 = zb[5 * p + 1], b2 = zb[5 * p + 2], b3 = zb[5 * p + 3], b4 = zb[5 * p + 4];
+    uint32_t p0 = GAMMA1 - (b0 | (b1 << 8) | ((b2 & 0xf) << 16));
+    uint32_t p1 = GAMMA1 - ((b2 >> 4) | (b3 << 4) | (b4 << 12));
+    p0 += (uint32_t)((int32_t)p0 >> 31) & Q;
+    p1 += (uint32_t)((int32_t)p1 >> 31) & Q;
+    reject |= exceeds1(p0, GAMMA1 - BETA) | exceeds1(p1, GAMMA1 - BETA);
+    r[2 * p] = p0;
+    r[2 * p + 1] = p1;
+  }
+  c_to_s(r, o.tile, o.v);
+  LaneTw t;
+  load_lane_tw_fwd(t, zetas, o.v);
+  ntt_octet(r, o.tile, o.v, t);
+  if (active) gstore_C(zh + (op * L + j) * N, o.v, r);
+  reject = __any_sync(octmask, reject);
+  if (reject && active && o.v == 0) atomicOr(flags + op, 1u);
+}
+
+// w1' = UseHint(InvNTT(A z - c t1 2^d), h), packed (dilithium.go:297-316, rounding.go:98-135): octet per (op, i)
+__global__ void __launch_bounds__(128) verify_w_kernel(const uint8_t* __restrict__ pk, size_t pk_stride, int key_shared,
+                                                       const uint32_t* __restrict__ A, const uint32_t* __restrict__ zh,
+                                                       const uint32_t* __restrict__ cpoly,
+                                                       const uint32_t* __restrict__ hintbits, size_t n,
+                                                       uint8_t* __restrict__ w1p, const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  __shared__ uint32_t izs[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) izs[i] = zetas[256 + i];
+  __syncthreads();
+  const OctetCtx o = octet_ctx(tiles);
+  const size_t total = n * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= total) return;
+  const bool active = base + o.oct < total;
+  const size_t u = active ? base + o.oct : total - 1;
+  const size_t op = u % n;
+  const int i = (int)(u / n);
+  // t1[i] * 2^d, NTT  (dilithium.go:299-300); t1: 10-bit fields, 32 coefficients = 40 bytes = 10 words
+  uint32_t r[32];
+  {
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(pk + op * pk_stride + 32 + POLY_T1 * i + 40 * o.v);
+    uint32_t w[11];
+#pragma unroll
+    for (int q = 0; q < 10; q++) w[q] = __ldg(src + q);
+    w[10] = 0;
+#pragma unroll
+    for (int q = 0; q < 32; q++) {
+      const int bit = 10 * q, wi = bit >> 5, sh = bit & 31;
+      uint32_t f = w[wi] >> sh;
+      if (sh > 22) f |= w[wi + 1] << (32 - sh);
+      r[q] = (f & 0x3ff) << 13;
+    }
+  }
+  c_to_s(r, o.tile, o.v);
+  {
+    LaneTw t;
+    load_lane_tw_fwd(t, zetas, o.v);
+    ntt_octet(r, o.tile, o.v, t);
+  }
+  // Az[i] - c-hat * that, ReduceLe2Q (C layout)
+  const uint32_t* Ai = A + ((key_shared ? 0 : op) * (K * L) + i * L) * N;
+  const uint4* cp = reinterpret_cast<const uint4*>(cpoly + op * N + 32 * o.v);
+#pragma unroll
+  for (int c = 0; c < 8; c++) {
+    const uint4 ch = cp[c];
+    r[4 * c] = 2 * Q - mont_mul(r[4 * c], ch.x);
+    r[4 * c + 1] = 2 * Q - mont_mul(r[4 * c + 1], ch.y);
+    r[4 * c + 2] = 2 * Q - mont_mul(r[4 * c + 2], ch.z);
+    r[4 * c + 3] = 2 * Q - mont_mul(r[4 * c + 3], ch.w);
+  }
+#pragma unroll 1
+  for (int j = 0; j < L; j++) {
+    const uint4* ap = reinterpret_cast<const uint4*>(Ai + j * N + 32 * o.v);
+    const uint4* zp = reinterpret_cast<const uint4*>(zh + (op * L + j) * N + 32 * o.v);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const uint4 x = __ldg(ap + c), z = zp[c];
+      r[4 * c] += mont_mul(x.x, z.x);
+      r[4 * c + 1] += mont_mul(x.y, z.y);
+      r[4 * c + 2] += mont_mul(x.z, z.z);
+      r[4 * c + 3] += mont_mul(x.w, z.w);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c++) r[c] = reduce_le2q(r[c]);
+  invntt_octet_smem(r, o.tile, o.v, izs);  // -> S layout
+  uint8_t* w1b = w1p + op * (K * POLY_W1) + i * POLY_W1;
+  const uint32_t* hb = hintbits + 48 * op + 8 * i;
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    const uint32_t hbits = (hb[s >> 1] >> (16 * (s & 1) + 2 * o.v)) & 3;
+    uint32_t q0, h0, q1, h1;
+    decompose(le2q_modq(r[2 * s]), q0, h0);
+    decompose(le2q_modq(r[2 * s + 1]), q1, h1);
+    if (hbits & 1) h0 = (q0 > Q) ? ((h0 + 1) & 15) : ((h0 - 1) & 15);
+    if (hbits & 2) h1 = (q1 > Q) ? ((h1 + 1) & 15) : ((h1 - 1) & 15);
+    if (active) w1b[8 * s + o.v] = (uint8_t)(h0 | (h1 << 4));
+  }
+}
+
+// ok = valid && (c~ == H(mu || w1')) (dilithium.go:318-331): thread per op
+__global__ void __launch_bounds__(128) verify_final_kernel(const uint8_t* __restrict__ sig, const uint64_t* __restrict__ mu,
+                                                           const uint8_t* __restrict__ w1p,
+                                                           const uint32_t* __restrict__ flags, size_t n,
+                                                           uint8_t* __restrict__ okout) {
+  const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= n) return;
+  uint64_t a[25];
+  keccak::zero(a);
+  const uint64_t* w1w = reinterpret_cast<const uint64_t*>(w1p + op * (K * POLY_W1));
+#pragma unroll 1
+  for (int b = 0; b < 6; b++) {
+#pragma unroll
+    for (int w = 0; w < 17; w++) {
+      const int k = 17 * b + w;
+      a[w] ^= (k < 8) ? mu[8 * op + k] : w1w[k - 8];
+    }
+    keccak::f1600(a);
+  }
+  a[0] ^= w1w[94];
+  a[1] ^= w1w[95];
+  a[2] ^= 0x1f;
+  a[16] ^= 0x8000000000000000ull;
+  keccak::f1600(a);
+  const uint8_t* sg = sig + op * (size_t)SIG_BYTES;
+  bool same = true;
+  for (int i = 0; i < CTILDE; i++) same &= sg[i] == (uint8_t)(a[i >> 3] >> (8 * (i & 7)));
+  okout[op] = (same && flags[op] == 0) ? 1 : 0;
+}
+
+static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off,
+                         const uint8_t* ctxstr, int ctxlen, const uint8_t* sig, uint8_t* okout, size_t n, int internal,
+                         cudaStream_t st, int slot) {
+  Ctx& c = ctx();
+  const bool shared = pk_stride == 0;
+  const size_t nkeys = shared ? 1 : n;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t oA = take(nkeys * K * L * 1024), oMu = take(n * 64), oZh = take(n * L * 1024), oC = take(n * 1024),
+               oHb = take(n * 48 * 4), oFl = take(n * 4), oW1 = take(n * K * POLY_W1), oAct = take(n * 4);
+  void* base = nullptr;
+  int rc = ensure_work(slot, off, &base);
+  if (rc) return rc;
+  char* b = (char*)base;
+  uint32_t* A = (uint32_t*)(b + oA);
+  uint64_t* mu = (uint64_t*)(b + oMu);
+  uint32_t* zh = (uint32_t*)(b + oZh);
+  uint32_t* cp = (uint32_t*)(b + oC);
+  uint32_t* hb = (uint32_t*)(b + oHb);
+  uint32_t* fl = (uint32_t*)(b + oFl);
+  uint8_t* w1p = (uint8_t*)(b + oW1);
+  uint32_t* act = (uint32_t*)(b + oAct);
+  const uint32_t* zetas = (const uint32_t*)c.dil_tw;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    attr_set = true;
+  }
+  auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
+  {
+    KernelScope ks(KID_MLDSA_EXPAND, st);  // ExpandA(rho): rho is the first 32 bytes of pk
+    expand_a_kernel<<<blocks(nkeys * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(pk, pk_stride,
+                                                                                                        nkeys, A);
+  }
+  {
+    KernelScope ks(KID_MLDSA_MU, st);
+    verify_prep_kernel<<<blocks(n, 128), 128, 0, st>>>(pk, pk_stride, msgs, msg_off, ctxstr, ctxlen, internal, sig, n, mu,
+                                                       cp, hb, fl);
+  }
+  {
+    KernelScope ks(KID_MLDSA_W, st);
+    verify_z_kernel<<<blocks(n * L, 16), 128, 0, st>>>(sig, n, zh, fl, zetas);
+  }
+  {
+    KernelScope ks(KID_MLDSA_COMPACT, st);
+    iota_kernel<<<blocks(n, 256), 256, 0, st>>>(act, n);
+  }
+  {
+    KernelScope ks(KID_MLDSA_RESPONSE, st);
+    cntt_kernel<<<blocks(n, 16), 128, 0, st>>>(act, n, cp, zetas);
+  }
+  {
+    KernelScope ks(KID_MLDSA_W, st);
+    verify_w_kernel<<<blocks(n * K, 16), 128, 0, st>>>(pk, pk_stride, shared ? 1 : 0, A, zh, cp, hb, n, w1p, zetas);
+  }
+  {
+    KernelScope ks(KID_MLDSA_CHALLENGE, st);
+    verify_final_kernel<<<blocks(n, 128), 128, 0, st>>>(sig, mu, w1p, fl, n, okout);
+  }
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// ================================================================== KeyGen
+// NewKeyFromSeed, internal/dilithium.go:181-241 (+ computeT0andT1 :253-267).
+// (rho, rho', key) = SHAKE256(seed || K || L, 128); thread per op
+__global__ void __launch_bounds__(128) kg_seed_kernel(const uint8_t* __restrict__ seed, size_t n, uint8_t* __restrict__ pk,
+                                                      uint8_t* __restrict__ sk, uint64_t* __restrict__ sseed) {
+  const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= n) return;
+  const uint64_t* sd = reinterpret_cast<const uint64_t*>(seed + 32 * op);
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int i = 0; i < 4; i++) a[i] = sd[i];
+  a[4] = (uint64_t)K | ((uint64_t)L << 8) | (0x1full << 16);
+  a[16] = 0x8000000000000000ull;
+  keccak::f1600(a);
+  uint64_t* pkw = reinterpret_cast<uint64_t*>(pk + op * (size_t)PK_BYTES);
+  uint64_t* skw = reinterpret_cast<uint64_t*>(sk + op * (size_t)SK_BYTES);
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    pkw[i] = a[i];       // rho
+    skw[i] = a[i];
+    skw[4 + i] = a[12 + i];  // key = eSeed[96:128]
+  }
+#pragma unroll
+  for (int i = 0; i < 8; i++) sseed[8 * op + i] = a[4 + i];  // rho' = eSeed[32:96]
+}
+
+// s1, s2 = PolyDeriveUniformLeqEta (sample.go:129-181, eta = 4): thread per (op, poly); the accepted nibbles
+// are at once the PackLeqEta image (internal/pack.go:13-20), so the packed key is written here too.
+__global__ void __launch_bounds__(kExpThreads) kg_eta_kernel(const uint64_t* __restrict__ sseed, size_t n,
+                                                             uint32_t* __restrict__ spoly, uint8_t* __restrict__ sk) {
+  extern __shared__ __align__(16) uint32_t rows[];
+  const size_t s0 = (size_t)blockIdx.x * blockDim.x, total = n * (L + K);
+  const size_t s = s0 + threadIdx.x;
+  const size_t sc = s < total ? s : total - 1;
+  const size_t op = sc % n;
+  const int p = (int)(sc / n);
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int w = 0; w < 8; w++) a[w] = sseed[8 * op + w];
+  a[8] = (uint64_t)p | (0x1full << 16);  // nonce = p (s1: 0..L-1, s2: L..L+K-1), little endian 16 bit
+  a[16] = 0x8000000000000000ull;
+  uint32_t* row = rows + threadIdx.x * kExpRow;
+  int ctr = 0;
+  do {
+    keccak::f1600(a);
+#pragma unroll
+    for (int w = 0; w < 17; w++) {
+      const uint64_t x = a[w];
+#pragma unroll
+      for (int q = 0; q < 16; q++) {
+        const uint32_t t = (uint32_t)(x >> (4 * q)) & 15;
+        row[ctr] = t;  // the nibble itself; Q + eta - t is formed on the way out
+        ctr += (t <= 2 * ETA && ctr < N);
+      }
+    }
+  } while (ctr < N);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int q = warp; q < kExpThreads; q += kExpThreads / 32) {
+    const size_t sp = s0 + q;
+    if (sp >= total) break;
+    const size_t qop = sp % n;
+    const int qp = (int)(sp / n);
+    uint32_t* dst = spoly + (qop * (L + K) + qp) * N;
+    uint8_t* pb = sk + qop * (size_t)SK_BYTES + OFF_S1 + 128 * qp;
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+      const uint32_t t0 = rows[q * kExpRow + 64 * w + 2 * lane], t1 = rows[q * kExpRow + 64 * w + 2 * lane + 1];
+      *reinterpret_cast<uint2*>(dst + 64 * w + 2 * lane) = make_uint2(Q + ETA - t0, Q + ETA - t1);
+      pb[32 * w + lane] = (uint8_t)(t0 | (t1 << 4));
+    }
+  }
+}
+
+// s1h = NTT(s1): octet per (op, j)
+__global__ void __launch_bounds__(128) kg_s1ntt_kernel(const uint32_t* __restrict__ spoly, size_t n, uint32_t* __restrict__ s1h,
+                                                       const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const OctetCtx o = octet_ctx(tiles);
+  const size_t total = n * L, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= total) return;
+  const bool active = base + o.oct < total;
+  const size_t u = active ? base + o.oct : total - 1;
+  const size_t op = u % n;
+  const int j = (int)(u / n);
+  uint32_t r[32];
+  gload_S(spoly + (op * (L + K) + j) * N, o.v, r);
+  LaneTw t;
+  load_lane_tw_fwd(t, zetas, o.v);
+  ntt_octet(r, o.tile, o.v, t);
+  if (active) gstore_C(s1h + (op * L + j) * N, o.v, r);
+}
+
+// t = Normalize(InvNTT(ReduceLe2Q(A[i] . s1h)) + s2[i]); Power2Round; PackT1 -> pk, PackT0 -> sk: octet per (op, i)
+__global__ void __launch_bounds__(128) kg_t_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ s1h,
+                                                   const uint32_t* __restrict__ spoly, size_t n, uint8_t* __restrict__ pk,
+                                                   uint8_t* __restrict__ sk, const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const OctetCtx o = octet_ctx(tiles);
+  const size_t total = n * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= total) return;
+  const bool active = base + o.oct < total;
+  const size_t u = active ? base + o.oct : total - 1;
+  const size_t op = u % n;
+  const int i = (int)(u / n);
+  const uint32_t* Ai = A + (op * (K * L) + i * L) * N;
+  uint32_t r[32];
+#pragma unroll
+  for (int c = 0; c < 32; c++) r[c] = 0;
+#pragma unroll 1
+  for (int j = 0; j < L; j++) {
+    const uint4* ap = reinterpret_cast<const uint4*>(Ai + j * N + 32 * o.v);
+    const uint4* sp = reinterpret_cast<const uint4*>(s1h + (op * L + j) * N + 32 * o.v);
+#pragma unroll
+    for (int c = 0; c < 8; c++) {
+      const uint4 x = __ldg(ap + c), z = sp[c];
+      r[4 * c] += mont_mul(x.x, z.x);
+      r[4 * c + 1] += mont_mul(x.y, z.y);
+      r[4 * c + 2] += mont_mul(x.z, z.z);
+      r[4 * c + 3] += mont_mul(x.w, z.w);
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 32; c++) r[c] = reduce_le2q(r[c]);
+  LaneTw t;
+  load_lane_tw_inv(t, zetas + 256, o.v);
+  invntt_octet(r, o.tile, o.v, t);  // S layout
+  const uint32_t* s2 = spoly + (op * (L + K) + L + i) * N;
+#pragma unroll
+  for (int s = 0; s < 16; s++) {
+    const uint2 e = *reinterpret_cast<const uint2*>(s2 + 16 * s + 2 * o.v);
+    r[2 * s] = modq(r[2 * s] + e.x);
+    r[2 * s + 1] = modq(r[2 * s + 1] + e.y);
+  }
+  s_to_c(r, o.tile, o.v);
+  // Power2Round (field.go:35-49), PackT1 (pack.go:88-100): 10 words, PackT0 (pack.go:23-54): 13 words
+  uint64_t acc1 = 0, acc0 = 0;
+  int b1 = 0, b0 = 0, o1 = 0, o0 = 0;
+  uint32_t* d1 = reinterpret_cast<uint32_t*>(pk + op * (size_t)PK_BYTES + 32 + POLY_T1 * i) + 10 * o.v;
+  uint32_t* d0 = reinterpret_cast<uint32_t*>(sk + op * (size_t)SK_BYTES + OFF_T0 + 416 * i) + 13 * o.v;
+#pragma unroll
+  for (int c = 0; c < 32; c++) {
+    const uint32_t a = r[c];
+    uint32_t a0 = a & 0x1fff;
+    a0 -= (1u << 12) + 1;
+    a0 += (uint32_t)((int32_t)a0 >> 31) & (1u << 13);
+    a0 -= (1u << 12) - 1;
+    const uint32_t a1 = (a - a0) >> 13;
+    acc1 |= (uint64_t)(a1 & 0x3ff) << b1;
+    b1 += 10;
+    if (b1 >= 32) {
+      if (active) d1[o1] = (uint32_t)acc1;
+      o1++;
+      acc1 >>= 32;
+      b1 -= 32;
+    }
+    acc0 |= (uint64_t)(((1u << 12) - a0) & 0x1fff) << b0;  // Q + 2^12 - (Q + a0)
+    b0 += 13;
+    if (b0 >= 32) {
+      if (active) d0[o0] = (uint32_t)acc0;
+      o0++;
+      acc0 >>= 32;
+      b0 -= 32;
+    }
+  }
+}
+
+// tr = SHAKE256(pk, 64) -> sk[64:128] (dilithium.go:233-236): thread per op
+__global__ void __launch_bounds__(128) kg_tr_kernel(const uint8_t* __restrict__ pk, size_t n, uint8_t* __restrict__ sk) {
+  const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (op >= n) return;
+  const uint64_t* pw = reinterpret_cast<const uint64_t*>(pk + op * (size_t)PK_BYTES);
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll 1
+  for (int b = 0; b < 14; b++) {
+#pragma unroll
+    for (int w = 0; w < 17; w++) a[w] ^= pw[17 * b + w];
+    keccak::f1600(a);
+  }
+#pragma unroll
+  for (int w = 0; w < 6; w++) a[w] ^= pw[238 + w];
+  a[6] ^= 0x1f;
+  a[16] ^= 0x8000000000000000ull;
+  keccak::f1600(a);
+  uint64_t* tr = reinterpret_cast<uint64_t*>(sk + op * (size_t)SK_BYTES + OFF_TR);
+#pragma unroll
+  for (int i = 0; i < 8; i++) tr[i] = a[i];
+}
+
+static int keygen_device(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t n, cudaStream_t st, int slot) {
+  Ctx& c = ctx();
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t oA = take(n * K * L * 1024), oSs = take(n * 64), oSp = take(n * (L + K) * 1024), oSh = take(n * L * 1024);
+  void* base = nullptr;
+  int rc = ensure_work(slot, off, &base);
+  if (rc) return rc;
+  char* b = (char*)base;
+  uint32_t* A = (uint32_t*)(b + oA);
+  uint64_t* sseed = (uint64_t*)(b + oSs);
+  uint32_t* spoly = (uint32_t*)(b + oSp);
+  uint32_t* s1h = (uint32_t*)(b + oSh);
+  const uint32_t* zetas = (const uint32_t*)c.dil_tw;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    CB200_CUDA(cudaFuncSetAttribute(kg_eta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    attr_set = true;
+  }
+  auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
+  {
+    KernelScope ks(KID_MLDSA_MU, st);
+    kg_seed_kernel<<<blocks(n, 128), 128, 0, st>>>(seeds, n, pk, sk, sseed);
+  }
+  {
+    KernelScope ks(KID_MLDSA_MASK, st);
+    kg_eta_kernel<<<blocks(n * (L + K), kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(sseed, n, spoly, sk);
+  }
+  {
+    KernelScope ks(KID_MLDSA_EXPAND, st);
+    expand_a_kernel<<<blocks(n * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(pk, PK_BYTES, n, A);
+  }
+  {
+    KernelScope ks(KID_MLDSA_W, st);
+    kg_s1ntt_kernel<<<blocks(n * L, 16), 128, 0, st>>>(spoly, n, s1h, zetas);
+  }
+  {
+    KernelScope ks(KID_MLDSA_W, st);
+    kg_t_kernel<<<blocks(n * K, 16), 128, 0, st>>>(A, s1h, spoly, n, pk, sk, zetas);
+  }
+  {
+    KernelScope ks(KID_MLDSA_CHALLENGE, st);
+    kg_tr_kernel<<<blocks(n, 128), 128, 0, st>>>(pk, n, sk);
+  }
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
 // ------------------------------------------------------------------ host side
 static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off,
                        const uint8_t* ctxstr, int ctxlen, const uint8_t* rnd, uint8_t* sig, uint8_t* status, size_t n,
@@ -803,7 +1366,98 @@ int cb200_mldsa65_sign(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   return 0;
 }
 
+int cb200_mldsa65_verify(const uint8_t* pk, size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off,
+                         const uint8_t* context, size_t ctxlen, const uint8_t* sig, uint8_t* ok, size_t n, int flags) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (!pk || !msgs || !msg_off || !sig || !ok || ctxlen > 255 || (ctxlen && !context) ||
+      (pk_stride != 0 && pk_stride < 1952)) {
+    set_error("cb200_mldsa65_verify: bad argument");
+    return CB200_ERR_ARG;
+  }
+  const int internal = flags & CB200_SIGN_INTERNAL;
+  const bool dev = is_device_ptr(ok);
+  if (dev != is_device_ptr(pk) || dev != is_device_ptr(msgs) || dev != is_device_ptr(msg_off) || dev != is_device_ptr(sig)) {
+    set_error("cb200_mldsa65_verify: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  if (dev) {
+    if (((uintptr_t)pk | pk_stride | (uintptr_t)msg_off) & 15) {
+      set_error("cb200_mldsa65_verify: device pk and pk_stride must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    const uint8_t* dctx = nullptr;
+    if (ctxlen) {
+      CB200_CUDA(cudaMemcpyAsync(ctx().small, context, ctxlen, cudaMemcpyHostToDevice, ctx().cur));
+      dctx = (const uint8_t*)ctx().small;
+    }
+    return mldsa::verify_device(pk, pk_stride, msgs, msg_off, dctx, (int)ctxlen, sig, ok, n, internal, ctx().cur, 3);
+  }
+  Ctx& c = ctx();
+  std::lock_guard<std::mutex> lock(c.mu);
+  cudaStream_t st = c.pipe[0];
+  const size_t msg_bytes = (size_t)msg_off[n];
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t nk = pk_stride ? n : 1;
+  const size_t oPk = take(nk * 1952), oMsg = take(msg_bytes + 8), oOff = take((n + 1) * 8), oSig = take(n * (size_t)3309),
+               oOk = take(n), oCtx = take(256);
+  rc = ensure_scratch(0, off);
+  if (rc) return rc;
+  char* d = (char*)c.scratch[0];
+  if (pk_stride == 0 || pk_stride == 1952)
+    CB200_CUDA(cudaMemcpyAsync(d + oPk, pk, nk * 1952, cudaMemcpyHostToDevice, st));
+  else
+    CB200_CUDA(cudaMemcpy2DAsync(d + oPk, 1952, pk, pk_stride, 1952, n, cudaMemcpyHostToDevice, st));
+  if (msg_bytes) CB200_CUDA(cudaMemcpyAsync(d + oMsg, msgs, msg_bytes, cudaMemcpyHostToDevice, st));
+  CB200_CUDA(cudaMemcpyAsync(d + oOff, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
+  CB200_CUDA(cudaMemcpyAsync(d + oSig, sig, n * (size_t)3309, cudaMemcpyHostToDevice, st));
+  if (ctxlen) CB200_CUDA(cudaMemcpyAsync(d + oCtx, context, ctxlen, cudaMemcpyHostToDevice, st));
+  rc = mldsa::verify_device((const uint8_t*)d + oPk, pk_stride ? 1952 : 0, (const uint8_t*)d + oMsg,
+                            (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : nullptr, (int)ctxlen,
+                            (const uint8_t*)d + oSig, (uint8_t*)d + oOk, n, internal, st, 0);
+  if (rc) return rc;
+  CB200_CUDA(cudaMemcpyAsync(ok, d + oOk, n, cudaMemcpyDeviceToHost, st));
+  CB200_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int cb200_mldsa65_keygen(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (!seeds || !pk || !sk) {
+    set_error("cb200_mldsa65_keygen: null pointer");
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(pk);
+  if (dev != is_device_ptr(seeds) || dev != is_device_ptr(sk)) {
+    set_error("cb200_mldsa65_keygen: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  if (dev) {
+    if (((uintptr_t)seeds | (uintptr_t)pk | (uintptr_t)sk) & 15) {
+      set_error("cb200_mldsa65_keygen: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    return mldsa::keygen_device(seeds, pk, sk, n, ctx().cur, 3);
+  }
+  std::vector<Buf> bufs(3);
+  bufs[0] = Buf{seeds, nullptr, 32, false, 0};
+  bufs[1] = Buf{nullptr, pk, 1952, false, 0};
+  bufs[2] = Buf{nullptr, sk, 4032, false, 0};
+  return run_staged(bufs, n, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+    return mldsa::keygen_device((const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
+  });
+}
+
 size_t cb200_mldsa65_signature_size(void) { return 3309; }
+size_t cb200_mldsa65_public_key_size(void) { return 1952; }
 size_t cb200_mldsa65_private_key_size(void) { return 4032; }
 
 }  // extern "C"

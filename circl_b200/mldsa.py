@@ -35,6 +35,24 @@ class SignatureOpts:
         self.Context = Context
 
 
+class PublicKey:
+    def __init__(self, scheme, packed: bytes):
+        self._scheme, self._packed = scheme, bytes(packed)
+
+    def Scheme(self):
+        return self._scheme
+
+    def MarshalBinary(self) -> bytes:
+        return self._packed
+
+    def Equal(self, other) -> bool:
+        return isinstance(other, PublicKey) and other._packed == self._packed
+
+
+class ErrPubKeySize(SignError):
+    pass
+
+
 class PrivateKey:
     def __init__(self, scheme, packed: bytes):
         self._scheme, self._packed = scheme, bytes(packed)
@@ -111,13 +129,64 @@ class Scheme:
             return sig, int(attempts.value)
         return sig
 
+    def DeriveKey(self, seed: bytes):
+        """sign.Scheme.DeriveKey (dilithium.go:266-276): key pair from a 32-byte seed (batch of one)."""
+        if len(seed) != self.SeedSize():
+            raise ValueError("sign: invalid seed size")  # the reference panics with sign.ErrSeedSize
+        pk, sk = self.DeriveKeyBatch(np.frombuffer(seed, dtype=np.uint8).reshape(1, 32))
+        return PublicKey(self, pk[0].tobytes()), PrivateKey(self, sk[0].tobytes())
+
     def GenerateKey(self):
-        raise NotImplementedError("key generation is not on the accelerated path yet (SURVEY.md 8(f) row 2)")
+        import os
+        return self.DeriveKey(os.urandom(32))
 
-    DeriveKey = GenerateKey
+    def DeriveKeyBatch(self, seeds):
+        """seeds: (n, 32) uint8 -> (pk (n, 1952), sk (n, 4032)) packed keys."""
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
+        if seeds.ndim != 2 or seeds.shape[1] != 32:
+            raise ValueError("sign: invalid seed size")
+        n = seeds.shape[0]
+        pk = np.empty((n, 1952), dtype=np.uint8)
+        sk = np.empty((n, 4032), dtype=np.uint8)
+        check(lib().cb200_mldsa65_keygen(seeds.ctypes.data, pk.ctypes.data, sk.ctypes.data, n))
+        return pk, sk
 
-    def Verify(self, pk, message, signature, opts=None):
-        raise NotImplementedError("verification is not on the accelerated path yet (SURVEY.md 8(f) row 3)")
+    def UnmarshalBinaryPublicKey(self, buf: bytes) -> PublicKey:
+        if len(buf) != self.PublicKeySize():
+            raise ErrPubKeySize("sign: invalid public key size")  # dilithium.go:337-340
+        return PublicKey(self, buf)
+
+    def Verify(self, pk: PublicKey, message: bytes, signature: bytes, opts: SignatureOpts | None = None) -> bool:
+        """sign.Scheme.Verify (dilithium.go:305-330), batch of one."""
+        if not isinstance(pk, PublicKey):
+            raise TypeError("sign: wrong public key type")
+        ctx = opts.Context if opts is not None else b""
+        if len(ctx) > 255 or len(signature) != self.SignatureSize():
+            return False  # dilithium.go:116-118, internal/dilithium.go:82-84
+        return bool(self.VerifyBatch(pk, [message], np.frombuffer(signature, dtype=np.uint8).reshape(1, -1), ctx=ctx)[0])
+
+    def VerifyBatch(self, pks, messages, sigs, ctx: bytes = b"", internal: bool = False):
+        """pks: one PublicKey (shared) or (n, 1952) uint8; sigs: (n, 3309) uint8 -> (n,) bool array."""
+        n = len(messages)
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in messages], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(messages) + b"\0" * 8, dtype=np.uint8)
+        if isinstance(pks, PublicKey):
+            pk = np.frombuffer(pks._packed, dtype=np.uint8)
+            stride = 0
+        else:
+            pk = np.ascontiguousarray(pks, dtype=np.uint8)
+            if pk.shape != (n, 1952):
+                raise ErrPubKeySize("sign: invalid public key size")
+            stride = 1952
+        sigs = np.ascontiguousarray(sigs, dtype=np.uint8)
+        assert sigs.shape == (n, 3309)
+        ok = np.zeros((n,), dtype=np.uint8)
+        cbuf = (C.c_uint8 * max(1, len(ctx))).from_buffer_copy(ctx or b"\0")
+        check(lib().cb200_mldsa65_verify(pk.ctypes.data, stride, blob.ctypes.data, off.ctypes.data,
+                                         C.cast(cbuf, C.c_void_p), len(ctx), sigs.ctypes.data, ok.ctypes.data, n,
+                                         SIGN_INTERNAL if internal else 0))
+        return ok.astype(bool)
 
 
 _SCHEME = Scheme()

@@ -136,6 +136,16 @@ size_t cb200_mlkem_ciphertext_size(int k);
 int cb200_mldsa65_sign(const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *msg_off,
                        const uint8_t *context, size_t ctxlen, const uint8_t *rnd, uint8_t *sig, uint8_t *status,
                        size_t n, int flags, uint64_t *attempts);
+/* sign.Scheme.Verify       sign/mldsa/mldsa65/dilithium.go:305-330,115-138 -> internal.Verify internal/dilithium.go:273-332,
+ * including (*PublicKey).Unpack (:113-126): A = ExpandA(rho), tr = H(pk) rebuilt on the device.
+ * pk: packed public key(s), 1952 bytes, op i uses pk + i*pk_stride (0 = shared); sig: n x 3309 bytes;
+ * ok: n bytes, 1 = valid.  A signature of the wrong length is the caller's (shim's) `false`. */
+int cb200_mldsa65_verify(const uint8_t *pk, size_t pk_stride, const uint8_t *msgs, const uint64_t *msg_off,
+                         const uint8_t *context, size_t ctxlen, const uint8_t *sig, uint8_t *ok, size_t n, int flags);
+/* sign.Scheme.DeriveKey    sign/mldsa/mldsa65/dilithium.go:266-276 -> internal.NewKeyFromSeed internal/dilithium.go:181-241.
+ * seeds: n x 32; pk: n x 1952; sk: n x 4032 (packed, = MarshalBinary). */
+int cb200_mldsa65_keygen(const uint8_t *seeds, uint8_t *pk, uint8_t *sk, size_t n);
+size_t cb200_mldsa65_public_key_size(void);
 size_t cb200_mldsa65_signature_size(void);
 size_t cb200_mldsa65_private_key_size(void);
 

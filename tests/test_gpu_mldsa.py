@@ -84,3 +84,78 @@ def test_many_ops_property(cb):
     assert 3.5 < attempts / n < 7.0
     for i in range(0, n, 331):
         assert sig[i].tobytes() == oracle.mldsa65_sign(sk, msgs[i])[0]
+
+
+# ---------------------------------------------------------------- Verify
+def test_acvp_sigver(cb, mldsa65_acvp):
+    # sign/mldsa/mldsa65/acvp_test.go:124-163: one pk, 15 signatures, expected pass / fail
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName("ML-DSA-65")
+    g = mldsa65_acvp["sigver"]
+    pk = scheme.UnmarshalBinaryPublicKey(bytes.fromhex(g["pk"]))
+    msgs = [bytes.fromhex(t["message"]) for t in g["tests"]]
+    sigs = np.stack([np.frombuffer(bytes.fromhex(t["signature"]), dtype=np.uint8) for t in g["tests"]])
+    ok = scheme.VerifyBatch(pk, msgs, sigs, internal=True)
+    assert ok.tolist() == [t["testPassed"] for t in g["tests"]]
+    assert True in ok.tolist() and False in ok.tolist()
+
+
+def test_sign_then_verify_on_gpu_and_tampering(cb):
+    import oracle
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName("ML-DSA-65")
+    n = 600
+    pool = [oracle.mldsa65_keygen(_h(2, j, 32)) for j in range(6)]
+    sks = np.stack([np.frombuffer(pool[i % 6][1], dtype=np.uint8) for i in range(n)])
+    pks = np.stack([np.frombuffer(pool[i % 6][0], dtype=np.uint8) for i in range(n)])
+    msgs = [_h(6, i, 1 + i % 200) for i in range(n)]
+    ctx = b"ctx"
+    sig = scheme.SignBatch(sks, msgs, ctx=ctx)
+    assert scheme.VerifyBatch(pks, msgs, sig, ctx=ctx).all()
+    assert not scheme.VerifyBatch(pks, msgs, sig, ctx=b"other").any()       # wrong context
+    bad = sig.copy()
+    bad[0, 3] ^= 1                 # c~
+    bad[1, 48 + 7] ^= 0x10         # z
+    bad[2, 3309 - 1] ^= 1          # hint switch-over point
+    bad[3, 3309 - 20] = 200        # padding index not zero / ordering
+    got = scheme.VerifyBatch(pks, msgs, bad, ctx=ctx)
+    want = [oracle.mldsa65_verify(pool[i % 6][0], msgs[i], bad[i].tobytes(), ctx=ctx) for i in range(8)]
+    assert got[:8].tolist() == want and not any(want[:4]) and all(want[4:])
+    # shared public key + single-op API
+    pk0 = scheme.UnmarshalBinaryPublicKey(pool[0][0])
+    idx = list(range(0, n, 6))
+    assert scheme.VerifyBatch(pk0, [msgs[i] for i in idx], sig[idx], ctx=ctx).all()
+    assert scheme.Verify(pk0, msgs[0], sig[0].tobytes(), mldsa.SignatureOpts(Context=ctx))
+    assert not scheme.Verify(pk0, msgs[0], sig[0].tobytes()[:-1], mldsa.SignatureOpts(Context=ctx))
+
+
+# ---------------------------------------------------------------- KeyGen
+def test_acvp_keygen(cb, mldsa65_acvp):
+    # sign/mldsa/mldsa65/acvp_test.go:47-80: seed -> pk, sk
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName("ML-DSA-65")
+    tests = mldsa65_acvp["keygen"]
+    seeds = np.stack([np.frombuffer(bytes.fromhex(t["seed"]), dtype=np.uint8) for t in tests])
+    pk, sk = scheme.DeriveKeyBatch(seeds)
+    for i, t in enumerate(tests):
+        assert pk[i].tobytes().hex().upper() == t["pk"].upper(), t["tcId"]
+        assert sk[i].tobytes().hex().upper() == t["sk"].upper(), t["tcId"]
+
+
+def test_keygen_sign_verify_all_on_gpu(cb):
+    """sign/schemes/schemes_test.go:17 style API round trip with nothing but the GPU path."""
+    import oracle
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName("ML-DSA-65")
+    n = 2000
+    seeds = np.frombuffer(hashlib.shake_256(b"dsa-keygen").digest(32 * n), dtype=np.uint8).reshape(n, 32)
+    pk, sk = scheme.DeriveKeyBatch(seeds)
+    for i in range(0, n, 397):
+        wpk, wsk = oracle.mldsa65_keygen(seeds[i].tobytes())
+        assert pk[i].tobytes() == wpk and sk[i].tobytes() == wsk
+    msgs = [_h(7, i, 40) for i in range(n)]
+    sig = scheme.SignBatch(sk, msgs)
+    assert scheme.VerifyBatch(pk, msgs, sig).all()
+    assert not scheme.VerifyBatch(pk, msgs[1:] + msgs[:1], sig).any()
+    p1, s1 = scheme.DeriveKey(seeds[0].tobytes())
+    assert p1.MarshalBinary() == pk[0].tobytes() and scheme.Verify(p1, b"m", scheme.Sign(s1, b"m"))

@@ -66,9 +66,14 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise ImportError(
-                f"{LIB_PATH} is missing: build it with `python -m circl_b200.build` "
-                "(nvcc, sm_100a). circl_b200 has no CPU fallback.")
+            # Not a fallback: the only way forward is the CUDA library itself, so build it (nvcc, sm_100a).
+            try:
+                from .build import build_library
+                build_library()
+            except Exception as e:  # pragma: no cover
+                raise ImportError(
+                    f"{LIB_PATH} is missing and could not be built with nvcc ({e}). "
+                    "circl_b200 has no CPU fallback.") from e
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SYMBOLS.items():
             if not hasattr(L, name):

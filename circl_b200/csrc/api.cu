@@ -192,6 +192,13 @@ int cb200_init(int device) {
   }
   CB200_CUDA(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
   for (int s = 0; s < 3; s++) CB200_CUDA(cudaStreamCreateWithFlags(&c.pipe[s], cudaStreamNonBlocking));
+  for (int w = 0; w < 4; w++) {
+    CB200_CUDA(cudaEventCreateWithFlags(&c.ev_fork[w], cudaEventDisableTiming));
+    for (int l = 0; l < 2; l++) {
+      CB200_CUDA(cudaStreamCreateWithFlags(&c.lane[w][l], cudaStreamNonBlocking));
+      CB200_CUDA(cudaEventCreateWithFlags(&c.ev_join[w][l], cudaEventDisableTiming));
+    }
+  }
   c.cur = nullptr;  // CUDA legacy default stream until the caller names one
   int32_t ktw[256];
   kyber_fill_twiddles(ktw);
@@ -215,6 +222,16 @@ void cb200_shutdown(void) {
     c.scratch_bytes[s] = 0;
     if (c.pipe[s]) cudaStreamDestroy(c.pipe[s]);
     c.pipe[s] = nullptr;
+  }
+  for (int w = 0; w < 4; w++) {
+    if (c.ev_fork[w]) cudaEventDestroy(c.ev_fork[w]);
+    c.ev_fork[w] = nullptr;
+    for (int l = 0; l < 2; l++) {
+      if (c.lane[w][l]) cudaStreamDestroy(c.lane[w][l]);
+      if (c.ev_join[w][l]) cudaEventDestroy(c.ev_join[w][l]);
+      c.lane[w][l] = nullptr;
+      c.ev_join[w][l] = nullptr;
+    }
   }
   for (int s = 0; s < 4; s++) {
     if (c.work[s]) cudaFree(c.work[s]);

@@ -37,6 +37,10 @@ struct Ctx {
   size_t scratch_bytes[3] = {0, 0, 0};
   // grow-only work areas for the multi-kernel pipelines (ML-KEM / ML-DSA)
   // slot 0..2 belong to the staging pipeline streams, slot 3 to device-pointer calls
+  // two internal "lanes" per work slot: consecutive sub-batches of a pipeline alternate between them so that
+  // the tail of one sub-batch's kernels overlaps the head of the next (fork/join on events around them)
+  cudaStream_t lane[4][2] = {};
+  cudaEvent_t ev_fork[4] = {}, ev_join[4][2] = {};
   void* pinned = nullptr;       // grow-only pinned host staging for small per-op outputs (status bytes)
   size_t pinned_bytes = 0;
   void* work[4] = {nullptr, nullptr, nullptr, nullptr};

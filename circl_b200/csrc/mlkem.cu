@@ -894,15 +894,17 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
     off += (bytes + 255) & ~(size_t)255;
     return o;
   };
-  const size_t o_h = take(nkeys * 32), o_r = take(n * 32), o_A = take(subkeys * K * K * 512),
-               o_n = take(sub * P::n_noise * 512);
+  const size_t o_h = take(nkeys * 32), o_r = take(n * 32);
+  size_t o_A[2], o_n[2];
+  o_A[0] = take(subkeys * K * K * 512);
+  o_A[1] = shared ? o_A[0] : take(subkeys * K * K * 512);
+  o_n[0] = take(sub * P::n_noise * 512);
+  o_n[1] = take(sub * P::n_noise * 512);
   void* base = nullptr;
   int rc = ensure_work(slot, off, &base);
   if (rc) return rc;
   uint64_t* h = (uint64_t*)((char*)base + o_h);
   uint64_t* r = (uint64_t*)((char*)base + o_r);
-  int16_t* A = (int16_t*)((char*)base + o_A);
-  int16_t* noise = (int16_t*)((char*)base + o_n);
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -917,24 +919,43 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
     KernelScope ks(KID_MLKEM_G, st);
     g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, (const uint8_t*)h, shared ? 0 : 32, n, ss, r);
   }
-  for (size_t first = 0; first < n; first += sub) {
+  if (shared) {  // one key: A^T is derived once, before the sub-batches fork
+    KernelScope ks(KID_MLKEM_SAMPLE, st);
+    sample_kernel<K><<<(unsigned)((K * K + 127) / 128), 128, kSampleSmem, st>>>(
+        ek + 384 * K, 0, 1, r, 0, (int16_t*)((char*)base + o_A[0]), (int16_t*)((char*)base + o_n[0]), (K * K + 127) / 128, 1,
+        P::n_noise, 4);
+  }
+  // Sub-batches alternate between two internal streams (fork/join on events): the tail wave of one
+  // sub-batch's kernels overlaps the next sub-batch instead of idling SMs.
+  CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
+  for (int l = 0; l < 2; l++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][l], c.ev_fork[slot], 0));
+  int l = 0;
+  for (size_t first = 0; first < n; first += sub, l ^= 1) {
+    // per-kernel event timing (cb200_profile_enable) wants true, non-overlapped durations: stay on one stream
+    cudaStream_t ls = c.profiling ? st : c.lane[slot][l];
+    int16_t* A = (int16_t*)((char*)base + o_A[l]);
+    int16_t* noise = (int16_t*)((char*)base + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
-    const size_t keys_here = shared ? (first == 0 ? 1 : 0) : cnt;  // shared key: A^T is derived once
+    const size_t keys_here = shared ? 0 : cnt;
     const size_t mat_blocks = (keys_here * K * K + 127) / 128;
     const size_t noise_blocks = (cnt * P::n_noise + 127) / 128;
     {
-      KernelScope ks(KID_MLKEM_SAMPLE, st);
-      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, st>>>(
+      KernelScope ks(KID_MLKEM_SAMPLE, ls);
+      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
           ek + 384 * K + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise,
           mat_blocks, 1, P::n_noise, 4);
     }
     {
-      KernelScope ks(KID_MLKEM_ENCRYPT, st);
-      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
+      KernelScope ks(KID_MLKEM_ENCRYPT, ls);
+      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
           ek + (shared ? 0 : first * ek_stride), ek_stride, A, shared ? 1 : 0, noise, seeds + 32 * first, cnt,
           ct + first * P::ct_bytes, ss + 32 * first, status ? status + first : nullptr,
           (const kyber::TwPair*)c.kyber_tw, 0);
     }
+  }
+  for (int q = 0; q < 2; q++) {
+    CB200_CUDA(cudaEventRecord(c.ev_join[slot][q], c.lane[slot][q]));
+    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_join[slot][q], 0));
   }
   CB200_CUDA(cudaGetLastError());
   return 0;

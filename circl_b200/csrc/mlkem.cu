@@ -35,7 +35,8 @@ struct Params {
   static constexpr int dv = (K == 4) ? 5 : 4;
   static constexpr int ek_bytes = 384 * K + 32;
   static constexpr int ct_bytes = 32 * (du * K + dv);
-  static constexpr int n_noise = 2 * K + 1;  // r[0..K), e1[0..K), e2   (eta1 = eta2 = 2 for K = 3, 4)
+  static constexpr int eta1 = (K == 2) ? 3 : 2;  // pke/kyber/kyber{512,768,1024}/internal/params.go
+  static constexpr int n_noise = 2 * K + 1;      // r[0..K) (eta1), e1[0..K), e2 (eta2 = 2)
 };
 
 // ------------------------------------------------------------------ 1. hashes
@@ -152,6 +153,35 @@ constexpr size_t kSub = 8192;
 constexpr int kRowWords = 129;  // 256 int16 + 2 slack, odd word stride
 constexpr int kSampleSmem = 128 * kRowWords * 4;
 
+// CBD_3 of 192 bytes (sample.go:31-62): 6-byte windows, 8 coefficients each; w = 24 squeezed words
+__device__ __forceinline__ void cbd3_store(const uint64_t (&w)[24], int16_t* __restrict__ dst) {
+  uint4* out = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+  for (int g = 0; g < 8; g++) {  // 3 words -> 4 windows -> 32 coefficients
+    const uint64_t w0 = w[3 * g], w1 = w[3 * g + 1], w2 = w[3 * g + 2];
+    uint64_t t[4];
+    t[0] = w0;
+    t[1] = (w0 >> 48) | (w1 << 16);
+    t[2] = (w1 >> 32) | (w2 << 32);
+    t[3] = w2 >> 16;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      const uint64_t x = t[q];
+      uint64_t d = x & 0x249249249249ull;
+      d += (x >> 1) & 0x249249249249ull;
+      d += (x >> 2) & 0x249249249249ull;
+      uint32_t c[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        const int c0 = (int)((d >> (12 * j)) & 7) - (int)((d >> (12 * j + 3)) & 7);
+        const int c1 = (int)((d >> (12 * j + 6)) & 7) - (int)((d >> (12 * j + 9)) & 7);
+        c[j] = ((uint32_t)c0 & 0xffffu) | ((uint32_t)c1 << 16);
+      }
+      out[4 * g + q] = make_uint4(c[0], c[1], c[2], c[3]);
+    }
+  }
+}
+
 // Stream index space (blockDim-aligned so that warps never mix stream kinds):
 //   [0, nkeys*K*K)               matrix streams, s = (i*K + j) * nkeys + key  -> A^T[key][i][j] = XOF(rho, i, j)
 //   then n*(2K+1) noise streams, s = nonce * n + op                            -> PRF(r_op, nonce)
@@ -159,9 +189,12 @@ template <int K>
 __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__ rho0, size_t ek_stride, size_t nkeys,
                                                      const uint64_t* __restrict__ r, size_t n,
                                                      int16_t* __restrict__ A, int16_t* __restrict__ noise,
-                                                     size_t mat_blocks, int transpose, int n_noise, int r_words) {
+                                                     size_t mat_blocks, int transpose, int n_noise, int r_words,
+                                                     int n_eta1) {
   // rho0 + key*ek_stride is rho of that key; transpose = 1 derives A^T (encryption), 0 derives A (key
-  // generation, mat.go:13-29); n_noise PRF streams per op, seeded by r[op*r_words .. +4)
+  // generation, mat.go:13-29); n_noise PRF streams per op, seeded by r[op*r_words .. +4); the first n_eta1
+  // nonces use eta1 (3 for ML-KEM-512), the others eta2 = 2
+  using P = Params<K>;
   uint64_t a[25];
   keccak::zero(a);
   if (blockIdx.x < mat_blocks) {
@@ -208,7 +241,18 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
     a[4] = (uint64_t)nonce | (0x1full << 8);
     a[16] = 0x8000000000000000ull;  // rate 136
     keccak::f1600(a);
-    cbd2_store(a, noise + (op * n_noise + nonce) * N);
+    int16_t* dst = noise + (op * n_noise + nonce) * N;
+    if (P::eta1 == 3 && nonce < n_eta1) {
+      uint64_t w[24];
+#pragma unroll
+      for (int q = 0; q < 17; q++) w[q] = a[q];
+      keccak::f1600(a);
+#pragma unroll
+      for (int q = 0; q < 7; q++) w[17 + q] = a[q];
+      cbd3_store(w, dst);
+    } else {
+      cbd2_store(a, dst);
+    }
   }
 }
 
@@ -633,7 +677,12 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
     return o;
   };
   const size_t o_h = take(n * 32), o_r = take(n * 32), o_m = take(n * 32), o_k = take(n * 32),
-               o_ct2 = take(n * (size_t)P::ct_bytes), o_A = take(sub * K * K * 512), o_n = take(sub * P::n_noise * 512);
+               o_ct2 = take(n * (size_t)P::ct_bytes);
+  size_t o_A[2], o_n[2];
+  for (int q = 0; q < 2; q++) {
+    o_A[q] = take(sub * K * K * 512);
+    o_n[q] = take(sub * P::n_noise * 512);
+  }
   void* base = nullptr;
   int rc = ensure_work(slot, off, &base);
   if (rc) return rc;
@@ -643,8 +692,6 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
   uint8_t* mprime = (uint8_t*)(b + o_m);
   uint8_t* kbar = (uint8_t*)(b + o_k);
   uint8_t* ct2 = (uint8_t*)(b + o_ct2);
-  int16_t* A = (int16_t*)(b + o_A);
-  int16_t* noise = (int16_t*)(b + o_n);
   const uint8_t* ek = dk + 384 * K;  // dk = sk || ek || H(ek) || z (kyber.go:187-201)
   static bool attr_set = false;
   if (!attr_set) {
@@ -664,20 +711,30 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
     KernelScope ks(KID_MLKEM_G, st);
     g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(mprime, dk + 384 * K + P::ek_bytes, dk_stride, n, kbar, r);
   }
-  for (size_t first = 0; first < n; first += sub) {
+  CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
+  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][q], c.ev_fork[slot], 0));
+  int l = 0;
+  for (size_t first = 0; first < n; first += sub, l ^= 1) {
+    cudaStream_t ls = c.profiling ? st : c.lane[slot][l];
+    int16_t* A = (int16_t*)(b + o_A[l]);
+    int16_t* noise = (int16_t*)(b + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
     const size_t mat_blocks = (cnt * K * K + 127) / 128, noise_blocks = (cnt * P::n_noise + 127) / 128;
     {
-      KernelScope ks(KID_MLKEM_SAMPLE, st);
-      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, st>>>(
-          ek + 384 * K + first * dk_stride, dk_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks, 1, P::n_noise, 4);
+      KernelScope ks(KID_MLKEM_SAMPLE, ls);
+      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
+          ek + 384 * K + first * dk_stride, dk_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks, 1, P::n_noise, 4, K);
     }
     {
-      KernelScope ks(KID_MLKEM_ENCRYPT, st);
-      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
+      KernelScope ks(KID_MLKEM_ENCRYPT, ls);
+      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
           ek + first * dk_stride, dk_stride, A, 0, noise, mprime + 32 * first, cnt, ct2 + first * P::ct_bytes, nullptr,
           nullptr, tw, 1);
     }
+  }
+  for (int q = 0; q < 2; q++) {
+    CB200_CUDA(cudaEventRecord(c.ev_join[slot][q], c.lane[slot][q]));
+    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_join[slot][q], 0));
   }
   {
     KernelScope ks(KID_MLKEM_G, st);
@@ -829,15 +886,18 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
     off += (bytes + 255) & ~(size_t)255;
     return o;
   };
-  const size_t o_rs = take(n * 64), o_h = take(n * 32), o_A = take(sub * K * K * 512), o_n = take(sub * 2 * K * 512);
+  const size_t o_rs = take(n * 64), o_h = take(n * 32);
+  size_t o_A[2], o_n[2];
+  for (int q = 0; q < 2; q++) {
+    o_A[q] = take(sub * K * K * 512);
+    o_n[q] = take(sub * 2 * K * 512);
+  }
   void* base = nullptr;
   int rc = ensure_work(slot, off, &base);
   if (rc) return rc;
   char* b = (char*)base;
   uint64_t* rs = (uint64_t*)(b + o_rs);
   uint64_t* h = (uint64_t*)(b + o_h);
-  int16_t* A = (int16_t*)(b + o_A);
-  int16_t* noise = (int16_t*)(b + o_n);
   static bool attr_set = false;
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
@@ -847,19 +907,29 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
     KernelScope ks(KID_MLKEM_G, st);
     keygen_seed_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, n, rs, ek, dk);
   }
-  for (size_t first = 0; first < n; first += sub) {
+  CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
+  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][q], c.ev_fork[slot], 0));
+  int l = 0;
+  for (size_t first = 0; first < n; first += sub, l ^= 1) {
+    cudaStream_t ls = c.profiling ? st : c.lane[slot][l];
+    int16_t* A = (int16_t*)(b + o_A[l]);
+    int16_t* noise = (int16_t*)(b + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
     const size_t mat_blocks = (cnt * K * K + 127) / 128, noise_blocks = (cnt * 2 * K + 127) / 128;
     {  // A (not transposed) from rho = rs[0..4), s/e noise from sigma = rs[4..8)
-      KernelScope ks(KID_MLKEM_SAMPLE, st);
-      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, st>>>(
-          (const uint8_t*)(rs + 8 * first), 64, cnt, rs + 8 * first + 4, cnt, A, noise, mat_blocks, 0, 2 * K, 8);
+      KernelScope ks(KID_MLKEM_SAMPLE, ls);
+      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
+          (const uint8_t*)(rs + 8 * first), 64, cnt, rs + 8 * first + 4, cnt, A, noise, mat_blocks, 0, 2 * K, 8, 2 * K);
     }
     {
-      KernelScope ks(KID_MLKEM_ENCRYPT, st);
-      keygen_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, st>>>(
+      KernelScope ks(KID_MLKEM_ENCRYPT, ls);
+      keygen_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
           A, noise, cnt, ek + first * P::ek_bytes, dk + first * dksz, (const kyber::TwPair*)c.kyber_tw);
     }
+  }
+  for (int q = 0; q < 2; q++) {
+    CB200_CUDA(cudaEventRecord(c.ev_join[slot][q], c.lane[slot][q]));
+    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_join[slot][q], 0));
   }
   {  // H(ek) into dk (kyber.go:69-75)
     KernelScope ks(KID_MLKEM_HASH_EK, st);
@@ -923,7 +993,7 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
     KernelScope ks(KID_MLKEM_SAMPLE, st);
     sample_kernel<K><<<(unsigned)((K * K + 127) / 128), 128, kSampleSmem, st>>>(
         ek + 384 * K, 0, 1, r, 0, (int16_t*)((char*)base + o_A[0]), (int16_t*)((char*)base + o_n[0]), (K * K + 127) / 128, 1,
-        P::n_noise, 4);
+        P::n_noise, 4, K);
   }
   // Sub-batches alternate between two internal streams (fork/join on events): the tail wave of one
   // sub-batch's kernels overlaps the next sub-batch instead of idling SMs.
@@ -943,7 +1013,7 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
       KernelScope ks(KID_MLKEM_SAMPLE, ls);
       sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
           ek + 384 * K + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise,
-          mat_blocks, 1, P::n_noise, 4);
+          mat_blocks, 1, P::n_noise, 4, K);
     }
     {
       KernelScope ks(KID_MLKEM_ENCRYPT, ls);
@@ -963,8 +1033,9 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
 
 static int encaps_any(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
                       uint8_t* status, size_t n, cudaStream_t st, int slot) {
-  return k == 3 ? encaps_device<3>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
-                : encaps_device<4>(ek, ek_stride, seeds, ct, ss, status, n, st, slot);
+  return k == 2   ? encaps_device<2>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
+         : k == 3 ? encaps_device<3>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
+                  : encaps_device<4>(ek, ek_stride, seeds, ct, ss, status, n, st, slot);
 }
 
 }  // namespace mlkem
@@ -977,8 +1048,8 @@ extern "C" {
 int cb200_mlkem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n) {
   int rc = require_ready();
   if (rc) return rc;
-  if (k != 3 && k != 4) {
-    set_error("cb200_mlkem_keygen: k must be 3 (ML-KEM-768) or 4 (ML-KEM-1024), got %d", k);
+  if (k < 2 || k > 4) {
+    set_error("cb200_mlkem_keygen: k must be 2, 3 or 4 (ML-KEM-512/768/1024), got %d", k);
     return CB200_ERR_ARG;
   }
   if (n == 0) return 0;
@@ -992,7 +1063,9 @@ int cb200_mlkem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, si
     return CB200_ERR_ARG;
   }
   auto run = [&](const uint8_t* s_, uint8_t* e_, uint8_t* d_, size_t cnt, cudaStream_t st, int slot) {
-    return k == 3 ? mlkem::keygen_device<3>(s_, e_, d_, cnt, st, slot) : mlkem::keygen_device<4>(s_, e_, d_, cnt, st, slot);
+    return k == 2   ? mlkem::keygen_device<2>(s_, e_, d_, cnt, st, slot)
+           : k == 3 ? mlkem::keygen_device<3>(s_, e_, d_, cnt, st, slot)
+                    : mlkem::keygen_device<4>(s_, e_, d_, cnt, st, slot);
   };
   if (dev) {
     if (((uintptr_t)seeds | (uintptr_t)ek | (uintptr_t)dk) & 15) {
@@ -1016,8 +1089,8 @@ int cb200_mlkem_decaps(int k, const uint8_t* dk, size_t dk_stride, const uint8_t
                        size_t n) {
   int rc = require_ready();
   if (rc) return rc;
-  if (k != 3 && k != 4) {
-    set_error("cb200_mlkem_decaps: k must be 3 (ML-KEM-768) or 4 (ML-KEM-1024), got %d", k);
+  if (k < 2 || k > 4) {
+    set_error("cb200_mlkem_decaps: k must be 2, 3 or 4 (ML-KEM-512/768/1024), got %d", k);
     return CB200_ERR_ARG;
   }
   if (n == 0) return 0;
@@ -1033,8 +1106,9 @@ int cb200_mlkem_decaps(int k, const uint8_t* dk, size_t dk_stride, const uint8_t
   }
   auto run = [&](const uint8_t* d_dk, size_t stride, const uint8_t* d_ct, uint8_t* d_ss, uint8_t* d_st, size_t cnt,
                  cudaStream_t st, int slot) {
-    return k == 3 ? mlkem::decaps_device<3>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot)
-                  : mlkem::decaps_device<4>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot);
+    return k == 2   ? mlkem::decaps_device<2>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot)
+           : k == 3 ? mlkem::decaps_device<3>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot)
+                    : mlkem::decaps_device<4>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot);
   };
   if (dev) {
     if (((uintptr_t)dk | (uintptr_t)ct | (uintptr_t)ss | dk_stride) & 15) {
@@ -1104,8 +1178,8 @@ int cb200_mlkem_encaps(int k, const uint8_t* ek, size_t ek_stride, const uint8_t
                        uint8_t* status, size_t n) {
   int rc = require_ready();
   if (rc) return rc;
-  if (k != 3 && k != 4) {
-    set_error("cb200_mlkem_encaps: k must be 3 (ML-KEM-768) or 4 (ML-KEM-1024), got %d", k);
+  if (k < 2 || k > 4) {
+    set_error("cb200_mlkem_encaps: k must be 2, 3 or 4 (ML-KEM-512/768/1024), got %d", k);
     return CB200_ERR_ARG;
   }
   if (n == 0) return 0;

@@ -1,4 +1,4 @@
-"""kem.Scheme mirror for ML-KEM-768 / ML-KEM-1024 over the C ABI.
+"""kem.Scheme mirror for ML-KEM-512 / ML-KEM-768 / ML-KEM-1024 over the C ABI.
 
 Mirrors the method names, argument meaning and error behaviour of
   kem/kem.go:33-121                      (kem.Scheme, kem.Err*)
@@ -106,7 +106,7 @@ class Scheme:
         return 768 * self._k + 96
 
     def CiphertextSize(self) -> int:
-        return {3: 1088, 4: 1568}[self._k]
+        return {2: 768, 3: 1088, 4: 1568}[self._k]
 
     def SharedKeySize(self) -> int:
         return 32
@@ -291,7 +291,8 @@ class Scheme:
             raise
         return ss
 
-_SCHEMES = {"ml-kem-768": Scheme("ML-KEM-768", 3), "ml-kem-1024": Scheme("ML-KEM-1024", 4)}
+_SCHEMES = {"ml-kem-512": Scheme("ML-KEM-512", 2), "ml-kem-768": Scheme("ML-KEM-768", 3),
+            "ml-kem-1024": Scheme("ML-KEM-1024", 4)}
 
 
 def ByName(name: str):

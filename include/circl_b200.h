@@ -95,7 +95,7 @@ int cb200_dil_exceeds(const uint32_t *polys, uint32_t bound, uint8_t *flags, siz
 /* ---- ML-KEM ---- */
 /* scheme.UnmarshalBinaryPublicKey + EncapsulateDeterministically
  *   kem/mlkem/mlkem768/kyber.go:390-396,359-374,103-137 (mlkem1024: same lines)
- * k = 3 (ML-KEM-768: ek 1184, ct 1088) or 4 (ML-KEM-1024: ek 1568, ct 1568).
+ * k = 2 (ML-KEM-512: ek 800, ct 768), 3 (ML-KEM-768: ek 1184, ct 1088) or 4 (ML-KEM-1024: ek 1568, ct 1568).
  * ek_stride = 0: one ek shared by all n operations (parsed once);
  * otherwise op i uses ek + i*ek_stride and A^T, H(ek) are rebuilt on device per op.
  * seeds: n x 32 (the message m); ct: n x CiphertextSize; ss: n x 32.

@@ -10,7 +10,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 
-KS = {"ML-KEM-768": 3, "ML-KEM-1024": 4}
+KS = {"ML-KEM-512": 2, "ML-KEM-768": 3, "ML-KEM-1024": 4}
 
 
 @pytest.fixture(scope="module")

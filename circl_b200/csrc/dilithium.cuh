@@ -311,6 +311,28 @@ __device__ __forceinline__ void invntt_octet_smem(uint32_t (&r)[32], uint32_t* t
   __syncwarp();
   inv_pass_S(r);
 }
+// "I" (interleaved) layout for coefficient-wise work straight from global memory:
+//   r[4c+e] = coefficient 32c + 4v + e, i.e. per instruction an octet reads 8 x 16 = 128 contiguous bytes.
+// Pointwise products do not care about the layout as long as both operands share it; i_to_c brings the
+// result into the C layout the inverse transform starts from.
+__device__ __forceinline__ void gload_I(const uint32_t* __restrict__ poly, int v, uint4 (&w)[8]) {
+  const uint4* p = reinterpret_cast<const uint4*>(poly) + v;
+#pragma unroll
+  for (int c = 0; c < 8; c++) w[c] = p[8 * c];
+}
+__device__ __forceinline__ void gload_I_ro(const uint32_t* __restrict__ poly, int v, uint4 (&w)[8]) {
+  const uint4* p = reinterpret_cast<const uint4*>(poly) + v;
+#pragma unroll
+  for (int c = 0; c < 8; c++) w[c] = __ldg(p + 8 * c);
+}
+__device__ __forceinline__ void i_to_c(uint32_t (&r)[32], uint32_t* tile, int v) {
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+    *reinterpret_cast<uint4*>(tile + 36 * c + 4 * v) = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
+  __syncwarp();
+  load_C(tile, v, r);
+  __syncwarp();
+}
 // layout changes without arithmetic
 __device__ __forceinline__ void s_to_c(uint32_t (&r)[32], uint32_t* tile, int v) {
   store_S(tile, v, r);

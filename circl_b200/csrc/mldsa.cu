@@ -324,20 +324,21 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
 #pragma unroll
   for (int c = 0; c < 32; c++) acc[c] = 0;
 #pragma unroll 1
-  for (int j = 0; j < L; j++) {
-    const uint4* ap = reinterpret_cast<const uint4*>(Ai + j * N + 32 * o.v);
-    const uint4* yp = reinterpret_cast<const uint4*>(yh + (op * L + j) * N + 32 * o.v);
+  for (int j = 0; j < L; j++) {  // coalesced "I" layout loads (128 contiguous bytes per octet and instruction)
+    uint4 x[8], z[8];
+    gload_I_ro(Ai + j * N, o.v, x);
+    gload_I(yh + (op * L + j) * N, o.v, z);
 #pragma unroll
     for (int c = 0; c < 8; c++) {
-      const uint4 x = __ldg(ap + c), z = yp[c];
-      acc[4 * c] += mont_mul(x.x, z.x);
-      acc[4 * c + 1] += mont_mul(x.y, z.y);
-      acc[4 * c + 2] += mont_mul(x.z, z.z);
-      acc[4 * c + 3] += mont_mul(x.w, z.w);
+      acc[4 * c] += mont_mul(x[c].x, z[c].x);
+      acc[4 * c + 1] += mont_mul(x[c].y, z[c].y);
+      acc[4 * c + 2] += mont_mul(x[c].z, z[c].z);
+      acc[4 * c + 3] += mont_mul(x[c].w, z[c].w);
     }
   }
 #pragma unroll
   for (int c = 0; c < 32; c++) acc[c] = reduce_le2q(acc[c]);
+  i_to_c(acc, o.tile, o.v);
   LaneTw t;
   load_lane_tw_inv(t, zetas + 256, o.v);
   invntt_octet(acc, o.tile, o.v, t);  // -> S layout: acc[2s+b] = coefficient 16s + 2v + b
@@ -445,16 +446,17 @@ __global__ void __launch_bounds__(128) cntt_kernel(const uint32_t* __restrict__ 
 // InvNTT(c-hat . x-hat) on an octet: returns S layout
 __device__ __forceinline__ void c_times(uint32_t (&r)[32], const uint32_t* __restrict__ chat,
                                         const uint32_t* __restrict__ xhat, const OctetCtx& o, const volatile uint32_t* iz) {
-  const uint4* cp = reinterpret_cast<const uint4*>(chat + 32 * o.v);
-  const uint4* xp = reinterpret_cast<const uint4*>(xhat + 32 * o.v);
+  uint4 x[8], z[8];
+  gload_I(chat, o.v, x);
+  gload_I_ro(xhat, o.v, z);
 #pragma unroll
   for (int c = 0; c < 8; c++) {
-    const uint4 x = cp[c], z = __ldg(xp + c);
-    r[4 * c] = mont_mul(x.x, z.x);
-    r[4 * c + 1] = mont_mul(x.y, z.y);
-    r[4 * c + 2] = mont_mul(x.z, z.z);
-    r[4 * c + 3] = mont_mul(x.w, z.w);
+    r[4 * c] = mont_mul(x[c].x, z[c].x);
+    r[4 * c + 1] = mont_mul(x[c].y, z[c].y);
+    r[4 * c + 2] = mont_mul(x[c].z, z[c].z);
+    r[4 * c + 3] = mont_mul(x[c].w, z[c].w);
   }
+  i_to_c(r, o.tile, o.v);
   invntt_octet_smem(r, o.tile, o.v, iz);
 }
 

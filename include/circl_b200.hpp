@@ -1,0 +1,302 @@
+// include/circl_b200.hpp -- C++ host-side mirror of CIRCL's kem.Scheme / sign.Scheme over the C ABI.
+//
+// CIRCL is Go and this build image has no Go toolchain, so besides the cgo shim delivered as source
+// (go/), this header is the *compiled* host side above libcirclb200.so: same method names, argument
+// meaning and error behaviour as
+//   kem/kem.go:14-121            kem.Scheme, kem.PublicKey/PrivateKey, kem.Err*
+//   kem/mlkem/mlkem768/kyber.go:267-407   (scheme boilerplate; mlkem512/1024 identical)
+//   sign/sign.go:14-119          sign.Scheme, sign.SignatureOpts, sign.Err*
+//   sign/mldsa/mldsa65/dilithium.go:256-366
+//   kem/schemes/schemes.go:57-72, sign/schemes/schemes.go:56-71   (ByName, case-insensitive)
+// Go's (value, error) returns become exceptions; Go panics (programmer errors) become std::logic_error.
+// Batch methods are added beside the single-op ones.  Header-only; link with -lcirclb200.
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "circl_b200.h"
+
+namespace circl {
+
+using Bytes = std::vector<uint8_t>;
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+inline void init(int device = 0) {
+  if (cb200_init(device) != 0) throw Error(cb200_last_error());
+}
+inline void fill_random(uint8_t* p, size_t n) {  // crypto/rand stand-in for the mirror (std::random_device)
+  std::random_device rd;
+  for (size_t i = 0; i < n; i++) p[i] = (uint8_t)rd();
+}
+
+namespace kem {
+
+struct ErrTypeMismatch : Error { ErrTypeMismatch() : Error("kem: type mismatch") {} };
+struct ErrSeedSize : Error { ErrSeedSize() : Error("kem: invalid seed size") {} };
+struct ErrPubKeySize : Error { ErrPubKeySize() : Error("kem: invalid public key size") {} };
+struct ErrCiphertextSize : Error { ErrCiphertextSize() : Error("kem: invalid ciphertext size") {} };
+struct ErrPrivKeySize : Error { ErrPrivKeySize() : Error("kem: invalid private key size") {} };
+struct ErrPubKey : Error { ErrPubKey() : Error("kem: invalid public key") {} };
+struct ErrPrivKey : Error { ErrPrivKey() : Error("kem: invalid private key") {} };
+
+class Scheme;
+
+class PublicKey {  // kem.PublicKey (kem/kem.go:14-20)
+ public:
+  PublicKey(const Scheme* s, Bytes b) : scheme_(s), packed_(std::move(b)) {}
+  const Scheme* GetScheme() const { return scheme_; }
+  const Bytes& MarshalBinary() const { return packed_; }
+  bool Equal(const PublicKey& o) const { return scheme_ == o.scheme_ && packed_ == o.packed_; }
+
+ private:
+  const Scheme* scheme_;
+  Bytes packed_;
+};
+
+class PrivateKey {  // kem.PrivateKey (kem/kem.go:22-30)
+ public:
+  PrivateKey(const Scheme* s, Bytes b) : scheme_(s), packed_(std::move(b)) {}
+  const Scheme* GetScheme() const { return scheme_; }
+  const Bytes& MarshalBinary() const { return packed_; }
+  bool Equal(const PrivateKey& o) const { return scheme_ == o.scheme_ && packed_ == o.packed_; }
+  PublicKey Public() const;
+
+ private:
+  const Scheme* scheme_;
+  Bytes packed_;
+};
+
+class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024
+ public:
+  Scheme(std::string name, int k) : name_(std::move(name)), k_(k) {}
+  const std::string& Name() const { return name_; }
+  size_t CiphertextSize() const { return cb200_mlkem_ciphertext_size(k_); }
+  size_t SharedKeySize() const { return 32; }
+  size_t PrivateKeySize() const { return cb200_mlkem_private_key_size(k_); }
+  size_t PublicKeySize() const { return cb200_mlkem_public_key_size(k_); }
+  size_t SeedSize() const { return 64; }
+  size_t EncapsulationSeedSize() const { return 32; }
+
+  std::pair<PublicKey, PrivateKey> DeriveKeyPair(const Bytes& seed) const {  // kyber.go:337-346
+    if (seed.size() != SeedSize()) throw std::logic_error("kem: invalid seed size");  // Go panics here
+    Bytes ek(PublicKeySize()), dk(PrivateKeySize());
+    check(cb200_mlkem_keygen(k_, seed.data(), ek.data(), dk.data(), 1));
+    return {PublicKey(this, std::move(ek)), PrivateKey(this, std::move(dk))};
+  }
+  std::pair<PublicKey, PrivateKey> GenerateKeyPair() const {  // kyber.go:281-283
+    Bytes seed(SeedSize());
+    fill_random(seed.data(), seed.size());
+    return DeriveKeyPair(seed);
+  }
+  PublicKey UnmarshalBinaryPublicKey(const Bytes& buf) const {  // kyber.go:390-396
+    if (buf.size() != PublicKeySize()) throw ErrPubKeySize();
+    return PublicKey(this, buf);
+  }
+  PrivateKey UnmarshalBinaryPrivateKey(const Bytes& buf) const {  // kyber.go:398-407
+    if (buf.size() != PrivateKeySize()) throw ErrPrivKeySize();
+    return PrivateKey(this, buf);
+  }
+  // (ct, ss)
+  std::pair<Bytes, Bytes> EncapsulateDeterministically(const PublicKey& pk, const Bytes& seed) const {  // kyber.go:359-374
+    if (seed.size() != EncapsulationSeedSize()) throw ErrSeedSize();
+    if (pk.GetScheme() != this) throw ErrTypeMismatch();
+    Bytes ct(CiphertextSize()), ss(32);
+    check(cb200_mlkem_encaps(k_, pk.MarshalBinary().data(), 0, seed.data(), ct.data(), ss.data(), nullptr, 1));
+    return {std::move(ct), std::move(ss)};
+  }
+  std::pair<Bytes, Bytes> Encapsulate(const PublicKey& pk) const {  // kyber.go:348-357
+    Bytes seed(EncapsulationSeedSize());
+    fill_random(seed.data(), seed.size());
+    return EncapsulateDeterministically(pk, seed);
+  }
+  Bytes Decapsulate(const PrivateKey& sk, const Bytes& ct) const {  // kyber.go:376-388
+    if (sk.GetScheme() != this) throw ErrTypeMismatch();
+    if (ct.size() != CiphertextSize()) throw ErrCiphertextSize();
+    Bytes ss(32);
+    check(cb200_mlkem_decaps(k_, sk.MarshalBinary().data(), 0, ct.data(), ss.data(), nullptr, 1));
+    return ss;
+  }
+  // ---- batch entry points (keys: one packed key = shared, or n keys back to back)
+  void EncapsulateBatch(const Bytes& eks, const Bytes& seeds, Bytes& cts, Bytes& sss) const {
+    if (seeds.size() % 32) throw ErrSeedSize();
+    const size_t n = seeds.size() / 32;
+    const bool shared = eks.size() == PublicKeySize();
+    if (!shared && eks.size() != n * PublicKeySize()) throw ErrPubKeySize();
+    cts.resize(n * CiphertextSize());
+    sss.resize(n * 32);
+    check(cb200_mlkem_encaps(k_, eks.data(), shared ? 0 : PublicKeySize(), seeds.data(), cts.data(), sss.data(), nullptr, n));
+  }
+  void DecapsulateBatch(const Bytes& dks, const Bytes& cts, Bytes& sss) const {
+    if (cts.size() % CiphertextSize()) throw ErrCiphertextSize();
+    const size_t n = cts.size() / CiphertextSize();
+    const bool shared = dks.size() == PrivateKeySize();
+    if (!shared && dks.size() != n * PrivateKeySize()) throw ErrPrivKeySize();
+    sss.resize(n * 32);
+    check(cb200_mlkem_decaps(k_, dks.data(), shared ? 0 : PrivateKeySize(), cts.data(), sss.data(), nullptr, n));
+  }
+  void DeriveKeyPairBatch(const Bytes& seeds, Bytes& eks, Bytes& dks) const {
+    if (seeds.size() % 64) throw ErrSeedSize();
+    const size_t n = seeds.size() / 64;
+    eks.resize(n * PublicKeySize());
+    dks.resize(n * PrivateKeySize());
+    check(cb200_mlkem_keygen(k_, seeds.data(), eks.data(), dks.data(), n));
+  }
+  int k() const { return k_; }
+
+ private:
+  static void check(int rc) {
+    if (rc == 0) return;
+    if (rc == CB200_ERR_PUBKEY) throw ErrPubKey();
+    if (rc == CB200_ERR_PRIVKEY) throw ErrPrivKey();
+    if (rc == CB200_ERR_ARG) throw std::logic_error(cb200_last_error());
+    throw Error(cb200_last_error());
+  }
+  std::string name_;
+  int k_;
+};
+
+inline PublicKey PrivateKey::Public() const {
+  const int k = scheme_->k();
+  return PublicKey(scheme_, Bytes(packed_.begin() + 384 * k, packed_.begin() + 384 * k + 384 * k + 32));
+}
+
+inline std::string lower(std::string s) {
+  std::transform(s.begin(), s.end(), s.begin(), [](unsigned char c) { return (char)std::tolower(c); });
+  return s;
+}
+inline const std::vector<const Scheme*>& All() {  // kem/schemes/schemes.go:75
+  static const Scheme s512("ML-KEM-512", 2), s768("ML-KEM-768", 3), s1024("ML-KEM-1024", 4);
+  static const std::vector<const Scheme*> all = {&s512, &s768, &s1024};
+  return all;
+}
+inline const Scheme* ByName(const std::string& name) {  // kem/schemes/schemes.go:70 (nullptr = no such scheme)
+  for (const Scheme* s : All())
+    if (lower(s->Name()) == lower(name)) return s;
+  return nullptr;
+}
+
+}  // namespace kem
+
+namespace sign {
+
+struct ErrContextTooLong : Error { ErrContextTooLong() : Error("sign: context string too long") {} };
+struct ErrPubKeySize : Error { ErrPubKeySize() : Error("sign: invalid public key size") {} };
+struct ErrPrivKeySize : Error { ErrPrivKeySize() : Error("sign: invalid private key size") {} };
+struct ErrSeedSize : Error { ErrSeedSize() : Error("sign: invalid seed size") {} };
+
+struct SignatureOpts {  // sign/sign.go:14-18
+  std::string Context;
+};
+
+class Scheme;
+class PublicKey {
+ public:
+  PublicKey(const Scheme* s, Bytes b) : scheme_(s), packed_(std::move(b)) {}
+  const Scheme* GetScheme() const { return scheme_; }
+  const Bytes& MarshalBinary() const { return packed_; }
+  bool Equal(const PublicKey& o) const { return packed_ == o.packed_; }
+
+ private:
+  const Scheme* scheme_;
+  Bytes packed_;
+};
+class PrivateKey {
+ public:
+  PrivateKey(const Scheme* s, Bytes b) : scheme_(s), packed_(std::move(b)) {}
+  const Scheme* GetScheme() const { return scheme_; }
+  const Bytes& MarshalBinary() const { return packed_; }
+  bool Equal(const PrivateKey& o) const { return packed_ == o.packed_; }
+
+ private:
+  const Scheme* scheme_;
+  Bytes packed_;
+};
+
+class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-65
+ public:
+  std::string Name() const { return "ML-DSA-65"; }
+  size_t PublicKeySize() const { return cb200_mldsa65_public_key_size(); }
+  size_t PrivateKeySize() const { return cb200_mldsa65_private_key_size(); }
+  size_t SignatureSize() const { return cb200_mldsa65_signature_size(); }
+  size_t SeedSize() const { return 32; }
+  bool SupportsContext() const { return true; }
+
+  std::pair<PublicKey, PrivateKey> DeriveKey(const Bytes& seed) const {  // dilithium.go:266-276
+    if (seed.size() != SeedSize()) throw std::logic_error("sign: invalid seed size");  // Go panics here
+    Bytes pk(PublicKeySize()), sk(PrivateKeySize());
+    check(cb200_mldsa65_keygen(seed.data(), pk.data(), sk.data(), 1));
+    return {PublicKey(this, std::move(pk)), PrivateKey(this, std::move(sk))};
+  }
+  std::pair<PublicKey, PrivateKey> GenerateKey() const {
+    Bytes seed(SeedSize());
+    fill_random(seed.data(), seed.size());
+    return DeriveKey(seed);
+  }
+  PublicKey UnmarshalBinaryPublicKey(const Bytes& b) const {
+    if (b.size() != PublicKeySize()) throw ErrPubKeySize();
+    return PublicKey(this, b);
+  }
+  PrivateKey UnmarshalBinaryPrivateKey(const Bytes& b) const {
+    if (b.size() != PrivateKeySize()) throw ErrPrivKeySize();
+    return PrivateKey(this, b);
+  }
+  // deterministic signing, as sign.Scheme.Sign does (dilithium.go:282-303)
+  Bytes Sign(const PrivateKey& sk, const Bytes& msg, const SignatureOpts* opts = nullptr) const {
+    const std::string ctx = opts ? opts->Context : std::string();
+    if (ctx.size() > 255) throw ErrContextTooLong();
+    Bytes sig(SignatureSize());
+    const uint64_t off[2] = {0, msg.size()};
+    Bytes padded(msg);
+    padded.resize(msg.size() + 8);
+    check(cb200_mldsa65_sign(sk.MarshalBinary().data(), 0, padded.data(), off, (const uint8_t*)ctx.data(), ctx.size(), nullptr,
+                             sig.data(), nullptr, 1, 0, nullptr));
+    return sig;
+  }
+  bool Verify(const PublicKey& pk, const Bytes& msg, const Bytes& sig, const SignatureOpts* opts = nullptr) const {
+    const std::string ctx = opts ? opts->Context : std::string();
+    if (ctx.size() > 255 || sig.size() != SignatureSize()) return false;  // dilithium.go:116-118
+    uint8_t ok = 0;
+    const uint64_t off[2] = {0, msg.size()};
+    Bytes padded(msg);
+    padded.resize(msg.size() + 8);
+    check(cb200_mldsa65_verify(pk.MarshalBinary().data(), 0, padded.data(), off, (const uint8_t*)ctx.data(), ctx.size(),
+                               sig.data(), &ok, 1, 0));
+    return ok != 0;
+  }
+  // batch: messages back to back with n+1 offsets; sks: one key (shared) or n keys
+  void SignBatch(const Bytes& sks, const Bytes& msgs, const std::vector<uint64_t>& off, const std::string& ctx, Bytes& sigs) const {
+    if (ctx.size() > 255) throw ErrContextTooLong();
+    const size_t n = off.size() - 1;
+    const bool shared = sks.size() == PrivateKeySize();
+    if (!shared && sks.size() != n * PrivateKeySize()) throw ErrPrivKeySize();
+    sigs.resize(n * SignatureSize());
+    Bytes padded(msgs);
+    padded.resize(msgs.size() + 8);
+    check(cb200_mldsa65_sign(sks.data(), shared ? 0 : PrivateKeySize(), padded.data(), off.data(), (const uint8_t*)ctx.data(),
+                             ctx.size(), nullptr, sigs.data(), nullptr, n, 0, nullptr));
+  }
+
+ private:
+  static void check(int rc) {
+    if (rc == 0) return;
+    if (rc == CB200_ERR_ARG) throw std::logic_error(cb200_last_error());
+    throw Error(cb200_last_error());  // includes CB200_ERR_SIGN_ATTEMPTS (the reference panics after 576 attempts)
+  }
+};
+
+inline const Scheme* ByName(const std::string& name) {  // sign/schemes/schemes.go:69
+  static const Scheme mldsa65;
+  return kem::lower(name) == "ml-dsa-65" ? &mldsa65 : nullptr;
+}
+
+}  // namespace sign
+}  // namespace circl

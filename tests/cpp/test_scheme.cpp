@@ -1,0 +1,98 @@
+// tests/cpp/test_scheme.cpp -- exercises include/circl_b200.hpp (the compiled host-side mirror of kem.Scheme /
+// sign.Scheme) the way kem/schemes/schemes_test.go:53 and sign/schemes/schemes_test.go:17 exercise the Go API.
+// Prints hex transcripts for fixed seeds; tests/test_gpu_cpp_host.py compares them with the oracle.
+#include <cstdio>
+#include <cstdlib>
+
+#include "circl_b200.hpp"
+
+using namespace circl;
+
+static void hex(const char* tag, const Bytes& b) {
+  printf("%s=", tag);
+  for (uint8_t x : b) printf("%02x", x);
+  printf("\n");
+}
+#define REQUIRE(c)                                             \
+  do {                                                         \
+    if (!(c)) {                                                \
+      fprintf(stderr, "REQUIRE failed: %s (%s:%d)\n", #c, __FILE__, __LINE__); \
+      return 1;                                                \
+    }                                                          \
+  } while (0)
+
+int main() {
+  init(0);
+  for (const char* name : {"ML-KEM-512", "ml-kem-768", "ML-KEM-1024"}) {
+    const kem::Scheme* s = kem::ByName(name);
+    REQUIRE(s != nullptr);
+    Bytes seed(s->SeedSize()), eseed(s->EncapsulationSeedSize());
+    for (size_t i = 0; i < seed.size(); i++) seed[i] = (uint8_t)(i * 7 + s->k());
+    for (size_t i = 0; i < eseed.size(); i++) eseed[i] = (uint8_t)(255 - i);
+    auto kp = s->DeriveKeyPair(seed);
+    REQUIRE(kp.first.MarshalBinary().size() == s->PublicKeySize());
+    REQUIRE(kp.second.Public().Equal(kp.first));
+    auto enc = s->EncapsulateDeterministically(kp.first, eseed);
+    REQUIRE(enc.first.size() == s->CiphertextSize() && enc.second.size() == s->SharedKeySize());
+    REQUIRE(s->Decapsulate(kp.second, enc.first) == enc.second);
+    Bytes bad = enc.first;
+    bad[3] ^= 1;
+    REQUIRE(s->Decapsulate(kp.second, bad) != enc.second);  // implicit rejection
+    printf("scheme=%s\n", s->Name().c_str());
+    hex("ek", kp.first.MarshalBinary());
+    hex("dk", kp.second.MarshalBinary());
+    hex("ct", enc.first);
+    hex("ss", enc.second);
+    hex("ss_rejected", s->Decapsulate(kp.second, bad));
+    // error behaviour
+    bool threw = false;
+    try { s->UnmarshalBinaryPublicKey(Bytes(10)); } catch (const kem::ErrPubKeySize&) { threw = true; }
+    REQUIRE(threw);
+    threw = false;
+    try { s->EncapsulateDeterministically(kp.first, Bytes(31)); } catch (const kem::ErrSeedSize&) { threw = true; }
+    REQUIRE(threw);
+    threw = false;
+    Bytes noncanon = kp.first.MarshalBinary();
+    noncanon[0] = 0xff;
+    noncanon[1] |= 0x0f;
+    try { s->EncapsulateDeterministically(s->UnmarshalBinaryPublicKey(noncanon), eseed); } catch (const kem::ErrPubKey&) { threw = true; }
+    REQUIRE(threw);
+    // batch of 300 with a shared key equals 300 single calls on the first and last
+    Bytes seeds(32 * 300), cts, sss;
+    for (size_t i = 0; i < seeds.size(); i++) seeds[i] = (uint8_t)(i * 13);
+    s->EncapsulateBatch(kp.first.MarshalBinary(), seeds, cts, sss);
+    auto one = s->EncapsulateDeterministically(kp.first, Bytes(seeds.end() - 32, seeds.end()));
+    REQUIRE(Bytes(cts.end() - s->CiphertextSize(), cts.end()) == one.first);
+    Bytes back;
+    s->DecapsulateBatch(kp.second.MarshalBinary(), cts, back);
+    REQUIRE(back == sss);
+  }
+  REQUIRE(kem::ByName("no-such-kem") == nullptr);
+
+  const sign::Scheme* d = sign::ByName("ML-DSA-65");
+  REQUIRE(d != nullptr && d->SupportsContext());
+  Bytes dseed(32);
+  for (size_t i = 0; i < 32; i++) dseed[i] = (uint8_t)(3 * i + 1);
+  auto dk = d->DeriveKey(dseed);
+  Bytes msg = {'h', 'e', 'l', 'l', 'o'};
+  sign::SignatureOpts opts{"ctx"};
+  Bytes sig = d->Sign(dk.second, msg, &opts);
+  REQUIRE(sig.size() == d->SignatureSize());
+  REQUIRE(d->Verify(dk.first, msg, sig, &opts));
+  REQUIRE(!d->Verify(dk.first, msg, sig));  // wrong context
+  Bytes tam = sig;
+  tam[100] ^= 4;
+  REQUIRE(!d->Verify(dk.first, msg, tam, &opts));
+  REQUIRE(!d->Verify(dk.first, msg, Bytes(sig.begin(), sig.end() - 1), &opts));
+  bool threw = false;
+  sign::SignatureOpts longctx{std::string(256, 'x')};
+  try { d->Sign(dk.second, msg, &longctx); } catch (const sign::ErrContextTooLong&) { threw = true; }
+  REQUIRE(threw);
+  printf("scheme=%s\n", d->Name().c_str());
+  hex("pk", dk.first.MarshalBinary());
+  hex("sk", dk.second.MarshalBinary());
+  hex("sig", sig);
+  printf("ALL OK\n");
+  cb200_shutdown();
+  return 0;
+}

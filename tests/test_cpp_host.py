@@ -1,0 +1,56 @@
+"""The compiled host-side mirror (include/circl_b200.hpp): it must compile against the header (CPU),
+and on the GPU its transcripts must equal the oracle's for the same seeds."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "tests", "cpp", "test_scheme")
+
+
+def build_exe():
+    from circl_b200 import _ffi
+    assert os.path.exists(_ffi.LIB_PATH)
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "tests", "cpp", "test_scheme.cpp"), "-o", EXE,
+           "-L", os.path.join(ROOT, "circl_b200"), "-lcirclb200", "-Wl,-rpath," + os.path.join(ROOT, "circl_b200")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    return EXE
+
+
+def test_cpp_host_layer_compiles_and_links():
+    build_exe()
+
+
+@pytest.mark.gpu
+def test_cpp_host_layer_matches_oracle():
+    import oracle
+    exe = build_exe()
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "ALL OK" in r.stdout
+    blocks, cur = {}, None
+    for line in r.stdout.splitlines():
+        if line.startswith("scheme="):
+            cur = line.split("=", 1)[1]
+            blocks[cur] = {}
+        elif "=" in line and cur:
+            k, v = line.split("=", 1)
+            blocks[cur][k] = bytes.fromhex(v)
+    for name, k in (("ML-KEM-512", 2), ("ML-KEM-768", 3), ("ML-KEM-1024", 4)):
+        seed = bytes((i * 7 + k) & 0xFF for i in range(64))
+        eseed = bytes(255 - i for i in range(32))
+        ek, dk = oracle.mlkem_keygen(k, seed)
+        ct, ss = oracle.mlkem_encaps(k, ek, eseed)
+        b = blocks[name]
+        assert (b["ek"], b["dk"], b["ct"], b["ss"]) == (ek, dk, ct, ss)
+        bad = bytearray(ct)
+        bad[3] ^= 1
+        assert b["ss_rejected"] == oracle.mlkem_decaps(k, dk, bytes(bad))
+    dseed = bytes((3 * i + 1) & 0xFF for i in range(32))
+    pk, sk = oracle.mldsa65_keygen(dseed)
+    b = blocks["ML-DSA-65"]
+    assert (b["pk"], b["sk"]) == (pk, sk)
+    assert b["sig"] == oracle.mldsa65_sign(sk, b"hello", ctx=b"ctx")[0]

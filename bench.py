@@ -64,6 +64,16 @@ def host_threads() -> int:
     return n
 
 
+def ncu_traffic(kernel: str, units_per_launch: float):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json), scaled
+    to the units this run's launches process; None if no capture exists for that kernel."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[kernel]
+        return t["bytes_per_launch"] * units_per_launch / t["units_per_launch"]
+    except Exception:
+        return None
+
+
 def measured_peak():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -310,10 +320,11 @@ def run_mldsa(args):
     # process the whole batch, so its per-step time is the launch duration the roofline refers to
     achieved = MLDSA["bytes_per_op"] * n / (kernels[dom_name]["ms_total"] * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                "frac": achieved / peak, "traffic": ncu_traffic(dom_name, n * att), "peak_kind": peak_kind,
                 "share_of_step": kernels[dom_name]["ms_total"] / tot,
                 "note": "integer-ALU (Keccak + NTT) bound; achieved = 7373 algorithmic B/op x batch / time of this kernel "
-                        "class summed over the rounds of one step",
+                        "class summed over the rounds of one step; traffic = ncu dram bytes of the first round scaled to "
+                        "all op-rounds of the step",
                 "kernels_ms_per_step": {k_: round(v["ms_total"], 3) for k_, v in kernels.items()}}
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -518,10 +529,11 @@ def main():
     dom_ms = dom["ms_total"] / dom["launches"]
     achieved = wl["bytes_per_op"] * units_per_launch / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_kind": peak_kind,
+                "frac": achieved / peak, "traffic": ncu_traffic(dom_name, units_per_launch), "peak_kind": peak_kind,
                 "share_of_step": dom["ms_total"] / total_kernel_ms,
-                "note": "path is integer-ALU (Keccak) bound, not HBM bound; achieved = %d algorithmic B/op x %d ops "
-                        "per launch / mean launch time" % (wl["bytes_per_op"], int(units_per_launch)),
+                "note": "path is integer-ALU (Keccak) bound, not HBM bound (ncu: sample_kernel ALU pipe 89% active, "
+                        "profiles/r01b_ncu_mlkem.txt); achieved = %d algorithmic B/op x %d ops per launch / mean "
+                        "launch time; traffic = ncu dram bytes per launch" % (wl["bytes_per_op"], int(units_per_launch)),
                 "kernels_ms_per_step": {k_: round(v["ms_total"], 4) for k_, v in kernels.items()}}
 
     # ---- secondary: raw 256-point NTT (BASELINE configs[1]); 512 MiB in place, larger than L2
@@ -548,7 +560,8 @@ def main():
             gbs = npoly * 1024 / (ms * 1e-3) / 1e9
             ntt[label] = {"value": world * npoly / (ms * 1e-3), "unit": "NTT/s", "ms_per_step": ms,
                           "roofline": {"bound": "hbm", "achieved": gbs, "peak": peak, "unit": "GB/s",
-                                       "frac": gbs / peak, "traffic": None, "peak_kind": peak_kind}}
+                                       "frac": gbs / peak, "peak_kind": peak_kind,
+                                       "traffic": ncu_traffic("kyber_ntt" if label == "forward" else "kyber_invntt", npoly)}}
         ntt["config"] = {"workload": NTT_DESC, "polys_per_gpu": npoly, "bytes_per_ntt": 1024,
                          "l2": "input 512 MiB > 126 MB L2; kernel reads and writes every byte once"}
         # e2e for the NTT through the C ABI with pinned host memory

@@ -84,42 +84,72 @@ def measured_peak():
     return 6650.0, "fallback"
 
 
-# ---------------------------------------------------------------- synthetic inputs
-def synth_keys(k: int, count: int, seed: int):
-    """`count` canonical encapsulation keys: 256k uniform coefficients < q packed 12-bit, then rho.
-    (Any such byte string is a valid ML-KEM ek; no private key is needed to encapsulate.)"""
+# ---------------------------------------------------------------- synthetic inputs (SURVEY.md 8(d))
+def _shake(tag: int, i: int, width: int, outlen: int) -> bytes:
+    import hashlib
+    return hashlib.shake_256(bytes([tag]) + i.to_bytes(width, "little")).digest(outlen)
+
+
+def keygen_seeds(tag: int, count: int, outlen: int):
+    """Key-pool seeds: SHAKE256(tag || LE32(j), outlen)  (tag 0x00: ML-KEM d||z, 0x02: ML-DSA xi)."""
     import numpy as np
-    rng = np.random.default_rng(seed)
-    coef = rng.integers(0, Q, size=(count, 128 * k, 2), dtype=np.uint16).astype(np.uint32)
-    t0, t1 = coef[..., 0], coef[..., 1]
-    packed = np.stack([t0 & 0xFF, (t0 >> 8) | ((t1 & 0xF) << 4), t1 >> 4], axis=-1).astype(np.uint8)
-    rho = rng.integers(0, 256, size=(count, 32), dtype=np.uint8)
-    return np.concatenate([packed.reshape(count, 384 * k), rho], axis=1)
+    return np.frombuffer(b"".join(_shake(tag, j, 4, outlen) for j in range(count)), dtype=np.uint8).reshape(count, outlen)
 
 
-def synth_mldsa_keys(count: int, seed: int):
-    """`count` well-formed ML-DSA-65 private keys: rho, key, tr random; s1, s2 nibbles uniform in 0..8
-    (eta = 4); t0 uniform 13-bit fields.  Signing never checks t0 against s1, s2, and real t0 is
-    uniform in (-2^12, 2^12], so these exercise exactly the distribution of genuine keys."""
+def op_seeds(tag: int, first: int, n: int):
+    """Per-op 32-byte inputs: SHAKE256(tag || LE64(i), 32)  (tag 0x01: ML-KEM m_i, 0x03: ML-DSA msg_i)."""
     import numpy as np
-    rng = np.random.default_rng(seed)
-    head = rng.integers(0, 256, size=(count, 128), dtype=np.uint8)
-    nib = rng.integers(0, 9, size=(count, 11 * 256), dtype=np.uint8)
-    s = (nib[:, 0::2] | (nib[:, 1::2] << 4)).astype(np.uint8)
-    t0 = rng.integers(0, 256, size=(count, 6 * 416), dtype=np.uint8)
-    return np.concatenate([head, s, t0], axis=1)
+    return np.frombuffer(b"".join(_shake(tag, i, 8, 32) for i in range(first, first + n)), dtype=np.uint8).reshape(n, 32)
 
 
-def synth_seeds(n: int, seed: int):
+def mlkem_key_pool(k: int, count: int, on_gpu: bool):
+    """1024 real encapsulation keys DeriveKeyPair(SHAKE256(0x00 || LE32(j), 64)).  Our arm derives them with the
+    GPU KeyGen of this library (the product path); the reference arm with the CPU restatement."""
     import numpy as np
-    return np.random.default_rng(seed).integers(0, 256, size=(n, 32), dtype=np.uint8)
+    seeds = keygen_seeds(0x00, count, 64)
+    if on_gpu:
+        from circl_b200 import mlkem
+        name = {2: "ML-KEM-512", 3: "ML-KEM-768", 4: "ML-KEM-1024"}[k]
+        return mlkem.ByName(name).DeriveKeyPairBatch(seeds)[0]
+    import oracle
+    return np.stack([np.frombuffer(oracle.mlkem_keygen(k, s.tobytes())[0], dtype=np.uint8) for s in seeds])
 
 
-def synth_polys(n: int, seed: int):
-    """RandAbsLeQ distribution of pke/kyber/internal/common/ntt_test.go:41-47."""
+def mldsa_key_pool(count: int, on_gpu: bool):
+    """1024 real ML-DSA-65 private keys DeriveKey(SHAKE256(0x02 || LE32(j), 32))."""
     import numpy as np
-    rng = np.random.default_rng(seed)
-    return (rng.integers(0, 2 * Q, size=(n, 256), dtype=np.uint16).astype(np.int32) - Q).astype(np.int16)
+    seeds = keygen_seeds(0x02, count, 32)
+    if on_gpu:
+        from circl_b200 import mldsa
+        return mldsa.ByName("ML-DSA-65").DeriveKeyBatch(seeds)[1]
+    import oracle
+    return np.stack([np.frombuffer(oracle.mldsa65_keygen(s.tobytes())[1], dtype=np.uint8) for s in seeds])
+
+
+def synth_polys(first_poly: int, n: int, device="cpu"):
+    """c = (splitmix64(0x243F6A8885A308D3 + idx) mod 6658) - 3329, idx = poly*256 + j: the RandAbsLeQ
+    distribution of pke/kyber/internal/common/ntt_test.go:41-47 from a counter-based generator.
+    Returns an (n, 256) int16 torch tensor on `device` (two's-complement int64 arithmetic, chunked)."""
+    import torch
+
+    def s64(x):  # uint64 constant -> the int64 with the same bits
+        return x - (1 << 64) if x >= (1 << 63) else x
+
+    def lsr(z, k):  # logical shift right on int64 bit patterns
+        return (z >> k) & ((1 << (64 - k)) - 1)
+
+    out = torch.empty((n, 256), dtype=torch.int16, device=device)
+    chunk = 1 << 17
+    for lo in range(0, n, chunk):
+        m = min(chunk, n - lo)
+        idx = torch.arange((first_poly + lo) * 256, (first_poly + lo + m) * 256, dtype=torch.int64, device=device)
+        z = idx + s64((0x243F6A8885A308D3 + 0x9E3779B97F4A7C15) & ((1 << 64) - 1))
+        z = (z ^ lsr(z, 30)) * s64(0xBF58476D1CE4E5B9)
+        z = (z ^ lsr(z, 27)) * s64(0x94D049BB133111EB)
+        z = z ^ lsr(z, 31)
+        r = torch.remainder(z, 6658) + torch.where(z < 0, (1 << 64) % 6658, 0)
+        out[lo:lo + m] = (torch.remainder(r, 6658) - 3329).to(torch.int16).view(m, 256)
+    return out
 
 
 # ---------------------------------------------------------------- clocks sampler
@@ -175,10 +205,10 @@ def run_reference(args):
     threads = host_threads()
     wl = WORKLOADS[args.workload]
     sample = 1 << 17
-    keys = synth_keys(wl["k"], 1024, seed=2024)
+    keys = mlkem_key_pool(wl["k"], 1024, on_gpu=False)
     idx = np.arange(sample) % 1024
     eks = np.ascontiguousarray(keys[idx])
-    seeds = synth_seeds(sample, seed=7)
+    seeds = op_seeds(0x01, 0, sample)
     times = []
     for step in range(args.warmup + args.steps):
         t0 = time.perf_counter()
@@ -211,15 +241,15 @@ def run_mldsa(args):
     rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
     log2 = args.batch_log2 if args.batch_log2 != 20 else 18
     n = 1 << log2
-    keys = synth_mldsa_keys(1024, seed=4242)
     threads = host_threads()
     if args.impl == "reference":
         if rank != 0:
             return 0
         import oracle
         sample = 1 << 12
+        keys = mldsa_key_pool(1024, on_gpu=False)
         sks = np.ascontiguousarray(keys[np.arange(sample) % 1024])
-        msgs = [bytes(m) for m in synth_seeds(sample, seed=9)]
+        msgs = [bytes(m) for m in op_seeds(0x03, 0, sample)]
         times = []
         for step in range(args.warmup + args.steps):
             t0 = time.perf_counter()
@@ -248,11 +278,12 @@ def run_mldsa(args):
     circl_b200.init(local)
     L = lib()
     peak, peak_kind = measured_peak()
+    keys = mldsa_key_pool(1024, on_gpu=True)
     gidx = (np.arange(n, dtype=np.int64) + rank * n) % 1024
     sk_h = torch.empty((n, 4032), dtype=torch.uint8, pin_memory=True)
     sk_h.numpy()[:] = keys[gidx]
     msg_h = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
-    msg_h.numpy()[:] = synth_seeds(n, seed=9 + rank)
+    msg_h.numpy()[:] = op_seeds(0x03, rank * n, n)
     off_h = torch.arange(0, 32 * (n + 1), 32, dtype=torch.int64).pin_memory()
     sig_h = torch.empty((n, 3309), dtype=torch.uint8, pin_memory=True)
     sk_d, msg_d, off_d = sk_h.cuda(), msg_h.cuda(), off_h.cuda()
@@ -343,7 +374,7 @@ def run_mldsa(args):
             "metric": "ML-DSA-65 sign/sec", "value": world * n / (ms_step * 1e-3), "unit": "sign/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "uint32", "data": "synthetic",
-            "config": {"workload": MLDSA["desc"], "batch_per_gpu": n, "sk": "per-op (stride 4032)", "key_pool": 1024,
+            "config": {"workload": MLDSA["desc"], "batch_per_gpu": n, "sk": "per-op (stride 4032)", "key_pool": "1024 keys DeriveKeyPair(SHAKE256(0x00||LE32(j))), op i uses key i mod 1024; m_i = SHAKE256(0x01||LE64(i))",
                        "attempts_per_signature": att, "l2": "per-op state 65 KB x batch, far larger than L2"},
             "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "sign/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": n * (4032 + 32 + 8), "d2h_bytes_per_step": n * 3310,
@@ -407,12 +438,12 @@ def main():
         return float(t.item())
 
     # ---- inputs: shard r owns global op indices [r*n, (r+1)*n); op i uses key pool[i mod 1024]
-    keys = synth_keys(wl["k"], 1024, seed=2024)
+    keys = mlkem_key_pool(wl["k"], 1024, on_gpu=True)
     gidx = (np.arange(n, dtype=np.int64) + rank * n) % 1024
     eks_h = torch.empty((n, wl["ek"]), dtype=torch.uint8, pin_memory=True)
     eks_h.numpy()[:] = keys[gidx]
     seeds_h = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
-    seeds_h.numpy()[:] = synth_seeds(n, seed=7 + rank)
+    seeds_h.numpy()[:] = op_seeds(0x01, rank * n, n)
     ct_h = torch.empty((n, wl["ct"]), dtype=torch.uint8, pin_memory=True)
     ss_h = torch.empty((n, 32), dtype=torch.uint8, pin_memory=True)
     eks_d, seeds_d = eks_h.cuda(), seeds_h.cuda()
@@ -542,9 +573,9 @@ def main():
         del eks_d, ct_d
         torch.cuda.empty_cache()
         npoly = 1 << 20
+        polys_d = synth_polys(rank * npoly, npoly, device="cuda")
         polys_h = torch.empty((npoly, 256), dtype=torch.int16, pin_memory=True)
-        polys_h.numpy()[:] = synth_polys(npoly, seed=11 + rank)
-        polys_d = polys_h.cuda()
+        polys_h.copy_(polys_d)
         ntt = {}
         for label, fn in (("forward", kyber.ntt_), ("inverse", kyber.inv_ntt_)):
             for _ in range(args.warmup):
@@ -591,7 +622,7 @@ def main():
                          "generic Go path (no Go toolchain on this image)",
                "outputs_match_gpu": parity}
         if ntt is not None:
-            ps = synth_polys(1 << 16, seed=11)
+            ps = synth_polys(0, 1 << 16).numpy()
             t0 = time.perf_counter()
             oracle.kyber_ntt_inplace_mt(ps, False, threads)
             ntt["cpu_baseline"] = {"value": (1 << 16) / (time.perf_counter() - t0), "unit": "NTT/s", "cores": threads,
@@ -604,7 +635,7 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
             "config": {"workload": wl["desc"], "batch_per_gpu": n, "ek": "per-op (stride %d)" % wl["ek"],
-                       "key_pool": 1024, "l2": "inputs+outputs 2.3 GiB per step, larger than L2",
+                       "key_pool": "1024 keys DeriveKeyPair(SHAKE256(0x00||LE32(j))), op i uses key i mod 1024; m_i = SHAKE256(0x01||LE64(i))", "l2": "inputs+outputs 2.3 GiB per step, larger than L2",
                        "sharding": "contiguous index ranges per rank; no collective during compute, results gathered to rank 0"},
             "e2e": {"value": world * n / (e2e_ms * 1e-3), "unit": "encaps/s", "ms_per_step": e2e_ms,
                     "h2d_bytes_per_step": n * (wl["ek"] + 32), "d2h_bytes_per_step": n * (wl["ct"] + 32 + 1),

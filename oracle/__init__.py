@@ -365,3 +365,59 @@ def mldsa65_sign_batch(sk: np.ndarray, msgs: list[bytes], rnd=None, nthreads: in
     if att < 0:
         raise RuntimeError("sign_batch failed")
     return sig, att
+
+
+# ------------------------------------------------------------------ ML-DSA, run-time parameter set (44 / 65 / 87)
+def mldsa_sizes(mode: int):
+    L = lib()
+    for f in ("orc_mldsa_pk_size", "orc_mldsa_sk_size", "orc_mldsa_sig_size"):
+        getattr(L, f).restype = C.c_size_t
+    return L.orc_mldsa_pk_size(mode), L.orc_mldsa_sk_size(mode), L.orc_mldsa_sig_size(mode)
+
+
+def mldsa_keygen(mode: int, seed32: bytes):
+    pksz, sksz, _ = mldsa_sizes(mode)
+    pk, sk = (C.c_uint8 * pksz)(), (C.c_uint8 * sksz)()
+    lib().orc_mldsa_keygen(mode, pk, sk, _buf(seed32))
+    return bytes(pk), bytes(sk)
+
+
+def mldsa_sign(mode: int, sk: bytes, msg: bytes, ctx: bytes = b"", rnd: bytes = bytes(32), internal: bool = False):
+    _, _, sigsz = mldsa_sizes(mode)
+    sig = (C.c_uint8 * sigsz)()
+    L = lib()
+    L.orc_mldsa_sign.restype = C.c_int
+    n = L.orc_mldsa_sign(mode, sig, _buf(sk), _buf(msg) if msg else None, C.c_size_t(len(msg)),
+                         _buf(ctx) if ctx else None, C.c_size_t(len(ctx)), _buf(rnd), int(internal))
+    if n < 0:
+        raise RuntimeError("sign: 576 attempts exhausted")
+    return bytes(sig), n
+
+
+def mldsa_verify(mode: int, pk: bytes, msg: bytes, sig: bytes, ctx: bytes = b"", internal: bool = False) -> bool:
+    L = lib()
+    L.orc_mldsa_verify.restype = C.c_int
+    return bool(L.orc_mldsa_verify(mode, _buf(pk), _buf(msg) if msg else None, C.c_size_t(len(msg)),
+                                   _buf(ctx) if ctx else None, C.c_size_t(len(ctx)), _buf(sig),
+                                   C.c_size_t(len(sig)), int(internal)))
+
+
+def mldsa_sign_batch(mode: int, sk: np.ndarray, msgs: list[bytes], rnd=None, nthreads: int = 1):
+    n = len(msgs)
+    _, sksz, sigsz = mldsa_sizes(mode)
+    sk = np.ascontiguousarray(sk, dtype=np.uint8)
+    stride = 0 if sk.ndim == 1 else sk.shape[1]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    blob = np.frombuffer(b"".join(msgs) or b"\0", dtype=np.uint8)
+    sig = np.empty((n, sigsz), dtype=np.uint8)
+    r = None if rnd is None else np.ascontiguousarray(rnd, dtype=np.uint8)
+    L = lib()
+    L.orc_mldsa_sign_batch.restype = C.c_int
+    L.orc_mldsa_sign_batch.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                       C.c_size_t, C.c_int]
+    att = L.orc_mldsa_sign_batch(mode, _ptr(sig), _ptr(sk), stride, _ptr(blob), _ptr(off),
+                                 None if r is None else _ptr(r), n, nthreads)
+    if att < 0:
+        raise RuntimeError("sign_batch failed")
+    return sig, att

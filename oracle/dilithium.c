@@ -5,8 +5,11 @@
  *   sign/internal/dilithium/{field.go, ntt.go, poly.go, pack.go, params/params.go}
  *   sign/mldsa/mldsa65/internal/{params.go, mat.go, vec.go, sample.go, rounding.go, pack.go, dilithium.go}
  *   sign/mldsa/mldsa65/dilithium.go:56-98 (external-interface framing, unsafeSignInternal)
- * Parameter set fixed to ML-DSA-65 (K=6, L=5, eta=4, tau=49, gamma1=2^19,
- * gamma2=261888, omega=55, c~ = 48 B, tr = 64 B, NIST=true).
+ * The parameter set is a run-time value (sign/dilithium/gen.go:80-162, NIST=true, tr = 64 B):
+ *   ML-DSA-44  K=4 L=4 eta=2 tau=39 gamma1=2^17 gamma2=(q-1)/88 omega=80 c~=32
+ *   ML-DSA-65  K=6 L=5 eta=4 tau=49 gamma1=2^19 gamma2=(q-1)/32 omega=55 c~=48
+ *   ML-DSA-87  K=8 L=7 eta=2 tau=60 gamma1=2^19 gamma2=(q-1)/32 omega=75 c~=64
+ * instead of one generated package per mode.
  */
 #include "oracle.h"
 #include <stdlib.h>
@@ -17,25 +20,38 @@
 #define QINV 4236238847u /* -(q^-1) mod 2^32, params.go */
 #define ROVER256 41978u
 #define D 13
-#define K 6
-#define L 5
-#define ETA 4
-#define TAU 49
-#define BETA (TAU * ETA)
-#define GAMMA1 (1u << 19)
-#define GAMMA2 261888u
-#define ALPHA (2 * GAMMA2)
-#define OMEGA 55
-#define CTILDE 48
+#define KMAX 8
+#define LMAX 7
 #define TRSIZE 64
-#define POLY_LEQETA 128
 #define POLY_T0 416
 #define POLY_T1 320
-#define POLY_LEGAMMA1 640
-#define POLY_W1 128
-#define SK_SIZE (32 + 32 + TRSIZE + POLY_LEQETA * (L + K) + POLY_T0 * K) /* 4032 */
-#define PK_SIZE (32 + POLY_T1 * K)                                        /* 1952 */
-#define SIG_SIZE (L * POLY_LEGAMMA1 + OMEGA + K + CTILDE)                 /* 3309 */
+
+typedef struct {
+  int mode, k, l, eta, tau, gamma1_bits, omega, ctilde;
+  uint32_t gamma2;
+} dparams;
+static const dparams MODES[3] = {
+    {44, 4, 4, 2, 39, 17, 80, 32, (Q - 1) / 88},
+    {65, 6, 5, 4, 49, 19, 55, 48, (Q - 1) / 32},
+    {87, 8, 7, 2, 60, 19, 75, 64, (Q - 1) / 32},
+};
+static const dparams *mode_of(int mode) {
+  for (int i = 0; i < 3; i++)
+    if (MODES[i].mode == mode) return &MODES[i];
+  return NULL;
+}
+#define P_BETA(p) ((uint32_t)((p)->tau * (p)->eta))
+#define P_GAMMA1(p) (1u << (p)->gamma1_bits)
+#define P_ALPHA(p) (2 * (p)->gamma2)
+#define P_LEQETA(p) ((p)->eta == 2 ? 96 : 128)                 /* PolyLeqEtaSize */
+#define P_LEGAMMA1(p) (32 * ((p)->gamma1_bits + 1))            /* PolyLeGamma1Size */
+#define P_W1(p) (32 * (23 - (p)->gamma1_bits))                 /* PolyW1Size */
+#define P_SK(p) (32 + 32 + TRSIZE + P_LEQETA(p) * ((p)->l + (p)->k) + POLY_T0 * (p)->k)
+#define P_PK(p) (32 + POLY_T1 * (p)->k)
+#define P_SIG(p) ((p)->l * P_LEGAMMA1(p) + (p)->omega + (p)->k + (p)->ctilde)
+size_t orc_mldsa_sk_size(int mode) { return P_SK(mode_of(mode)); }
+size_t orc_mldsa_pk_size(int mode) { return P_PK(mode_of(mode)); }
+size_t orc_mldsa_sig_size(int mode) { return P_SIG(mode_of(mode)); }
 
 typedef uint32_t poly[N];
 
@@ -195,55 +211,56 @@ static void unpack_t0(poly p, const uint8_t *buf) { /* pack.go:56-86 */
   unpack_bits(p, buf, N, 13);
   for (int i = 0; i < N; i++) p[i] = Q + (1u << (D - 1)) - p[i];
 }
-static void pack_leqeta(uint8_t *buf, const poly p) { /* internal/pack.go:13-20 */
+static void pack_leqeta(const dparams *P, uint8_t *buf, const poly p) { /* internal/pack.go:13-47: 4 or 3 bits */
   poly t;
-  for (int i = 0; i < N; i++) t[i] = (uint8_t)(Q + ETA - p[i]) & 15;
-  pack_bits(buf, t, N, 4);
+  for (int i = 0; i < N; i++) t[i] = (uint8_t)(Q + P->eta - p[i]);
+  pack_bits(buf, t, N, P->eta == 2 ? 3 : 4);
 }
-static void unpack_leqeta(poly p, const uint8_t *buf) { /* internal/pack.go:49-57 */
-  unpack_bits(p, buf, N, 4);
-  for (int i = 0; i < N; i++) p[i] = Q + ETA - p[i];
+static void unpack_leqeta(const dparams *P, poly p, const uint8_t *buf) { /* internal/pack.go:49-75 */
+  unpack_bits(p, buf, N, P->eta == 2 ? 3 : 4);
+  for (int i = 0; i < N; i++) p[i] = Q + P->eta - p[i];
 }
-static void unpack_legamma1(poly p, const uint8_t *buf) { /* internal/pack.go:177-195 */
-  unpack_bits(p, buf, N, 20);
+static void unpack_legamma1(const dparams *P, poly p, const uint8_t *buf) { /* internal/pack.go:146-203: 18 or 20 bits */
+  unpack_bits(p, buf, N, P->gamma1_bits + 1);
   for (int i = 0; i < N; i++) {
-    uint32_t v = GAMMA1 - p[i];
+    uint32_t v = P_GAMMA1(P) - p[i];
     v += (uint32_t)((int32_t)v >> 31) & Q;
     p[i] = v;
   }
 }
-static void pack_legamma1(uint8_t *buf, const poly p) { /* internal/pack.go:236-252 */
+static void pack_legamma1(const dparams *P, uint8_t *buf, const poly p) { /* internal/pack.go:205-254 */
   poly t;
   for (int i = 0; i < N; i++) {
-    uint32_t v = GAMMA1 - p[i];
+    uint32_t v = P_GAMMA1(P) - p[i];
     v += (uint32_t)((int32_t)v >> 31) & Q;
     t[i] = v;
   }
-  pack_bits(buf, t, N, 20);
+  pack_bits(buf, t, N, P->gamma1_bits + 1);
 }
-static void pack_w1(uint8_t *buf, const poly p) { pack_bits(buf, p, N, 4); } /* PackLe16, pack.go:102-108 */
-static void pack_hint(uint8_t *buf, poly h[K]) {                               /* internal/pack.go:77-95 */
+/* PolyPackW1 (internal/pack.go:256-271): PackLe16 (4 bits) for gamma1 = 2^19, 6 bits for gamma1 = 2^17 */
+static void pack_w1(const dparams *P, uint8_t *buf, const poly p) { pack_bits(buf, p, N, 23 - P->gamma1_bits); }
+static void pack_hint(const dparams *P, uint8_t *buf, poly *h) { /* internal/pack.go:77-95 */
   uint8_t off = 0;
-  for (int i = 0; i < K; i++) {
+  for (int i = 0; i < P->k; i++) {
     for (int j = 0; j < N; j++)
       if (h[i][j] != 0) buf[off++] = (uint8_t)j;
-    buf[OMEGA + i] = off;
+    buf[P->omega + i] = off;
   }
-  for (; off < OMEGA; off++) buf[off] = 0;
+  for (; off < P->omega; off++) buf[off] = 0;
 }
-static int unpack_hint(poly h[K], const uint8_t *buf) { /* internal/pack.go:113-140 */
-  memset(h, 0, sizeof(poly) * K);
+static int unpack_hint(const dparams *P, poly *h, const uint8_t *buf) { /* internal/pack.go:113-140 */
+  memset(h, 0, sizeof(poly) * P->k);
   uint8_t prev = 0;
-  for (int i = 0; i < K; i++) {
-    uint8_t sop = buf[OMEGA + i];
-    if (sop < prev || sop > OMEGA) return 0;
+  for (int i = 0; i < P->k; i++) {
+    uint8_t sop = buf[P->omega + i];
+    if (sop < prev || sop > P->omega) return 0;
     for (uint8_t j = prev; j < sop; j++) {
       if (j > prev && buf[j] <= buf[j - 1]) return 0;
       h[i][buf[j]] = 1;
     }
     prev = sop;
   }
-  for (uint8_t j = prev; j < OMEGA; j++)
+  for (uint8_t j = prev; j < P->omega; j++)
     if (buf[j] != 0) return 0;
   return 1;
 }
@@ -265,7 +282,7 @@ void orc_dil_derive_uniform(uint32_t p[N], const uint8_t seed[32], uint16_t nonc
     }
   }
 }
-void orc_dil_derive_leqeta(uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { /* sample.go:129-181, eta = 4 */
+static void derive_leqeta(const dparams *P, uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { /* sample.go:129-181 */
   orc_sponge h;
   uint8_t iv[66], buf[136];
   memcpy(iv, seed, 64);
@@ -273,33 +290,39 @@ void orc_dil_derive_leqeta(uint32_t p[N], const uint8_t seed[64], uint16_t nonce
   orc_sponge_init(&h, 136, 0x1f);
   orc_sponge_write(&h, iv, 66);
   int i = 0;
+  const uint32_t eta = (uint32_t)P->eta;
   while (i < N) {
     orc_sponge_read(&h, buf, 136);
     for (int j = 0; j < 136 && i < N; j++) {
       uint32_t t1 = buf[j] & 15, t2 = buf[j] >> 4;
-      if (t1 <= 2 * ETA) p[i++] = Q + ETA - t1;
-      if (t2 <= 2 * ETA && i < N) p[i++] = Q + ETA - t2;
+      if (eta == 2) {
+        if (t1 <= 14) { t1 -= ((205 * t1) >> 10) * 5; p[i++] = Q + eta - t1; }
+        if (t2 <= 14 && i < N) { t2 -= ((205 * t2) >> 10) * 5; p[i++] = Q + eta - t2; }
+      } else {
+        if (t1 <= 2 * eta) p[i++] = Q + eta - t1;
+        if (t2 <= 2 * eta && i < N) p[i++] = Q + eta - t2;
+      }
     }
   }
 }
-void orc_dil_derive_legamma1(uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { /* sample.go:197-209 */
-  uint8_t iv[66], buf[POLY_LEGAMMA1];
+static void derive_legamma1(const dparams *P, uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { /* sample.go:197-209 */
+  uint8_t iv[66], buf[640];
   memcpy(iv, seed, 64);
   iv[64] = (uint8_t)nonce; iv[65] = (uint8_t)(nonce >> 8);
-  orc_shake256(buf, POLY_LEGAMMA1, iv, 66);
-  unpack_legamma1(p, buf);
+  orc_shake256(buf, (size_t)P_LEGAMMA1(P), iv, 66);
+  unpack_legamma1(P, p, buf);
 }
-void orc_dil_derive_ball(uint32_t p[N], const uint8_t seed[CTILDE]) { /* sample.go:299-339 */
+static void derive_ball(const dparams *P, uint32_t p[N], const uint8_t *seed) { /* sample.go:299-339 */
   orc_sponge h;
   uint8_t buf[136];
   orc_sponge_init(&h, 136, 0x1f);
-  orc_sponge_write(&h, seed, CTILDE);
+  orc_sponge_write(&h, seed, (size_t)P->ctilde);
   orc_sponge_read(&h, buf, 136);
   uint64_t signs;
   memcpy(&signs, buf, 8);
   int off = 8;
   memset(p, 0, sizeof(poly));
-  for (unsigned i = N - TAU; i < N; i++) {
+  for (unsigned i = N - (unsigned)P->tau; i < N; i++) {
     unsigned b;
     for (;;) {
       if (off >= 136) { orc_sponge_read(&h, buf, 136); off = 0; }
@@ -312,88 +335,98 @@ void orc_dil_derive_ball(uint32_t p[N], const uint8_t seed[CTILDE]) { /* sample.
     signs >>= 1;
   }
 }
+/* the ML-DSA-65 instances kept for the sampler-vector tests */
+void orc_dil_derive_leqeta(uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { derive_leqeta(mode_of(65), p, seed, nonce); }
+void orc_dil_derive_legamma1(uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { derive_legamma1(mode_of(65), p, seed, nonce); }
+void orc_dil_derive_ball(uint32_t p[N], const uint8_t seed[48]) { derive_ball(mode_of(65), p, seed); }
 
 /* ---- rounding.go ---- */
-static void decompose(uint32_t a, uint32_t *a0plusq, uint32_t *a1o) { /* rounding.go:13-43, alpha = 523776 */
+static void decompose(const dparams *P, uint32_t a, uint32_t *a0plusq, uint32_t *a1o) { /* rounding.go:13-43 */
   uint32_t a1 = (a + 127) >> 7;
-  a1 = (a1 * 1025 + (1u << 21)) >> 22;
-  a1 &= 15;
-  uint32_t a0 = a - a1 * ALPHA;
+  if (P_ALPHA(P) == 523776) {
+    a1 = (a1 * 1025 + (1u << 21)) >> 22;
+    a1 &= 15;
+  } else { /* alpha = 190464 */
+    a1 = (a1 * 11275 + (1u << 23)) >> 24;
+    a1 ^= (uint32_t)((int32_t)(43 - a1) >> 31) & a1;
+  }
+  uint32_t a0 = a - a1 * P_ALPHA(P);
   a0 += (uint32_t)((int32_t)(a0 - (Q - 1) / 2) >> 31) & Q;
   *a0plusq = a0;
   *a1o = a1;
 }
-static uint32_t make_hint(uint32_t z0, uint32_t r1) { /* rounding.go:56-67 */
-  if (z0 <= GAMMA2 || z0 > Q - GAMMA2 || (z0 == Q - GAMMA2 && r1 == 0)) return 0;
+static uint32_t make_hint(const dparams *P, uint32_t z0, uint32_t r1) { /* rounding.go:56-67 */
+  if (z0 <= P->gamma2 || z0 > Q - P->gamma2 || (z0 == Q - P->gamma2 && r1 == 0)) return 0;
   return 1;
 }
 void orc_dil_decompose(const uint32_t *p, uint32_t *p0, uint32_t *p1) {
-  for (int i = 0; i < N; i++) decompose(p[i], &p0[i], &p1[i]);
+  for (int i = 0; i < N; i++) decompose(mode_of(65), p[i], &p0[i], &p1[i]);
 }
 
 /* ---- private key (dilithium.go:56-72, Unpack :142-163) ---- */
 typedef struct {
   uint8_t rho[32], key[32], tr[TRSIZE];
-  poly s1[L], s2[K], t0[K];
-  poly A[K][L], s1h[L], s2h[K], t0h[K];
+  poly s1[LMAX], s2[KMAX], t0[KMAX];
+  poly A[KMAX][LMAX], s1h[LMAX], s2h[KMAX], t0h[KMAX];
 } privkey;
 
-static void mat_derive(poly A[K][L], const uint8_t rho[32]) { /* mat.go:15-23 */
-  for (int i = 0; i < K; i++)
-    for (int j = 0; j < L; j++) orc_dil_derive_uniform(A[i][j], rho, (uint16_t)((i << 8) + j));
+static void mat_derive(const dparams *P, poly A[KMAX][LMAX], const uint8_t rho[32]) { /* mat.go:15-23 */
+  for (int i = 0; i < P->k; i++)
+    for (int j = 0; j < P->l; j++) orc_dil_derive_uniform(A[i][j], rho, (uint16_t)((i << 8) + j));
 }
-static void dot_hat(poly p, poly a[L], poly b[L]) { /* mat.go:52-59 */
+static void dot_hat(const dparams *P, poly p, poly *a, poly *b) { /* mat.go:52-59 */
   poly t;
   memset(p, 0, sizeof(poly));
-  for (int i = 0; i < L; i++) {
+  for (int i = 0; i < P->l; i++) {
     orc_dil_mulhat(t, a[i], b[i]);
     p_add(p, t, p);
   }
 }
-static void sk_cache(privkey *sk) {
-  mat_derive(sk->A, sk->rho);
-  for (int i = 0; i < K; i++) { memcpy(sk->t0h[i], sk->t0[i], sizeof(poly)); orc_dil_ntt(sk->t0h[i]); }
-  for (int i = 0; i < L; i++) { memcpy(sk->s1h[i], sk->s1[i], sizeof(poly)); orc_dil_ntt(sk->s1h[i]); }
-  for (int i = 0; i < K; i++) { memcpy(sk->s2h[i], sk->s2[i], sizeof(poly)); orc_dil_ntt(sk->s2h[i]); }
+static void sk_cache(const dparams *P, privkey *sk) {
+  mat_derive(P, sk->A, sk->rho);
+  for (int i = 0; i < P->k; i++) { memcpy(sk->t0h[i], sk->t0[i], sizeof(poly)); orc_dil_ntt(sk->t0h[i]); }
+  for (int i = 0; i < P->l; i++) { memcpy(sk->s1h[i], sk->s1[i], sizeof(poly)); orc_dil_ntt(sk->s1h[i]); }
+  for (int i = 0; i < P->k; i++) { memcpy(sk->s2h[i], sk->s2[i], sizeof(poly)); orc_dil_ntt(sk->s2h[i]); }
 }
-static void sk_unpack(privkey *sk, const uint8_t *buf) {
+static void sk_unpack(const dparams *P, privkey *sk, const uint8_t *buf) {
   memcpy(sk->rho, buf, 32);
   memcpy(sk->key, buf + 32, 32);
   memcpy(sk->tr, buf + 64, TRSIZE);
   const uint8_t *p = buf + 64 + TRSIZE;
-  for (int i = 0; i < L; i++, p += POLY_LEQETA) unpack_leqeta(sk->s1[i], p);
-  for (int i = 0; i < K; i++, p += POLY_LEQETA) unpack_leqeta(sk->s2[i], p);
-  for (int i = 0; i < K; i++, p += POLY_T0) unpack_t0(sk->t0[i], p);
-  sk_cache(sk);
+  for (int i = 0; i < P->l; i++, p += P_LEQETA(P)) unpack_leqeta(P, sk->s1[i], p);
+  for (int i = 0; i < P->k; i++, p += P_LEQETA(P)) unpack_leqeta(P, sk->s2[i], p);
+  for (int i = 0; i < P->k; i++, p += POLY_T0) unpack_t0(sk->t0[i], p);
+  sk_cache(P, sk);
 }
-static void sk_pack(const privkey *sk, uint8_t *buf) { /* dilithium.go:129-139 */
+static void sk_pack(const dparams *P, const privkey *sk, uint8_t *buf) { /* dilithium.go:129-139 */
   memcpy(buf, sk->rho, 32);
   memcpy(buf + 32, sk->key, 32);
   memcpy(buf + 64, sk->tr, TRSIZE);
   uint8_t *p = buf + 64 + TRSIZE;
-  for (int i = 0; i < L; i++, p += POLY_LEQETA) pack_leqeta(p, sk->s1[i]);
-  for (int i = 0; i < K; i++, p += POLY_LEQETA) pack_leqeta(p, sk->s2[i]);
-  for (int i = 0; i < K; i++, p += POLY_T0) pack_t0(p, sk->t0[i]);
+  for (int i = 0; i < P->l; i++, p += P_LEQETA(P)) pack_leqeta(P, p, sk->s1[i]);
+  for (int i = 0; i < P->k; i++, p += P_LEQETA(P)) pack_leqeta(P, p, sk->s2[i]);
+  for (int i = 0; i < P->k; i++, p += POLY_T0) pack_t0(p, sk->t0[i]);
 }
 
 /* NewKeyFromSeed, dilithium.go:181-241 (+ computeT0andT1 :253-267) */
-void orc_mldsa65_keygen(uint8_t pk[PK_SIZE], uint8_t skb[SK_SIZE], const uint8_t seed[32]) {
+void orc_mldsa_keygen(int mode, uint8_t *pk, uint8_t *skb, const uint8_t seed[32]) {
+  const dparams *P = mode_of(mode);
   privkey *sk = (privkey *)malloc(sizeof(privkey));
   uint8_t in[34], eseed[128];
   memcpy(in, seed, 32);
-  in[32] = K; in[33] = L;
+  in[32] = (uint8_t)P->k; in[33] = (uint8_t)P->l;
   orc_shake256(eseed, 128, in, 34);
   memcpy(sk->rho, eseed, 32);
   const uint8_t *sseed = eseed + 32;
   memcpy(sk->key, eseed + 96, 32);
-  for (int i = 0; i < L; i++) orc_dil_derive_leqeta(sk->s1[i], sseed, (uint16_t)i);
-  for (int i = 0; i < K; i++) orc_dil_derive_leqeta(sk->s2[i], sseed, (uint16_t)(i + L));
-  mat_derive(sk->A, sk->rho);
-  for (int i = 0; i < L; i++) { memcpy(sk->s1h[i], sk->s1[i], sizeof(poly)); orc_dil_ntt(sk->s1h[i]); }
-  poly t1[K];
-  for (int i = 0; i < K; i++) {
+  for (int i = 0; i < P->l; i++) derive_leqeta(P, sk->s1[i], sseed, (uint16_t)i);
+  for (int i = 0; i < P->k; i++) derive_leqeta(P, sk->s2[i], sseed, (uint16_t)(i + P->l));
+  mat_derive(P, sk->A, sk->rho);
+  for (int i = 0; i < P->l; i++) { memcpy(sk->s1h[i], sk->s1[i], sizeof(poly)); orc_dil_ntt(sk->s1h[i]); }
+  poly t1[KMAX];
+  for (int i = 0; i < P->k; i++) {
     poly t;
-    dot_hat(t, sk->A[i], sk->s1h);
+    dot_hat(P, t, sk->A[i], sk->s1h);
     p_reduce_le2q(t);
     orc_dil_invntt(t);
     p_add(t, t, sk->s2[i]);
@@ -401,16 +434,18 @@ void orc_mldsa65_keygen(uint8_t pk[PK_SIZE], uint8_t skb[SK_SIZE], const uint8_t
     for (int j = 0; j < N; j++) power2round(t[j], &sk->t0[i][j], &t1[i][j]);
   }
   memcpy(pk, sk->rho, 32);
-  for (int i = 0; i < K; i++) pack_t1(pk + 32 + POLY_T1 * i, t1[i]);
-  orc_shake256(sk->tr, TRSIZE, pk, PK_SIZE);
-  sk_pack(sk, skb);
+  for (int i = 0; i < P->k; i++) pack_t1(pk + 32 + POLY_T1 * i, t1[i]);
+  orc_shake256(sk->tr, TRSIZE, pk, (size_t)P_PK(P));
+  sk_pack(P, sk, skb);
   free(sk);
 }
 
-/* ML-DSA.Sign_internal: internal/dilithium.go:340-470.  mu_in = message bytes M'
- * (already framed by the caller).  Returns the number of attempts, or -1 after 576. */
-static int sign_internal(const privkey *sk, const uint8_t *msg, size_t msglen, const uint8_t rnd[32], uint8_t *sig) {
-  uint8_t mu[64], rhop[64], w1p[POLY_W1 * K], ctilde[CTILDE];
+/* ML-DSA.Sign_internal: internal/dilithium.go:340-470.  msg = M' (already framed by the caller).
+ * Returns the number of attempts, or -1 after 576. */
+static int sign_internal(const dparams *P, const privkey *sk, const uint8_t *msg, size_t msglen, const uint8_t rnd[32],
+                         uint8_t *sig) {
+  uint8_t mu[64], rhop[64], w1p[192 * KMAX], ctilde[64];
+  const int K = P->k, L = P->l;
   orc_sponge h;
   orc_sponge_init(&h, 136, 0x1f);
   orc_sponge_write(&h, sk->tr, TRSIZE);
@@ -422,31 +457,31 @@ static int sign_internal(const privkey *sk, const uint8_t *msg, size_t msglen, c
   orc_sponge_write(&h, mu, 64);
   orc_sponge_read(&h, rhop, 64);
 
-  poly *y = malloc(sizeof(poly) * L), *yh = malloc(sizeof(poly) * L), *z = malloc(sizeof(poly) * L);
-  poly *w = malloc(sizeof(poly) * K), *w0 = malloc(sizeof(poly) * K), *w1 = malloc(sizeof(poly) * K);
-  poly *w0mcs2 = malloc(sizeof(poly) * K), *ct0 = malloc(sizeof(poly) * K), *hint = malloc(sizeof(poly) * K);
+  poly *y = malloc(sizeof(poly) * LMAX), *yh = malloc(sizeof(poly) * LMAX), *z = malloc(sizeof(poly) * LMAX);
+  poly *w = malloc(sizeof(poly) * KMAX), *w0 = malloc(sizeof(poly) * KMAX), *w1 = malloc(sizeof(poly) * KMAX);
+  poly *w0mcs2 = malloc(sizeof(poly) * KMAX), *ct0 = malloc(sizeof(poly) * KMAX), *hint = malloc(sizeof(poly) * KMAX);
   poly ch;
   uint16_t ynonce = 0;
   int attempt = 0, ok = 0;
   while (!ok) {
     attempt++;
     if (attempt >= 576) { attempt = -1; break; }
-    for (int i = 0; i < L; i++) orc_dil_derive_legamma1(y[i], rhop, (uint16_t)(ynonce + i));
+    for (int i = 0; i < L; i++) derive_legamma1(P, y[i], rhop, (uint16_t)(ynonce + i));
     ynonce = (uint16_t)(ynonce + L);
     for (int i = 0; i < L; i++) { memcpy(yh[i], y[i], sizeof(poly)); orc_dil_ntt(yh[i]); }
     for (int i = 0; i < K; i++) {
-      dot_hat(w[i], ((privkey *)sk)->A[i], yh);
+      dot_hat(P, w[i], ((privkey *)sk)->A[i], yh);
       p_reduce_le2q(w[i]);
       orc_dil_invntt(w[i]);
       p_normalize_le2q(w[i]);
-      orc_dil_decompose(w[i], w0[i], w1[i]);
-      pack_w1(w1p + POLY_W1 * i, w1[i]);
+      for (int j = 0; j < N; j++) decompose(P, w[i][j], &w0[i][j], &w1[i][j]);
+      pack_w1(P, w1p + P_W1(P) * i, w1[i]);
     }
     orc_sponge_init(&h, 136, 0x1f);
     orc_sponge_write(&h, mu, 64);
-    orc_sponge_write(&h, w1p, sizeof w1p);
-    orc_sponge_read(&h, ctilde, CTILDE);
-    orc_dil_derive_ball(ch, ctilde);
+    orc_sponge_write(&h, w1p, (size_t)(P_W1(P) * K));
+    orc_sponge_read(&h, ctilde, (size_t)P->ctilde);
+    derive_ball(P, ch, ctilde);
     orc_dil_ntt(ch);
     int rej = 0;
     for (int i = 0; i < K; i++) {
@@ -454,7 +489,7 @@ static int sign_internal(const privkey *sk, const uint8_t *msg, size_t msglen, c
       orc_dil_invntt(w0mcs2[i]);
       p_sub(w0mcs2[i], w0[i], w0mcs2[i]);
       p_normalize(w0mcs2[i]);
-      rej |= p_exceeds(w0mcs2[i], GAMMA2 - BETA);
+      rej |= p_exceeds(w0mcs2[i], P->gamma2 - P_BETA(P));
     }
     if (rej) continue;
     for (int i = 0; i < L; i++) {
@@ -462,14 +497,14 @@ static int sign_internal(const privkey *sk, const uint8_t *msg, size_t msglen, c
       orc_dil_invntt(z[i]);
       p_add(z[i], z[i], y[i]);
       p_normalize(z[i]);
-      rej |= p_exceeds(z[i], GAMMA1 - BETA);
+      rej |= p_exceeds(z[i], P_GAMMA1(P) - P_BETA(P));
     }
     if (rej) continue;
     for (int i = 0; i < K; i++) {
       orc_dil_mulhat(ct0[i], ch, sk->t0h[i]);
       orc_dil_invntt(ct0[i]);
       p_normalize_le2q(ct0[i]);
-      rej |= p_exceeds(ct0[i], GAMMA2);
+      rej |= p_exceeds(ct0[i], P->gamma2);
     }
     if (rej) continue;
     uint32_t pop = 0;
@@ -477,36 +512,37 @@ static int sign_internal(const privkey *sk, const uint8_t *msg, size_t msglen, c
       poly s;
       p_add(s, w0mcs2[i], ct0[i]);
       p_normalize_le2q(s);
-      for (int j = 0; j < N; j++) { hint[i][j] = make_hint(s[j], w1[i][j]); pop += hint[i][j]; }
+      for (int j = 0; j < N; j++) { hint[i][j] = make_hint(P, s[j], w1[i][j]); pop += hint[i][j]; }
     }
-    if (pop > OMEGA) continue;
+    if (pop > (uint32_t)P->omega) continue;
     ok = 1;
   }
   if (ok) {
-    memcpy(sig, ctilde, CTILDE);
-    for (int i = 0; i < L; i++) pack_legamma1(sig + CTILDE + POLY_LEGAMMA1 * i, z[i]);
-    pack_hint(sig + CTILDE + L * POLY_LEGAMMA1, hint);
+    memcpy(sig, ctilde, (size_t)P->ctilde);
+    for (int i = 0; i < L; i++) pack_legamma1(P, sig + P->ctilde + P_LEGAMMA1(P) * i, z[i]);
+    pack_hint(P, sig + P->ctilde + L * P_LEGAMMA1(P), hint);
   }
   free(y); free(yh); free(z); free(w); free(w0); free(w1); free(w0mcs2); free(ct0); free(hint);
   return attempt;
 }
 
-/* sk: packed 4032 B.  internal != 0: ML-DSA.Sign_internal on msg as given (ACVP internal
- * interface, mldsa65/dilithium.go:87-98); else the external framing 0x00 || len(ctx) || ctx || msg
+/* sk: packed.  internal != 0: ML-DSA.Sign_internal on msg as given (ACVP internal interface,
+ * mldsa65/dilithium.go:87-98); else the external framing 0x00 || len(ctx) || ctx || msg
  * (mldsa65/dilithium.go:56-84).  rnd: 32 bytes (all zero = deterministic).  Returns attempts or -1. */
-int orc_mldsa65_sign(uint8_t sig[SIG_SIZE], const uint8_t *skb, const uint8_t *msg, size_t msglen,
-                     const uint8_t *ctx, size_t ctxlen, const uint8_t rnd[32], int internal) {
+int orc_mldsa_sign(int mode, uint8_t *sig, const uint8_t *skb, const uint8_t *msg, size_t msglen, const uint8_t *ctx,
+                   size_t ctxlen, const uint8_t rnd[32], int internal) {
+  const dparams *P = mode_of(mode);
   privkey *sk = (privkey *)malloc(sizeof(privkey));
-  sk_unpack(sk, skb);
+  sk_unpack(P, sk, skb);
   int rc;
   if (internal) {
-    rc = sign_internal(sk, msg, msglen, rnd, sig);
+    rc = sign_internal(P, sk, msg, msglen, rnd, sig);
   } else {
     uint8_t *m = (uint8_t *)malloc(2 + ctxlen + msglen);
     m[0] = 0; m[1] = (uint8_t)ctxlen;
     if (ctxlen) memcpy(m + 2, ctx, ctxlen);
     memcpy(m + 2 + ctxlen, msg, msglen);
-    rc = sign_internal(sk, m, 2 + ctxlen + msglen, rnd, sig);
+    rc = sign_internal(P, sk, m, 2 + ctxlen + msglen, rnd, sig);
     free(m);
   }
   free(sk);
@@ -514,19 +550,21 @@ int orc_mldsa65_sign(uint8_t sig[SIG_SIZE], const uint8_t *skb, const uint8_t *m
 }
 
 /* Verify (internal/dilithium.go:273-332); same message conventions as sign. returns 1 = valid */
-int orc_mldsa65_verify(const uint8_t pkb[PK_SIZE], const uint8_t *msg, size_t msglen, const uint8_t *ctx, size_t ctxlen,
-                       const uint8_t *sig, size_t siglen, int internal) {
-  if (siglen != SIG_SIZE) return 0;
-  poly *z = malloc(sizeof(poly) * L), *hint = malloc(sizeof(poly) * K), *t1 = malloc(sizeof(poly) * K);
-  poly(*A)[L] = malloc(sizeof(poly) * K * L);
+int orc_mldsa_verify(int mode, const uint8_t *pkb, const uint8_t *msg, size_t msglen, const uint8_t *ctx, size_t ctxlen,
+                     const uint8_t *sig, size_t siglen, int internal) {
+  const dparams *P = mode_of(mode);
+  const int K = P->k, L = P->l;
+  if (siglen != (size_t)P_SIG(P)) return 0;
+  poly *z = malloc(sizeof(poly) * LMAX), *hint = malloc(sizeof(poly) * KMAX), *t1 = malloc(sizeof(poly) * KMAX);
+  poly(*A)[LMAX] = malloc(sizeof(poly) * KMAX * LMAX);
   int ok = 0;
-  for (int i = 0; i < L; i++) unpack_legamma1(z[i], sig + CTILDE + POLY_LEGAMMA1 * i);
+  for (int i = 0; i < L; i++) unpack_legamma1(P, z[i], sig + P->ctilde + P_LEGAMMA1(P) * i);
   for (int i = 0; i < L; i++)
-    if (p_exceeds(z[i], GAMMA1 - BETA)) goto done;
-  if (!unpack_hint(hint, sig + CTILDE + L * POLY_LEGAMMA1)) goto done;
+    if (p_exceeds(z[i], P_GAMMA1(P) - P_BETA(P))) goto done;
+  if (!unpack_hint(P, hint, sig + P->ctilde + L * P_LEGAMMA1(P))) goto done;
   {
-    uint8_t tr[TRSIZE], mu[64], w1p[POLY_W1 * K], cp[CTILDE];
-    orc_shake256(tr, TRSIZE, pkb, PK_SIZE);
+    uint8_t tr[TRSIZE], mu[64], w1p[192 * KMAX], cp[64];
+    orc_shake256(tr, TRSIZE, pkb, (size_t)P_PK(P));
     orc_sponge h;
     orc_sponge_init(&h, 136, 0x1f);
     orc_sponge_write(&h, tr, TRSIZE);
@@ -537,15 +575,15 @@ int orc_mldsa65_verify(const uint8_t pkb[PK_SIZE], const uint8_t *msg, size_t ms
     }
     orc_sponge_write(&h, msg, msglen);
     orc_sponge_read(&h, mu, 64);
-    mat_derive(A, pkb);
+    mat_derive(P, A, pkb);
     for (int i = 0; i < K; i++) unpack_t1(t1[i], pkb + 32 + POLY_T1 * i);
     for (int i = 0; i < L; i++) orc_dil_ntt(z[i]);
     poly ch;
-    orc_dil_derive_ball(ch, sig);
+    derive_ball(P, ch, sig);
     orc_dil_ntt(ch);
     for (int i = 0; i < K; i++) {
       poly az, t, q0, w1;
-      dot_hat(az, A[i], z);
+      dot_hat(P, az, A[i], z);
       for (int j = 0; j < N; j++) t[j] = t1[i][j] << D;
       orc_dil_ntt(t);
       orc_dil_mulhat(t, t, ch);
@@ -553,16 +591,24 @@ int orc_mldsa65_verify(const uint8_t pkb[PK_SIZE], const uint8_t *msg, size_t ms
       p_reduce_le2q(t);
       orc_dil_invntt(t);
       p_normalize_le2q(t);
-      orc_dil_decompose(t, q0, w1); /* PolyUseHint, rounding.go:98-135 (gamma2 = 261888) */
-      for (int j = 0; j < N; j++)
-        if (hint[i][j]) w1[j] = (q0[j] > Q) ? ((w1[j] + 1) & 15) : ((w1[j] - 1) & 15);
-      pack_w1(w1p + POLY_W1 * i, w1);
+      for (int j = 0; j < N; j++) decompose(P, t[j], &q0[j], &w1[j]); /* PolyUseHint, rounding.go:98-135 */
+      for (int j = 0; j < N; j++) {
+        if (!hint[i][j]) continue;
+        if (P->gamma2 == 261888) {
+          w1[j] = (q0[j] > Q) ? ((w1[j] + 1) & 15) : ((w1[j] - 1) & 15);
+        } else if (q0[j] > Q) {
+          w1[j] = (w1[j] == 43) ? 0 : w1[j] + 1;
+        } else {
+          w1[j] = (w1[j] == 0) ? 43 : w1[j] - 1;
+        }
+      }
+      pack_w1(P, w1p + P_W1(P) * i, w1);
     }
     orc_sponge_init(&h, 136, 0x1f);
     orc_sponge_write(&h, mu, 64);
-    orc_sponge_write(&h, w1p, sizeof w1p);
-    orc_sponge_read(&h, cp, CTILDE);
-    ok = memcmp(cp, sig, CTILDE) == 0;
+    orc_sponge_write(&h, w1p, (size_t)(P_W1(P) * K));
+    orc_sponge_read(&h, cp, (size_t)P->ctilde);
+    ok = memcmp(cp, sig, (size_t)P->ctilde) == 0;
   }
 done:
   free(z); free(hint); free(t1); free(A);
@@ -571,8 +617,8 @@ done:
 
 #include <pthread.h>
 typedef struct {
-  uint8_t *sig; const uint8_t *sk; size_t sk_stride; const uint8_t *msgs; const uint64_t *off; const uint8_t *rnd;
-  size_t lo, hi; int fails; long attempts;
+  const dparams *P; uint8_t *sig; const uint8_t *sk; size_t sk_stride; const uint8_t *msgs; const uint64_t *off;
+  const uint8_t *rnd; size_t lo, hi; int fails; long attempts;
 } sign_job;
 static void *sign_worker(void *arg) {
   sign_job *j = (sign_job *)arg;
@@ -581,13 +627,13 @@ static void *sign_worker(void *arg) {
   const uint8_t *last = NULL;
   for (size_t i = j->lo; i < j->hi; i++) {
     const uint8_t *skb = j->sk + i * j->sk_stride;
-    if (skb != last) { sk_unpack(sk, skb); last = skb; } /* per-op sk is re-expanded, like the GPU path */
+    if (skb != last) { sk_unpack(j->P, sk, skb); last = skb; } /* per-op sk is re-expanded, like the GPU path */
     const uint8_t *m = j->msgs + j->off[i];
     size_t mlen = (size_t)(j->off[i + 1] - j->off[i]);
     uint8_t *fm = (uint8_t *)malloc(2 + mlen);
     fm[0] = 0; fm[1] = 0;
     memcpy(fm + 2, m, mlen);
-    int a = sign_internal(sk, fm, 2 + mlen, j->rnd ? j->rnd + 32 * i : zero, j->sig + i * SIG_SIZE);
+    int a = sign_internal(j->P, sk, fm, 2 + mlen, j->rnd ? j->rnd + 32 * i : zero, j->sig + i * (size_t)P_SIG(j->P));
     free(fm);
     if (a < 0) j->fails++; else j->attempts += a;
   }
@@ -596,8 +642,8 @@ static void *sign_worker(void *arg) {
 }
 /* batched external-interface signing with empty context; msgs concatenated, off[n+1] offsets.
  * returns total attempts (>0) or -1 on failure */
-int orc_mldsa65_sign_batch(uint8_t *sig, const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *off,
-                           const uint8_t *rnd, size_t n, int nthreads) {
+int orc_mldsa_sign_batch(int mode, uint8_t *sig, const uint8_t *sk, size_t sk_stride, const uint8_t *msgs,
+                         const uint64_t *off, const uint8_t *rnd, size_t n, int nthreads) {
   if (nthreads < 1) nthreads = 1;
   if ((size_t)nthreads > n) nthreads = n ? (int)n : 1;
   pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
@@ -605,10 +651,25 @@ int orc_mldsa65_sign_batch(uint8_t *sig, const uint8_t *sk, size_t sk_stride, co
   long attempts = 0;
   int fails = 0;
   for (int t = 0; t < nthreads; t++) {
-    jobs[t] = (sign_job){sig, sk, sk_stride, msgs, off, rnd, n * t / nthreads, n * (t + 1) / nthreads, 0, 0};
+    jobs[t] = (sign_job){mode_of(mode), sig, sk, sk_stride, msgs, off, rnd, n * t / nthreads, n * (t + 1) / nthreads, 0, 0};
     pthread_create(&th[t], NULL, sign_worker, &jobs[t]);
   }
   for (int t = 0; t < nthreads; t++) { pthread_join(th[t], NULL); fails += jobs[t].fails; attempts += jobs[t].attempts; }
   free(th); free(jobs);
   return fails ? -1 : (int)attempts;
+}
+
+/* ML-DSA-65 entry points kept under their original names */
+void orc_mldsa65_keygen(uint8_t pk[1952], uint8_t sk[4032], const uint8_t seed[32]) { orc_mldsa_keygen(65, pk, sk, seed); }
+int orc_mldsa65_sign(uint8_t sig[3309], const uint8_t *sk, const uint8_t *msg, size_t msglen, const uint8_t *ctx,
+                     size_t ctxlen, const uint8_t rnd[32], int internal) {
+  return orc_mldsa_sign(65, sig, sk, msg, msglen, ctx, ctxlen, rnd, internal);
+}
+int orc_mldsa65_verify(const uint8_t pk[1952], const uint8_t *msg, size_t msglen, const uint8_t *ctx, size_t ctxlen,
+                       const uint8_t *sig, size_t siglen, int internal) {
+  return orc_mldsa_verify(65, pk, msg, msglen, ctx, ctxlen, sig, siglen, internal);
+}
+int orc_mldsa65_sign_batch(uint8_t *sig, const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *off,
+                           const uint8_t *rnd, size_t n, int nthreads) {
+  return orc_mldsa_sign_batch(65, sig, sk, sk_stride, msgs, off, rnd, n, nthreads);
 }

@@ -112,6 +112,18 @@ int orc_mldsa65_verify(const uint8_t pk[1952], const uint8_t *msg, size_t msglen
 int orc_mldsa65_sign_batch(uint8_t *sig, const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *off,
                            const uint8_t *rnd, size_t n, int nthreads);
 
+/* run-time parameter set: mode = 44, 65 or 87 (sign/dilithium/gen.go:80-162) */
+size_t orc_mldsa_sk_size(int mode);
+size_t orc_mldsa_pk_size(int mode);
+size_t orc_mldsa_sig_size(int mode);
+void orc_mldsa_keygen(int mode, uint8_t *pk, uint8_t *sk, const uint8_t seed[32]);
+int orc_mldsa_sign(int mode, uint8_t *sig, const uint8_t *sk, const uint8_t *msg, size_t msglen, const uint8_t *ctx,
+                   size_t ctxlen, const uint8_t rnd[32], int internal);
+int orc_mldsa_verify(int mode, const uint8_t *pk, const uint8_t *msg, size_t msglen, const uint8_t *ctx, size_t ctxlen,
+                     const uint8_t *sig, size_t siglen, int internal);
+int orc_mldsa_sign_batch(int mode, uint8_t *sig, const uint8_t *sk, size_t sk_stride, const uint8_t *msgs,
+                         const uint64_t *off, const uint8_t *rnd, size_t n, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

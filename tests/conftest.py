@@ -39,3 +39,8 @@ def sampler_vectors():
 @pytest.fixture(scope="session")
 def keccak_kats():
     return load_golden("keccak_kats.json.gz")
+
+
+@pytest.fixture(scope="session")
+def mldsa_other_acvp():
+    return load_golden("mldsa_other_acvp.json.gz")

@@ -98,6 +98,38 @@ def mldsa65():
     dump("mldsa65_acvp.json.gz", out)
 
 
+def mldsa_other():
+    """ML-DSA-44 and ML-DSA-87: a subset of the same ACVP files (the first vectors of every group)."""
+    out = {"source": "sign/mldsa/testdata (NIST ACVP FIPS 204), ML-DSA-44 / ML-DSA-87, first vectors of each group"}
+    for ps in ("ML-DSA-44", "ML-DSA-87"):
+        o = {"siggen": [], "sigver": {}, "keygen": []}
+        prompt, res = acvp("sign/mldsa/testdata/ML-DSA-sigGen-FIPS204")
+        for g in prompt["testGroups"]:
+            if g["parameterSet"] != ps:
+                continue
+            for t in g["tests"][:3]:
+                o["siggen"].append({"tcId": t["tcId"], "deterministic": g["deterministic"], "sk": t["sk"],
+                                    "message": t["message"], "rnd": t.get("rnd", "00" * 32),
+                                    "signature": res[t["tcId"]]["signature"]})
+        prompt, res = acvp("sign/mldsa/testdata/ML-DSA-sigVer-FIPS204")
+        for g in prompt["testGroups"]:
+            if g["parameterSet"] != ps:
+                continue
+            tests = g["tests"]
+            passed = [t for t in tests if res[t["tcId"]]["testPassed"]][:3]
+            failed = [t for t in tests if not res[t["tcId"]]["testPassed"]][:5]
+            o["sigver"] = {"pk": g["pk"], "tests": [{"tcId": t["tcId"], "message": t["message"], "signature": t["signature"],
+                                                     "testPassed": res[t["tcId"]]["testPassed"]} for t in passed + failed]}
+        prompt, res = acvp("sign/mldsa/testdata/ML-DSA-keyGen-FIPS204")
+        for g in prompt["testGroups"]:
+            if g["parameterSet"] != ps:
+                continue
+            o["keygen"] = [{"tcId": t["tcId"], "seed": t["seed"], "pk": res[t["tcId"]]["pk"], "sk": res[t["tcId"]]["sk"]}
+                           for t in g["tests"][:5]]
+        out[ps] = o
+    dump("mldsa_other_acvp.json.gz", out)
+
+
 def go_array(path, func, var=None, which=0):
     """Pull the `which`-th `{...}` integer literal that follows `func <func>(` in a Go test file."""
     src = open(os.path.join(REF, path)).read()
@@ -139,6 +171,8 @@ def samplers():
         "ML-KEM-768": re.search(r'"ML-KEM-768", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
         "ML-KEM-1024": re.search(r'"ML-KEM-1024", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
         "ML-DSA-65": re.search(r'"ML-DSA-65", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
+        "ML-DSA-44": re.search(r'"ML-DSA-44", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
+        "ML-DSA-87": re.search(r'"ML-DSA-87", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
     }
     dump("sampler_vectors.json.gz", out)
 
@@ -161,5 +195,6 @@ def keccak_kats():
 if __name__ == "__main__":
     mlkem()
     mldsa65()
+    mldsa_other()
     samplers()
     keccak_kats()

@@ -113,3 +113,50 @@ def test_mulhat_is_negacyclic_product():
         full = np.concatenate([full, [0]])
         school = (full[:256] - full[256:]) % Q
         assert np.array_equal(p[i].astype(object), school)
+
+
+# ---------------------------------------------------------------- ML-DSA-44 / ML-DSA-87 (run-time parameter set)
+import pytest
+
+MODES = {"ML-DSA-44": 44, "ML-DSA-87": 87}
+
+
+@pytest.mark.parametrize("ps", list(MODES))
+def test_other_modes_acvp(mldsa_other_acvp, ps):
+    mode = MODES[ps]
+    g = mldsa_other_acvp[ps]
+    for t in g["keygen"]:
+        pk, sk = oracle.mldsa_keygen(mode, bytes.fromhex(t["seed"]))
+        assert pk.hex().upper() == t["pk"].upper() and sk.hex().upper() == t["sk"].upper(), t["tcId"]
+    for t in g["siggen"]:
+        sig, _ = oracle.mldsa_sign(mode, bytes.fromhex(t["sk"]), bytes.fromhex(t["message"]), rnd=bytes.fromhex(t["rnd"]),
+                                   internal=True)
+        assert sig.hex().upper() == t["signature"].upper(), t["tcId"]
+    pk = bytes.fromhex(g["sigver"]["pk"])
+    seen = set()
+    for t in g["sigver"]["tests"]:
+        got = oracle.mldsa_verify(mode, pk, bytes.fromhex(t["message"]), bytes.fromhex(t["signature"]), internal=True)
+        assert got == t["testPassed"], t["tcId"]
+        seen.add(got)
+    assert seen == {True, False}
+
+
+@pytest.mark.parametrize("ps", list(MODES))
+def test_other_modes_pqcgenkat_hash(sampler_vectors, ps):
+    # sign/dilithium/kat_test.go:43-100 (header names Dilithium2 / Dilithium5)
+    mode = MODES[ps]
+    g = DRBG(bytes(range(48)))
+    f = hashlib.sha256()
+    f.update(("# %s\n\n" % {44: "Dilithium2", 87: "Dilithium5"}[mode]).encode())
+    _, _, sigsz = oracle.mldsa_sizes(mode)
+    for i in range(100):
+        mlen = 33 * (i + 1)
+        seed = g.fill(48)
+        msg = g.fill(mlen)
+        f.update(("count = %d\nseed = %s\nmlen = %d\nmsg = %s\n" % (i, seed.hex().upper(), mlen, msg.hex().upper())).encode())
+        pk, sk = oracle.mldsa_keygen(mode, DRBG(seed).fill(32))
+        f.update(("pk = %s\nsk = %s\nsmlen = %d\n" % (pk.hex().upper(), sk.hex().upper(), mlen + sigsz)).encode())
+        sig, _ = oracle.mldsa_sign(mode, sk, msg)
+        f.update(("sm = %s%s\n\n" % (sig.hex().upper(), msg.hex().upper())).encode())
+        assert oracle.mldsa_verify(mode, pk, msg, sig)
+    assert f.hexdigest() == sampler_vectors["kat_sha256"][ps]

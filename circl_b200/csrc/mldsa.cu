@@ -28,18 +28,79 @@ namespace mldsa {
 
 using namespace dil;
 
-constexpr int K = 6, L = 5, ETA = 4, TAU = 49, BETA = TAU * ETA, OMEGA = 55, CTILDE = 48;
-constexpr uint32_t GAMMA1 = 1u << 19, GAMMA2 = 261888u, ALPHA = 2 * GAMMA2;
-constexpr int SK_BYTES = 4032, SIG_BYTES = 3309, POLY_Z = 640, POLY_W1 = 128;
-constexpr int OFF_KEY = 32, OFF_TR = 64, OFF_S1 = 128, OFF_S2 = OFF_S1 + 128 * L, OFF_T0 = OFF_S2 + 128 * K;
-constexpr int NKEYPOLY = L + K + K;  // s1h | s2h | t0h
+// Parameter sets (sign/dilithium/gen.go:80-162, NIST = true, tr = 64 bytes)
+template <int MODE>
+struct Params;
+template <>
+struct Params<44> {
+  static constexpr int K = 4, L = 4, ETA = 2, TAU = 39, G1BITS = 17, OMEGA = 80, CTILDE = 32;
+  static constexpr uint32_t GAMMA2 = (Q - 1) / 88;
+};
+template <>
+struct Params<65> {
+  static constexpr int K = 6, L = 5, ETA = 4, TAU = 49, G1BITS = 19, OMEGA = 55, CTILDE = 48;
+  static constexpr uint32_t GAMMA2 = (Q - 1) / 32;
+};
+template <>
+struct Params<87> {
+  static constexpr int K = 8, L = 7, ETA = 2, TAU = 60, G1BITS = 19, OMEGA = 75, CTILDE = 64;
+  static constexpr uint32_t GAMMA2 = (Q - 1) / 32;
+};
+// local aliases of the parameter set inside a templated kernel / function
+#define MLDSA_USE(P)                                                                                         \
+  constexpr int K = P::K, L = P::L, ETA = P::ETA, TAU = P::TAU, BETA = P::TAU * P::ETA, OMEGA = P::OMEGA,  \
+                CTILDE = P::CTILDE, ZBITS = P::G1BITS + 1, W1BITS = 23 - P::G1BITS, POLY_ETA = (P::ETA == 2 ? 96 : 128), \
+                POLY_Z = 32 * (P::G1BITS + 1), POLY_W1 = 32 * (23 - P::G1BITS), NKEYPOLY = P::L + 2 * P::K,   \
+                OFF_S2 = OFF_S1 + POLY_ETA * P::L, OFF_T0 = OFF_S2 + POLY_ETA * P::K,                          \
+                SK_BYTES = OFF_T0 + 416 * P::K, PK_BYTES = 32 + 320 * P::K,                                    \
+                SIG_BYTES = P::CTILDE + P::L * POLY_Z + P::OMEGA + P::K;                                       \
+  constexpr uint32_t GAMMA1 = 1u << P::G1BITS, GAMMA2 = P::GAMMA2, ALPHA = 2 * P::GAMMA2;                     \
+  (void)K; (void)L; (void)ETA; (void)TAU; (void)BETA; (void)OMEGA; (void)CTILDE; (void)ZBITS; (void)W1BITS;    \
+  (void)POLY_ETA; (void)POLY_Z; (void)POLY_W1; (void)NKEYPOLY; (void)OFF_S2; (void)OFF_T0; (void)SK_BYTES;     \
+  (void)PK_BYTES; (void)SIG_BYTES; (void)GAMMA1; (void)GAMMA2; (void)ALPHA
+constexpr int OFF_KEY = 32, OFF_TR = 64, OFF_S1 = 128, POLY_T1 = 320;
 constexpr int MAX_ATTEMPTS = 576;
+
+// j-th 64-bit word of PackW1(w1) (internal/pack.go:256-271) for one op, built from the byte-per-coefficient
+// buffer: 4-bit PackLe16 when gamma1 = 2^19, 6-bit fields when gamma1 = 2^17.
+template <class P>
+__device__ __forceinline__ uint64_t w1_word(const uint8_t* __restrict__ w1u_op, int j) {
+  constexpr int W1BITS = 23 - P::G1BITS, WPP = 4 * W1BITS;  // words per polynomial
+  const uint8_t* poly = w1u_op + (j / WPP) * 256;
+  const int q = j % WPP;
+  if constexpr (W1BITS == 4) {
+    const uint4 b = *reinterpret_cast<const uint4*>(poly + 16 * q);
+    const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+    uint64_t r = 0;
+#pragma unroll
+    for (int i = 0; i < 16; i++) r |= (uint64_t)((w[i >> 2] >> (8 * (i & 3))) & 15) << (4 * i);
+    return r;
+  } else {
+    const int c0 = (64 * q) / 6, rem = 64 * q - 6 * c0;
+    unsigned __int128 acc = 0;
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      const int c = c0 + i < 256 ? c0 + i : 255;
+      acc |= (unsigned __int128)(poly[c] & 63) << (6 * i);
+    }
+    return (uint64_t)(acc >> rem);
+  }
+}
+
+// 32 fields of BITS bits (little-endian bit stream) from nw 32-bit words with static indexing
+template <int BITS, int NW>
+__device__ __forceinline__ uint32_t field32(const uint32_t (&w)[NW], int i) {
+  const int bit = BITS * i, wi = bit >> 5, sh = bit & 31;
+  uint32_t f = w[wi] >> sh;
+  if (sh + BITS > 32) f |= w[wi + 1] << (32 - sh);
+  return f & ((1u << BITS) - 1);
+}
 
 struct Work {
   uint32_t *A, *sh;        // per key: A [30][256]; sh = s1h[5] | s2h[6] | t0h[6]
   uint64_t *mu, *rhop;     // per op: 8 words each
   uint32_t *y, *yh, *w0;   // per op: [5][256], [5][256], [6][256]
-  uint8_t* w1p;            // per op: 768 bytes
+  uint8_t* w1u;            // per op: K x 256 bytes, w1 one byte per coefficient (packed on the fly when hashed)
   uint8_t* zbuf;           // per op: 5 x 640 bytes, z packed (word aligned; copied into the signature on accept)
   uint32_t* c;             // per op: [256] challenge polynomial, then its NTT
   uint64_t* ctilde;        // per op: 6 words
@@ -53,8 +114,10 @@ constexpr int kExpThreads = 64;
 constexpr int kExpRow = 257;  // 256 words + 1 slack, odd stride
 
 // ExpandA (mat.go:15-23, sample.go:92-123): A[i][j] = RejNTTPoly(SHAKE128(rho || le16((i<<8)+j)))
+template <class P>
 __global__ void __launch_bounds__(kExpThreads) expand_a_kernel(const uint8_t* __restrict__ sk, size_t sk_stride,
                                                                size_t nkeys, uint32_t* __restrict__ A) {
+  MLDSA_USE(P);
   extern __shared__ __align__(16) uint32_t rows[];
   const size_t s0 = (size_t)blockIdx.x * blockDim.x, total = nkeys * K * L;
   const size_t s = s0 + threadIdx.x;
@@ -104,8 +167,10 @@ __global__ void __launch_bounds__(kExpThreads) expand_a_kernel(const uint8_t* __
 }
 
 // s1h, s2h, t0h = NTT(unpack(...)) (dilithium.go:150-162): one octet per (key, polynomial)
+template <class P>
 __global__ void __launch_bounds__(128) expand_s_kernel(const uint8_t* __restrict__ sk, size_t sk_stride, size_t nkeys,
                                                        uint32_t* __restrict__ sh, const uint32_t* __restrict__ zetas) {
+  MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
   uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
@@ -119,11 +184,15 @@ __global__ void __launch_bounds__(128) expand_s_kernel(const uint8_t* __restrict
   const int p = (int)(u % NKEYPOLY);
   const uint8_t* skp = sk + key * sk_stride;
   uint32_t r[32];
-  if (p < L + K) {  // PolyUnpackLeqEta (internal/pack.go:49-57), eta = 4: nibbles
-    const uint4 q4 = __ldg(reinterpret_cast<const uint4*>(skp + OFF_S1 + 128 * p + 16 * v));
-    const uint32_t w[4] = {q4.x, q4.y, q4.z, q4.w};
+  if (p < L + K) {  // PolyUnpackLeqEta (internal/pack.go:49-75): nibbles (eta = 4) or 3-bit fields (eta = 2)
+    constexpr int EB = (ETA == 2) ? 3 : 4;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(skp + OFF_S1 + POLY_ETA * p + 4 * EB * v);
+    uint32_t w[EB + 1];
 #pragma unroll
-    for (int i = 0; i < 32; i++) r[i] = Q + ETA - ((w[i >> 3] >> (4 * (i & 7))) & 15);
+    for (int i = 0; i < EB; i++) w[i] = __ldg(src + i);
+    w[EB] = 0;
+#pragma unroll
+    for (int i = 0; i < 32; i++) r[i] = Q + ETA - field32<EB>(w, i);
   } else {  // UnpackT0 (pack.go:56-86): 13-bit fields, Q + 2^12 - x
     const uint32_t* src = reinterpret_cast<const uint32_t*>(skp + OFF_T0 + 416 * (p - L - K) + 52 * v);
     uint32_t w[14];
@@ -176,12 +245,14 @@ struct ByteSponge {  // SHAKE256 absorber for unaligned byte streams (thread-loc
   }
 };
 
+template <class P>
 __global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk, size_t sk_stride,
                                                  const uint8_t* __restrict__ msgs, const uint64_t* __restrict__ msg_off,
                                                  const uint8_t* __restrict__ ctx, int ctxlen, int internal,
                                                  const uint8_t* __restrict__ rnd, size_t n, uint64_t* __restrict__ mu,
                                                  uint64_t* __restrict__ rhop, uint32_t* __restrict__ attempt,
                                                  uint32_t* __restrict__ act) {
+  MLDSA_USE(P);
   const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= n) return;
   const uint8_t* skp = sk + op * sk_stride;
@@ -222,9 +293,11 @@ __global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk,
 
 // ------------------------------------------------------------------ per-round kernels
 // y[i] = ExpandMask(rho', L*attempt + i)  (sample.go:187-209, pack.go:177-195)
+template <class P>
 __global__ void __launch_bounds__(128) mask_kernel(const uint32_t* __restrict__ act, size_t nact,
                                                    const uint64_t* __restrict__ rhop,
                                                    const uint32_t* __restrict__ attempt, uint32_t* __restrict__ y) {
+  MLDSA_USE(P);
   const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nact * L) return;
   const size_t op = act[s % nact];
@@ -246,18 +319,16 @@ __global__ void __launch_bounds__(128) mask_kernel(const uint32_t* __restrict__ 
   buf[85] = 0;
   uint4* out = reinterpret_cast<uint4*>(y + (op * L + i) * N);
 #pragma unroll 2
-  for (int p = 0; p < 64; p++) {  // 10 bytes -> 4 coefficients
+  for (int p = 0; p < 64; p++) {  // 4 coefficients of ZBITS bits each (internal/pack.go:146-203)
     uint32_t cf[4];
 #pragma unroll
-    for (int h = 0; h < 2; h++) {
-      const int byte = 10 * p + 5 * h, wi = byte >> 3, sh = (byte & 7) * 8;
-      uint64_t v40 = buf[wi] >> sh;
-      if (sh > 24) v40 |= buf[wi + 1] << (64 - sh);
-      uint32_t p0 = GAMMA1 - (uint32_t)(v40 & 0xfffff), p1 = GAMMA1 - (uint32_t)((v40 >> 20) & 0xfffff);
-      p0 += (uint32_t)((int32_t)p0 >> 31) & Q;
-      p1 += (uint32_t)((int32_t)p1 >> 31) & Q;
-      cf[2 * h] = p0;
-      cf[2 * h + 1] = p1;
+    for (int h = 0; h < 4; h++) {
+      const int bit = ZBITS * (4 * p + h), wi = bit >> 6, sh = bit & 63;
+      uint64_t f = buf[wi] >> sh;
+      if (sh + ZBITS > 64) f |= buf[wi + 1] << (64 - sh);
+      uint32_t c = GAMMA1 - ((uint32_t)f & ((1u << ZBITS) - 1));
+      c += (uint32_t)((int32_t)c >> 31) & Q;
+      cf[h] = c;
     }
     out[p] = make_uint4(cf[0], cf[1], cf[2], cf[3]);
   }
@@ -278,9 +349,11 @@ __device__ __forceinline__ OctetCtx octet_ctx(uint32_t* tiles) {
 }
 
 // yh = NTT(y): octet per (active op, j)
+template <class P>
 __global__ void __launch_bounds__(128) yntt_kernel(const uint32_t* __restrict__ act, size_t nact,
                                                    const uint32_t* __restrict__ y, uint32_t* __restrict__ yh,
                                                    const uint32_t* __restrict__ zetas) {
+  MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   const OctetCtx o = octet_ctx(tiles);
   const size_t total = nact * L, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
@@ -297,20 +370,29 @@ __global__ void __launch_bounds__(128) yntt_kernel(const uint32_t* __restrict__ 
   if (active) gstore_C(yh + (op * L + j) * N, o.v, r);
 }
 
-// decompose (rounding.go:13-43, alpha = 523776)
+// decompose (rounding.go:13-43): alpha = 523776 (gamma2 = (q-1)/32) or 190464 (gamma2 = (q-1)/88)
+template <class P>
 __device__ __forceinline__ void decompose(uint32_t a, uint32_t& a0plusq, uint32_t& a1) {
+  constexpr uint32_t ALPHA = 2 * P::GAMMA2;
   a1 = (a + 127) >> 7;
-  a1 = (a1 * 1025 + (1u << 21)) >> 22;
-  a1 &= 15;
+  if constexpr (ALPHA == 523776) {
+    a1 = (a1 * 1025 + (1u << 21)) >> 22;
+    a1 &= 15;
+  } else {
+    a1 = (a1 * 11275 + (1u << 23)) >> 24;
+    a1 ^= (uint32_t)((int32_t)(43 - a1) >> 31) & a1;
+  }
   a0plusq = a - a1 * ALPHA;
   a0plusq += (uint32_t)((int32_t)(a0plusq - (Q - 1) / 2) >> 31) & Q;
 }
 
 // w[i] = InvNTT(ReduceLe2Q(A[i] . yh)), NormalizeAssumingLe2Q, Decompose (dilithium.go:386-394): octet per (op, i)
+template <class P>
 __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
                                                 const uint32_t* __restrict__ A, const uint32_t* __restrict__ yh,
-                                                uint32_t* __restrict__ w0, uint8_t* __restrict__ w1p,
+                                                uint32_t* __restrict__ w0, uint8_t* __restrict__ w1u,
                                                 const uint32_t* __restrict__ zetas) {
+  MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   const OctetCtx o = octet_ctx(tiles);
   const size_t total = nact * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
@@ -343,57 +425,60 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
   load_lane_tw_inv(t, zetas + 256, o.v);
   invntt_octet(acc, o.tile, o.v, t);  // -> S layout: acc[2s+b] = coefficient 16s + 2v + b
   uint32_t* w0p = w0 + (op * K + i) * N;
-  uint8_t* w1b = w1p + op * (K * POLY_W1) + i * POLY_W1;
+  uint8_t* w1b = w1u + (op * K + i) * 256;
 #pragma unroll
   for (int s = 0; s < 16; s++) {
     uint32_t lo0, hi0, lo1, hi1;
-    decompose(le2q_modq(acc[2 * s]), lo0, hi0);
-    decompose(le2q_modq(acc[2 * s + 1]), lo1, hi1);
+    decompose<P>(le2q_modq(acc[2 * s]), lo0, hi0);
+    decompose<P>(le2q_modq(acc[2 * s + 1]), lo1, hi1);
     if (active) {
       *reinterpret_cast<uint2*>(w0p + 16 * s + 2 * o.v) = make_uint2(lo0, lo1);
-      w1b[8 * s + o.v] = (uint8_t)(hi0 | (hi1 << 4));  // PackLe16 (pack.go:102-108)
+      *reinterpret_cast<uint16_t*>(w1b + 16 * s + 2 * o.v) = (uint16_t)(hi0 | (hi1 << 8));  // one byte per coefficient
     }
   }
 }
 
 // c~ = H(mu || w1) (dilithium.go:397-401), c = SampleInBall(c~) (sample.go:299-339): thread per op
+template <class P>
 __global__ void __launch_bounds__(128) challenge_kernel(const uint32_t* __restrict__ act, size_t nact,
-                                                        const uint64_t* __restrict__ mu, const uint8_t* __restrict__ w1p,
+                                                        const uint64_t* __restrict__ mu, const uint8_t* __restrict__ w1u,
                                                         uint64_t* __restrict__ ctilde, uint32_t* __restrict__ cpoly,
                                                         uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags,
                                                         uint32_t* __restrict__ hintcnt) {
+  MLDSA_USE(P);
   const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nact) return;
   const size_t op = act[s];
   uint64_t a[25];
   keccak::zero(a);
-  // stream = mu (8 words) || w1 packed (96 words) = 104 words = 6 full blocks + 2 words
-  const uint64_t* w1w = reinterpret_cast<const uint64_t*>(w1p + op * (K * POLY_W1));
+  // stream = mu (8 words) || PackW1(w1) (K * POLY_W1 / 8 words), absorbed 17 words at a time
+  constexpr int WORDS = 8 + K * POLY_W1 / 8, FULL = WORDS / 17, REM = WORDS % 17, CTW = CTILDE / 8;
+  const uint8_t* w1o = w1u + op * (K * 256);
 #pragma unroll 1
-  for (int b = 0; b < 6; b++) {
+  for (int b = 0; b < FULL; b++) {
 #pragma unroll
     for (int w = 0; w < 17; w++) {
       const int k = 17 * b + w;
-      a[w] ^= (k < 8) ? mu[8 * op + k] : w1w[k - 8];
+      a[w] ^= (k < 8) ? mu[8 * op + k] : w1_word<P>(w1o, k - 8);
     }
     keccak::f1600(a);
   }
-  a[0] ^= w1w[102 - 8];
-  a[1] ^= w1w[103 - 8];
-  a[2] ^= 0x1f;
+#pragma unroll
+  for (int w = 0; w < REM; w++) a[w] ^= w1_word<P>(w1o, 17 * FULL + w - 8);
+  a[REM] ^= 0x1f;
   a[16] ^= 0x8000000000000000ull;
   keccak::f1600(a);
-  uint64_t ct[6];
+  uint64_t ct[CTW];
 #pragma unroll
-  for (int i = 0; i < 6; i++) {
+  for (int i = 0; i < CTW; i++) {
     ct[i] = a[i];
-    ctilde[6 * op + i] = ct[i];
+    ctilde[CTW * op + i] = ct[i];
   }
   // SampleInBall
   keccak::zero(a);
 #pragma unroll
-  for (int i = 0; i < 6; i++) a[i] = ct[i];
-  a[6] = 0x1f;
+  for (int i = 0; i < CTW; i++) a[i] = ct[i];
+  a[CTW] = 0x1f;
   a[16] = 0x8000000000000000ull;
   keccak::f1600(a);
   uint64_t buf[17];
@@ -420,7 +505,7 @@ __global__ void __launch_bounds__(128) challenge_kernel(const uint32_t* __restri
     c[b] = (signs & 1) ? Q - 1 : 1;
     signs >>= 1;
   }
-  for (int i = 0; i < 48; i++) hintbits[48 * op + i] = 0;
+  for (int i = 0; i < 8 * K; i++) hintbits[8 * K * op + i] = 0;
   flags[op] = 0;
   hintcnt[op] = 0;
 }
@@ -461,18 +546,22 @@ __device__ __forceinline__ void c_times(uint32_t (&r)[32], const uint32_t* __res
 }
 
 // makeHint (rounding.go:56-67)
+template <class P>
 __device__ __forceinline__ uint32_t make_hint(uint32_t z0, uint32_t r1) {
+  constexpr uint32_t GAMMA2 = P::GAMMA2;
   return (z0 <= GAMMA2 || z0 > Q - GAMMA2 || (z0 == Q - GAMMA2 && r1 == 0)) ? 0u : 1u;
 }
 
 // The three norm checks + hint (dilithium.go:407-464): octet per (op, item), item < K: row i of the K-vectors
 // (w0 - c s2, c t0, hint), item >= K: polynomial j of z = y + c s1 (packed straight into the signature).
+template <class P>
 __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
                                                        const uint32_t* __restrict__ sh, const uint32_t* __restrict__ cpoly,
                                                        const uint32_t* __restrict__ y, const uint32_t* __restrict__ w0,
-                                                       const uint8_t* __restrict__ w1p, uint8_t* __restrict__ zbuf,
+                                                       const uint8_t* __restrict__ w1u, uint8_t* __restrict__ zbuf,
                                                        uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags,
                                                        uint32_t* __restrict__ hintcnt, const uint32_t* __restrict__ zetas) {
+  MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   __shared__ uint32_t izs[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) izs[i] = zetas[256 + i];
@@ -503,18 +592,18 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
     }
     uint32_t u0[32];
     c_times(u0, chat, keyp + (L + K + i) * N, o, ti);  // c t0[i]
-    const uint8_t* w1b = w1p + op * (K * POLY_W1) + i * POLY_W1;
+    const uint8_t* w1b = w1u + (op * K + i) * 256;
     uint32_t pop = 0;
 #pragma unroll
     for (int s = 0; s < 16; s++) {
       const uint32_t t0 = le2q_modq(u0[2 * s]), t1 = le2q_modq(u0[2 * s + 1]);
       reject |= exceeds1(t0, GAMMA2) | exceeds1(t1, GAMMA2);
-      const uint32_t h1byte = w1b[8 * s + o.v];
-      const uint32_t h0 = make_hint(le2q_modq(r[2 * s] + t0), h1byte & 15);
-      const uint32_t h1 = make_hint(le2q_modq(r[2 * s + 1] + t1), h1byte >> 4);
+      const uint32_t w1pair = *reinterpret_cast<const uint16_t*>(w1b + 16 * s + 2 * o.v);
+      const uint32_t h0 = make_hint<P>(le2q_modq(r[2 * s] + t0), w1pair & 0xff);
+      const uint32_t h1 = make_hint<P>(le2q_modq(r[2 * s + 1] + t1), w1pair >> 8);
       const uint32_t bits = h0 | (h1 << 1);
       pop += h0 + h1;
-      if (bits && active) atomicOr(hintbits + 48 * op + 8 * i + (s >> 1), bits << (16 * (s & 1) + 2 * o.v));
+      if (bits && active) atomicOr(hintbits + 8 * K * op + 8 * i + (s >> 1), bits << (16 * (s & 1) + 2 * o.v));
     }
     if (pop && active) atomicAdd(hintcnt + op, pop);
   } else {
@@ -531,15 +620,15 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
     // PolyPackLeGamma1 (internal/pack.go:236-252): 32 coefficients -> 20 aligned words in the staging
     // buffer; finalize copies them into the (3309-byte strided) signature only if the attempt is accepted
     s_to_c(r, o.tile, o.v);
-    uint32_t* zw = reinterpret_cast<uint32_t*>(zbuf + (op * L + j) * (size_t)POLY_Z) + 20 * o.v;
+    uint32_t* zw = reinterpret_cast<uint32_t*>(zbuf + (op * L + j) * (size_t)POLY_Z) + ZBITS * o.v;
     uint64_t accb = 0;
     int bits = 0, ow = 0;
 #pragma unroll
     for (int c = 0; c < 32; c++) {
       uint32_t p = GAMMA1 - r[c];
       p += (uint32_t)((int32_t)p >> 31) & Q;
-      accb |= (uint64_t)(p & 0xfffff) << bits;
-      bits += 20;
+      accb |= (uint64_t)(p & ((1u << ZBITS) - 1)) << bits;
+      bits += ZBITS;
       if (bits >= 32) {
         if (active) zw[ow] = (uint32_t)accb;
         ow++;
@@ -554,6 +643,7 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
 
 // accept -> c~, z and hints into the signature; reject -> next attempt (dilithium.go:369-377,459-469).
 // One warp per active op.
+template <class P>
 __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restrict__ act, size_t nact,
                                                        const uint64_t* __restrict__ ctilde,
                                                        const uint8_t* __restrict__ zbuf,
@@ -562,6 +652,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restric
                                                        const uint32_t* __restrict__ hintcnt, uint32_t* __restrict__ attempt,
                                                        uint8_t* __restrict__ sig, uint8_t* __restrict__ status,
                                                        uint32_t* __restrict__ next, uint32_t* __restrict__ next_count) {
+  MLDSA_USE(P);
   const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= nact) return;
@@ -569,7 +660,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restric
   uint8_t* sg = sig + op * (size_t)SIG_BYTES;
   const bool accept = flags[op] == 0 && hintcnt[op] <= OMEGA;
   if (accept) {
-    const uint8_t* ct = reinterpret_cast<const uint8_t*>(ctilde + 6 * op);
+    const uint8_t* ct = reinterpret_cast<const uint8_t*>(ctilde + (CTILDE / 8) * op);
     for (int i = lane; i < CTILDE; i += 32) sg[i] = ct[i];
     const uint8_t* zs = zbuf + op * (size_t)(L * POLY_Z);
     for (int i = lane; i < L * POLY_Z; i += 32) sg[CTILDE + i] = zs[i];
@@ -578,7 +669,7 @@ __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restric
       int off = 0;
       for (int i = 0; i < K; i++) {
         for (int w = 0; w < 8; w++) {
-          uint32_t m = hintbits[48 * op + 8 * i + w];
+          uint32_t m = hintbits[8 * K * op + 8 * i + w];
           while (m) {
             const int bit = __ffs(m) - 1;
             hb[off++] = (uint8_t)(32 * w + bit);
@@ -610,10 +701,10 @@ __global__ void iota_kernel(uint32_t* a, size_t n) {
 
 // ================================================================== Verify
 // internal/dilithium.go:273-332.  pk = rho (32) || t1 (6 x 320); sig = c~ (48) || z (5 x 640) || hints (61).
-constexpr int PK_BYTES = 1952, POLY_T1 = 320;
 
 // tr = H(pk), mu = H(tr || M'), c = SampleInBall(c~), hint unpacking with the validity rules of
 // UnpackHint (internal/pack.go:113-140).  One thread per op.
+template <class P>
 __global__ void __launch_bounds__(128) verify_prep_kernel(const uint8_t* __restrict__ pk, size_t pk_stride,
                                                           const uint8_t* __restrict__ msgs,
                                                           const uint64_t* __restrict__ msg_off,
@@ -621,23 +712,25 @@ __global__ void __launch_bounds__(128) verify_prep_kernel(const uint8_t* __restr
                                                           const uint8_t* __restrict__ sig, size_t n,
                                                           uint64_t* __restrict__ mu, uint32_t* __restrict__ cpoly,
                                                           uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags) {
+  MLDSA_USE(P);
   const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= n) return;
   const uint8_t* pkp = pk + op * pk_stride;
   const uint8_t* sg = sig + op * (size_t)SIG_BYTES;
   uint64_t a[25];
   keccak::zero(a);
-  {  // tr = SHAKE256(pk, 64): 244 words = 14 full blocks + 6 words (dilithium.go:122-125)
+  {  // tr = SHAKE256(pk, 64) (dilithium.go:122-125)
+    constexpr int PW = PK_BYTES / 8, FULL = PW / 17, REM = PW % 17;
     const uint64_t* pw = reinterpret_cast<const uint64_t*>(pkp);
 #pragma unroll 1
-    for (int b = 0; b < 14; b++) {
+    for (int b = 0; b < FULL; b++) {
 #pragma unroll
       for (int w = 0; w < 17; w++) a[w] ^= __ldg(pw + 17 * b + w);
       keccak::f1600(a);
     }
 #pragma unroll
-    for (int w = 0; w < 6; w++) a[w] ^= __ldg(pw + 238 + w);
-    a[6] ^= 0x1f;
+    for (int w = 0; w < REM; w++) a[w] ^= __ldg(pw + 17 * FULL + w);
+    a[REM] ^= 0x1f;
     a[16] ^= 0x8000000000000000ull;
     keccak::f1600(a);
   }
@@ -656,7 +749,7 @@ __global__ void __launch_bounds__(128) verify_prep_kernel(const uint8_t* __restr
   // c = SampleInBall(sig.c)
   keccak::zero(a);
   for (int i = 0; i < CTILDE; i++) a[i >> 3] |= (uint64_t)sg[i] << (8 * (i & 7));
-  a[6] = 0x1f;
+  a[CTILDE / 8] = 0x1f;
   a[16] = 0x8000000000000000ull;
   keccak::f1600(a);
   uint64_t buf[17];
@@ -684,8 +777,8 @@ __global__ void __launch_bounds__(128) verify_prep_kernel(const uint8_t* __restr
     signs >>= 1;
   }
   // UnpackHint
-  uint32_t* hb = hintbits + 48 * op;
-  for (int i = 0; i < 48; i++) hb[i] = 0;
+  uint32_t* hb = hintbits + 8 * K * op;
+  for (int i = 0; i < 8 * K; i++) hb[i] = 0;
   const uint8_t* hp = sg + CTILDE + L * POLY_Z;
   bool ok = true;
   int prev = 0;
@@ -710,8 +803,10 @@ __global__ void __launch_bounds__(128) verify_prep_kernel(const uint8_t* __restr
 }
 
 // zh[j] = NTT(UnpackLeGamma1(sig.z[j])), reject if z exceeds gamma1 - beta (dilithium.go:87-90): octet per (op, j)
+template <class P>
 __global__ void __launch_bounds__(128) verify_z_kernel(const uint8_t* __restrict__ sig, size_t n, uint32_t* __restrict__ zh,
                                                        uint32_t* __restrict__ flags, const uint32_t* __restrict__ zetas) {
+  MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   const OctetCtx o = octet_ctx(tiles);
   const unsigned octmask = 0xffu << (8 * o.oct);
@@ -721,19 +816,20 @@ __global__ void __launch_bounds__(128) verify_z_kernel(const uint8_t* __restrict
   const size_t u = active ? base + o.oct : total - 1;
   const size_t op = u % n;
   const int j = (int)(u / n);
-  const uint8_t* zb = sig + op * (size_t)SIG_BYTES + CTILDE + POLY_Z * j + 80 * o.v;  // unaligned: byte loads
+  const uint8_t* zb = sig + op * (size_t)SIG_BYTES + CTILDE + POLY_Z * j + 4 * ZBITS * o.v;  // unaligned: byte loads
+  uint32_t zw[ZBITS + 1];
+#pragma unroll
+  for (int q = 0; q < ZBITS; q++)
+    zw[q] = (uint32_t)zb[4 * q] | ((uint32_t)zb[4 * q + 1] << 8) | ((uint32_t)zb[4 * q + 2] << 16) | ((uint32_t)zb[4 * q + 3] << 24);
+  zw[ZBITS] = 0;
   uint32_t r[32];
   bool reject = false;
 #pragma unroll
-  for (int p = 0; p < 16; p++) {  // 5 bytes -> 2 coefficients (internal/pack.go:177-195)
-    const uint32_t b0 = zb[5 * p], b1 = zb[5 * p + 1], b2 = zb[5 * p + 2], b3 = zb[5 * p + 3], b4 = zb[5 * p + 4];
-    uint32_t p0 = GAMMA1 - (b0 | (b1 << 8) | ((b2 & 0xf) << 16));
-    uint32_t p1 = GAMMA1 - ((b2 >> 4) | (b3 << 4) | (b4 << 12));
-    p0 += (uint32_t)((int32_t)p0 >> 31) & Q;
-    p1 += (uint32_t)((int32_t)p1 >> 31) & Q;
-    reject |= exceeds1(p0, GAMMA1 - BETA) | exceeds1(p1, GAMMA1 - BETA);
-    r[2 * p] = p0;
-    r[2 * p + 1] = p1;
+  for (int q = 0; q < 32; q++) {  // PolyUnpackLeGamma1 (internal/pack.go:146-203)
+    uint32_t c = GAMMA1 - field32<ZBITS>(zw, q);
+    c += (uint32_t)((int32_t)c >> 31) & Q;
+    reject |= exceeds1(c, GAMMA1 - BETA);
+    r[q] = c;
   }
   c_to_s(r, o.tile, o.v);
   LaneTw t;
@@ -745,11 +841,13 @@ __global__ void __launch_bounds__(128) verify_z_kernel(const uint8_t* __restrict
 }
 
 // w1' = UseHint(InvNTT(A z - c t1 2^d), h), packed (dilithium.go:297-316, rounding.go:98-135): octet per (op, i)
+template <class P>
 __global__ void __launch_bounds__(128) verify_w_kernel(const uint8_t* __restrict__ pk, size_t pk_stride, int key_shared,
                                                        const uint32_t* __restrict__ A, const uint32_t* __restrict__ zh,
                                                        const uint32_t* __restrict__ cpoly,
                                                        const uint32_t* __restrict__ hintbits, size_t n,
-                                                       uint8_t* __restrict__ w1p, const uint32_t* __restrict__ zetas) {
+                                                       uint8_t* __restrict__ w1u, const uint32_t* __restrict__ zetas) {
+  MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   __shared__ uint32_t izs[256];
   for (int i = threadIdx.x; i < 256; i += blockDim.x) izs[i] = zetas[256 + i];
@@ -810,42 +908,55 @@ __global__ void __launch_bounds__(128) verify_w_kernel(const uint8_t* __restrict
 #pragma unroll
   for (int c = 0; c < 32; c++) r[c] = reduce_le2q(r[c]);
   invntt_octet_smem(r, o.tile, o.v, izs);  // -> S layout
-  uint8_t* w1b = w1p + op * (K * POLY_W1) + i * POLY_W1;
-  const uint32_t* hb = hintbits + 48 * op + 8 * i;
+  uint8_t* w1b = w1u + (op * K + i) * 256;
+  const uint32_t* hb = hintbits + 8 * K * op + 8 * i;
 #pragma unroll
   for (int s = 0; s < 16; s++) {
     const uint32_t hbits = (hb[s >> 1] >> (16 * (s & 1) + 2 * o.v)) & 3;
-    uint32_t q0, h0, q1, h1;
-    decompose(le2q_modq(r[2 * s]), q0, h0);
-    decompose(le2q_modq(r[2 * s + 1]), q1, h1);
-    if (hbits & 1) h0 = (q0 > Q) ? ((h0 + 1) & 15) : ((h0 - 1) & 15);
-    if (hbits & 2) h1 = (q1 > Q) ? ((h1 + 1) & 15) : ((h1 - 1) & 15);
-    if (active) w1b[8 * s + o.v] = (uint8_t)(h0 | (h1 << 4));
+    uint32_t q[2], h[2];
+    decompose<P>(le2q_modq(r[2 * s]), q[0], h[0]);
+    decompose<P>(le2q_modq(r[2 * s + 1]), q[1], h[1]);
+#pragma unroll
+    for (int e = 0; e < 2; e++) {  // PolyUseHint (rounding.go:98-135)
+      if (!((hbits >> e) & 1)) continue;
+      if constexpr (P::GAMMA2 == 261888) {
+        h[e] = (q[e] > Q) ? ((h[e] + 1) & 15) : ((h[e] - 1) & 15);
+      } else {
+        if (q[e] > Q)
+          h[e] = (h[e] == 43) ? 0 : h[e] + 1;
+        else
+          h[e] = (h[e] == 0) ? 43 : h[e] - 1;
+      }
+    }
+    if (active) *reinterpret_cast<uint16_t*>(w1b + 16 * s + 2 * o.v) = (uint16_t)(h[0] | (h[1] << 8));
   }
 }
 
 // ok = valid && (c~ == H(mu || w1')) (dilithium.go:318-331): thread per op
+template <class P>
 __global__ void __launch_bounds__(128) verify_final_kernel(const uint8_t* __restrict__ sig, const uint64_t* __restrict__ mu,
-                                                           const uint8_t* __restrict__ w1p,
+                                                           const uint8_t* __restrict__ w1u,
                                                            const uint32_t* __restrict__ flags, size_t n,
                                                            uint8_t* __restrict__ okout) {
+  MLDSA_USE(P);
   const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= n) return;
   uint64_t a[25];
   keccak::zero(a);
-  const uint64_t* w1w = reinterpret_cast<const uint64_t*>(w1p + op * (K * POLY_W1));
+  constexpr int WORDS = 8 + K * POLY_W1 / 8, FULL = WORDS / 17, REM = WORDS % 17;
+  const uint8_t* w1o = w1u + op * (K * 256);
 #pragma unroll 1
-  for (int b = 0; b < 6; b++) {
+  for (int b = 0; b < FULL; b++) {
 #pragma unroll
     for (int w = 0; w < 17; w++) {
       const int k = 17 * b + w;
-      a[w] ^= (k < 8) ? mu[8 * op + k] : w1w[k - 8];
+      a[w] ^= (k < 8) ? mu[8 * op + k] : w1_word<P>(w1o, k - 8);
     }
     keccak::f1600(a);
   }
-  a[0] ^= w1w[94];
-  a[1] ^= w1w[95];
-  a[2] ^= 0x1f;
+#pragma unroll
+  for (int w = 0; w < REM; w++) a[w] ^= w1_word<P>(w1o, 17 * FULL + w - 8);
+  a[REM] ^= 0x1f;
   a[16] ^= 0x8000000000000000ull;
   keccak::f1600(a);
   const uint8_t* sg = sig + op * (size_t)SIG_BYTES;
@@ -854,9 +965,11 @@ __global__ void __launch_bounds__(128) verify_final_kernel(const uint8_t* __rest
   okout[op] = (same && flags[op] == 0) ? 1 : 0;
 }
 
+template <class P>
 static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off,
                          const uint8_t* ctxstr, int ctxlen, const uint8_t* sig, uint8_t* okout, size_t n, int internal,
                          cudaStream_t st, int slot) {
+  MLDSA_USE(P);
   Ctx& c = ctx();
   const bool shared = pk_stride == 0;
   const size_t nkeys = shared ? 1 : n;
@@ -867,7 +980,7 @@ static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
     return o;
   };
   const size_t oA = take(nkeys * K * L * 1024), oMu = take(n * 64), oZh = take(n * L * 1024), oC = take(n * 1024),
-               oHb = take(n * 48 * 4), oFl = take(n * 4), oW1 = take(n * K * POLY_W1), oAct = take(n * 4);
+               oHb = take(n * 8 * K * 4), oFl = take(n * 4), oW1 = take(n * K * 256), oAct = take(n * 4);
   void* base = nullptr;
   int rc = ensure_work(slot, off, &base);
   if (rc) return rc;
@@ -883,23 +996,23 @@ static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
   static bool attr_set = false;
   if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
     attr_set = true;
   }
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
   {
     KernelScope ks(KID_MLDSA_EXPAND, st);  // ExpandA(rho): rho is the first 32 bytes of pk
-    expand_a_kernel<<<blocks(nkeys * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(pk, pk_stride,
+    expand_a_kernel<P><<<blocks(nkeys * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(pk, pk_stride,
                                                                                                         nkeys, A);
   }
   {
     KernelScope ks(KID_MLDSA_MU, st);
-    verify_prep_kernel<<<blocks(n, 128), 128, 0, st>>>(pk, pk_stride, msgs, msg_off, ctxstr, ctxlen, internal, sig, n, mu,
+    verify_prep_kernel<P><<<blocks(n, 128), 128, 0, st>>>(pk, pk_stride, msgs, msg_off, ctxstr, ctxlen, internal, sig, n, mu,
                                                        cp, hb, fl);
   }
   {
     KernelScope ks(KID_MLDSA_W, st);
-    verify_z_kernel<<<blocks(n * L, 16), 128, 0, st>>>(sig, n, zh, fl, zetas);
+    verify_z_kernel<P><<<blocks(n * L, 16), 128, 0, st>>>(sig, n, zh, fl, zetas);
   }
   {
     KernelScope ks(KID_MLDSA_COMPACT, st);
@@ -911,11 +1024,11 @@ static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
   }
   {
     KernelScope ks(KID_MLDSA_W, st);
-    verify_w_kernel<<<blocks(n * K, 16), 128, 0, st>>>(pk, pk_stride, shared ? 1 : 0, A, zh, cp, hb, n, w1p, zetas);
+    verify_w_kernel<P><<<blocks(n * K, 16), 128, 0, st>>>(pk, pk_stride, shared ? 1 : 0, A, zh, cp, hb, n, w1p, zetas);
   }
   {
     KernelScope ks(KID_MLDSA_CHALLENGE, st);
-    verify_final_kernel<<<blocks(n, 128), 128, 0, st>>>(sig, mu, w1p, fl, n, okout);
+    verify_final_kernel<P><<<blocks(n, 128), 128, 0, st>>>(sig, mu, w1p, fl, n, okout);
   }
   CB200_CUDA(cudaGetLastError());
   return 0;
@@ -924,8 +1037,10 @@ static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
 // ================================================================== KeyGen
 // NewKeyFromSeed, internal/dilithium.go:181-241 (+ computeT0andT1 :253-267).
 // (rho, rho', key) = SHAKE256(seed || K || L, 128); thread per op
+template <class P>
 __global__ void __launch_bounds__(128) kg_seed_kernel(const uint8_t* __restrict__ seed, size_t n, uint8_t* __restrict__ pk,
                                                       uint8_t* __restrict__ sk, uint64_t* __restrict__ sseed) {
+  MLDSA_USE(P);
   const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= n) return;
   const uint64_t* sd = reinterpret_cast<const uint64_t*>(seed + 32 * op);
@@ -950,8 +1065,10 @@ __global__ void __launch_bounds__(128) kg_seed_kernel(const uint8_t* __restrict_
 
 // s1, s2 = PolyDeriveUniformLeqEta (sample.go:129-181, eta = 4): thread per (op, poly); the accepted nibbles
 // are at once the PackLeqEta image (internal/pack.go:13-20), so the packed key is written here too.
+template <class P>
 __global__ void __launch_bounds__(kExpThreads) kg_eta_kernel(const uint64_t* __restrict__ sseed, size_t n,
                                                              uint32_t* __restrict__ spoly, uint8_t* __restrict__ sk) {
+  MLDSA_USE(P);
   extern __shared__ __align__(16) uint32_t rows[];
   const size_t s0 = (size_t)blockIdx.x * blockDim.x, total = n * (L + K);
   const size_t s = s0 + threadIdx.x;
@@ -973,9 +1090,16 @@ __global__ void __launch_bounds__(kExpThreads) kg_eta_kernel(const uint64_t* __r
       const uint64_t x = a[w];
 #pragma unroll
       for (int q = 0; q < 16; q++) {
-        const uint32_t t = (uint32_t)(x >> (4 * q)) & 15;
-        row[ctr] = t;  // the nibble itself; Q + eta - t is formed on the way out
-        ctr += (t <= 2 * ETA && ctr < N);
+        uint32_t t = (uint32_t)(x >> (4 * q)) & 15;
+        bool ok;
+        if constexpr (ETA == 2) {  // accept t <= 14, reduce mod 5 (sample.go:144-156)
+          ok = t <= 14;
+          t -= ((205 * t) >> 10) * 5;
+        } else {
+          ok = t <= 2 * ETA;
+        }
+        row[ctr] = t;  // eta - coefficient; Q + eta - t is formed on the way out
+        ctr += (ok && ctr < N);
       }
     }
   } while (ctr < N);
@@ -987,19 +1111,32 @@ __global__ void __launch_bounds__(kExpThreads) kg_eta_kernel(const uint64_t* __r
     const size_t qop = sp % n;
     const int qp = (int)(sp / n);
     uint32_t* dst = spoly + (qop * (L + K) + qp) * N;
-    uint8_t* pb = sk + qop * (size_t)SK_BYTES + OFF_S1 + 128 * qp;
+    uint8_t* pb = sk + qop * (size_t)SK_BYTES + OFF_S1 + POLY_ETA * qp;
+    // each lane owns coefficients 8*lane .. 8*lane+7: 8 values -> 4 bytes (eta = 4) or 3 bytes (eta = 2)
+    uint32_t t[8];
 #pragma unroll
-    for (int w = 0; w < 4; w++) {
-      const uint32_t t0 = rows[q * kExpRow + 64 * w + 2 * lane], t1 = rows[q * kExpRow + 64 * w + 2 * lane + 1];
-      *reinterpret_cast<uint2*>(dst + 64 * w + 2 * lane) = make_uint2(Q + ETA - t0, Q + ETA - t1);
-      pb[32 * w + lane] = (uint8_t)(t0 | (t1 << 4));
+    for (int e = 0; e < 8; e++) t[e] = rows[q * kExpRow + 8 * lane + e];
+    *reinterpret_cast<uint4*>(dst + 8 * lane) = make_uint4(Q + ETA - t[0], Q + ETA - t[1], Q + ETA - t[2], Q + ETA - t[3]);
+    *reinterpret_cast<uint4*>(dst + 8 * lane + 4) = make_uint4(Q + ETA - t[4], Q + ETA - t[5], Q + ETA - t[6], Q + ETA - t[7]);
+    if constexpr (ETA == 4) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) pb[4 * lane + e] = (uint8_t)(t[2 * e] | (t[2 * e + 1] << 4));
+    } else {
+      uint32_t bits = 0;
+#pragma unroll
+      for (int e = 0; e < 8; e++) bits |= t[e] << (3 * e);
+      pb[3 * lane] = (uint8_t)bits;
+      pb[3 * lane + 1] = (uint8_t)(bits >> 8);
+      pb[3 * lane + 2] = (uint8_t)(bits >> 16);
     }
   }
 }
 
 // s1h = NTT(s1): octet per (op, j)
+template <class P>
 __global__ void __launch_bounds__(128) kg_s1ntt_kernel(const uint32_t* __restrict__ spoly, size_t n, uint32_t* __restrict__ s1h,
                                                        const uint32_t* __restrict__ zetas) {
+  MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   const OctetCtx o = octet_ctx(tiles);
   const size_t total = n * L, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
@@ -1017,9 +1154,11 @@ __global__ void __launch_bounds__(128) kg_s1ntt_kernel(const uint32_t* __restric
 }
 
 // t = Normalize(InvNTT(ReduceLe2Q(A[i] . s1h)) + s2[i]); Power2Round; PackT1 -> pk, PackT0 -> sk: octet per (op, i)
+template <class P>
 __global__ void __launch_bounds__(128) kg_t_kernel(const uint32_t* __restrict__ A, const uint32_t* __restrict__ s1h,
                                                    const uint32_t* __restrict__ spoly, size_t n, uint8_t* __restrict__ pk,
                                                    uint8_t* __restrict__ sk, const uint32_t* __restrict__ zetas) {
+  MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   const OctetCtx o = octet_ctx(tiles);
   const size_t total = n * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
@@ -1091,21 +1230,24 @@ __global__ void __launch_bounds__(128) kg_t_kernel(const uint32_t* __restrict__ 
 }
 
 // tr = SHAKE256(pk, 64) -> sk[64:128] (dilithium.go:233-236): thread per op
+template <class P>
 __global__ void __launch_bounds__(128) kg_tr_kernel(const uint8_t* __restrict__ pk, size_t n, uint8_t* __restrict__ sk) {
+  MLDSA_USE(P);
   const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= n) return;
   const uint64_t* pw = reinterpret_cast<const uint64_t*>(pk + op * (size_t)PK_BYTES);
   uint64_t a[25];
   keccak::zero(a);
+  constexpr int PW = PK_BYTES / 8, FULL = PW / 17, REM = PW % 17;
 #pragma unroll 1
-  for (int b = 0; b < 14; b++) {
+  for (int b = 0; b < FULL; b++) {
 #pragma unroll
     for (int w = 0; w < 17; w++) a[w] ^= pw[17 * b + w];
     keccak::f1600(a);
   }
 #pragma unroll
-  for (int w = 0; w < 6; w++) a[w] ^= pw[238 + w];
-  a[6] ^= 0x1f;
+  for (int w = 0; w < REM; w++) a[w] ^= pw[17 * FULL + w];
+  a[REM] ^= 0x1f;
   a[16] ^= 0x8000000000000000ull;
   keccak::f1600(a);
   uint64_t* tr = reinterpret_cast<uint64_t*>(sk + op * (size_t)SK_BYTES + OFF_TR);
@@ -1113,7 +1255,9 @@ __global__ void __launch_bounds__(128) kg_tr_kernel(const uint8_t* __restrict__ 
   for (int i = 0; i < 8; i++) tr[i] = a[i];
 }
 
+template <class P>
 static int keygen_device(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t n, cudaStream_t st, int slot) {
+  MLDSA_USE(P);
   Ctx& c = ctx();
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -1133,43 +1277,45 @@ static int keygen_device(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t 
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
   static bool attr_set = false;
   if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
-    CB200_CUDA(cudaFuncSetAttribute(kg_eta_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    CB200_CUDA(cudaFuncSetAttribute(kg_eta_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
     attr_set = true;
   }
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
   {
     KernelScope ks(KID_MLDSA_MU, st);
-    kg_seed_kernel<<<blocks(n, 128), 128, 0, st>>>(seeds, n, pk, sk, sseed);
+    kg_seed_kernel<P><<<blocks(n, 128), 128, 0, st>>>(seeds, n, pk, sk, sseed);
   }
   {
     KernelScope ks(KID_MLDSA_MASK, st);
-    kg_eta_kernel<<<blocks(n * (L + K), kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(sseed, n, spoly, sk);
+    kg_eta_kernel<P><<<blocks(n * (L + K), kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(sseed, n, spoly, sk);
   }
   {
     KernelScope ks(KID_MLDSA_EXPAND, st);
-    expand_a_kernel<<<blocks(n * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(pk, PK_BYTES, n, A);
+    expand_a_kernel<P><<<blocks(n * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(pk, PK_BYTES, n, A);
   }
   {
     KernelScope ks(KID_MLDSA_W, st);
-    kg_s1ntt_kernel<<<blocks(n * L, 16), 128, 0, st>>>(spoly, n, s1h, zetas);
+    kg_s1ntt_kernel<P><<<blocks(n * L, 16), 128, 0, st>>>(spoly, n, s1h, zetas);
   }
   {
     KernelScope ks(KID_MLDSA_W, st);
-    kg_t_kernel<<<blocks(n * K, 16), 128, 0, st>>>(A, s1h, spoly, n, pk, sk, zetas);
+    kg_t_kernel<P><<<blocks(n * K, 16), 128, 0, st>>>(A, s1h, spoly, n, pk, sk, zetas);
   }
   {
     KernelScope ks(KID_MLDSA_CHALLENGE, st);
-    kg_tr_kernel<<<blocks(n, 128), 128, 0, st>>>(pk, n, sk);
+    kg_tr_kernel<P><<<blocks(n, 128), 128, 0, st>>>(pk, n, sk);
   }
   CB200_CUDA(cudaGetLastError());
   return 0;
 }
 
 // ------------------------------------------------------------------ host side
+template <class P>
 static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off,
                        const uint8_t* ctxstr, int ctxlen, const uint8_t* rnd, uint8_t* sig, uint8_t* status, size_t n,
                        int internal, cudaStream_t st, int slot, uint64_t* attempts_out) {
+  MLDSA_USE(P);
   Ctx& c = ctx();
   const bool shared = sk_stride == 0;
   const size_t nkeys = shared ? 1 : n;
@@ -1181,7 +1327,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   };
   const size_t oA = take(nkeys * K * L * 1024), oS = take(nkeys * NKEYPOLY * 1024), oMu = take(n * 64),
                oRh = take(n * 64), oY = take(n * L * 1024), oYh = take(n * L * 1024), oW0 = take(n * K * 1024),
-               oW1 = take(n * K * POLY_W1), oZ = take(n * L * POLY_Z), oC = take(n * 1024), oCt = take(n * 48), oHb = take(n * 48 * 4),
+               oW1 = take(n * K * 256), oZ = take(n * L * POLY_Z), oC = take(n * 1024), oCt = take(n * CTILDE), oHb = take(n * 8 * K * 4),
                oFl = take(n * 4), oHc = take(n * 4), oAt = take(n * 4), oA0 = take(n * 4), oA1 = take(n * 4),
                oCnt = take(16);
   void* base = nullptr;
@@ -1196,7 +1342,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   w.y = (uint32_t*)(b + oY);
   w.yh = (uint32_t*)(b + oYh);
   w.w0 = (uint32_t*)(b + oW0);
-  w.w1p = (uint8_t*)(b + oW1);
+  w.w1u = (uint8_t*)(b + oW1);
   w.zbuf = (uint8_t*)(b + oZ);
   w.c = (uint32_t*)(b + oC);
   w.ctilde = (uint64_t*)(b + oCt);
@@ -1211,22 +1357,22 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
 
   static bool attr_set = false;
   if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
     attr_set = true;
   }
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
   {
     KernelScope ks(KID_MLDSA_EXPAND, st);
-    expand_a_kernel<<<blocks(nkeys * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(sk, sk_stride,
+    expand_a_kernel<P><<<blocks(nkeys * K * L, kExpThreads), kExpThreads, kExpThreads * kExpRow * 4, st>>>(sk, sk_stride,
                                                                                                         nkeys, w.A);
   }
   {
     KernelScope ks(KID_MLDSA_EXPAND, st);
-    expand_s_kernel<<<blocks(nkeys * NKEYPOLY, 16), 128, 0, st>>>(sk, sk_stride, nkeys, w.sh, zetas);
+    expand_s_kernel<P><<<blocks(nkeys * NKEYPOLY, 16), 128, 0, st>>>(sk, sk_stride, nkeys, w.sh, zetas);
   }
   {
     KernelScope ks(KID_MLDSA_MU, st);
-    mu_kernel<<<blocks(n, 128), 128, 0, st>>>(sk, sk_stride, msgs, msg_off, ctxstr, ctxlen, internal, rnd, n, w.mu, w.rhop,
+    mu_kernel<P><<<blocks(n, 128), 128, 0, st>>>(sk, sk_stride, msgs, msg_off, ctxstr, ctxlen, internal, rnd, n, w.mu, w.rhop,
                                               w.attempt, w.act[0]);
   }
   CB200_CUDA(cudaGetLastError());
@@ -1245,19 +1391,19 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     CB200_CUDA(cudaMemsetAsync(w.count + (cur ^ 1), 0, 4, st));
     {
       KernelScope ks(KID_MLDSA_MASK, st);
-      mask_kernel<<<blocks(nact * L, 128), 128, 0, st>>>(act, nact, w.rhop, w.attempt, w.y);
+      mask_kernel<P><<<blocks(nact * L, 128), 128, 0, st>>>(act, nact, w.rhop, w.attempt, w.y);
     }
     {
       KernelScope ks(KID_MLDSA_W, st);
-      yntt_kernel<<<blocks(nact * L, 16), 128, 0, st>>>(act, nact, w.y, w.yh, zetas);
+      yntt_kernel<P><<<blocks(nact * L, 16), 128, 0, st>>>(act, nact, w.y, w.yh, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_W, st);
-      w_kernel<<<blocks(nact * K, 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1p, zetas);
+      w_kernel<P><<<blocks(nact * K, 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_CHALLENGE, st);
-      challenge_kernel<<<blocks(nact, 128), 128, 0, st>>>(act, nact, w.mu, w.w1p, w.ctilde, w.c, w.hintbits, w.flags,
+      challenge_kernel<P><<<blocks(nact, 128), 128, 0, st>>>(act, nact, w.mu, w.w1u, w.ctilde, w.c, w.hintbits, w.flags,
                                                           w.hintcnt);
     }
     {
@@ -1266,12 +1412,12 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     }
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
-      response_kernel<<<blocks(nact * (K + L), 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1p,
+      response_kernel<P><<<blocks(nact * (K + L), 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u,
                                                                   w.zbuf, w.hintbits, w.flags, w.hintcnt, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_COMPACT, st);
-      finalize_kernel<<<blocks(nact * 32, 128), 128, 0, st>>>(act, nact, w.ctilde, w.zbuf, w.hintbits, w.flags, w.hintcnt,
+      finalize_kernel<P><<<blocks(nact * 32, 128), 128, 0, st>>>(act, nact, w.ctilde, w.zbuf, w.hintbits, w.flags, w.hintcnt,
                                                               w.attempt, sig, status, w.act[cur ^ 1], w.count + (cur ^ 1));
     }
     CB200_CUDA(cudaMemcpyAsync((void*)h_count, w.count + (cur ^ 1), 4, cudaMemcpyDeviceToHost, st));
@@ -1289,28 +1435,81 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
 
 using namespace cb200;
 
+namespace {
+
+struct ModeSizes {
+  size_t pk, sk, sig;
+};
+bool mode_sizes(int mode, ModeSizes* m) {
+  switch (mode) {
+    case 44: *m = {1312, 2560, 2420}; return true;
+    case 65: *m = {1952, 4032, 3309}; return true;
+    case 87: *m = {2592, 4896, 4627}; return true;
+  }
+  return false;
+}
+
+template <class... A>
+int dispatch_sign(int mode, A... a) {
+  return mode == 44   ? mldsa::sign_device<mldsa::Params<44>>(a...)
+         : mode == 65 ? mldsa::sign_device<mldsa::Params<65>>(a...)
+                      : mldsa::sign_device<mldsa::Params<87>>(a...);
+}
+template <class... A>
+int dispatch_verify(int mode, A... a) {
+  return mode == 44   ? mldsa::verify_device<mldsa::Params<44>>(a...)
+         : mode == 65 ? mldsa::verify_device<mldsa::Params<65>>(a...)
+                      : mldsa::verify_device<mldsa::Params<87>>(a...);
+}
+template <class... A>
+int dispatch_keygen(int mode, A... a) {
+  return mode == 44   ? mldsa::keygen_device<mldsa::Params<44>>(a...)
+         : mode == 65 ? mldsa::keygen_device<mldsa::Params<65>>(a...)
+                      : mldsa::keygen_device<mldsa::Params<87>>(a...);
+}
+
+}  // namespace
+
 extern "C" {
 
-int cb200_mldsa65_sign(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off,
-                       const uint8_t* context, size_t ctxlen, const uint8_t* rnd, uint8_t* sig, uint8_t* status, size_t n,
-                       int flags, uint64_t* attempts) {
+size_t cb200_mldsa_public_key_size(int mode) {
+  ModeSizes m;
+  return mode_sizes(mode, &m) ? m.pk : 0;
+}
+size_t cb200_mldsa_private_key_size(int mode) {
+  ModeSizes m;
+  return mode_sizes(mode, &m) ? m.sk : 0;
+}
+size_t cb200_mldsa_signature_size(int mode) {
+  ModeSizes m;
+  return mode_sizes(mode, &m) ? m.sig : 0;
+}
+
+int cb200_mldsa_sign(int mode, const uint8_t* sk, size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off,
+                     const uint8_t* context, size_t ctxlen, const uint8_t* rnd, uint8_t* sig, uint8_t* status, size_t n,
+                     int flags, uint64_t* attempts) {
   int rc = require_ready();
   if (rc) return rc;
+  ModeSizes ms;
+  if (!mode_sizes(mode, &ms)) {
+    set_error("cb200_mldsa_sign: mode must be 44, 65 or 87, got %d", mode);
+    return CB200_ERR_ARG;
+  }
   if (n == 0) return 0;
-  if (!sk || !msgs || !msg_off || !sig || ctxlen > 255 || (ctxlen && !context) || (sk_stride != 0 && sk_stride < 4032)) {
-    set_error("cb200_mldsa65_sign: bad argument");  // len(ctx) > 255 is sign.ErrContextTooLong in the Go shim
+  if (!sk || !msgs || !msg_off || !sig || ctxlen > 255 || (ctxlen && !context) || (sk_stride != 0 && sk_stride < ms.sk)) {
+    set_error("cb200_mldsa_sign: bad argument");  // len(ctx) > 255 is sign.ErrContextTooLong in the Go shim
     return CB200_ERR_ARG;
   }
   const int internal = flags & CB200_SIGN_INTERNAL;
   const bool dev = is_device_ptr(sig);
   if (dev != is_device_ptr(sk) || dev != is_device_ptr(msgs) || dev != is_device_ptr(msg_off) ||
       (rnd && dev != is_device_ptr(rnd)) || (status && dev != is_device_ptr(status))) {
-    set_error("cb200_mldsa65_sign: mixed host/device pointers");
+    set_error("cb200_mldsa_sign: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
   if (dev) {
     if (((uintptr_t)sk | sk_stride | (uintptr_t)msg_off) & 15) {
-      set_error("cb200_mldsa65_sign: device sk and sk_stride must be 16-byte aligned");
+      set_error("cb200_mldsa_sign: device sk and sk_stride must be 16-byte aligned");
       return CB200_ERR_ARG;
     }
     const uint8_t* dctx = nullptr;
@@ -1318,10 +1517,10 @@ int cb200_mldsa65_sign(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
       CB200_CUDA(cudaMemcpyAsync(ctx().small, context, ctxlen, cudaMemcpyHostToDevice, ctx().cur));
       dctx = (const uint8_t*)ctx().small;
     }
-    return mldsa::sign_device(sk, sk_stride, msgs, msg_off, dctx, (int)ctxlen, rnd, sig, status, n, internal, ctx().cur, 3,
-                              attempts);
+    return dispatch_sign(mode, sk, sk_stride, msgs, msg_off, dctx, (int)ctxlen, rnd, sig, status, n, internal, ctx().cur, 3,
+                         attempts);
   }
-  // host pointers: one staged pass (signing is compute-heavy: ~7.4 KB of traffic per ~1e6 instructions)
+  // host pointers: one staged pass (signing is compute-heavy: ~7 KB of traffic per ~1e6 instructions)
   Ctx& c = ctx();
   std::lock_guard<std::mutex> lock(c.mu);
   cudaStream_t st = c.pipe[0];
@@ -1333,28 +1532,28 @@ int cb200_mldsa65_sign(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     return o;
   };
   const size_t nk = sk_stride ? n : 1;
-  const size_t oSk = take(nk * 4032), oMsg = take(msg_bytes + 8), oOff = take((n + 1) * 8), oRnd = take(n * 32),
-               oSig = take(n * (size_t)3309), oSt = take(n), oCtx = take(256);
+  const size_t oSk = take(nk * ms.sk), oMsg = take(msg_bytes + 8), oOff = take((n + 1) * 8), oRnd = take(n * 32),
+               oSig = take(n * ms.sig), oSt = take(n), oCtx = take(256);
   rc = ensure_scratch(0, off);
   if (rc) return rc;
   char* d = (char*)c.scratch[0];
-  if (sk_stride == 0 || sk_stride == 4032)
-    CB200_CUDA(cudaMemcpyAsync(d + oSk, sk, nk * 4032, cudaMemcpyHostToDevice, st));
+  if (sk_stride == 0 || sk_stride == ms.sk)
+    CB200_CUDA(cudaMemcpyAsync(d + oSk, sk, nk * ms.sk, cudaMemcpyHostToDevice, st));
   else
-    CB200_CUDA(cudaMemcpy2DAsync(d + oSk, 4032, sk, sk_stride, 4032, n, cudaMemcpyHostToDevice, st));
+    CB200_CUDA(cudaMemcpy2DAsync(d + oSk, ms.sk, sk, sk_stride, ms.sk, n, cudaMemcpyHostToDevice, st));
   if (msg_bytes) CB200_CUDA(cudaMemcpyAsync(d + oMsg, msgs, msg_bytes, cudaMemcpyHostToDevice, st));
   CB200_CUDA(cudaMemcpyAsync(d + oOff, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
   if (rnd) CB200_CUDA(cudaMemcpyAsync(d + oRnd, rnd, n * 32, cudaMemcpyHostToDevice, st));
   if (ctxlen) CB200_CUDA(cudaMemcpyAsync(d + oCtx, context, ctxlen, cudaMemcpyHostToDevice, st));
-  rc = mldsa::sign_device((const uint8_t*)d + oSk, sk_stride ? 4032 : 0, (const uint8_t*)d + oMsg,
-                          (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : nullptr, (int)ctxlen,
-                          rnd ? (const uint8_t*)d + oRnd : nullptr, (uint8_t*)d + oSig, (uint8_t*)d + oSt, n, internal,
-                          st, 0, attempts);
+  rc = dispatch_sign(mode, (const uint8_t*)d + oSk, sk_stride ? ms.sk : (size_t)0, (const uint8_t*)d + oMsg,
+                     (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : (const uint8_t*)nullptr, (int)ctxlen,
+                     rnd ? (const uint8_t*)d + oRnd : (const uint8_t*)nullptr, (uint8_t*)d + oSig, (uint8_t*)d + oSt, n,
+                     internal, st, 0, attempts);
   if (rc) return rc;
   void* pin = nullptr;
   rc = ensure_pinned(n + 64, &pin);
   if (rc) return rc;
-  CB200_CUDA(cudaMemcpyAsync(sig, d + oSig, n * (size_t)3309, cudaMemcpyDeviceToHost, st));
+  CB200_CUDA(cudaMemcpyAsync(sig, d + oSig, n * ms.sig, cudaMemcpyDeviceToHost, st));
   CB200_CUDA(cudaMemcpyAsync(pin, d + oSt, n, cudaMemcpyDeviceToHost, st));
   CB200_CUDA(cudaStreamSynchronize(st));
   size_t nbad = 0;
@@ -1362,31 +1561,36 @@ int cb200_mldsa65_sign(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   for (size_t i = 0; i < n; i++) nbad += hs[i] != 0;
   if (status) memcpy(status, hs, n);
   if (nbad) {
-    set_error("cb200_mldsa65_sign: %zu of %zu signatures exhausted 576 attempts", nbad, n);
+    set_error("cb200_mldsa_sign: %zu of %zu signatures exhausted 576 attempts", nbad, n);
     return CB200_ERR_SIGN_ATTEMPTS;
   }
   return 0;
 }
 
-int cb200_mldsa65_verify(const uint8_t* pk, size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off,
-                         const uint8_t* context, size_t ctxlen, const uint8_t* sig, uint8_t* ok, size_t n, int flags) {
+int cb200_mldsa_verify(int mode, const uint8_t* pk, size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off,
+                       const uint8_t* context, size_t ctxlen, const uint8_t* sig, uint8_t* ok, size_t n, int flags) {
   int rc = require_ready();
   if (rc) return rc;
+  ModeSizes ms;
+  if (!mode_sizes(mode, &ms)) {
+    set_error("cb200_mldsa_verify: mode must be 44, 65 or 87, got %d", mode);
+    return CB200_ERR_ARG;
+  }
   if (n == 0) return 0;
   if (!pk || !msgs || !msg_off || !sig || !ok || ctxlen > 255 || (ctxlen && !context) ||
-      (pk_stride != 0 && pk_stride < 1952)) {
-    set_error("cb200_mldsa65_verify: bad argument");
+      (pk_stride != 0 && pk_stride < ms.pk)) {
+    set_error("cb200_mldsa_verify: bad argument");
     return CB200_ERR_ARG;
   }
   const int internal = flags & CB200_SIGN_INTERNAL;
   const bool dev = is_device_ptr(ok);
   if (dev != is_device_ptr(pk) || dev != is_device_ptr(msgs) || dev != is_device_ptr(msg_off) || dev != is_device_ptr(sig)) {
-    set_error("cb200_mldsa65_verify: mixed host/device pointers");
+    set_error("cb200_mldsa_verify: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
   if (dev) {
     if (((uintptr_t)pk | pk_stride | (uintptr_t)msg_off) & 15) {
-      set_error("cb200_mldsa65_verify: device pk and pk_stride must be 16-byte aligned");
+      set_error("cb200_mldsa_verify: device pk and pk_stride must be 16-byte aligned");
       return CB200_ERR_ARG;
     }
     const uint8_t* dctx = nullptr;
@@ -1394,7 +1598,7 @@ int cb200_mldsa65_verify(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
       CB200_CUDA(cudaMemcpyAsync(ctx().small, context, ctxlen, cudaMemcpyHostToDevice, ctx().cur));
       dctx = (const uint8_t*)ctx().small;
     }
-    return mldsa::verify_device(pk, pk_stride, msgs, msg_off, dctx, (int)ctxlen, sig, ok, n, internal, ctx().cur, 3);
+    return dispatch_verify(mode, pk, pk_stride, msgs, msg_off, dctx, (int)ctxlen, sig, ok, n, internal, ctx().cur, 3);
   }
   Ctx& c = ctx();
   std::lock_guard<std::mutex> lock(c.mu);
@@ -1407,57 +1611,75 @@ int cb200_mldsa65_verify(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
     return o;
   };
   const size_t nk = pk_stride ? n : 1;
-  const size_t oPk = take(nk * 1952), oMsg = take(msg_bytes + 8), oOff = take((n + 1) * 8), oSig = take(n * (size_t)3309),
+  const size_t oPk = take(nk * ms.pk), oMsg = take(msg_bytes + 8), oOff = take((n + 1) * 8), oSig = take(n * ms.sig),
                oOk = take(n), oCtx = take(256);
   rc = ensure_scratch(0, off);
   if (rc) return rc;
   char* d = (char*)c.scratch[0];
-  if (pk_stride == 0 || pk_stride == 1952)
-    CB200_CUDA(cudaMemcpyAsync(d + oPk, pk, nk * 1952, cudaMemcpyHostToDevice, st));
+  if (pk_stride == 0 || pk_stride == ms.pk)
+    CB200_CUDA(cudaMemcpyAsync(d + oPk, pk, nk * ms.pk, cudaMemcpyHostToDevice, st));
   else
-    CB200_CUDA(cudaMemcpy2DAsync(d + oPk, 1952, pk, pk_stride, 1952, n, cudaMemcpyHostToDevice, st));
+    CB200_CUDA(cudaMemcpy2DAsync(d + oPk, ms.pk, pk, pk_stride, ms.pk, n, cudaMemcpyHostToDevice, st));
   if (msg_bytes) CB200_CUDA(cudaMemcpyAsync(d + oMsg, msgs, msg_bytes, cudaMemcpyHostToDevice, st));
   CB200_CUDA(cudaMemcpyAsync(d + oOff, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CB200_CUDA(cudaMemcpyAsync(d + oSig, sig, n * (size_t)3309, cudaMemcpyHostToDevice, st));
+  CB200_CUDA(cudaMemcpyAsync(d + oSig, sig, n * ms.sig, cudaMemcpyHostToDevice, st));
   if (ctxlen) CB200_CUDA(cudaMemcpyAsync(d + oCtx, context, ctxlen, cudaMemcpyHostToDevice, st));
-  rc = mldsa::verify_device((const uint8_t*)d + oPk, pk_stride ? 1952 : 0, (const uint8_t*)d + oMsg,
-                            (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : nullptr, (int)ctxlen,
-                            (const uint8_t*)d + oSig, (uint8_t*)d + oOk, n, internal, st, 0);
+  rc = dispatch_verify(mode, (const uint8_t*)d + oPk, pk_stride ? ms.pk : (size_t)0, (const uint8_t*)d + oMsg,
+                       (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : (const uint8_t*)nullptr,
+                       (int)ctxlen, (const uint8_t*)d + oSig, (uint8_t*)d + oOk, n, internal, st, 0);
   if (rc) return rc;
   CB200_CUDA(cudaMemcpyAsync(ok, d + oOk, n, cudaMemcpyDeviceToHost, st));
   CB200_CUDA(cudaStreamSynchronize(st));
   return 0;
 }
 
-int cb200_mldsa65_keygen(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t n) {
+int cb200_mldsa_keygen(int mode, const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t n) {
   int rc = require_ready();
   if (rc) return rc;
+  ModeSizes ms;
+  if (!mode_sizes(mode, &ms)) {
+    set_error("cb200_mldsa_keygen: mode must be 44, 65 or 87, got %d", mode);
+    return CB200_ERR_ARG;
+  }
   if (n == 0) return 0;
   if (!seeds || !pk || !sk) {
-    set_error("cb200_mldsa65_keygen: null pointer");
+    set_error("cb200_mldsa_keygen: null pointer");
     return CB200_ERR_ARG;
   }
   const bool dev = is_device_ptr(pk);
   if (dev != is_device_ptr(seeds) || dev != is_device_ptr(sk)) {
-    set_error("cb200_mldsa65_keygen: mixed host/device pointers");
+    set_error("cb200_mldsa_keygen: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
   if (dev) {
     if (((uintptr_t)seeds | (uintptr_t)pk | (uintptr_t)sk) & 15) {
-      set_error("cb200_mldsa65_keygen: device buffers must be 16-byte aligned");
+      set_error("cb200_mldsa_keygen: device buffers must be 16-byte aligned");
       return CB200_ERR_ARG;
     }
-    return mldsa::keygen_device(seeds, pk, sk, n, ctx().cur, 3);
+    return dispatch_keygen(mode, seeds, pk, sk, n, ctx().cur, 3);
   }
   std::vector<Buf> bufs(3);
   bufs[0] = Buf{seeds, nullptr, 32, false, 0};
-  bufs[1] = Buf{nullptr, pk, 1952, false, 0};
-  bufs[2] = Buf{nullptr, sk, 4032, false, 0};
-  return run_staged(bufs, n, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
-    return mldsa::keygen_device((const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
+  bufs[1] = Buf{nullptr, pk, ms.pk, false, 0};
+  bufs[2] = Buf{nullptr, sk, ms.sk, false, 0};
+  return run_staged(bufs, n, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) -> int {
+    return dispatch_keygen(mode, (const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
   });
 }
 
+/* ML-DSA-65 entry points under their original names */
+int cb200_mldsa65_sign(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off,
+                       const uint8_t* context, size_t ctxlen, const uint8_t* rnd, uint8_t* sig, uint8_t* status, size_t n,
+                       int flags, uint64_t* attempts) {
+  return cb200_mldsa_sign(65, sk, sk_stride, msgs, msg_off, context, ctxlen, rnd, sig, status, n, flags, attempts);
+}
+int cb200_mldsa65_verify(const uint8_t* pk, size_t pk_stride, const uint8_t* msgs, const uint64_t* msg_off,
+                         const uint8_t* context, size_t ctxlen, const uint8_t* sig, uint8_t* ok, size_t n, int flags) {
+  return cb200_mldsa_verify(65, pk, pk_stride, msgs, msg_off, context, ctxlen, sig, ok, n, flags);
+}
+int cb200_mldsa65_keygen(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t n) {
+  return cb200_mldsa_keygen(65, seeds, pk, sk, n);
+}
 size_t cb200_mldsa65_signature_size(void) { return 3309; }
 size_t cb200_mldsa65_public_key_size(void) { return 1952; }
 size_t cb200_mldsa65_private_key_size(void) { return 4032; }

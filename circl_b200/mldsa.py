@@ -1,4 +1,4 @@
-"""sign.Scheme mirror for ML-DSA-65 over the C ABI.
+"""sign.Scheme mirror for ML-DSA-44 / ML-DSA-65 / ML-DSA-87 over the C ABI.
 
 Mirrors sign/sign.go:48-119 (sign.Scheme, SignatureOpts, errors) and
 sign/mldsa/mldsa65/dilithium.go:256-366 for the path this repository accelerates
@@ -68,17 +68,22 @@ class PrivateKey:
 
 
 class Scheme:
+    """sign.Scheme for one parameter set (mode 44, 65 or 87; sign/dilithium/gen.go:80-162)."""
+
+    def __init__(self, name: str = "ML-DSA-65", mode: int = 65):
+        self._name, self._mode = name, mode
+
     def Name(self) -> str:
-        return "ML-DSA-65"
+        return self._name
 
     def PublicKeySize(self) -> int:
-        return 1952
+        return {44: 1312, 65: 1952, 87: 2592}[self._mode]
 
     def PrivateKeySize(self) -> int:
-        return 4032
+        return {44: 2560, 65: 4032, 87: 4896}[self._mode]
 
     def SignatureSize(self) -> int:
-        return 3309
+        return {44: 2420, 65: 3309, 87: 4627}[self._mode]
 
     def SeedSize(self) -> int:
         return 32
@@ -113,15 +118,15 @@ class Scheme:
             stride = 0
         else:
             sk = np.ascontiguousarray(sks, dtype=np.uint8)
-            if sk.shape != (n, 4032):
+            if sk.shape != (n, self.PrivateKeySize()):
                 raise ErrPrivKeySize("sign: invalid private key size")
-            stride = 4032
-        sig = np.empty((n, 3309), dtype=np.uint8)
+            stride = self.PrivateKeySize()
+        sig = np.empty((n, self.SignatureSize()), dtype=np.uint8)
         status = np.zeros((n,), dtype=np.uint8)
         attempts = C.c_uint64(0)
         r = None if rnd is None else np.ascontiguousarray(rnd, dtype=np.uint8)
         cbuf = (C.c_uint8 * max(1, len(ctx))).from_buffer_copy(ctx or b"\0")
-        check(lib().cb200_mldsa65_sign(sk.ctypes.data, stride, blob.ctypes.data, off.ctypes.data,
+        check(lib().cb200_mldsa_sign(self._mode, sk.ctypes.data, stride, blob.ctypes.data, off.ctypes.data,
                                        C.cast(cbuf, C.c_void_p), len(ctx), None if r is None else r.ctypes.data,
                                        sig.ctypes.data, status.ctypes.data, n, SIGN_INTERNAL if internal else 0,
                                        C.cast(C.pointer(attempts), C.c_void_p)))
@@ -146,9 +151,9 @@ class Scheme:
         if seeds.ndim != 2 or seeds.shape[1] != 32:
             raise ValueError("sign: invalid seed size")
         n = seeds.shape[0]
-        pk = np.empty((n, 1952), dtype=np.uint8)
-        sk = np.empty((n, 4032), dtype=np.uint8)
-        check(lib().cb200_mldsa65_keygen(seeds.ctypes.data, pk.ctypes.data, sk.ctypes.data, n))
+        pk = np.empty((n, self.PublicKeySize()), dtype=np.uint8)
+        sk = np.empty((n, self.PrivateKeySize()), dtype=np.uint8)
+        check(lib().cb200_mldsa_keygen(self._mode, seeds.ctypes.data, pk.ctypes.data, sk.ctypes.data, n))
         return pk, sk
 
     def UnmarshalBinaryPublicKey(self, buf: bytes) -> PublicKey:
@@ -176,22 +181,26 @@ class Scheme:
             stride = 0
         else:
             pk = np.ascontiguousarray(pks, dtype=np.uint8)
-            if pk.shape != (n, 1952):
+            if pk.shape != (n, self.PublicKeySize()):
                 raise ErrPubKeySize("sign: invalid public key size")
-            stride = 1952
+            stride = self.PublicKeySize()
         sigs = np.ascontiguousarray(sigs, dtype=np.uint8)
-        assert sigs.shape == (n, 3309)
+        assert sigs.shape == (n, self.SignatureSize())
         ok = np.zeros((n,), dtype=np.uint8)
         cbuf = (C.c_uint8 * max(1, len(ctx))).from_buffer_copy(ctx or b"\0")
-        check(lib().cb200_mldsa65_verify(pk.ctypes.data, stride, blob.ctypes.data, off.ctypes.data,
+        check(lib().cb200_mldsa_verify(self._mode, pk.ctypes.data, stride, blob.ctypes.data, off.ctypes.data,
                                          C.cast(cbuf, C.c_void_p), len(ctx), sigs.ctypes.data, ok.ctypes.data, n,
                                          SIGN_INTERNAL if internal else 0))
         return ok.astype(bool)
 
 
-_SCHEME = Scheme()
+_SCHEMES = {"ml-dsa-44": Scheme("ML-DSA-44", 44), "ml-dsa-65": Scheme("ML-DSA-65", 65), "ml-dsa-87": Scheme("ML-DSA-87", 87)}
 
 
 def ByName(name: str):
-    """sign/schemes/schemes.go:69 -- case-insensitive lookup."""
-    return _SCHEME if name.lower() == "ml-dsa-65" else None
+    """sign/schemes/schemes.go:69 -- case-insensitive lookup; None if unknown."""
+    return _SCHEMES.get(name.lower())
+
+
+def All():
+    return list(_SCHEMES.values())

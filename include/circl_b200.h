@@ -119,6 +119,21 @@ size_t cb200_mlkem_private_key_size(int k);
 size_t cb200_mlkem_public_key_size(int k);
 size_t cb200_mlkem_ciphertext_size(int k);
 
+#define CB200_SIGN_INTERNAL 1 /* flags: ML-DSA.Sign_internal / Verify_internal on the message as given */
+
+/* ---- ML-DSA (mode = 44, 65 or 87; sign/dilithium/gen.go:80-162) ----
+ * Same contracts as the ML-DSA-65 entry points documented below, with the parameter set as first argument:
+ * sk 2560 / 4032 / 4896, pk 1312 / 1952 / 2592, sig 2420 / 3309 / 4627 bytes. */
+int cb200_mldsa_sign(int mode, const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *msg_off,
+                     const uint8_t *context, size_t ctxlen, const uint8_t *rnd, uint8_t *sig, uint8_t *status, size_t n,
+                     int flags, uint64_t *attempts);
+int cb200_mldsa_verify(int mode, const uint8_t *pk, size_t pk_stride, const uint8_t *msgs, const uint64_t *msg_off,
+                       const uint8_t *context, size_t ctxlen, const uint8_t *sig, uint8_t *ok, size_t n, int flags);
+int cb200_mldsa_keygen(int mode, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, size_t n);
+size_t cb200_mldsa_public_key_size(int mode);
+size_t cb200_mldsa_private_key_size(int mode);
+size_t cb200_mldsa_signature_size(int mode);
+
 /* ---- ML-DSA-65 ---- */
 /* sign.Scheme.Sign / SignTo    sign/mldsa/mldsa65/dilithium.go:282-303,56-84  ->
  * internal.SignTo (ML-DSA.Sign_internal)  sign/mldsa/mldsa65/internal/dilithium.go:340-470,
@@ -132,7 +147,6 @@ size_t cb200_mlkem_ciphertext_size(int k);
  * panics there); attempts (optional, host pointer): total rejection-loop iterations of the batch.
  * flags: CB200_SIGN_INTERNAL = ML-DSA.Sign_internal on the message as given (no 0x00||len||ctx framing,
  * the ACVP interface, sign/mldsa/mldsa65/dilithium.go:87-98). */
-#define CB200_SIGN_INTERNAL 1
 int cb200_mldsa65_sign(const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *msg_off,
                        const uint8_t *context, size_t ctxlen, const uint8_t *rnd, uint8_t *sig, uint8_t *status,
                        size_t n, int flags, uint64_t *attempts);

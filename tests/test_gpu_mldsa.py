@@ -159,3 +159,58 @@ def test_keygen_sign_verify_all_on_gpu(cb):
     assert not scheme.VerifyBatch(pk, msgs[1:] + msgs[:1], sig).any()
     p1, s1 = scheme.DeriveKey(seeds[0].tobytes())
     assert p1.MarshalBinary() == pk[0].tobytes() and scheme.Verify(p1, b"m", scheme.Sign(s1, b"m"))
+
+
+# ---------------------------------------------------------------- ML-DSA-44 / ML-DSA-87
+OTHER = {"ML-DSA-44": 44, "ML-DSA-87": 87}
+
+
+@pytest.mark.parametrize("ps", list(OTHER))
+def test_other_modes_acvp(cb, mldsa_other_acvp, ps):
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName(ps)
+    g = mldsa_other_acvp[ps]
+    seeds = np.stack([np.frombuffer(bytes.fromhex(t["seed"]), dtype=np.uint8) for t in g["keygen"]])
+    pk, sk = scheme.DeriveKeyBatch(seeds)
+    for i, t in enumerate(g["keygen"]):
+        assert pk[i].tobytes().hex().upper() == t["pk"].upper() and sk[i].tobytes().hex().upper() == t["sk"].upper()
+    tests = g["siggen"]
+    sks = np.stack([np.frombuffer(bytes.fromhex(t["sk"]), dtype=np.uint8) for t in tests])
+    rnd = np.stack([np.frombuffer(bytes.fromhex(t["rnd"]), dtype=np.uint8) for t in tests])
+    sig = scheme.SignBatch(sks, [bytes.fromhex(t["message"]) for t in tests], rnd=rnd, internal=True)
+    for i, t in enumerate(tests):
+        assert sig[i].tobytes().hex().upper() == t["signature"].upper(), t["tcId"]
+    v = g["sigver"]
+    ok = scheme.VerifyBatch(scheme.UnmarshalBinaryPublicKey(bytes.fromhex(v["pk"])),
+                            [bytes.fromhex(t["message"]) for t in v["tests"]],
+                            np.stack([np.frombuffer(bytes.fromhex(t["signature"]), dtype=np.uint8) for t in v["tests"]]),
+                            internal=True)
+    assert ok.tolist() == [t["testPassed"] for t in v["tests"]]
+
+
+@pytest.mark.parametrize("ps", list(OTHER))
+def test_other_modes_vs_oracle_and_roundtrip(cb, ps):
+    import oracle
+    from circl_b200 import mldsa
+    mode = OTHER[ps]
+    scheme = mldsa.ByName(ps)
+    n = 500
+    seeds = np.frombuffer(hashlib.shake_256(ps.encode()).digest(32 * n), dtype=np.uint8).reshape(n, 32)
+    pk, sk = scheme.DeriveKeyBatch(seeds)
+    for i in range(0, n, 101):
+        wpk, wsk = oracle.mldsa_keygen(mode, seeds[i].tobytes())
+        assert pk[i].tobytes() == wpk and sk[i].tobytes() == wsk
+    msgs = [_h(8, i, 10 + i % 120) for i in range(n)]
+    sig, attempts = scheme.SignBatch(sk, msgs, ctx=b"c", return_attempts=True)
+    for i in range(0, n, 37):
+        want, _ = oracle.mldsa_sign(mode, sk[i].tobytes(), msgs[i], ctx=b"c")
+        assert sig[i].tobytes() == want
+    want_all, want_attempts = oracle.mldsa_sign_batch(mode, sk[:64], msgs[:64], nthreads=8)
+    sig64, att64 = scheme.SignBatch(sk[:64], msgs[:64], return_attempts=True)
+    assert np.array_equal(sig64, want_all) and att64 == want_attempts
+    assert scheme.VerifyBatch(pk, msgs, sig, ctx=b"c").all()
+    bad = sig.copy()
+    bad[:, 70] ^= 2
+    got = scheme.VerifyBatch(pk, msgs, bad, ctx=b"c")
+    assert got[:20].tolist() == [oracle.mldsa_verify(mode, pk[i].tobytes(), msgs[i], bad[i].tobytes(), ctx=b"c") for i in range(20)]
+    assert not got.any()

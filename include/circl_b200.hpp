@@ -221,19 +221,20 @@ class PrivateKey {
   Bytes packed_;
 };
 
-class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-65
+class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-44 / ML-DSA-65 / ML-DSA-87
  public:
-  std::string Name() const { return "ML-DSA-65"; }
-  size_t PublicKeySize() const { return cb200_mldsa65_public_key_size(); }
-  size_t PrivateKeySize() const { return cb200_mldsa65_private_key_size(); }
-  size_t SignatureSize() const { return cb200_mldsa65_signature_size(); }
+  Scheme(std::string name, int mode) : name_(std::move(name)), mode_(mode) {}
+  const std::string& Name() const { return name_; }
+  size_t PublicKeySize() const { return cb200_mldsa_public_key_size(mode_); }
+  size_t PrivateKeySize() const { return cb200_mldsa_private_key_size(mode_); }
+  size_t SignatureSize() const { return cb200_mldsa_signature_size(mode_); }
   size_t SeedSize() const { return 32; }
   bool SupportsContext() const { return true; }
 
   std::pair<PublicKey, PrivateKey> DeriveKey(const Bytes& seed) const {  // dilithium.go:266-276
     if (seed.size() != SeedSize()) throw std::logic_error("sign: invalid seed size");  // Go panics here
     Bytes pk(PublicKeySize()), sk(PrivateKeySize());
-    check(cb200_mldsa65_keygen(seed.data(), pk.data(), sk.data(), 1));
+    check(cb200_mldsa_keygen(mode_, seed.data(), pk.data(), sk.data(), 1));
     return {PublicKey(this, std::move(pk)), PrivateKey(this, std::move(sk))};
   }
   std::pair<PublicKey, PrivateKey> GenerateKey() const {
@@ -257,7 +258,7 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-65
     const uint64_t off[2] = {0, msg.size()};
     Bytes padded(msg);
     padded.resize(msg.size() + 8);
-    check(cb200_mldsa65_sign(sk.MarshalBinary().data(), 0, padded.data(), off, (const uint8_t*)ctx.data(), ctx.size(), nullptr,
+    check(cb200_mldsa_sign(mode_, sk.MarshalBinary().data(), 0, padded.data(), off, (const uint8_t*)ctx.data(), ctx.size(), nullptr,
                              sig.data(), nullptr, 1, 0, nullptr));
     return sig;
   }
@@ -268,7 +269,7 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-65
     const uint64_t off[2] = {0, msg.size()};
     Bytes padded(msg);
     padded.resize(msg.size() + 8);
-    check(cb200_mldsa65_verify(pk.MarshalBinary().data(), 0, padded.data(), off, (const uint8_t*)ctx.data(), ctx.size(),
+    check(cb200_mldsa_verify(mode_, pk.MarshalBinary().data(), 0, padded.data(), off, (const uint8_t*)ctx.data(), ctx.size(),
                                sig.data(), &ok, 1, 0));
     return ok != 0;
   }
@@ -281,7 +282,7 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-65
     sigs.resize(n * SignatureSize());
     Bytes padded(msgs);
     padded.resize(msgs.size() + 8);
-    check(cb200_mldsa65_sign(sks.data(), shared ? 0 : PrivateKeySize(), padded.data(), off.data(), (const uint8_t*)ctx.data(),
+    check(cb200_mldsa_sign(mode_, sks.data(), shared ? 0 : PrivateKeySize(), padded.data(), off.data(), (const uint8_t*)ctx.data(),
                              ctx.size(), nullptr, sigs.data(), nullptr, n, 0, nullptr));
   }
 
@@ -291,11 +292,19 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-65
     if (rc == CB200_ERR_ARG) throw std::logic_error(cb200_last_error());
     throw Error(cb200_last_error());  // includes CB200_ERR_SIGN_ATTEMPTS (the reference panics after 576 attempts)
   }
+  std::string name_;
+  int mode_;
 };
 
-inline const Scheme* ByName(const std::string& name) {  // sign/schemes/schemes.go:69
-  static const Scheme mldsa65;
-  return kem::lower(name) == "ml-dsa-65" ? &mldsa65 : nullptr;
+inline const std::vector<const Scheme*>& All() {
+  static const Scheme s44("ML-DSA-44", 44), s65("ML-DSA-65", 65), s87("ML-DSA-87", 87);
+  static const std::vector<const Scheme*> all = {&s44, &s65, &s87};
+  return all;
+}
+inline const Scheme* ByName(const std::string& name) {  // sign/schemes/schemes.go:69 (nullptr = no such scheme)
+  for (const Scheme* s : All())
+    if (kem::lower(s->Name()) == kem::lower(name)) return s;
+  return nullptr;
 }
 
 }  // namespace sign

@@ -88,6 +88,14 @@ int main() {
   sign::SignatureOpts longctx{std::string(256, 'x')};
   try { d->Sign(dk.second, msg, &longctx); } catch (const sign::ErrContextTooLong&) { threw = true; }
   REQUIRE(threw);
+  for (const char* other : {"ML-DSA-44", "ml-dsa-87"}) {  // the other parameter sets: sign/verify round trip
+    const sign::Scheme* o = sign::ByName(other);
+    REQUIRE(o != nullptr);
+    auto ok2 = o->DeriveKey(dseed);
+    Bytes s2 = o->Sign(ok2.second, msg);
+    REQUIRE(s2.size() == o->SignatureSize() && o->Verify(ok2.first, msg, s2));
+  }
+  REQUIRE(sign::ByName("ML-DSA-99") == nullptr);
   printf("scheme=%s\n", d->Name().c_str());
   hex("pk", dk.first.MarshalBinary());
   hex("sk", dk.second.MarshalBinary());

@@ -751,7 +751,7 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
 template <int K>
 __global__ void __launch_bounds__(128) keygen_seed_kernel(const uint8_t* __restrict__ seed, size_t n,
                                                           uint64_t* __restrict__ rs, uint8_t* __restrict__ ek,
-                                                          uint8_t* __restrict__ dk) {
+                                                          uint8_t* __restrict__ dk, int mlkem) {
   using P = Params<K>;
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
@@ -760,8 +760,8 @@ __global__ void __launch_bounds__(128) keygen_seed_kernel(const uint8_t* __restr
   keccak::zero(a);
 #pragma unroll
   for (int j = 0; j < 4; j++) a[j] = sd[j];
-  a[4] = (uint64_t)K | (0x06ull << 8);
-  a[8] = 0x8000000000000000ull;  // SHA3-512, rate 72
+  a[4] = mlkem ? ((uint64_t)K | (0x06ull << 8)) : 0x06ull;  // round-3 Kyber hashes the bare 32-byte seed
+  a[8] = 0x8000000000000000ull;                               // SHA3-512, rate 72
   keccak::f1600(a);
   uint64_t* ekr = reinterpret_cast<uint64_t*>(ek + i * P::ek_bytes + 384 * K);
   uint64_t* dkr = reinterpret_cast<uint64_t*>(dk + i * (768 * K + 96) + 384 * K + 384 * K);
@@ -875,7 +875,8 @@ __global__ void __launch_bounds__(kEncThreads) keygen_kernel(const int16_t* __re
 }
 
 template <int K>
-static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n, cudaStream_t st, int slot) {
+static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n, cudaStream_t st, int slot,
+                         int mlkem = 1) {
   using P = Params<K>;
   Ctx& c = ctx();
   const size_t sub = n < kSub ? n : kSub;
@@ -905,7 +906,7 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
   }
   {
     KernelScope ks(KID_MLKEM_G, st);
-    keygen_seed_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, n, rs, ek, dk);
+    keygen_seed_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, n, rs, ek, dk, mlkem);
   }
   CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
   for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][q], c.ev_fork[slot], 0));
@@ -936,6 +937,179 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
     hash_ek_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ek, P::ek_bytes, n, h);
   }
   CB200_CUDA(cudaMemcpy2DAsync(dk + 384 * K + P::ek_bytes, dksz, h, 32, 32, n, cudaMemcpyDeviceToDevice, st));
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
+// ------------------------------------------------------------------ 6. round-3 Kyber KEM
+// kem/kyber/kyber768/kyber.go:98-198: same K-PKE; m = H(seed) ("hash of shame"), ss = KDF(K || H(ct)),
+// implicit rejection replaces K by z.  Thread per op.
+__global__ void __launch_bounds__(128) r3_m_kernel(const uint8_t* __restrict__ seeds, size_t n, uint8_t* __restrict__ m) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int j = 0; j < 4; j++) a[j] = reinterpret_cast<const uint64_t*>(seeds + 32 * i)[j];
+  a[4] = 0x06;
+  a[16] = 0x8000000000000000ull;  // SHA3-256, rate 136
+  keccak::f1600(a);
+#pragma unroll
+  for (int j = 0; j < 4; j++) reinterpret_cast<uint64_t*>(m + 32 * i)[j] = a[j];
+}
+
+// ss = SHAKE256(Kbar' || SHA3-256(ct), 32) with Kbar' = Kbar, or z when ct2 is given and differs from ct
+template <int K>
+__global__ void __launch_bounds__(128) r3_kdf_kernel(const uint8_t* __restrict__ ct, const uint8_t* __restrict__ ct2,
+                                                     const uint8_t* __restrict__ kbar, const uint8_t* __restrict__ z,
+                                                     size_t z_stride, size_t n, uint8_t* __restrict__ ss) {
+  using P = Params<K>;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t* c1 = reinterpret_cast<const uint64_t*>(ct + i * P::ct_bytes);
+  const uint64_t* c2 = ct2 ? reinterpret_cast<const uint64_t*>(ct2 + i * P::ct_bytes) : nullptr;
+  constexpr int words = P::ct_bytes / 8, full = words / 17, rem = words % 17;
+  uint64_t a[25];
+  keccak::zero(a);
+  uint64_t diff = 0;
+#pragma unroll 1
+  for (int b = 0; b < full; b++) {
+#pragma unroll
+    for (int w = 0; w < 17; w++) {
+      const uint64_t x = c1[17 * b + w];
+      if (c2) diff |= x ^ c2[17 * b + w];
+      a[w] ^= x;
+    }
+    keccak::f1600(a);
+  }
+#pragma unroll
+  for (int w = 0; w < rem; w++) {
+    const uint64_t x = c1[17 * full + w];
+    if (c2) diff |= x ^ c2[17 * full + w];
+    a[w] ^= x;
+  }
+  a[rem] ^= 0x06;
+  a[16] ^= 0x8000000000000000ull;
+  keccak::f1600(a);
+  uint64_t hc[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) hc[j] = a[j];
+  const uint64_t* kb = (diff != 0) ? reinterpret_cast<const uint64_t*>(z + i * z_stride)
+                                   : reinterpret_cast<const uint64_t*>(kbar + 32 * i);
+  keccak::zero(a);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    a[j] = kb[j];
+    a[4 + j] = hc[j];
+  }
+  a[8] = 0x1f;
+  a[16] = 0x8000000000000000ull;  // SHAKE256
+  keccak::f1600(a);
+#pragma unroll
+  for (int j = 0; j < 4; j++) reinterpret_cast<uint64_t*>(ss + 32 * i)[j] = a[j];
+}
+
+// shared tail of round-3 encaps / decaps: (Kbar, r) = G(m || h), ct = Enc(ek, m, r) with the lenient key parse
+template <int K>
+static int r3_encrypt(const uint8_t* ek, size_t ek_stride, const uint8_t* h, size_t h_stride, const uint8_t* m, uint8_t* ct,
+                      uint8_t* kbar, uint64_t* r, char* base, const size_t (&o_A)[2], const size_t (&o_n)[2], size_t n,
+                      cudaStream_t st, int slot) {
+  using P = Params<K>;
+  Ctx& c = ctx();
+  const size_t sub = n < kSub ? n : kSub;
+  {
+    KernelScope ks(KID_MLKEM_G, st);
+    g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m, h, h_stride, n, kbar, r);
+  }
+  CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
+  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][q], c.ev_fork[slot], 0));
+  int l = 0;
+  for (size_t first = 0; first < n; first += sub, l ^= 1) {
+    cudaStream_t ls = c.profiling ? st : c.lane[slot][l];
+    int16_t* A = (int16_t*)(base + o_A[l]);
+    int16_t* noise = (int16_t*)(base + o_n[l]);
+    const size_t cnt = (n - first < sub) ? n - first : sub;
+    const size_t mat_blocks = (cnt * K * K + 127) / 128, noise_blocks = (cnt * P::n_noise + 127) / 128;
+    {
+      KernelScope ks(KID_MLKEM_SAMPLE, ls);
+      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
+          ek + 384 * K + first * ek_stride, ek_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks, 1, P::n_noise, 4, K);
+    }
+    {
+      KernelScope ks(KID_MLKEM_ENCRYPT, ls);
+      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
+          ek + first * ek_stride, ek_stride, A, 0, noise, m + 32 * first, cnt, ct + first * P::ct_bytes, nullptr, nullptr,
+          (const kyber::TwPair*)c.kyber_tw, 1);
+    }
+  }
+  for (int q = 0; q < 2; q++) {
+    CB200_CUDA(cudaEventRecord(c.ev_join[slot][q], c.lane[slot][q]));
+    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_join[slot][q], 0));
+  }
+  return 0;
+}
+
+// mode 0: encaps (in = seeds, key = ek), mode 1: decaps (in = ct, key = dk); per-op keys
+template <int K>
+static int r3_device(int decaps, const uint8_t* key, size_t key_stride, const uint8_t* in, uint8_t* ct_out, uint8_t* ss, size_t n,
+                     cudaStream_t st, int slot) {
+  using P = Params<K>;
+  Ctx& c = ctx();
+  const size_t sub = n < kSub ? n : kSub;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    size_t o = off;
+    off += (bytes + 255) & ~(size_t)255;
+    return o;
+  };
+  const size_t o_h = take(n * 32), o_r = take(n * 32), o_m = take(n * 32), o_k = take(n * 32),
+               o_ct2 = take(decaps ? n * (size_t)P::ct_bytes : 0);
+  size_t o_A[2], o_n[2];
+  for (int q = 0; q < 2; q++) {
+    o_A[q] = take(sub * K * K * 512);
+    o_n[q] = take(sub * P::n_noise * 512);
+  }
+  void* basev = nullptr;
+  int rc = ensure_work(slot, off, &basev);
+  if (rc) return rc;
+  char* b = (char*)basev;
+  uint64_t* h = (uint64_t*)(b + o_h);
+  uint64_t* r = (uint64_t*)(b + o_r);
+  uint8_t* m = (uint8_t*)(b + o_m);
+  uint8_t* kbar = (uint8_t*)(b + o_k);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
+    attr_set = true;
+  }
+  const kyber::TwPair* tw = (const kyber::TwPair*)c.kyber_tw;
+  if (!decaps) {
+    {
+      KernelScope ks(KID_MLKEM_G, st);
+      r3_m_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, n, m);
+    }
+    {
+      KernelScope ks(KID_MLKEM_HASH_EK, st);
+      hash_ek_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(key, key_stride, n, h);
+    }
+    rc = r3_encrypt<K>(key, key_stride, (const uint8_t*)h, 32, m, ct_out, kbar, r, b, o_A, o_n, n, st, slot);
+    if (rc) return rc;
+    KernelScope ks(KID_MLKEM_G, st);
+    r3_kdf_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(ct_out, nullptr, kbar, nullptr, 0, n, ss);
+  } else {
+    uint8_t* ct2 = (uint8_t*)(b + o_ct2);
+    const uint8_t* ek = key + 384 * K;
+    {
+      KernelScope ks(KID_MLKEM_ENCRYPT, st);
+      decrypt_kernel<K><<<(unsigned)((n + 15) / 16), kEncThreads, 0, st>>>(key, key_stride, in, n, m, tw);
+    }
+    rc = r3_encrypt<K>(ek, key_stride, key + 384 * K + P::ek_bytes, key_stride, m, ct2, kbar, r, b, o_A, o_n, n, st, slot);
+    if (rc) return rc;
+    KernelScope ks(KID_MLKEM_G, st);
+    r3_kdf_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(in, ct2, kbar, key + 384 * K + P::ek_bytes + 32, key_stride,
+                                                                  n, ss);
+  }
   CB200_CUDA(cudaGetLastError());
   return 0;
 }
@@ -1081,6 +1255,71 @@ int cb200_mlkem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, si
   return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return run((const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
   });
+}
+
+// ---- round-3 Kyber512/768/1024 KEM (kem/kyber): same sizes as ML-KEM-512/768/1024
+int cb200_kyber_kem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (k < 2 || k > 4 || !seeds || !ek || !dk) {
+    set_error("cb200_kyber_kem_keygen: bad argument");
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  const bool dev = is_device_ptr(ek);
+  if (dev != is_device_ptr(seeds) || dev != is_device_ptr(dk)) {
+    set_error("cb200_kyber_kem_keygen: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  auto run = [&](const uint8_t* s_, uint8_t* e_, uint8_t* d_, size_t cnt, cudaStream_t st, int slot) {
+    return k == 2   ? mlkem::keygen_device<2>(s_, e_, d_, cnt, st, slot, 0)
+           : k == 3 ? mlkem::keygen_device<3>(s_, e_, d_, cnt, st, slot, 0)
+                    : mlkem::keygen_device<4>(s_, e_, d_, cnt, st, slot, 0);
+  };
+  if (dev) return run(seeds, ek, dk, n, ctx().cur, 3);
+  std::vector<Buf> bufs(3);
+  bufs[0] = Buf{seeds, nullptr, 64, false, 0};
+  bufs[1] = Buf{nullptr, ek, cb200_mlkem_public_key_size(k), false, 0};
+  bufs[2] = Buf{nullptr, dk, 768u * k + 96, false, 0};
+  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+    return run((const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
+  });
+}
+
+static int kyber_kem_run(int decaps, int k, const uint8_t* key, const uint8_t* in, uint8_t* ct, uint8_t* ss, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (k < 2 || k > 4 || !key || !in || !ss || (!decaps && !ct)) {
+    set_error("cb200_kyber_kem_%s: bad argument", decaps ? "decaps" : "encaps");
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  const size_t keysz = decaps ? 768u * k + 96 : cb200_mlkem_public_key_size(k), ctsz = cb200_mlkem_ciphertext_size(k);
+  const bool dev = is_device_ptr(ss);
+  if (dev != is_device_ptr(key) || dev != is_device_ptr(in) || (ct && dev != is_device_ptr(ct))) {
+    set_error("cb200_kyber_kem: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  auto run = [&](const uint8_t* k_, const uint8_t* i_, uint8_t* c_, uint8_t* s_, size_t cnt, cudaStream_t st, int slot) {
+    return k == 2   ? mlkem::r3_device<2>(decaps, k_, keysz, i_, c_, s_, cnt, st, slot)
+           : k == 3 ? mlkem::r3_device<3>(decaps, k_, keysz, i_, c_, s_, cnt, st, slot)
+                    : mlkem::r3_device<4>(decaps, k_, keysz, i_, c_, s_, cnt, st, slot);
+  };
+  if (dev) return run(key, in, ct, ss, n, ctx().cur, 3);
+  std::vector<Buf> bufs(4);
+  bufs[0] = Buf{key, nullptr, keysz, false, 0};
+  bufs[1] = Buf{in, nullptr, decaps ? ctsz : (size_t)32, false, 0};
+  bufs[2] = Buf{nullptr, decaps ? nullptr : ct, ctsz, false, 0};
+  bufs[3] = Buf{nullptr, ss, 32, false, 0};
+  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+    return run((const uint8_t*)d[0], (const uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], cnt, st, slot);
+  });
+}
+int cb200_kyber_kem_encaps(int k, const uint8_t* ek, const uint8_t* seeds, uint8_t* ct, uint8_t* ss, size_t n) {
+  return kyber_kem_run(0, k, ek, seeds, ct, ss, n);
+}
+int cb200_kyber_kem_decaps(int k, const uint8_t* dk, const uint8_t* ct, uint8_t* ss, size_t n) {
+  return kyber_kem_run(1, k, dk, ct, nullptr, ss, n);
 }
 
 size_t cb200_mlkem_private_key_size(int k) { return (k >= 2 && k <= 4) ? 768u * k + 96 : 0; }

@@ -421,3 +421,24 @@ def mldsa_sign_batch(mode: int, sk: np.ndarray, msgs: list[bytes], rnd=None, nth
     if att < 0:
         raise RuntimeError("sign_batch failed")
     return sig, att
+
+
+# ------------------------------------------------------------------ round-3 Kyber KEM (kem/kyber)
+def kyber_kem_keygen(k: int, seed64: bytes):
+    eksz, dksz, _ = mlkem_sizes(k)
+    ek, dk = (C.c_uint8 * eksz)(), (C.c_uint8 * dksz)()
+    lib().orc_kyber_kem_keygen(k, ek, dk, _buf(seed64))
+    return bytes(ek), bytes(dk)
+
+
+def kyber_kem_encaps(k: int, ek: bytes, seed32: bytes):
+    _, _, ctsz = mlkem_sizes(k)
+    ct, ss = (C.c_uint8 * ctsz)(), (C.c_uint8 * 32)()
+    lib().orc_kyber_kem_encaps(k, ct, ss, _buf(ek), _buf(seed32))
+    return bytes(ct), bytes(ss)
+
+
+def kyber_kem_decaps(k: int, dk: bytes, ct: bytes) -> bytes:
+    ss = (C.c_uint8 * 32)()
+    lib().orc_kyber_kem_decaps(k, ss, _buf(dk), _buf(ct))
+    return bytes(ss)

@@ -315,13 +315,14 @@ static int pk_unpack(int k, int16_t *th, int16_t *aT, const uint8_t *ek) {
   return bad ? -1 : 0;
 }
 
-void orc_mlkem_keygen(int k, uint8_t *ek, uint8_t *dk, const uint8_t seed[64]) {
-  /* kem/mlkem/mlkem768/kyber.go:57-78 -> pke/kyber/kyber768/kyber.go:77-86 -> cpapke.go:66-110 */
+static void kem_keygen(int k, int mlkem, uint8_t *ek, uint8_t *dk, const uint8_t seed[64]) {
+  /* kem/mlkem/mlkem768/kyber.go:57-78 -> pke/kyber/kyber768/kyber.go:77-86 -> cpapke.go:66-110;
+   * round-3 Kyber (kem/kyber/kyber768/kyber.go:56-77) hashes the 32-byte seed without the K byte */
   uint8_t seed2[33], exp[64];
   int16_t A[16 * N], sh[4 * N], eh[4 * N], th[4 * N];
   memcpy(seed2, seed, 32);
   seed2[32] = (uint8_t)k;
-  orc_sha3_512(exp, seed2, 33);
+  orc_sha3_512(exp, seed2, mlkem ? 33 : 32);
   const uint8_t *rho = exp, *sigma = exp + 32;
   mat_derive(A, k, rho, 0);
   for (int i = 0; i < k; i++) {
@@ -347,6 +348,62 @@ void orc_mlkem_keygen(int k, uint8_t *ek, uint8_t *dk, const uint8_t seed[64]) {
   memcpy(dk + 384 * k, ek, eksz);
   orc_sha3_256(dk + 384 * k + eksz, ek, eksz);
   memcpy(dk + 384 * k + eksz + 32, seed + 32, 32);
+}
+
+void orc_mlkem_keygen(int k, uint8_t *ek, uint8_t *dk, const uint8_t seed[64]) { kem_keygen(k, 1, ek, dk, seed); }
+void orc_kyber_kem_keygen(int k, uint8_t *ek, uint8_t *dk, const uint8_t seed[64]) { kem_keygen(k, 0, ek, dk, seed); }
+
+/* PublicKey.Unpack (cpapke.go:58-63): no modulus check, t-hat normalised */
+static void pk_unpack_lenient(int k, int16_t *th, int16_t *aT, const uint8_t *ek) {
+  for (int i = 0; i < k; i++) {
+    orc_kyber_unpack(th + i * N, ek + 384 * i);
+    orc_kyber_normalize(th + i * N);
+  }
+  mat_derive(aT, k, ek + 384 * k, 1);
+}
+
+/* round-3 Kyber Encapsulate (kem/kyber/kyber768/kyber.go:98-137): m = H(seed), (K, r) = G(m || H(pk)),
+ * ct = Enc(pk, m, r), ss = KDF(K || H(ct)) */
+void orc_kyber_kem_encaps(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *ek, const uint8_t seed[32]) {
+  int16_t th[4 * N], aT[16 * N];
+  uint8_t m[32], g_in[64], kr[64];
+  size_t ctsz = orc_mlkem_ct_size(k);
+  pk_unpack_lenient(k, th, aT, ek);
+  orc_sha3_256(m, seed, 32);
+  memcpy(g_in, m, 32);
+  orc_sha3_256(g_in + 32, ek, orc_mlkem_ek_size(k));
+  orc_sha3_512(kr, g_in, 64);
+  cpapke_encrypt(k, ct, th, aT, m, kr + 32);
+  orc_sha3_256(kr + 32, ct, ctsz);
+  orc_shake256(ss, 32, kr, 64);
+}
+
+/* round-3 Kyber Decapsulate (kem/kyber/kyber768/kyber.go:139-176) */
+void orc_kyber_kem_decaps(int k, uint8_t ss[32], const uint8_t *dk, const uint8_t *ct) {
+  int16_t sh[4 * N], th[4 * N], aT[16 * N], u[4 * N], v[N], mp[N];
+  size_t eksz = orc_mlkem_ek_size(k), ctsz = orc_mlkem_ct_size(k);
+  const uint8_t *ek = dk + 384 * k, *hpk = ek + eksz, *z = hpk + 32;
+  uint8_t m2[32], g_in[64], kr2[64];
+  int du = du_of(k), dv = dv_of(k);
+  for (int i = 0; i < k; i++) { orc_kyber_unpack(sh + i * N, dk + 384 * i); orc_kyber_normalize(sh + i * N); }
+  pk_unpack_lenient(k, th, aT, ek);
+  for (int i = 0; i < k; i++) { orc_kyber_decompress(u + i * N, ct + i * 32 * du, du); orc_kyber_ntt(u + i * N); }
+  orc_kyber_decompress(v, ct + k * 32 * du, dv);
+  dot_hat(mp, sh, u, k);
+  orc_kyber_barrett(mp);
+  orc_kyber_invntt(mp);
+  orc_kyber_sub(mp, v, mp);
+  orc_kyber_normalize(mp);
+  orc_kyber_msg_compress(m2, mp);
+  memcpy(g_in, m2, 32);
+  memcpy(g_in + 32, hpk, 32);
+  orc_sha3_512(kr2, g_in, 64);
+  uint8_t *ct2 = (uint8_t *)malloc(ctsz);
+  cpapke_encrypt(k, ct2, th, aT, m2, kr2 + 32);
+  orc_sha3_256(kr2 + 32, ct, ctsz);
+  if (memcmp(ct, ct2, ctsz) != 0) memcpy(kr2, z, 32);
+  free(ct2);
+  orc_shake256(ss, 32, kr2, 64);
 }
 
 int orc_mlkem_encaps(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *ek, const uint8_t m[32]) {

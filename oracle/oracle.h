@@ -79,6 +79,10 @@ void orc_mlkem_keygen(int k, uint8_t *ek, uint8_t *dk, const uint8_t seed[64]);
 int orc_mlkem_encaps(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *ek, const uint8_t m[32]);
 /* returns 0, or -2 if H(ek) stored in dk mismatches (kem.ErrPrivKey) */
 int orc_mlkem_decaps(int k, uint8_t ss[32], const uint8_t *dk, const uint8_t *ct);
+/* round-3 Kyber512/768/1024 KEM (kem/kyber/kyber768/kyber.go:56-176): same K-PKE, different hashing */
+void orc_kyber_kem_keygen(int k, uint8_t *ek, uint8_t *dk, const uint8_t seed[64]);
+void orc_kyber_kem_encaps(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *ek, const uint8_t seed[32]);
+void orc_kyber_kem_decaps(int k, uint8_t ss[32], const uint8_t *dk, const uint8_t *ct);
 /* batched; ek_stride == 0 => one ek for all ops. returns number of failures */
 int orc_mlkem_encaps_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, size_t ek_stride,
                            const uint8_t *m, size_t n, int nthreads);

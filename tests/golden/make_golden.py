@@ -171,6 +171,9 @@ def samplers():
         "ML-KEM-768": re.search(r'"ML-KEM-768", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
         "ML-KEM-1024": re.search(r'"ML-KEM-1024", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
         "ML-DSA-65": re.search(r'"ML-DSA-65", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
+        "Kyber512": re.search(r'"Kyber512", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
+        "Kyber768": re.search(r'"Kyber768", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
+        "Kyber1024": re.search(r'"Kyber1024", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
         "ML-DSA-44": re.search(r'"ML-DSA-44", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
         "ML-DSA-87": re.search(r'"ML-DSA-87", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
     }

@@ -215,3 +215,22 @@ def test_invntt_matches_table_driven_model(sampler_vectors):
     got = oracle.kyber_invntt(polys)
     for i in range(6):
         assert got[i].tolist() == invntt(polys[i].tolist())
+
+
+@pytest.mark.parametrize("name,k", [("Kyber512", 2), ("Kyber768", 3), ("Kyber1024", 4)])
+def test_round3_kyber_pqcgenkat_hash(sampler_vectors, name, k):
+    # kem/kyber/kat_test.go:42-94, round-3 branch: the key seed comes from two 32-byte randombytes calls
+    g = DRBG(bytes(range(48)))
+    f = hashlib.sha256()
+    f.update(("# %s\n\n" % name).encode())
+    for i in range(100):
+        seed = g.fill(48)
+        f.update(("count = %d\nseed = %s\n" % (i, seed.hex().upper())).encode())
+        g2 = DRBG(seed)
+        kseed = g2.fill(32) + g2.fill(32)
+        eseed = g2.fill(32)
+        ek, dk = oracle.kyber_kem_keygen(k, kseed)
+        ct, ss = oracle.kyber_kem_encaps(k, ek, eseed)
+        assert oracle.kyber_kem_decaps(k, dk, ct) == ss
+        f.update(("pk = %s\nsk = %s\nct = %s\nss = %s\n\n" % (ek.hex().upper(), dk.hex().upper(), ct.hex().upper(), ss.hex().upper())).encode())
+    assert f.hexdigest() == sampler_vectors["kat_sha256"][name]

@@ -1286,40 +1286,55 @@ int cb200_kyber_kem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk
   });
 }
 
-static int kyber_kem_run(int decaps, int k, const uint8_t* key, const uint8_t* in, uint8_t* ct, uint8_t* ss, size_t n) {
+static int kyber_kem_run(int decaps, int k, const uint8_t* key, size_t key_stride, const uint8_t* in, uint8_t* ct, uint8_t* ss,
+                         size_t n) {
   int rc = require_ready();
   if (rc) return rc;
-  if (k < 2 || k > 4 || !key || !in || !ss || (!decaps && !ct)) {
-    set_error("cb200_kyber_kem_%s: bad argument", decaps ? "decaps" : "encaps");
+  const char* fn = decaps ? "cb200_kyber_kem_decaps" : "cb200_kyber_kem_encaps";
+  if (k < 2 || k > 4) {
+    set_error("%s: k must be 2, 3 or 4 (Kyber512/768/1024), got %d", fn, k);
     return CB200_ERR_ARG;
   }
   if (n == 0) return 0;
   const size_t keysz = decaps ? 768u * k + 96 : cb200_mlkem_public_key_size(k), ctsz = cb200_mlkem_ciphertext_size(k);
-  const bool dev = is_device_ptr(ss);
-  if (dev != is_device_ptr(key) || dev != is_device_ptr(in) || (ct && dev != is_device_ptr(ct))) {
-    set_error("cb200_kyber_kem: mixed host/device pointers");
+  if (!key || !in || !ss || (!decaps && !ct) || (key_stride != 0 && key_stride < keysz)) {
+    set_error("%s: bad argument", fn);
     return CB200_ERR_ARG;
   }
-  auto run = [&](const uint8_t* k_, const uint8_t* i_, uint8_t* c_, uint8_t* s_, size_t cnt, cudaStream_t st, int slot) {
-    return k == 2   ? mlkem::r3_device<2>(decaps, k_, keysz, i_, c_, s_, cnt, st, slot)
-           : k == 3 ? mlkem::r3_device<3>(decaps, k_, keysz, i_, c_, s_, cnt, st, slot)
-                    : mlkem::r3_device<4>(decaps, k_, keysz, i_, c_, s_, cnt, st, slot);
+  const bool dev = is_device_ptr(ss);
+  if (dev != is_device_ptr(key) || dev != is_device_ptr(in) || (ct && dev != is_device_ptr(ct))) {
+    set_error("%s: mixed host/device pointers", fn);
+    return CB200_ERR_ARG;
+  }
+  auto run = [&](const uint8_t* k_, size_t ks_, const uint8_t* i_, uint8_t* c_, uint8_t* s_, size_t cnt, cudaStream_t st,
+                 int slot) {
+    return k == 2   ? mlkem::r3_device<2>(decaps, k_, ks_, i_, c_, s_, cnt, st, slot)
+           : k == 3 ? mlkem::r3_device<3>(decaps, k_, ks_, i_, c_, s_, cnt, st, slot)
+                    : mlkem::r3_device<4>(decaps, k_, ks_, i_, c_, s_, cnt, st, slot);
   };
-  if (dev) return run(key, in, ct, ss, n, ctx().cur, 3);
-  std::vector<Buf> bufs(4);
-  bufs[0] = Buf{key, nullptr, keysz, false, 0};
-  bufs[1] = Buf{in, nullptr, decaps ? ctsz : (size_t)32, false, 0};
-  bufs[2] = Buf{nullptr, decaps ? nullptr : ct, ctsz, false, 0};
-  bufs[3] = Buf{nullptr, ss, 32, false, 0};
+  if (dev) {
+    if (((uintptr_t)key | (uintptr_t)in | (uintptr_t)ct | (uintptr_t)ss | key_stride) & 15) {
+      set_error("%s: device buffers and the key stride must be 16-byte aligned", fn);
+      return CB200_ERR_ARG;
+    }
+    return run(key, key_stride, in, ct, ss, n, ctx().cur, 3);
+  }
+  std::vector<Buf> bufs;
+  bufs.push_back(Buf{key, nullptr, keysz, key_stride == 0, key_stride});
+  bufs.push_back(Buf{in, nullptr, decaps ? ctsz : (size_t)32, false, 0});
+  bufs.push_back(Buf{nullptr, ss, 32, false, 0});
+  if (!decaps) bufs.push_back(Buf{nullptr, ct, ctsz, false, 0});
   return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
-    return run((const uint8_t*)d[0], (const uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], cnt, st, slot);
+    return run((const uint8_t*)d[0], key_stride == 0 ? 0 : keysz, (const uint8_t*)d[1], decaps ? nullptr : (uint8_t*)d[3],
+               (uint8_t*)d[2], cnt, st, slot);
   });
 }
-int cb200_kyber_kem_encaps(int k, const uint8_t* ek, const uint8_t* seeds, uint8_t* ct, uint8_t* ss, size_t n) {
-  return kyber_kem_run(0, k, ek, seeds, ct, ss, n);
+int cb200_kyber_kem_encaps(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
+                           size_t n) {
+  return kyber_kem_run(0, k, ek, ek_stride, seeds, ct, ss, n);
 }
-int cb200_kyber_kem_decaps(int k, const uint8_t* dk, const uint8_t* ct, uint8_t* ss, size_t n) {
-  return kyber_kem_run(1, k, dk, ct, nullptr, ss, n);
+int cb200_kyber_kem_decaps(int k, const uint8_t* dk, size_t dk_stride, const uint8_t* ct, uint8_t* ss, size_t n) {
+  return kyber_kem_run(1, k, dk, dk_stride, ct, nullptr, ss, n);
 }
 
 size_t cb200_mlkem_private_key_size(int k) { return (k >= 2 && k <= 4) ? 768u * k + 96 : 0; }

@@ -1,4 +1,4 @@
-"""kem.Scheme mirror for ML-KEM-512 / ML-KEM-768 / ML-KEM-1024 over the C ABI.
+"""kem.Scheme mirror for ML-KEM-512/768/1024 and round-3 Kyber512/768/1024 over the C ABI.
 
 Mirrors the method names, argument meaning and error behaviour of
   kem/kem.go:33-121                      (kem.Scheme, kem.Err*)
@@ -92,8 +92,25 @@ def _is_torch(x) -> bool:
 
 
 class Scheme:
-    def __init__(self, name: str, k: int):
-        self._name, self._k = name, k
+    def __init__(self, name: str, k: int, round3: bool = False):
+        self._name, self._k, self._round3 = name, k, round3
+
+    # One place decides which C entry points serve this scheme: FIPS 203 (kem/mlkem) or the round-3
+    # submission (kem/kyber/kyber768/kyber.go), whose calls carry no status array because round-3
+    # key parsing cannot fail (no modulus check, no H(ek) check).
+    def _c_encaps(self, ek, stride, seeds, ct, ss, status, n):
+        if self._round3:
+            return lib().cb200_kyber_kem_encaps(self._k, ek, stride, seeds, ct, ss, n)
+        return lib().cb200_mlkem_encaps(self._k, ek, stride, seeds, ct, ss, status, n)
+
+    def _c_decaps(self, dk, stride, ct, ss, status, n):
+        if self._round3:
+            return lib().cb200_kyber_kem_decaps(self._k, dk, stride, ct, ss, n)
+        return lib().cb200_mlkem_decaps(self._k, dk, stride, ct, ss, status, n)
+
+    def _c_keygen(self, seeds, ek, dk, n):
+        fn = lib().cb200_kyber_kem_keygen if self._round3 else lib().cb200_mlkem_keygen
+        return fn(self._k, seeds, ek, dk, n)
 
     # ---- kem.Scheme size/identity methods (kyber.go:271-279) ----
     def Name(self) -> str:
@@ -163,8 +180,8 @@ class Scheme:
             ss = torch.empty((n, 32), dtype=torch.uint8, device=seeds.device) if ss is None else ss
             status = torch.zeros((n,), dtype=torch.uint8, device=seeds.device)
             check(lib().cb200_set_stream(torch.cuda.current_stream().cuda_stream))
-            check(lib().cb200_mlkem_encaps(k, ek.data_ptr(), stride, seeds.data_ptr(), ct.data_ptr(), ss.data_ptr(),
-                                           status.data_ptr(), n))
+            check(self._c_encaps(ek.data_ptr(), stride, seeds.data_ptr(), ct.data_ptr(), ss.data_ptr(),
+                                 status.data_ptr(), n))
             self._last_status = status  # read lazily: the call is asynchronous on the torch stream
             return ct, ss
         seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
@@ -183,8 +200,8 @@ class Scheme:
         ss = np.empty((n, 32), dtype=np.uint8) if ss is None else ss
         status = np.zeros((n,), dtype=np.uint8)
         try:
-            check(lib().cb200_mlkem_encaps(k, ek.ctypes.data, stride, seeds.ctypes.data, ct.ctypes.data,
-                                           ss.ctypes.data, status.ctypes.data, n))
+            check(self._c_encaps(ek.ctypes.data, stride, seeds.ctypes.data, ct.ctypes.data,
+                                 ss.ctypes.data, status.ctypes.data, n))
         except Cb200Error as e:
             if e.code == -3:
                 err = ErrPubKey("kem: invalid public key")
@@ -224,7 +241,7 @@ class Scheme:
             ek = torch.empty((n, eksz), dtype=torch.uint8, device=seeds.device)
             dk = torch.empty((n, dksz), dtype=torch.uint8, device=seeds.device)
             check(lib().cb200_set_stream(torch.cuda.current_stream().cuda_stream))
-            check(lib().cb200_mlkem_keygen(k, seeds.data_ptr(), ek.data_ptr(), dk.data_ptr(), n))
+            check(self._c_keygen(seeds.data_ptr(), ek.data_ptr(), dk.data_ptr(), n))
             return ek, dk
         seeds = np.ascontiguousarray(seeds, dtype=np.uint8)
         if seeds.ndim != 2 or seeds.shape[1] != 64:
@@ -232,7 +249,7 @@ class Scheme:
         n = seeds.shape[0]
         ek = np.empty((n, eksz), dtype=np.uint8)
         dk = np.empty((n, dksz), dtype=np.uint8)
-        check(lib().cb200_mlkem_keygen(k, seeds.ctypes.data, ek.ctypes.data, dk.ctypes.data, n))
+        check(self._c_keygen(seeds.ctypes.data, ek.ctypes.data, dk.ctypes.data, n))
         return ek, dk
 
     def UnmarshalBinaryPrivateKey(self, buf: bytes) -> PrivateKey:
@@ -263,7 +280,7 @@ class Scheme:
             ss = torch.empty((n, 32), dtype=torch.uint8, device=cts.device) if ss is None else ss
             status = torch.zeros((n,), dtype=torch.uint8, device=cts.device)
             check(lib().cb200_set_stream(torch.cuda.current_stream().cuda_stream))
-            check(lib().cb200_mlkem_decaps(k, sks.data_ptr(), dksz, cts.data_ptr(), ss.data_ptr(), status.data_ptr(), n))
+            check(self._c_decaps(sks.data_ptr(), dksz, cts.data_ptr(), ss.data_ptr(), status.data_ptr(), n))
             self._last_status = status
             return ss
         cts = np.ascontiguousarray(cts, dtype=np.uint8)
@@ -281,8 +298,8 @@ class Scheme:
         ss = np.empty((n, 32), dtype=np.uint8) if ss is None else ss
         status = np.zeros((n,), dtype=np.uint8)
         try:
-            check(lib().cb200_mlkem_decaps(k, dk.ctypes.data, stride, cts.ctypes.data, ss.ctypes.data,
-                                           status.ctypes.data, n))
+            check(self._c_decaps(dk.ctypes.data, stride, cts.ctypes.data, ss.ctypes.data,
+                                 status.ctypes.data, n))
         except Cb200Error as e:
             if e.code == -5:
                 err = ErrPrivKey("kem: invalid private key")
@@ -292,7 +309,10 @@ class Scheme:
         return ss
 
 _SCHEMES = {"ml-kem-512": Scheme("ML-KEM-512", 2), "ml-kem-768": Scheme("ML-KEM-768", 3),
-            "ml-kem-1024": Scheme("ML-KEM-1024", 4)}
+            "ml-kem-1024": Scheme("ML-KEM-1024", 4),
+            # round-3 Kyber (kem/kyber/kyber{512,768,1024}); same sizes, different FO wrapper
+            "kyber512": Scheme("Kyber512", 2, True), "kyber768": Scheme("Kyber768", 3, True),
+            "kyber1024": Scheme("Kyber1024", 4, True)}
 
 
 def ByName(name: str):

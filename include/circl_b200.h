@@ -123,10 +123,12 @@ size_t cb200_mlkem_ciphertext_size(int k);
 
 /* ---- round-3 Kyber512/768/1024 KEM (k = 2, 3, 4): kem/kyber/kyber768/kyber.go:56-198 ----
  * Same K-PKE and byte sizes as ML-KEM; the FO wrapper differs (m = H(seed), ss = KDF(K || H(ct)), key generation
- * without the K byte, no modulus check of ek).  One packed key per operation (n keys back to back). */
+ * without the K byte, no modulus check of ek, no H(ek) check of dk -- hence no status array).  Strides as in
+ * cb200_mlkem_*: 0 = one key shared by all operations. */
 int cb200_kyber_kem_keygen(int k, const uint8_t *seeds, uint8_t *ek, uint8_t *dk, size_t n);
-int cb200_kyber_kem_encaps(int k, const uint8_t *ek, const uint8_t *seeds, uint8_t *ct, uint8_t *ss, size_t n);
-int cb200_kyber_kem_decaps(int k, const uint8_t *dk, const uint8_t *ct, uint8_t *ss, size_t n);
+int cb200_kyber_kem_encaps(int k, const uint8_t *ek, size_t ek_stride, const uint8_t *seeds, uint8_t *ct, uint8_t *ss,
+                           size_t n);
+int cb200_kyber_kem_decaps(int k, const uint8_t *dk, size_t dk_stride, const uint8_t *ct, uint8_t *ss, size_t n);
 
 /* ---- ML-DSA (mode = 44, 65 or 87; sign/dilithium/gen.go:80-162) ----
  * Same contracts as the ML-DSA-65 entry points documented below, with the parameter set as first argument:

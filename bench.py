@@ -566,6 +566,20 @@ def main():
                         "profiles/r01b_ncu_mlkem.txt); achieved = %d algorithmic B/op x %d ops per launch / mean "
                         "launch time; traffic = ncu dram bytes per launch" % (wl["bytes_per_op"], int(units_per_launch)),
                 "kernels_ms_per_step": {k_: round(v["ms_total"], 4) for k_, v in kernels.items()}}
+    # The binding resource is the integer-ALU pipe, so state that roofline too: Keccak-f[1600] permutations
+    # (24 rounds x 192 LOP3/SHF per thread) against the pipe rate measured by scripts/ubench_pipes.cu
+    # (profiles/r01_ubench_pipes.txt: 0.475 warp-instr/clk/SMSP for LOP3 and SHF).
+    k = wl["k"]
+    perms = {"mlkem_sample": 3 * k * k + (2 * k + 1), "mlkem_hash_ek": (384 * k + 32) // 136 + 1}.get(dom_name)
+    if perms:
+        sm_hz = 1.965e9
+        alu_peak = 148 * 4 * 0.475 * 32 * sm_hz / (24 * 192)
+        alu_ach = perms * units_per_launch / (dom_ms * 1e-3)
+        roofline["alu"] = {"bound": "int-alu", "achieved": alu_ach, "peak": alu_peak, "unit": "keccak-f/s",
+                           "frac": alu_ach / alu_peak,
+                           "note": "%d Keccak-f per op in this kernel (3 SHAKE128 blocks per matrix entry + 1 SHAKE256 "
+                                   "block per noise polynomial); the remainder of the ALU time is rejection parsing "
+                                   "and CBD" % perms}
 
     # ---- secondary: raw 256-point NTT (BASELINE configs[1]); 512 MiB in place, larger than L2
     ntt = None

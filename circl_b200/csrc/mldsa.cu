@@ -96,11 +96,37 @@ __device__ __forceinline__ uint32_t field32(const uint32_t (&w)[NW], int i) {
   return f & ((1u << BITS) - 1);
 }
 
+// Sign keeps w1 in the final PackW1 byte order when w1 has 4 bits (gamma2 = (q-1)/32: two coefficients per byte, 128
+// bytes per polynomial) so the challenge hash absorbs it as is; the 6-bit case keeps one byte per coefficient and is
+// packed by w1_word.  Verify always uses the byte-per-coefficient form.
+template <class P>
+struct SignW1 {
+  static constexpr bool packed = (23 - P::G1BITS) == 4;
+  static constexpr int stride = packed ? 128 : 256;  // bytes per polynomial
+  // coefficients 16s + 2v and 16s + 2v + 1
+  static __device__ __forceinline__ void store(uint8_t* poly, int s, int v, uint32_t hi0, uint32_t hi1) {
+    if constexpr (packed) poly[8 * s + v] = (uint8_t)(hi0 | (hi1 << 4));
+    else *reinterpret_cast<uint16_t*>(poly + 16 * s + 2 * v) = (uint16_t)(hi0 | (hi1 << 8));
+  }
+  static __device__ __forceinline__ void load(const uint8_t* poly, int s, int v, uint32_t& hi0, uint32_t& hi1) {
+    if constexpr (packed) {
+      const uint32_t b = poly[8 * s + v];
+      hi0 = b & 15;
+      hi1 = b >> 4;
+    } else {
+      const uint32_t b = *reinterpret_cast<const uint16_t*>(poly + 16 * s + 2 * v);
+      hi0 = b & 0xff;
+      hi1 = b >> 8;
+    }
+  }
+};
+
 struct Work {
   uint32_t *A, *sh;        // per key: A [30][256]; sh = s1h[5] | s2h[6] | t0h[6]
   uint64_t *mu, *rhop;     // per op: 8 words each
   uint32_t *y, *yh, *w0;   // per op: [5][256], [5][256], [6][256]
-  uint8_t* w1u;            // per op: K x 256 bytes, w1 one byte per coefficient (packed on the fly when hashed)
+  uint8_t* w1u;            // per op: K x SignW1::stride bytes: PackW1 layout (4-bit w1) or one byte per coefficient (6-bit)
+  uint32_t* cmask;         // per op: 8 words "c[i] != 0" | 8 words "c[i] == -1" from SampleInBall
   uint8_t* zbuf;           // per op: 5 x 640 bytes, z packed (word aligned; copied into the signature on accept)
   uint32_t* c;             // per op: [256] challenge polynomial, then its NTT
   uint64_t* ctilde;        // per op: 6 words
@@ -360,8 +386,8 @@ __global__ void __launch_bounds__(128) yntt_kernel(const uint32_t* __restrict__ 
   if (base >= total) return;
   const bool active = base + o.oct < total;
   const size_t u = active ? base + o.oct : total - 1;
-  const size_t op = act[u % nact];
-  const int j = (int)(u / nact);
+  const size_t op = act[u / L];
+  const int j = (int)(u % L);
   uint32_t r[32];
   gload_S(y + (op * L + j) * N, o.v, r);
   LaneTw t;
@@ -399,8 +425,8 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
   if (base >= total) return;
   const bool active = base + o.oct < total;
   const size_t u = active ? base + o.oct : total - 1;
-  const size_t op = act[u % nact];
-  const int i = (int)(u / nact);
+  const size_t op = act[u / K];  // the K rows of one op sit next to each other: y-hat is read from DRAM once
+  const int i = (int)(u % K);
   const uint32_t* Ai = A + ((key_shared ? 0 : op) * (K * L) + i * L) * N;
   uint32_t acc[32];
 #pragma unroll
@@ -425,7 +451,7 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
   load_lane_tw_inv(t, zetas + 256, o.v);
   invntt_octet(acc, o.tile, o.v, t);  // -> S layout: acc[2s+b] = coefficient 16s + 2v + b
   uint32_t* w0p = w0 + (op * K + i) * N;
-  uint8_t* w1b = w1u + (op * K + i) * 256;
+  uint8_t* w1b = w1u + (op * K + i) * SignW1<P>::stride;
 #pragma unroll
   for (int s = 0; s < 16; s++) {
     uint32_t lo0, hi0, lo1, hi1;
@@ -433,38 +459,67 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
     decompose<P>(le2q_modq(acc[2 * s + 1]), lo1, hi1);
     if (active) {
       *reinterpret_cast<uint2*>(w0p + 16 * s + 2 * o.v) = make_uint2(lo0, lo1);
-      *reinterpret_cast<uint16_t*>(w1b + 16 * s + 2 * o.v) = (uint16_t)(hi0 | (hi1 << 8));  // one byte per coefficient
+      SignW1<P>::store(w1b, s, o.v, hi0, hi1);
     }
   }
 }
 
-// c~ = H(mu || w1) (dilithium.go:397-401), c = SampleInBall(c~) (sample.go:299-339): thread per op
+// c~ = H(mu || w1) (dilithium.go:397-401), c = SampleInBall(c~) (sample.go:299-339): thread per op.
+// With packed w1 each warp first copies the (mu, w1) rows of its 32 ops into shared memory with coalesced loads
+// (odd row stride: the per-thread absorb reads are bank-conflict free).  c never exists as 256 words in memory:
+// SampleInBall keeps it as two 256-bit masks in registers and cntt_mask_kernel expands them.
+constexpr int kChThreads = 64;
 template <class P>
-__global__ void __launch_bounds__(128) challenge_kernel(const uint32_t* __restrict__ act, size_t nact,
-                                                        const uint64_t* __restrict__ mu, const uint8_t* __restrict__ w1u,
-                                                        uint64_t* __restrict__ ctilde, uint32_t* __restrict__ cpoly,
-                                                        uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags,
-                                                        uint32_t* __restrict__ hintcnt) {
+constexpr int ch_row_words() {
+  return (16 + P::K * 32) | 1;
+}
+template <class P>
+__global__ void __launch_bounds__(kChThreads) challenge_kernel(const uint32_t* __restrict__ act, size_t nact,
+                                                               const uint64_t* __restrict__ mu,
+                                                               const uint8_t* __restrict__ w1u, uint64_t* __restrict__ ctilde,
+                                                               uint32_t* __restrict__ cmask, uint32_t* __restrict__ flags,
+                                                               uint32_t* __restrict__ hintcnt) {
   MLDSA_USE(P);
-  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ __align__(16) uint32_t rows[];
+  constexpr int ROWP = ch_row_words<P>();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t s0 = (size_t)blockIdx.x * kChThreads + warp * 32;
+  const uint32_t* myrow = rows + (warp * 32 + lane) * ROWP;
+  if constexpr (SignW1<P>::packed) {
+    uint32_t* wrows = rows + warp * 32 * ROWP;
+#pragma unroll 4
+    for (int t = 0; t < 32; t++) {
+      if (s0 + t < nact) {
+        const size_t o = act[s0 + t];
+        const uint32_t* m = reinterpret_cast<const uint32_t*>(mu + 8 * o);
+        const uint32_t* w = reinterpret_cast<const uint32_t*>(w1u + o * (K * 128));
+        if (lane < 16) wrows[t * ROWP + lane] = m[lane];
+#pragma unroll
+        for (int x = 0; x < K; x++) wrows[t * ROWP + 16 + 32 * x + lane] = ldg_stream32(w + 32 * x + lane);
+      }
+    }
+    __syncwarp();
+  }
+  const size_t s = s0 + lane;
   if (s >= nact) return;
   const size_t op = act[s];
   uint64_t a[25];
   keccak::zero(a);
   // stream = mu (8 words) || PackW1(w1) (K * POLY_W1 / 8 words), absorbed 17 words at a time
   constexpr int WORDS = 8 + K * POLY_W1 / 8, FULL = WORDS / 17, REM = WORDS % 17, CTW = CTILDE / 8;
-  const uint8_t* w1o = w1u + op * (K * 256);
+  const uint8_t* w1o = w1u + op * (K * SignW1<P>::stride);
+  auto word = [&](int k) -> uint64_t {
+    if constexpr (SignW1<P>::packed) return (uint64_t)myrow[2 * k] | ((uint64_t)myrow[2 * k + 1] << 32);
+    else return (k < 8) ? mu[8 * op + k] : w1_word<P>(w1o, k - 8);
+  };
 #pragma unroll 1
   for (int b = 0; b < FULL; b++) {
 #pragma unroll
-    for (int w = 0; w < 17; w++) {
-      const int k = 17 * b + w;
-      a[w] ^= (k < 8) ? mu[8 * op + k] : w1_word<P>(w1o, k - 8);
-    }
+    for (int w = 0; w < 17; w++) a[w] ^= word(17 * b + w);
     keccak::f1600(a);
   }
 #pragma unroll
-  for (int w = 0; w < REM; w++) a[w] ^= w1_word<P>(w1o, 17 * FULL + w - 8);
+  for (int w = 0; w < REM; w++) a[w] ^= word(17 * FULL + w);
   a[REM] ^= 0x1f;
   a[16] ^= 0x8000000000000000ull;
   keccak::f1600(a);
@@ -474,7 +529,8 @@ __global__ void __launch_bounds__(128) challenge_kernel(const uint32_t* __restri
     ct[i] = a[i];
     ctilde[CTW * op + i] = ct[i];
   }
-  // SampleInBall
+  // SampleInBall: nz = positions with c != 0, ng = positions with c == -1.  Every i of the loop lies in the top
+  // 64-bit word (i >= 256 - TAU >= 192) and is untouched before its iteration.
   keccak::zero(a);
 #pragma unroll
   for (int i = 0; i < CTW; i++) a[i] = ct[i];
@@ -486,8 +542,8 @@ __global__ void __launch_bounds__(128) challenge_kernel(const uint32_t* __restri
   for (int i = 0; i < 17; i++) buf[i] = a[i];
   uint64_t signs = buf[0];
   int off = 8;
-  uint32_t* c = cpoly + op * N;
-  for (int i = 0; i < N; i += 4) *reinterpret_cast<uint4*>(c + i) = make_uint4(0, 0, 0, 0);
+  uint64_t nz[4] = {0, 0, 0, 0}, ng[4] = {0, 0, 0, 0};
+  static_assert(256 - TAU >= 192, "SampleInBall indices must stay in the top word");
   for (int i = N - TAU; i < N; i++) {
     uint32_t b;
     for (;;) {
@@ -497,17 +553,70 @@ __global__ void __launch_bounds__(128) challenge_kernel(const uint32_t* __restri
         for (int q = 0; q < 17; q++) buf[q] = a[q];
         off = 0;
       }
-      b = (uint32_t)(buf[off >> 3] >> (8 * (off & 7))) & 0xff;
+      uint64_t wsel = buf[0];
+#pragma unroll
+      for (int q = 1; q < 17; q++) wsel = ((off >> 3) == q) ? buf[q] : wsel;
+      b = (uint32_t)(wsel >> (8 * (off & 7))) & 0xff;
       off++;
       if (b <= (uint32_t)i) break;
     }
-    c[i] = c[b];
-    c[b] = (signs & 1) ? Q - 1 : 1;
+    const int bq = b >> 6, br = b & 63;
+    uint64_t wn = nz[0], wg = ng[0];
+#pragma unroll
+    for (int q = 1; q < 4; q++) {
+      wn = (bq == q) ? nz[q] : wn;
+      wg = (bq == q) ? ng[q] : wg;
+    }
+    // c[i] = c[b]
+    nz[3] |= ((wn >> br) & 1) << (i - 192);
+    ng[3] |= ((wg >> br) & 1) << (i - 192);
+    // c[b] = 1 - 2 * sign
+    const uint64_t bit = 1ull << br, sg = (signs & 1) << br;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      nz[q] |= (bq == q) ? bit : 0;
+      ng[q] = (bq == q) ? ((ng[q] & ~bit) | sg) : ng[q];
+    }
     signs >>= 1;
   }
-  for (int i = 0; i < 8 * K; i++) hintbits[8 * K * op + i] = 0;
+  uint4* cm = reinterpret_cast<uint4*>(cmask + 16 * op);
+  cm[0] = make_uint4((uint32_t)nz[0], (uint32_t)(nz[0] >> 32), (uint32_t)nz[1], (uint32_t)(nz[1] >> 32));
+  cm[1] = make_uint4((uint32_t)nz[2], (uint32_t)(nz[2] >> 32), (uint32_t)nz[3], (uint32_t)(nz[3] >> 32));
+  cm[2] = make_uint4((uint32_t)ng[0], (uint32_t)(ng[0] >> 32), (uint32_t)ng[1], (uint32_t)(ng[1] >> 32));
+  cm[3] = make_uint4((uint32_t)ng[2], (uint32_t)(ng[2] >> 32), (uint32_t)ng[3], (uint32_t)(ng[3] >> 32));
   flags[op] = 0;
   hintcnt[op] = 0;
+}
+
+// c-hat = NTT(c) for Sign: octet per active op; c is expanded from the SampleInBall masks
+__global__ void __launch_bounds__(128) cntt_mask_kernel(const uint32_t* __restrict__ act, size_t nact,
+                                                        const uint32_t* __restrict__ cmask, uint32_t* __restrict__ cpoly,
+                                                        const uint32_t* __restrict__ zetas) {
+  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
+  const OctetCtx o = octet_ctx(tiles);
+  const size_t base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+  if (base >= nact) return;
+  const bool active = base + o.oct < nact;
+  const size_t op = act[active ? base + o.oct : nact - 1];
+  const uint4* cm = reinterpret_cast<const uint4*>(cmask + 16 * op);
+  const uint4 n0 = cm[0], n1 = cm[1], g0 = cm[2], g1 = cm[3];
+  const uint32_t nzw[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
+  const uint32_t ngw[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+  uint32_t r[32];
+#pragma unroll
+  for (int s = 0; s < 16; s++) {  // S layout: r[2s + b] = coefficient 16s + 2v + b = bit 16 (s & 1) + 2v + b of word s >> 1
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      const int sh = 16 * (s & 1) + 2 * o.v + b;
+      const uint32_t isnz = (nzw[s >> 1] >> sh) & 1, isng = (ngw[s >> 1] >> sh) & 1;
+      r[2 * s + b] = isnz ? (isng ? Q - 1 : 1u) : 0u;
+    }
+  }
+  LaneTw t;
+  load_lane_tw_fwd(t, zetas, o.v);
+  ntt_octet(r, o.tile, o.v, t);
+  __syncwarp();
+  if (active) gstore_C(cpoly + op * N, o.v, r);
 }
 
 // c-hat = NTT(c): octet per active op
@@ -552,12 +661,17 @@ __device__ __forceinline__ uint32_t make_hint(uint32_t z0, uint32_t r1) {
   return (z0 <= GAMMA2 || z0 > Q - GAMMA2 || (z0 == Q - GAMMA2 && r1 == 0)) ? 0u : 1u;
 }
 
-// The three norm checks + hint (dilithium.go:407-464): octet per (op, item), item < K: row i of the K-vectors
-// (w0 - c s2, c t0, hint), item >= K: polynomial j of z = y + c s1 (packed straight into the signature).
-template <class P>
+// The three norm checks + hint (dilithium.go:407-464).  Any failed check rejects the attempt and nothing of a rejected
+// attempt is ever output, so the checks may run in any order; they run as three launches, cheapest filter first, and
+// a warp of a later stage leaves at once when an earlier stage already rejected its op (81 % of the attempts of
+// ML-DSA-65 never reach stage 2):
+//   stage 0: r0 = w0 - c s2 (K octets per op, rows of one op adjacent), kept in place of w0 for stage 2
+//   stage 1: z[0..3] = y + c s1, packed straight into the signature staging buffer (one warp per op)
+//   stage 2: z[4..L), c t0 and the hints (ceil((L - 4 + K) / 4) warps per op)
+template <class P, int STAGE>
 __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
                                                        const uint32_t* __restrict__ sh, const uint32_t* __restrict__ cpoly,
-                                                       const uint32_t* __restrict__ y, const uint32_t* __restrict__ w0,
+                                                       const uint32_t* __restrict__ y, uint32_t* __restrict__ w0,
                                                        const uint8_t* __restrict__ w1u, uint8_t* __restrict__ zbuf,
                                                        uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags,
                                                        uint32_t* __restrict__ hintcnt, const uint32_t* __restrict__ zetas) {
@@ -569,71 +683,100 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
   const volatile uint32_t* ti = izs;
   const OctetCtx o = octet_ctx(tiles);
   const unsigned octmask = 0xffu << (8 * o.oct);
-  const size_t total = nact * (K + L), base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
-  if (base >= total) return;
-  const bool active = base + o.oct < total;
-  const size_t u = active ? base + o.oct : total - 1;
-  const size_t op = act[u % nact];
-  const int item = (int)(u / nact);
+  constexpr int ZB = 4;  // z polynomials checked by stage 1 (L >= 4 in every mode)
+  constexpr int ITEMS = STAGE == 0 ? K : STAGE == 1 ? ZB : (L - ZB) + K;
+  constexpr int WPO = (ITEMS + 3) / 4;  // warps per op in stages 1 and 2
+  size_t op;
+  int item;
+  bool active;
+  if constexpr (STAGE == 0) {
+    const size_t total = nact * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
+    if (base >= total) return;
+    active = base + o.oct < total;
+    const size_t u = active ? base + o.oct : total - 1;
+    op = act[u / K];
+    item = (int)(u % K);
+  } else {
+    const size_t wi = (size_t)blockIdx.x * 4 + o.warp;
+    if (wi >= nact * WPO) return;
+    op = act[wi / WPO];
+    if (flags[op]) return;  // same op for the whole warp: rejected by an earlier stage
+    item = (int)(wi % WPO) * 4 + o.oct;
+    active = item < ITEMS;
+    if (!active) item = ITEMS - 1;
+  }
   const uint32_t* keyp = sh + (key_shared ? 0 : op) * (NKEYPOLY * N);
   const uint32_t* chat = cpoly + op * N;
   uint32_t r[32];
   bool reject = false;
-  if (item < K) {
+  if constexpr (STAGE == 0) {
     const int i = item;
     c_times(r, chat, keyp + (L + i) * N, o, ti);  // c s2[i]
-    const uint32_t* w0p = w0 + (op * K + i) * N;
+    uint32_t* w0p = w0 + (op * K + i) * N;
 #pragma unroll
     for (int s = 0; s < 16; s++) {
       const uint2 a = *reinterpret_cast<const uint2*>(w0p + 16 * s + 2 * o.v);
-      r[2 * s] = modq(a.x + (2 * Q - r[2 * s]));          // w0 - c s2, Normalize
+      r[2 * s] = modq(a.x + (2 * Q - r[2 * s]));  // w0 - c s2, Normalize
       r[2 * s + 1] = modq(a.y + (2 * Q - r[2 * s + 1]));
       reject |= exceeds1(r[2 * s], GAMMA2 - BETA) | exceeds1(r[2 * s + 1], GAMMA2 - BETA);
+      if (active) *reinterpret_cast<uint2*>(w0p + 16 * s + 2 * o.v) = make_uint2(r[2 * s], r[2 * s + 1]);
     }
-    uint32_t u0[32];
-    c_times(u0, chat, keyp + (L + K + i) * N, o, ti);  // c t0[i]
-    const uint8_t* w1b = w1u + (op * K + i) * 256;
-    uint32_t pop = 0;
-#pragma unroll
-    for (int s = 0; s < 16; s++) {
-      const uint32_t t0 = le2q_modq(u0[2 * s]), t1 = le2q_modq(u0[2 * s + 1]);
-      reject |= exceeds1(t0, GAMMA2) | exceeds1(t1, GAMMA2);
-      const uint32_t w1pair = *reinterpret_cast<const uint16_t*>(w1b + 16 * s + 2 * o.v);
-      const uint32_t h0 = make_hint<P>(le2q_modq(r[2 * s] + t0), w1pair & 0xff);
-      const uint32_t h1 = make_hint<P>(le2q_modq(r[2 * s + 1] + t1), w1pair >> 8);
-      const uint32_t bits = h0 | (h1 << 1);
-      pop += h0 + h1;
-      if (bits && active) atomicOr(hintbits + 8 * K * op + 8 * i + (s >> 1), bits << (16 * (s & 1) + 2 * o.v));
-    }
-    if (pop && active) atomicAdd(hintcnt + op, pop);
   } else {
-    const int j = item - K;
-    c_times(r, chat, keyp + j * N, o, ti);  // c s1[j]
-    const uint32_t* yp = y + (op * L + j) * N;
+    // every octet of the warp runs the same sequence of warp-level exchanges; only the arithmetic in between differs
+    const bool is_z = STAGE == 1 || item < L - ZB;
+    const int j = STAGE == 1 ? item : (is_z ? ZB + item : 0);
+    const int i = is_z ? 0 : item - (L - ZB);
+    // the 8 hint words of row i belong to this octet alone; the exchanges inside c_times order the stores below
+    // before the atomicOr of the other lanes
+    if (STAGE == 2 && !is_z && active) hintbits[8 * K * op + 8 * i + o.v] = 0;
+    c_times(r, chat, is_z ? keyp + j * N : keyp + (L + K + i) * N, o, ti);  // c s1[j]  or  c t0[i]
+    if (is_z) {
+      const uint32_t* yp = y + (op * L + j) * N;
 #pragma unroll
-    for (int s = 0; s < 16; s++) {
-      const uint2 a = *reinterpret_cast<const uint2*>(yp + 16 * s + 2 * o.v);
-      r[2 * s] = modq(r[2 * s] + a.x);
-      r[2 * s + 1] = modq(r[2 * s + 1] + a.y);
-      reject |= exceeds1(r[2 * s], GAMMA1 - BETA) | exceeds1(r[2 * s + 1], GAMMA1 - BETA);
+      for (int s = 0; s < 16; s++) {
+        const uint2 a = *reinterpret_cast<const uint2*>(yp + 16 * s + 2 * o.v);
+        r[2 * s] = modq(r[2 * s] + a.x);
+        r[2 * s + 1] = modq(r[2 * s + 1] + a.y);
+        reject |= exceeds1(r[2 * s], GAMMA1 - BETA) | exceeds1(r[2 * s + 1], GAMMA1 - BETA);
+      }
+    } else if constexpr (STAGE == 2) {
+      const uint32_t* r0p = w0 + (op * K + i) * N;  // w0 - c s2 from stage 0
+      const uint8_t* w1b = w1u + (op * K + i) * SignW1<P>::stride;
+      uint32_t pop = 0;
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        const uint32_t t0 = le2q_modq(r[2 * s]), t1 = le2q_modq(r[2 * s + 1]);
+        reject |= exceeds1(t0, GAMMA2) | exceeds1(t1, GAMMA2);
+        const uint2 r0 = *reinterpret_cast<const uint2*>(r0p + 16 * s + 2 * o.v);
+        uint32_t w1a, w1c;
+        SignW1<P>::load(w1b, s, o.v, w1a, w1c);
+        const uint32_t h0 = make_hint<P>(le2q_modq(r0.x + t0), w1a);
+        const uint32_t h1 = make_hint<P>(le2q_modq(r0.y + t1), w1c);
+        const uint32_t bits = h0 | (h1 << 1);
+        pop += h0 + h1;
+        if (bits && active) atomicOr(hintbits + 8 * K * op + 8 * i + (s >> 1), bits << (16 * (s & 1) + 2 * o.v));
+      }
+      if (pop && active) atomicAdd(hintcnt + op, pop);
     }
     // PolyPackLeGamma1 (internal/pack.go:236-252): 32 coefficients -> 20 aligned words in the staging
     // buffer; finalize copies them into the (3309-byte strided) signature only if the attempt is accepted
     s_to_c(r, o.tile, o.v);
-    uint32_t* zw = reinterpret_cast<uint32_t*>(zbuf + (op * L + j) * (size_t)POLY_Z) + ZBITS * o.v;
-    uint64_t accb = 0;
-    int bits = 0, ow = 0;
+    if (is_z) {
+      uint32_t* zw = reinterpret_cast<uint32_t*>(zbuf + (op * L + j) * (size_t)POLY_Z) + ZBITS * o.v;
+      uint64_t accb = 0;
+      int bits = 0, ow = 0;
 #pragma unroll
-    for (int c = 0; c < 32; c++) {
-      uint32_t p = GAMMA1 - r[c];
-      p += (uint32_t)((int32_t)p >> 31) & Q;
-      accb |= (uint64_t)(p & ((1u << ZBITS) - 1)) << bits;
-      bits += ZBITS;
-      if (bits >= 32) {
-        if (active) zw[ow] = (uint32_t)accb;
-        ow++;
-        accb >>= 32;
-        bits -= 32;
+      for (int c = 0; c < 32; c++) {
+        uint32_t p = GAMMA1 - r[c];
+        p += (uint32_t)((int32_t)p >> 31) & Q;
+        accb |= (uint64_t)(p & ((1u << ZBITS) - 1)) << bits;
+        bits += ZBITS;
+        if (bits >= 32) {
+          if (active) zw[ow] = (uint32_t)accb;
+          ow++;
+          accb >>= 32;
+          bits -= 32;
+        }
       }
     }
   }
@@ -1327,7 +1470,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   };
   const size_t oA = take(nkeys * K * L * 1024), oS = take(nkeys * NKEYPOLY * 1024), oMu = take(n * 64),
                oRh = take(n * 64), oY = take(n * L * 1024), oYh = take(n * L * 1024), oW0 = take(n * K * 1024),
-               oW1 = take(n * K * 256), oZ = take(n * L * POLY_Z), oC = take(n * 1024), oCt = take(n * CTILDE), oHb = take(n * 8 * K * 4),
+               oW1 = take(n * K * SignW1<P>::stride), oCm = take(n * 64), oZ = take(n * L * POLY_Z), oC = take(n * 1024), oCt = take(n * CTILDE), oHb = take(n * 8 * K * 4),
                oFl = take(n * 4), oHc = take(n * 4), oAt = take(n * 4), oA0 = take(n * 4), oA1 = take(n * 4),
                oCnt = take(16);
   void* base = nullptr;
@@ -1343,6 +1486,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   w.yh = (uint32_t*)(b + oYh);
   w.w0 = (uint32_t*)(b + oW0);
   w.w1u = (uint8_t*)(b + oW1);
+  w.cmask = (uint32_t*)(b + oCm);
   w.zbuf = (uint8_t*)(b + oZ);
   w.c = (uint32_t*)(b + oC);
   w.ctilde = (uint64_t*)(b + oCt);
@@ -1354,10 +1498,12 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   w.act[1] = (uint32_t*)(b + oA1);
   w.count = (uint32_t*)(b + oCnt);
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
+  constexpr int kChSmem = SignW1<P>::packed ? kChThreads * ch_row_words<P>() * 4 : 0;
 
   static bool attr_set = false;
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
+    if (kChSmem) CB200_CUDA(cudaFuncSetAttribute(challenge_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmem));
     attr_set = true;
   }
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
@@ -1403,17 +1549,21 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     }
     {
       KernelScope ks(KID_MLDSA_CHALLENGE, st);
-      challenge_kernel<P><<<blocks(nact, 128), 128, 0, st>>>(act, nact, w.mu, w.w1u, w.ctilde, w.c, w.hintbits, w.flags,
-                                                          w.hintcnt);
+      challenge_kernel<P><<<blocks(nact, kChThreads), kChThreads, kChSmem, st>>>(act, nact, w.mu, w.w1u, w.ctilde, w.cmask,
+                                                                                 w.flags, w.hintcnt);
     }
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
-      cntt_kernel<<<blocks(nact, 16), 128, 0, st>>>(act, nact, w.c, zetas);
+      cntt_mask_kernel<<<blocks(nact, 16), 128, 0, st>>>(act, nact, w.cmask, w.c, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
-      response_kernel<P><<<blocks(nact * (K + L), 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u,
-                                                                  w.zbuf, w.hintbits, w.flags, w.hintcnt, zetas);
+      response_kernel<P, 0><<<blocks(nact * K, 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u,
+                                                                 w.zbuf, w.hintbits, w.flags, w.hintcnt, zetas);
+      response_kernel<P, 1><<<blocks(nact, 4), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u, w.zbuf,
+                                                             w.hintbits, w.flags, w.hintcnt, zetas);
+      response_kernel<P, 2><<<blocks(nact * ((L - 4 + K + 3) / 4), 4), 128, 0, st>>>(
+          act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u, w.zbuf, w.hintbits, w.flags, w.hintcnt, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_COMPACT, st);

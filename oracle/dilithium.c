@@ -29,14 +29,20 @@
 typedef struct {
   int mode, k, l, eta, tau, gamma1_bits, omega, ctilde;
   uint32_t gamma2;
+  int nist, tr; /* params.go: NIST, TRSize */
 } dparams;
-static const dparams MODES[3] = {
-    {44, 4, 4, 2, 39, 17, 80, 32, (Q - 1) / 88},
-    {65, 6, 5, 4, 49, 19, 55, 48, (Q - 1) / 32},
-    {87, 8, 7, 2, 60, 19, 75, 64, (Q - 1) / 32},
+/* modes 44/65/87 = ML-DSA (sign/mldsa/mldsaNN/internal/params.go); modes 2/3/5 = round-3 Dilithium2/3/5
+ * (sign/dilithium/modeN/internal/params.go: NIST = false, TRSize = 32, CTildeSize = 32) */
+static const dparams MODES[6] = {
+    {44, 4, 4, 2, 39, 17, 80, 32, (Q - 1) / 88, 1, 64},
+    {65, 6, 5, 4, 49, 19, 55, 48, (Q - 1) / 32, 1, 64},
+    {87, 8, 7, 2, 60, 19, 75, 64, (Q - 1) / 32, 1, 64},
+    {2, 4, 4, 2, 39, 17, 80, 32, (Q - 1) / 88, 0, 32},
+    {3, 6, 5, 4, 49, 19, 55, 32, (Q - 1) / 32, 0, 32},
+    {5, 8, 7, 2, 60, 19, 75, 32, (Q - 1) / 32, 0, 32},
 };
 static const dparams *mode_of(int mode) {
-  for (int i = 0; i < 3; i++)
+  for (int i = 0; i < 6; i++)
     if (MODES[i].mode == mode) return &MODES[i];
   return NULL;
 }
@@ -46,7 +52,7 @@ static const dparams *mode_of(int mode) {
 #define P_LEQETA(p) ((p)->eta == 2 ? 96 : 128)                 /* PolyLeqEtaSize */
 #define P_LEGAMMA1(p) (32 * ((p)->gamma1_bits + 1))            /* PolyLeGamma1Size */
 #define P_W1(p) (32 * (23 - (p)->gamma1_bits))                 /* PolyW1Size */
-#define P_SK(p) (32 + 32 + TRSIZE + P_LEQETA(p) * ((p)->l + (p)->k) + POLY_T0 * (p)->k)
+#define P_SK(p) (32 + 32 + (p)->tr + P_LEQETA(p) * ((p)->l + (p)->k) + POLY_T0 * (p)->k)
 #define P_PK(p) (32 + POLY_T1 * (p)->k)
 #define P_SIG(p) ((p)->l * P_LEGAMMA1(p) + (p)->omega + (p)->k + (p)->ctilde)
 size_t orc_mldsa_sk_size(int mode) { return P_SK(mode_of(mode)); }
@@ -391,8 +397,8 @@ static void sk_cache(const dparams *P, privkey *sk) {
 static void sk_unpack(const dparams *P, privkey *sk, const uint8_t *buf) {
   memcpy(sk->rho, buf, 32);
   memcpy(sk->key, buf + 32, 32);
-  memcpy(sk->tr, buf + 64, TRSIZE);
-  const uint8_t *p = buf + 64 + TRSIZE;
+  memcpy(sk->tr, buf + 64, (size_t)P->tr);
+  const uint8_t *p = buf + 64 + P->tr;
   for (int i = 0; i < P->l; i++, p += P_LEQETA(P)) unpack_leqeta(P, sk->s1[i], p);
   for (int i = 0; i < P->k; i++, p += P_LEQETA(P)) unpack_leqeta(P, sk->s2[i], p);
   for (int i = 0; i < P->k; i++, p += POLY_T0) unpack_t0(sk->t0[i], p);
@@ -401,8 +407,8 @@ static void sk_unpack(const dparams *P, privkey *sk, const uint8_t *buf) {
 static void sk_pack(const dparams *P, const privkey *sk, uint8_t *buf) { /* dilithium.go:129-139 */
   memcpy(buf, sk->rho, 32);
   memcpy(buf + 32, sk->key, 32);
-  memcpy(buf + 64, sk->tr, TRSIZE);
-  uint8_t *p = buf + 64 + TRSIZE;
+  memcpy(buf + 64, sk->tr, (size_t)P->tr);
+  uint8_t *p = buf + 64 + P->tr;
   for (int i = 0; i < P->l; i++, p += P_LEQETA(P)) pack_leqeta(P, p, sk->s1[i]);
   for (int i = 0; i < P->k; i++, p += P_LEQETA(P)) pack_leqeta(P, p, sk->s2[i]);
   for (int i = 0; i < P->k; i++, p += POLY_T0) pack_t0(p, sk->t0[i]);
@@ -415,7 +421,7 @@ void orc_mldsa_keygen(int mode, uint8_t *pk, uint8_t *skb, const uint8_t seed[32
   uint8_t in[34], eseed[128];
   memcpy(in, seed, 32);
   in[32] = (uint8_t)P->k; in[33] = (uint8_t)P->l;
-  orc_shake256(eseed, 128, in, 34);
+  orc_shake256(eseed, 128, in, P->nist ? 34 : 32); /* dilithium.go:191-193: K, L only when NIST */
   memcpy(sk->rho, eseed, 32);
   const uint8_t *sseed = eseed + 32;
   memcpy(sk->key, eseed + 96, 32);
@@ -435,7 +441,7 @@ void orc_mldsa_keygen(int mode, uint8_t *pk, uint8_t *skb, const uint8_t seed[32
   }
   memcpy(pk, sk->rho, 32);
   for (int i = 0; i < P->k; i++) pack_t1(pk + 32 + POLY_T1 * i, t1[i]);
-  orc_shake256(sk->tr, TRSIZE, pk, (size_t)P_PK(P));
+  orc_shake256(sk->tr, (size_t)P->tr, pk, (size_t)P_PK(P));
   sk_pack(P, sk, skb);
   free(sk);
 }
@@ -448,12 +454,12 @@ static int sign_internal(const dparams *P, const privkey *sk, const uint8_t *msg
   const int K = P->k, L = P->l;
   orc_sponge h;
   orc_sponge_init(&h, 136, 0x1f);
-  orc_sponge_write(&h, sk->tr, TRSIZE);
+  orc_sponge_write(&h, sk->tr, (size_t)P->tr);
   orc_sponge_write(&h, msg, msglen);
   orc_sponge_read(&h, mu, 64);
   orc_sponge_init(&h, 136, 0x1f);
   orc_sponge_write(&h, sk->key, 32);
-  orc_sponge_write(&h, rnd, 32);
+  if (P->nist) orc_sponge_write(&h, rnd, 32); /* dilithium.go:360-362 */
   orc_sponge_write(&h, mu, 64);
   orc_sponge_read(&h, rhop, 64);
 
@@ -564,10 +570,10 @@ int orc_mldsa_verify(int mode, const uint8_t *pkb, const uint8_t *msg, size_t ms
   if (!unpack_hint(P, hint, sig + P->ctilde + L * P_LEGAMMA1(P))) goto done;
   {
     uint8_t tr[TRSIZE], mu[64], w1p[192 * KMAX], cp[64];
-    orc_shake256(tr, TRSIZE, pkb, (size_t)P_PK(P));
+    orc_shake256(tr, (size_t)P->tr, pkb, (size_t)P_PK(P));
     orc_sponge h;
     orc_sponge_init(&h, 136, 0x1f);
-    orc_sponge_write(&h, tr, TRSIZE);
+    orc_sponge_write(&h, tr, (size_t)P->tr);
     if (!internal) {
       uint8_t pre[2] = {0, (uint8_t)ctxlen};
       orc_sponge_write(&h, pre, 2);

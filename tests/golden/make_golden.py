@@ -176,6 +176,9 @@ def samplers():
         "Kyber1024": re.search(r'"Kyber1024", "([0-9a-f]{64})"', open(os.path.join(REF, "kem/kyber/kat_test.go")).read()).group(1),
         "ML-DSA-44": re.search(r'"ML-DSA-44", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
         "ML-DSA-87": re.search(r'"ML-DSA-87", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
+        "Dilithium2": re.search(r'"Dilithium2", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
+        "Dilithium3": re.search(r'"Dilithium3", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
+        "Dilithium5": re.search(r'"Dilithium5", "([0-9a-f]{64})"', open(os.path.join(REF, "sign/dilithium/kat_test.go")).read()).group(1),
     }
     dump("sampler_vectors.json.gz", out)
 

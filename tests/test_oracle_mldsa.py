@@ -160,3 +160,24 @@ def test_other_modes_pqcgenkat_hash(sampler_vectors, ps):
         f.update(("sm = %s%s\n\n" % (sig.hex().upper(), msg.hex().upper())).encode())
         assert oracle.mldsa_verify(mode, pk, msg, sig)
     assert f.hexdigest() == sampler_vectors["kat_sha256"][ps]
+
+
+@pytest.mark.parametrize("name,mode", [("Dilithium2", 2), ("Dilithium3", 3), ("Dilithium5", 5)])
+def test_round3_dilithium_pqcgenkat_hash(sampler_vectors, name, mode):
+    # sign/dilithium/kat_test.go:25-27: round-3 parameter sets (NIST = false: tr and c~ of 32 bytes, no K/L in the key
+    # seed hash, no rnd, raw message -- sign/dilithium/mode3/dilithium.go:54-77)
+    g = DRBG(bytes(range(48)))
+    f = hashlib.sha256()
+    f.update(("# %s\n\n" % name).encode())
+    _, _, sigsz = oracle.mldsa_sizes(mode)
+    for i in range(100):
+        mlen = 33 * (i + 1)
+        seed = g.fill(48)
+        msg = g.fill(mlen)
+        f.update(("count = %d\nseed = %s\nmlen = %d\nmsg = %s\n" % (i, seed.hex().upper(), mlen, msg.hex().upper())).encode())
+        pk, sk = oracle.mldsa_keygen(mode, DRBG(seed).fill(32))
+        f.update(("pk = %s\nsk = %s\nsmlen = %d\n" % (pk.hex().upper(), sk.hex().upper(), mlen + sigsz)).encode())
+        sig, _ = oracle.mldsa_sign(mode, sk, msg, internal=True)
+        f.update(("sm = %s%s\n\n" % (sig.hex().upper(), msg.hex().upper())).encode())
+        assert oracle.mldsa_verify(mode, pk, msg, sig, internal=True)
+    assert f.hexdigest() == sampler_vectors["kat_sha256"][name]

@@ -190,6 +190,7 @@ int cb200_init(int device) {
     set_error("cb200_init: device %d is sm_%d%d; this build contains only sm_100a code", device, prop.major, prop.minor);
     return CB200_ERR_NOT_INIT;
   }
+  c.sm_count = prop.multiProcessorCount;
   CB200_CUDA(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
   for (int s = 0; s < 3; s++) CB200_CUDA(cudaStreamCreateWithFlags(&c.pipe[s], cudaStreamNonBlocking));
   for (int w = 0; w < 4; w++) {

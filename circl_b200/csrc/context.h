@@ -21,6 +21,7 @@ struct ProfRec {
 struct Ctx {
   bool ready = false;
   int device = -1;
+  int sm_count = 148;           // multiprocessors of the device (sizes the persistent grids)
   cudaStream_t own = nullptr;   // library stream
   cudaStream_t cur = nullptr;   // stream used for device-pointer calls (own or user supplied)
   cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};  // host-pointer calls: H2D -> kernels -> D2H per chunk

@@ -18,6 +18,8 @@
 // yNonce advances by L every attempt; the first attempt passing all four checks wins; 576 attempts cap.
 #include <string.h>
 
+#include <algorithm>
+
 #include "../../include/circl_b200.h"
 #include "context.h"
 #include "dilithium.cuh"
@@ -28,37 +30,60 @@ namespace mldsa {
 
 using namespace dil;
 
-// Parameter sets (sign/dilithium/gen.go:80-162, NIST = true, tr = 64 bytes)
+// Parameter sets (sign/dilithium/gen.go:80-162).  44/65/87: ML-DSA (NIST = true, tr = 64 bytes); 2/3/5: the round-3
+// Dilithium2/3/5 of sign/dilithium/mode{2,3,5} (NIST = false: tr and c~ are 32 bytes, the key seed is hashed without
+// K and L, rho' = H(key || mu) without rnd, and the message is hashed as given).
 template <int MODE>
 struct Params;
 template <>
 struct Params<44> {
   static constexpr int K = 4, L = 4, ETA = 2, TAU = 39, G1BITS = 17, OMEGA = 80, CTILDE = 32;
   static constexpr uint32_t GAMMA2 = (Q - 1) / 88;
+  static constexpr int TR = 64;
+  static constexpr bool NIST = true;
 };
 template <>
 struct Params<65> {
   static constexpr int K = 6, L = 5, ETA = 4, TAU = 49, G1BITS = 19, OMEGA = 55, CTILDE = 48;
   static constexpr uint32_t GAMMA2 = (Q - 1) / 32;
+  static constexpr int TR = 64;
+  static constexpr bool NIST = true;
 };
 template <>
 struct Params<87> {
   static constexpr int K = 8, L = 7, ETA = 2, TAU = 60, G1BITS = 19, OMEGA = 75, CTILDE = 64;
   static constexpr uint32_t GAMMA2 = (Q - 1) / 32;
+  static constexpr int TR = 64;
+  static constexpr bool NIST = true;
+};
+template <>
+struct Params<2> : Params<44> {
+  static constexpr int CTILDE = 32, TR = 32;
+  static constexpr bool NIST = false;
+};
+template <>
+struct Params<3> : Params<65> {
+  static constexpr int CTILDE = 32, TR = 32;
+  static constexpr bool NIST = false;
+};
+template <>
+struct Params<5> : Params<87> {
+  static constexpr int CTILDE = 32, TR = 32;
+  static constexpr bool NIST = false;
 };
 // local aliases of the parameter set inside a templated kernel / function
 #define MLDSA_USE(P)                                                                                         \
   constexpr int K = P::K, L = P::L, ETA = P::ETA, TAU = P::TAU, BETA = P::TAU * P::ETA, OMEGA = P::OMEGA,  \
                 CTILDE = P::CTILDE, ZBITS = P::G1BITS + 1, W1BITS = 23 - P::G1BITS, POLY_ETA = (P::ETA == 2 ? 96 : 128), \
                 POLY_Z = 32 * (P::G1BITS + 1), POLY_W1 = 32 * (23 - P::G1BITS), NKEYPOLY = P::L + 2 * P::K,   \
-                OFF_S2 = OFF_S1 + POLY_ETA * P::L, OFF_T0 = OFF_S2 + POLY_ETA * P::K,                          \
+                TR = P::TR, OFF_S1 = 64 + P::TR, OFF_S2 = OFF_S1 + POLY_ETA * P::L, OFF_T0 = OFF_S2 + POLY_ETA * P::K,                          \
                 SK_BYTES = OFF_T0 + 416 * P::K, PK_BYTES = 32 + 320 * P::K,                                    \
                 SIG_BYTES = P::CTILDE + P::L * POLY_Z + P::OMEGA + P::K;                                       \
   constexpr uint32_t GAMMA1 = 1u << P::G1BITS, GAMMA2 = P::GAMMA2, ALPHA = 2 * P::GAMMA2;                     \
   (void)K; (void)L; (void)ETA; (void)TAU; (void)BETA; (void)OMEGA; (void)CTILDE; (void)ZBITS; (void)W1BITS;    \
   (void)POLY_ETA; (void)POLY_Z; (void)POLY_W1; (void)NKEYPOLY; (void)OFF_S2; (void)OFF_T0; (void)SK_BYTES;     \
-  (void)PK_BYTES; (void)SIG_BYTES; (void)GAMMA1; (void)GAMMA2; (void)ALPHA
-constexpr int OFF_KEY = 32, OFF_TR = 64, OFF_S1 = 128, POLY_T1 = 320;
+  (void)PK_BYTES; (void)SIG_BYTES; (void)GAMMA1; (void)GAMMA2; (void)ALPHA; (void)TR
+constexpr int OFF_KEY = 32, OFF_TR = 64, POLY_T1 = 320;
 constexpr int MAX_ATTEMPTS = 576;
 
 // j-th 64-bit word of PackW1(w1) (internal/pack.go:256-271) for one op, built from the byte-per-coefficient
@@ -131,8 +156,9 @@ struct Work {
   uint32_t* c;             // per op: [256] challenge polynomial, then its NTT
   uint64_t* ctilde;        // per op: 6 words
   uint32_t *hintbits, *flags, *hintcnt, *attempt;  // per op: [48], 1, 1, 1
+  uint32_t *pass, *list1, *list2;  // per op: 2 interleaved pass counters (stage 0, stage 1); survivors of response stages 0 and 1
   uint32_t* act[2];        // active lists
-  uint32_t* count;         // [2] list lengths (device)
+  uint32_t* count;         // [4] list lengths (device): act[0], act[1], list1, list2
 };
 
 // ------------------------------------------------------------------ key expansion
@@ -284,8 +310,8 @@ __global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk,
   const uint8_t* skp = sk + op * sk_stride;
   ByteSponge sp;
   sp.init();
-  for (int i = 0; i < 64; i++) sp.put(skp[OFF_TR + i]);  // mu = H(tr || M')  (dilithium.go:354-357)
-  if (!internal) {                                         // mldsa65/dilithium.go:71-79
+  for (int i = 0; i < TR; i++) sp.put(skp[OFF_TR + i]);  // mu = H(tr || M')  (dilithium.go:354-357)
+  if (!internal && P::NIST) {                              // mldsa65/dilithium.go:71-79
     sp.put(0);
     sp.put((uint8_t)ctxlen);
     for (int i = 0; i < ctxlen; i++) sp.put(ctx[i]);
@@ -303,13 +329,19 @@ __global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk,
   uint64_t a[25];
   keccak::zero(a);
 #pragma unroll
-  for (int i = 0; i < 4; i++) {
-    a[i] = keccak::ld64(skp + OFF_KEY + 8 * i);
-    a[4 + i] = rnd ? keccak::ld64(rnd + 32 * op + 8 * i) : 0;
-  }
+  for (int i = 0; i < 4; i++) a[i] = keccak::ld64(skp + OFF_KEY + 8 * i);
+  if constexpr (P::NIST) {
 #pragma unroll
-  for (int i = 0; i < 8; i++) a[8 + i] = m[i];
-  a[16] = 0x800000000000001full;
+    for (int i = 0; i < 4; i++) a[4 + i] = rnd ? keccak::ld64(rnd + 32 * op + 8 * i) : 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[8 + i] = m[i];
+    a[16] = 0x800000000000001full;
+  } else {  // round 3: rho' = H(key || mu), 96 bytes
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[4 + i] = m[i];
+    a[12] = 0x1f;
+    a[16] = 0x8000000000000000ull;
+  }
   keccak::f1600(a);
 #pragma unroll
   for (int i = 0; i < 8; i++) rhop[8 * op + i] = a[i];
@@ -465,61 +497,87 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
 }
 
 // c~ = H(mu || w1) (dilithium.go:397-401), c = SampleInBall(c~) (sample.go:299-339): thread per op.
-// With packed w1 each warp first copies the (mu, w1) rows of its 32 ops into shared memory with coalesced loads
-// (odd row stride: the per-thread absorb reads are bank-conflict free).  c never exists as 256 words in memory:
-// SampleInBall keeps it as two 256-bit masks in registers and cntt_mask_kernel expands them.
+// With packed w1 the hash input is staged through shared memory: two rate blocks at a time, each warp copies that
+// slice of the (mu || w1) rows of its 32 ops with coalesced loads into rows of odd stride, from which the per-thread
+// absorb reads are bank-conflict free.  c never exists as 256 words in memory: SampleInBall keeps it as two 256-bit
+// masks in registers and cntt_mask_kernel expands them.
 constexpr int kChThreads = 64;
 template <class P>
-constexpr int ch_row_words() {
-  return (16 + P::K * 32) | 1;
-}
+struct ChLayout {
+  static constexpr int WORDS = 8 + P::K * 4 * (23 - P::G1BITS);  // 64-bit words of mu || PackW1(w1)
+  static constexpr int FULL = WORDS / 17, REM = WORDS % 17;
+  static constexpr int BPP = 2, NPH = (FULL + BPP - 1) / BPP;     // rate blocks per phase, phases
+  static constexpr int PHW = BPP * 17 + REM;                       // 64-bit words a phase may hold
+  static constexpr int ROWP = (2 * PHW) | 1;                       // 32-bit words per row
+  static constexpr int smem = (23 - P::G1BITS) == 4 ? kChThreads * ROWP * 4 : 0;
+};
 template <class P>
 __global__ void __launch_bounds__(kChThreads) challenge_kernel(const uint32_t* __restrict__ act, size_t nact,
                                                                const uint64_t* __restrict__ mu,
                                                                const uint8_t* __restrict__ w1u, uint64_t* __restrict__ ctilde,
                                                                uint32_t* __restrict__ cmask, uint32_t* __restrict__ flags,
-                                                               uint32_t* __restrict__ hintcnt) {
+                                                               uint32_t* __restrict__ hintcnt, uint32_t* __restrict__ pass) {
   MLDSA_USE(P);
+  using CL = ChLayout<P>;
   extern __shared__ __align__(16) uint32_t rows[];
-  constexpr int ROWP = ch_row_words<P>();
+  constexpr int ROWP = CL::ROWP, WORDS = CL::WORDS, FULL = CL::FULL, REM = CL::REM, CTW = CTILDE / 8;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const size_t s0 = (size_t)blockIdx.x * kChThreads + warp * 32;
-  const uint32_t* myrow = rows + (warp * 32 + lane) * ROWP;
-  if constexpr (SignW1<P>::packed) {
-    uint32_t* wrows = rows + warp * 32 * ROWP;
-#pragma unroll 4
-    for (int t = 0; t < 32; t++) {
-      if (s0 + t < nact) {
-        const size_t o = act[s0 + t];
-        const uint32_t* m = reinterpret_cast<const uint32_t*>(mu + 8 * o);
-        const uint32_t* w = reinterpret_cast<const uint32_t*>(w1u + o * (K * 128));
-        if (lane < 16) wrows[t * ROWP + lane] = m[lane];
-#pragma unroll
-        for (int x = 0; x < K; x++) wrows[t * ROWP + 16 + 32 * x + lane] = ldg_stream32(w + 32 * x + lane);
-      }
-    }
-    __syncwarp();
-  }
+  if (s0 >= nact) return;
   const size_t s = s0 + lane;
-  if (s >= nact) return;
-  const size_t op = act[s];
+  const bool valid = s < nact;
+  const size_t op = act[valid ? s : nact - 1];
   uint64_t a[25];
   keccak::zero(a);
-  // stream = mu (8 words) || PackW1(w1) (K * POLY_W1 / 8 words), absorbed 17 words at a time
-  constexpr int WORDS = 8 + K * POLY_W1 / 8, FULL = WORDS / 17, REM = WORDS % 17, CTW = CTILDE / 8;
-  const uint8_t* w1o = w1u + op * (K * SignW1<P>::stride);
-  auto word = [&](int k) -> uint64_t {
-    if constexpr (SignW1<P>::packed) return (uint64_t)myrow[2 * k] | ((uint64_t)myrow[2 * k + 1] << 32);
-    else return (k < 8) ? mu[8 * op + k] : w1_word<P>(w1o, k - 8);
-  };
+  if constexpr (SignW1<P>::packed) {
+    uint32_t* wrows = rows + warp * 32 * ROWP;
+    const uint32_t* myrow = wrows + lane * ROWP;
 #pragma unroll 1
-  for (int b = 0; b < FULL; b++) {
+    for (int ph = 0; ph < CL::NPH; ph++) {
+      const int first = ph * CL::BPP * 17;                                       // first 64-bit word of this phase
+      const int nw = (ph == CL::NPH - 1) ? WORDS - first : CL::BPP * 17;         // 64-bit words staged
+      __syncwarp();
+      const int nrows = nact - s0 < 32 ? (int)(nact - s0) : 32;
+#pragma unroll 8
+      for (int t = 0; t < nrows; t++) {
+        const size_t ot = __shfl_sync(0xffffffffu, (uint32_t)op, t);
+        const uint32_t* m32 = reinterpret_cast<const uint32_t*>(mu + 8 * ot);
+        const uint32_t* w32 = reinterpret_cast<const uint32_t*>(w1u + ot * (K * 128));
+        for (int x = lane; x < 2 * nw; x += 32) {
+          const int g = 2 * first + x;  // 32-bit word of the stream
+          wrows[t * ROWP + x] = g < 16 ? m32[g] : ldg_stream32(w32 + (g - 16));
+        }
+      }
+      __syncwarp();
+      const int b_end = (ph + 1) * CL::BPP < FULL ? (ph + 1) * CL::BPP : FULL;
+#pragma unroll 1
+      for (int b = ph * CL::BPP; b < b_end; b++) {
+        const uint32_t* src = myrow + 2 * (17 * b - first);
 #pragma unroll
-    for (int w = 0; w < 17; w++) a[w] ^= word(17 * b + w);
-    keccak::f1600(a);
+        for (int w = 0; w < 17; w++) a[w] ^= (uint64_t)src[2 * w] | ((uint64_t)src[2 * w + 1] << 32);
+        keccak::f1600(a);
+      }
+      if (ph == CL::NPH - 1) {
+        const uint32_t* src = myrow + 2 * (17 * FULL - first);
+#pragma unroll
+        for (int w = 0; w < REM; w++) a[w] ^= (uint64_t)src[2 * w] | ((uint64_t)src[2 * w + 1] << 32);
+      }
+    }
+  } else {
+    const uint8_t* w1o = w1u + op * (K * SignW1<P>::stride);
+#pragma unroll 1
+    for (int b = 0; b < FULL; b++) {
+#pragma unroll
+      for (int w = 0; w < 17; w++) {
+        const int k = 17 * b + w;
+        a[w] ^= (k < 8) ? mu[8 * op + k] : w1_word<P>(w1o, k - 8);
+      }
+      keccak::f1600(a);
+    }
+#pragma unroll
+    for (int w = 0; w < REM; w++) a[w] ^= w1_word<P>(w1o, 17 * FULL + w - 8);
   }
-#pragma unroll
-  for (int w = 0; w < REM; w++) a[w] ^= word(17 * FULL + w);
+  if (!valid) return;
   a[REM] ^= 0x1f;
   a[16] ^= 0x8000000000000000ull;
   keccak::f1600(a);
@@ -584,8 +642,10 @@ __global__ void __launch_bounds__(kChThreads) challenge_kernel(const uint32_t* _
   cm[1] = make_uint4((uint32_t)nz[2], (uint32_t)(nz[2] >> 32), (uint32_t)nz[3], (uint32_t)(nz[3] >> 32));
   cm[2] = make_uint4((uint32_t)ng[0], (uint32_t)(ng[0] >> 32), (uint32_t)ng[1], (uint32_t)(ng[1] >> 32));
   cm[3] = make_uint4((uint32_t)ng[2], (uint32_t)(ng[2] >> 32), (uint32_t)ng[3], (uint32_t)(ng[3] >> 32));
-  flags[op] = 0;
+  flags[op] = 1;  // cleared when the op passes response stage 1
   hintcnt[op] = 0;
+  pass[2 * op] = 0;
+  pass[2 * op + 1] = 0;
 }
 
 // c-hat = NTT(c) for Sign: octet per active op; c is expanded from the SampleInBall masks
@@ -662,19 +722,24 @@ __device__ __forceinline__ uint32_t make_hint(uint32_t z0, uint32_t r1) {
 }
 
 // The three norm checks + hint (dilithium.go:407-464).  Any failed check rejects the attempt and nothing of a rejected
-// attempt is ever output, so the checks may run in any order; they run as three launches, cheapest filter first, and
-// a warp of a later stage leaves at once when an earlier stage already rejected its op (81 % of the attempts of
-// ML-DSA-65 never reach stage 2):
-//   stage 0: r0 = w0 - c s2 (K octets per op, rows of one op adjacent), kept in place of w0 for stage 2
-//   stage 1: z[0..3] = y + c s1, packed straight into the signature staging buffer (one warp per op)
-//   stage 2: z[4..L), c t0 and the hints (ceil((L - 4 + K) / 4) warps per op)
+// attempt is ever output, so the checks may run in any order; they run as three launches, cheapest filter first, each
+// over the compacted list of ops that survived the previous one (81 % of the attempts of ML-DSA-65 never reach the
+// last stage).  A unit of work is one (op, polynomial) pair on one octet; the units of a list are dealt to the octets
+// of a persistent grid with no padding between ops.
+//   stage 0: r0 = w0 - c s2, kept in place of w0 for stage 2           K units per op of the active list
+//   stage 1: z = y + c s1, packed into the signature staging buffer     L units per op of list1
+//   stage 2: c t0 and the hints                                         K units per op of list2
+// An op moves to the next list when its last unit passes (per-op counter); passing stage 1 clears flags[op], which
+// the challenge kernel set, and stage 2 sets it again on a failure, so finalize accepts exactly the ops with flags == 0.
 template <class P, int STAGE>
-__global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
-                                                       const uint32_t* __restrict__ sh, const uint32_t* __restrict__ cpoly,
-                                                       const uint32_t* __restrict__ y, uint32_t* __restrict__ w0,
-                                                       const uint8_t* __restrict__ w1u, uint8_t* __restrict__ zbuf,
-                                                       uint32_t* __restrict__ hintbits, uint32_t* __restrict__ flags,
-                                                       uint32_t* __restrict__ hintcnt, const uint32_t* __restrict__ zetas) {
+__global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restrict__ list, const uint32_t* __restrict__ count_dev,
+                                                       size_t count_host, int key_shared, const uint32_t* __restrict__ sh,
+                                                       const uint32_t* __restrict__ cpoly, const uint32_t* __restrict__ y,
+                                                       uint32_t* __restrict__ w0, const uint8_t* __restrict__ w1u,
+                                                       uint8_t* __restrict__ zbuf, uint32_t* __restrict__ hintbits,
+                                                       uint32_t* __restrict__ flags, uint32_t* __restrict__ hintcnt,
+                                                       uint32_t* __restrict__ pass, uint32_t* __restrict__ next_list,
+                                                       uint32_t* __restrict__ next_count, const uint32_t* __restrict__ zetas) {
   MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   __shared__ uint32_t izs[256];
@@ -683,54 +748,32 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
   const volatile uint32_t* ti = izs;
   const OctetCtx o = octet_ctx(tiles);
   const unsigned octmask = 0xffu << (8 * o.oct);
-  constexpr int ZB = 4;  // z polynomials checked by stage 1 (L >= 4 in every mode)
-  constexpr int ITEMS = STAGE == 0 ? K : STAGE == 1 ? ZB : (L - ZB) + K;
-  constexpr int WPO = (ITEMS + 3) / 4;  // warps per op in stages 1 and 2
-  size_t op;
-  int item;
-  bool active;
-  if constexpr (STAGE == 0) {
-    const size_t total = nact * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
-    if (base >= total) return;
-    active = base + o.oct < total;
+  constexpr int ITEMS = STAGE == 1 ? L : K;
+  const size_t total = (count_dev ? (size_t)*count_dev : count_host) * ITEMS;
+  for (size_t base = ((size_t)blockIdx.x * 4 + o.warp) * 4; base < total; base += (size_t)gridDim.x * 16) {
+    const bool active = base + o.oct < total;
     const size_t u = active ? base + o.oct : total - 1;
-    op = act[u / K];
-    item = (int)(u % K);
-  } else {
-    const size_t wi = (size_t)blockIdx.x * 4 + o.warp;
-    if (wi >= nact * WPO) return;
-    op = act[wi / WPO];
-    if (flags[op]) return;  // same op for the whole warp: rejected by an earlier stage
-    item = (int)(wi % WPO) * 4 + o.oct;
-    active = item < ITEMS;
-    if (!active) item = ITEMS - 1;
-  }
-  const uint32_t* keyp = sh + (key_shared ? 0 : op) * (NKEYPOLY * N);
-  const uint32_t* chat = cpoly + op * N;
-  uint32_t r[32];
-  bool reject = false;
-  if constexpr (STAGE == 0) {
-    const int i = item;
-    c_times(r, chat, keyp + (L + i) * N, o, ti);  // c s2[i]
-    uint32_t* w0p = w0 + (op * K + i) * N;
+    const size_t op = list[u / ITEMS];
+    const int item = (int)(u % ITEMS);
+    const uint32_t* keyp = sh + (key_shared ? 0 : op) * (NKEYPOLY * N);
+    const uint32_t* chat = cpoly + op * N;
+    uint32_t r[32];
+    bool reject = false;
+    if constexpr (STAGE == 0) {
+      const int i = item;
+      c_times(r, chat, keyp + (L + i) * N, o, ti);  // c s2[i]
+      uint32_t* w0p = w0 + (op * K + i) * N;
 #pragma unroll
-    for (int s = 0; s < 16; s++) {
-      const uint2 a = *reinterpret_cast<const uint2*>(w0p + 16 * s + 2 * o.v);
-      r[2 * s] = modq(a.x + (2 * Q - r[2 * s]));  // w0 - c s2, Normalize
-      r[2 * s + 1] = modq(a.y + (2 * Q - r[2 * s + 1]));
-      reject |= exceeds1(r[2 * s], GAMMA2 - BETA) | exceeds1(r[2 * s + 1], GAMMA2 - BETA);
-      if (active) *reinterpret_cast<uint2*>(w0p + 16 * s + 2 * o.v) = make_uint2(r[2 * s], r[2 * s + 1]);
-    }
-  } else {
-    // every octet of the warp runs the same sequence of warp-level exchanges; only the arithmetic in between differs
-    const bool is_z = STAGE == 1 || item < L - ZB;
-    const int j = STAGE == 1 ? item : (is_z ? ZB + item : 0);
-    const int i = is_z ? 0 : item - (L - ZB);
-    // the 8 hint words of row i belong to this octet alone; the exchanges inside c_times order the stores below
-    // before the atomicOr of the other lanes
-    if (STAGE == 2 && !is_z && active) hintbits[8 * K * op + 8 * i + o.v] = 0;
-    c_times(r, chat, is_z ? keyp + j * N : keyp + (L + K + i) * N, o, ti);  // c s1[j]  or  c t0[i]
-    if (is_z) {
+      for (int s = 0; s < 16; s++) {
+        const uint2 a = *reinterpret_cast<const uint2*>(w0p + 16 * s + 2 * o.v);
+        r[2 * s] = modq(a.x + (2 * Q - r[2 * s]));  // w0 - c s2, Normalize
+        r[2 * s + 1] = modq(a.y + (2 * Q - r[2 * s + 1]));
+        reject |= exceeds1(r[2 * s], GAMMA2 - BETA) | exceeds1(r[2 * s + 1], GAMMA2 - BETA);
+        if (active) *reinterpret_cast<uint2*>(w0p + 16 * s + 2 * o.v) = make_uint2(r[2 * s], r[2 * s + 1]);
+      }
+    } else if constexpr (STAGE == 1) {
+      const int j = item;
+      c_times(r, chat, keyp + j * N, o, ti);  // c s1[j]
       const uint32_t* yp = y + (op * L + j) * N;
 #pragma unroll
       for (int s = 0; s < 16; s++) {
@@ -739,8 +782,32 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
         r[2 * s + 1] = modq(r[2 * s + 1] + a.y);
         reject |= exceeds1(r[2 * s], GAMMA1 - BETA) | exceeds1(r[2 * s + 1], GAMMA1 - BETA);
       }
-    } else if constexpr (STAGE == 2) {
-      const uint32_t* r0p = w0 + (op * K + i) * N;  // w0 - c s2 from stage 0
+      // PolyPackLeGamma1 (internal/pack.go:236-252): 32 coefficients -> 20 aligned words in the staging
+      // buffer; finalize copies them into the (3309-byte strided) signature only if the attempt is accepted
+      s_to_c(r, o.tile, o.v);
+      uint32_t* zw = reinterpret_cast<uint32_t*>(zbuf + (op * L + j) * (size_t)POLY_Z) + ZBITS * o.v;
+      uint64_t accb = 0;
+      int bits = 0, ow = 0;
+#pragma unroll
+      for (int c = 0; c < 32; c++) {
+        uint32_t p = GAMMA1 - r[c];
+        p += (uint32_t)((int32_t)p >> 31) & Q;
+        accb |= (uint64_t)(p & ((1u << ZBITS) - 1)) << bits;
+        bits += ZBITS;
+        if (bits >= 32) {
+          if (active) zw[ow] = (uint32_t)accb;
+          ow++;
+          accb >>= 32;
+          bits -= 32;
+        }
+      }
+    } else {
+      const int i = item;
+      // the 8 hint words of row i belong to this octet alone; the exchanges inside c_times order these stores
+      // before the atomicOr of the other lanes
+      if (active) hintbits[8 * K * op + 8 * i + o.v] = 0;
+      c_times(r, chat, keyp + (L + K + i) * N, o, ti);  // c t0[i]
+      const uint32_t* r0p = w0 + (op * K + i) * N;        // w0 - c s2 from stage 0
       const uint8_t* w1b = w1u + (op * K + i) * SignW1<P>::stride;
       uint32_t pop = 0;
 #pragma unroll
@@ -758,30 +825,18 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
       }
       if (pop && active) atomicAdd(hintcnt + op, pop);
     }
-    // PolyPackLeGamma1 (internal/pack.go:236-252): 32 coefficients -> 20 aligned words in the staging
-    // buffer; finalize copies them into the (3309-byte strided) signature only if the attempt is accepted
-    s_to_c(r, o.tile, o.v);
-    if (is_z) {
-      uint32_t* zw = reinterpret_cast<uint32_t*>(zbuf + (op * L + j) * (size_t)POLY_Z) + ZBITS * o.v;
-      uint64_t accb = 0;
-      int bits = 0, ow = 0;
-#pragma unroll
-      for (int c = 0; c < 32; c++) {
-        uint32_t p = GAMMA1 - r[c];
-        p += (uint32_t)((int32_t)p >> 31) & Q;
-        accb |= (uint64_t)(p & ((1u << ZBITS) - 1)) << bits;
-        bits += ZBITS;
-        if (bits >= 32) {
-          if (active) zw[ow] = (uint32_t)accb;
-          ow++;
-          accb >>= 32;
-          bits -= 32;
+    reject = __any_sync(octmask, reject);
+    if (active && o.v == 0) {
+      if constexpr (STAGE == 2) {
+        if (reject) atomicOr(flags + op, 1u);
+      } else if (!reject) {
+        if (atomicAdd(pass + 2 * op, 1u) == (uint32_t)(ITEMS - 1)) {  // last unit of this op: all of them passed
+          if constexpr (STAGE == 1) flags[op] = 0;
+          next_list[atomicAdd(next_count, 1u)] = (uint32_t)op;
         }
       }
     }
   }
-  reject = __any_sync(octmask, reject);
-  if (reject && active && o.v == 0) atomicOr(flags + op, 1u);
 }
 
 // accept -> c~, z and hints into the signature; reject -> next attempt (dilithium.go:369-377,459-469).
@@ -879,8 +934,8 @@ __global__ void __launch_bounds__(128) verify_prep_kernel(const uint8_t* __restr
   }
   ByteSponge sp;
   sp.init();
-  for (int i = 0; i < 64; i++) sp.put((uint8_t)(a[i >> 3] >> (8 * (i & 7))));
-  if (!internal) {
+  for (int i = 0; i < TR; i++) sp.put((uint8_t)(a[i >> 3] >> (8 * (i & 7))));
+  if (!internal && P::NIST) {
     sp.put(0);
     sp.put((uint8_t)ctxlen);
     for (int i = 0; i < ctxlen; i++) sp.put(ctxstr[i]);
@@ -1191,7 +1246,7 @@ __global__ void __launch_bounds__(128) kg_seed_kernel(const uint8_t* __restrict_
   keccak::zero(a);
 #pragma unroll
   for (int i = 0; i < 4; i++) a[i] = sd[i];
-  a[4] = (uint64_t)K | ((uint64_t)L << 8) | (0x1full << 16);
+  a[4] = P::NIST ? ((uint64_t)K | ((uint64_t)L << 8) | (0x1full << 16)) : 0x1full;  // dilithium.go:191-193
   a[16] = 0x8000000000000000ull;
   keccak::f1600(a);
   uint64_t* pkw = reinterpret_cast<uint64_t*>(pk + op * (size_t)PK_BYTES);
@@ -1395,7 +1450,7 @@ __global__ void __launch_bounds__(128) kg_tr_kernel(const uint8_t* __restrict__ 
   keccak::f1600(a);
   uint64_t* tr = reinterpret_cast<uint64_t*>(sk + op * (size_t)SK_BYTES + OFF_TR);
 #pragma unroll
-  for (int i = 0; i < 8; i++) tr[i] = a[i];
+  for (int i = 0; i < TR / 8; i++) tr[i] = a[i];
 }
 
 template <class P>
@@ -1472,7 +1527,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
                oRh = take(n * 64), oY = take(n * L * 1024), oYh = take(n * L * 1024), oW0 = take(n * K * 1024),
                oW1 = take(n * K * SignW1<P>::stride), oCm = take(n * 64), oZ = take(n * L * POLY_Z), oC = take(n * 1024), oCt = take(n * CTILDE), oHb = take(n * 8 * K * 4),
                oFl = take(n * 4), oHc = take(n * 4), oAt = take(n * 4), oA0 = take(n * 4), oA1 = take(n * 4),
-               oCnt = take(16);
+               oPs = take(n * 8), oL1 = take(n * 4), oL2 = take(n * 4), oCnt = take(16);
   void* base = nullptr;
   int rc = ensure_work(slot, off, &base);
   if (rc) return rc;
@@ -1497,8 +1552,11 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   w.act[0] = (uint32_t*)(b + oA0);
   w.act[1] = (uint32_t*)(b + oA1);
   w.count = (uint32_t*)(b + oCnt);
+  w.pass = (uint32_t*)(b + oPs);
+  w.list1 = (uint32_t*)(b + oL1);
+  w.list2 = (uint32_t*)(b + oL2);
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
-  constexpr int kChSmem = SignW1<P>::packed ? kChThreads * ch_row_words<P>() * 4 : 0;
+  constexpr int kChSmem = ChLayout<P>::smem;
 
   static bool attr_set = false;
   if (!attr_set) {
@@ -1535,6 +1593,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     total_attempts += nact;
     const uint32_t* act = w.act[cur];
     CB200_CUDA(cudaMemsetAsync(w.count + (cur ^ 1), 0, 4, st));
+    CB200_CUDA(cudaMemsetAsync(w.count + 2, 0, 8, st));
     {
       KernelScope ks(KID_MLDSA_MASK, st);
       mask_kernel<P><<<blocks(nact * L, 128), 128, 0, st>>>(act, nact, w.rhop, w.attempt, w.y);
@@ -1550,7 +1609,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     {
       KernelScope ks(KID_MLDSA_CHALLENGE, st);
       challenge_kernel<P><<<blocks(nact, kChThreads), kChThreads, kChSmem, st>>>(act, nact, w.mu, w.w1u, w.ctilde, w.cmask,
-                                                                                 w.flags, w.hintcnt);
+                                                                                 w.flags, w.hintcnt, w.pass);
     }
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
@@ -1558,12 +1617,17 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     }
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
-      response_kernel<P, 0><<<blocks(nact * K, 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u,
-                                                                 w.zbuf, w.hintbits, w.flags, w.hintcnt, zetas);
-      response_kernel<P, 1><<<blocks(nact, 4), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u, w.zbuf,
-                                                             w.hintbits, w.flags, w.hintcnt, zetas);
-      response_kernel<P, 2><<<blocks(nact * ((L - 4 + K + 3) / 4), 4), 128, 0, st>>>(
-          act, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u, w.zbuf, w.hintbits, w.flags, w.hintcnt, zetas);
+      // persistent grids: at most 8 blocks per SM, fewer when the list is short
+      auto grid = [&](size_t units) { return (unsigned)std::min<size_t>((units + 15) / 16, (size_t)c.sm_count * 8); };
+      response_kernel<P, 0><<<grid(nact * K), 128, 0, st>>>(act, nullptr, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u,
+                                                            w.zbuf, w.hintbits, w.flags, w.hintcnt, w.pass, w.list1,
+                                                            w.count + 2, zetas);
+      response_kernel<P, 1><<<grid(nact * L), 128, 0, st>>>(w.list1, w.count + 2, 0, shared ? 1 : 0, w.sh, w.c, w.y, w.w0,
+                                                            w.w1u, w.zbuf, w.hintbits, w.flags, w.hintcnt, w.pass + 1,
+                                                            w.list2, w.count + 3, zetas);
+      response_kernel<P, 2><<<grid(nact * K), 128, 0, st>>>(w.list2, w.count + 3, 0, shared ? 1 : 0, w.sh, w.c, w.y, w.w0,
+                                                            w.w1u, w.zbuf, w.hintbits, w.flags, w.hintcnt, nullptr, nullptr,
+                                                            nullptr, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_COMPACT, st);
@@ -1595,27 +1659,45 @@ bool mode_sizes(int mode, ModeSizes* m) {
     case 44: *m = {1312, 2560, 2420}; return true;
     case 65: *m = {1952, 4032, 3309}; return true;
     case 87: *m = {2592, 4896, 4627}; return true;
+    case 2: *m = {1312, 2528, 2420}; return true;  // round-3 Dilithium2/3/5 (sign/dilithium/mode*/internal)
+    case 3: *m = {1952, 4000, 3293}; return true;
+    case 5: *m = {2592, 4864, 4595}; return true;
   }
   return false;
 }
 
 template <class... A>
 int dispatch_sign(int mode, A... a) {
-  return mode == 44   ? mldsa::sign_device<mldsa::Params<44>>(a...)
-         : mode == 65 ? mldsa::sign_device<mldsa::Params<65>>(a...)
-                      : mldsa::sign_device<mldsa::Params<87>>(a...);
+  switch (mode) {
+    case 44: return mldsa::sign_device<mldsa::Params<44>>(a...);
+    case 65: return mldsa::sign_device<mldsa::Params<65>>(a...);
+    case 87: return mldsa::sign_device<mldsa::Params<87>>(a...);
+    case 2: return mldsa::sign_device<mldsa::Params<2>>(a...);
+    case 3: return mldsa::sign_device<mldsa::Params<3>>(a...);
+    default: return mldsa::sign_device<mldsa::Params<5>>(a...);
+  }
 }
 template <class... A>
 int dispatch_verify(int mode, A... a) {
-  return mode == 44   ? mldsa::verify_device<mldsa::Params<44>>(a...)
-         : mode == 65 ? mldsa::verify_device<mldsa::Params<65>>(a...)
-                      : mldsa::verify_device<mldsa::Params<87>>(a...);
+  switch (mode) {
+    case 44: return mldsa::verify_device<mldsa::Params<44>>(a...);
+    case 65: return mldsa::verify_device<mldsa::Params<65>>(a...);
+    case 87: return mldsa::verify_device<mldsa::Params<87>>(a...);
+    case 2: return mldsa::verify_device<mldsa::Params<2>>(a...);
+    case 3: return mldsa::verify_device<mldsa::Params<3>>(a...);
+    default: return mldsa::verify_device<mldsa::Params<5>>(a...);
+  }
 }
 template <class... A>
 int dispatch_keygen(int mode, A... a) {
-  return mode == 44   ? mldsa::keygen_device<mldsa::Params<44>>(a...)
-         : mode == 65 ? mldsa::keygen_device<mldsa::Params<65>>(a...)
-                      : mldsa::keygen_device<mldsa::Params<87>>(a...);
+  switch (mode) {
+    case 44: return mldsa::keygen_device<mldsa::Params<44>>(a...);
+    case 65: return mldsa::keygen_device<mldsa::Params<65>>(a...);
+    case 87: return mldsa::keygen_device<mldsa::Params<87>>(a...);
+    case 2: return mldsa::keygen_device<mldsa::Params<2>>(a...);
+    case 3: return mldsa::keygen_device<mldsa::Params<3>>(a...);
+    default: return mldsa::keygen_device<mldsa::Params<5>>(a...);
+  }
 }
 
 }  // namespace
@@ -1642,10 +1724,14 @@ int cb200_mldsa_sign(int mode, const uint8_t* sk, size_t sk_stride, const uint8_
   if (rc) return rc;
   ModeSizes ms;
   if (!mode_sizes(mode, &ms)) {
-    set_error("cb200_mldsa_sign: mode must be 44, 65 or 87, got %d", mode);
+    set_error("cb200_mldsa_sign: mode must be 44, 65, 87 (ML-DSA) or 2, 3, 5 (round-3 Dilithium), got %d", mode);
     return CB200_ERR_ARG;
   }
   if (n == 0) return 0;
+  if (mode < 10 && ctxlen) {  // sign.ErrContextNotSupported (sign/dilithium/mode3/dilithium.go:227-229)
+    set_error("cb200_mldsa_sign: round-3 Dilithium takes no context string");
+    return CB200_ERR_ARG;
+  }
   if (!sk || !msgs || !msg_off || !sig || ctxlen > 255 || (ctxlen && !context) || (sk_stride != 0 && sk_stride < ms.sk)) {
     set_error("cb200_mldsa_sign: bad argument");  // len(ctx) > 255 is sign.ErrContextTooLong in the Go shim
     return CB200_ERR_ARG;
@@ -1723,10 +1809,14 @@ int cb200_mldsa_verify(int mode, const uint8_t* pk, size_t pk_stride, const uint
   if (rc) return rc;
   ModeSizes ms;
   if (!mode_sizes(mode, &ms)) {
-    set_error("cb200_mldsa_verify: mode must be 44, 65 or 87, got %d", mode);
+    set_error("cb200_mldsa_verify: mode must be 44, 65, 87 (ML-DSA) or 2, 3, 5 (round-3 Dilithium), got %d", mode);
     return CB200_ERR_ARG;
   }
   if (n == 0) return 0;
+  if (mode < 10 && ctxlen) {
+    set_error("cb200_mldsa_verify: round-3 Dilithium takes no context string");
+    return CB200_ERR_ARG;
+  }
   if (!pk || !msgs || !msg_off || !sig || !ok || ctxlen > 255 || (ctxlen && !context) ||
       (pk_stride != 0 && pk_stride < ms.pk)) {
     set_error("cb200_mldsa_verify: bad argument");
@@ -1788,7 +1878,7 @@ int cb200_mldsa_keygen(int mode, const uint8_t* seeds, uint8_t* pk, uint8_t* sk,
   if (rc) return rc;
   ModeSizes ms;
   if (!mode_sizes(mode, &ms)) {
-    set_error("cb200_mldsa_keygen: mode must be 44, 65 or 87, got %d", mode);
+    set_error("cb200_mldsa_keygen: mode must be 44, 65, 87 (ML-DSA) or 2, 3, 5 (round-3 Dilithium), got %d", mode);
     return CB200_ERR_ARG;
   }
   if (n == 0) return 0;

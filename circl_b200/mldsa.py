@@ -20,6 +20,10 @@ class SignError(Exception):
     pass
 
 
+class ErrContextNotSupported(SignError):   # sign.ErrContextNotSupported (round-3 Dilithium, mode3/dilithium.go:227-229)
+    pass
+
+
 class ErrContextTooLong(SignError):   # sign.ErrContextTooLong
     pass
 
@@ -68,7 +72,8 @@ class PrivateKey:
 
 
 class Scheme:
-    """sign.Scheme for one parameter set (mode 44, 65 or 87; sign/dilithium/gen.go:80-162)."""
+    """sign.Scheme for one parameter set (sign/dilithium/gen.go:80-162): mode 44, 65, 87 = ML-DSA; mode 2, 3, 5 = the
+    round-3 Dilithium2/3/5 of sign/dilithium/mode{2,3,5} (no context string, no rnd, 32-byte tr and c~)."""
 
     def __init__(self, name: str = "ML-DSA-65", mode: int = 65):
         self._name, self._mode = name, mode
@@ -77,19 +82,19 @@ class Scheme:
         return self._name
 
     def PublicKeySize(self) -> int:
-        return {44: 1312, 65: 1952, 87: 2592}[self._mode]
+        return {44: 1312, 65: 1952, 87: 2592, 2: 1312, 3: 1952, 5: 2592}[self._mode]
 
     def PrivateKeySize(self) -> int:
-        return {44: 2560, 65: 4032, 87: 4896}[self._mode]
+        return {44: 2560, 65: 4032, 87: 4896, 2: 2528, 3: 4000, 5: 4864}[self._mode]
 
     def SignatureSize(self) -> int:
-        return {44: 2420, 65: 3309, 87: 4627}[self._mode]
+        return {44: 2420, 65: 3309, 87: 4627, 2: 2420, 3: 3293, 5: 4595}[self._mode]
 
     def SeedSize(self) -> int:
         return 32
 
     def SupportsContext(self) -> bool:
-        return True
+        return self._mode > 10  # sign/dilithium/mode3/dilithium.go:208-210: round 3 has no context
 
     def UnmarshalBinaryPrivateKey(self, buf: bytes) -> PrivateKey:
         if len(buf) != self.PrivateKeySize():
@@ -107,6 +112,8 @@ class Scheme:
         """Batched Sign.  sks: one PrivateKey (shared, expanded once) or an (n, 4032) uint8 array
         (expanded on the device per op).  messages: list of bytes.  rnd: None (deterministic) or
         (n, 32) uint8.  internal=True selects ML-DSA.Sign_internal (no context framing; ACVP)."""
+        if ctx and not self.SupportsContext():
+            raise ErrContextNotSupported("sign: context not supported")
         if len(ctx) > 255:
             raise ErrContextTooLong("sign: context string too long")
         n = len(messages)
@@ -166,6 +173,8 @@ class Scheme:
         if not isinstance(pk, PublicKey):
             raise TypeError("sign: wrong public key type")
         ctx = opts.Context if opts is not None else b""
+        if ctx and not self.SupportsContext():
+            raise ErrContextNotSupported("sign: context not supported")
         if len(ctx) > 255 or len(signature) != self.SignatureSize():
             return False  # dilithium.go:116-118, internal/dilithium.go:82-84
         return bool(self.VerifyBatch(pk, [message], np.frombuffer(signature, dtype=np.uint8).reshape(1, -1), ctx=ctx)[0])
@@ -194,7 +203,8 @@ class Scheme:
         return ok.astype(bool)
 
 
-_SCHEMES = {"ml-dsa-44": Scheme("ML-DSA-44", 44), "ml-dsa-65": Scheme("ML-DSA-65", 65), "ml-dsa-87": Scheme("ML-DSA-87", 87)}
+_SCHEMES = {"ml-dsa-44": Scheme("ML-DSA-44", 44), "ml-dsa-65": Scheme("ML-DSA-65", 65), "ml-dsa-87": Scheme("ML-DSA-87", 87),
+            "dilithium2": Scheme("Dilithium2", 2), "dilithium3": Scheme("Dilithium3", 3), "dilithium5": Scheme("Dilithium5", 5)}
 
 
 def ByName(name: str):

@@ -75,9 +75,9 @@ class PrivateKey {  // kem.PrivateKey (kem/kem.go:22-30)
   Bytes packed_;
 };
 
-class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024
+class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024 and round-3 Kyber512/768/1024
  public:
-  Scheme(std::string name, int k) : name_(std::move(name)), k_(k) {}
+  Scheme(std::string name, int k, bool round3 = false) : name_(std::move(name)), k_(k), round3_(round3) {}
   const std::string& Name() const { return name_; }
   size_t CiphertextSize() const { return cb200_mlkem_ciphertext_size(k_); }
   size_t SharedKeySize() const { return 32; }
@@ -89,7 +89,8 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024
   std::pair<PublicKey, PrivateKey> DeriveKeyPair(const Bytes& seed) const {  // kyber.go:337-346
     if (seed.size() != SeedSize()) throw std::logic_error("kem: invalid seed size");  // Go panics here
     Bytes ek(PublicKeySize()), dk(PrivateKeySize());
-    check(cb200_mlkem_keygen(k_, seed.data(), ek.data(), dk.data(), 1));
+    check(round3_ ? cb200_kyber_kem_keygen(k_, seed.data(), ek.data(), dk.data(), 1)
+                  : cb200_mlkem_keygen(k_, seed.data(), ek.data(), dk.data(), 1));
     return {PublicKey(this, std::move(ek)), PrivateKey(this, std::move(dk))};
   }
   std::pair<PublicKey, PrivateKey> GenerateKeyPair() const {  // kyber.go:281-283
@@ -110,7 +111,8 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024
     if (seed.size() != EncapsulationSeedSize()) throw ErrSeedSize();
     if (pk.GetScheme() != this) throw ErrTypeMismatch();
     Bytes ct(CiphertextSize()), ss(32);
-    check(cb200_mlkem_encaps(k_, pk.MarshalBinary().data(), 0, seed.data(), ct.data(), ss.data(), nullptr, 1));
+    check(round3_ ? cb200_kyber_kem_encaps(k_, pk.MarshalBinary().data(), 0, seed.data(), ct.data(), ss.data(), 1)
+                  : cb200_mlkem_encaps(k_, pk.MarshalBinary().data(), 0, seed.data(), ct.data(), ss.data(), nullptr, 1));
     return {std::move(ct), std::move(ss)};
   }
   std::pair<Bytes, Bytes> Encapsulate(const PublicKey& pk) const {  // kyber.go:348-357
@@ -122,7 +124,8 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024
     if (sk.GetScheme() != this) throw ErrTypeMismatch();
     if (ct.size() != CiphertextSize()) throw ErrCiphertextSize();
     Bytes ss(32);
-    check(cb200_mlkem_decaps(k_, sk.MarshalBinary().data(), 0, ct.data(), ss.data(), nullptr, 1));
+    check(round3_ ? cb200_kyber_kem_decaps(k_, sk.MarshalBinary().data(), 0, ct.data(), ss.data(), 1)
+                  : cb200_mlkem_decaps(k_, sk.MarshalBinary().data(), 0, ct.data(), ss.data(), nullptr, 1));
     return ss;
   }
   // ---- batch entry points (keys: one packed key = shared, or n keys back to back)
@@ -133,7 +136,8 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024
     if (!shared && eks.size() != n * PublicKeySize()) throw ErrPubKeySize();
     cts.resize(n * CiphertextSize());
     sss.resize(n * 32);
-    check(cb200_mlkem_encaps(k_, eks.data(), shared ? 0 : PublicKeySize(), seeds.data(), cts.data(), sss.data(), nullptr, n));
+    check(round3_ ? cb200_kyber_kem_encaps(k_, eks.data(), shared ? 0 : PublicKeySize(), seeds.data(), cts.data(), sss.data(), n)
+                  : cb200_mlkem_encaps(k_, eks.data(), shared ? 0 : PublicKeySize(), seeds.data(), cts.data(), sss.data(), nullptr, n));
   }
   void DecapsulateBatch(const Bytes& dks, const Bytes& cts, Bytes& sss) const {
     if (cts.size() % CiphertextSize()) throw ErrCiphertextSize();
@@ -141,14 +145,16 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024
     const bool shared = dks.size() == PrivateKeySize();
     if (!shared && dks.size() != n * PrivateKeySize()) throw ErrPrivKeySize();
     sss.resize(n * 32);
-    check(cb200_mlkem_decaps(k_, dks.data(), shared ? 0 : PrivateKeySize(), cts.data(), sss.data(), nullptr, n));
+    check(round3_ ? cb200_kyber_kem_decaps(k_, dks.data(), shared ? 0 : PrivateKeySize(), cts.data(), sss.data(), n)
+                  : cb200_mlkem_decaps(k_, dks.data(), shared ? 0 : PrivateKeySize(), cts.data(), sss.data(), nullptr, n));
   }
   void DeriveKeyPairBatch(const Bytes& seeds, Bytes& eks, Bytes& dks) const {
     if (seeds.size() % 64) throw ErrSeedSize();
     const size_t n = seeds.size() / 64;
     eks.resize(n * PublicKeySize());
     dks.resize(n * PrivateKeySize());
-    check(cb200_mlkem_keygen(k_, seeds.data(), eks.data(), dks.data(), n));
+    check(round3_ ? cb200_kyber_kem_keygen(k_, seeds.data(), eks.data(), dks.data(), n)
+                  : cb200_mlkem_keygen(k_, seeds.data(), eks.data(), dks.data(), n));
   }
   int k() const { return k_; }
 
@@ -162,6 +168,7 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024
   }
   std::string name_;
   int k_;
+  bool round3_;
 };
 
 inline PublicKey PrivateKey::Public() const {
@@ -175,7 +182,8 @@ inline std::string lower(std::string s) {
 }
 inline const std::vector<const Scheme*>& All() {  // kem/schemes/schemes.go:75
   static const Scheme s512("ML-KEM-512", 2), s768("ML-KEM-768", 3), s1024("ML-KEM-1024", 4);
-  static const std::vector<const Scheme*> all = {&s512, &s768, &s1024};
+  static const Scheme k512("Kyber512", 2, true), k768("Kyber768", 3, true), k1024("Kyber1024", 4, true);
+  static const std::vector<const Scheme*> all = {&s512, &s768, &s1024, &k512, &k768, &k1024};
   return all;
 }
 inline const Scheme* ByName(const std::string& name) {  // kem/schemes/schemes.go:70 (nullptr = no such scheme)
@@ -189,6 +197,7 @@ inline const Scheme* ByName(const std::string& name) {  // kem/schemes/schemes.g
 namespace sign {
 
 struct ErrContextTooLong : Error { ErrContextTooLong() : Error("sign: context string too long") {} };
+struct ErrContextNotSupported : Error { ErrContextNotSupported() : Error("sign: context not supported") {} };
 struct ErrPubKeySize : Error { ErrPubKeySize() : Error("sign: invalid public key size") {} };
 struct ErrPrivKeySize : Error { ErrPrivKeySize() : Error("sign: invalid private key size") {} };
 struct ErrSeedSize : Error { ErrSeedSize() : Error("sign: invalid seed size") {} };
@@ -221,7 +230,7 @@ class PrivateKey {
   Bytes packed_;
 };
 
-class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-44 / ML-DSA-65 / ML-DSA-87
+class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-44/65/87 (modes 44, 65, 87) and round-3 Dilithium2/3/5 (2, 3, 5)
  public:
   Scheme(std::string name, int mode) : name_(std::move(name)), mode_(mode) {}
   const std::string& Name() const { return name_; }
@@ -229,7 +238,7 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-44 / ML-DSA-65 / 
   size_t PrivateKeySize() const { return cb200_mldsa_private_key_size(mode_); }
   size_t SignatureSize() const { return cb200_mldsa_signature_size(mode_); }
   size_t SeedSize() const { return 32; }
-  bool SupportsContext() const { return true; }
+  bool SupportsContext() const { return mode_ > 10; }  // round 3: sign.ErrContextNotSupported
 
   std::pair<PublicKey, PrivateKey> DeriveKey(const Bytes& seed) const {  // dilithium.go:266-276
     if (seed.size() != SeedSize()) throw std::logic_error("sign: invalid seed size");  // Go panics here
@@ -253,6 +262,7 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-44 / ML-DSA-65 / 
   // deterministic signing, as sign.Scheme.Sign does (dilithium.go:282-303)
   Bytes Sign(const PrivateKey& sk, const Bytes& msg, const SignatureOpts* opts = nullptr) const {
     const std::string ctx = opts ? opts->Context : std::string();
+    if (!ctx.empty() && !SupportsContext()) throw ErrContextNotSupported();
     if (ctx.size() > 255) throw ErrContextTooLong();
     Bytes sig(SignatureSize());
     const uint64_t off[2] = {0, msg.size()};
@@ -275,6 +285,7 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-44 / ML-DSA-65 / 
   }
   // batch: messages back to back with n+1 offsets; sks: one key (shared) or n keys
   void SignBatch(const Bytes& sks, const Bytes& msgs, const std::vector<uint64_t>& off, const std::string& ctx, Bytes& sigs) const {
+    if (!ctx.empty() && !SupportsContext()) throw ErrContextNotSupported();
     if (ctx.size() > 255) throw ErrContextTooLong();
     const size_t n = off.size() - 1;
     const bool shared = sks.size() == PrivateKeySize();
@@ -298,7 +309,8 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-44 / ML-DSA-65 / 
 
 inline const std::vector<const Scheme*>& All() {
   static const Scheme s44("ML-DSA-44", 44), s65("ML-DSA-65", 65), s87("ML-DSA-87", 87);
-  static const std::vector<const Scheme*> all = {&s44, &s65, &s87};
+  static const Scheme d2("Dilithium2", 2), d3("Dilithium3", 3), d5("Dilithium5", 5);
+  static const std::vector<const Scheme*> all = {&s44, &s65, &s87, &d2, &d3, &d5};
   return all;
 }
 inline const Scheme* ByName(const std::string& name) {  // sign/schemes/schemes.go:69 (nullptr = no such scheme)

@@ -541,7 +541,7 @@ int orc_mldsa_sign(int mode, uint8_t *sig, const uint8_t *skb, const uint8_t *ms
   privkey *sk = (privkey *)malloc(sizeof(privkey));
   sk_unpack(P, sk, skb);
   int rc;
-  if (internal) {
+  if (internal || !P->nist) { /* round 3 signs the message as given (sign/dilithium/mode3/dilithium.go:54-64) */
     rc = sign_internal(P, sk, msg, msglen, rnd, sig);
   } else {
     uint8_t *m = (uint8_t *)malloc(2 + ctxlen + msglen);
@@ -574,7 +574,7 @@ int orc_mldsa_verify(int mode, const uint8_t *pkb, const uint8_t *msg, size_t ms
     orc_sponge h;
     orc_sponge_init(&h, 136, 0x1f);
     orc_sponge_write(&h, tr, (size_t)P->tr);
-    if (!internal) {
+    if (!internal && P->nist) {
       uint8_t pre[2] = {0, (uint8_t)ctxlen};
       orc_sponge_write(&h, pre, 2);
       orc_sponge_write(&h, ctx, ctxlen);
@@ -639,7 +639,9 @@ static void *sign_worker(void *arg) {
     uint8_t *fm = (uint8_t *)malloc(2 + mlen);
     fm[0] = 0; fm[1] = 0;
     memcpy(fm + 2, m, mlen);
-    int a = sign_internal(j->P, sk, fm, 2 + mlen, j->rnd ? j->rnd + 32 * i : zero, j->sig + i * (size_t)P_SIG(j->P));
+    const int pre = j->P->nist ? 0 : 2; /* round 3: no framing */
+    int a = sign_internal(j->P, sk, fm + pre, 2 + mlen - pre, j->rnd ? j->rnd + 32 * i : zero,
+                          j->sig + i * (size_t)P_SIG(j->P));
     free(fm);
     if (a < 0) j->fails++; else j->attempts += a;
   }

@@ -96,6 +96,36 @@ int main() {
     REQUIRE(s2.size() == o->SignatureSize() && o->Verify(ok2.first, msg, s2));
   }
   REQUIRE(sign::ByName("ML-DSA-99") == nullptr);
+  // round-3 wrappers (kem/kyber/kyber768, sign/dilithium/mode3): same classes, other entry points / parameter sets
+  for (const char* name : {"Kyber512", "kyber768", "Kyber1024"}) {
+    const kem::Scheme* s = kem::ByName(name);
+    REQUIRE(s != nullptr);
+    Bytes seed(s->SeedSize()), eseed(s->EncapsulationSeedSize());
+    for (size_t i = 0; i < seed.size(); i++) seed[i] = (uint8_t)(i * 11 + s->k());
+    for (size_t i = 0; i < eseed.size(); i++) eseed[i] = (uint8_t)(i ^ 0x5a);
+    auto kp = s->DeriveKeyPair(seed);
+    auto enc = s->EncapsulateDeterministically(kp.first, eseed);
+    REQUIRE(s->Decapsulate(kp.second, enc.first) == enc.second);
+    printf("scheme=%s\n", s->Name().c_str());
+    hex("ek", kp.first.MarshalBinary());
+    hex("dk", kp.second.MarshalBinary());
+    hex("ct", enc.first);
+    hex("ss", enc.second);
+  }
+  {
+    const sign::Scheme* r3 = sign::ByName("dilithium3");
+    REQUIRE(r3 != nullptr && !r3->SupportsContext() && r3->SignatureSize() == 3293);
+    auto k3 = r3->DeriveKey(dseed);
+    Bytes s3 = r3->Sign(k3.second, msg);
+    REQUIRE(r3->Verify(k3.first, msg, s3));
+    threw = false;
+    try { r3->Sign(k3.second, msg, &opts); } catch (const sign::ErrContextNotSupported&) { threw = true; }
+    REQUIRE(threw);
+    printf("scheme=%s\n", r3->Name().c_str());
+    hex("pk", k3.first.MarshalBinary());
+    hex("sk", k3.second.MarshalBinary());
+    hex("sig", s3);
+  }
   printf("scheme=%s\n", d->Name().c_str());
   hex("pk", dk.first.MarshalBinary());
   hex("sk", dk.second.MarshalBinary());

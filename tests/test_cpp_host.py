@@ -54,3 +54,14 @@ def test_cpp_host_layer_matches_oracle():
     b = blocks["ML-DSA-65"]
     assert (b["pk"], b["sk"]) == (pk, sk)
     assert b["sig"] == oracle.mldsa65_sign(sk, b"hello", ctx=b"ctx")[0]
+    for name, k in (("Kyber512", 2), ("Kyber768", 3), ("Kyber1024", 4)):
+        seed = bytes((i * 11 + k) & 0xFF for i in range(64))
+        eseed = bytes(i ^ 0x5A for i in range(32))
+        ek, dk = oracle.kyber_kem_keygen(k, seed)
+        b = blocks[name]
+        assert (b["ek"], b["dk"]) == (ek, dk)
+        assert (b["ct"], b["ss"]) == oracle.kyber_kem_encaps(k, ek, eseed)
+    pk, sk = oracle.mldsa_keygen(3, dseed)
+    b = blocks["Dilithium3"]
+    assert (b["pk"], b["sk"]) == (pk, sk)
+    assert b["sig"] == oracle.mldsa_sign(3, sk, b"hello")[0]

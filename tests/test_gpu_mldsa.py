@@ -214,3 +214,60 @@ def test_other_modes_vs_oracle_and_roundtrip(cb, ps):
     got = scheme.VerifyBatch(pk, msgs, bad, ctx=b"c")
     assert got[:20].tolist() == [oracle.mldsa_verify(mode, pk[i].tobytes(), msgs[i], bad[i].tobytes(), ctx=b"c") for i in range(20)]
     assert not got.any()
+
+
+ROUND3 = {"Dilithium2": 2, "Dilithium3": 3, "Dilithium5": 5}
+
+
+@pytest.mark.parametrize("ps", list(ROUND3))
+def test_round3_dilithium_pqcsignkat_transcript_on_gpu(cb, sampler_vectors, ps):
+    # sign/dilithium/kat_test.go:18-100 with every key pair and signature computed by the CUDA path in three batches
+    from nist_drbg import DRBG
+    from circl_b200 import mldsa
+    scheme = mldsa.ByName(ps)
+    assert scheme.Name() == ps and not scheme.SupportsContext()
+    g = DRBG(bytes(range(48)))
+    seeds, msgs, eseeds = [], [], []
+    for i in range(100):
+        seeds.append(g.fill(48))
+        msgs.append(g.fill(33 * (i + 1)))
+        eseeds.append(DRBG(seeds[-1]).fill(32))
+    pk, sk = scheme.DeriveKeyBatch(np.frombuffer(b"".join(eseeds), dtype=np.uint8).reshape(100, 32))
+    sig = scheme.SignBatch(sk, msgs)
+    assert scheme.VerifyBatch(pk, msgs, sig).all()
+    f = hashlib.sha256()
+    f.update(("# %s\n\n" % ps).encode())
+    for i in range(100):
+        mlen = len(msgs[i])
+        f.update(("count = %d\nseed = %s\nmlen = %d\nmsg = %s\n" % (i, seeds[i].hex().upper(), mlen, msgs[i].hex().upper())).encode())
+        f.update(("pk = %s\nsk = %s\nsmlen = %d\n" % (pk[i].tobytes().hex().upper(), sk[i].tobytes().hex().upper(),
+                                                     mlen + scheme.SignatureSize())).encode())
+        f.update(("sm = %s%s\n\n" % (sig[i].tobytes().hex().upper(), msgs[i].hex().upper())).encode())
+    assert f.hexdigest() == sampler_vectors["kat_sha256"][ps]
+
+
+@pytest.mark.parametrize("ps", list(ROUND3))
+def test_round3_dilithium_vs_oracle(cb, ps):
+    import oracle
+    from circl_b200 import mldsa
+    mode, scheme = ROUND3[ps], mldsa.ByName(ps)
+    n = 300
+    seeds = np.frombuffer(hashlib.shake_256(ps.encode()).digest(32 * n), dtype=np.uint8).reshape(n, 32)
+    pk, sk = scheme.DeriveKeyBatch(seeds)
+    msgs = [_h(9, i, 1 + i % 200) for i in range(n)]
+    sig, attempts = scheme.SignBatch(sk, msgs, return_attempts=True)
+    want, want_attempts = oracle.mldsa_sign_batch(mode, sk, msgs, nthreads=8)
+    assert np.array_equal(sig, want) and attempts == want_attempts
+    for i in range(0, n, 59):
+        assert (pk[i].tobytes(), sk[i].tobytes()) == oracle.mldsa_keygen(mode, seeds[i].tobytes())
+    # one shared key, single calls, tampering
+    p0, s0 = scheme.DeriveKey(seeds[0].tobytes())
+    one = scheme.Sign(s0, b"round three")
+    assert one == oracle.mldsa_sign(mode, s0.MarshalBinary(), b"round three")[0]
+    assert scheme.Verify(p0, b"round three", one) and not scheme.Verify(p0, b"round thre3", one)
+    bad = sig.copy()
+    bad[:, 40] ^= 1
+    got = scheme.VerifyBatch(pk, msgs, bad)
+    assert got[:16].tolist() == [oracle.mldsa_verify(mode, pk[i].tobytes(), msgs[i], bad[i].tobytes()) for i in range(16)]
+    with pytest.raises(mldsa.ErrContextNotSupported):
+        scheme.Sign(s0, b"m", mldsa.SignatureOpts(Context=b"ctx"))

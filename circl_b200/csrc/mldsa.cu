@@ -444,54 +444,102 @@ __device__ __forceinline__ void decompose(uint32_t a, uint32_t& a0plusq, uint32_
   a0plusq += (uint32_t)((int32_t)(a0plusq - (Q - 1) / 2) >> 31) & Q;
 }
 
-// w[i] = InvNTT(ReduceLe2Q(A[i] . yh)), NormalizeAssumingLe2Q, Decompose (dilithium.go:386-394): octet per (op, i)
+// w[i] = InvNTT(ReduceLe2Q(A[i] . yh)), NormalizeAssumingLe2Q, Decompose (dilithium.go:386-394).
+// A unit of work is one row (op, i); the units are dealt to the octets of a persistent grid, adjacent octets taking
+// adjacent rows so that the K rows of an op read its y-hat while it is hot in L2.  The row of A -- L polynomials of
+// 1 KB, 30 KB per op and by far the largest stream of the signing loop -- does not pass through registers: lane 0 of
+// each octet keeps kWSlots 1 KB bulk copies (TMA engine, one mbarrier per slot) in flight into the octet's ring in
+// shared memory, always kWSlots polynomials ahead of the arithmetic, also across the end of a row, so the DRAM
+// latency of the next row hides behind the inverse NTT and Decompose of the current one.
+constexpr int kWSlots = 3;
+constexpr int kWSmem = 16 * kWSlots * 1024 + 16 * kPolyWords * 4 + 16 * kWSlots * 8;
 template <class P>
 __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
                                                 const uint32_t* __restrict__ A, const uint32_t* __restrict__ yh,
                                                 uint32_t* __restrict__ w0, uint8_t* __restrict__ w1u,
                                                 const uint32_t* __restrict__ zetas) {
   MLDSA_USE(P);
-  __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
-  const OctetCtx o = octet_ctx(tiles);
-  const size_t total = nact * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
-  if (base >= total) return;
-  const bool active = base + o.oct < total;
-  const size_t u = active ? base + o.oct : total - 1;
-  const size_t op = act[u / K];  // the K rows of one op sit next to each other: y-hat is read from DRAM once
-  const int i = (int)(u % K);
-  const uint32_t* Ai = A + ((key_shared ? 0 : op) * (K * L) + i * L) * N;
-  uint32_t acc[32];
+  extern __shared__ __align__(128) uint8_t wsm[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7, ob = warp * 4 + oct;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(wsm) + ob * (kWSlots * 256);
+  uint32_t* tile = reinterpret_cast<uint32_t*>(wsm + 16 * kWSlots * 1024) + ob * kPolyWords;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 16 * kWSlots * 1024 + 16 * kPolyWords * 4) + ob * kWSlots;
+  if (v == 0) {
 #pragma unroll
-  for (int c = 0; c < 32; c++) acc[c] = 0;
-#pragma unroll 1
-  for (int j = 0; j < L; j++) {  // coalesced "I" layout loads (128 contiguous bytes per octet and instruction)
-    uint4 x[8], z[8];
-    gload_I_ro(Ai + j * N, o.v, x);
-    gload_I(yh + (op * L + j) * N, o.v, z);
-#pragma unroll
-    for (int c = 0; c < 8; c++) {
-      acc[4 * c] += mont_mul(x[c].x, z[c].x);
-      acc[4 * c + 1] += mont_mul(x[c].y, z[c].y);
-      acc[4 * c + 2] += mont_mul(x[c].z, z[c].z);
-      acc[4 * c + 3] += mont_mul(x[c].w, z[c].w);
-    }
+    for (int q = 0; q < kWSlots; q++) mbar_init(bars + q, 1);
+    fence_barrier_init();
   }
-#pragma unroll
-  for (int c = 0; c < 32; c++) acc[c] = reduce_le2q(acc[c]);
-  i_to_c(acc, o.tile, o.v);
+  __syncthreads();
+  const size_t total = nact * K, G = (size_t)gridDim.x * 16, first = ((size_t)blockIdx.x * 4 + warp) * 4;
+  if (first >= total) return;
+  const size_t n_it = (total - first + G - 1) / G;  // the same for the four octets of a warp
+  const size_t n_chunks = n_it * L;
+  auto unit = [&](size_t it) {
+    const size_t u = first + it * G + oct;
+    return u < total ? u : total - 1;  // octets past the end repeat the last unit and store nothing
+  };
+  auto issue = [&](size_t c) {  // lane 0 of the octet: fetch polynomial c % L of row unit(c / L) into slot c % kWSlots
+    const size_t u = unit(c / L);
+    const size_t op = act[u / K];
+    const uint32_t* src = A + ((key_shared ? 0 : op) * (size_t)(K * L) + (u % K) * L + c % L) * N;
+    uint64_t* bar = bars + c % kWSlots;
+    mbar_expect_tx(bar, 1024);
+    bulk_g2s(ring + (c % kWSlots) * 256, src, 1024, bar);
+  };
+  if (v == 0)
+    for (size_t c = 0; c < (size_t)kWSlots && c < n_chunks; c++) issue(c);
   LaneTw t;
-  load_lane_tw_inv(t, zetas + 256, o.v);
-  invntt_octet(acc, o.tile, o.v, t);  // -> S layout: acc[2s+b] = coefficient 16s + 2v + b
-  uint32_t* w0p = w0 + (op * K + i) * N;
-  uint8_t* w1b = w1u + (op * K + i) * SignW1<P>::stride;
+  load_lane_tw_inv(t, zetas + 256, v);
+  size_t c = 0;
+  uint4 zc[8];  // y-hat polynomial of the chunk about to be multiplied, always loaded one chunk ahead
+  gload_I(yh + ((size_t)act[unit(0) / K] * L) * N, v, zc);
+  for (size_t it = 0; it < n_it; it++) {
+    const size_t u = unit(it);
+    const bool active = first + it * G + oct < total;
+    const size_t op = act[u / K];
+    const int i = (int)(u % K);
+    uint32_t acc[32];
 #pragma unroll
-  for (int s = 0; s < 16; s++) {
-    uint32_t lo0, hi0, lo1, hi1;
-    decompose<P>(le2q_modq(acc[2 * s]), lo0, hi0);
-    decompose<P>(le2q_modq(acc[2 * s + 1]), lo1, hi1);
-    if (active) {
-      *reinterpret_cast<uint2*>(w0p + 16 * s + 2 * o.v) = make_uint2(lo0, lo1);
-      SignW1<P>::store(w1b, s, o.v, hi0, hi1);
+    for (int q = 0; q < 32; q++) acc[q] = 0;
+#pragma unroll
+    for (int j = 0; j < L; j++, c++) {
+      uint4 zn[8];
+      if (j + 1 < L) {
+        gload_I(yh + (op * L + j + 1) * N, v, zn);
+      } else if (it + 1 < n_it) {
+        gload_I(yh + ((size_t)act[unit(it + 1) / K] * L) * N, v, zn);
+      }
+      const int slot = (int)(c % kWSlots);
+      mbar_wait(bars + slot, (uint32_t)((c / kWSlots) & 1));
+      const uint4* xs = reinterpret_cast<const uint4*>(ring + slot * 256) + v;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        const uint4 x = xs[8 * q];
+        acc[4 * q] += mont_mul(x.x, zc[q].x);
+        acc[4 * q + 1] += mont_mul(x.y, zc[q].y);
+        acc[4 * q + 2] += mont_mul(x.z, zc[q].z);
+        acc[4 * q + 3] += mont_mul(x.w, zc[q].w);
+      }
+      __syncwarp();  // every lane of the octet is done with the slot
+      if (v == 0 && c + kWSlots < n_chunks) issue(c + kWSlots);
+#pragma unroll
+      for (int q = 0; q < 8; q++) zc[q] = zn[q];
+    }
+#pragma unroll
+    for (int q = 0; q < 32; q++) acc[q] = reduce_le2q(acc[q]);
+    i_to_c(acc, tile, v);
+    invntt_octet(acc, tile, v, t);  // -> S layout: acc[2s+b] = coefficient 16s + 2v + b
+    uint32_t* w0p = w0 + (op * K + i) * N;
+    uint8_t* w1b = w1u + (op * K + i) * SignW1<P>::stride;
+#pragma unroll
+    for (int s = 0; s < 16; s++) {
+      uint32_t lo0, hi0, lo1, hi1;
+      decompose<P>(le2q_modq(acc[2 * s]), lo0, hi0);
+      decompose<P>(le2q_modq(acc[2 * s + 1]), lo1, hi1);
+      if (active) {
+        *reinterpret_cast<uint2*>(w0p + 16 * s + 2 * v) = make_uint2(lo0, lo1);
+        SignW1<P>::store(w1b, s, v, hi0, hi1);
+      }
     }
   }
 }
@@ -1562,6 +1610,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
     if (kChSmem) CB200_CUDA(cudaFuncSetAttribute(challenge_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmem));
+    CB200_CUDA(cudaFuncSetAttribute(w_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
     attr_set = true;
   }
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
@@ -1604,7 +1653,8 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     }
     {
       KernelScope ks(KID_MLDSA_W, st);
-      w_kernel<P><<<blocks(nact * K, 16), 128, 0, st>>>(act, nact, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, zetas);
+      w_kernel<P><<<(unsigned)std::min<size_t>((nact * K + 15) / 16, (size_t)c.sm_count * 3), 128, kWSmem, st>>>(
+          act, nact, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_CHALLENGE, st);

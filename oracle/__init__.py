@@ -442,3 +442,62 @@ def kyber_kem_decaps(k: int, dk: bytes, ct: bytes) -> bytes:
     ss = (C.c_uint8 * 32)()
     lib().orc_kyber_kem_decaps(k, ss, _buf(dk), _buf(ct))
     return bytes(ss)
+
+
+# ------------------------------------------------------------------ X25519, X-Wing, kem/hybrid (hybrid.c)
+HYBRID_IDS = {"X25519MLKEM768": 0, "Kyber768-X25519": 1, "Kyber512-X25519": 2}
+
+
+def x25519(scalar: bytes, point: bytes | None = None):
+    """(out, ok): dh/x25519 KeyGen (point None) or Shared; ok False for the low-order points."""
+    out = (C.c_uint8 * 32)()
+    ok = lib().orc_x25519(out, _buf(scalar), _buf(point) if point is not None else None)
+    return bytes(out), bool(ok)
+
+
+def xwing_keygen(seed32: bytes) -> bytes:
+    pk = (C.c_uint8 * 1216)()
+    lib().orc_xwing_keygen(pk, _buf(seed32))
+    return bytes(pk)
+
+
+def xwing_encaps(pk: bytes, eseed64: bytes):
+    ct, ss = (C.c_uint8 * 1120)(), (C.c_uint8 * 32)()
+    if lib().orc_xwing_encaps(ct, ss, _buf(pk), _buf(eseed64)):
+        raise ValueError("kem.ErrPubKey")
+    return bytes(ct), bytes(ss)
+
+
+def xwing_decaps(sk32: bytes, ct: bytes) -> bytes:
+    ss = (C.c_uint8 * 32)()
+    lib().orc_xwing_decaps(ss, _buf(sk32), _buf(ct))
+    return bytes(ss)
+
+
+def hybrid_sizes(name: str):
+    L, i = lib(), HYBRID_IDS[name]
+    for f in (L.orc_hybrid_pk_size, L.orc_hybrid_sk_size, L.orc_hybrid_ct_size):
+        f.restype = C.c_size_t
+    return L.orc_hybrid_pk_size(i), L.orc_hybrid_sk_size(i), L.orc_hybrid_ct_size(i)
+
+
+def hybrid_keygen(name: str, seed64: bytes):
+    pksz, sksz, _ = hybrid_sizes(name)
+    pk, sk = (C.c_uint8 * pksz)(), (C.c_uint8 * sksz)()
+    lib().orc_hybrid_keygen(HYBRID_IDS[name], pk, sk, _buf(seed64))
+    return bytes(pk), bytes(sk)
+
+
+def hybrid_encaps(name: str, pk: bytes, seed32: bytes):
+    """(ct, ss, rc): rc 1 = kem.ErrPubKey."""
+    _, _, ctsz = hybrid_sizes(name)
+    ct, ss = (C.c_uint8 * ctsz)(), (C.c_uint8 * 64)()
+    rc = lib().orc_hybrid_encaps(HYBRID_IDS[name], ct, ss, _buf(pk), _buf(seed32))
+    return bytes(ct), bytes(ss), rc
+
+
+def hybrid_decaps(name: str, sk: bytes, ct: bytes):
+    """(ss, rc): rc 1 = kem.ErrPubKey (low-order X25519 share), 2 = kem.ErrPrivKey."""
+    ss = (C.c_uint8 * 64)()
+    rc = lib().orc_hybrid_decaps(HYBRID_IDS[name], ss, _buf(sk), _buf(ct))
+    return bytes(ss), rc

@@ -84,6 +84,18 @@ void orc_kyber_kem_keygen(int k, uint8_t *ek, uint8_t *dk, const uint8_t seed[64
 void orc_kyber_kem_encaps(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *ek, const uint8_t seed[32]);
 void orc_kyber_kem_decaps(int k, uint8_t ss[32], const uint8_t *dk, const uint8_t *ct);
 /* batched; ek_stride == 0 => one ek for all ops. returns number of failures */
+/* ---- hybrid.c: X25519, X-Wing, kem/hybrid ---- */
+int orc_x25519(uint8_t out[32], const uint8_t scalar[32], const uint8_t *point /* NULL = base point */);
+void orc_xwing_keygen(uint8_t pk[1216], const uint8_t seed[32]);
+int orc_xwing_encaps(uint8_t ct[1120], uint8_t ss[32], const uint8_t pk[1216], const uint8_t eseed[64]);
+void orc_xwing_decaps(uint8_t ss[32], const uint8_t sk[32], const uint8_t ct[1120]);
+size_t orc_hybrid_pk_size(int id); /* id 0 X25519MLKEM768, 1 Kyber768-X25519, 2 Kyber512-X25519 */
+size_t orc_hybrid_sk_size(int id);
+size_t orc_hybrid_ct_size(int id);
+void orc_hybrid_keygen(int id, uint8_t *pk, uint8_t *sk, const uint8_t seed[64]);
+int orc_hybrid_encaps(int id, uint8_t *ct, uint8_t *ss, const uint8_t *pk, const uint8_t seed[32]);
+int orc_hybrid_decaps(int id, uint8_t *ss, const uint8_t *sk, const uint8_t *ct);
+
 int orc_mlkem_encaps_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, size_t ek_stride,
                            const uint8_t *m, size_t n, int nthreads);
 

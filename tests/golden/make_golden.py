@@ -183,6 +183,20 @@ def samplers():
     dump("sampler_vectors.json.gz", out)
 
 
+def x25519_vectors():
+    """dh/x25519/testdata (RFC 7748 section 5.2 and 6.1, Wycheproof) + the X-Wing draft vectors hash."""
+    import gzip
+    td = os.path.join(REF, "dh/x25519/testdata")
+    out = {"source": "dh/x25519/testdata/{rfc7748_kat_test,rfc7748_times_test,wycheproof_kat}.json.gz; kem/xwing/xwing_test.go:78-80"}
+    out["rfc7748_kat"] = json.load(gzip.open(os.path.join(td, "rfc7748_kat_test.json.gz")))
+    out["rfc7748_times"] = [v for v in json.load(gzip.open(os.path.join(td, "rfc7748_times_test.json.gz"))) if v["times"] <= 1000]
+    out["wycheproof"] = [{k: v[k] for k in ("tcId", "public", "private", "shared", "result")}
+                         for v in json.load(gzip.open(os.path.join(td, "wycheproof_kat.json.gz")))]
+    src = open(os.path.join(REF, "kem/xwing/xwing_test.go")).read()
+    out["xwing_vectors_shake128"] = re.search(r'want := "([0-9a-f]{64})"', src).group(1)
+    dump("x25519_vectors.json.gz", out)
+
+
 def keccak_kats():
     raw = open(os.path.join(REF, "internal/sha3/testdata/keccakKats.json.deflate"), "rb").read()
     kats = json.loads(zlib.decompress(raw, -15))["kats"]
@@ -204,3 +218,4 @@ if __name__ == "__main__":
     mldsa_other()
     samplers()
     keccak_kats()
+    x25519_vectors()

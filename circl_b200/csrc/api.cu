@@ -27,7 +27,7 @@ static const char* kKernelNames[KID_COUNT] = {
     "mlkem_hash_ek", "mlkem_g", "mlkem_sample", "mlkem_encrypt",
     "dil_ntt", "dil_invntt", "dil_dot", "dil_elementwise",
     "mldsa_expand_key", "mldsa_mu_rhoprime", "mldsa_mask", "mldsa_w", "mldsa_challenge", "mldsa_response",
-    "mldsa_compact"};
+    "mldsa_compact", "x25519", "hybrid_glue"};
 const char* kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? kKernelNames[id] : "?"; }
 
 KernelScope::KernelScope(int id_, cudaStream_t st_) : st(st_), id(id_) {
@@ -234,7 +234,7 @@ void cb200_shutdown(void) {
       c.ev_join[w][l] = nullptr;
     }
   }
-  for (int s = 0; s < 4; s++) {
+  for (int s = 0; s < 8; s++) {
     if (c.work[s]) cudaFree(c.work[s]);
     c.work[s] = nullptr;
     c.work_bytes[s] = 0;

@@ -44,8 +44,10 @@ struct Ctx {
   cudaEvent_t ev_fork[4] = {}, ev_join[4][2] = {};
   void* pinned = nullptr;       // grow-only pinned host staging for small per-op outputs (status bytes)
   size_t pinned_bytes = 0;
-  void* work[4] = {nullptr, nullptr, nullptr, nullptr};
-  size_t work_bytes[4] = {0, 0, 0, 0};
+  // work[0..3]: the lattice flows of pipeline slots 0..2 and of device-pointer calls (3);
+  // work[4..7]: second level, for the flows of hybrid.cu that call into the lattice flows of the same slot
+  void* work[8] = {};
+  size_t work_bytes[8] = {};
 };
 
 // Kernel classes for the optional per-kernel event timing (cb200_profile_*).
@@ -54,7 +56,7 @@ enum KernelId {
   KID_MLKEM_HASH_EK, KID_MLKEM_G, KID_MLKEM_SAMPLE, KID_MLKEM_ENCRYPT,
   KID_DIL_NTT, KID_DIL_INVNTT, KID_DIL_DOT, KID_DIL_EW,
   KID_MLDSA_EXPAND, KID_MLDSA_MU, KID_MLDSA_MASK, KID_MLDSA_W, KID_MLDSA_CHALLENGE, KID_MLDSA_RESPONSE,
-  KID_MLDSA_COMPACT, KID_COUNT
+  KID_MLDSA_COMPACT, KID_X25519, KID_HYBRID_GLUE, KID_COUNT
 };
 const char* kernel_name(int id);
 

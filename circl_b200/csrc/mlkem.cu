@@ -19,6 +19,7 @@
 
 #include "../../include/circl_b200.h"
 #include "context.h"
+#include "mlkem_internal.h"
 #include "keccak.cuh"
 #include "kyber.cuh"
 
@@ -1210,6 +1211,30 @@ static int encaps_any(int k, const uint8_t* ek, size_t ek_stride, const uint8_t*
   return k == 2   ? encaps_device<2>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
          : k == 3 ? encaps_device<3>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
                   : encaps_device<4>(ek, ek_stride, seeds, ct, ss, status, n, st, slot);
+}
+
+// ---- entry points for hybrid.cu (mlkem_internal.h)
+int dev_keygen(int k, int mlkem, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n, cudaStream_t st, int slot) {
+  return k == 2   ? keygen_device<2>(seeds, ek, dk, n, st, slot, mlkem)
+         : k == 3 ? keygen_device<3>(seeds, ek, dk, n, st, slot, mlkem)
+                  : keygen_device<4>(seeds, ek, dk, n, st, slot, mlkem);
+}
+int dev_encaps(int k, int mlkem, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
+               uint8_t* status, size_t n, cudaStream_t st, int slot) {
+  if (mlkem) return encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, st, slot);
+  return k == 2   ? r3_device<2>(0, ek, ek_stride, seeds, ct, ss, n, st, slot)
+         : k == 3 ? r3_device<3>(0, ek, ek_stride, seeds, ct, ss, n, st, slot)
+                  : r3_device<4>(0, ek, ek_stride, seeds, ct, ss, n, st, slot);
+}
+int dev_decaps(int k, int mlkem, const uint8_t* dk, size_t dk_stride, const uint8_t* ct, uint8_t* ss, uint8_t* status, size_t n,
+               cudaStream_t st, int slot) {
+  if (mlkem)
+    return k == 2   ? decaps_device<2>(dk, dk_stride, ct, ss, status, n, st, slot)
+           : k == 3 ? decaps_device<3>(dk, dk_stride, ct, ss, status, n, st, slot)
+                    : decaps_device<4>(dk, dk_stride, ct, ss, status, n, st, slot);
+  return k == 2   ? r3_device<2>(1, dk, dk_stride, ct, nullptr, ss, n, st, slot)
+         : k == 3 ? r3_device<3>(1, dk, dk_stride, ct, nullptr, ss, n, st, slot)
+                  : r3_device<4>(1, dk, dk_stride, ct, nullptr, ss, n, st, slot);
 }
 
 }  // namespace mlkem

@@ -130,6 +130,36 @@ int cb200_kyber_kem_encaps(int k, const uint8_t *ek, size_t ek_stride, const uin
                            size_t n);
 int cb200_kyber_kem_decaps(int k, const uint8_t *dk, size_t dk_stride, const uint8_t *ct, uint8_t *ss, size_t n);
 
+/* ---- callers on the wire side of ML-KEM ----
+ * cb200_x25519: dh/x25519 KeyGen (points == NULL: base point, key.go:44-46) or Shared (key.go:48-56) on n
+ * 32-byte scalars / points; status[i] = 1 where the point has small order (Shared returning false); the output is
+ * then all zero and the host-pointer call returns CB200_ERR_PUBKEY after finishing the batch. */
+int cb200_x25519(const uint8_t *scalars, const uint8_t *points, uint8_t *out, uint8_t *status, size_t n);
+
+/* X-Wing (kem/xwing/xwing.go:32-44): seed / sk 32, pk 1216 (ML-KEM-768 ek || X25519 pk), encapsulation seed 64,
+ * ct 1120, ss 32.  keygen = DeriveKeyPairPacked (:131-141; the packed sk is the seed itself), encaps = Encapsulate
+ * (:173-182, kem.ErrPubKey through status / CB200_ERR_PUBKEY as in cb200_mlkem_encaps), decaps = Decapsulate
+ * (:185-191, which re-derives the key pair from the 32-byte sk). */
+int cb200_xwing_keygen(const uint8_t *seeds, uint8_t *pk, size_t n);
+int cb200_xwing_encaps(const uint8_t *pk, size_t pk_stride, const uint8_t *eseeds, uint8_t *ct, uint8_t *ss,
+                       uint8_t *status, size_t n);
+int cb200_xwing_decaps(const uint8_t *sk, size_t sk_stride, const uint8_t *ct, uint8_t *ss, size_t n);
+
+/* kem/hybrid (hybrid.go:197-283 over xkem.go): keys, ciphertexts and the 64-byte shared secret are the two halves
+ * side by side in the order of hybrid.go:34-62; key seed 64, encapsulation seed 32.
+ * status bit 0 = kem.ErrPubKey (non-canonical ML-KEM ek or small-order X25519 share), bit 1 = kem.ErrPrivKey. */
+#define CB200_HYBRID_X25519MLKEM768 0  /* ML-KEM-768 || X25519:  pk 1216, sk 2432, ct 1120 */
+#define CB200_HYBRID_KYBER768_X25519 1 /* X25519 || Kyber768:    pk 1216, sk 2432, ct 1120 */
+#define CB200_HYBRID_KYBER512_X25519 2 /* X25519 || Kyber512:    pk 832,  sk 1664, ct 800  */
+int cb200_hybrid_keygen(int id, const uint8_t *seeds, uint8_t *pk, uint8_t *sk, size_t n);
+int cb200_hybrid_encaps(int id, const uint8_t *pk, size_t pk_stride, const uint8_t *seeds, uint8_t *ct, uint8_t *ss,
+                        uint8_t *status, size_t n);
+int cb200_hybrid_decaps(int id, const uint8_t *sk, size_t sk_stride, const uint8_t *ct, uint8_t *ss, uint8_t *status,
+                        size_t n);
+size_t cb200_hybrid_public_key_size(int id);
+size_t cb200_hybrid_private_key_size(int id);
+size_t cb200_hybrid_ciphertext_size(int id);
+
 /* ---- ML-DSA (mode = 44, 65 or 87; sign/dilithium/gen.go:80-162) ----
  * Same contracts as the ML-DSA-65 entry points documented below, with the parameter set as first argument:
  * sk 2560 / 4032 / 4896, pk 1312 / 1952 / 2592, sig 2420 / 3309 / 4627 bytes. */

@@ -89,3 +89,19 @@ def test_hybrid_roundtrip_and_low_order(name):
     bad_ct = low + ct[32:] if x_first else ct[:-32] + low
     assert oracle.hybrid_encaps(name, bad_pk, bytes(32))[2] == 1
     assert oracle.hybrid_decaps(name, sk, bad_ct)[1] == 1
+
+
+def test_device_x25519_limb_arithmetic_on_host(tmp_path):
+    """csrc/x25519.cuh compiled as plain C++ (CUDA qualifiers defined away) against the oracle: ladder, squaring,
+    inversion, canonical encoding and the small-order test, including non-canonical and small-order inputs."""
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    oracle.build()
+    exe = str(tmp_path / "x25519_limbs")
+    r = subprocess.run(["g++", "-O2", "-std=c++17", os.path.join(root, "tests", "cpp", "test_x25519_limbs.cpp"), "-o", exe,
+                        os.path.join(root, "oracle", "liboracle.so"), "-Wl,-rpath," + os.path.join(root, "oracle")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout

@@ -157,8 +157,14 @@ struct Work {
   uint64_t* ctilde;        // per op: 6 words
   uint32_t *hintbits, *flags, *hintcnt, *attempt;  // per op: [48], 1, 1, 1
   uint32_t *pass, *list1, *list2;  // per op: 2 interleaved pass counters (stage 0, stage 1); survivors of response stages 0 and 1
-  uint32_t* act[2];        // active lists
-  uint32_t* count;         // [4] list lengths (device): act[0], act[1], list1, list2
+  // Speculative attempts: once enough ops are finished, every active op tries T consecutive attempts in one round;
+  // attempt t >= 1 of op X runs in the per-op state slot of a finished op (its id comes from `done`), so a slot id
+  // indexes all per-round state while owner[slot] = X indexes the key, mu, rho' and the attempt counter.
+  uint32_t *owner, *tofs;  // per slot: the op it works for, and its attempt offset t
+  uint32_t *best;          // per op: min over accepted slots of (t << 24 | slot), 0xffffffff = none yet
+  uint32_t *done, *slots;  // ids of finished ops (free slots); the slot list of the current round
+  uint32_t* act[2];        // active lists (op ids)
+  uint32_t* count;         // [8] device counters: act[0], act[1], list1, list2, done, -, total attempts (64 bit)
 };
 
 // ------------------------------------------------------------------ key expansion
@@ -303,7 +309,8 @@ __global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk,
                                                  const uint8_t* __restrict__ ctx, int ctxlen, int internal,
                                                  const uint8_t* __restrict__ rnd, size_t n, uint64_t* __restrict__ mu,
                                                  uint64_t* __restrict__ rhop, uint32_t* __restrict__ attempt,
-                                                 uint32_t* __restrict__ act) {
+                                                 uint32_t* __restrict__ act, uint32_t* __restrict__ owner,
+                                                 uint32_t* __restrict__ tofs) {
   MLDSA_USE(P);
   const size_t op = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (op >= n) return;
@@ -347,6 +354,8 @@ __global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk,
   for (int i = 0; i < 8; i++) rhop[8 * op + i] = a[i];
   attempt[op] = 0;
   act[op] = (uint32_t)op;
+  owner[op] = (uint32_t)op;
+  tofs[op] = 0;
 }
 
 // ------------------------------------------------------------------ per-round kernels
@@ -354,17 +363,20 @@ __global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk,
 template <class P>
 __global__ void __launch_bounds__(128) mask_kernel(const uint32_t* __restrict__ act, size_t nact,
                                                    const uint64_t* __restrict__ rhop,
-                                                   const uint32_t* __restrict__ attempt, uint32_t* __restrict__ y) {
+                                                   const uint32_t* __restrict__ attempt,
+                                                   const uint32_t* __restrict__ owner, const uint32_t* __restrict__ tofs,
+                                                   uint32_t* __restrict__ y) {
   MLDSA_USE(P);
   const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= nact * L) return;
-  const size_t op = act[s % nact];
+  const size_t op = act[s % nact];  // state slot
+  const size_t own = owner[op];
   const int i = (int)(s / nact);
-  const uint32_t nonce = L * attempt[op] + i;
+  const uint32_t nonce = L * (attempt[own] + tofs[op]) + i;
   uint64_t a[25];
   keccak::zero(a);
 #pragma unroll
-  for (int w = 0; w < 8; w++) a[w] = rhop[8 * op + w];
+  for (int w = 0; w < 8; w++) a[w] = rhop[8 * own + w];
   a[8] = (uint64_t)(nonce & 0xffff) | (0x1full << 16);
   a[16] = 0x8000000000000000ull;
   uint64_t buf[86];
@@ -451,13 +463,13 @@ __device__ __forceinline__ void decompose(uint32_t a, uint32_t& a0plusq, uint32_
 // each octet keeps kWSlots 1 KB bulk copies (TMA engine, one mbarrier per slot) in flight into the octet's ring in
 // shared memory, always kWSlots polynomials ahead of the arithmetic, also across the end of a row, so the DRAM
 // latency of the next row hides behind the inverse NTT and Decompose of the current one.
-constexpr int kWSlots = 3;
+constexpr int kWSlots = 2;
 constexpr int kWSmem = 16 * kWSlots * 1024 + 16 * kPolyWords * 4 + 16 * kWSlots * 8;
 template <class P>
 __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
                                                 const uint32_t* __restrict__ A, const uint32_t* __restrict__ yh,
                                                 uint32_t* __restrict__ w0, uint8_t* __restrict__ w1u,
-                                                const uint32_t* __restrict__ zetas) {
+                                                const uint32_t* __restrict__ owner, const uint32_t* __restrict__ zetas) {
   MLDSA_USE(P);
   extern __shared__ __align__(128) uint8_t wsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7, ob = warp * 4 + oct;
@@ -480,8 +492,8 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
   };
   auto issue = [&](size_t c) {  // lane 0 of the octet: fetch polynomial c % L of row unit(c / L) into slot c % kWSlots
     const size_t u = unit(c / L);
-    const size_t op = act[u / K];
-    const uint32_t* src = A + ((key_shared ? 0 : op) * (size_t)(K * L) + (u % K) * L + c % L) * N;
+    const size_t own = key_shared ? 0 : owner[act[u / K]];
+    const uint32_t* src = A + (own * (size_t)(K * L) + (u % K) * L + c % L) * N;
     uint64_t* bar = bars + c % kWSlots;
     mbar_expect_tx(bar, 1024);
     bulk_g2s(ring + (c % kWSlots) * 256, src, 1024, bar);
@@ -491,8 +503,6 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
   LaneTw t;
   load_lane_tw_inv(t, zetas + 256, v);
   size_t c = 0;
-  uint4 zc[8];  // y-hat polynomial of the chunk about to be multiplied, always loaded one chunk ahead
-  gload_I(yh + ((size_t)act[unit(0) / K] * L) * N, v, zc);
   for (size_t it = 0; it < n_it; it++) {
     const size_t u = unit(it);
     const bool active = first + it * G + oct < total;
@@ -501,29 +511,23 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
     uint32_t acc[32];
 #pragma unroll
     for (int q = 0; q < 32; q++) acc[q] = 0;
-#pragma unroll
+#pragma unroll 1
     for (int j = 0; j < L; j++, c++) {
-      uint4 zn[8];
-      if (j + 1 < L) {
-        gload_I(yh + (op * L + j + 1) * N, v, zn);
-      } else if (it + 1 < n_it) {
-        gload_I(yh + ((size_t)act[unit(it + 1) / K] * L) * N, v, zn);
-      }
+      uint4 z[8];
+      gload_I(yh + (op * L + j) * N, v, z);  // issued before the wait: overlaps the tail of the bulk copy
       const int slot = (int)(c % kWSlots);
       mbar_wait(bars + slot, (uint32_t)((c / kWSlots) & 1));
       const uint4* xs = reinterpret_cast<const uint4*>(ring + slot * 256) + v;
 #pragma unroll
       for (int q = 0; q < 8; q++) {
         const uint4 x = xs[8 * q];
-        acc[4 * q] += mont_mul(x.x, zc[q].x);
-        acc[4 * q + 1] += mont_mul(x.y, zc[q].y);
-        acc[4 * q + 2] += mont_mul(x.z, zc[q].z);
-        acc[4 * q + 3] += mont_mul(x.w, zc[q].w);
+        acc[4 * q] += mont_mul(x.x, z[q].x);
+        acc[4 * q + 1] += mont_mul(x.y, z[q].y);
+        acc[4 * q + 2] += mont_mul(x.z, z[q].z);
+        acc[4 * q + 3] += mont_mul(x.w, z[q].w);
       }
       __syncwarp();  // every lane of the octet is done with the slot
       if (v == 0 && c + kWSlots < n_chunks) issue(c + kWSlots);
-#pragma unroll
-      for (int q = 0; q < 8; q++) zc[q] = zn[q];
     }
 #pragma unroll
     for (int q = 0; q < 32; q++) acc[q] = reduce_le2q(acc[q]);
@@ -564,7 +568,8 @@ __global__ void __launch_bounds__(kChThreads) challenge_kernel(const uint32_t* _
                                                                const uint64_t* __restrict__ mu,
                                                                const uint8_t* __restrict__ w1u, uint64_t* __restrict__ ctilde,
                                                                uint32_t* __restrict__ cmask, uint32_t* __restrict__ flags,
-                                                               uint32_t* __restrict__ hintcnt, uint32_t* __restrict__ pass) {
+                                                               uint32_t* __restrict__ hintcnt, uint32_t* __restrict__ pass,
+                                                               const uint32_t* __restrict__ owner) {
   MLDSA_USE(P);
   using CL = ChLayout<P>;
   extern __shared__ __align__(16) uint32_t rows[];
@@ -575,6 +580,7 @@ __global__ void __launch_bounds__(kChThreads) challenge_kernel(const uint32_t* _
   const size_t s = s0 + lane;
   const bool valid = s < nact;
   const size_t op = act[valid ? s : nact - 1];
+  const size_t own = owner[op];
   uint64_t a[25];
   keccak::zero(a);
   if constexpr (SignW1<P>::packed) {
@@ -588,8 +594,8 @@ __global__ void __launch_bounds__(kChThreads) challenge_kernel(const uint32_t* _
       const int nrows = nact - s0 < 32 ? (int)(nact - s0) : 32;
 #pragma unroll 8
       for (int t = 0; t < nrows; t++) {
-        const size_t ot = __shfl_sync(0xffffffffu, (uint32_t)op, t);
-        const uint32_t* m32 = reinterpret_cast<const uint32_t*>(mu + 8 * ot);
+        const size_t ot = __shfl_sync(0xffffffffu, (uint32_t)op, t), wt = __shfl_sync(0xffffffffu, (uint32_t)own, t);
+        const uint32_t* m32 = reinterpret_cast<const uint32_t*>(mu + 8 * wt);
         const uint32_t* w32 = reinterpret_cast<const uint32_t*>(w1u + ot * (K * 128));
         for (int x = lane; x < 2 * nw; x += 32) {
           const int g = 2 * first + x;  // 32-bit word of the stream
@@ -618,7 +624,7 @@ __global__ void __launch_bounds__(kChThreads) challenge_kernel(const uint32_t* _
 #pragma unroll
       for (int w = 0; w < 17; w++) {
         const int k = 17 * b + w;
-        a[w] ^= (k < 8) ? mu[8 * op + k] : w1_word<P>(w1o, k - 8);
+        a[w] ^= (k < 8) ? mu[8 * own + k] : w1_word<P>(w1o, k - 8);
       }
       keccak::f1600(a);
     }
@@ -787,7 +793,8 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
                                                        uint8_t* __restrict__ zbuf, uint32_t* __restrict__ hintbits,
                                                        uint32_t* __restrict__ flags, uint32_t* __restrict__ hintcnt,
                                                        uint32_t* __restrict__ pass, uint32_t* __restrict__ next_list,
-                                                       uint32_t* __restrict__ next_count, const uint32_t* __restrict__ zetas) {
+                                                       uint32_t* __restrict__ next_count, const uint32_t* __restrict__ owner,
+                                                       const uint32_t* __restrict__ zetas) {
   MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
   __shared__ uint32_t izs[256];
@@ -803,7 +810,7 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
     const size_t u = active ? base + o.oct : total - 1;
     const size_t op = list[u / ITEMS];
     const int item = (int)(u % ITEMS);
-    const uint32_t* keyp = sh + (key_shared ? 0 : op) * (NKEYPOLY * N);
+    const uint32_t* keyp = sh + (key_shared ? 0 : (size_t)owner[op]) * (NKEYPOLY * N);
     const uint32_t* chat = cpoly + op * N;
     uint32_t r[32];
     bool reject = false;
@@ -887,35 +894,70 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
   }
 }
 
-// accept -> c~, z and hints into the signature; reject -> next attempt (dilithium.go:369-377,459-469).
-// One warp per active op.
+// The slot list of a round: T attempts per active op; attempt 0 runs in the op's own slot, attempt t >= 1 in the
+// slot of a finished op.  One thread per (op, t).
+__global__ void spec_expand_kernel(const uint32_t* __restrict__ act, size_t nact, int T, const uint32_t* __restrict__ done,
+                                   uint32_t* __restrict__ slots, uint32_t* __restrict__ owner, uint32_t* __restrict__ tofs) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nact * T) return;
+  const size_t p = i / T;
+  const int t = (int)(i % T);
+  const uint32_t op = act[p];
+  const uint32_t slot = t == 0 ? op : done[p * (T - 1) + (t - 1)];
+  slots[i] = slot;
+  owner[slot] = op;
+  tofs[slot] = (uint32_t)t;
+}
+
+// accept / reject (dilithium.go:369-377,459-469), phase 1: every slot whose attempt passed all checks bids for its
+// op with (t << 24 | slot); the lowest t wins, i.e. the first passing attempt in the reference's order.
 template <class P>
-__global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restrict__ act, size_t nact,
+__global__ void finalize_bid_kernel(const uint32_t* __restrict__ slots, size_t nslots, const uint32_t* __restrict__ flags,
+                                    const uint32_t* __restrict__ hintcnt, const uint32_t* __restrict__ owner,
+                                    const uint32_t* __restrict__ tofs, const uint32_t* __restrict__ attempt,
+                                    uint32_t* __restrict__ best) {
+  MLDSA_USE(P);
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots) return;
+  const uint32_t slot = slots[i], own = owner[slot], t = tofs[slot];
+  // "attempt >= 576" (dilithium.go:372-377): attempts past the cap are never accepted
+  if (flags[slot] == 0 && hintcnt[slot] <= OMEGA && attempt[own] + t + 1 < (uint32_t)MAX_ATTEMPTS)
+    atomicMin(best + own, (t << 24) | slot);
+}
+
+// phase 2, one warp per active op: accepted -> c~, z and hints of the winning slot into the signature, the op id
+// joins the free-slot list; rejected -> T more attempts are spent and the op joins the next active list.
+template <class P>
+__global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restrict__ act, size_t nact, int T,
                                                        const uint64_t* __restrict__ ctilde,
                                                        const uint8_t* __restrict__ zbuf,
-                                                       const uint32_t* __restrict__ hintbits,
-                                                       const uint32_t* __restrict__ flags,
-                                                       const uint32_t* __restrict__ hintcnt, uint32_t* __restrict__ attempt,
-                                                       uint8_t* __restrict__ sig, uint8_t* __restrict__ status,
-                                                       uint32_t* __restrict__ next, uint32_t* __restrict__ next_count) {
+                                                       const uint32_t* __restrict__ hintbits, uint32_t* __restrict__ best,
+                                                       uint32_t* __restrict__ attempt, uint8_t* __restrict__ sig,
+                                                       uint8_t* __restrict__ status, uint32_t* __restrict__ next,
+                                                       uint32_t* __restrict__ next_count, uint32_t* __restrict__ done,
+                                                       uint32_t* __restrict__ done_count,
+                                                       unsigned long long* __restrict__ total_attempts) {
   MLDSA_USE(P);
   const size_t s = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (s >= nact) return;
   const size_t op = act[s];
   uint8_t* sg = sig + op * (size_t)SIG_BYTES;
-  const bool accept = flags[op] == 0 && hintcnt[op] <= OMEGA;
-  if (accept) {
-    const uint8_t* ct = reinterpret_cast<const uint8_t*>(ctilde + (CTILDE / 8) * op);
+  const uint32_t b = best[op];
+  __syncwarp();
+  if (lane == 0) best[op] = 0xffffffffu;
+  if (b != 0xffffffffu) {
+    const size_t slot = b & 0xffffffu;
+    const uint8_t* ct = reinterpret_cast<const uint8_t*>(ctilde + (CTILDE / 8) * slot);
     for (int i = lane; i < CTILDE; i += 32) sg[i] = ct[i];
-    const uint8_t* zs = zbuf + op * (size_t)(L * POLY_Z);
+    const uint8_t* zs = zbuf + slot * (size_t)(L * POLY_Z);
     for (int i = lane; i < L * POLY_Z; i += 32) sg[CTILDE + i] = zs[i];
     if (lane == 0) {
       uint8_t* hb = sg + CTILDE + L * POLY_Z;  // PackHint (internal/pack.go:77-95)
       int off = 0;
       for (int i = 0; i < K; i++) {
         for (int w = 0; w < 8; w++) {
-          uint32_t m = hintbits[8 * K * op + 8 * i + w];
+          uint32_t m = hintbits[8 * K * slot + 8 * i + w];
           while (m) {
             const int bit = __ffs(m) - 1;
             hb[off++] = (uint8_t)(32 * w + bit);
@@ -926,13 +968,19 @@ __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restric
       }
       for (; off < OMEGA; off++) hb[off] = 0;
       if (status) status[op] = 0;
+      atomicAdd(total_attempts, (unsigned long long)(attempt[op] + (b >> 24) + 1));
+      done[atomicAdd(done_count, 1u)] = (uint32_t)op;
     }
   } else {
-    const uint32_t at = attempt[op] + 1;
+    const uint32_t at = attempt[op] + T;
     __syncwarp();
-    if (at + 1 >= MAX_ATTEMPTS) {  // "attempt >= 576" (dilithium.go:372-377): give up, flag the op
+    if (at + 1 >= (uint32_t)MAX_ATTEMPTS) {  // every attempt below the cap has been tried: give up, flag the op
       for (int i = lane; i < SIG_BYTES; i += 32) sg[i] = 0;
-      if (lane == 0 && status) status[op] = 1;
+      if (lane == 0) {
+        if (status) status[op] = 1;
+        atomicAdd(total_attempts, (unsigned long long)(MAX_ATTEMPTS - 1));
+        done[atomicAdd(done_count, 1u)] = (uint32_t)op;
+      }
     } else if (lane == 0) {
       next[atomicAdd(next_count, 1u)] = (uint32_t)op;
     }
@@ -1575,7 +1623,8 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
                oRh = take(n * 64), oY = take(n * L * 1024), oYh = take(n * L * 1024), oW0 = take(n * K * 1024),
                oW1 = take(n * K * SignW1<P>::stride), oCm = take(n * 64), oZ = take(n * L * POLY_Z), oC = take(n * 1024), oCt = take(n * CTILDE), oHb = take(n * 8 * K * 4),
                oFl = take(n * 4), oHc = take(n * 4), oAt = take(n * 4), oA0 = take(n * 4), oA1 = take(n * 4),
-               oPs = take(n * 8), oL1 = take(n * 4), oL2 = take(n * 4), oCnt = take(16);
+               oPs = take(n * 8), oL1 = take(n * 4), oL2 = take(n * 4), oOw = take(n * 4), oTo = take(n * 4),
+               oBe = take(n * 4), oDn = take(n * 4), oSl = take(n * 4), oCnt = take(32);
   void* base = nullptr;
   int rc = ensure_work(slot, off, &base);
   if (rc) return rc;
@@ -1603,6 +1652,11 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   w.pass = (uint32_t*)(b + oPs);
   w.list1 = (uint32_t*)(b + oL1);
   w.list2 = (uint32_t*)(b + oL2);
+  w.owner = (uint32_t*)(b + oOw);
+  w.tofs = (uint32_t*)(b + oTo);
+  w.best = (uint32_t*)(b + oBe);
+  w.done = (uint32_t*)(b + oDn);
+  w.slots = (uint32_t*)(b + oSl);
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
   constexpr int kChSmem = ChLayout<P>::smem;
 
@@ -1626,7 +1680,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   {
     KernelScope ks(KID_MLDSA_MU, st);
     mu_kernel<P><<<blocks(n, 128), 128, 0, st>>>(sk, sk_stride, msgs, msg_off, ctxstr, ctxlen, internal, rnd, n, w.mu, w.rhop,
-                                              w.attempt, w.act[0]);
+                                              w.attempt, w.act[0], w.owner, w.tofs);
   }
   CB200_CUDA(cudaGetLastError());
 
@@ -1637,57 +1691,74 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   size_t nact = n;
   int cur = 0;
   uint64_t total_attempts = 0;
+  CB200_CUDA(cudaMemsetAsync(w.count, 0, 32, st));
+  CB200_CUDA(cudaMemsetAsync(w.best, 0xff, n * 4, st));
+  constexpr int kMaxSpec = 8;
+  auto pgrid = [&](size_t units, int per_sm) {
+    return (unsigned)std::min<size_t>((units + 15) / 16, (size_t)c.sm_count * per_sm);
+  };
   for (int round = 0; nact > 0; round++) {
     if (round >= MAX_ATTEMPTS) break;
-    total_attempts += nact;
+    // attempts per op this round: as many as there are free slots (ids of finished ops) to run them in
+    const int T = (int)std::min<size_t>(kMaxSpec, 1 + (n - nact) / nact);
+    const size_t ns = nact * T;
     const uint32_t* act = w.act[cur];
+    const uint32_t* sl = w.slots;
     CB200_CUDA(cudaMemsetAsync(w.count + (cur ^ 1), 0, 4, st));
     CB200_CUDA(cudaMemsetAsync(w.count + 2, 0, 8, st));
     {
+      KernelScope ks(KID_MLDSA_COMPACT, st);
+      spec_expand_kernel<<<blocks(ns, 256), 256, 0, st>>>(act, nact, T, w.done, w.slots, w.owner, w.tofs);
+    }
+    {
       KernelScope ks(KID_MLDSA_MASK, st);
-      mask_kernel<P><<<blocks(nact * L, 128), 128, 0, st>>>(act, nact, w.rhop, w.attempt, w.y);
+      mask_kernel<P><<<blocks(ns * L, 128), 128, 0, st>>>(sl, ns, w.rhop, w.attempt, w.owner, w.tofs, w.y);
     }
     {
       KernelScope ks(KID_MLDSA_W, st);
-      yntt_kernel<P><<<blocks(nact * L, 16), 128, 0, st>>>(act, nact, w.y, w.yh, zetas);
+      yntt_kernel<P><<<blocks(ns * L, 16), 128, 0, st>>>(sl, ns, w.y, w.yh, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_W, st);
-      w_kernel<P><<<(unsigned)std::min<size_t>((nact * K + 15) / 16, (size_t)c.sm_count * 3), 128, kWSmem, st>>>(
-          act, nact, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, zetas);
+      w_kernel<P><<<pgrid(ns * K, 4), 128, kWSmem, st>>>(sl, ns, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, w.owner, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_CHALLENGE, st);
-      challenge_kernel<P><<<blocks(nact, kChThreads), kChThreads, kChSmem, st>>>(act, nact, w.mu, w.w1u, w.ctilde, w.cmask,
-                                                                                 w.flags, w.hintcnt, w.pass);
+      challenge_kernel<P><<<blocks(ns, kChThreads), kChThreads, kChSmem, st>>>(sl, ns, w.mu, w.w1u, w.ctilde, w.cmask, w.flags,
+                                                                               w.hintcnt, w.pass, w.owner);
     }
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
-      cntt_mask_kernel<<<blocks(nact, 16), 128, 0, st>>>(act, nact, w.cmask, w.c, zetas);
+      cntt_mask_kernel<<<blocks(ns, 16), 128, 0, st>>>(sl, ns, w.cmask, w.c, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
-      // persistent grids: at most 8 blocks per SM, fewer when the list is short
-      auto grid = [&](size_t units) { return (unsigned)std::min<size_t>((units + 15) / 16, (size_t)c.sm_count * 8); };
-      response_kernel<P, 0><<<grid(nact * K), 128, 0, st>>>(act, nullptr, nact, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u,
-                                                            w.zbuf, w.hintbits, w.flags, w.hintcnt, w.pass, w.list1,
-                                                            w.count + 2, zetas);
-      response_kernel<P, 1><<<grid(nact * L), 128, 0, st>>>(w.list1, w.count + 2, 0, shared ? 1 : 0, w.sh, w.c, w.y, w.w0,
-                                                            w.w1u, w.zbuf, w.hintbits, w.flags, w.hintcnt, w.pass + 1,
-                                                            w.list2, w.count + 3, zetas);
-      response_kernel<P, 2><<<grid(nact * K), 128, 0, st>>>(w.list2, w.count + 3, 0, shared ? 1 : 0, w.sh, w.c, w.y, w.w0,
-                                                            w.w1u, w.zbuf, w.hintbits, w.flags, w.hintcnt, nullptr, nullptr,
-                                                            nullptr, zetas);
+      response_kernel<P, 0><<<pgrid(ns * K, 8), 128, 0, st>>>(sl, nullptr, ns, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u,
+                                                              w.zbuf, w.hintbits, w.flags, w.hintcnt, w.pass, w.list1,
+                                                              w.count + 2, w.owner, zetas);
+      response_kernel<P, 1><<<pgrid(ns * L, 8), 128, 0, st>>>(w.list1, w.count + 2, 0, shared ? 1 : 0, w.sh, w.c, w.y, w.w0,
+                                                              w.w1u, w.zbuf, w.hintbits, w.flags, w.hintcnt, w.pass + 1,
+                                                              w.list2, w.count + 3, w.owner, zetas);
+      response_kernel<P, 2><<<pgrid(ns * K, 8), 128, 0, st>>>(w.list2, w.count + 3, 0, shared ? 1 : 0, w.sh, w.c, w.y, w.w0,
+                                                              w.w1u, w.zbuf, w.hintbits, w.flags, w.hintcnt, nullptr, nullptr,
+                                                              nullptr, w.owner, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_COMPACT, st);
-      finalize_kernel<P><<<blocks(nact * 32, 128), 128, 0, st>>>(act, nact, w.ctilde, w.zbuf, w.hintbits, w.flags, w.hintcnt,
-                                                              w.attempt, sig, status, w.act[cur ^ 1], w.count + (cur ^ 1));
+      finalize_bid_kernel<P><<<blocks(ns, 256), 256, 0, st>>>(sl, ns, w.flags, w.hintcnt, w.owner, w.tofs, w.attempt, w.best);
+      finalize_kernel<P><<<blocks(nact * 32, 128), 128, 0, st>>>(
+          act, nact, T, w.ctilde, w.zbuf, w.hintbits, w.best, w.attempt, sig, status, w.act[cur ^ 1], w.count + (cur ^ 1),
+          w.done, w.count + 4, reinterpret_cast<unsigned long long*>(w.count + 6));
     }
     CB200_CUDA(cudaMemcpyAsync((void*)h_count, w.count + (cur ^ 1), 4, cudaMemcpyDeviceToHost, st));
     CB200_CUDA(cudaStreamSynchronize(st));
     nact = *h_count;
     cur ^= 1;
+  }
+  if (attempts_out) {
+    CB200_CUDA(cudaMemcpyAsync((void*)h_count, w.count + 6, 8, cudaMemcpyDeviceToHost, st));
+    CB200_CUDA(cudaStreamSynchronize(st));
+    total_attempts = *reinterpret_cast<volatile uint64_t*>(h_count);
   }
   CB200_CUDA(cudaGetLastError());
   if (attempts_out) *attempts_out = total_attempts;

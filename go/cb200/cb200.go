@@ -177,6 +177,78 @@ func MLDSA65Sign(sk []byte, shared bool, msgs [][]byte, ctx, rnd, sig []byte) er
 		prnd, (*C.uint8_t)(unsafe.Pointer(&sig[0])), nil, C.size_t(n), 0, nil))
 }
 
+// Hybrid scheme identifiers of include/circl_b200.h (kem/hybrid/hybrid.go:34-62).
+const (
+	HybridX25519MLKEM768 = 0
+	HybridKyber768X25519 = 1
+	HybridKyber512X25519 = 2
+)
+
+// X25519Batch: x25519.KeyGen (points == nil) or x25519.Shared (dh/x25519/key.go:44-56) on n 32-byte keys.
+// ok[i] is false where Shared would have returned false (point of small order); out[i] is then all zero.
+func X25519Batch(scalars, points, out []byte, ok []bool) error {
+	n := len(scalars) / 32
+	if len(out) != n*32 || (points != nil && len(points) != n*32) || (ok != nil && len(ok) != n) {
+		panic("cb200: X25519Batch buffers have the wrong length")
+	}
+	if n == 0 {
+		return nil
+	}
+	status := make([]byte, n)
+	var pp *C.uint8_t
+	if points != nil {
+		pp = (*C.uint8_t)(unsafe.Pointer(&points[0]))
+	}
+	rc := C.cb200_x25519((*C.uint8_t)(unsafe.Pointer(&scalars[0])), pp, (*C.uint8_t)(unsafe.Pointer(&out[0])),
+		(*C.uint8_t)(unsafe.Pointer(&status[0])), C.size_t(n))
+	for i := range ok {
+		ok[i] = status[i] == 0
+	}
+	if rc == C.CB200_ERR_PUBKEY { // reported per operation through ok, like the bool of x25519.Shared
+		return nil
+	}
+	return lastErr(rc)
+}
+
+// XWingEncaps: batched xwing.Encapsulate (kem/xwing/xwing.go:173-182).  pk: one packed 1216-byte key (shared) or n keys;
+// seeds: n*64 bytes; ct: n*1120; ss: n*32.  kem.ErrPubKey is returned if any ML-KEM half is not canonical.
+func XWingEncaps(pk []byte, shared bool, seeds, ct, ss []byte) error {
+	n := len(seeds) / 64
+	stride := C.size_t(1216)
+	if shared {
+		stride = 0
+	}
+	if len(ct) != n*1120 || len(ss) != n*32 || (shared && len(pk) != 1216) || (!shared && len(pk) != n*1216) {
+		panic("cb200: XWingEncaps buffers have the wrong length")
+	}
+	if n == 0 {
+		return nil
+	}
+	return lastErr(C.cb200_xwing_encaps((*C.uint8_t)(unsafe.Pointer(&pk[0])), stride, (*C.uint8_t)(unsafe.Pointer(&seeds[0])),
+		(*C.uint8_t)(unsafe.Pointer(&ct[0])), (*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n)))
+}
+
+// HybridEncaps: batched hybrid.scheme.EncapsulateDeterministically (kem/hybrid/hybrid.go:233-261); id is one of the
+// Hybrid* constants; seeds: n*32 bytes; ss: n*64 bytes (the two shared secrets side by side, hybrid.go:260).
+func HybridEncaps(id int, pk []byte, shared bool, seeds, ct, ss []byte) error {
+	n := len(seeds) / 32
+	pkSize := int(C.cb200_hybrid_public_key_size(C.int(id)))
+	ctSize := int(C.cb200_hybrid_ciphertext_size(C.int(id)))
+	stride := C.size_t(pkSize)
+	if shared {
+		stride = 0
+	}
+	if len(ct) != n*ctSize || len(ss) != n*64 || (shared && len(pk) != pkSize) || (!shared && len(pk) != n*pkSize) {
+		panic("cb200: HybridEncaps buffers have the wrong length")
+	}
+	if n == 0 {
+		return nil
+	}
+	return lastErr(C.cb200_hybrid_encaps(C.int(id), (*C.uint8_t)(unsafe.Pointer(&pk[0])), stride,
+		(*C.uint8_t)(unsafe.Pointer(&seeds[0])), (*C.uint8_t)(unsafe.Pointer(&ct[0])), (*C.uint8_t)(unsafe.Pointer(&ss[0])),
+		nil, C.size_t(n)))
+}
+
 // PinnedBytes returns a Go slice over cudaHostAlloc'd memory: large batches should live
 // here so that host<->device copies run at full PCIe speed and overlap with the kernels.
 func PinnedBytes(n int) ([]byte, func()) {

@@ -56,4 +56,38 @@ e = torch.randint(0, 8380417, (n, 256), device="cuda", dtype=torch.int32)
 for label, fn in (("Dilithium NTT", lambda: dl.ntt_(e)), ("Dilithium InvNTT", lambda: dl.inv_ntt_(e))):
     t = timed(fn, steps=10)
     res[label] = {"n": n, "ms": t, "per_s": n / (t * 1e-3), "GBps": n * 2048 / (t * 1e-3) / 1e9}
+del e
+torch.cuda.empty_cache()
+
+# wire-side callers: X25519, X-Wing, X25519MLKEM768, round-3 Kyber768, all device-resident
+from circl_b200 import hybrid  # noqa: E402
+n = 1 << 18
+g = torch.Generator(device="cuda").manual_seed(2)
+k32 = torch.randint(0, 256, (n, 32), generator=g, device="cuda", dtype=torch.uint8)
+t = timed(lambda: hybrid.x25519_keygen(k32), steps=3)
+pub = hybrid.x25519_keygen(k32)
+res["X25519 KeyGen"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+t = timed(lambda: hybrid.x25519_shared(k32, pub), steps=3)
+res["X25519 Shared"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+for name in ("X-Wing", "X25519MLKEM768"):
+    sch = hybrid.ByName(name)
+    seeds = torch.randint(0, 256, (n, sch.SeedSize()), generator=g, device="cuda", dtype=torch.uint8)
+    es = torch.randint(0, 256, (n, sch.EncapsulationSeedSize()), generator=g, device="cuda", dtype=torch.uint8)
+    t = timed(lambda: sch.DeriveKeyPairBatch(seeds), steps=3)
+    pk, sk = sch.DeriveKeyPairBatch(seeds)
+    res[f"{name} keygen"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+    t = timed(lambda: sch.EncapsulateBatch(pk, es), steps=3)
+    ct, ss = sch.EncapsulateBatch(pk, es)
+    res[f"{name} encaps"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+    t = timed(lambda: sch.DecapsulateBatch(sk, ct), steps=3)
+    res[f"{name} decaps"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3),
+                             "roundtrip_ok": bool(torch.equal(ss, sch.DecapsulateBatch(sk, ct)))}
+    del seeds, es, pk, sk, ct, ss
+    torch.cuda.empty_cache()
+k768 = mlkem.ByName("Kyber768")
+seeds = torch.randint(0, 256, (n, 64), generator=g, device="cuda", dtype=torch.uint8)
+ms = torch.randint(0, 256, (n, 32), generator=g, device="cuda", dtype=torch.uint8)
+ek, dk = k768.DeriveKeyPairBatch(seeds)
+t = timed(lambda: k768.EncapsulateBatch(ek, ms), steps=3)
+res["Kyber768 (round 3) encaps"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
 print(json.dumps(res, indent=1))

@@ -463,7 +463,7 @@ __device__ __forceinline__ void decompose(uint32_t a, uint32_t& a0plusq, uint32_
 // each octet keeps kWSlots 1 KB bulk copies (TMA engine, one mbarrier per slot) in flight into the octet's ring in
 // shared memory, always kWSlots polynomials ahead of the arithmetic, also across the end of a row, so the DRAM
 // latency of the next row hides behind the inverse NTT and Decompose of the current one.
-constexpr int kWSlots = 2;
+constexpr int kWSlots = 3;
 constexpr int kWSmem = 16 * kWSlots * 1024 + 16 * kPolyWords * 4 + 16 * kWSlots * 8;
 template <class P>
 __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
@@ -1720,7 +1720,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     }
     {
       KernelScope ks(KID_MLDSA_W, st);
-      w_kernel<P><<<pgrid(ns * K, 4), 128, kWSmem, st>>>(sl, ns, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, w.owner, zetas);
+      w_kernel<P><<<pgrid(ns * K, 3), 128, kWSmem, st>>>(sl, ns, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, w.owner, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_CHALLENGE, st);

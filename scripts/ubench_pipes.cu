@@ -40,6 +40,19 @@ __global__ void k(int32_t* out, int32_t seed) {
         asm volatile("add.s32 %0, %0, %1;" : "+r"(a[i]) : "r"(t));
         asm volatile("sub.s32 %0, %0, %1;" : "+r"(a[(i + 1) & 7]) : "r"(t));
       }
+      if (MODE == 11) {  // mad.wide.u32 with 64-bit accumulate (IMAD.WIDE.U32): the X25519 / Dilithium product
+        uint64_t acc = ((uint64_t)(uint32_t)a[(i + 1) & 7] << 32) | (uint32_t)a[i];
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(z), "r"(q));
+        a[i] = (int32_t)acc;
+        a[(i + 1) & 7] = (int32_t)(acc >> 32);
+      }
+      if (MODE == 12) {  // mad.wide.u32 + lop3 on other registers
+        uint64_t acc = ((uint64_t)(uint32_t)a[(i + 1) & 7] << 32) | (uint32_t)a[i];
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(z), "r"(q));
+        a[i] = (int32_t)acc;
+        a[(i + 1) & 7] = (int32_t)(acc >> 32);
+        asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a[(i + 4) & 7]) : "r"(z), "r"(q));
+      }
       if (MODE == 10) {  // butterfly B: 1 mul.lo + 2 mad.hi + 2 add
         int32_t m, h, t;
         asm volatile("mul.lo.s32 %0, %1, 31499;" : "=r"(m) : "r"(a[i]));
@@ -93,5 +106,7 @@ int main() {
   run<5>("mad.hi + add", 2);
   run<9>("butterfly A (3 IMAD,2 SHF,2 ADD)", 7);
   run<10>("butterfly B (1 IMAD,2 IMAD.HI,2 ADD)", 5);
+  run<11>("mad.wide.u32 (IMAD.WIDE)", 1);
+  run<12>("mad.wide.u32 + lop3", 2);
   return 0;
 }

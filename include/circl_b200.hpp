@@ -75,22 +75,34 @@ class PrivateKey {  // kem.PrivateKey (kem/kem.go:22-30)
   Bytes packed_;
 };
 
-class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024 and round-3 Kyber512/768/1024
+// kem.Scheme (kem/kem.go:33-82).  One class serves the four families behind the C ABI:
+//   MLKEM   ML-KEM-512/768/1024            kem/mlkem/mlkem768/kyber.go:267-407
+//   KYBER3  round-3 Kyber512/768/1024      kem/kyber/kyber768/kyber.go:267-407
+//   XWING   X-Wing                         kem/xwing/scheme.go:1-140
+//   HYBRID  X25519MLKEM768, Kyber768-X25519, Kyber512-X25519   kem/hybrid/hybrid.go:76-315
+class Scheme {
  public:
-  Scheme(std::string name, int k, bool round3 = false) : name_(std::move(name)), k_(k), round3_(round3) {}
+  enum Kind { MLKEM, KYBER3, XWING, HYBRID };
+  Scheme(std::string name, int k, bool round3 = false) : name_(std::move(name)), kind_(round3 ? KYBER3 : MLKEM), k_(k) {}
+  Scheme(std::string name, Kind kind, int id) : name_(std::move(name)), kind_(kind), k_(id) {}
   const std::string& Name() const { return name_; }
-  size_t CiphertextSize() const { return cb200_mlkem_ciphertext_size(k_); }
-  size_t SharedKeySize() const { return 32; }
-  size_t PrivateKeySize() const { return cb200_mlkem_private_key_size(k_); }
-  size_t PublicKeySize() const { return cb200_mlkem_public_key_size(k_); }
-  size_t SeedSize() const { return 64; }
-  size_t EncapsulationSeedSize() const { return 32; }
+  size_t CiphertextSize() const {
+    return kind_ == XWING ? 1120 : kind_ == HYBRID ? cb200_hybrid_ciphertext_size(k_) : cb200_mlkem_ciphertext_size(k_);
+  }
+  size_t SharedKeySize() const { return kind_ == HYBRID ? 64 : 32; }
+  size_t PrivateKeySize() const {
+    return kind_ == XWING ? 32 : kind_ == HYBRID ? cb200_hybrid_private_key_size(k_) : cb200_mlkem_private_key_size(k_);
+  }
+  size_t PublicKeySize() const {
+    return kind_ == XWING ? 1216 : kind_ == HYBRID ? cb200_hybrid_public_key_size(k_) : cb200_mlkem_public_key_size(k_);
+  }
+  size_t SeedSize() const { return kind_ == XWING ? 32 : 64; }
+  size_t EncapsulationSeedSize() const { return kind_ == XWING ? 64 : 32; }
 
   std::pair<PublicKey, PrivateKey> DeriveKeyPair(const Bytes& seed) const {  // kyber.go:337-346
     if (seed.size() != SeedSize()) throw std::logic_error("kem: invalid seed size");  // Go panics here
-    Bytes ek(PublicKeySize()), dk(PrivateKeySize());
-    check(round3_ ? cb200_kyber_kem_keygen(k_, seed.data(), ek.data(), dk.data(), 1)
-                  : cb200_mlkem_keygen(k_, seed.data(), ek.data(), dk.data(), 1));
+    Bytes ek, dk;
+    DeriveKeyPairBatch(seed, ek, dk);
     return {PublicKey(this, std::move(ek)), PrivateKey(this, std::move(dk))};
   }
   std::pair<PublicKey, PrivateKey> GenerateKeyPair() const {  // kyber.go:281-283
@@ -110,9 +122,8 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024 and rou
   std::pair<Bytes, Bytes> EncapsulateDeterministically(const PublicKey& pk, const Bytes& seed) const {  // kyber.go:359-374
     if (seed.size() != EncapsulationSeedSize()) throw ErrSeedSize();
     if (pk.GetScheme() != this) throw ErrTypeMismatch();
-    Bytes ct(CiphertextSize()), ss(32);
-    check(round3_ ? cb200_kyber_kem_encaps(k_, pk.MarshalBinary().data(), 0, seed.data(), ct.data(), ss.data(), 1)
-                  : cb200_mlkem_encaps(k_, pk.MarshalBinary().data(), 0, seed.data(), ct.data(), ss.data(), nullptr, 1));
+    Bytes ct, ss;
+    EncapsulateBatch(pk.MarshalBinary(), seed, ct, ss);
     return {std::move(ct), std::move(ss)};
   }
   std::pair<Bytes, Bytes> Encapsulate(const PublicKey& pk) const {  // kyber.go:348-357
@@ -123,40 +134,68 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024 and rou
   Bytes Decapsulate(const PrivateKey& sk, const Bytes& ct) const {  // kyber.go:376-388
     if (sk.GetScheme() != this) throw ErrTypeMismatch();
     if (ct.size() != CiphertextSize()) throw ErrCiphertextSize();
-    Bytes ss(32);
-    check(round3_ ? cb200_kyber_kem_decaps(k_, sk.MarshalBinary().data(), 0, ct.data(), ss.data(), 1)
-                  : cb200_mlkem_decaps(k_, sk.MarshalBinary().data(), 0, ct.data(), ss.data(), nullptr, 1));
+    Bytes ss;
+    DecapsulateBatch(sk.MarshalBinary(), ct, ss);
     return ss;
   }
-  // ---- batch entry points (keys: one packed key = shared, or n keys back to back)
+  // ---- batch entry points (keys: one packed key = shared by the batch, or n keys back to back)
   void EncapsulateBatch(const Bytes& eks, const Bytes& seeds, Bytes& cts, Bytes& sss) const {
-    if (seeds.size() % 32) throw ErrSeedSize();
-    const size_t n = seeds.size() / 32;
-    const bool shared = eks.size() == PublicKeySize();
-    if (!shared && eks.size() != n * PublicKeySize()) throw ErrPubKeySize();
+    const size_t es = EncapsulationSeedSize(), pks = PublicKeySize();
+    if (seeds.size() % es) throw ErrSeedSize();
+    const size_t n = seeds.size() / es;
+    const bool shared = eks.size() == pks;
+    if (!shared && eks.size() != n * pks) throw ErrPubKeySize();
+    const size_t stride = shared ? 0 : pks;
     cts.resize(n * CiphertextSize());
-    sss.resize(n * 32);
-    check(round3_ ? cb200_kyber_kem_encaps(k_, eks.data(), shared ? 0 : PublicKeySize(), seeds.data(), cts.data(), sss.data(), n)
-                  : cb200_mlkem_encaps(k_, eks.data(), shared ? 0 : PublicKeySize(), seeds.data(), cts.data(), sss.data(), nullptr, n));
+    sss.resize(n * SharedKeySize());
+    switch (kind_) {
+      case MLKEM: check(cb200_mlkem_encaps(k_, eks.data(), stride, seeds.data(), cts.data(), sss.data(), nullptr, n)); break;
+      case KYBER3: check(cb200_kyber_kem_encaps(k_, eks.data(), stride, seeds.data(), cts.data(), sss.data(), n)); break;
+      case XWING: check(cb200_xwing_encaps(eks.data(), stride, seeds.data(), cts.data(), sss.data(), nullptr, n)); break;
+      case HYBRID: check(cb200_hybrid_encaps(k_, eks.data(), stride, seeds.data(), cts.data(), sss.data(), nullptr, n)); break;
+    }
   }
   void DecapsulateBatch(const Bytes& dks, const Bytes& cts, Bytes& sss) const {
+    const size_t sks = PrivateKeySize();
     if (cts.size() % CiphertextSize()) throw ErrCiphertextSize();
     const size_t n = cts.size() / CiphertextSize();
-    const bool shared = dks.size() == PrivateKeySize();
-    if (!shared && dks.size() != n * PrivateKeySize()) throw ErrPrivKeySize();
-    sss.resize(n * 32);
-    check(round3_ ? cb200_kyber_kem_decaps(k_, dks.data(), shared ? 0 : PrivateKeySize(), cts.data(), sss.data(), n)
-                  : cb200_mlkem_decaps(k_, dks.data(), shared ? 0 : PrivateKeySize(), cts.data(), sss.data(), nullptr, n));
+    const bool shared = dks.size() == sks;
+    if (!shared && dks.size() != n * sks) throw ErrPrivKeySize();
+    const size_t stride = shared ? 0 : sks;
+    sss.resize(n * SharedKeySize());
+    switch (kind_) {
+      case MLKEM: check(cb200_mlkem_decaps(k_, dks.data(), stride, cts.data(), sss.data(), nullptr, n)); break;
+      case KYBER3: check(cb200_kyber_kem_decaps(k_, dks.data(), stride, cts.data(), sss.data(), n)); break;
+      case XWING: check(cb200_xwing_decaps(dks.data(), stride, cts.data(), sss.data(), n)); break;
+      case HYBRID: {
+        if (!shared || n == 1) {
+          check(cb200_hybrid_decaps(k_, dks.data(), sks, cts.data(), sss.data(), nullptr, n));
+        } else {  // the hybrid decapsulation flow takes one key per operation
+          Bytes rep(n * sks);
+          for (size_t i = 0; i < n; i++) std::copy(dks.begin(), dks.end(), rep.begin() + i * sks);
+          check(cb200_hybrid_decaps(k_, rep.data(), sks, cts.data(), sss.data(), nullptr, n));
+        }
+        break;
+      }
+    }
   }
   void DeriveKeyPairBatch(const Bytes& seeds, Bytes& eks, Bytes& dks) const {
-    if (seeds.size() % 64) throw ErrSeedSize();
-    const size_t n = seeds.size() / 64;
+    if (seeds.size() % SeedSize()) throw ErrSeedSize();
+    const size_t n = seeds.size() / SeedSize();
     eks.resize(n * PublicKeySize());
     dks.resize(n * PrivateKeySize());
-    check(round3_ ? cb200_kyber_kem_keygen(k_, seeds.data(), eks.data(), dks.data(), n)
-                  : cb200_mlkem_keygen(k_, seeds.data(), eks.data(), dks.data(), n));
+    switch (kind_) {
+      case MLKEM: check(cb200_mlkem_keygen(k_, seeds.data(), eks.data(), dks.data(), n)); break;
+      case KYBER3: check(cb200_kyber_kem_keygen(k_, seeds.data(), eks.data(), dks.data(), n)); break;
+      case XWING:  // the packed private key is the seed itself (xwing.go:68-73)
+        check(cb200_xwing_keygen(seeds.data(), eks.data(), n));
+        dks = seeds;
+        break;
+      case HYBRID: check(cb200_hybrid_keygen(k_, seeds.data(), eks.data(), dks.data(), n)); break;
+    }
   }
   int k() const { return k_; }
+  Kind kind() const { return kind_; }
 
  private:
   static void check(int rc) {
@@ -167,13 +206,29 @@ class Scheme {  // kem.Scheme (kem/kem.go:33-82) for ML-KEM-512/768/1024 and rou
     throw Error(cb200_last_error());
   }
   std::string name_;
-  int k_;
-  bool round3_;
+  Kind kind_;
+  int k_;  // K of the lattice scheme, or the hybrid identifier
 };
 
 inline PublicKey PrivateKey::Public() const {
-  const int k = scheme_->k();
-  return PublicKey(scheme_, Bytes(packed_.begin() + 384 * k, packed_.begin() + 384 * k + 384 * k + 32));
+  const Scheme* s = scheme_;
+  if (s->kind() == Scheme::XWING) {  // sk is the seed: derive again (xwing.go:278-281)
+    Bytes pk, sk;
+    s->DeriveKeyPairBatch(packed_, pk, sk);
+    return PublicKey(s, std::move(pk));
+  }
+  if (s->kind() == Scheme::HYBRID) {  // {first.Public(), second.Public()} (hybrid.go:151-153, xkem.go:68-84)
+    const size_t dk = s->PrivateKeySize() - 32, ek = s->PublicKeySize() - 32, kk = (dk - 96) / 768;
+    const bool x_first = s->k() != CB200_HYBRID_X25519MLKEM768;
+    Bytes pk(s->PublicKeySize());
+    const uint8_t* skm = packed_.data() + (x_first ? 32 : 0);
+    const uint8_t* skx = packed_.data() + (x_first ? 0 : dk);
+    std::copy(skm + 384 * kk, skm + 384 * kk + ek, pk.begin() + (x_first ? 32 : 0));
+    if (cb200_x25519(skx, nullptr, pk.data() + (x_first ? 0 : ek), nullptr, 1)) throw Error(cb200_last_error());
+    return PublicKey(s, std::move(pk));
+  }
+  const int k = s->k();
+  return PublicKey(s, Bytes(packed_.begin() + 384 * k, packed_.begin() + 384 * k + 384 * k + 32));
 }
 
 inline std::string lower(std::string s) {
@@ -183,7 +238,10 @@ inline std::string lower(std::string s) {
 inline const std::vector<const Scheme*>& All() {  // kem/schemes/schemes.go:75
   static const Scheme s512("ML-KEM-512", 2), s768("ML-KEM-768", 3), s1024("ML-KEM-1024", 4);
   static const Scheme k512("Kyber512", 2, true), k768("Kyber768", 3, true), k1024("Kyber1024", 4, true);
-  static const std::vector<const Scheme*> all = {&s512, &s768, &s1024, &k512, &k768, &k1024};
+  static const Scheme xw("X-Wing", Scheme::XWING, 0), xm("X25519MLKEM768", Scheme::HYBRID, CB200_HYBRID_X25519MLKEM768),
+      k7x("Kyber768-X25519", Scheme::HYBRID, CB200_HYBRID_KYBER768_X25519),
+      k5x("Kyber512-X25519", Scheme::HYBRID, CB200_HYBRID_KYBER512_X25519);
+  static const std::vector<const Scheme*> all = {&s512, &s768, &s1024, &k512, &k768, &k1024, &k5x, &k7x, &xm, &xw};
   return all;
 }
 inline const Scheme* ByName(const std::string& name) {  // kem/schemes/schemes.go:70 (nullptr = no such scheme)

@@ -112,6 +112,45 @@ int main() {
     hex("ct", enc.first);
     hex("ss", enc.second);
   }
+  for (const char* name : {"X-Wing", "X25519MLKEM768", "kyber768-x25519", "Kyber512-X25519"}) {
+    const kem::Scheme* s = kem::ByName(name);
+    REQUIRE(s != nullptr);
+    Bytes seed(s->SeedSize()), eseed(s->EncapsulationSeedSize());
+    for (size_t i = 0; i < seed.size(); i++) seed[i] = (uint8_t)(i * 5 + 3);
+    for (size_t i = 0; i < eseed.size(); i++) eseed[i] = (uint8_t)(i * 9 + 1);
+    auto kp = s->DeriveKeyPair(seed);
+    REQUIRE(kp.first.MarshalBinary().size() == s->PublicKeySize() && kp.second.MarshalBinary().size() == s->PrivateKeySize());
+    REQUIRE(kp.second.Public().Equal(kp.first));
+    auto enc = s->EncapsulateDeterministically(kp.first, eseed);
+    REQUIRE(enc.first.size() == s->CiphertextSize() && enc.second.size() == s->SharedKeySize());
+    REQUIRE(s->Decapsulate(kp.second, enc.first) == enc.second);
+    // batch with one shared key: last element equals the single call
+    Bytes seeds(s->EncapsulationSeedSize() * 40), cts, sss, back;
+    for (size_t i = 0; i < seeds.size(); i++) seeds[i] = (uint8_t)(i * 31 + 7);
+    s->EncapsulateBatch(kp.first.MarshalBinary(), seeds, cts, sss);
+    s->DecapsulateBatch(kp.second.MarshalBinary(), cts, back);
+    REQUIRE(back == sss);
+    if (s->kind() == kem::Scheme::HYBRID) {  // kem/hybrid/xkem_test.go: small-order X25519 share -> kem.ErrPubKey
+      const uint8_t low[32] = {0xe0, 0xeb, 0x7a, 0x7c, 0x3b, 0x41, 0xb8, 0xae, 0x16, 0x56, 0xe3, 0xfa, 0xf1, 0x9f, 0xc4, 0x6a,
+                               0xda, 0x09, 0x8d, 0xeb, 0x9c, 0x32, 0xb1, 0xfd, 0x86, 0x62, 0x05, 0x16, 0x5f, 0x49, 0xb8, 0x00};
+      const bool x_first = s->k() != CB200_HYBRID_X25519MLKEM768;
+      Bytes badpk = kp.first.MarshalBinary();
+      std::copy(low, low + 32, x_first ? badpk.begin() : badpk.end() - 32);
+      bool threw2 = false;
+      try { s->EncapsulateDeterministically(s->UnmarshalBinaryPublicKey(badpk), eseed); } catch (const kem::ErrPubKey&) { threw2 = true; }
+      REQUIRE(threw2);
+      Bytes badct = enc.first;
+      std::copy(low, low + 32, x_first ? badct.begin() : badct.end() - 32);
+      threw2 = false;
+      try { s->Decapsulate(kp.second, badct); } catch (const kem::ErrPubKey&) { threw2 = true; }
+      REQUIRE(threw2);
+    }
+    printf("scheme=%s\n", s->Name().c_str());
+    hex("pk", kp.first.MarshalBinary());
+    hex("sk", kp.second.MarshalBinary());
+    hex("ct", enc.first);
+    hex("ss", enc.second);
+  }
   {
     const sign::Scheme* r3 = sign::ByName("dilithium3");
     REQUIRE(r3 != nullptr && !r3->SupportsContext() && r3->SignatureSize() == 3293);

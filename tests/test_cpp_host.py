@@ -65,3 +65,12 @@ def test_cpp_host_layer_matches_oracle():
     b = blocks["Dilithium3"]
     assert (b["pk"], b["sk"]) == (pk, sk)
     assert b["sig"] == oracle.mldsa_sign(3, sk, b"hello")[0]
+    hseed64, hseed32 = bytes((i * 5 + 3) & 0xFF for i in range(64)), bytes((i * 5 + 3) & 0xFF for i in range(32))
+    e32, e64 = bytes((i * 9 + 1) & 0xFF for i in range(32)), bytes((i * 9 + 1) & 0xFF for i in range(64))
+    b = blocks["X-Wing"]
+    assert (b["pk"], b["sk"]) == (oracle.xwing_keygen(hseed32), hseed32)
+    assert (b["ct"], b["ss"]) == oracle.xwing_encaps(b["pk"], e64)
+    for name in ("X25519MLKEM768", "Kyber768-X25519", "Kyber512-X25519"):
+        b = blocks[name]
+        assert (b["pk"], b["sk"]) == oracle.hybrid_keygen(name, hseed64)
+        assert (b["ct"], b["ss"], 0) == oracle.hybrid_encaps(name, b["pk"], e32)

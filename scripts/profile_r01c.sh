@@ -8,12 +8,10 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-fil
     python bench.py --steps 1 --warmup 3 --batch-log2 17 --no-cpu-baseline > gpurun_out/bench_under_ncu_c.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"sample_kernel|encrypt_kernel|hash_ek" -s 6 -c 3 -o gpurun_out/prof_mlkem_c \
     python bench.py --steps 1 --warmup 3 --batch-log2 16 --no-cpu-baseline --no-ntt > gpurun_out/prof_mlkem_c.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"mask_kernel|yntt_kernel|w_kernel|challenge_kernel|cntt_mask|response_kernel|finalize_kernel" -c 10 \
-    -o gpurun_out/prof_sign_e python scripts/sign_once.py > gpurun_out/prof_sign_e.log 2>&1
+# (the ncu reports of the signing kernels and of x25519_kernel are taken by scripts/profile_r01c_sign.sh: gpurun_out/ is
+#  limited to 64 MiB per call)
 ncu --set full --clock-control none --import-source on -k regex:"ntt_kernel" -s 4 -c 4 -o gpurun_out/prof_ntt_c \
     python scripts/time_ring.py > gpurun_out/prof_ntt_c.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"x25519_kernel" -c 1 -o gpurun_out/prof_x25519 \
-    python scripts/x25519_once.py > gpurun_out/prof_x25519.log 2>&1
 python bench.py > gpurun_out/bench_r01c.json 2> gpurun_out/bench_r01c.err
 python bench.py --workload mldsa65 > gpurun_out/bench_mldsa_r01c.json 2> gpurun_out/bench_mldsa_r01c.err
 python bench.py --impl reference --steps 3 > gpurun_out/bench_ref_r01c.json 2>&1

@@ -950,8 +950,18 @@ __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restric
     const size_t slot = b & 0xffffffu;
     const uint8_t* ct = reinterpret_cast<const uint8_t*>(ctilde + (CTILDE / 8) * slot);
     for (int i = lane; i < CTILDE; i += 32) sg[i] = ct[i];
+    // z: word-aligned staging rows into a signature that starts at an arbitrary byte (SIG_BYTES is odd): bytes up to
+    // the first aligned destination word, then aligned words assembled from two source words, then the tail bytes
     const uint8_t* zs = zbuf + slot * (size_t)(L * POLY_Z);
-    for (int i = lane; i < L * POLY_Z; i += 32) sg[CTILDE + i] = zs[i];
+    const uint32_t* zw = reinterpret_cast<const uint32_t*>(zs);
+    uint8_t* zd = sg + CTILDE;
+    constexpr int ZB = L * POLY_Z;
+    const int head = (int)((4 - (reinterpret_cast<uintptr_t>(zd) & 3)) & 3);
+    if (lane < head) zd[lane] = zs[lane];
+    uint32_t* dw = reinterpret_cast<uint32_t*>(zd + head);
+    const int nw = (ZB - head) >> 2;
+    for (int j = lane; j < nw; j += 32) dw[j] = __funnelshift_r(zw[j], zw[j + 1], 8 * head);
+    for (int i = head + 4 * nw + lane; i < ZB; i += 32) zd[i] = zs[i];
     if (lane == 0) {
       uint8_t* hb = sg + CTILDE + L * POLY_Z;  // PackHint (internal/pack.go:77-95)
       int off = 0;

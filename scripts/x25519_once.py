@@ -1,4 +1,4 @@
-"""One X25519 Shared batch on device tensors (development aid for an ncu capture of x25519_kernel)."""
+"""X25519 KeyGen + Shared on device tensors, timed with CUDA events (development aid; also the ncu target for x25519_kernel)."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -13,4 +13,11 @@ k = torch.randint(0, 256, (n, 32), generator=g, device="cuda", dtype=torch.uint8
 p = hybrid.x25519_keygen(k)
 s, ok = hybrid.x25519_shared(k, p)
 torch.cuda.synchronize()
-print(n, bool(ok.all()))
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(3):
+    hybrid.x25519_keygen(k)
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 3
+print(n, bool(ok.all()), "%.3f ms per batch, %.3e scalar mult/s" % (ms, n / (ms * 1e-3)))

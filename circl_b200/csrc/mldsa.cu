@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "../../include/circl_b200.h"
 #include "context.h"
@@ -190,29 +191,37 @@ __global__ void __launch_bounds__(kExpThreads) expand_a_kernel(const uint8_t* __
   a[4] = (uint64_t)j | ((uint64_t)i << 8) | (0x1full << 16);  // nonce = (i<<8)+j, little endian
   a[20] = 0x8000000000000000ull;                               // SHAKE128 rate 168
   uint32_t* row = rows + threadIdx.x * kExpRow;
-  int ctr = 0;
+  // 56 candidates of 3 bytes per block (23 bits each); every candidate is stored at the write pointer (one slack
+  // word per row) and only the pointer advance is predicated.  The first four blocks cannot fill the row (224 < 256).
+  auto parse = [&](uint32_t* wp, auto checked) {
+#pragma unroll
+    for (int f = 0; f < 56; f++) {
+      const int bit = 24 * f, wi = bit >> 5, sh = bit & 31;
+      const uint32_t lo = (uint32_t)(a[wi >> 1] >> (32 * (wi & 1)));
+      uint32_t d;
+      if (sh + 24 <= 32) {
+        d = (lo >> sh) & 0x7fffff;
+      } else {
+        const uint32_t hi = (uint32_t)(a[(wi + 1) >> 1] >> (32 * ((wi + 1) & 1)));
+        d = __funnelshift_r(lo, hi, sh) & 0x7fffff;
+      }
+      *wp = d;
+      bool acc = d < Q;
+      if (decltype(checked)::value) acc = acc && wp < row + N;
+      wp += acc ? 1 : 0;
+    }
+    return wp;
+  };
+  uint32_t* wp = row;
+#pragma unroll 1
+  for (int b = 0; b < 4; b++) {
+    keccak::f1600(a);
+    wp = parse(wp, std::false_type{});
+  }
   do {
     keccak::f1600(a);
-#pragma unroll
-    for (int g = 0; g < 7; g++) {  // 3 words -> 8 candidates of 3 bytes
-      const uint64_t w0 = a[3 * g], w1 = a[3 * g + 1], w2 = a[3 * g + 2];
-      uint32_t t[8];
-      t[0] = (uint32_t)w0;
-      t[1] = (uint32_t)(w0 >> 24);
-      t[2] = (uint32_t)(w0 >> 48) | ((uint32_t)w1 << 16);
-      t[3] = (uint32_t)(w1 >> 8);
-      t[4] = (uint32_t)(w1 >> 32);
-      t[5] = (uint32_t)(w1 >> 56) | ((uint32_t)w2 << 8);
-      t[6] = (uint32_t)(w2 >> 16);
-      t[7] = (uint32_t)(w2 >> 40);
-#pragma unroll
-      for (int q = 0; q < 8; q++) {
-        const uint32_t d = t[q] & 0x7fffff;
-        row[ctr] = d;
-        ctr += (d < Q && ctr < N);
-      }
-    }
-  } while (ctr < N);
+    wp = parse(wp, std::true_type{});
+  } while (wp < row + N);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int p = warp; p < kExpThreads; p += kExpThreads / 32) {

@@ -101,33 +101,27 @@ __global__ void __launch_bounds__(128) g_kernel(const uint8_t* __restrict__ m, c
 }
 
 // ------------------------------------------------------------------ 2. samplers
-// 12-bit rejection sampling of one 168-byte SHAKE128 block (sample.go:203-233).
-// Accepted coefficients are appended to row[ctr...] (this thread's shared-memory row);
-// returns the new ctr (<= 256).
-__device__ __forceinline__ int reject_block(const uint64_t (&a)[25], int16_t* row, int ctr) {
+// 12-bit rejection sampling of one 168-byte SHAKE128 block (sample.go:203-233): 112 candidates, field f at bit 12 f
+// of the block (d1 = low, d2 = high 12 bits of each 3-byte group, in that order).  `wp` is the 32-bit shared-memory
+// address of the next free int16 of this thread's row: every candidate is stored there (clamped to the slack entry
+// behind the row once 256 are in) and only the advance is predicated -- per candidate a shift/mask pair, a min, a
+// compare, one STS and one predicated add, all on 32-bit registers.  Returns the new address (>= end when full).
+__device__ __forceinline__ uint32_t reject_block(const uint64_t (&a)[25], uint32_t wp, uint32_t end) {
 #pragma unroll
-  for (int g = 0; g < 7; g++) {
-    const uint64_t w0 = a[3 * g], w1 = a[3 * g + 1], w2 = a[3 * g + 2];
-    uint32_t t[8];
-    t[0] = (uint32_t)w0 & 0xffffff;
-    t[1] = (uint32_t)(w0 >> 24) & 0xffffff;
-    t[2] = (uint32_t)(w0 >> 48) | (((uint32_t)w1 & 0xff) << 16);
-    t[3] = (uint32_t)(w1 >> 8) & 0xffffff;
-    t[4] = (uint32_t)(w1 >> 32) & 0xffffff;
-    t[5] = (uint32_t)(w1 >> 56) | (((uint32_t)w2 & 0xffff) << 8);
-    t[6] = (uint32_t)(w2 >> 16) & 0xffffff;
-    t[7] = (uint32_t)(w2 >> 40);
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const uint32_t d1 = t[j] & 0xfff, d2 = t[j] >> 12;
-      // rows have 2 slack entries, so the store is unconditional and only the counter is predicated
-      row[ctr] = (int16_t)d1;
-      ctr += (d1 < (uint32_t)Q && ctr < N);
-      row[ctr] = (int16_t)d2;
-      ctr += (d2 < (uint32_t)Q && ctr < N);
+  for (int f = 0; f < 112; f++) {
+    const int bit = 12 * f, wi = bit >> 5, sh = bit & 31;
+    const uint32_t lo = (uint32_t)(a[wi >> 1] >> (32 * (wi & 1)));
+    uint32_t d;
+    if (sh + 12 <= 32) {
+      d = (lo >> sh) & 0xfff;
+    } else {
+      const uint32_t hi = (uint32_t)(a[(wi + 1) >> 1] >> (32 * ((wi + 1) & 1)));
+      d = __funnelshift_r(lo, hi, sh) & 0xfff;
     }
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(min(wp, end)), "h"((uint16_t)d) : "memory");
+    wp += (d < (uint32_t)Q) ? 2u : 0u;
   }
-  return ctr;
+  return wp;
 }
 
 // CBD_2 of 128 bytes (sample.go:80-93), written as 256 packed int16
@@ -216,11 +210,12 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
     a[4] = (uint64_t)(transpose ? i : j) | ((uint64_t)(transpose ? j : i) << 8) | (0x1full << 16);
     a[20] = 0x8000000000000000ull;                               // rate 168
     int16_t* row = reinterpret_cast<int16_t*>(rows + threadIdx.x * kRowWords);
-    int ctr = 0;
+    uint32_t wp = smem_u32(row);
+    const uint32_t wend = wp + 2 * N;
     do {
       keccak::f1600(a);
-      ctr = reject_block(a, row, ctr);
-    } while (ctr < N);
+      wp = reject_block(a, wp, wend);
+    } while (wp < wend);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int p = warp; p < (int)blockDim.x; p += blockDim.x / 32) {

@@ -120,6 +120,73 @@ __global__ void __launch_bounds__(256) ew_kernel(uint4* __restrict__ out, const 
   }
 }
 
+// Forward NTT with the input staged by the TMA engine.  Every octet owns two 608-byte slots of shared memory; lane 0
+// of the octet bulk-copies the next polynomial (512 B, one mbarrier per slot) into the free slot while the octet
+// works on the current one, whose slot -- once its coefficients are in registers -- is reused as the S<->C
+// transposition tile.  Slots are kPolyWords = 152 words apart, i.e. 24 banks: the raw S-layout reads
+// (word 8s + v) of the four octets of a warp fall into 32 distinct banks.  The global loads of the plain kernel
+// (16 dependent-latency LDG per lane and iteration) become shared-memory loads behind an mbarrier wait that has
+// normally completed an iteration earlier.
+__global__ void __launch_bounds__(kThreads, 6) ntt_fwd_tma_kernel(uint32_t* __restrict__ polys, size_t n,
+                                                                   const TwPair* __restrict__ tw) {
+  __shared__ __align__(16) uint32_t slots[kOctetsPerCta * 2 * kPolyWords];
+  __shared__ __align__(16) TwPair tws[128];
+  __shared__ __align__(8) uint64_t bar, bars[kOctetsPerCta * 2];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int oct = lane >> 3, v = lane & 7, ob = warp * 4 + oct;
+  uint32_t* slot0 = slots + ob * 2 * kPolyWords;
+  uint64_t* obar = bars + ob * 2;
+  if (threadIdx.x == 0) mbar_init(&bar, 1);
+  if (v == 0) {
+    mbar_init(obar, 1);
+    mbar_init(obar + 1, 1);
+  }
+  fence_barrier_init();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, sizeof(tws));
+    bulk_g2s(tws, tw, sizeof(tws), &bar);
+  }
+  const size_t stride = (size_t)gridDim.x * kOctetsPerCta, first = ((size_t)blockIdx.x * 4 + warp) * 4;
+  const size_t n_it = first < n ? (n - first + stride - 1) / stride : 0;  // the same for the four octets of a warp
+  auto poly_of = [&](size_t it) {
+    const size_t p = first + it * stride + oct;
+    return polys + (p < n ? p : n - 1) * (N / 2);  // idle octets recompute the last polynomial, never store
+  };
+  auto issue = [&](size_t it) {  // lane 0 of the octet
+    uint64_t* b = obar + (it & 1);
+    mbar_expect_tx(b, N * 2);
+    bulk_g2s(slot0 + (it & 1) * kPolyWords, poly_of(it), N * 2, b);
+  };
+  if (v == 0) {
+    if (n_it > 0) issue(0);
+    if (n_it > 1) issue(1);
+  }
+  mbar_wait(&bar, 0);
+  LaneTw t;
+  load_lane_tw(t, tws, v);
+  for (size_t it = 0; it < n_it; it++) {
+    uint32_t* slot = slot0 + (it & 1) * kPolyWords;
+    const bool active = first + it * stride + oct < n;
+    mbar_wait(obar + (it & 1), (uint32_t)((it >> 1) & 1));
+    int32_t r[32];
+#pragma unroll
+    for (int s = 0; s < 16; s++) unpack2(slot[8 * s + v], r[2 * s], r[2 * s + 1]);
+    __syncwarp();  // the raw polynomial is in registers: the slot becomes the transposition tile
+    fwd_pass_S(r);
+    store_S(slot, v, r);
+    __syncwarp();
+    load_C(slot, v, r);
+    __syncwarp();  // every lane is done with the tile: it may be refilled
+    if (v == 0 && it + 2 < n_it) {
+      fence_proxy_async();  // order the generic-proxy accesses above before the asynchronous write into the slot
+      issue(it + 2);
+    }
+    fwd_pass_C(r, t);
+    if (active) gstore_C(poly_of(it), v, r);
+  }
+}
+
 static int grid_for(size_t units, int per_cta, int ctas_per_sm) {
   size_t want = (units + per_cta - 1) / per_cta;
   size_t cap = (size_t)kNumSM * ctas_per_sm;
@@ -137,7 +204,7 @@ int launch_kyber_ntt(int16_t* d_polys, size_t n, int inverse, const void* tw, cu
   if (inverse)
     ntt_kernel<true><<<grid, kThreads, 0, st>>>((uint32_t*)d_polys, n, (const TwPair*)tw);
   else
-    ntt_kernel<false><<<grid, kThreads, 0, st>>>((uint32_t*)d_polys, n, (const TwPair*)tw);
+    ntt_fwd_tma_kernel<<<grid_for(n, kOctetsPerCta, 6), kThreads, 0, st>>>((uint32_t*)d_polys, n, (const TwPair*)tw);
   CB200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -563,7 +563,7 @@ def main():
                 "frac": achieved / peak, "traffic": ncu_traffic(dom_name, units_per_launch), "peak_kind": peak_kind,
                 "share_of_step": dom["ms_total"] / total_kernel_ms,
                 "note": "path is integer-ALU (Keccak) bound, not HBM bound (ncu: sample_kernel ALU pipe 89%% active, "
-                        "profiles/r01b_ncu_mlkem.txt); achieved = %d algorithmic B/op x %d ops per launch / mean "
+                        "profiles/r01c_ncu_mlkem.txt); achieved = %d algorithmic B/op x %d ops per launch / mean "
                         "launch time; traffic = ncu dram bytes per launch" % (wl["bytes_per_op"], int(units_per_launch)),
                 "kernels_ms_per_step": {k_: round(v["ms_total"], 4) for k_, v in kernels.items()}}
     # The binding resource is the integer-ALU pipe, so state that roofline too: Keccak-f[1600] permutations

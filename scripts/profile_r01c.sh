@@ -10,7 +10,7 @@ ncu --set full --clock-control none --import-source on -k regex:"sample_kernel|e
     python bench.py --steps 1 --warmup 3 --batch-log2 16 --no-cpu-baseline --no-ntt > gpurun_out/prof_mlkem_c.log 2>&1
 # (the ncu reports of the signing kernels and of x25519_kernel are taken by scripts/profile_r01c_sign.sh: gpurun_out/ is
 #  limited to 64 MiB per call)
-ncu --set full --clock-control none --import-source on -k regex:"ntt_kernel" -s 4 -c 4 -o gpurun_out/prof_ntt_c \
+ncu --set full --clock-control none --import-source on -k regex:"ntt_kernel|ntt_fwd_tma_kernel" -s 4 -c 6 -o gpurun_out/prof_ntt_c \
     python scripts/time_ring.py > gpurun_out/prof_ntt_c.log 2>&1
 python bench.py > gpurun_out/bench_r01c.json 2> gpurun_out/bench_r01c.err
 python bench.py --workload mldsa65 > gpurun_out/bench_mldsa_r01c.json 2> gpurun_out/bench_mldsa_r01c.err

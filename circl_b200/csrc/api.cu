@@ -245,7 +245,8 @@ void cb200_shutdown(void) {
   if (c.kyber_tw) cudaFree(c.kyber_tw);
   if (c.dil_tw) cudaFree(c.dil_tw);
   if (c.small) cudaFree(c.small);
-  c.kyber_tw = c.dil_tw = c.small = nullptr;
+  if (c.x25519_table) cudaFree(c.x25519_table);
+  c.kyber_tw = c.dil_tw = c.small = c.x25519_table = nullptr;
   if (c.own) cudaStreamDestroy(c.own);
   c.own = c.cur = nullptr;
   c.ready = false;

@@ -28,6 +28,7 @@ struct Ctx {
   void* kyber_tw = nullptr;     // 128 x {zeta, zetaq}
   void* dil_tw = nullptr;       // 256 x {zeta, invzeta}
   void* small = nullptr;        // 256-byte device buffer (ML-DSA context string)
+  void* x25519_table = nullptr; // 32 KiB: multiples 1..8 of 256^i B for the fixed-base X25519 KeyGen (x25519.cuh)
   std::atomic<uint64_t> launches{0};
   bool profiling = false;
   std::vector<ProfRec> prof;

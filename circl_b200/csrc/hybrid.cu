@@ -50,6 +50,18 @@ __global__ void __launch_bounds__(128) x25519_kernel(const uint8_t* __restrict__
   if (status && !ok) status[i] |= 1;
 }
 
+// out[i] = X25519(scalar[i], base point) through the fixed-base table (x25519.cuh): x25519.KeyGen (key.go:44-46)
+__global__ void __launch_bounds__(128) x25519_base_kernel(const uint8_t* __restrict__ scalars, size_t s_stride,
+                                                          uint8_t* __restrict__ out, size_t o_stride,
+                                                          const int32_t* __restrict__ table, size_t n) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  uint32_t k[8], r[8];
+  ld8(k, scalars + i * s_stride);
+  x25519::scalarmult_base(r, k, table);
+  st8(out + i * o_stride, r);
+}
+
 // out[i] = SHAKE256(in[i] (inlen bytes, <= 64), outlen <= 128 bytes), thread per op; inlen and outlen multiples of 8
 __global__ void __launch_bounds__(128) shake_kernel(const uint8_t* __restrict__ in, size_t in_stride, int inlen,
                                                     uint8_t* __restrict__ out, size_t out_stride, int outlen, size_t n) {
@@ -123,7 +135,10 @@ static void copy_rows(const uint8_t* src, size_t ss, uint8_t* dst, size_t ds, si
 static void x25519_launch(const uint8_t* k, size_t ks_, const uint8_t* p, size_t ps, uint8_t* o, size_t os, uint8_t* status,
                           size_t n, cudaStream_t st) {
   KernelScope ks(KID_X25519, st);
-  x25519_kernel<<<blocks(n, 128), 128, 0, st>>>(k, ks_, p, ps, o, os, status, n);
+  if (p)
+    x25519_kernel<<<blocks(n, 128), 128, 0, st>>>(k, ks_, p, ps, o, os, status, n);
+  else  // KeyGen: the base point never has small order, status stays untouched
+    x25519_base_kernel<<<blocks(n, 128), 128, 0, st>>>(k, ks_, o, os, (const int32_t*)ctx().x25519_table, n);
 }
 static void shake_launch(const uint8_t* in, size_t is, int inlen, uint8_t* out, size_t os, int outlen, size_t n,
                          cudaStream_t st) {

@@ -24,6 +24,21 @@ int main() {
     int wok = orc_x25519(want, (const uint8_t*)k, (const uint8_t*)p);
     if (memcmp(want, r, 32) || (int)ok != wok) { bad++; printf("mismatch t=%d ok=%d wok=%d\n", t, (int)ok, wok); }
   }
+  // fixed-base path: table built on the host exactly as cb200_init does, results against the oracle's ladder
+  static int32_t table[cb200::x25519::kBaseTableWords];
+  cb200::x25519::build_base_table(table);
+  for (int t = 0; t < 400; t++) {
+    uint32_t k[8], r[8];
+    for (int i = 0; i < 8; i++) k[i] = (uint32_t)rnd();
+    if (t == 0) for (int i = 0; i < 8; i++) k[i] = 0xffffffffu;   // every digit carries; top nibble 7 + carry
+    if (t == 1) for (int i = 0; i < 8; i++) k[i] = 0;             // clamp only
+    if (t == 2) for (int i = 0; i < 8; i++) k[i] = 0x77777777u;
+    if (t == 3) for (int i = 0; i < 8; i++) k[i] = 0x88888888u;
+    cb200::x25519::scalarmult_base(r, k, table);
+    uint8_t want[32];
+    orc_x25519(want, (const uint8_t*)k, nullptr);
+    if (memcmp(want, r, 32)) { bad++; printf("fixed-base mismatch t=%d\n", t); }
+  }
   printf("bad=%d\n", bad);
   return bad != 0;
 }

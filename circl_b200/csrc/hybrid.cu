@@ -30,7 +30,7 @@ __device__ __forceinline__ void st8(uint8_t* p, const uint32_t (&w)[8]) {
 
 // out[i] = X25519(scalar[i], point[i] or the base point); status[i] |= 1 when the point is of small order
 // (x25519.Shared returning false -> kem.ErrPubKey in xkem.go:150-152).  All strides are multiples of 4.
-__global__ void __launch_bounds__(128) x25519_kernel(const uint8_t* __restrict__ scalars, size_t s_stride,
+__global__ void __launch_bounds__(128, 2) x25519_kernel(const uint8_t* __restrict__ scalars, size_t s_stride,
                                                      const uint8_t* __restrict__ points, size_t p_stride,
                                                      uint8_t* __restrict__ out, size_t o_stride, uint8_t* __restrict__ status,
                                                      size_t n) {

@@ -20,4 +20,11 @@ for _ in range(3):
 b.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(b) / 3
-print(n, bool(ok.all()), "%.3f ms per batch, %.3e scalar mult/s" % (ms, n / (ms * 1e-3)))
+print(n, bool(ok.all()), "KeyGen %.3f ms per batch, %.3e /s" % (ms, n / (ms * 1e-3)))
+a.record()
+for _ in range(3):
+    hybrid.x25519_shared(k, p)
+b.record()
+torch.cuda.synchronize()
+ms = a.elapsed_time(b) / 3
+print(n, "Shared %.3f ms per batch, %.3e /s" % (ms, n / (ms * 1e-3)))

@@ -1627,7 +1627,9 @@ static int keygen_device(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t 
 template <class P>
 static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs, const uint64_t* msg_off,
                        const uint8_t* ctxstr, int ctxlen, const uint8_t* rnd, uint8_t* sig, uint8_t* status, size_t n,
-                       int internal, cudaStream_t st, int slot, uint64_t* attempts_out) {
+                       int internal, cudaStream_t st, int slot, uint64_t* attempts_out, volatile uint32_t* h_count) {
+  // h_count: 8 bytes of pinned host memory for the per-round counter (owned by the caller: the host-pointer path
+  // keeps per-op status bytes in the same pinned block)
   MLDSA_USE(P);
   Ctx& c = ctx();
   const bool shared = sk_stride == 0;
@@ -1703,10 +1705,6 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   }
   CB200_CUDA(cudaGetLastError());
 
-  void* pin = nullptr;
-  rc = ensure_pinned(n + 64, &pin);  // the caller may be using the first n bytes for status staging
-  if (rc) return rc;
-  volatile uint32_t* h_count = (volatile uint32_t*)((char*)pin + ((n + 15) & ~(size_t)15));
   size_t nact = n;
   int cur = 0;
   uint64_t total_attempts = 0;
@@ -1893,47 +1891,89 @@ int cb200_mldsa_sign(int mode, const uint8_t* sk, size_t sk_stride, const uint8_
       CB200_CUDA(cudaMemcpyAsync(ctx().small, context, ctxlen, cudaMemcpyHostToDevice, ctx().cur));
       dctx = (const uint8_t*)ctx().small;
     }
+    void* pin0 = nullptr;
+    rc = ensure_pinned(64, &pin0);
+    if (rc) return rc;
     return dispatch_sign(mode, sk, sk_stride, msgs, msg_off, dctx, (int)ctxlen, rnd, sig, status, n, internal, ctx().cur, 3,
-                         attempts);
+                         attempts, (volatile uint32_t*)pin0);
   }
-  // host pointers: one staged pass (signing is compute-heavy: ~7 KB of traffic per ~1e6 instructions)
+  // host pointers: chunks of 2^16 signatures through the three staging slots.  The rejection loop of a chunk keeps
+  // the host busy (one counter read per round), so the input of chunk i+1 is put in flight before chunk i starts and
+  // the signatures of chunk i travel back while chunk i+1 runs.
   Ctx& c = ctx();
   std::lock_guard<std::mutex> lock(c.mu);
-  cudaStream_t st = c.pipe[0];
-  const size_t msg_bytes = (size_t)msg_off[n];
+  constexpr size_t kChunk = 1u << 16;
+  const size_t nchunks = (n + kChunk - 1) / kChunk, cmax = n < kChunk ? n : kChunk;
+  size_t max_msg = 0;
+  for (size_t first = 0; first < n; first += kChunk) {
+    const size_t cnt = n - first < kChunk ? n - first : kChunk;
+    max_msg = std::max<size_t>(max_msg, (size_t)(msg_off[first + cnt] - msg_off[first]));
+  }
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
     off += (bytes + 255) & ~(size_t)255;
     return o;
   };
-  const size_t nk = sk_stride ? n : 1;
-  const size_t oSk = take(nk * ms.sk), oMsg = take(msg_bytes + 8), oOff = take((n + 1) * 8), oRnd = take(n * 32),
-               oSig = take(n * ms.sig), oSt = take(n), oCtx = take(256);
-  rc = ensure_scratch(0, off);
-  if (rc) return rc;
-  char* d = (char*)c.scratch[0];
-  if (sk_stride == 0 || sk_stride == ms.sk)
-    CB200_CUDA(cudaMemcpyAsync(d + oSk, sk, nk * ms.sk, cudaMemcpyHostToDevice, st));
-  else
-    CB200_CUDA(cudaMemcpy2DAsync(d + oSk, ms.sk, sk, sk_stride, ms.sk, n, cudaMemcpyHostToDevice, st));
-  if (msg_bytes) CB200_CUDA(cudaMemcpyAsync(d + oMsg, msgs, msg_bytes, cudaMemcpyHostToDevice, st));
-  CB200_CUDA(cudaMemcpyAsync(d + oOff, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  if (rnd) CB200_CUDA(cudaMemcpyAsync(d + oRnd, rnd, n * 32, cudaMemcpyHostToDevice, st));
-  if (ctxlen) CB200_CUDA(cudaMemcpyAsync(d + oCtx, context, ctxlen, cudaMemcpyHostToDevice, st));
-  rc = dispatch_sign(mode, (const uint8_t*)d + oSk, sk_stride ? ms.sk : (size_t)0, (const uint8_t*)d + oMsg,
-                     (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : (const uint8_t*)nullptr, (int)ctxlen,
-                     rnd ? (const uint8_t*)d + oRnd : (const uint8_t*)nullptr, (uint8_t*)d + oSig, (uint8_t*)d + oSt, n,
-                     internal, st, 0, attempts);
-  if (rc) return rc;
+  const size_t oSk = take((sk_stride ? cmax : 1) * ms.sk), oMsg = take(max_msg + 8), oOff = take((cmax + 1) * 8),
+               oRnd = take(cmax * 32), oSig = take(cmax * ms.sig), oSt = take(cmax), oCtx = take(256);
+  const int nslots = nchunks < 3 ? (int)nchunks : 3;
+  for (int sl = 0; sl < nslots; sl++) {
+    rc = ensure_scratch(sl, off);
+    if (rc) return rc;
+  }
   void* pin = nullptr;
   rc = ensure_pinned(n + 64, &pin);
   if (rc) return rc;
-  CB200_CUDA(cudaMemcpyAsync(sig, d + oSig, n * ms.sig, cudaMemcpyDeviceToHost, st));
-  CB200_CUDA(cudaMemcpyAsync(pin, d + oSt, n, cudaMemcpyDeviceToHost, st));
-  CB200_CUDA(cudaStreamSynchronize(st));
+  uint8_t* hs = (uint8_t*)pin;
+  volatile uint32_t* h_count = (volatile uint32_t*)((char*)pin + ((n + 15) & ~(size_t)15));
+  std::vector<std::vector<uint64_t>> rebased(nchunks);  // message offsets relative to the chunk; alive until the final sync
+  auto issue_h2d = [&](size_t ci) -> int {
+    const size_t first = ci * kChunk, cnt = n - first < kChunk ? n - first : kChunk;
+    const int sl = (int)(ci % 3);
+    cudaStream_t st = c.pipe[sl];
+    char* d = (char*)c.scratch[sl];
+    if (sk_stride == 0)
+      CB200_CUDA(cudaMemcpyAsync(d + oSk, sk, ms.sk, cudaMemcpyHostToDevice, st));
+    else if (sk_stride == ms.sk)
+      CB200_CUDA(cudaMemcpyAsync(d + oSk, sk + first * ms.sk, cnt * ms.sk, cudaMemcpyHostToDevice, st));
+    else
+      CB200_CUDA(cudaMemcpy2DAsync(d + oSk, ms.sk, sk + first * sk_stride, sk_stride, ms.sk, cnt, cudaMemcpyHostToDevice, st));
+    const uint64_t m0 = msg_off[first], mb = msg_off[first + cnt] - m0;
+    if (mb) CB200_CUDA(cudaMemcpyAsync(d + oMsg, msgs + m0, mb, cudaMemcpyHostToDevice, st));
+    std::vector<uint64_t>& ro = rebased[ci];
+    ro.resize(cnt + 1);
+    for (size_t i = 0; i <= cnt; i++) ro[i] = msg_off[first + i] - m0;
+    CB200_CUDA(cudaMemcpyAsync(d + oOff, ro.data(), (cnt + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (rnd) CB200_CUDA(cudaMemcpyAsync(d + oRnd, rnd + 32 * first, cnt * 32, cudaMemcpyHostToDevice, st));
+    if (ctxlen) CB200_CUDA(cudaMemcpyAsync(d + oCtx, context, ctxlen, cudaMemcpyHostToDevice, st));
+    return 0;
+  };
+  uint64_t total_attempts = 0;
+  rc = issue_h2d(0);
+  for (size_t ci = 0; ci < nchunks && rc == 0; ci++) {
+    const size_t first = ci * kChunk, cnt = n - first < kChunk ? n - first : kChunk;
+    const int sl = (int)(ci % 3);
+    cudaStream_t st = c.pipe[sl];
+    char* d = (char*)c.scratch[sl];
+    if (ci + 1 < nchunks) {
+      rc = issue_h2d(ci + 1);
+      if (rc) break;
+    }
+    uint64_t att = 0;
+    rc = dispatch_sign(mode, (const uint8_t*)d + oSk, sk_stride ? ms.sk : (size_t)0, (const uint8_t*)d + oMsg,
+                       (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : (const uint8_t*)nullptr, (int)ctxlen,
+                       rnd ? (const uint8_t*)d + oRnd : (const uint8_t*)nullptr, (uint8_t*)d + oSig, (uint8_t*)d + oSt, cnt,
+                       internal, st, sl, attempts ? &att : (uint64_t*)nullptr, h_count);
+    if (rc) break;
+    total_attempts += att;
+    CB200_CUDA(cudaMemcpyAsync(sig + first * ms.sig, d + oSig, cnt * ms.sig, cudaMemcpyDeviceToHost, st));
+    CB200_CUDA(cudaMemcpyAsync(hs + first, d + oSt, cnt, cudaMemcpyDeviceToHost, st));
+  }
+  for (int sl = 0; sl < 3; sl++) CB200_CUDA(cudaStreamSynchronize(c.pipe[sl]));
+  if (rc) return rc;
+  if (attempts) *attempts = total_attempts;
   size_t nbad = 0;
-  const uint8_t* hs = (const uint8_t*)pin;
   for (size_t i = 0; i < n; i++) nbad += hs[i] != 0;
   if (status) memcpy(status, hs, n);
   if (nbad) {

@@ -119,10 +119,33 @@ int run_staged(std::vector<Buf>& bufs, size_t n, size_t chunk,
     int rc = ensure_scratch(s, off[nb]);
     if (rc) return rc;
   }
+  // Chunk schedule: the first and the last chunks are short (1/4, 1/4, 1/2 of `chunk` on the way up, the mirror
+  // image on the way down) so that the part of the pipeline that cannot overlap -- the first input copy and the last
+  // kernels + output copy -- is a quarter of a chunk instead of a whole one.  Only worth it for long batches.
+  std::vector<size_t> sched;
+  {
+    const size_t ramp[3] = {chunk / 4, chunk / 4, chunk / 2};
+    size_t left = n;
+    std::vector<size_t> tail;
+    if (n >= 6 * chunk && chunk >= 4096) {
+      for (size_t r : ramp) {
+        sched.push_back(r);
+        tail.push_back(r);
+        left -= 2 * r;
+      }
+    }
+    while (left > 0) {
+      const size_t cnt = left < chunk ? left : chunk;
+      sched.push_back(cnt);
+      left -= cnt;
+    }
+    for (size_t k = tail.size(); k-- > 0;) sched.push_back(tail[k]);
+  }
   std::vector<void*> dev(nb);
   int slot = 0, rc = 0;
-  for (size_t first = 0; first < n && rc == 0; first += chunk, slot = (slot + 1) % 3) {
-    const size_t count = (n - first < chunk) ? n - first : chunk;
+  size_t first = 0;
+  for (size_t ci = 0; ci < sched.size() && rc == 0; first += sched[ci], ci++, slot = (slot + 1) % 3) {
+    const size_t count = sched[ci];
     cudaStream_t st = c.pipe[slot];
     for (size_t i = 0; i < nb; i++) {
       dev[i] = (char*)c.scratch[slot] + off[i];

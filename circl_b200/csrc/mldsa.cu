@@ -1750,6 +1750,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     }
     {
       KernelScope ks(KID_MLDSA_RESPONSE, st);
+      count_launch(2);  // three launches in this scope
       response_kernel<P, 0><<<pgrid(ns * K, 8), 128, 0, st>>>(sl, nullptr, ns, shared ? 1 : 0, w.sh, w.c, w.y, w.w0, w.w1u,
                                                               w.zbuf, w.hintbits, w.flags, w.hintcnt, w.pass, w.list1,
                                                               w.count + 2, w.owner, zetas);
@@ -1762,6 +1763,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     }
     {
       KernelScope ks(KID_MLDSA_COMPACT, st);
+      count_launch(1);  // two launches in this scope
       finalize_bid_kernel<P><<<blocks(ns, 256), 256, 0, st>>>(sl, ns, w.flags, w.hintcnt, w.owner, w.tofs, w.attempt, w.best);
       finalize_kernel<P><<<blocks(nact * 32, 128), 128, 0, st>>>(
           act, nact, T, w.ctilde, w.zbuf, w.hintbits, w.best, w.attempt, sig, status, w.act[cur ^ 1], w.count + (cur ^ 1),

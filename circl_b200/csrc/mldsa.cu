@@ -1307,7 +1307,7 @@ static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
   uint8_t* w1p = (uint8_t*)(b + oW1);
   uint32_t* act = (uint32_t*)(b + oAct);
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
     attr_set = true;
@@ -1588,7 +1588,7 @@ static int keygen_device(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t 
   uint32_t* spoly = (uint32_t*)(b + oSp);
   uint32_t* s1h = (uint32_t*)(b + oSh);
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
     CB200_CUDA(cudaFuncSetAttribute(kg_eta_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
@@ -1681,7 +1681,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
   constexpr int kChSmem = ChLayout<P>::smem;
 
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
     if (kChSmem) CB200_CUDA(cudaFuncSetAttribute(challenge_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmem));

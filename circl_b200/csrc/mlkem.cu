@@ -689,7 +689,7 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
   uint8_t* kbar = (uint8_t*)(b + o_k);
   uint8_t* ct2 = (uint8_t*)(b + o_ct2);
   const uint8_t* ek = dk + 384 * K;  // dk = sk || ek || H(ek) || z (kyber.go:187-201)
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
     attr_set = true;
@@ -895,7 +895,7 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
   char* b = (char*)base;
   uint64_t* rs = (uint64_t*)(b + o_rs);
   uint64_t* h = (uint64_t*)(b + o_h);
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
     attr_set = true;
@@ -1074,7 +1074,7 @@ static int r3_device(int decaps, const uint8_t* key, size_t key_stride, const ui
   uint64_t* r = (uint64_t*)(b + o_r);
   uint8_t* m = (uint8_t*)(b + o_m);
   uint8_t* kbar = (uint8_t*)(b + o_k);
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
     attr_set = true;
@@ -1146,7 +1146,7 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
   uint64_t* h = (uint64_t*)((char*)base + o_h);
   uint64_t* r = (uint64_t*)((char*)base + o_r);
 
-  static bool attr_set = false;
+  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
   if (!attr_set) {
     CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
     attr_set = true;

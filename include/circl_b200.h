@@ -160,9 +160,12 @@ size_t cb200_hybrid_public_key_size(int id);
 size_t cb200_hybrid_private_key_size(int id);
 size_t cb200_hybrid_ciphertext_size(int id);
 
-/* ---- ML-DSA (mode = 44, 65 or 87; sign/dilithium/gen.go:80-162) ----
+/* ---- ML-DSA (mode = 44, 65 or 87) and round-3 Dilithium (mode = 2, 3 or 5); sign/dilithium/gen.go:80-162 ----
  * Same contracts as the ML-DSA-65 entry points documented below, with the parameter set as first argument:
- * sk 2560 / 4032 / 4896, pk 1312 / 1952 / 2592, sig 2420 / 3309 / 4627 bytes. */
+ *   ML-DSA-44 / 65 / 87 (sign/mldsa/mldsa{44,65,87}):    sk 2560 / 4032 / 4896, pk 1312 / 1952 / 2592, sig 2420 / 3309 / 4627
+ *   Dilithium2 / 3 / 5  (sign/dilithium/mode{2,3,5}):     sk 2528 / 4000 / 4864, pk 1312 / 1952 / 2592, sig 2420 / 3293 / 4595
+ * Round 3 (NIST = false, internal/params.go:15-17) has no context string (a non-empty one is CB200_ERR_ARG, the
+ * reference's sign.ErrContextNotSupported), ignores rnd and flags, and signs the message as given. */
 int cb200_mldsa_sign(int mode, const uint8_t *sk, size_t sk_stride, const uint8_t *msgs, const uint64_t *msg_off,
                      const uint8_t *context, size_t ctxlen, const uint8_t *rnd, uint8_t *sig, uint8_t *status, size_t n,
                      int flags, uint64_t *attempts);

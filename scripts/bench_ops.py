@@ -90,4 +90,36 @@ ms = torch.randint(0, 256, (n, 32), generator=g, device="cuda", dtype=torch.uint
 ek, dk = k768.DeriveKeyPairBatch(seeds)
 t = timed(lambda: k768.EncapsulateBatch(ek, ms), steps=3)
 res["Kyber768 (round 3) encaps"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+del seeds, ms, ek, dk
+torch.cuda.empty_cache()
+
+# ML-DSA family, device-resident through the C ABI (CUDA events): key generation, signing and verification for
+# ML-DSA-44/65/87 and round-3 Dilithium3; per-op keys, 32-byte messages
+from circl_b200 import mldsa  # noqa: E402
+from circl_b200._ffi import check, lib  # noqa: E402
+
+L = lib()
+n = 1 << 17
+g = torch.Generator(device="cuda").manual_seed(9)
+dseeds = torch.randint(0, 256, (n, 32), generator=g, device="cuda", dtype=torch.uint8)
+msg_d = torch.randint(0, 256, (n * 32 + 8,), generator=g, device="cuda", dtype=torch.uint8)
+off_d = (torch.arange(n + 1, device="cuda", dtype=torch.int64) * 32).contiguous()
+check(L.cb200_set_stream(torch.cuda.current_stream().cuda_stream))
+for name, mode in (("ML-DSA-44", 44), ("ML-DSA-65", 65), ("ML-DSA-87", 87), ("Dilithium3", 3)):
+    sch = mldsa.ByName(name)
+    pk = torch.empty((n, sch.PublicKeySize()), dtype=torch.uint8, device="cuda")
+    sk = torch.empty((n, sch.PrivateKeySize()), dtype=torch.uint8, device="cuda")
+    sig = torch.empty((n, sch.SignatureSize()), dtype=torch.uint8, device="cuda")
+    st = torch.zeros((n,), dtype=torch.uint8, device="cuda")
+    ok = torch.zeros((n,), dtype=torch.uint8, device="cuda")
+    t = timed(lambda: check(L.cb200_mldsa_keygen(mode, dseeds.data_ptr(), pk.data_ptr(), sk.data_ptr(), n)), steps=3)
+    res[f"{name} keygen"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+    t = timed(lambda: check(L.cb200_mldsa_sign(mode, sk.data_ptr(), sch.PrivateKeySize(), msg_d.data_ptr(), off_d.data_ptr(),
+                                               None, 0, None, sig.data_ptr(), st.data_ptr(), n, 0, None)), steps=2, warm=2)
+    res[f"{name} sign"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3)}
+    t = timed(lambda: check(L.cb200_mldsa_verify(mode, pk.data_ptr(), sch.PublicKeySize(), msg_d.data_ptr(), off_d.data_ptr(),
+                                                 None, 0, sig.data_ptr(), ok.data_ptr(), n, 0)), steps=3)
+    res[f"{name} verify"] = {"n": n, "ms": t, "per_s": n / (t * 1e-3), "all_valid": bool(ok.all().item())}
+    del pk, sk, sig
+    torch.cuda.empty_cache()
 print(json.dumps(res, indent=1))

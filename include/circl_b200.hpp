@@ -354,6 +354,27 @@ class Scheme {  // sign.Scheme (sign/sign.go:48-94) for ML-DSA-44/65/87 (modes 4
     check(cb200_mldsa_sign(mode_, sks.data(), shared ? 0 : PrivateKeySize(), padded.data(), off.data(), (const uint8_t*)ctx.data(),
                              ctx.size(), nullptr, sigs.data(), nullptr, n, 0, nullptr));
   }
+  // ok[i] = 1 where signature i verifies; pks: one key (shared) or n keys
+  void VerifyBatch(const Bytes& pks, const Bytes& msgs, const std::vector<uint64_t>& off, const std::string& ctx,
+                   const Bytes& sigs, Bytes& ok) const {
+    if (!ctx.empty() && !SupportsContext()) throw ErrContextNotSupported();
+    const size_t n = off.size() - 1;
+    const bool shared = pks.size() == PublicKeySize();
+    if (!shared && pks.size() != n * PublicKeySize()) throw ErrPubKeySize();
+    ok.assign(n, 0);
+    if (ctx.size() > 255 || sigs.size() != n * SignatureSize()) return;  // dilithium.go:116-118: such signatures are invalid
+    Bytes padded(msgs);
+    padded.resize(msgs.size() + 8);
+    check(cb200_mldsa_verify(mode_, pks.data(), shared ? 0 : PublicKeySize(), padded.data(), off.data(), (const uint8_t*)ctx.data(),
+                               ctx.size(), sigs.data(), ok.data(), n, 0));
+  }
+  void DeriveKeyBatch(const Bytes& seeds, Bytes& pks, Bytes& sks) const {
+    if (seeds.size() % SeedSize()) throw ErrSeedSize();
+    const size_t n = seeds.size() / SeedSize();
+    pks.resize(n * PublicKeySize());
+    sks.resize(n * PrivateKeySize());
+    check(cb200_mldsa_keygen(mode_, seeds.data(), pks.data(), sks.data(), n));
+  }
 
  private:
   static void check(int rc) {

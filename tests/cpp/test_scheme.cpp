@@ -95,6 +95,23 @@ int main() {
     Bytes s2 = o->Sign(ok2.second, msg);
     REQUIRE(s2.size() == o->SignatureSize() && o->Verify(ok2.first, msg, s2));
   }
+  {  // batch entry points of sign.Scheme: 40 keys, messages of growing length, one tampered signature
+    const size_t nb = 40;
+    Bytes seeds(32 * nb), pks, sks, msgs, sigs, okv;
+    for (size_t i = 0; i < seeds.size(); i++) seeds[i] = (uint8_t)(i * 17 + 5);
+    d->DeriveKeyBatch(seeds, pks, sks);
+    REQUIRE(Bytes(pks.begin(), pks.begin() + d->PublicKeySize()) ==
+            d->DeriveKey(Bytes(seeds.begin(), seeds.begin() + 32)).first.MarshalBinary());
+    std::vector<uint64_t> off(nb + 1, 0);
+    for (size_t i = 0; i < nb; i++) {
+      for (size_t j = 0; j <= i; j++) msgs.push_back((uint8_t)(i + 3 * j));
+      off[i + 1] = msgs.size();
+    }
+    d->SignBatch(sks, msgs, off, "batch", sigs);
+    sigs[5 * d->SignatureSize() + 77] ^= 1;
+    d->VerifyBatch(pks, msgs, off, "batch", sigs, okv);
+    for (size_t i = 0; i < nb; i++) REQUIRE((okv[i] != 0) == (i != 5));
+  }
   REQUIRE(sign::ByName("ML-DSA-99") == nullptr);
   // round-3 wrappers (kem/kyber/kyber768, sign/dilithium/mode3): same classes, other entry points / parameter sets
   for (const char* name : {"Kyber512", "kyber768", "Kyber1024"}) {

@@ -66,3 +66,50 @@ def test_x25519_against_openssl():
         pa, pb = oracle.x25519(a)[0], oracle.x25519(b)[0]
         assert ska.public_key().public_bytes(**raw) == pa and skb.public_key().public_bytes(**raw) == pb
         assert ska.exchange(skb.public_key()) == oracle.x25519(a, pb)[0] == oracle.x25519(b, pa)[0]
+
+
+@pytest.mark.parametrize("name", ["X25519MLKEM768"])
+def test_hybrid_composition_rebuilt_from_openssl_parts(name):
+    """kem/hybrid has no vectors in the reference: rebuild X25519MLKEM768 (hybrid.go:197-283 over xkem.go:118-183) from
+    OpenSSL's ML-KEM-768 and X25519 plus hashlib's SHAKE256, and compare with the oracle's composition."""
+    from cryptography.hazmat.primitives import serialization
+    raw = dict(encoding=serialization.Encoding.Raw, format=serialization.PublicFormat.Raw)
+    for i in range(6):
+        seed, eseed = _h(7, i, 64), _h(8, i, 32)
+        pk, sk = oracle.hybrid_keygen(name, seed)
+        ex = hashlib.shake_256(seed).digest(96)                  # first.SeedSize (64) || second.SeedSize (32)
+        m_priv = mlkem.MLKEM768PrivateKey.from_seed_bytes(ex[:64])
+        x_sk = hashlib.shake_256(ex[64:]).digest(32)             # xScheme.DeriveKeyPair
+        x_priv = x25519.X25519PrivateKey.from_private_bytes(x_sk)
+        assert pk == m_priv.public_key().public_bytes_raw() + x_priv.public_key().public_bytes(**raw)
+        assert sk[2400:] == x_sk
+        ct, ss, rc = oracle.hybrid_encaps(name, pk, eseed)
+        assert rc == 0
+        es = hashlib.shake_256(eseed).digest(64)                 # first / second encapsulation seeds
+        e_priv = x25519.X25519PrivateKey.from_private_bytes(hashlib.shake_256(es[32:]).digest(32))
+        assert ct[1088:] == e_priv.public_key().public_bytes(**raw)
+        assert ss[32:] == e_priv.exchange(x_priv.public_key())
+        assert ss[:32] == m_priv.decapsulate(ct[:1088])
+        assert ct[:1088] == oracle.mlkem_encaps(3, pk[:1184], es[:32])[0]
+        assert oracle.hybrid_decaps(name, sk, ct) == (ss, 0)
+
+
+def test_xwing_composition_rebuilt_from_openssl_parts():
+    """X-Wing (kem/xwing/xwing.go:47-66,108-130,209-272) from OpenSSL's parts and hashlib's SHA3-256 / SHAKE256."""
+    from cryptography.hazmat.primitives import serialization
+    raw = dict(encoding=serialization.Encoding.Raw, format=serialization.PublicFormat.Raw)
+    for i in range(6):
+        seed, eseed = _h(9, i, 32), _h(10, i, 64)
+        pk = oracle.xwing_keygen(seed)
+        ex = hashlib.shake_256(seed).digest(96)
+        m_priv = mlkem.MLKEM768PrivateKey.from_seed_bytes(ex[:64])
+        x_priv = x25519.X25519PrivateKey.from_private_bytes(ex[64:])
+        pk_x = x_priv.public_key().public_bytes(**raw)
+        assert pk == m_priv.public_key().public_bytes_raw() + pk_x
+        ct, ss = oracle.xwing_encaps(pk, eseed)
+        e_priv = x25519.X25519PrivateKey.from_private_bytes(eseed[32:])
+        ct_x = e_priv.public_key().public_bytes(**raw)
+        assert ct[1088:] == ct_x
+        ss_x, ss_m = e_priv.exchange(x_priv.public_key()), m_priv.decapsulate(ct[:1088])
+        assert ss == hashlib.sha3_256(ss_m + ss_x + ct_x + pk_x + b"\\.//^\\").digest()
+        assert oracle.xwing_decaps(seed, ct) == ss

@@ -7,6 +7,8 @@ of the reference's interfaces used by the tests and the bench:
 
   circl_b200.kyber   -- pke/kyber/internal/common Poly method surface (batched)
   circl_b200.mlkem   -- kem.Scheme for ML-KEM-768 / ML-KEM-1024 (+ batch methods)
+  circl_b200.keccak  -- simd/keccakf1600 + internal/sha3 (batched permutation and one-shot sponges)
 """
 from ._ffi import Cb200Error, lib, check  # noqa: F401
-from .runtime import init, shutdown, device_count, set_stream, synchronize, launch_count  # noqa: F401
+from .runtime import (init, init_devices, active_devices, bind_thread_to_device, release_stream, shutdown,  # noqa: F401
+                      device_count, set_stream, synchronize, launch_count)

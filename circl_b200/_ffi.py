@@ -14,12 +14,16 @@ LIB_PATH = os.path.join(_HERE, "libcirclb200.so")
 # every symbol include/circl_b200.h declares (checked by tests/test_abi.py)
 SYMBOLS = {
     "cb200_init": (C.c_int, [C.c_int]),
+    "cb200_init_devices": (C.c_int, [C.c_int]),
+    "cb200_active_devices": (C.c_int, []),
     "cb200_shutdown": (None, []),
     "cb200_device_count": (C.c_int, []),
     "cb200_last_error": (C.c_char_p, []),
     "cb200_version": (C.c_char_p, []),
     "cb200_set_stream": (C.c_int, [C.c_void_p]),
+    "cb200_release_stream": (C.c_int, [C.c_void_p]),
     "cb200_synchronize": (C.c_int, []),
+    "cb200_bind_thread_to_device": (C.c_int, [C.c_int]),
     "cb200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "cb200_host_free": (None, [C.c_void_p]),
     "cb200_launch_count": (C.c_uint64, []),
@@ -36,6 +40,20 @@ SYMBOLS = {
     "cb200_dil_dot": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
     "cb200_dil_poly_op": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cb200_dil_exceeds": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_size_t]),
+    "cb200_keccak_f1600": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int]),
+    "cb200_sha3": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "cb200_kyber_derive_uniform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "cb200_kyber_derive_noise": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "cb200_kyber_pack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cb200_kyber_unpack": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cb200_kyber_compress": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "cb200_kyber_decompress": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_size_t]),
+    "cb200_dil_derive_uniform": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "cb200_dil_derive_leq_eta": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "cb200_dil_derive_le_gamma1": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]),
+    "cb200_dil_derive_ball": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]),
+    "cb200_dil_power2round": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cb200_dil_pack_le16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "cb200_mlkem_encaps": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t]),
     "cb200_kyber_kem_keygen": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),

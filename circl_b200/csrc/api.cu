@@ -1,7 +1,12 @@
 // circl_b200/csrc/api.cu -- C ABI of libcirclb200.so (declared in include/circl_b200.h):
-// context, pointer classification, host staging pipeline and the Kyber ring entry points.
+// runtime (devices, worker threads, work sets), pointer classification, the host staging pipeline with its
+// multi-GPU sharding, and the Kyber ring entry points.
+#include <sched.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "../../include/circl_b200.h"
 #include "common.cuh"
@@ -17,57 +22,83 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-Ctx& ctx() {
-  static Ctx c;
-  return c;
+Runtime& rt() {
+  static Runtime r;
+  return r;
 }
+
+// per-thread binding (see context.h)
+static thread_local Dev* t_dev = nullptr;
+static thread_local WorkSet* t_ws3 = nullptr;
+static thread_local cudaStream_t t_stream = nullptr;  // cb200_set_stream
+
+Dev& ctx() {
+  if (!t_dev) {  // programming error inside the library: a flow ran outside DeviceCall / worker thread
+    fprintf(stderr, "cb200: internal error: no device bound to this thread\n");
+    abort();
+  }
+  return *t_dev;
+}
+WorkSet& wset(int slot) {
+  if (slot >= 0 && slot < 3) return ctx().staging[slot];
+  if (!t_ws3) {
+    fprintf(stderr, "cb200: internal error: no work set bound to this thread\n");
+    abort();
+  }
+  return *t_ws3;
+}
+bool profiling_on() { return rt().profiling; }
 
 static const char* kKernelNames[KID_COUNT] = {
     "kyber_ntt", "kyber_invntt", "kyber_dot", "kyber_elementwise",
     "mlkem_hash_ek", "mlkem_g", "mlkem_sample", "mlkem_encrypt",
     "dil_ntt", "dil_invntt", "dil_dot", "dil_elementwise",
     "mldsa_expand_key", "mldsa_mu_rhoprime", "mldsa_mask", "mldsa_w", "mldsa_challenge", "mldsa_response",
-    "mldsa_compact", "x25519", "hybrid_glue"};
+    "mldsa_compact", "x25519", "hybrid_glue", "keccak_f1600", "sampler"};
 const char* kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? kKernelNames[id] : "?"; }
 
 KernelScope::KernelScope(int id_, cudaStream_t st_) : st(st_), id(id_) {
-  Ctx& c = ctx();
-  c.launches.fetch_add(1, std::memory_order_relaxed);
-  if (c.profiling) {
+  Runtime& r = rt();
+  r.launches.fetch_add(1, std::memory_order_relaxed);
+  if (r.profiling) {
     cudaEventCreate(&a);
     cudaEventRecord(a, st);
   }
 }
 KernelScope::~KernelScope() {
   if (!a) return;
-  Ctx& c = ctx();
+  Runtime& r = rt();
   cudaEvent_t b;
   cudaEventCreate(&b);
   cudaEventRecord(b, st);
-  std::lock_guard<std::mutex> lock(c.prof_mu);
-  c.prof.push_back(ProfRec{id, a, b});
+  std::lock_guard<std::mutex> lock(r.prof_mu);
+  r.prof.push_back(ProfRec{id, a, b});
 }
 
 int require_ready() {
-  if (!ctx().ready) {
-    set_error("cb200: not initialised (call cb200_init; there is no CPU fallback)");
+  if (!rt().ready) {
+    set_error("cb200: not initialised (call cb200_init or cb200_init_devices; there is no CPU fallback)");
     return CB200_ERR_NOT_INIT;
   }
   return 0;
 }
 
-bool is_device_ptr(const void* p) {
+bool is_device_ptr(const void* p, int* device) {
   if (!p) return false;
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
     cudaGetLastError();
     return false;
   }
-  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
+    if (device) *device = a.device;
+    return true;
+  }
+  return false;
 }
 
 int ensure_scratch(int slot, size_t bytes) {
-  Ctx& c = ctx();
+  Dev& c = ctx();
   if (c.scratch_bytes[slot] >= bytes) return 0;
   if (c.scratch[slot]) CB200_CUDA(cudaFree(c.scratch[slot]));
   c.scratch[slot] = nullptr;
@@ -78,21 +109,23 @@ int ensure_scratch(int slot, size_t bytes) {
 }
 
 int ensure_work(int slot, size_t bytes, void** out) {
-  Ctx& c = ctx();
-  if (c.work_bytes[slot] < bytes) {
-    CB200_CUDA(cudaDeviceSynchronize());
-    if (c.work[slot]) CB200_CUDA(cudaFree(c.work[slot]));
-    c.work[slot] = nullptr;
-    c.work_bytes[slot] = 0;
-    CB200_CUDA(cudaMalloc(&c.work[slot], bytes));
-    c.work_bytes[slot] = bytes;
+  const int level = slot >> 2;
+  WorkSet& w = wset(slot & 3);
+  if (w.work_bytes[level] < bytes) {
+    // kernels of earlier calls on this set may still be running: the set is only ever used from one stream (and
+    // the lanes joined to it), and cudaFree waits for the device
+    if (w.work[level]) CB200_CUDA(cudaFree(w.work[level]));
+    w.work[level] = nullptr;
+    w.work_bytes[level] = 0;
+    CB200_CUDA(cudaMalloc(&w.work[level], bytes));
+    w.work_bytes[level] = bytes;
   }
-  *out = c.work[slot];
+  *out = w.work[level];
   return 0;
 }
 
 int ensure_pinned(size_t bytes, void** out) {
-  Ctx& c = ctx();
+  Dev& c = ctx();
   if (c.pinned_bytes < bytes) {
     if (c.pinned) CB200_CUDA(cudaFreeHost(c.pinned));
     c.pinned = nullptr;
@@ -104,10 +137,252 @@ int ensure_pinned(size_t bytes, void** out) {
   return 0;
 }
 
-int run_staged(std::vector<Buf>& bufs, size_t n, size_t chunk,
+int ensure_smem_attr(const void* func, int bytes) {
+  Dev& c = ctx();
+  std::lock_guard<std::mutex> lock(c.attr_mu);
+  if (c.attr_done.count(func)) return 0;
+  CB200_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+  c.attr_done.insert(func);
+  return 0;
+}
+
+// ---------------------------------------------------------------- work sets and devices
+static int wset_create(WorkSet& w) {  // the owning device is current
+  CB200_CUDA(cudaEventCreateWithFlags(&w.ev_fork, cudaEventDisableTiming));
+  for (int l = 0; l < 2; l++) {
+    CB200_CUDA(cudaStreamCreateWithFlags(&w.lane[l], cudaStreamNonBlocking));
+    CB200_CUDA(cudaEventCreateWithFlags(&w.ev_join[l], cudaEventDisableTiming));
+  }
+  CB200_CUDA(cudaMalloc(&w.small, 256));
+  CB200_CUDA(cudaHostAlloc(&w.pin, 64, cudaHostAllocDefault));
+  return 0;
+}
+static void wset_destroy(WorkSet& w) {
+  for (int l = 0; l < 2; l++) {
+    if (w.work[l]) cudaFree(w.work[l]);
+    w.work[l] = nullptr;
+    w.work_bytes[l] = 0;
+    if (w.lane[l]) cudaStreamDestroy(w.lane[l]);
+    if (w.ev_join[l]) cudaEventDestroy(w.ev_join[l]);
+    w.lane[l] = nullptr;
+    w.ev_join[l] = nullptr;
+  }
+  if (w.ev_fork) cudaEventDestroy(w.ev_fork);
+  w.ev_fork = nullptr;
+  if (w.small) cudaFree(w.small);
+  if (w.pin) cudaFreeHost(w.pin);
+  w.small = w.pin = nullptr;
+}
+
+// CPUs next to a GPU: /sys/bus/pci/devices/<bus id>/local_cpulist, intersected with what this process may use.
+static bool local_cpus(int device, cpu_set_t* out) {
+  char id[32] = "";
+  if (cudaDeviceGetPCIBusId(id, sizeof id, device) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  for (char* p = id; *p; p++) *p = (char)tolower(*p);
+  char path[128];
+  snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/local_cpulist", id);
+  FILE* f = fopen(path, "r");
+  if (!f) return false;
+  char line[1024] = "";
+  const bool got = fgets(line, sizeof line, f) != nullptr;
+  fclose(f);
+  if (!got) return false;
+  cpu_set_t allowed;
+  CPU_ZERO(&allowed);
+  if (sched_getaffinity(0, sizeof allowed, &allowed) != 0) return false;
+  CPU_ZERO(out);
+  int n = 0;
+  for (char* tok = strtok(line, ",\n"); tok; tok = strtok(nullptr, ",\n")) {
+    int lo = 0, hi = 0;
+    const int k = sscanf(tok, "%d-%d", &lo, &hi);
+    if (k < 1) continue;
+    if (k == 1) hi = lo;
+    for (int c = lo; c <= hi && c < CPU_SETSIZE; c++)
+      if (CPU_ISSET(c, &allowed)) {
+        CPU_SET(c, out);
+        n++;
+      }
+  }
+  return n > 0;
+}
+static int bind_thread_near(int device) {
+  if (getenv("CB200_NO_AFFINITY")) return 0;
+  cpu_set_t set;
+  if (!local_cpus(device, &set)) return 0;
+  return sched_setaffinity(0, sizeof set, &set) == 0 ? CPU_COUNT(&set) : 0;
+}
+
+static void worker_main(Dev* d) {
+  cudaSetDevice(d->device);
+  bind_thread_near(d->device);  // staging copies from pageable memory and status scans stay on the GPU's NUMA node
+  t_dev = d;
+  for (;;) {
+    std::function<void()> job;
+    {
+      std::unique_lock<std::mutex> lk(d->q_mu);
+      d->q_cv.wait(lk, [&] { return d->stop || !d->q.empty(); });
+      if (d->q.empty()) return;
+      job = std::move(d->q.front());
+      d->q.pop_front();
+    }
+    job();
+  }
+}
+
+static int dev_create(int device, std::unique_ptr<Dev>* out) {
+  CB200_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CB200_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("cb200_init: device %d is sm_%d%d; this build contains only sm_100a code", device, prop.major, prop.minor);
+    return CB200_ERR_NOT_INIT;
+  }
+  std::unique_ptr<Dev> d(new Dev);
+  d->device = device;
+  d->sm_count = prop.multiProcessorCount;
+  for (int s = 0; s < 3; s++) {
+    CB200_CUDA(cudaStreamCreateWithFlags(&d->pipe[s], cudaStreamNonBlocking));
+    int rc = wset_create(d->staging[s]);
+    if (rc) return rc;
+  }
+  int32_t ktw[256];
+  kyber_fill_twiddles(ktw);
+  CB200_CUDA(cudaMalloc(&d->kyber_tw, sizeof ktw));
+  CB200_CUDA(cudaMemcpy(d->kyber_tw, ktw, sizeof ktw, cudaMemcpyHostToDevice));
+  int rc = init_extra_tables(*d);
+  if (rc) return rc;
+  d->worker = std::thread(worker_main, d.get());
+  *out = std::move(d);
+  return 0;
+}
+static void dev_destroy(Dev& d) {
+  {
+    std::lock_guard<std::mutex> lk(d.q_mu);
+    d.stop = true;
+  }
+  d.q_cv.notify_all();
+  if (d.worker.joinable()) d.worker.join();
+  cudaSetDevice(d.device);
+  cudaDeviceSynchronize();
+  for (int s = 0; s < 3; s++) {
+    if (d.scratch[s]) cudaFree(d.scratch[s]);
+    if (d.pipe[s]) cudaStreamDestroy(d.pipe[s]);
+    wset_destroy(d.staging[s]);
+  }
+  for (auto& kv : d.sets) wset_destroy(*kv.second);
+  d.sets.clear();
+  if (d.pinned) cudaFreeHost(d.pinned);
+  if (d.kyber_tw) cudaFree(d.kyber_tw);
+  if (d.dil_tw) cudaFree(d.dil_tw);
+  if (d.x25519_table) cudaFree(d.x25519_table);
+}
+static Dev* dev_by_ordinal(int device) {
+  for (auto& d : rt().devs)
+    if (d->device == device) return d.get();
+  return nullptr;
+}
+
+DeviceCall::DeviceCall(const void* buf) : prev_dev_(t_dev), prev_ws_(t_ws3) {
+  int ordinal = -1;
+  if (!is_device_ptr(buf, &ordinal)) {
+    set_error("cb200: internal error: DeviceCall on a host pointer");
+    rc = CB200_ERR_ARG;
+    return;
+  }
+  dev = dev_by_ordinal(ordinal);
+  if (!dev) {
+    set_error("cb200: the buffers live on GPU %d, which this library was not initialised on", ordinal);
+    rc = CB200_ERR_NOT_INIT;
+    return;
+  }
+  cudaGetDevice(&prev_device_);
+  if (prev_device_ != ordinal && cudaSetDevice(ordinal) != cudaSuccess) {
+    set_error("cb200: cudaSetDevice(%d) failed: %s", ordinal, cudaGetErrorString(cudaGetLastError()));
+    rc = CB200_ERR_NOT_INIT;
+    return;
+  }
+  st = t_stream;
+  {
+    std::lock_guard<std::mutex> lk(dev->sets_mu);
+    std::unique_ptr<WorkSet>& slot = dev->sets[st];
+    if (!slot) {
+      slot.reset(new WorkSet);
+      rc = wset_create(*slot);
+      if (rc) {
+        wset_destroy(*slot);
+        dev->sets.erase(st);
+        return;
+      }
+    }
+    ws = slot.get();
+  }
+  lock_ = std::unique_lock<std::mutex>(ws->mu);
+  t_dev = dev;
+  t_ws3 = ws;
+}
+DeviceCall::~DeviceCall() {
+  if (lock_.owns_lock()) lock_.unlock();
+  t_dev = prev_dev_;
+  t_ws3 = prev_ws_;
+  if (prev_device_ >= 0 && dev && prev_device_ != dev->device) cudaSetDevice(prev_device_);
+}
+
+// ---------------------------------------------------------------- host-pointer calls
+static void post(Dev& d, std::function<void()> job) {
+  {
+    std::lock_guard<std::mutex> lk(d.q_mu);
+    d.q.push_back(std::move(job));
+  }
+  d.q_cv.notify_one();
+}
+
+int for_each_shard(size_t n, size_t min_shard, const std::function<int(size_t first, size_t count)>& fn) {
+  Runtime& r = rt();
+  const size_t nd = r.devs.size();
+  if (nd == 0) return require_ready();
+  if (min_shard == 0) min_shard = 1;
+  size_t shards = 1;
+  if (nd > 1 && n >= 2 * min_shard) shards = std::min(nd, n / min_shard);
+  struct Res {
+    int rc = 0;
+    std::string err;
+  };
+  std::vector<Res> res(shards);
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t done = 0;
+  const size_t rot = shards == 1 ? r.next_dev.fetch_add(1, std::memory_order_relaxed) % nd : 0;
+  for (size_t s = 0; s < shards; s++) {
+    const size_t first = n * s / shards, cnt = n * (s + 1) / shards - first;
+    Dev& d = *r.devs[(s + rot) % nd];
+    post(d, [&, s, first, cnt] {
+      g_err[0] = 0;
+      const int rc = cnt ? fn(first, cnt) : 0;
+      res[s].rc = rc;
+      if (rc) res[s].err = g_err;
+      std::lock_guard<std::mutex> lk(mu);
+      done++;
+      cv.notify_one();
+    });
+  }
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done == shards; });
+  }
+  for (size_t s = 0; s < shards; s++)
+    if (res[s].rc) {
+      set_error("%s", res[s].err.c_str());
+      return res[s].rc;
+    }
+  return 0;
+}
+
+int run_staged(std::vector<Buf>& bufs, size_t first0, size_t n, size_t chunk,
                const std::function<int(void** dev, size_t count, size_t first, cudaStream_t st, int slot)>& body) {
-  Ctx& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
+  Dev& c = ctx();
   if (chunk == 0 || chunk > n) chunk = n;
   const size_t nb = bufs.size();
   std::vector<size_t> off(nb + 1, 0);
@@ -143,7 +418,7 @@ int run_staged(std::vector<Buf>& bufs, size_t n, size_t chunk,
   }
   std::vector<void*> dev(nb);
   int slot = 0, rc = 0;
-  size_t first = 0;
+  size_t first = first0;
   for (size_t ci = 0; ci < sched.size() && rc == 0; first += sched[ci], ci++, slot = (slot + 1) % 3) {
     const size_t count = sched[ci];
     cudaStream_t st = c.pipe[slot];
@@ -171,6 +446,45 @@ int run_staged(std::vector<Buf>& bufs, size_t n, size_t chunk,
   return rc;
 }
 
+int HostCall::run(size_t n) {
+  bit0 = 0;
+  bit1 = 0;
+  return for_each_shard(n, min_shard, [&](size_t first0, size_t cnt) -> int {
+    std::vector<Buf> b = bufs;
+    uint8_t* pin = nullptr;
+    if (status_buf >= 0) {
+      void* p = nullptr;
+      int rc = ensure_pinned(cnt, &p);
+      if (rc) return rc;
+      pin = (uint8_t*)p;
+      b[status_buf].host_out = pin - first0;  // element `first` of the batch lands at pin[first - first0]
+    }
+    int rc = run_staged(b, first0, cnt, chunk, body);
+    if (rc) return rc;
+    if (pin) {
+      size_t c0 = 0, c1 = 0;
+      for (size_t i = 0; i < cnt; i++) {
+        c0 += (pin[i] & 1) != 0;
+        c1 += (pin[i] & 2) != 0;
+      }
+      bit0 += c0;
+      bit1 += c1;
+      if (user_status) memcpy(user_status + first0, pin, cnt);
+    }
+    return 0;
+  });
+}
+
+int run_host(const std::vector<Buf>& bufs, size_t n, size_t chunk, size_t min_shard,
+             const std::function<int(void** dev, size_t count, size_t first, cudaStream_t st, int slot)>& body) {
+  HostCall hc;
+  hc.bufs = bufs;
+  hc.chunk = chunk;
+  hc.min_shard = min_shard;
+  hc.body = body;
+  return hc.run(n);
+}
+
 // number of polynomials per staging chunk: 64 MiB of int16 polys keeps three
 // chunks in flight well under any memory pressure and amortises launch latency.
 static constexpr size_t kPolyChunk = 1u << 17;
@@ -181,7 +495,7 @@ using namespace cb200;
 
 extern "C" {
 
-const char* cb200_version(void) { return "circl_b200 0.1 (sm_100a)"; }
+const char* cb200_version(void) { return "circl_b200 0.2 (sm_100a)"; }
 const char* cb200_last_error(void) { return g_err; }
 
 int cb200_device_count(void) {
@@ -193,11 +507,38 @@ int cb200_device_count(void) {
   return n;
 }
 
+static int init_list(const int* ordinals, int count) {
+  Runtime& r = rt();
+  std::lock_guard<std::mutex> lock(r.init_mu);
+  if (r.ready) {
+    bool same = (int)r.devs.size() == count;
+    for (int i = 0; same && i < count; i++) same = r.devs[i]->device == ordinals[i];
+    if (same) return 0;
+    r.ready = false;
+    for (auto& d : r.devs) dev_destroy(*d);
+    r.devs.clear();
+  }
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (int i = 0; i < count; i++) {
+    std::unique_ptr<Dev> d;
+    int rc = dev_create(ordinals[i], &d);
+    if (rc) {
+      for (auto& e : r.devs) dev_destroy(*e);
+      r.devs.clear();
+      return rc;
+    }
+    r.devs.push_back(std::move(d));
+  }
+  // leave the caller's current device as it was (first GPU of the set if it had none of ours selected)
+  cudaSetDevice(dev_by_ordinal(prev) ? prev : ordinals[0]);
+  r.launches = 0;
+  r.ready = true;
+  return 0;
+}
+
 int cb200_init(int device) {
-  Ctx& c = ctx();
-  if (c.ready && c.device == device) return 0;
-  if (c.ready) cb200_shutdown();
-  int n = cb200_device_count();
+  const int n = cb200_device_count();
   if (n <= 0) {
     set_error("cb200_init: no CUDA device visible (this library has no CPU fallback)");
     return CB200_ERR_NOT_INIT;
@@ -206,93 +547,87 @@ int cb200_init(int device) {
     set_error("cb200_init: device %d out of range (have %d)", device, n);
     return CB200_ERR_ARG;
   }
-  CB200_CUDA(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  CB200_CUDA(cudaGetDeviceProperties(&prop, device));
-  if (prop.major != 10) {
-    set_error("cb200_init: device %d is sm_%d%d; this build contains only sm_100a code", device, prop.major, prop.minor);
-    return CB200_ERR_NOT_INIT;
-  }
-  c.sm_count = prop.multiProcessorCount;
-  CB200_CUDA(cudaStreamCreateWithFlags(&c.own, cudaStreamNonBlocking));
-  for (int s = 0; s < 3; s++) CB200_CUDA(cudaStreamCreateWithFlags(&c.pipe[s], cudaStreamNonBlocking));
-  for (int w = 0; w < 4; w++) {
-    CB200_CUDA(cudaEventCreateWithFlags(&c.ev_fork[w], cudaEventDisableTiming));
-    for (int l = 0; l < 2; l++) {
-      CB200_CUDA(cudaStreamCreateWithFlags(&c.lane[w][l], cudaStreamNonBlocking));
-      CB200_CUDA(cudaEventCreateWithFlags(&c.ev_join[w][l], cudaEventDisableTiming));
-    }
-  }
-  c.cur = nullptr;  // CUDA legacy default stream until the caller names one
-  int32_t ktw[256];
-  kyber_fill_twiddles(ktw);
-  CB200_CUDA(cudaMalloc(&c.kyber_tw, sizeof ktw));
-  CB200_CUDA(cudaMemcpy(c.kyber_tw, ktw, sizeof ktw, cudaMemcpyHostToDevice));
-  int rc = init_extra_tables();
-  if (rc) return rc;
-  c.device = device;
-  c.launches = 0;
-  c.ready = true;
-  return 0;
+  const int rc = init_list(&device, 1);
+  if (rc == 0) cudaSetDevice(device);
+  return rc;
 }
 
+int cb200_init_devices(int ndev) {
+  const int n = cb200_device_count();
+  if (n <= 0) {
+    set_error("cb200_init_devices: no CUDA device visible (this library has no CPU fallback)");
+    return CB200_ERR_NOT_INIT;
+  }
+  if (ndev <= 0) ndev = n;
+  if (ndev > n) {
+    set_error("cb200_init_devices: %d GPUs requested, %d visible", ndev, n);
+    return CB200_ERR_ARG;
+  }
+  std::vector<int> ord(ndev);
+  for (int i = 0; i < ndev; i++) ord[i] = i;
+  return init_list(ord.data(), ndev);
+}
+
+int cb200_active_devices(void) { return rt().ready ? (int)rt().devs.size() : 0; }
+
 void cb200_shutdown(void) {
-  Ctx& c = ctx();
-  if (!c.ready) return;
-  cudaDeviceSynchronize();
-  for (int s = 0; s < 3; s++) {
-    if (c.scratch[s]) cudaFree(c.scratch[s]);
-    c.scratch[s] = nullptr;
-    c.scratch_bytes[s] = 0;
-    if (c.pipe[s]) cudaStreamDestroy(c.pipe[s]);
-    c.pipe[s] = nullptr;
-  }
-  for (int w = 0; w < 4; w++) {
-    if (c.ev_fork[w]) cudaEventDestroy(c.ev_fork[w]);
-    c.ev_fork[w] = nullptr;
-    for (int l = 0; l < 2; l++) {
-      if (c.lane[w][l]) cudaStreamDestroy(c.lane[w][l]);
-      if (c.ev_join[w][l]) cudaEventDestroy(c.ev_join[w][l]);
-      c.lane[w][l] = nullptr;
-      c.ev_join[w][l] = nullptr;
-    }
-  }
-  for (int s = 0; s < 8; s++) {
-    if (c.work[s]) cudaFree(c.work[s]);
-    c.work[s] = nullptr;
-    c.work_bytes[s] = 0;
-  }
-  if (c.pinned) cudaFreeHost(c.pinned);
-  c.pinned = nullptr;
-  c.pinned_bytes = 0;
-  if (c.kyber_tw) cudaFree(c.kyber_tw);
-  if (c.dil_tw) cudaFree(c.dil_tw);
-  if (c.small) cudaFree(c.small);
-  if (c.x25519_table) cudaFree(c.x25519_table);
-  c.kyber_tw = c.dil_tw = c.small = c.x25519_table = nullptr;
-  if (c.own) cudaStreamDestroy(c.own);
-  c.own = c.cur = nullptr;
-  c.ready = false;
-  c.device = -1;
+  Runtime& r = rt();
+  std::lock_guard<std::mutex> lock(r.init_mu);
+  if (!r.ready) return;
+  r.ready = false;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (auto& d : r.devs) dev_destroy(*d);
+  r.devs.clear();
+  if (prev >= 0) cudaSetDevice(prev);
 }
 
 int cb200_set_stream(void* s) {
   int rc = require_ready();
   if (rc) return rc;
-  ctx().cur = (cudaStream_t)s;
+  t_stream = (cudaStream_t)s;
+  return 0;
+}
+
+int cb200_release_stream(void* s) {
+  int rc = require_ready();
+  if (rc) return rc;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (auto& d : rt().devs) {
+    std::unique_ptr<WorkSet> w;
+    {
+      std::lock_guard<std::mutex> lk(d->sets_mu);
+      auto it = d->sets.find((cudaStream_t)s);
+      if (it == d->sets.end()) continue;
+      w = std::move(it->second);
+      d->sets.erase(it);
+    }
+    std::lock_guard<std::mutex> lk(w->mu);
+    cudaSetDevice(d->device);
+    cudaStreamSynchronize((cudaStream_t)s);
+    wset_destroy(*w);
+  }
+  if (prev >= 0) cudaSetDevice(prev);
   return 0;
 }
 
 int cb200_synchronize(void) {
   int rc = require_ready();
   if (rc) return rc;
-  CB200_CUDA(cudaStreamSynchronize(ctx().cur));
+  CB200_CUDA(cudaStreamSynchronize(t_stream));
   return 0;
+}
+
+int cb200_bind_thread_to_device(int device) {
+  const int n = bind_thread_near(device);
+  if (n == 0) set_error("cb200_bind_thread_to_device: no local_cpulist for GPU %d (affinity unchanged)", device);
+  return n;
 }
 
 void* cb200_host_alloc(size_t bytes) {
   void* p = nullptr;
-  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) {
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) {
     set_error("cb200_host_alloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
     return nullptr;
   }
@@ -302,12 +637,12 @@ void cb200_host_free(void* p) {
   if (p) cudaFreeHost(p);
 }
 
-uint64_t cb200_launch_count(void) { return ctx().launches.load(); }
+uint64_t cb200_launch_count(void) { return rt().launches.load(); }
 
 int cb200_profile_enable(int on) {
   int rc = require_ready();
   if (rc) return rc;
-  ctx().profiling = on != 0;
+  rt().profiling = on != 0;
   return 0;
 }
 int cb200_profile_kernel_count(void) { return KID_COUNT; }
@@ -315,24 +650,30 @@ const char* cb200_profile_kernel_name(int id) { return kernel_name(id); }
 int cb200_profile_read(double* ms_total, uint64_t* launches, int n) {
   int rc = require_ready();
   if (rc) return rc;
-  Ctx& c = ctx();
-  CB200_CUDA(cudaDeviceSynchronize());
-  std::lock_guard<std::mutex> lock(c.prof_mu);
+  Runtime& r = rt();
+  int prev = -1;
+  cudaGetDevice(&prev);
+  for (auto& d : r.devs) {
+    cudaSetDevice(d->device);
+    CB200_CUDA(cudaDeviceSynchronize());
+  }
+  if (prev >= 0) cudaSetDevice(prev);
+  std::lock_guard<std::mutex> lock(r.prof_mu);
   for (int i = 0; i < n; i++) {
     ms_total[i] = 0;
     launches[i] = 0;
   }
-  for (ProfRec& r : c.prof) {
+  for (ProfRec& p : r.prof) {
     float ms = 0;
-    cudaEventElapsedTime(&ms, r.a, r.b);
-    if (r.id < n) {
-      ms_total[r.id] += ms;
-      launches[r.id] += 1;
+    cudaEventElapsedTime(&ms, p.a, p.b);
+    if (p.id < n) {
+      ms_total[p.id] += ms;
+      launches[p.id] += 1;
     }
-    cudaEventDestroy(r.a);
-    cudaEventDestroy(r.b);
+    cudaEventDestroy(p.a);
+    cudaEventDestroy(p.b);
   }
-  c.prof.clear();
+  r.prof.clear();
   return 0;
 }
 
@@ -345,12 +686,23 @@ int cb200_kyber_ntt(int16_t* polys, size_t n, int inverse) {
     set_error("cb200_kyber_ntt: null pointer");
     return CB200_ERR_ARG;
   }
-  if (is_device_ptr(polys)) return launch_kyber_ntt(polys, n, inverse, ctx().kyber_tw, ctx().cur);
-  std::vector<Buf> bufs(1);
-  bufs[0] = Buf{polys, polys, 512, false, 0};
-  return run_staged(bufs, n, kPolyChunk, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+  if (is_device_ptr(polys)) {
+    if ((uintptr_t)polys & 15) {
+      set_error("cb200_kyber_ntt: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(polys);
+    if (call.rc) return call.rc;
+    return launch_kyber_ntt(polys, n, inverse, ctx().kyber_tw, call.st);
+  }
+  HostCall hc;
+  hc.bufs = {Buf{polys, polys, 512, false, 0}};
+  hc.chunk = kPolyChunk;
+  hc.min_shard = 1u << 15;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
     return launch_kyber_ntt((int16_t*)d[0], cnt, inverse, ctx().kyber_tw, st);
-  });
+  };
+  return hc.run(n);
 }
 
 int cb200_kyber_dot(int16_t* out, const int16_t* a, const int16_t* b, int k, size_t n) {
@@ -366,14 +718,24 @@ int cb200_kyber_dot(int16_t* out, const int16_t* a, const int16_t* b, int k, siz
     set_error("cb200_kyber_dot: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return launch_kyber_dot(out, a, b, k, n, ctx().kyber_tw, ctx().cur);
-  std::vector<Buf> bufs(3);
-  bufs[0] = Buf{nullptr, out, 512, false, 0};
-  bufs[1] = Buf{a, nullptr, 512 * (size_t)k, false, 0};
-  bufs[2] = Buf{b, nullptr, 512 * (size_t)k, false, 0};
-  return run_staged(bufs, n, kPolyChunk / k, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+  if (dev) {
+    if (((uintptr_t)out | (uintptr_t)a | (uintptr_t)b) & 15) {
+      set_error("cb200_kyber_dot: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(out);
+    if (call.rc) return call.rc;
+    return launch_kyber_dot(out, a, b, k, n, ctx().kyber_tw, call.st);
+  }
+  HostCall hc;
+  hc.bufs = {Buf{nullptr, out, 512, false, 0}, Buf{a, nullptr, 512 * (size_t)k, false, 0},
+             Buf{b, nullptr, 512 * (size_t)k, false, 0}};
+  hc.chunk = kPolyChunk / k;
+  hc.min_shard = (1u << 15) / k;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
     return launch_kyber_dot((int16_t*)d[0], (const int16_t*)d[1], (const int16_t*)d[2], k, cnt, ctx().kyber_tw, st);
-  });
+  };
+  return hc.run(n);
 }
 
 int cb200_kyber_mulhat(int16_t* out, const int16_t* a, const int16_t* b, size_t n) {
@@ -394,14 +756,24 @@ int cb200_kyber_poly_op(int op, int16_t* out, const int16_t* a, const int16_t* b
     set_error("cb200_kyber_poly_op: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return launch_kyber_poly_op(op, out, a, b, n, ctx().cur);
-  std::vector<Buf> bufs(3);
-  bufs[0] = Buf{nullptr, out, 512, false, 0};
-  bufs[1] = Buf{a, nullptr, 512, false, 0};
-  bufs[2] = Buf{binary ? b : nullptr, nullptr, 512, false, 0};
-  return run_staged(bufs, n, kPolyChunk, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+  if (dev) {
+    if (((uintptr_t)out | (uintptr_t)a | (uintptr_t)(binary ? b : nullptr)) & 15) {
+      set_error("cb200_kyber_poly_op: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(out);
+    if (call.rc) return call.rc;
+    return launch_kyber_poly_op(op, out, a, b, n, call.st);
+  }
+  HostCall hc;
+  hc.bufs = {Buf{nullptr, out, 512, false, 0}, Buf{a, nullptr, 512, false, 0},
+             Buf{binary ? b : nullptr, nullptr, 512, false, 0}};
+  hc.chunk = kPolyChunk;
+  hc.min_shard = 1u << 15;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
     return launch_kyber_poly_op(op, (int16_t*)d[0], (const int16_t*)d[1], (const int16_t*)d[2], cnt, st);
-  });
+  };
+  return hc.run(n);
 }
 
 }  // extern "C"

@@ -100,6 +100,40 @@ __global__ void __launch_bounds__(256) exceeds_kernel(const uint4* __restrict__ 
   if (lane == 0) flags[warp] = ex ? 1 : 0;
 }
 
+// (*Poly).Power2Round (poly.go:77-84, field.go:35-49): a = a1 2^13 + a0 with -2^12 < a0 <= 2^12; returns Q + a0 and a1
+__device__ __forceinline__ void power2round1(uint32_t a, uint32_t& a0q, uint32_t& a1) {
+  uint32_t a0 = a & 0x1fff;
+  a0 -= (1u << 12) + 1;
+  a0 += (uint32_t)((int32_t)a0 >> 31) & (1u << 13);
+  a0 -= (1u << 12) - 1;
+  a0q = Q + a0;
+  a1 = (a - a0) >> 13;
+}
+__global__ void __launch_bounds__(256) power2round_kernel(uint4* __restrict__ a0q, uint4* __restrict__ a1,
+                                                          const uint4* __restrict__ a, size_t nvec) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 x = a[i];
+    uint4 lo, hi;
+    power2round1(x.x, lo.x, hi.x);
+    power2round1(x.y, lo.y, hi.y);
+    power2round1(x.z, lo.z, hi.z);
+    power2round1(x.w, lo.w, hi.w);
+    a0q[i] = lo;
+    a1[i] = hi;
+  }
+}
+// (*Poly).PackLe16 (pack.go:102-108): thread per 8 coefficients -> 4 bytes
+__global__ void __launch_bounds__(256) pack_le16_kernel(uint32_t* __restrict__ out, const uint4* __restrict__ a, size_t nwords) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nwords; i += (size_t)gridDim.x * blockDim.x) {
+    const uint4 x = a[2 * i], y = a[2 * i + 1];
+    const uint32_t c[8] = {x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w};
+    uint32_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) w |= (uint32_t)(uint8_t)(c[2 * k] | (c[2 * k + 1] << 4)) << (8 * k);
+    out[i] = w;
+  }
+}
+
 static int grid_for(size_t units, int per_cta, int ctas_per_sm) {
   size_t want = (units + per_cta - 1) / per_cta;
   size_t cap = (size_t)kNumSM * ctas_per_sm;
@@ -160,6 +194,25 @@ int launch_dil_exceeds(const uint32_t* a, uint32_t bound, size_t n, uint8_t* fla
   return 0;
 }
 
+int launch_dil_power2round(uint32_t* a0q, uint32_t* a1, const uint32_t* a, size_t n, cudaStream_t st) {
+  using namespace dil;
+  if (n == 0) return 0;
+  KernelScope ks(KID_DIL_EW, st);
+  const size_t nvec = n * (N / 4);
+  power2round_kernel<<<grid_for(nvec, 256, 8), 256, 0, st>>>((uint4*)a0q, (uint4*)a1, (const uint4*)a, nvec);
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_dil_pack_le16(uint8_t* out, const uint32_t* a, size_t n, cudaStream_t st) {
+  using namespace dil;
+  if (n == 0) return 0;
+  KernelScope ks(KID_DIL_EW, st);
+  const size_t nwords = n * (N / 8);
+  pack_le16_kernel<<<grid_for(nwords, 256, 8), 256, 0, st>>>((uint32_t*)out, (const uint4*)a, nwords);
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
 void dil_fill_twiddles(uint32_t* out /* 512: Zetas | InvZetas */) {
   for (int i = 0; i < 256; i++) {
     out[i] = dil::zeta_of(i);
@@ -181,10 +234,18 @@ int cb200_dil_ntt(uint32_t* polys, size_t n, int inverse) {
     set_error("cb200_dil_ntt: null pointer");
     return CB200_ERR_ARG;
   }
-  if (is_device_ptr(polys)) return launch_dil_ntt(polys, n, inverse, ctx().dil_tw, ctx().cur);
+  if (is_device_ptr(polys)) {
+    if ((uintptr_t)polys & 15) {
+      set_error("cb200_dil_ntt: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(polys);
+    if (call.rc) return call.rc;
+    return launch_dil_ntt(polys, n, inverse, ctx().dil_tw, call.st);
+  }
   std::vector<Buf> bufs(1);
   bufs[0] = Buf{polys, polys, 1024, false, 0};
-  return run_staged(bufs, n, 1u << 16, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+  return run_host(bufs, n, 1u << 16, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
     return launch_dil_ntt((uint32_t*)d[0], cnt, inverse, ctx().dil_tw, st);
   });
 }
@@ -202,12 +263,20 @@ int cb200_dil_dot(uint32_t* out, const uint32_t* a, const uint32_t* b, int k, si
     set_error("cb200_dil_dot: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return launch_dil_dot(out, a, b, k, n, ctx().cur);
+  if (dev) {
+    if (((uintptr_t)out | (uintptr_t)a | (uintptr_t)b) & 15) {
+      set_error("cb200_dil_dot: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(out);
+    if (call.rc) return call.rc;
+    return launch_dil_dot(out, a, b, k, n, call.st);
+  }
   std::vector<Buf> bufs(3);
   bufs[0] = Buf{nullptr, out, 1024, false, 0};
   bufs[1] = Buf{a, nullptr, 1024 * (size_t)k, false, 0};
   bufs[2] = Buf{b, nullptr, 1024 * (size_t)k, false, 0};
-  return run_staged(bufs, n, (1u << 16) / k, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+  return run_host(bufs, n, (1u << 16) / k, (1u << 14) / k, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
     return launch_dil_dot((uint32_t*)d[0], (const uint32_t*)d[1], (const uint32_t*)d[2], k, cnt, st);
   });
 }
@@ -230,12 +299,20 @@ int cb200_dil_poly_op(int op, uint32_t* out, const uint32_t* a, const uint32_t* 
     set_error("cb200_dil_poly_op: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return launch_dil_poly_op(op, out, a, b, n, ctx().cur);
+  if (dev) {
+    if (((uintptr_t)out | (uintptr_t)a | (uintptr_t)(binary ? b : nullptr)) & 15) {
+      set_error("cb200_dil_poly_op: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(out);
+    if (call.rc) return call.rc;
+    return launch_dil_poly_op(op, out, a, b, n, call.st);
+  }
   std::vector<Buf> bufs(3);
   bufs[0] = Buf{nullptr, out, 1024, false, 0};
   bufs[1] = Buf{a, nullptr, 1024, false, 0};
   bufs[2] = Buf{binary ? b : nullptr, nullptr, 1024, false, 0};
-  return run_staged(bufs, n, 1u << 16, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+  return run_host(bufs, n, 1u << 16, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
     return launch_dil_poly_op(op, (uint32_t*)d[0], (const uint32_t*)d[1], (const uint32_t*)d[2], cnt, st);
   });
 }
@@ -253,12 +330,77 @@ int cb200_dil_exceeds(const uint32_t* polys, uint32_t bound, uint8_t* flags, siz
     set_error("cb200_dil_exceeds: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return launch_dil_exceeds(polys, bound, n, flags, ctx().cur);
+  if (dev) {
+    if ((uintptr_t)polys & 15) {
+      set_error("cb200_dil_exceeds: device polynomials must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(polys);
+    if (call.rc) return call.rc;
+    return launch_dil_exceeds(polys, bound, n, flags, call.st);
+  }
   std::vector<Buf> bufs(2);
   bufs[0] = Buf{polys, nullptr, 1024, false, 0};
   bufs[1] = Buf{nullptr, flags, 1, false, 0};
-  return run_staged(bufs, n, 1u << 16, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+  return run_host(bufs, n, 1u << 16, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
     return launch_dil_exceeds((const uint32_t*)d[0], bound, cnt, (uint8_t*)d[1], st);
+  });
+}
+
+int cb200_dil_power2round(uint32_t* a0plusq, uint32_t* a1, const uint32_t* a, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (!a0plusq || !a1 || !a) {
+    set_error("cb200_dil_power2round: null pointer");
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(a);
+  if (dev != is_device_ptr(a0plusq) || dev != is_device_ptr(a1)) {
+    set_error("cb200_dil_power2round: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  if (dev) {
+    if (((uintptr_t)a0plusq | (uintptr_t)a1 | (uintptr_t)a) & 15) {
+      set_error("cb200_dil_power2round: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(a);
+    if (call.rc) return call.rc;
+    return launch_dil_power2round(a0plusq, a1, a, n, call.st);
+  }
+  std::vector<Buf> bufs = {Buf{a, nullptr, 1024, false, 0}, Buf{nullptr, a0plusq, 1024, false, 0},
+                           Buf{nullptr, a1, 1024, false, 0}};
+  return run_host(bufs, n, 1u << 16, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+    return launch_dil_power2round((uint32_t*)d[1], (uint32_t*)d[2], (const uint32_t*)d[0], cnt, st);
+  });
+}
+
+int cb200_dil_pack_le16(uint8_t* out, const uint32_t* polys, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (!out || !polys) {
+    set_error("cb200_dil_pack_le16: null pointer");
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(out);
+  if (dev != is_device_ptr(polys)) {
+    set_error("cb200_dil_pack_le16: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  if (dev) {
+    if (((uintptr_t)out & 3) || ((uintptr_t)polys & 15)) {
+      set_error("cb200_dil_pack_le16: device buffers must be aligned (polynomials 16, output 4 bytes)");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(out);
+    if (call.rc) return call.rc;
+    return launch_dil_pack_le16(out, polys, n, call.st);
+  }
+  std::vector<Buf> bufs = {Buf{polys, nullptr, 1024, false, 0}, Buf{nullptr, out, 128, false, 0}};
+  return run_host(bufs, n, 1u << 16, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+    return launch_dil_pack_le16((uint8_t*)d[1], (const uint32_t*)d[0], cnt, st);
   });
 }
 

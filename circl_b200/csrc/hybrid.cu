@@ -332,14 +332,8 @@ static bool same_side(std::initializer_list<const void*> ps, bool* dev) {
   }
   return true;
 }
-// per-op status bytes come back through pinned memory; returns the first error class found
-static int status_result(const uint8_t* st, uint8_t* user, size_t n, const char* fn) {
-  size_t pub = 0, priv = 0;
-  for (size_t i = 0; i < n; i++) {
-    pub += (st[i] & 1) != 0;
-    priv += (st[i] & 2) != 0;
-  }
-  if (user) memcpy(user, st, n);
+// the first error class found among the per-op status bytes of a host-pointer call (counted by HostCall)
+static int status_result(size_t pub, size_t priv, size_t n, const char* fn) {
   if (pub) {
     set_error("%s: %zu of %zu operations hit an invalid public key or key share (kem.ErrPubKey)", fn, pub, n);
     return CB200_ERR_PUBKEY;
@@ -349,6 +343,13 @@ static int status_result(const uint8_t* st, uint8_t* user, size_t n, const char*
     return CB200_ERR_PRIVKEY;
   }
   return 0;
+}
+// device-pointer calls read their buffers with 32-, 64- and 128-bit accesses
+static bool aligned16(std::initializer_list<const void*> ps, std::initializer_list<size_t> strides) {
+  uintptr_t acc = 0;
+  for (const void* p : ps) acc |= (uintptr_t)p;
+  for (size_t v : strides) acc |= v;
+  return (acc & 15) == 0;
 }
 
 }  // namespace hybrid
@@ -373,28 +374,34 @@ int cb200_x25519(const uint8_t* scalars, const uint8_t* points, uint8_t* out, ui
     return CB200_ERR_ARG;
   }
   if (dev) {
-    if (status) CB200_CUDA(cudaMemsetAsync(status, 0, n, ctx().cur));
-    x25519_launch(scalars, 32, points, 32, out, 32, status, n, ctx().cur);
+    if (!aligned16({scalars, points, out}, {})) {
+      set_error("cb200_x25519: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(out);
+    if (call.rc) return call.rc;
+    if (status) CB200_CUDA(cudaMemsetAsync(status, 0, n, call.st));
+    x25519_launch(scalars, 32, points, 32, out, 32, status, n, call.st);
     CB200_CUDA(cudaGetLastError());
     return 0;
   }
-  void* pin = nullptr;
-  rc = ensure_pinned(n, &pin);
-  if (rc) return rc;
-  std::vector<Buf> bufs;
-  bufs.push_back(Buf{scalars, nullptr, 32, false, 0});
-  bufs.push_back(Buf{nullptr, out, 32, false, 0});
-  bufs.push_back(Buf{nullptr, pin, 1, false, 0});
-  if (points) bufs.push_back(Buf{points, nullptr, 32, false, 0});
-  rc = run_staged(bufs, n, 1u << 17, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+  HostCall hc;
+  hc.bufs = {Buf{scalars, nullptr, 32, false, 0}, Buf{nullptr, out, 32, false, 0}, Buf{nullptr, nullptr, 1, false, 0}};
+  if (points) hc.bufs.push_back(Buf{points, nullptr, 32, false, 0});
+  hc.chunk = 1u << 17;
+  hc.min_shard = 1u << 14;
+  hc.status_buf = 2;
+  hc.user_status = status;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int) -> int {
     CB200_CUDA(cudaMemsetAsync(d[2], 0, cnt, st));
     x25519_launch((const uint8_t*)d[0], 32, points ? (const uint8_t*)d[3] : nullptr, 32, (uint8_t*)d[1], 32, (uint8_t*)d[2],
                   cnt, st);
     CB200_CUDA(cudaGetLastError());
     return 0;
-  });
+  };
+  rc = hc.run(n);
   if (rc) return rc;
-  return status_result((const uint8_t*)pin, status, n, "cb200_x25519");
+  return status_result(hc.bit0, hc.bit1, n, "cb200_x25519");
 }
 
 int cb200_xwing_keygen(const uint8_t* seeds, uint8_t* pk, size_t n) {
@@ -410,9 +417,17 @@ int cb200_xwing_keygen(const uint8_t* seeds, uint8_t* pk, size_t n) {
     set_error("cb200_xwing_keygen: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return xwing_keygen_dev(seeds, pk, n, ctx().cur, 3);
+  if (dev) {
+    if (!aligned16({seeds, pk}, {})) {
+      set_error("cb200_xwing_keygen: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(pk);
+    if (call.rc) return call.rc;
+    return xwing_keygen_dev(seeds, pk, n, call.st, 3);
+  }
   std::vector<Buf> bufs = {Buf{seeds, nullptr, 32, false, 0}, Buf{nullptr, pk, 1216, false, 0}};
-  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+  return run_host(bufs, n, 1u << 15, 1u << 13, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return xwing_keygen_dev((const uint8_t*)d[0], (uint8_t*)d[1], cnt, st, slot);
   });
 }
@@ -431,18 +446,29 @@ int cb200_xwing_encaps(const uint8_t* pk, size_t pk_stride, const uint8_t* eseed
     set_error("cb200_xwing_encaps: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return xwing_encaps_dev(pk, pk_stride, eseeds, ct, ss, status, n, ctx().cur, 3);
-  void* pin = nullptr;
-  rc = ensure_pinned(n, &pin);
-  if (rc) return rc;
-  std::vector<Buf> bufs = {Buf{pk, nullptr, 1216, pk_stride == 0, pk_stride}, Buf{eseeds, nullptr, 64, false, 0},
-                           Buf{nullptr, ct, 1120, false, 0}, Buf{nullptr, ss, 32, false, 0}, Buf{nullptr, pin, 1, false, 0}};
-  rc = run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+  if (dev) {
+    if (!aligned16({pk, eseeds, ct, ss}, {pk_stride})) {
+      set_error("cb200_xwing_encaps: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(ct);
+    if (call.rc) return call.rc;
+    return xwing_encaps_dev(pk, pk_stride, eseeds, ct, ss, status, n, call.st, 3);
+  }
+  HostCall hc;
+  hc.bufs = {Buf{pk, nullptr, 1216, pk_stride == 0, pk_stride}, Buf{eseeds, nullptr, 64, false, 0},
+             Buf{nullptr, ct, 1120, false, 0}, Buf{nullptr, ss, 32, false, 0}, Buf{nullptr, nullptr, 1, false, 0}};
+  hc.chunk = 1u << 15;
+  hc.min_shard = 1u << 13;
+  hc.status_buf = 4;
+  hc.user_status = status;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return xwing_encaps_dev((const uint8_t*)d[0], pk_stride == 0 ? 0 : 1216, (const uint8_t*)d[1], (uint8_t*)d[2],
                             (uint8_t*)d[3], (uint8_t*)d[4], cnt, st, slot);
-  });
+  };
+  rc = hc.run(n);
   if (rc) return rc;
-  return status_result((const uint8_t*)pin, status, n, "cb200_xwing_encaps");
+  return status_result(hc.bit0, hc.bit1, n, "cb200_xwing_encaps");
 }
 
 int cb200_xwing_decaps(const uint8_t* sk, size_t sk_stride, const uint8_t* ct, uint8_t* ss, size_t n) {
@@ -458,10 +484,18 @@ int cb200_xwing_decaps(const uint8_t* sk, size_t sk_stride, const uint8_t* ct, u
     set_error("cb200_xwing_decaps: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return xwing_decaps_dev(sk, sk_stride, ct, ss, n, ctx().cur, 3);
+  if (dev) {
+    if (!aligned16({sk, ct, ss}, {sk_stride})) {
+      set_error("cb200_xwing_decaps: device buffers and sk_stride must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(ss);
+    if (call.rc) return call.rc;
+    return xwing_decaps_dev(sk, sk_stride, ct, ss, n, call.st, 3);
+  }
   std::vector<Buf> bufs = {Buf{sk, nullptr, 32, sk_stride == 0, sk_stride}, Buf{ct, nullptr, 1120, false, 0},
                            Buf{nullptr, ss, 32, false, 0}};
-  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+  return run_host(bufs, n, 1u << 15, 1u << 13, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return xwing_decaps_dev((const uint8_t*)d[0], sk_stride == 0 ? 0 : 32, (const uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
   });
 }
@@ -493,10 +527,18 @@ int cb200_hybrid_keygen(int id, const uint8_t* seeds, uint8_t* pk, uint8_t* sk, 
     set_error("cb200_hybrid_keygen: mixed host/device pointers");
     return CB200_ERR_ARG;
   }
-  if (dev) return hybrid_keygen_dev(H, seeds, pk, sk, n, ctx().cur, 3);
+  if (dev) {
+    if (!aligned16({seeds, pk, sk}, {})) {
+      set_error("cb200_hybrid_keygen: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(pk);
+    if (call.rc) return call.rc;
+    return hybrid_keygen_dev(H, seeds, pk, sk, n, call.st, 3);
+  }
   std::vector<Buf> bufs = {Buf{seeds, nullptr, 64, false, 0}, Buf{nullptr, pk, H.ek + 32, false, 0},
                            Buf{nullptr, sk, H.dk + 32, false, 0}};
-  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+  return run_host(bufs, n, 1u << 15, 1u << 13, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return hybrid_keygen_dev(H, (const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
   });
 }
@@ -521,21 +563,29 @@ int cb200_hybrid_encaps(int id, const uint8_t* pk, size_t pk_stride, const uint8
       set_error("cb200_hybrid_encaps: device-pointer calls need a status array (it carries kem.ErrPubKey)");
       return CB200_ERR_ARG;
     }
-    return hybrid_encaps_dev(H, pk, pk_stride, seeds, ct, ss, status, n, ctx().cur, 3);
+    if (!aligned16({pk, seeds, ct, ss}, {pk_stride})) {
+      set_error("cb200_hybrid_encaps: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(ct);
+    if (call.rc) return call.rc;
+    return hybrid_encaps_dev(H, pk, pk_stride, seeds, ct, ss, status, n, call.st, 3);
   }
-  void* pin = nullptr;
-  rc = ensure_pinned(n, &pin);
-  if (rc) return rc;
   const size_t pks = H.ek + 32;
-  std::vector<Buf> bufs = {Buf{pk, nullptr, pks, pk_stride == 0, pk_stride}, Buf{seeds, nullptr, 32, false, 0},
-                           Buf{nullptr, ct, H.ct + 32, false, 0}, Buf{nullptr, ss, 64, false, 0},
-                           Buf{nullptr, pin, 1, false, 0}};
-  rc = run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+  HostCall hc;
+  hc.bufs = {Buf{pk, nullptr, pks, pk_stride == 0, pk_stride}, Buf{seeds, nullptr, 32, false, 0},
+             Buf{nullptr, ct, H.ct + 32, false, 0}, Buf{nullptr, ss, 64, false, 0}, Buf{nullptr, nullptr, 1, false, 0}};
+  hc.chunk = 1u << 15;
+  hc.min_shard = 1u << 13;
+  hc.status_buf = 4;
+  hc.user_status = status;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return hybrid_encaps_dev(H, (const uint8_t*)d[0], pk_stride == 0 ? 0 : pks, (const uint8_t*)d[1], (uint8_t*)d[2],
                              (uint8_t*)d[3], (uint8_t*)d[4], cnt, st, slot);
-  });
+  };
+  rc = hc.run(n);
   if (rc) return rc;
-  return status_result((const uint8_t*)pin, status, n, "cb200_hybrid_encaps");
+  return status_result(hc.bit0, hc.bit1, n, "cb200_hybrid_encaps");
 }
 
 int cb200_hybrid_decaps(int id, const uint8_t* sk, size_t sk_stride, const uint8_t* ct, uint8_t* ss, uint8_t* status, size_t n) {
@@ -557,20 +607,28 @@ int cb200_hybrid_decaps(int id, const uint8_t* sk, size_t sk_stride, const uint8
       set_error("cb200_hybrid_decaps: device-pointer calls need a status array (it carries kem.ErrPubKey / kem.ErrPrivKey)");
       return CB200_ERR_ARG;
     }
-    return hybrid_decaps_dev(H, sk, sk_stride, ct, ss, status, n, ctx().cur, 3);
+    if (!aligned16({sk, ct, ss}, {})) {
+      set_error("cb200_hybrid_decaps: device buffers must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(ss);
+    if (call.rc) return call.rc;
+    return hybrid_decaps_dev(H, sk, sk_stride, ct, ss, status, n, call.st, 3);
   }
-  void* pin = nullptr;
-  rc = ensure_pinned(n, &pin);
-  if (rc) return rc;
   const size_t sks = H.dk + 32;
-  std::vector<Buf> bufs = {Buf{sk, nullptr, sks, false, sk_stride}, Buf{ct, nullptr, H.ct + 32, false, 0},
-                           Buf{nullptr, ss, 64, false, 0}, Buf{nullptr, pin, 1, false, 0}};
-  rc = run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
-    return hybrid_decaps_dev(H, (const uint8_t*)d[0], sks, (const uint8_t*)d[1], (uint8_t*)d[2],
-                             (uint8_t*)d[3], cnt, st, slot);
-  });
+  HostCall hc;
+  hc.bufs = {Buf{sk, nullptr, sks, false, sk_stride}, Buf{ct, nullptr, H.ct + 32, false, 0},
+             Buf{nullptr, ss, 64, false, 0}, Buf{nullptr, nullptr, 1, false, 0}};
+  hc.chunk = 1u << 15;
+  hc.min_shard = 1u << 13;
+  hc.status_buf = 3;
+  hc.user_status = status;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+    return hybrid_decaps_dev(H, (const uint8_t*)d[0], sks, (const uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], cnt, st, slot);
+  };
+  rc = hc.run(n);
   if (rc) return rc;
-  return status_result((const uint8_t*)pin, status, n, "cb200_hybrid_decaps");
+  return status_result(hc.bit0, hc.bit1, n, "cb200_hybrid_decaps");
 }
 
 }  // extern "C"

@@ -23,7 +23,10 @@ int launch_dil_ntt(uint32_t* d_polys, size_t n, int inverse, const void* tw, cud
 int launch_dil_dot(uint32_t* out, const uint32_t* a, const uint32_t* b, int k, size_t n, cudaStream_t st);
 int launch_dil_poly_op(int op, uint32_t* out, const uint32_t* a, const uint32_t* b, size_t n, cudaStream_t st);
 int launch_dil_exceeds(const uint32_t* a, uint32_t bound, size_t n, uint8_t* flags, cudaStream_t st);
+int launch_dil_power2round(uint32_t* a0q, uint32_t* a1, const uint32_t* a, size_t n, cudaStream_t st);
+int launch_dil_pack_le16(uint8_t* out, const uint32_t* a, size_t n, cudaStream_t st);
 void dil_fill_twiddles(uint32_t* out);
-// tables.cu: twiddle tables other than Kyber's (ML-DSA); called from cb200_init
-int init_extra_tables();
+// tables.cu: twiddle tables other than Kyber's (ML-DSA) and the X25519 base table; called once per GPU at init
+struct Dev;
+int init_extra_tables(Dev& d);
 }  // namespace cb200

@@ -172,27 +172,11 @@ struct Work {
 constexpr int kExpThreads = 64;
 constexpr int kExpRow = 257;  // 256 words + 1 slack, odd stride
 
-// ExpandA (mat.go:15-23, sample.go:92-123): A[i][j] = RejNTTPoly(SHAKE128(rho || le16((i<<8)+j)))
-template <class P>
-__global__ void __launch_bounds__(kExpThreads) expand_a_kernel(const uint8_t* __restrict__ sk, size_t sk_stride,
-                                                               size_t nkeys, uint32_t* __restrict__ A) {
-  MLDSA_USE(P);
-  extern __shared__ __align__(16) uint32_t rows[];
-  const size_t s0 = (size_t)blockIdx.x * blockDim.x, total = nkeys * K * L;
-  const size_t s = s0 + threadIdx.x;
-  const size_t sc = s < total ? s : total - 1;
-  const size_t key = sc % nkeys;
-  const int ij = (int)(sc / nkeys), i = ij / L, j = ij % L;
-  const uint8_t* rho = sk + key * sk_stride;
-  uint64_t a[25];
-  keccak::zero(a);
-#pragma unroll
-  for (int w = 0; w < 4; w++) a[w] = keccak::ld64(rho + 8 * w);
-  a[4] = (uint64_t)j | ((uint64_t)i << 8) | (0x1full << 16);  // nonce = (i<<8)+j, little endian
-  a[20] = 0x8000000000000000ull;                               // SHAKE128 rate 168
-  uint32_t* row = rows + threadIdx.x * kExpRow;
-  // 56 candidates of 3 bytes per block (23 bits each); every candidate is stored at the write pointer (one slack
-  // word per row) and only the pointer advance is predicated.  The first four blocks cannot fill the row (224 < 256).
+// One SHAKE128 stream of PolyDeriveUniform (sample.go:92-123): `a` holds the absorbed, padded block seed || nonce; the
+// 256 accepted coefficients land in this thread's shared-memory row (kExpRow words).
+// 56 candidates of 3 bytes per block (23 bits each); every candidate is stored at the write pointer (one slack
+// word per row) and only the pointer advance is predicated.  The first four blocks cannot fill the row (224 < 256).
+__device__ __forceinline__ void uniform_stream(uint64_t (&a)[25], uint32_t* row) {
   auto parse = [&](uint32_t* wp, auto checked) {
 #pragma unroll
     for (int f = 0; f < 56; f++) {
@@ -222,6 +206,27 @@ __global__ void __launch_bounds__(kExpThreads) expand_a_kernel(const uint8_t* __
     keccak::f1600(a);
     wp = parse(wp, std::true_type{});
   } while (wp < row + N);
+}
+
+// ExpandA (mat.go:15-23, sample.go:92-123): A[i][j] = RejNTTPoly(SHAKE128(rho || le16((i<<8)+j)))
+template <class P>
+__global__ void __launch_bounds__(kExpThreads) expand_a_kernel(const uint8_t* __restrict__ sk, size_t sk_stride,
+                                                               size_t nkeys, uint32_t* __restrict__ A) {
+  MLDSA_USE(P);
+  extern __shared__ __align__(16) uint32_t rows[];
+  const size_t s0 = (size_t)blockIdx.x * blockDim.x, total = nkeys * K * L;
+  const size_t s = s0 + threadIdx.x;
+  const size_t sc = s < total ? s : total - 1;
+  const size_t key = sc % nkeys;
+  const int ij = (int)(sc / nkeys), i = ij / L, j = ij % L;
+  const uint8_t* rho = sk + key * sk_stride;
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int w = 0; w < 4; w++) a[w] = keccak::ld64(rho + 8 * w);
+  a[4] = (uint64_t)j | ((uint64_t)i << 8) | (0x1full << 16);  // nonce = (i<<8)+j, little endian
+  a[20] = 0x8000000000000000ull;                               // SHAKE128 rate 168
+  uniform_stream(a, rows + threadIdx.x * kExpRow);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int p = warp; p < kExpThreads; p += kExpThreads / 32) {
@@ -367,6 +372,36 @@ __global__ void __launch_bounds__(128) mu_kernel(const uint8_t* __restrict__ sk,
   tofs[op] = 0;
 }
 
+// PolyDeriveUniformLeGamma1 (sample.go:197-209, internal/pack.go:146-203): `a` holds the absorbed, padded block
+// seed || nonce; five SHAKE256 blocks are unpacked to 256 coefficients gamma1 - field (mod q) at `dst`.
+template <class P>
+__device__ __forceinline__ void legamma1_poly(uint64_t (&a)[25], uint32_t* __restrict__ dst) {
+  MLDSA_USE(P);
+  uint64_t buf[86];
+#pragma unroll
+  for (int b = 0; b < 5; b++) {
+    keccak::f1600(a);
+#pragma unroll
+    for (int w = 0; w < 17; w++) buf[17 * b + w] = a[w];
+  }
+  buf[85] = 0;
+  uint4* out = reinterpret_cast<uint4*>(dst);
+#pragma unroll 2
+  for (int p = 0; p < 64; p++) {  // 4 coefficients of ZBITS bits each (internal/pack.go:146-203)
+    uint32_t cf[4];
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+      const int bit = ZBITS * (4 * p + h), wi = bit >> 6, sh = bit & 63;
+      uint64_t f = buf[wi] >> sh;
+      if (sh + ZBITS > 64) f |= buf[wi + 1] << (64 - sh);
+      uint32_t c = GAMMA1 - ((uint32_t)f & ((1u << ZBITS) - 1));
+      c += (uint32_t)((int32_t)c >> 31) & Q;
+      cf[h] = c;
+    }
+    out[p] = make_uint4(cf[0], cf[1], cf[2], cf[3]);
+  }
+}
+
 // ------------------------------------------------------------------ per-round kernels
 // y[i] = ExpandMask(rho', L*attempt + i)  (sample.go:187-209, pack.go:177-195)
 template <class P>
@@ -388,29 +423,7 @@ __global__ void __launch_bounds__(128) mask_kernel(const uint32_t* __restrict__ 
   for (int w = 0; w < 8; w++) a[w] = rhop[8 * own + w];
   a[8] = (uint64_t)(nonce & 0xffff) | (0x1full << 16);
   a[16] = 0x8000000000000000ull;
-  uint64_t buf[86];
-#pragma unroll
-  for (int b = 0; b < 5; b++) {
-    keccak::f1600(a);
-#pragma unroll
-    for (int w = 0; w < 17; w++) buf[17 * b + w] = a[w];
-  }
-  buf[85] = 0;
-  uint4* out = reinterpret_cast<uint4*>(y + (op * L + i) * N);
-#pragma unroll 2
-  for (int p = 0; p < 64; p++) {  // 4 coefficients of ZBITS bits each (internal/pack.go:146-203)
-    uint32_t cf[4];
-#pragma unroll
-    for (int h = 0; h < 4; h++) {
-      const int bit = ZBITS * (4 * p + h), wi = bit >> 6, sh = bit & 63;
-      uint64_t f = buf[wi] >> sh;
-      if (sh + ZBITS > 64) f |= buf[wi + 1] << (64 - sh);
-      uint32_t c = GAMMA1 - ((uint32_t)f & ((1u << ZBITS) - 1));
-      c += (uint32_t)((int32_t)c >> 31) & Q;
-      cf[h] = c;
-    }
-    out[p] = make_uint4(cf[0], cf[1], cf[2], cf[3]);
-  }
+  legamma1_poly<P>(a, y + (op * L + i) * N);
 }
 
 struct OctetCtx {
@@ -557,6 +570,65 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
   }
 }
 
+// SampleInBall (sample.go:299-339) on c~ = ct: nz = positions with c != 0, ng = positions with c == -1; `a` is scratch.
+template <class P>
+__device__ __forceinline__ void sample_in_ball(const uint64_t (&ct)[P::CTILDE / 8], uint64_t (&a)[25], uint64_t (&nz)[4],
+                                               uint64_t (&ng)[4]) {
+  MLDSA_USE(P);
+  constexpr int CTW = CTILDE / 8;
+  // SampleInBall: nz = positions with c != 0, ng = positions with c == -1.  Every i of the loop lies in the top
+  // 64-bit word (i >= 256 - TAU >= 192) and is untouched before its iteration.
+  keccak::zero(a);
+#pragma unroll
+  for (int i = 0; i < CTW; i++) a[i] = ct[i];
+  a[CTW] = 0x1f;
+  a[16] = 0x8000000000000000ull;
+  keccak::f1600(a);
+  uint64_t buf[17];
+#pragma unroll
+  for (int i = 0; i < 17; i++) buf[i] = a[i];
+  uint64_t signs = buf[0];
+  int off = 8;
+#pragma unroll
+  for (int q = 0; q < 4; q++) nz[q] = ng[q] = 0;
+  static_assert(256 - TAU >= 192, "SampleInBall indices must stay in the top word");
+  for (int i = N - TAU; i < N; i++) {
+    uint32_t b;
+    for (;;) {
+      if (off >= 136) {
+        keccak::f1600(a);
+#pragma unroll
+        for (int q = 0; q < 17; q++) buf[q] = a[q];
+        off = 0;
+      }
+      uint64_t wsel = buf[0];
+#pragma unroll
+      for (int q = 1; q < 17; q++) wsel = ((off >> 3) == q) ? buf[q] : wsel;
+      b = (uint32_t)(wsel >> (8 * (off & 7))) & 0xff;
+      off++;
+      if (b <= (uint32_t)i) break;
+    }
+    const int bq = b >> 6, br = b & 63;
+    uint64_t wn = nz[0], wg = ng[0];
+#pragma unroll
+    for (int q = 1; q < 4; q++) {
+      wn = (bq == q) ? nz[q] : wn;
+      wg = (bq == q) ? ng[q] : wg;
+    }
+    // c[i] = c[b]
+    nz[3] |= ((wn >> br) & 1) << (i - 192);
+    ng[3] |= ((wg >> br) & 1) << (i - 192);
+    // c[b] = 1 - 2 * sign
+    const uint64_t bit = 1ull << br, sg = (signs & 1) << br;
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      nz[q] |= (bq == q) ? bit : 0;
+      ng[q] = (bq == q) ? ((ng[q] & ~bit) | sg) : ng[q];
+    }
+    signs >>= 1;
+  }
+}
+
 // c~ = H(mu || w1) (dilithium.go:397-401), c = SampleInBall(c~) (sample.go:299-339): thread per op.
 // With packed w1 the hash input is staged through shared memory: two rate blocks at a time, each warp copies that
 // slice of the (mu || w1) rows of its 32 ops with coalesced loads into rows of odd stride, from which the per-thread
@@ -650,56 +722,8 @@ __global__ void __launch_bounds__(kChThreads) challenge_kernel(const uint32_t* _
     ct[i] = a[i];
     ctilde[CTW * op + i] = ct[i];
   }
-  // SampleInBall: nz = positions with c != 0, ng = positions with c == -1.  Every i of the loop lies in the top
-  // 64-bit word (i >= 256 - TAU >= 192) and is untouched before its iteration.
-  keccak::zero(a);
-#pragma unroll
-  for (int i = 0; i < CTW; i++) a[i] = ct[i];
-  a[CTW] = 0x1f;
-  a[16] = 0x8000000000000000ull;
-  keccak::f1600(a);
-  uint64_t buf[17];
-#pragma unroll
-  for (int i = 0; i < 17; i++) buf[i] = a[i];
-  uint64_t signs = buf[0];
-  int off = 8;
-  uint64_t nz[4] = {0, 0, 0, 0}, ng[4] = {0, 0, 0, 0};
-  static_assert(256 - TAU >= 192, "SampleInBall indices must stay in the top word");
-  for (int i = N - TAU; i < N; i++) {
-    uint32_t b;
-    for (;;) {
-      if (off >= 136) {
-        keccak::f1600(a);
-#pragma unroll
-        for (int q = 0; q < 17; q++) buf[q] = a[q];
-        off = 0;
-      }
-      uint64_t wsel = buf[0];
-#pragma unroll
-      for (int q = 1; q < 17; q++) wsel = ((off >> 3) == q) ? buf[q] : wsel;
-      b = (uint32_t)(wsel >> (8 * (off & 7))) & 0xff;
-      off++;
-      if (b <= (uint32_t)i) break;
-    }
-    const int bq = b >> 6, br = b & 63;
-    uint64_t wn = nz[0], wg = ng[0];
-#pragma unroll
-    for (int q = 1; q < 4; q++) {
-      wn = (bq == q) ? nz[q] : wn;
-      wg = (bq == q) ? ng[q] : wg;
-    }
-    // c[i] = c[b]
-    nz[3] |= ((wn >> br) & 1) << (i - 192);
-    ng[3] |= ((wg >> br) & 1) << (i - 192);
-    // c[b] = 1 - 2 * sign
-    const uint64_t bit = 1ull << br, sg = (signs & 1) << br;
-#pragma unroll
-    for (int q = 0; q < 4; q++) {
-      nz[q] |= (bq == q) ? bit : 0;
-      ng[q] = (bq == q) ? ((ng[q] & ~bit) | sg) : ng[q];
-    }
-    signs >>= 1;
-  }
+  uint64_t nz[4], ng[4];
+  sample_in_ball<P>(ct, a, nz, ng);
   uint4* cm = reinterpret_cast<uint4*>(cmask + 16 * op);
   cm[0] = make_uint4((uint32_t)nz[0], (uint32_t)(nz[0] >> 32), (uint32_t)nz[1], (uint32_t)(nz[1] >> 32));
   cm[1] = make_uint4((uint32_t)nz[2], (uint32_t)(nz[2] >> 32), (uint32_t)nz[3], (uint32_t)(nz[3] >> 32));
@@ -1283,7 +1307,7 @@ static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
                          const uint8_t* ctxstr, int ctxlen, const uint8_t* sig, uint8_t* okout, size_t n, int internal,
                          cudaStream_t st, int slot) {
   MLDSA_USE(P);
-  Ctx& c = ctx();
+  Dev& c = ctx();
   const bool shared = pk_stride == 0;
   const size_t nkeys = shared ? 1 : n;
   size_t off = 0;
@@ -1307,11 +1331,7 @@ static int verify_device(const uint8_t* pk, size_t pk_stride, const uint8_t* msg
   uint8_t* w1p = (uint8_t*)(b + oW1);
   uint32_t* act = (uint32_t*)(b + oAct);
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
-  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
-  if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr((const void*)expand_a_kernel<P>, kExpThreads * kExpRow * 4)) return arc;
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
   {
     KernelScope ks(KID_MLDSA_EXPAND, st);  // ExpandA(rho): rho is the first 32 bytes of pk
@@ -1376,25 +1396,10 @@ __global__ void __launch_bounds__(128) kg_seed_kernel(const uint8_t* __restrict_
   for (int i = 0; i < 8; i++) sseed[8 * op + i] = a[4 + i];  // rho' = eSeed[32:96]
 }
 
-// s1, s2 = PolyDeriveUniformLeqEta (sample.go:129-181, eta = 4): thread per (op, poly); the accepted nibbles
-// are at once the PackLeqEta image (internal/pack.go:13-20), so the packed key is written here too.
-template <class P>
-__global__ void __launch_bounds__(kExpThreads) kg_eta_kernel(const uint64_t* __restrict__ sseed, size_t n,
-                                                             uint32_t* __restrict__ spoly, uint8_t* __restrict__ sk) {
-  MLDSA_USE(P);
-  extern __shared__ __align__(16) uint32_t rows[];
-  const size_t s0 = (size_t)blockIdx.x * blockDim.x, total = n * (L + K);
-  const size_t s = s0 + threadIdx.x;
-  const size_t sc = s < total ? s : total - 1;
-  const size_t op = sc % n;
-  const int p = (int)(sc / n);
-  uint64_t a[25];
-  keccak::zero(a);
-#pragma unroll
-  for (int w = 0; w < 8; w++) a[w] = sseed[8 * op + w];
-  a[8] = (uint64_t)p | (0x1full << 16);  // nonce = p (s1: 0..L-1, s2: L..L+K-1), little endian 16 bit
-  a[16] = 0x8000000000000000ull;
-  uint32_t* row = rows + threadIdx.x * kExpRow;
+// One SHAKE256 stream of PolyDeriveUniformLeqEta (sample.go:129-181): `a` holds the absorbed, padded block
+// seed || nonce; row[i] = t_i, the accepted nibble (reduced mod 5 for eta = 2), i.e. eta - coefficient.
+template <int ETA>
+__device__ __forceinline__ void leqeta_stream(uint64_t (&a)[25], uint32_t* row) {
   int ctr = 0;
   do {
     keccak::f1600(a);
@@ -1416,6 +1421,27 @@ __global__ void __launch_bounds__(kExpThreads) kg_eta_kernel(const uint64_t* __r
       }
     }
   } while (ctr < N);
+}
+
+// s1, s2 = PolyDeriveUniformLeqEta (sample.go:129-181, eta = 4): thread per (op, poly); the accepted nibbles
+// are at once the PackLeqEta image (internal/pack.go:13-20), so the packed key is written here too.
+template <class P>
+__global__ void __launch_bounds__(kExpThreads) kg_eta_kernel(const uint64_t* __restrict__ sseed, size_t n,
+                                                             uint32_t* __restrict__ spoly, uint8_t* __restrict__ sk) {
+  MLDSA_USE(P);
+  extern __shared__ __align__(16) uint32_t rows[];
+  const size_t s0 = (size_t)blockIdx.x * blockDim.x, total = n * (L + K);
+  const size_t s = s0 + threadIdx.x;
+  const size_t sc = s < total ? s : total - 1;
+  const size_t op = sc % n;
+  const int p = (int)(sc / n);
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int w = 0; w < 8; w++) a[w] = sseed[8 * op + w];
+  a[8] = (uint64_t)p | (0x1full << 16);  // nonce = p (s1: 0..L-1, s2: L..L+K-1), little endian 16 bit
+  a[16] = 0x8000000000000000ull;
+  leqeta_stream<ETA>(a, rows + threadIdx.x * kExpRow);
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   for (int q = warp; q < kExpThreads; q += kExpThreads / 32) {
@@ -1571,7 +1597,7 @@ __global__ void __launch_bounds__(128) kg_tr_kernel(const uint8_t* __restrict__ 
 template <class P>
 static int keygen_device(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t n, cudaStream_t st, int slot) {
   MLDSA_USE(P);
-  Ctx& c = ctx();
+  Dev& c = ctx();
   size_t off = 0;
   auto take = [&](size_t bytes) {
     size_t o = off;
@@ -1588,12 +1614,8 @@ static int keygen_device(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t 
   uint32_t* spoly = (uint32_t*)(b + oSp);
   uint32_t* s1h = (uint32_t*)(b + oSh);
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
-  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
-  if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
-    CB200_CUDA(cudaFuncSetAttribute(kg_eta_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr((const void*)expand_a_kernel<P>, kExpThreads * kExpRow * 4)) return arc;
+  if (int arc = ensure_smem_attr((const void*)kg_eta_kernel<P>, kExpThreads * kExpRow * 4)) return arc;
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
   {
     KernelScope ks(KID_MLDSA_MU, st);
@@ -1631,7 +1653,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   // h_count: 8 bytes of pinned host memory for the per-round counter (owned by the caller: the host-pointer path
   // keeps per-op status bytes in the same pinned block)
   MLDSA_USE(P);
-  Ctx& c = ctx();
+  Dev& c = ctx();
   const bool shared = sk_stride == 0;
   const size_t nkeys = shared ? 1 : n;
   size_t off = 0;
@@ -1681,13 +1703,9 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   const uint32_t* zetas = (const uint32_t*)c.dil_tw;
   constexpr int kChSmem = ChLayout<P>::smem;
 
-  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
-  if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(expand_a_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kExpThreads * kExpRow * 4));
-    if (kChSmem) CB200_CUDA(cudaFuncSetAttribute(challenge_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kChSmem));
-    CB200_CUDA(cudaFuncSetAttribute(w_kernel<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmem));
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr((const void*)expand_a_kernel<P>, kExpThreads * kExpRow * 4)) return arc;
+  if (kChSmem) if (int arc = ensure_smem_attr((const void*)challenge_kernel<P>, kChSmem)) return arc;
+  if (int arc = ensure_smem_attr((const void*)w_kernel<P>, kWSmem)) return arc;
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
   {
     KernelScope ks(KID_MLDSA_EXPAND, st);
@@ -1782,6 +1800,89 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
   CB200_CUDA(cudaGetLastError());
   if (attempts_out) *attempts_out = total_attempts;
   return 0;
+}
+
+// ------------------------------------------------------------------ the samplers on their own (thread per polynomial)
+// seed bytes at an arbitrary address -> the first `words` lanes of a zeroed state
+__device__ __forceinline__ void absorb_seed(uint64_t (&a)[25], const uint8_t* seed, int words) {
+  keccak::zero(a);
+#pragma unroll
+  for (int w = 0; w < 8; w++) {
+    if (w >= words) break;
+    uint64_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) v |= (uint64_t)seed[8 * w + b] << (8 * b);
+    a[w] = v;
+  }
+}
+// rows of kExpRow words -> polynomials (one warp per row, coalesced)
+__device__ __forceinline__ void rows_out(const uint32_t* rows, size_t s0, size_t n, uint32_t* __restrict__ polys, uint32_t base,
+                                         bool negate) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = warp; p < kExpThreads; p += kExpThreads / 32) {
+    if (s0 + p >= n) break;
+    uint32_t* dst = polys + (s0 + p) * N;
+#pragma unroll
+    for (int w = 0; w < 8; w++) {
+      const uint32_t t = rows[p * kExpRow + 32 * w + lane];
+      dst[32 * w + lane] = negate ? base - t : t;
+    }
+  }
+}
+__global__ void __launch_bounds__(kExpThreads) derive_uniform_kernel(const uint8_t* __restrict__ seeds, size_t seed_stride,
+                                                                     const uint16_t* __restrict__ nonces, size_t n,
+                                                                     uint32_t* __restrict__ polys) {
+  extern __shared__ __align__(16) uint32_t rows[];
+  const size_t s0 = (size_t)blockIdx.x * blockDim.x, s = s0 + threadIdx.x, sc = s < n ? s : n - 1;
+  uint64_t a[25];
+  absorb_seed(a, seeds + sc * seed_stride, 4);
+  a[4] = (uint64_t)nonces[sc] | (0x1full << 16);
+  a[20] = 0x8000000000000000ull;
+  uniform_stream(a, rows + threadIdx.x * kExpRow);
+  __syncthreads();
+  rows_out(rows, s0, n, polys, 0, false);
+}
+template <int ETA>
+__global__ void __launch_bounds__(kExpThreads) derive_leqeta_kernel(const uint8_t* __restrict__ seeds, size_t seed_stride,
+                                                                    const uint16_t* __restrict__ nonces, size_t n,
+                                                                    uint32_t* __restrict__ polys) {
+  extern __shared__ __align__(16) uint32_t rows[];
+  const size_t s0 = (size_t)blockIdx.x * blockDim.x, s = s0 + threadIdx.x, sc = s < n ? s : n - 1;
+  uint64_t a[25];
+  absorb_seed(a, seeds + sc * seed_stride, 8);
+  a[8] = (uint64_t)nonces[sc] | (0x1full << 16);
+  a[16] = 0x8000000000000000ull;
+  leqeta_stream<ETA>(a, rows + threadIdx.x * kExpRow);
+  __syncthreads();
+  rows_out(rows, s0, n, polys, Q + ETA, true);  // p[i] = Q + eta - t (sample.go:158,171)
+}
+template <class P>
+__global__ void __launch_bounds__(128) derive_legamma1_kernel(const uint8_t* __restrict__ seeds, size_t seed_stride,
+                                                              const uint16_t* __restrict__ nonces, size_t n,
+                                                              uint32_t* __restrict__ polys) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  uint64_t a[25];
+  absorb_seed(a, seeds + s * seed_stride, 8);
+  a[8] = (uint64_t)nonces[s] | (0x1full << 16);
+  a[16] = 0x8000000000000000ull;
+  legamma1_poly<P>(a, polys + s * N);
+}
+template <class P>
+__global__ void __launch_bounds__(64) derive_ball_kernel(const uint8_t* __restrict__ seeds, size_t seed_stride, size_t n,
+                                                         uint32_t* __restrict__ polys) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  constexpr int CTW = P::CTILDE / 8;
+  uint64_t a[25], ct[CTW], nz[4], ng[4];
+  absorb_seed(a, seeds + s * seed_stride, CTW);
+#pragma unroll
+  for (int i = 0; i < CTW; i++) ct[i] = a[i];
+  sample_in_ball<P>(ct, a, nz, ng);
+  uint32_t* dst = polys + s * N;
+#pragma unroll 1
+  for (int q = 0; q < 4; q++)
+    for (int b = 0; b < 64; b++) dst[64 * q + b] = ((nz[q] >> b) & 1) ? (((ng[q] >> b) & 1) ? Q - 1 : 1u) : 0u;
 }
 
 }  // namespace mldsa
@@ -1888,27 +1989,33 @@ int cb200_mldsa_sign(int mode, const uint8_t* sk, size_t sk_stride, const uint8_
       set_error("cb200_mldsa_sign: device sk and sk_stride must be 16-byte aligned");
       return CB200_ERR_ARG;
     }
+    if (n >= (1u << 24)) {  // the attempt bid of the finalize step packs (attempt << 24 | slot)
+      set_error("cb200_mldsa_sign: a device-pointer batch is limited to 2^24 - 1 signatures per call (got %zu)", n);
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(sig);
+    if (call.rc) return call.rc;
     const uint8_t* dctx = nullptr;
     if (ctxlen) {  // the context string is at most 255 bytes and always a host pointer: stage it
-      CB200_CUDA(cudaMemcpyAsync(ctx().small, context, ctxlen, cudaMemcpyHostToDevice, ctx().cur));
-      dctx = (const uint8_t*)ctx().small;
+      CB200_CUDA(cudaMemcpyAsync(call.ws->small, context, ctxlen, cudaMemcpyHostToDevice, call.st));
+      dctx = (const uint8_t*)call.ws->small;
     }
-    void* pin0 = nullptr;
-    rc = ensure_pinned(64, &pin0);
-    if (rc) return rc;
-    return dispatch_sign(mode, sk, sk_stride, msgs, msg_off, dctx, (int)ctxlen, rnd, sig, status, n, internal, ctx().cur, 3,
-                         attempts, (volatile uint32_t*)pin0);
+    return dispatch_sign(mode, sk, sk_stride, msgs, msg_off, dctx, (int)ctxlen, rnd, sig, status, n, internal, call.st, 3,
+                         attempts, (volatile uint32_t*)call.ws->pin);
   }
-  // host pointers: chunks of 2^16 signatures through the three staging slots.  The rejection loop of a chunk keeps
-  // the host busy (one counter read per round), so the input of chunk i+1 is put in flight before chunk i starts and
-  // the signatures of chunk i travel back while chunk i+1 runs.
-  Ctx& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
+  // host pointers: one contiguous range of the batch per GPU; on each GPU chunks of 2^16 signatures go through the three
+  // staging slots.  The rejection loop of a chunk keeps the host busy (one counter read per round), so the input of
+  // chunk i+1 is put in flight before chunk i starts and the signatures of chunk i travel back while chunk i+1 runs.
+  std::atomic<uint64_t> all_attempts{0};
+  std::atomic<size_t> all_bad{0};
+  rc = for_each_shard(n, 1u << 12, [&](size_t sh_first, size_t sh_n) -> int {
+  Dev& c = ctx();
+  int rc = 0;
   constexpr size_t kChunk = 1u << 16;
-  const size_t nchunks = (n + kChunk - 1) / kChunk, cmax = n < kChunk ? n : kChunk;
+  const size_t nchunks = (sh_n + kChunk - 1) / kChunk, cmax = sh_n < kChunk ? sh_n : kChunk;
   size_t max_msg = 0;
-  for (size_t first = 0; first < n; first += kChunk) {
-    const size_t cnt = n - first < kChunk ? n - first : kChunk;
+  for (size_t first = sh_first; first < sh_first + sh_n; first += kChunk) {
+    const size_t cnt = sh_first + sh_n - first < kChunk ? sh_first + sh_n - first : kChunk;
     max_msg = std::max<size_t>(max_msg, (size_t)(msg_off[first + cnt] - msg_off[first]));
   }
   size_t off = 0;
@@ -1925,13 +2032,13 @@ int cb200_mldsa_sign(int mode, const uint8_t* sk, size_t sk_stride, const uint8_
     if (rc) return rc;
   }
   void* pin = nullptr;
-  rc = ensure_pinned(n + 64, &pin);
+  rc = ensure_pinned(sh_n + 64, &pin);
   if (rc) return rc;
   uint8_t* hs = (uint8_t*)pin;
-  volatile uint32_t* h_count = (volatile uint32_t*)((char*)pin + ((n + 15) & ~(size_t)15));
+  volatile uint32_t* h_count = (volatile uint32_t*)((char*)pin + ((sh_n + 15) & ~(size_t)15));
   std::vector<std::vector<uint64_t>> rebased(nchunks);  // message offsets relative to the chunk; alive until the final sync
   auto issue_h2d = [&](size_t ci) -> int {
-    const size_t first = ci * kChunk, cnt = n - first < kChunk ? n - first : kChunk;
+    const size_t first = sh_first + ci * kChunk, cnt = sh_first + sh_n - first < kChunk ? sh_first + sh_n - first : kChunk;
     const int sl = (int)(ci % 3);
     cudaStream_t st = c.pipe[sl];
     char* d = (char*)c.scratch[sl];
@@ -1954,7 +2061,7 @@ int cb200_mldsa_sign(int mode, const uint8_t* sk, size_t sk_stride, const uint8_
   uint64_t total_attempts = 0;
   rc = issue_h2d(0);
   for (size_t ci = 0; ci < nchunks && rc == 0; ci++) {
-    const size_t first = ci * kChunk, cnt = n - first < kChunk ? n - first : kChunk;
+    const size_t first = sh_first + ci * kChunk, cnt = sh_first + sh_n - first < kChunk ? sh_first + sh_n - first : kChunk;
     const int sl = (int)(ci % 3);
     cudaStream_t st = c.pipe[sl];
     char* d = (char*)c.scratch[sl];
@@ -1970,16 +2077,21 @@ int cb200_mldsa_sign(int mode, const uint8_t* sk, size_t sk_stride, const uint8_
     if (rc) break;
     total_attempts += att;
     CB200_CUDA(cudaMemcpyAsync(sig + first * ms.sig, d + oSig, cnt * ms.sig, cudaMemcpyDeviceToHost, st));
-    CB200_CUDA(cudaMemcpyAsync(hs + first, d + oSt, cnt, cudaMemcpyDeviceToHost, st));
+    CB200_CUDA(cudaMemcpyAsync(hs + (first - sh_first), d + oSt, cnt, cudaMemcpyDeviceToHost, st));
   }
   for (int sl = 0; sl < 3; sl++) CB200_CUDA(cudaStreamSynchronize(c.pipe[sl]));
   if (rc) return rc;
-  if (attempts) *attempts = total_attempts;
+  all_attempts += total_attempts;
   size_t nbad = 0;
-  for (size_t i = 0; i < n; i++) nbad += hs[i] != 0;
-  if (status) memcpy(status, hs, n);
-  if (nbad) {
-    set_error("cb200_mldsa_sign: %zu of %zu signatures exhausted 576 attempts", nbad, n);
+  for (size_t i = 0; i < sh_n; i++) nbad += hs[i] != 0;
+  all_bad += nbad;
+  if (status) memcpy(status + sh_first, hs, sh_n);
+  return 0;
+  });
+  if (rc) return rc;
+  if (attempts) *attempts = all_attempts.load();
+  if (all_bad.load()) {
+    set_error("cb200_mldsa_sign: %zu of %zu signatures exhausted 576 attempts", all_bad.load(), n);
     return CB200_ERR_SIGN_ATTEMPTS;
   }
   return 0;
@@ -2015,44 +2127,57 @@ int cb200_mldsa_verify(int mode, const uint8_t* pk, size_t pk_stride, const uint
       set_error("cb200_mldsa_verify: device pk and pk_stride must be 16-byte aligned");
       return CB200_ERR_ARG;
     }
+    DeviceCall call(ok);
+    if (call.rc) return call.rc;
     const uint8_t* dctx = nullptr;
     if (ctxlen) {
-      CB200_CUDA(cudaMemcpyAsync(ctx().small, context, ctxlen, cudaMemcpyHostToDevice, ctx().cur));
-      dctx = (const uint8_t*)ctx().small;
+      CB200_CUDA(cudaMemcpyAsync(call.ws->small, context, ctxlen, cudaMemcpyHostToDevice, call.st));
+      dctx = (const uint8_t*)call.ws->small;
     }
-    return dispatch_verify(mode, pk, pk_stride, msgs, msg_off, dctx, (int)ctxlen, sig, ok, n, internal, ctx().cur, 3);
+    return dispatch_verify(mode, pk, pk_stride, msgs, msg_off, dctx, (int)ctxlen, sig, ok, n, internal, call.st, 3);
   }
-  Ctx& c = ctx();
-  std::lock_guard<std::mutex> lock(c.mu);
-  cudaStream_t st = c.pipe[0];
-  const size_t msg_bytes = (size_t)msg_off[n];
-  size_t off = 0;
-  auto take = [&](size_t bytes) {
-    size_t o = off;
-    off += (bytes + 255) & ~(size_t)255;
-    return o;
-  };
-  const size_t nk = pk_stride ? n : 1;
-  const size_t oPk = take(nk * ms.pk), oMsg = take(msg_bytes + 8), oOff = take((n + 1) * 8), oSig = take(n * ms.sig),
-               oOk = take(n), oCtx = take(256);
-  rc = ensure_scratch(0, off);
-  if (rc) return rc;
-  char* d = (char*)c.scratch[0];
-  if (pk_stride == 0 || pk_stride == ms.pk)
-    CB200_CUDA(cudaMemcpyAsync(d + oPk, pk, nk * ms.pk, cudaMemcpyHostToDevice, st));
-  else
-    CB200_CUDA(cudaMemcpy2DAsync(d + oPk, ms.pk, pk, pk_stride, ms.pk, n, cudaMemcpyHostToDevice, st));
-  if (msg_bytes) CB200_CUDA(cudaMemcpyAsync(d + oMsg, msgs, msg_bytes, cudaMemcpyHostToDevice, st));
-  CB200_CUDA(cudaMemcpyAsync(d + oOff, msg_off, (n + 1) * 8, cudaMemcpyHostToDevice, st));
-  CB200_CUDA(cudaMemcpyAsync(d + oSig, sig, n * ms.sig, cudaMemcpyHostToDevice, st));
-  if (ctxlen) CB200_CUDA(cudaMemcpyAsync(d + oCtx, context, ctxlen, cudaMemcpyHostToDevice, st));
-  rc = dispatch_verify(mode, (const uint8_t*)d + oPk, pk_stride ? ms.pk : (size_t)0, (const uint8_t*)d + oMsg,
-                       (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : (const uint8_t*)nullptr,
-                       (int)ctxlen, (const uint8_t*)d + oSig, (uint8_t*)d + oOk, n, internal, st, 0);
-  if (rc) return rc;
-  CB200_CUDA(cudaMemcpyAsync(ok, d + oOk, n, cudaMemcpyDeviceToHost, st));
-  CB200_CUDA(cudaStreamSynchronize(st));
-  return 0;
+  // host pointers: one contiguous range per GPU, each in chunks of 2^15 signatures on the first staging slot
+  return for_each_shard(n, 1u << 12, [&](size_t sh_first, size_t sh_n) -> int {
+    Dev& c = ctx();
+    cudaStream_t st = c.pipe[0];
+    constexpr size_t kChunk = 1u << 15;
+    for (size_t first = sh_first; first < sh_first + sh_n; first += kChunk) {
+      const size_t cnt = sh_first + sh_n - first < kChunk ? sh_first + sh_n - first : kChunk;
+      const uint64_t m0 = msg_off[first];
+      const size_t msg_bytes = (size_t)(msg_off[first + cnt] - m0);
+      size_t off = 0;
+      auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return o;
+      };
+      const size_t nk = pk_stride ? cnt : 1;
+      const size_t oPk = take(nk * ms.pk), oMsg = take(msg_bytes + 8), oOff = take((cnt + 1) * 8), oSig = take(cnt * ms.sig),
+                   oOk = take(cnt), oCtx = take(256);
+      int rc = ensure_scratch(0, off);
+      if (rc) return rc;
+      char* d = (char*)c.scratch[0];
+      if (pk_stride == 0)
+        CB200_CUDA(cudaMemcpyAsync(d + oPk, pk, ms.pk, cudaMemcpyHostToDevice, st));
+      else if (pk_stride == ms.pk)
+        CB200_CUDA(cudaMemcpyAsync(d + oPk, pk + first * ms.pk, nk * ms.pk, cudaMemcpyHostToDevice, st));
+      else
+        CB200_CUDA(cudaMemcpy2DAsync(d + oPk, ms.pk, pk + first * pk_stride, pk_stride, ms.pk, cnt, cudaMemcpyHostToDevice, st));
+      if (msg_bytes) CB200_CUDA(cudaMemcpyAsync(d + oMsg, msgs + m0, msg_bytes, cudaMemcpyHostToDevice, st));
+      std::vector<uint64_t> ro(cnt + 1);
+      for (size_t i = 0; i <= cnt; i++) ro[i] = msg_off[first + i] - m0;
+      CB200_CUDA(cudaMemcpyAsync(d + oOff, ro.data(), (cnt + 1) * 8, cudaMemcpyHostToDevice, st));
+      CB200_CUDA(cudaMemcpyAsync(d + oSig, sig + first * ms.sig, cnt * ms.sig, cudaMemcpyHostToDevice, st));
+      if (ctxlen) CB200_CUDA(cudaMemcpyAsync(d + oCtx, context, ctxlen, cudaMemcpyHostToDevice, st));
+      rc = dispatch_verify(mode, (const uint8_t*)d + oPk, pk_stride ? ms.pk : (size_t)0, (const uint8_t*)d + oMsg,
+                           (const uint64_t*)(d + oOff), ctxlen ? (const uint8_t*)d + oCtx : (const uint8_t*)nullptr,
+                           (int)ctxlen, (const uint8_t*)d + oSig, (uint8_t*)d + oOk, cnt, internal, st, 0);
+      if (rc) return rc;
+      CB200_CUDA(cudaMemcpyAsync(ok + first, d + oOk, cnt, cudaMemcpyDeviceToHost, st));
+      CB200_CUDA(cudaStreamSynchronize(st));  // `ro` and the scratch are reused by the next chunk
+    }
+    return 0;
+  });
 }
 
 int cb200_mldsa_keygen(int mode, const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t n) {
@@ -2078,13 +2203,15 @@ int cb200_mldsa_keygen(int mode, const uint8_t* seeds, uint8_t* pk, uint8_t* sk,
       set_error("cb200_mldsa_keygen: device buffers must be 16-byte aligned");
       return CB200_ERR_ARG;
     }
-    return dispatch_keygen(mode, seeds, pk, sk, n, ctx().cur, 3);
+    DeviceCall call(pk);
+    if (call.rc) return call.rc;
+    return dispatch_keygen(mode, seeds, pk, sk, n, call.st, 3);
   }
   std::vector<Buf> bufs(3);
   bufs[0] = Buf{seeds, nullptr, 32, false, 0};
   bufs[1] = Buf{nullptr, pk, ms.pk, false, 0};
   bufs[2] = Buf{nullptr, sk, ms.sk, false, 0};
-  return run_staged(bufs, n, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) -> int {
+  return run_host(bufs, n, 1u << 14, 1u << 12, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) -> int {
     return dispatch_keygen(mode, (const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
   });
 }
@@ -2105,5 +2232,89 @@ int cb200_mldsa65_keygen(const uint8_t* seeds, uint8_t* pk, uint8_t* sk, size_t 
 size_t cb200_mldsa65_signature_size(void) { return 3309; }
 size_t cb200_mldsa65_public_key_size(void) { return 1952; }
 size_t cb200_mldsa65_private_key_size(void) { return 4032; }
+
+/* ---- the samplers as entry points of their own (sign/mldsa/mldsa{44,65,87}/internal/sample.go) ---- */
+static int sampler_entry(const char* fn, int kind, int mode, uint32_t* polys, const uint8_t* seeds, size_t seed_stride,
+                         size_t seed_len, const uint16_t* nonces, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (mode != 44 && mode != 65 && mode != 87) {
+    set_error("%s: mode must be 44, 65 or 87, got %d", fn, mode);
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  if (!polys || !seeds || (kind != 3 && !nonces) || (seed_stride != 0 && seed_stride < seed_len)) {
+    set_error("%s: bad argument", fn);
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(polys);
+  if (dev != is_device_ptr(seeds) || (nonces && dev != is_device_ptr(nonces))) {
+    set_error("%s: mixed host/device pointers", fn);
+    return CB200_ERR_ARG;
+  }
+  auto launch = [&](const uint8_t* sd, size_t stride, const uint16_t* nn, uint32_t* out, size_t cnt, cudaStream_t st) -> int {
+    using namespace mldsa;
+    KernelScope ks(KID_SAMPLER, st);
+    const unsigned g64 = (unsigned)((cnt + kExpThreads - 1) / kExpThreads), g128 = (unsigned)((cnt + 127) / 128);
+    constexpr int smem = kExpThreads * kExpRow * 4;
+    if (kind == 0) {
+      if (int arc = ensure_smem_attr((const void*)derive_uniform_kernel, smem)) return arc;
+      derive_uniform_kernel<<<g64, kExpThreads, smem, st>>>(sd, stride, nn, cnt, out);
+    } else if (kind == 1) {
+      if (mode == 65) {
+        if (int arc = ensure_smem_attr((const void*)derive_leqeta_kernel<4>, smem)) return arc;
+        derive_leqeta_kernel<4><<<g64, kExpThreads, smem, st>>>(sd, stride, nn, cnt, out);
+      } else {
+        if (int arc = ensure_smem_attr((const void*)derive_leqeta_kernel<2>, smem)) return arc;
+        derive_leqeta_kernel<2><<<g64, kExpThreads, smem, st>>>(sd, stride, nn, cnt, out);
+      }
+    } else if (kind == 2) {
+      if (mode == 44)
+        derive_legamma1_kernel<Params<44>><<<g128, 128, 0, st>>>(sd, stride, nn, cnt, out);
+      else
+        derive_legamma1_kernel<Params<65>><<<g128, 128, 0, st>>>(sd, stride, nn, cnt, out);  // 87: the same gamma1
+    } else {
+      if (mode == 44)
+        derive_ball_kernel<Params<44>><<<g64, 64, 0, st>>>(sd, stride, cnt, out);
+      else if (mode == 65)
+        derive_ball_kernel<Params<65>><<<g64, 64, 0, st>>>(sd, stride, cnt, out);
+      else
+        derive_ball_kernel<Params<87>><<<g64, 64, 0, st>>>(sd, stride, cnt, out);
+    }
+    CB200_CUDA(cudaGetLastError());
+    return 0;
+  };
+  if (dev) {
+    if (((uintptr_t)polys & 15) || (nonces && ((uintptr_t)nonces & 1))) {
+      set_error("%s: device polynomials must be 16-byte aligned", fn);
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(polys);
+    if (call.rc) return call.rc;
+    return launch(seeds, seed_stride, nonces, polys, n, call.st);
+  }
+  std::vector<Buf> bufs = {Buf{seeds, nullptr, seed_len, seed_stride == 0, seed_stride},
+                           Buf{nullptr, polys, 1024, false, 0}};
+  if (nonces) bufs.push_back(Buf{nonces, nullptr, 2, false, 0});
+  return run_host(bufs, n, 1u << 15, 1u << 13, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+    return launch((const uint8_t*)d[0], seed_stride == 0 ? 0 : seed_len, nonces ? (const uint16_t*)d[2] : nullptr,
+                  (uint32_t*)d[1], cnt, st);
+  });
+}
+int cb200_dil_derive_uniform(uint32_t* polys, const uint8_t* seeds, size_t seed_stride, const uint16_t* nonces, size_t n) {
+  return sampler_entry("cb200_dil_derive_uniform", 0, 65, polys, seeds, seed_stride, 32, nonces, n);
+}
+int cb200_dil_derive_leq_eta(int mode, uint32_t* polys, const uint8_t* seeds, size_t seed_stride, const uint16_t* nonces,
+                             size_t n) {
+  return sampler_entry("cb200_dil_derive_leq_eta", 1, mode, polys, seeds, seed_stride, 64, nonces, n);
+}
+int cb200_dil_derive_le_gamma1(int mode, uint32_t* polys, const uint8_t* seeds, size_t seed_stride, const uint16_t* nonces,
+                               size_t n) {
+  return sampler_entry("cb200_dil_derive_le_gamma1", 2, mode, polys, seeds, seed_stride, 64, nonces, n);
+}
+int cb200_dil_derive_ball(int mode, uint32_t* polys, const uint8_t* seeds, size_t seed_stride, size_t n) {
+  const size_t len = mode == 44 ? 32 : mode == 65 ? 48 : 64;
+  return sampler_entry("cb200_dil_derive_ball", 3, mode, polys, seeds, seed_stride, len, nullptr, n);
+}
 
 }  // extern "C"

@@ -17,6 +17,8 @@
 //   3. encrypt_kernel one octet (8 lanes) per op: NTT(r), A^T o r, t o r, InvNTT, +e, compress
 #include <string.h>
 
+#include <algorithm>
+
 #include "../../include/circl_b200.h"
 #include "context.h"
 #include "mlkem_internal.h"
@@ -177,6 +179,34 @@ __device__ __forceinline__ void cbd3_store(const uint64_t (&w)[24], int16_t* __r
   }
 }
 
+// One SHAKE128 stream of DeriveUniform (sample.go:192-236): `a` holds the absorbed, padded first block; the 256 accepted
+// coefficients land in this thread's shared-memory row (256 int16 + slack, kRowWords words).
+__device__ __forceinline__ void uniform_stream(uint64_t (&a)[25], uint32_t* row_words) {
+  int16_t* row = reinterpret_cast<int16_t*>(row_words);
+  uint32_t wp = smem_u32(row);
+  const uint32_t wend = wp + 2 * N;
+  do {
+    keccak::f1600(a);
+    wp = reject_block(a, wp, wend);
+  } while (wp < wend);
+}
+// One SHAKE256 PRF stream of DeriveNoise (sample.go:31-95): `a` holds the absorbed, padded block seed || nonce
+template <int ETA>
+__device__ __forceinline__ void noise_stream(uint64_t (&a)[25], int16_t* __restrict__ dst) {
+  keccak::f1600(a);
+  if constexpr (ETA == 3) {
+    uint64_t w[24];
+#pragma unroll
+    for (int q = 0; q < 17; q++) w[q] = a[q];
+    keccak::f1600(a);
+#pragma unroll
+    for (int q = 0; q < 7; q++) w[17 + q] = a[q];
+    cbd3_store(w, dst);
+  } else {
+    cbd2_store(a, dst);
+  }
+}
+
 // Stream index space (blockDim-aligned so that warps never mix stream kinds):
 //   [0, nkeys*K*K)               matrix streams, s = (i*K + j) * nkeys + key  -> A^T[key][i][j] = XOF(rho, i, j)
 //   then n*(2K+1) noise streams, s = nonce * n + op                            -> PRF(r_op, nonce)
@@ -209,13 +239,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
     // m[i][j] = XOF(rho, x, y) with (x, y) = (i, j) if transpose else (j, i)
     a[4] = (uint64_t)(transpose ? i : j) | ((uint64_t)(transpose ? j : i) << 8) | (0x1full << 16);
     a[20] = 0x8000000000000000ull;                               // rate 168
-    int16_t* row = reinterpret_cast<int16_t*>(rows + threadIdx.x * kRowWords);
-    uint32_t wp = smem_u32(row);
-    const uint32_t wend = wp + 2 * N;
-    do {
-      keccak::f1600(a);
-      wp = reject_block(a, wp, wend);
-    } while (wp < wend);
+    uniform_stream(a, rows + threadIdx.x * kRowWords);
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int p = warp; p < (int)blockDim.x; p += blockDim.x / 32) {
@@ -236,19 +260,11 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
     for (int w = 0; w < 4; w++) a[w] = r[r_words * op + w];
     a[4] = (uint64_t)nonce | (0x1full << 8);
     a[16] = 0x8000000000000000ull;  // rate 136
-    keccak::f1600(a);
     int16_t* dst = noise + (op * n_noise + nonce) * N;
-    if (P::eta1 == 3 && nonce < n_eta1) {
-      uint64_t w[24];
-#pragma unroll
-      for (int q = 0; q < 17; q++) w[q] = a[q];
-      keccak::f1600(a);
-#pragma unroll
-      for (int q = 0; q < 7; q++) w[17 + q] = a[q];
-      cbd3_store(w, dst);
-    } else {
-      cbd2_store(a, dst);
-    }
+    if (P::eta1 == 3 && nonce < n_eta1)
+      noise_stream<3>(a, dst);
+    else
+      noise_stream<2>(a, dst);
   }
 }
 
@@ -664,7 +680,8 @@ template <int K>
 static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct, uint8_t* ss, uint8_t* status, size_t n,
                          cudaStream_t st, int slot) {
   using P = Params<K>;
-  Ctx& c = ctx();
+  Dev& c = ctx();
+  WorkSet& ws = wset(slot);
   const size_t sub = n < kSub ? n : kSub;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -689,11 +706,7 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
   uint8_t* kbar = (uint8_t*)(b + o_k);
   uint8_t* ct2 = (uint8_t*)(b + o_ct2);
   const uint8_t* ek = dk + 384 * K;  // dk = sk || ek || H(ek) || z (kyber.go:187-201)
-  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
-  if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr((const void*)sample_kernel<K>, kSampleSmem)) return arc;
   const kyber::TwPair* tw = (const kyber::TwPair*)c.kyber_tw;
   {
     KernelScope ks(KID_MLKEM_ENCRYPT, st);
@@ -707,11 +720,11 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
     KernelScope ks(KID_MLKEM_G, st);
     g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(mprime, dk + 384 * K + P::ek_bytes, dk_stride, n, kbar, r);
   }
-  CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
-  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][q], c.ev_fork[slot], 0));
+  CB200_CUDA(cudaEventRecord(ws.ev_fork, st));
+  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(ws.lane[q], ws.ev_fork, 0));
   int l = 0;
   for (size_t first = 0; first < n; first += sub, l ^= 1) {
-    cudaStream_t ls = c.profiling ? st : c.lane[slot][l];
+    cudaStream_t ls = profiling_on() ? st : ws.lane[l];
     int16_t* A = (int16_t*)(b + o_A[l]);
     int16_t* noise = (int16_t*)(b + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
@@ -729,8 +742,8 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
     }
   }
   for (int q = 0; q < 2; q++) {
-    CB200_CUDA(cudaEventRecord(c.ev_join[slot][q], c.lane[slot][q]));
-    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_join[slot][q], 0));
+    CB200_CUDA(cudaEventRecord(ws.ev_join[q], ws.lane[q]));
+    CB200_CUDA(cudaStreamWaitEvent(st, ws.ev_join[q], 0));
   }
   {
     KernelScope ks(KID_MLKEM_G, st);
@@ -874,7 +887,8 @@ template <int K>
 static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n, cudaStream_t st, int slot,
                          int mlkem = 1) {
   using P = Params<K>;
-  Ctx& c = ctx();
+  Dev& c = ctx();
+  WorkSet& ws = wset(slot);
   const size_t sub = n < kSub ? n : kSub;
   constexpr size_t dksz = 768 * K + 96;
   size_t off = 0;
@@ -895,20 +909,16 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
   char* b = (char*)base;
   uint64_t* rs = (uint64_t*)(b + o_rs);
   uint64_t* h = (uint64_t*)(b + o_h);
-  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
-  if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr((const void*)sample_kernel<K>, kSampleSmem)) return arc;
   {
     KernelScope ks(KID_MLKEM_G, st);
     keygen_seed_kernel<K><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, n, rs, ek, dk, mlkem);
   }
-  CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
-  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][q], c.ev_fork[slot], 0));
+  CB200_CUDA(cudaEventRecord(ws.ev_fork, st));
+  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(ws.lane[q], ws.ev_fork, 0));
   int l = 0;
   for (size_t first = 0; first < n; first += sub, l ^= 1) {
-    cudaStream_t ls = c.profiling ? st : c.lane[slot][l];
+    cudaStream_t ls = profiling_on() ? st : ws.lane[l];
     int16_t* A = (int16_t*)(b + o_A[l]);
     int16_t* noise = (int16_t*)(b + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
@@ -925,8 +935,8 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
     }
   }
   for (int q = 0; q < 2; q++) {
-    CB200_CUDA(cudaEventRecord(c.ev_join[slot][q], c.lane[slot][q]));
-    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_join[slot][q], 0));
+    CB200_CUDA(cudaEventRecord(ws.ev_join[q], ws.lane[q]));
+    CB200_CUDA(cudaStreamWaitEvent(st, ws.ev_join[q], 0));
   }
   {  // H(ek) into dk (kyber.go:69-75)
     KernelScope ks(KID_MLKEM_HASH_EK, st);
@@ -1012,17 +1022,18 @@ static int r3_encrypt(const uint8_t* ek, size_t ek_stride, const uint8_t* h, siz
                       uint8_t* kbar, uint64_t* r, char* base, const size_t (&o_A)[2], const size_t (&o_n)[2], size_t n,
                       cudaStream_t st, int slot) {
   using P = Params<K>;
-  Ctx& c = ctx();
+  Dev& c = ctx();
+  WorkSet& ws = wset(slot);
   const size_t sub = n < kSub ? n : kSub;
   {
     KernelScope ks(KID_MLKEM_G, st);
     g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(m, h, h_stride, n, kbar, r);
   }
-  CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
-  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][q], c.ev_fork[slot], 0));
+  CB200_CUDA(cudaEventRecord(ws.ev_fork, st));
+  for (int q = 0; q < 2; q++) CB200_CUDA(cudaStreamWaitEvent(ws.lane[q], ws.ev_fork, 0));
   int l = 0;
   for (size_t first = 0; first < n; first += sub, l ^= 1) {
-    cudaStream_t ls = c.profiling ? st : c.lane[slot][l];
+    cudaStream_t ls = profiling_on() ? st : ws.lane[l];
     int16_t* A = (int16_t*)(base + o_A[l]);
     int16_t* noise = (int16_t*)(base + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
@@ -1040,8 +1051,8 @@ static int r3_encrypt(const uint8_t* ek, size_t ek_stride, const uint8_t* h, siz
     }
   }
   for (int q = 0; q < 2; q++) {
-    CB200_CUDA(cudaEventRecord(c.ev_join[slot][q], c.lane[slot][q]));
-    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_join[slot][q], 0));
+    CB200_CUDA(cudaEventRecord(ws.ev_join[q], ws.lane[q]));
+    CB200_CUDA(cudaStreamWaitEvent(st, ws.ev_join[q], 0));
   }
   return 0;
 }
@@ -1051,7 +1062,8 @@ template <int K>
 static int r3_device(int decaps, const uint8_t* key, size_t key_stride, const uint8_t* in, uint8_t* ct_out, uint8_t* ss, size_t n,
                      cudaStream_t st, int slot) {
   using P = Params<K>;
-  Ctx& c = ctx();
+  Dev& c = ctx();
+  WorkSet& ws = wset(slot);
   const size_t sub = n < kSub ? n : kSub;
   size_t off = 0;
   auto take = [&](size_t bytes) {
@@ -1074,11 +1086,7 @@ static int r3_device(int decaps, const uint8_t* key, size_t key_stride, const ui
   uint64_t* r = (uint64_t*)(b + o_r);
   uint8_t* m = (uint8_t*)(b + o_m);
   uint8_t* kbar = (uint8_t*)(b + o_k);
-  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
-  if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr((const void*)sample_kernel<K>, kSampleSmem)) return arc;
   const kyber::TwPair* tw = (const kyber::TwPair*)c.kyber_tw;
   if (!decaps) {
     {
@@ -1123,7 +1131,8 @@ template <int K>
 static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
                          uint8_t* status, size_t n, cudaStream_t st, int slot) {
   using P = Params<K>;
-  Ctx& c = ctx();
+  Dev& c = ctx();
+  WorkSet& ws = wset(slot);
   const bool shared = (ek_stride == 0);
   const size_t nkeys = shared ? 1 : n;
   const size_t sub = n < kSub ? n : kSub;
@@ -1146,11 +1155,7 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
   uint64_t* h = (uint64_t*)((char*)base + o_h);
   uint64_t* r = (uint64_t*)((char*)base + o_r);
 
-  static std::atomic<bool> attr_set{false};  // idempotent work; the flag only saves the calls
-  if (!attr_set) {
-    CB200_CUDA(cudaFuncSetAttribute(sample_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSampleSmem));
-    attr_set = true;
-  }
+  if (int arc = ensure_smem_attr((const void*)sample_kernel<K>, kSampleSmem)) return arc;
   {
     KernelScope ks(KID_MLKEM_HASH_EK, st);
     hash_ek_kernel<K><<<(unsigned)((nkeys + 127) / 128), 128, 0, st>>>(ek, ek_stride, nkeys, h);
@@ -1167,12 +1172,12 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
   }
   // Sub-batches alternate between two internal streams (fork/join on events): the tail wave of one
   // sub-batch's kernels overlaps the next sub-batch instead of idling SMs.
-  CB200_CUDA(cudaEventRecord(c.ev_fork[slot], st));
-  for (int l = 0; l < 2; l++) CB200_CUDA(cudaStreamWaitEvent(c.lane[slot][l], c.ev_fork[slot], 0));
+  CB200_CUDA(cudaEventRecord(ws.ev_fork, st));
+  for (int l = 0; l < 2; l++) CB200_CUDA(cudaStreamWaitEvent(ws.lane[l], ws.ev_fork, 0));
   int l = 0;
   for (size_t first = 0; first < n; first += sub, l ^= 1) {
     // per-kernel event timing (cb200_profile_enable) wants true, non-overlapped durations: stay on one stream
-    cudaStream_t ls = c.profiling ? st : c.lane[slot][l];
+    cudaStream_t ls = profiling_on() ? st : ws.lane[l];
     int16_t* A = (int16_t*)((char*)base + o_A[l]);
     int16_t* noise = (int16_t*)((char*)base + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
@@ -1194,8 +1199,8 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
     }
   }
   for (int q = 0; q < 2; q++) {
-    CB200_CUDA(cudaEventRecord(c.ev_join[slot][q], c.lane[slot][q]));
-    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_join[slot][q], 0));
+    CB200_CUDA(cudaEventRecord(ws.ev_join[q], ws.lane[q]));
+    CB200_CUDA(cudaStreamWaitEvent(st, ws.ev_join[q], 0));
   }
   CB200_CUDA(cudaGetLastError());
   return 0;
@@ -1206,6 +1211,161 @@ static int encaps_any(int k, const uint8_t* ek, size_t ek_stride, const uint8_t*
   return k == 2   ? encaps_device<2>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
          : k == 3 ? encaps_device<3>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
                   : encaps_device<4>(ek, ek_stride, seeds, ct, ss, status, n, st, slot);
+}
+
+// ------------------------------------------------------------------ 7. the sampler and serialisation surface on its own
+// (*Poly).DeriveUniform (sample.go:192-236) for n independent (seed, x, y): the matrix branch of sample_kernel
+__global__ void __launch_bounds__(128) derive_uniform_kernel(const uint8_t* __restrict__ seeds, size_t seed_stride,
+                                                             const uint8_t* __restrict__ xy, size_t n,
+                                                             int16_t* __restrict__ polys) {
+  extern __shared__ __align__(16) uint32_t rows[];
+  const size_t s0 = (size_t)blockIdx.x * blockDim.x, s = s0 + threadIdx.x, sc = s < n ? s : n - 1;
+  const uint8_t* seed = seeds + sc * seed_stride;
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) v |= (uint64_t)seed[8 * w + b] << (8 * b);
+    a[w] = v;
+  }
+  a[4] = (uint64_t)xy[2 * sc] | ((uint64_t)xy[2 * sc + 1] << 8) | (0x1full << 16);
+  a[20] = 0x8000000000000000ull;
+  uniform_stream(a, rows + threadIdx.x * kRowWords);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int p = warp; p < (int)blockDim.x; p += blockDim.x / 32) {
+    if (s0 + p >= n) break;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(polys + (s0 + p) * N);
+#pragma unroll
+    for (int w = 0; w < 4; w++) dst[32 * w + lane] = rows[p * kRowWords + 32 * w + lane];
+  }
+}
+// (*Poly).DeriveNoise (sample.go:31-95) for n independent (seed, nonce): the noise branch of sample_kernel
+template <int ETA>
+__global__ void __launch_bounds__(128) derive_noise_kernel(const uint8_t* __restrict__ seeds, size_t seed_stride,
+                                                           const uint8_t* __restrict__ nonces, size_t n,
+                                                           int16_t* __restrict__ polys) {
+  const size_t s = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const uint8_t* seed = seeds + s * seed_stride;
+  uint64_t a[25];
+  keccak::zero(a);
+#pragma unroll
+  for (int w = 0; w < 4; w++) {
+    uint64_t v = 0;
+#pragma unroll
+    for (int b = 0; b < 8; b++) v |= (uint64_t)seed[8 * w + b] << (8 * b);
+    a[w] = v;
+  }
+  a[4] = (uint64_t)nonces[s] | (0x1full << 8);
+  a[16] = 0x8000000000000000ull;
+  noise_stream<ETA>(a, polys + s * N);
+}
+
+// Pack / Unpack / CompressTo / Decompress / CompressMessageTo / DecompressMessage (poly.go:106-328): octet per
+// polynomial on the C layout, the same lane code the fused kernels use.  OP 0 = pack, 1 = unpack, 2 = compress, 3 = decompress.
+template <int OP, int D>
+__global__ void __launch_bounds__(128) codec_kernel(const void* __restrict__ in, void* __restrict__ out, size_t n) {
+  using namespace kyber;
+  const int lane = threadIdx.x & 31, v = lane & 7;
+  const size_t p = (size_t)blockIdx.x * 16 + (threadIdx.x >> 3);
+  if (p >= n) return;
+  constexpr int bytes = (D == 12) ? 384 : 32 * D;
+  int32_t r[32];
+  if (OP == 0 || OP == 2) {
+    gload_C(reinterpret_cast<const uint32_t*>(in) + p * (N / 2), v, r);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(reinterpret_cast<uint8_t*>(out) + p * bytes);
+    if (OP == 0) {
+      uint32_t w[12];
+      pack12_C(r, w);
+#pragma unroll
+      for (int i = 0; i < 12; i++) dst[12 * v + i] = w[i];
+    } else if (D == 1) {  // CompressMessageTo, poly.go:150-166: bit i of m <- coefficient i = 32 v + i
+      uint32_t word = 0;
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        int32_t x = (1664 << 16) - r[i];
+        x = (x >> 31) ^ x;
+        x &= 0xffff0000;
+        x -= (832 << 16);
+        word |= ((uint32_t)x >> 31) << i;
+      }
+      dst[v] = word;
+    } else {
+      compress_store_C<(D == 12 || D == 1) ? 4 : D>(r, dst + v * D);
+    }
+  } else {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + p * bytes;
+    if (OP == 1) {
+      unpack12_C(src + 48 * v, r);
+    } else if (D == 1) {  // DecompressMessage, poly.go:134-147
+      const uint32_t word = reinterpret_cast<const uint32_t*>(src)[v];
+#pragma unroll
+      for (int i = 0; i < 32; i++) r[i] = ((word >> i) & 1) ? ((Q + 1) / 2) << 16 : 0;
+    } else {
+      decompress_C<(D == 12 || D == 1) ? 4 : D>(reinterpret_cast<const uint32_t*>(src) + v * D, r);
+    }
+    gstore_C(reinterpret_cast<uint32_t*>(out) + p * (N / 2), v, r);
+  }
+}
+template <int OP>
+static int launch_codec(int d, const void* in, void* out, size_t n, cudaStream_t st) {
+  KernelScope ks(KID_KYBER_EW, st);
+  const unsigned grid = (unsigned)((n + 15) / 16);
+  switch (d) {
+    case 1: codec_kernel<OP, 1><<<grid, 128, 0, st>>>(in, out, n); break;
+    case 4: codec_kernel<OP, 4><<<grid, 128, 0, st>>>(in, out, n); break;
+    case 5: codec_kernel<OP, 5><<<grid, 128, 0, st>>>(in, out, n); break;
+    case 10: codec_kernel<OP, 10><<<grid, 128, 0, st>>>(in, out, n); break;
+    case 11: codec_kernel<OP, 11><<<grid, 128, 0, st>>>(in, out, n); break;
+    default: codec_kernel<OP, 12><<<grid, 128, 0, st>>>(in, out, n); break;
+  }
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_kyber_codec(int op, int d, const void* in, void* out, size_t n, cudaStream_t st) {
+  switch (op) {
+    case 0: return launch_codec<0>(12, in, out, n, st);
+    case 1: return launch_codec<1>(12, in, out, n, st);
+    case 2: return launch_codec<2>(d, in, out, n, st);
+    default: return launch_codec<3>(d, in, out, n, st);
+  }
+}
+int launch_derive_uniform(const uint8_t* seeds, size_t seed_stride, const uint8_t* xy, int16_t* polys, size_t n,
+                          cudaStream_t st) {
+  if (int arc = ensure_smem_attr((const void*)derive_uniform_kernel, kSampleSmem)) return arc;
+  KernelScope ks(KID_SAMPLER, st);
+  derive_uniform_kernel<<<(unsigned)((n + 127) / 128), 128, kSampleSmem, st>>>(seeds, seed_stride, xy, n, polys);
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+int launch_derive_noise(int eta, const uint8_t* seeds, size_t seed_stride, const uint8_t* nonces, int16_t* polys, size_t n,
+                        cudaStream_t st) {
+  KernelScope ks(KID_SAMPLER, st);
+  if (eta == 3)
+    derive_noise_kernel<3><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, seed_stride, nonces, n, polys);
+  else
+    derive_noise_kernel<2><<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, seed_stride, nonces, n, polys);
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// dst[i] = src for i < n: one packed key made per-op for the flows that index keys by operation
+__global__ void __launch_bounds__(256) replicate_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int words,
+                                                        size_t n) {
+  const size_t total = n * (size_t)words;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x)
+    dst[i] = __ldg(src + (i % words));
+}
+int replicate_rows(const uint8_t* src, uint8_t* dst, size_t width, size_t n, cudaStream_t st) {
+  KernelScope ks(KID_HYBRID_GLUE, st);
+  const size_t total = n * (width / 16);
+  replicate_kernel<<<(unsigned)std::min<size_t>((total + 255) / 256, 148 * 8), 256, 0, st>>>(
+      (const uint4*)src, (uint4*)dst, (int)(width / 16), n);
+  CB200_CUDA(cudaGetLastError());
+  return 0;
 }
 
 // ---- entry points for hybrid.cu (mlkem_internal.h)
@@ -1237,73 +1397,70 @@ int dev_decaps(int k, int mlkem, const uint8_t* dk, size_t dk_stride, const uint
 
 using namespace cb200;
 
+namespace {
+
+// Error text of a batch whose per-op status bytes had bits set (host-pointer calls)
+int status_error(const char* fn, size_t bit0, size_t bit1, size_t n) {
+  if (bit0) {
+    set_error("%s: %zu of %zu encapsulation keys are not canonical (kem.ErrPubKey)", fn, bit0, n);
+    return CB200_ERR_PUBKEY;
+  }
+  if (bit1) {
+    set_error("%s: H(ek) stored in %zu of %zu private keys does not match (kem.ErrPrivKey)", fn, bit1, n);
+    return CB200_ERR_PRIVKEY;
+  }
+  return 0;
+}
+
+}  // namespace
+
 extern "C" {
 
-int cb200_mlkem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n) {
+static int keygen_entry(const char* fn, int mlkem_flag, int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n) {
   int rc = require_ready();
   if (rc) return rc;
   if (k < 2 || k > 4) {
-    set_error("cb200_mlkem_keygen: k must be 2, 3 or 4 (ML-KEM-512/768/1024), got %d", k);
+    set_error("%s: k must be 2, 3 or 4 (ML-KEM-512/768/1024 or Kyber512/768/1024), got %d", fn, k);
     return CB200_ERR_ARG;
   }
   if (n == 0) return 0;
   if (!seeds || !ek || !dk) {
-    set_error("cb200_mlkem_keygen: null pointer");
+    set_error("%s: null pointer", fn);
     return CB200_ERR_ARG;
   }
   const bool dev = is_device_ptr(ek);
   if (dev != is_device_ptr(seeds) || dev != is_device_ptr(dk)) {
-    set_error("cb200_mlkem_keygen: mixed host/device pointers");
+    set_error("%s: mixed host/device pointers", fn);
     return CB200_ERR_ARG;
   }
   auto run = [&](const uint8_t* s_, uint8_t* e_, uint8_t* d_, size_t cnt, cudaStream_t st, int slot) {
-    return k == 2   ? mlkem::keygen_device<2>(s_, e_, d_, cnt, st, slot)
-           : k == 3 ? mlkem::keygen_device<3>(s_, e_, d_, cnt, st, slot)
-                    : mlkem::keygen_device<4>(s_, e_, d_, cnt, st, slot);
+    return mlkem::dev_keygen(k, mlkem_flag, s_, e_, d_, cnt, st, slot);
   };
   if (dev) {
     if (((uintptr_t)seeds | (uintptr_t)ek | (uintptr_t)dk) & 15) {
-      set_error("cb200_mlkem_keygen: device buffers must be 16-byte aligned");
+      set_error("%s: device buffers must be 16-byte aligned", fn);
       return CB200_ERR_ARG;
     }
-    return run(seeds, ek, dk, n, ctx().cur, 3);
+    DeviceCall call(ek);
+    if (call.rc) return call.rc;
+    return run(seeds, ek, dk, n, call.st, 3);
   }
   std::vector<Buf> bufs(3);
   bufs[0] = Buf{seeds, nullptr, 64, false, 0};
   bufs[1] = Buf{nullptr, ek, cb200_mlkem_public_key_size(k), false, 0};
   bufs[2] = Buf{nullptr, dk, 768u * k + 96, false, 0};
-  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+  return run_host(bufs, n, 1u << 15, 1u << 13, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return run((const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
   });
 }
 
+int cb200_mlkem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n) {
+  return keygen_entry("cb200_mlkem_keygen", 1, k, seeds, ek, dk, n);
+}
+
 // ---- round-3 Kyber512/768/1024 KEM (kem/kyber): same sizes as ML-KEM-512/768/1024
 int cb200_kyber_kem_keygen(int k, const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t n) {
-  int rc = require_ready();
-  if (rc) return rc;
-  if (k < 2 || k > 4 || !seeds || !ek || !dk) {
-    set_error("cb200_kyber_kem_keygen: bad argument");
-    return CB200_ERR_ARG;
-  }
-  if (n == 0) return 0;
-  const bool dev = is_device_ptr(ek);
-  if (dev != is_device_ptr(seeds) || dev != is_device_ptr(dk)) {
-    set_error("cb200_kyber_kem_keygen: mixed host/device pointers");
-    return CB200_ERR_ARG;
-  }
-  auto run = [&](const uint8_t* s_, uint8_t* e_, uint8_t* d_, size_t cnt, cudaStream_t st, int slot) {
-    return k == 2   ? mlkem::keygen_device<2>(s_, e_, d_, cnt, st, slot, 0)
-           : k == 3 ? mlkem::keygen_device<3>(s_, e_, d_, cnt, st, slot, 0)
-                    : mlkem::keygen_device<4>(s_, e_, d_, cnt, st, slot, 0);
-  };
-  if (dev) return run(seeds, ek, dk, n, ctx().cur, 3);
-  std::vector<Buf> bufs(3);
-  bufs[0] = Buf{seeds, nullptr, 64, false, 0};
-  bufs[1] = Buf{nullptr, ek, cb200_mlkem_public_key_size(k), false, 0};
-  bufs[2] = Buf{nullptr, dk, 768u * k + 96, false, 0};
-  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
-    return run((const uint8_t*)d[0], (uint8_t*)d[1], (uint8_t*)d[2], cnt, st, slot);
-  });
+  return keygen_entry("cb200_kyber_kem_keygen", 0, k, seeds, ek, dk, n);
 }
 
 static int kyber_kem_run(int decaps, int k, const uint8_t* key, size_t key_stride, const uint8_t* in, uint8_t* ct, uint8_t* ss,
@@ -1337,14 +1494,20 @@ static int kyber_kem_run(int decaps, int k, const uint8_t* key, size_t key_strid
       set_error("%s: device buffers and the key stride must be 16-byte aligned", fn);
       return CB200_ERR_ARG;
     }
-    return run(key, key_stride, in, ct, ss, n, ctx().cur, 3);
+    if (key_stride == 0 && decaps) {
+      set_error("%s: a shared dk needs host pointers (the device path expects one dk per op)", fn);
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(ss);
+    if (call.rc) return call.rc;
+    return run(key, key_stride, in, ct, ss, n, call.st, 3);
   }
   std::vector<Buf> bufs;
   bufs.push_back(Buf{key, nullptr, keysz, key_stride == 0, key_stride});
   bufs.push_back(Buf{in, nullptr, decaps ? ctsz : (size_t)32, false, 0});
   bufs.push_back(Buf{nullptr, ss, 32, false, 0});
   if (!decaps) bufs.push_back(Buf{nullptr, ct, ctsz, false, 0});
-  return run_staged(bufs, n, 1u << 15, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+  return run_host(bufs, n, 1u << 15, 1u << 13, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return run((const uint8_t*)d[0], key_stride == 0 ? 0 : keysz, (const uint8_t*)d[1], decaps ? nullptr : (uint8_t*)d[3],
                (uint8_t*)d[2], cnt, st, slot);
   });
@@ -1379,11 +1542,7 @@ int cb200_mlkem_decaps(int k, const uint8_t* dk, size_t dk_stride, const uint8_t
     return CB200_ERR_ARG;
   }
   auto run = [&](const uint8_t* d_dk, size_t stride, const uint8_t* d_ct, uint8_t* d_ss, uint8_t* d_st, size_t cnt,
-                 cudaStream_t st, int slot) {
-    return k == 2   ? mlkem::decaps_device<2>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot)
-           : k == 3 ? mlkem::decaps_device<3>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot)
-                    : mlkem::decaps_device<4>(d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot);
-  };
+                 cudaStream_t st, int slot) { return mlkem::dev_decaps(k, 1, d_dk, stride, d_ct, d_ss, d_st, cnt, st, slot); };
   if (dev) {
     if (((uintptr_t)dk | (uintptr_t)ct | (uintptr_t)ss | dk_stride) & 15) {
       set_error("cb200_mlkem_decaps: device buffers and dk_stride must be 16-byte aligned");
@@ -1393,56 +1552,31 @@ int cb200_mlkem_decaps(int k, const uint8_t* dk, size_t dk_stride, const uint8_t
       set_error("cb200_mlkem_decaps: a shared dk needs host pointers (device path expects one dk per op)");
       return CB200_ERR_ARG;
     }
-    return run(dk, dk_stride, ct, ss, status, n, ctx().cur, 3);
+    DeviceCall call(ss);
+    if (call.rc) return call.rc;
+    return run(dk, dk_stride, ct, ss, status, n, call.st, 3);
   }
-  uint8_t* user_status = status;
-  void* pin = nullptr;
-  rc = ensure_pinned(n, &pin);
-  if (rc) return rc;
-  status = (uint8_t*)pin;
-  // a shared dk is replicated per op inside each staged chunk (the decapsulation pipeline is per-op)
-  std::vector<uint8_t> rep;
-  const uint8_t* dk_src = dk;
-  size_t host_stride = dk_stride;
-  const size_t chunk = 1u << 15;
-  if (dk_stride == 0) {
-    const size_t m = n < chunk ? n : chunk;
-    rep.resize(m * dksz);
-    for (size_t i = 0; i < m; i++) memcpy(rep.data() + i * dksz, dk, dksz);
-    dk_src = rep.data();
-  }
-  std::vector<Buf> bufs(4);
-  bufs[0] = Buf{dk_src, nullptr, dksz, false, dk_stride == 0 ? dksz : host_stride};
-  bufs[1] = Buf{ct, nullptr, ctsz, false, 0};
-  bufs[2] = Buf{nullptr, ss, 32, false, 0};
-  bufs[3] = Buf{nullptr, status, 1, false, 0};
-  if (dk_stride == 0) {
-    // every chunk reuses the same replicated block: run chunk by chunk with first = 0 for the dk buffer
-    for (size_t first = 0; first < n && rc == 0; first += chunk) {
-      const size_t cnt = n - first < chunk ? n - first : chunk;
-      std::vector<Buf> b2(4);
-      b2[0] = Buf{dk_src, nullptr, dksz, false, 0};
-      b2[1] = Buf{ct + first * ctsz, nullptr, ctsz, false, 0};
-      b2[2] = Buf{nullptr, ss + first * 32, 32, false, 0};
-      b2[3] = Buf{nullptr, status + first, 1, false, 0};
-      rc = run_staged(b2, cnt, cnt, [&](void** d, size_t c2, size_t, cudaStream_t st, int slot) {
-        return run((const uint8_t*)d[0], dksz, (const uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], c2, st, slot);
-      });
+  // a shared dk is replicated per op on the device inside each staged chunk (the decapsulation pipeline is per-op)
+  HostCall hc;
+  hc.bufs = {Buf{dk, nullptr, dksz, dk_stride == 0, dk_stride}, Buf{ct, nullptr, ctsz, false, 0},
+             Buf{nullptr, ss, 32, false, 0}, Buf{nullptr, nullptr, 1, false, 0}};
+  if (dk_stride == 0) hc.bufs.push_back(Buf{nullptr, nullptr, dksz, false, 0});  // per-op replicas (device only)
+  hc.chunk = 1u << 15;
+  hc.min_shard = 1u << 13;
+  hc.status_buf = 3;
+  hc.user_status = status;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) -> int {
+    const uint8_t* keys = (const uint8_t*)d[0];
+    if (dk_stride == 0) {
+      int r = mlkem::replicate_rows((const uint8_t*)d[0], (uint8_t*)d[4], dksz, cnt, st);
+      if (r) return r;
+      keys = (const uint8_t*)d[4];
     }
-  } else {
-    rc = run_staged(bufs, n, chunk, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
-      return run((const uint8_t*)d[0], dksz, (const uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], cnt, st, slot);
-    });
-  }
+    return run(keys, dksz, (const uint8_t*)d[1], (uint8_t*)d[2], (uint8_t*)d[3], cnt, st, slot);
+  };
+  rc = hc.run(n);
   if (rc) return rc;
-  size_t nbad = 0;
-  for (size_t i = 0; i < n; i++) nbad += status[i] != 0;
-  if (user_status) memcpy(user_status, status, n);
-  if (nbad) {
-    set_error("cb200_mlkem_decaps: H(ek) stored in %zu of %zu private keys does not match (kem.ErrPrivKey)", nbad, n);
-    return CB200_ERR_PRIVKEY;
-  }
-  return 0;
+  return status_error("cb200_mlkem_decaps", 0, hc.bit1, n);
 }
 
 size_t cb200_mlkem_public_key_size(int k) { return (k >= 2 && k <= 4) ? 384u * k + 32 : 0; }
@@ -1474,34 +1608,134 @@ int cb200_mlkem_encaps(int k, const uint8_t* ek, size_t ek_stride, const uint8_t
       return CB200_ERR_ARG;
     }
     // status is needed to report kem.ErrPubKey; with device pointers the caller reads it asynchronously
-    return mlkem::encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, ctx().cur, 3);
+    DeviceCall call(ct);
+    if (call.rc) return call.rc;
+    return mlkem::encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, call.st, 3);
   }
-  // host pointers: stage chunks through HBM on three streams (H2D | kernels | D2H overlap)
-  // per-op status always comes back (it carries kem.ErrPubKey); pinned so the D2H copy stays asynchronous
-  uint8_t* user_status = status;
-  void* pin = nullptr;
-  rc = ensure_pinned(n, &pin);
-  if (rc) return rc;
-  status = (uint8_t*)pin;
-  std::vector<Buf> bufs(5);
-  bufs[0] = Buf{ek, nullptr, eksz, ek_stride == 0, ek_stride};
-  bufs[1] = Buf{seeds, nullptr, 32, false, 0};
-  bufs[2] = Buf{nullptr, ct, ctsz, false, 0};
-  bufs[3] = Buf{nullptr, ss, 32, false, 0};
-  bufs[4] = Buf{nullptr, status, 1, false, 0};
-  rc = run_staged(bufs, n, 1u << 16, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
+  // host pointers: one contiguous index range per GPU, each staged through HBM in chunks on three streams
+  // (H2D | kernels | D2H overlap); the per-op status always comes back (it carries kem.ErrPubKey)
+  HostCall hc;
+  hc.bufs = {Buf{ek, nullptr, eksz, ek_stride == 0, ek_stride}, Buf{seeds, nullptr, 32, false, 0},
+             Buf{nullptr, ct, ctsz, false, 0}, Buf{nullptr, ss, 32, false, 0}, Buf{nullptr, nullptr, 1, false, 0}};
+  hc.chunk = 1u << 16;
+  hc.min_shard = 1u << 13;
+  hc.status_buf = 4;
+  hc.user_status = status;
+  hc.body = [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
     return mlkem::encaps_any(k, (const uint8_t*)d[0], ek_stride == 0 ? 0 : eksz, (const uint8_t*)d[1],
                              (uint8_t*)d[2], (uint8_t*)d[3], (uint8_t*)d[4], cnt, st, slot);
-  });
+  };
+  rc = hc.run(n);
   if (rc) return rc;
-  size_t nbad = 0;
-  for (size_t i = 0; i < n; i++) nbad += status[i] != 0;
-  if (user_status) memcpy(user_status, status, n);
-  if (nbad) {
-    set_error("cb200_mlkem_encaps: %zu of %zu encapsulation keys are not canonical (kem.ErrPubKey)", nbad, n);
-    return CB200_ERR_PUBKEY;
+  return status_error("cb200_mlkem_encaps", hc.bit0, 0, n);
+}
+
+int cb200_kyber_derive_uniform(int16_t* polys, const uint8_t* seeds, size_t seed_stride, const uint8_t* xy, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (n == 0) return 0;
+  if (!polys || !seeds || !xy || (seed_stride != 0 && seed_stride < 32)) {
+    set_error("cb200_kyber_derive_uniform: bad argument");
+    return CB200_ERR_ARG;
   }
-  return 0;
+  const bool dev = is_device_ptr(polys);
+  if (dev != is_device_ptr(seeds) || dev != is_device_ptr(xy)) {
+    set_error("cb200_kyber_derive_uniform: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  if (dev) {
+    if ((uintptr_t)polys & 15) {
+      set_error("cb200_kyber_derive_uniform: device polynomials must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(polys);
+    if (call.rc) return call.rc;
+    return mlkem::launch_derive_uniform(seeds, seed_stride, xy, polys, n, call.st);
+  }
+  std::vector<Buf> bufs = {Buf{seeds, nullptr, 32, seed_stride == 0, seed_stride}, Buf{xy, nullptr, 2, false, 0},
+                           Buf{nullptr, polys, 512, false, 0}};
+  return run_host(bufs, n, 1u << 16, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+    return mlkem::launch_derive_uniform((const uint8_t*)d[0], seed_stride == 0 ? 0 : 32, (const uint8_t*)d[1], (int16_t*)d[2],
+                                        cnt, st);
+  });
+}
+
+int cb200_kyber_derive_noise(int16_t* polys, int eta, const uint8_t* seeds, size_t seed_stride, const uint8_t* nonces,
+                             size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (eta != 2 && eta != 3) {
+    set_error("cb200_kyber_derive_noise: eta must be 2 or 3, got %d", eta);  // sample.go:19-28 panics likewise
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  if (!polys || !seeds || !nonces || (seed_stride != 0 && seed_stride < 32)) {
+    set_error("cb200_kyber_derive_noise: bad argument");
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(polys);
+  if (dev != is_device_ptr(seeds) || dev != is_device_ptr(nonces)) {
+    set_error("cb200_kyber_derive_noise: mixed host/device pointers");
+    return CB200_ERR_ARG;
+  }
+  if (dev) {
+    if ((uintptr_t)polys & 15) {
+      set_error("cb200_kyber_derive_noise: device polynomials must be 16-byte aligned");
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(polys);
+    if (call.rc) return call.rc;
+    return mlkem::launch_derive_noise(eta, seeds, seed_stride, nonces, polys, n, call.st);
+  }
+  std::vector<Buf> bufs = {Buf{seeds, nullptr, 32, seed_stride == 0, seed_stride}, Buf{nonces, nullptr, 1, false, 0},
+                           Buf{nullptr, polys, 512, false, 0}};
+  return run_host(bufs, n, 1u << 16, 1u << 14, [&](void** d, size_t cnt, size_t, cudaStream_t st, int) {
+    return mlkem::launch_derive_noise(eta, (const uint8_t*)d[0], seed_stride == 0 ? 0 : 32, (const uint8_t*)d[1],
+                                      (int16_t*)d[2], cnt, st);
+  });
+}
+
+// op 0 pack, 1 unpack, 2 compress, 3 decompress; polys is the int16 side, bytes the packed side
+static int codec_entry(const char* fn, int op, int d, const void* in, void* out, size_t n) {
+  int rc = require_ready();
+  if (rc) return rc;
+  if (op >= 2 && d != 1 && d != 4 && d != 5 && d != 10 && d != 11) {
+    set_error("%s: d must be 1, 4, 5, 10 or 11, got %d", fn, d);  // poly.go:176,258 panic on other sizes
+    return CB200_ERR_ARG;
+  }
+  if (n == 0) return 0;
+  if (!in || !out) {
+    set_error("%s: null pointer", fn);
+    return CB200_ERR_ARG;
+  }
+  const bool dev = is_device_ptr(out);
+  if (dev != is_device_ptr(in)) {
+    set_error("%s: mixed host/device pointers", fn);
+    return CB200_ERR_ARG;
+  }
+  const size_t bytes = op < 2 ? 384 : 32 * (size_t)d;
+  const size_t in_unit = (op == 0 || op == 2) ? 512 : bytes, out_unit = (op == 0 || op == 2) ? bytes : 512;
+  if (dev) {
+    if (((uintptr_t)in | (uintptr_t)out) & 15) {
+      set_error("%s: device buffers must be 16-byte aligned", fn);
+      return CB200_ERR_ARG;
+    }
+    DeviceCall call(out);
+    if (call.rc) return call.rc;
+    return mlkem::launch_kyber_codec(op, d, in, out, n, call.st);
+  }
+  std::vector<Buf> bufs = {Buf{in, nullptr, in_unit, false, 0}, Buf{nullptr, out, out_unit, false, 0}};
+  return run_host(bufs, n, 1u << 17, 1u << 15, [&](void** dv, size_t cnt, size_t, cudaStream_t st, int) {
+    return mlkem::launch_kyber_codec(op, d, dv[0], dv[1], cnt, st);
+  });
+}
+int cb200_kyber_pack(uint8_t* out, const int16_t* polys, size_t n) { return codec_entry("cb200_kyber_pack", 0, 12, polys, out, n); }
+int cb200_kyber_unpack(int16_t* polys, const uint8_t* in, size_t n) { return codec_entry("cb200_kyber_unpack", 1, 12, in, polys, n); }
+int cb200_kyber_compress(uint8_t* out, const int16_t* polys, int d, size_t n) {
+  return codec_entry("cb200_kyber_compress", 2, d, polys, out, n);
+}
+int cb200_kyber_decompress(int16_t* polys, const uint8_t* in, int d, size_t n) {
+  return codec_entry("cb200_kyber_decompress", 3, d, in, polys, n);
 }
 
 }  // extern "C"

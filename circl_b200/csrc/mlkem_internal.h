@@ -18,5 +18,8 @@ int dev_encaps(int k, int mlkem, const uint8_t* ek, size_t ek_stride, const uint
 int dev_decaps(int k, int mlkem, const uint8_t* dk, size_t dk_stride, const uint8_t* ct, uint8_t* ss, uint8_t* status, size_t n,
                cudaStream_t st, int slot);
 
+// dst[i*width .. ) = src[0 .. width) for i < n (width a multiple of 16, 16-byte aligned buffers)
+int replicate_rows(const uint8_t* src, uint8_t* dst, size_t width, size_t n, cudaStream_t st);
+
 }  // namespace mlkem
 }  // namespace cb200

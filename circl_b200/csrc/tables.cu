@@ -6,14 +6,12 @@
 #include <vector>
 
 namespace cb200 {
-int init_extra_tables() {
-  Ctx& c = ctx();
+int init_extra_tables(Dev& c) {  // device c.device is current
   uint32_t tw[512];
   dil_fill_twiddles(tw);
   if (c.dil_tw) cudaFree(c.dil_tw);
   CB200_CUDA(cudaMalloc(&c.dil_tw, sizeof tw));
   CB200_CUDA(cudaMemcpy(c.dil_tw, tw, sizeof tw, cudaMemcpyHostToDevice));
-  if (!c.small) CB200_CUDA(cudaMalloc(&c.small, 256));
   // fixed-base table of X25519 KeyGen: 256 affine multiples of the base point, computed here with the same limb
   // code the kernels use (x25519.cuh is host/device code)
   std::vector<int32_t> xt(x25519::kBaseTableWords);

@@ -122,3 +122,77 @@ def exceeds(p, bound: int):
     flags = np.empty((n,), dtype=np.uint8)
     check(lib().cb200_dil_exceeds(_ptr(p), bound, flags.ctypes.data, n))
     return flags
+
+
+# ---- samplers and packers (sign/mldsa/mldsa{44,65,87}/internal/sample.go, sign/internal/dilithium/generic.go) ----
+def _raw(x) -> int:
+    if _is_torch(x):
+        assert x.is_cuda and x.is_contiguous()
+        return x.data_ptr()
+    assert isinstance(x, np.ndarray) and x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data
+
+
+def _new(ref, shape, dtype):
+    if _is_torch(ref):
+        import torch
+        return torch.empty(shape, dtype={np.uint32: torch.int32, np.uint8: torch.uint8}[dtype], device=ref.device)
+    return np.empty(shape, dtype=dtype)
+
+
+def derive_uniform(seeds, nonces):
+    """PolyDeriveUniform: seeds (n, 32) uint8 or (32,) shared, nonces (n,) uint16 -> (n, 256) uint32."""
+    n = _numel(nonces)
+    shared = _numel(seeds) == 32
+    out = _new(nonces, (n, N), np.uint32)
+    _sync_stream(nonces)
+    check(lib().cb200_dil_derive_uniform(_raw(out), _raw(seeds), 0 if shared else 32, _raw(nonces), n))
+    return out
+
+
+def derive_leq_eta(mode: int, seeds, nonces):
+    """PolyDeriveUniformLeqEta of ML-DSA-`mode`: seeds (n, 64) or (64,) shared, nonces (n,) uint16."""
+    n = _numel(nonces)
+    shared = _numel(seeds) == 64
+    out = _new(nonces, (n, N), np.uint32)
+    _sync_stream(nonces)
+    check(lib().cb200_dil_derive_leq_eta(mode, _raw(out), _raw(seeds), 0 if shared else 64, _raw(nonces), n))
+    return out
+
+
+def derive_le_gamma1(mode: int, seeds, nonces):
+    """PolyDeriveUniformLeGamma1 of ML-DSA-`mode`: seeds (n, 64) or (64,) shared, nonces (n,) uint16."""
+    n = _numel(nonces)
+    shared = _numel(seeds) == 64
+    out = _new(nonces, (n, N), np.uint32)
+    _sync_stream(nonces)
+    check(lib().cb200_dil_derive_le_gamma1(mode, _raw(out), _raw(seeds), 0 if shared else 64, _raw(nonces), n))
+    return out
+
+
+def derive_ball(mode: int, seeds):
+    """PolyDeriveUniformBall of ML-DSA-`mode`: seeds (n, 32 | 48 | 64) uint8 (c~) -> (n, 256) uint32."""
+    ln = {44: 32, 65: 48, 87: 64}[mode]
+    n = _numel(seeds) // ln
+    out = _new(seeds, (n, N), np.uint32)
+    _sync_stream(seeds)
+    check(lib().cb200_dil_derive_ball(mode, _raw(out), _raw(seeds), ln, n))
+    return out
+
+
+def power2round(p):
+    """(*Poly).Power2Round: normalised (n, 256) -> (a0 + Q, a1)."""
+    n = _numel(p) // N
+    a0, a1 = _like(p), _like(p)
+    _sync_stream(p)
+    check(lib().cb200_dil_power2round(_ptr(a0), _ptr(a1), _ptr(p), n))
+    return a0, a1
+
+
+def pack_le16(p):
+    """(*Poly).PackLe16: (n, 256) with coefficients < 16 -> (n, 128) uint8."""
+    n = _numel(p) // N
+    out = _new(p, (n, 128), np.uint8)
+    _sync_stream(p)
+    check(lib().cb200_dil_pack_le16(_raw(out), _ptr(p), n))
+    return out

@@ -113,3 +113,75 @@ def normalize(p, out=None):
 
 def to_mont(p, out=None):
     return _unary(OP_TOMONT, p, out)
+
+
+# ---- samplers and serialisation (pke/kyber/internal/common/sample.go, poly.go) ----
+def _u8(x) -> int:
+    if _is_torch(x):
+        assert x.is_cuda and x.is_contiguous() and x.element_size() == 1
+        return x.data_ptr()
+    assert isinstance(x, np.ndarray) and x.dtype == np.uint8 and x.flags["C_CONTIGUOUS"]
+    return x.ctypes.data
+
+
+def _out(ref, shape, dtype):
+    if _is_torch(ref):
+        import torch
+        return torch.empty(shape, dtype={np.int16: torch.int16, np.uint8: torch.uint8}[dtype], device=ref.device)
+    return np.empty(shape, dtype=dtype)
+
+
+def derive_uniform(seeds, xy):
+    """(*Poly).DeriveUniform for n (seed, x, y): seeds (n, 32) or (32,) shared, xy (n, 2) uint8 -> (n, 256) int16."""
+    n = _numel(xy) // 2
+    shared = _numel(seeds) == 32
+    out = _out(xy, (n, N), np.int16)
+    _sync_stream(xy)
+    check(lib().cb200_kyber_derive_uniform(_ptr(out), _u8(seeds), 0 if shared else 32, _u8(xy), n))
+    return out
+
+
+def derive_noise(seeds, nonces, eta: int):
+    """(*Poly).DeriveNoise(eta): seeds (n, 32) or (32,) shared, nonces (n,) uint8 -> (n, 256) int16."""
+    n = _numel(nonces)
+    shared = _numel(seeds) == 32
+    out = _out(nonces, (n, N), np.int16)
+    _sync_stream(nonces)
+    check(lib().cb200_kyber_derive_noise(_ptr(out), eta, _u8(seeds), 0 if shared else 32, _u8(nonces), n))
+    return out
+
+
+def pack(p):
+    """(*Poly).Pack: (n, 256) normalised int16 -> (n, 384) uint8."""
+    n = _numel(p) // N
+    out = _out(p, (n, 384), np.uint8)
+    _sync_stream(p)
+    check(lib().cb200_kyber_pack(_u8(out), _ptr(p), n))
+    return out
+
+
+def unpack(buf):
+    """(*Poly).Unpack: (n, 384) uint8 -> (n, 256) int16."""
+    n = _numel(buf) // 384
+    out = _out(buf, (n, N), np.int16)
+    _sync_stream(buf)
+    check(lib().cb200_kyber_unpack(_ptr(out), _u8(buf), n))
+    return out
+
+
+def compress(p, d: int):
+    """(*Poly).CompressTo (d in 4, 5, 10, 11) / CompressMessageTo (d = 1): (n, 256) normalised -> (n, 32 d) uint8."""
+    n = _numel(p) // N
+    out = _out(p, (n, 32 * d), np.uint8)
+    _sync_stream(p)
+    check(lib().cb200_kyber_compress(_u8(out), _ptr(p), d, n))
+    return out
+
+
+def decompress(buf, d: int):
+    """(*Poly).Decompress / DecompressMessage: (n, 32 d) uint8 -> (n, 256) int16."""
+    n = _numel(buf) // (32 * d)
+    out = _out(buf, (n, N), np.int16)
+    _sync_stream(buf)
+    check(lib().cb200_kyber_decompress(_ptr(out), _u8(buf), d, n))
+    return out

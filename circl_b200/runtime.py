@@ -1,4 +1,4 @@
-"""Process-level runtime helpers (one process per GPU)."""
+"""Process-level runtime helpers: one process per GPU (init) or one process driving several (init_devices)."""
 from __future__ import annotations
 
 import os
@@ -16,6 +16,25 @@ def init(device: int | None = None) -> int:
         device = int(os.environ.get("LOCAL_RANK", "0"))
     check(lib().cb200_init(device))
     return device
+
+
+def init_devices(ndev: int = 0) -> int:
+    """One process drives GPUs 0..ndev-1 (0: all visible); host-pointer batches are sharded by index inside the library."""
+    check(lib().cb200_init_devices(ndev))
+    return int(lib().cb200_active_devices())
+
+
+def active_devices() -> int:
+    return int(lib().cb200_active_devices())
+
+
+def bind_thread_to_device(device: int) -> int:
+    """Pin the calling thread to the CPUs next to GPU `device` (NUMA-local pinned buffers for the host path)."""
+    return int(lib().cb200_bind_thread_to_device(device))
+
+
+def release_stream(cuda_stream_handle: int | None) -> None:
+    check(lib().cb200_release_stream(cuda_stream_handle))
 
 
 def shutdown() -> None:

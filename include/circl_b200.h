@@ -33,17 +33,34 @@ extern "C" {
 /* <= -100: CUDA runtime error (-100 - cudaError_t) */
 
 /* ---- lifetime ---- */
-int cb200_init(int device);            /* binds the calling process to one GPU (one process per GPU) */
+/* cb200_init_devices(ndev): one process drives GPUs 0..ndev-1 (ndev <= 0: every visible GPU).  Host-pointer batch
+ * calls are then cut into one contiguous index range per GPU inside the library and the results land in the
+ * caller's buffers in index order -- a kem.Scheme / sign.Scheme caller never sees devices (north_star: "batches
+ * shard by index across the 8 GPUs").  cb200_init(device): exactly one GPU (the one-process-per-GPU launch).
+ * Calling either again with another set re-initialises. */
+int cb200_init(int device);
+int cb200_init_devices(int ndev);
+int cb200_active_devices(void);        /* GPUs this process was initialised on (0 = not initialised) */
 void cb200_shutdown(void);
 int cb200_device_count(void);
-const char *cb200_last_error(void);
+const char *cb200_last_error(void);    /* message of the last failing call on this thread */
 const char *cb200_version(void);
-/* Use an existing CUDA stream (cudaStream_t cast to void*) for all subsequent
- * work on device pointers; NULL (the initial state) is CUDA's legacy default
- * stream.  Calls with device pointers are asynchronous on that stream; calls
- * with host pointers return after the results are in the caller's buffer. */
+/* Threading (kem/kem.go:33-82 and sign/sign.go:48-94 are goroutine-safe; so is this):
+ *  - host-pointer calls may be issued from any number of threads; each GPU runs the ranges it is given one after
+ *    the other on its own worker thread, small batches rotate over the GPUs;
+ *  - device-pointer calls run on the GPU that owns the buffers, asynchronously on the CUDA stream (cudaStream_t cast
+ *    to void*) the CALLING THREAD named with cb200_set_stream -- the setting is per thread; NULL, the initial state,
+ *    is CUDA's legacy default stream.  Scratch memory is kept per (GPU, stream): calls on different streams never
+ *    share it, calls on one stream from several threads are serialised in stream order.  cb200_release_stream frees
+ *    the scratch of a stream that is about to be destroyed.  A cgo caller wraps set_stream + call in
+ *    runtime.LockOSThread (go/cb200). */
 int cb200_set_stream(void *cuda_stream);
-int cb200_synchronize(void);
+int cb200_release_stream(void *cuda_stream);
+int cb200_synchronize(void);           /* waits for this thread's stream */
+/* Pins the calling thread to the CPUs next to GPU `device` (/sys/bus/pci/devices/<id>/local_cpulist); memory it
+ * allocates and first touches afterwards is local to that GPU's NUMA node.  Returns the number of CPUs, 0 if the
+ * topology is unknown (affinity unchanged).  The library's own worker threads do this themselves. */
+int cb200_bind_thread_to_device(int device);
 /* Pinned host memory for large batches handed to Go via unsafe.Slice. */
 void *cb200_host_alloc(size_t bytes);
 void cb200_host_free(void *p);
@@ -91,6 +108,51 @@ int cb200_dil_dot(uint32_t *out, const uint32_t *a, const uint32_t *b, int k, si
 int cb200_dil_poly_op(int op, uint32_t *out, const uint32_t *a, const uint32_t *b, size_t n);
 /* (*Poly).Exceeds        poly.go:51-71 (stubs_amd64.go:32 exceedsAVX2): flags[i] = 1 iff poly i exceeds bound */
 int cb200_dil_exceeds(const uint32_t *polys, uint32_t bound, uint8_t *flags, size_t n);
+
+/* ---- Keccak (simd/keccakf1600, internal/sha3): the on-device sampler's permutation, batched ---- */
+/* StateX4.Permute  simd/keccakf1600/f1600x.go:115-121 / KeccakF1600  internal/sha3/keccakf.go:12
+ * states: n x 25 little-endian 64-bit lanes (200 bytes per state, lane x+5y at index x+5y), permuted in place;
+ * turbo != 0: the 12-round TurboSHAKE variant (keccakf.go:12 `turbo`). */
+int cb200_keccak_f1600(uint64_t *states, size_t n, int turbo);
+/* One-shot sponges over n messages of equal length (internal/sha3/hashes.go:21,35; shake.go:56,74):
+ * bits = 128 / 256 selects SHAKE128 / SHAKE256 with `outlen` output bytes, bits = -256 / -512 selects SHA3-256 /
+ * SHA3-512 (outlen must be 32 / 64).  Message i = in + i*in_stride (in_stride 0: one message), output i at
+ * out + i*outlen. */
+int cb200_sha3(int bits, const uint8_t *in, size_t in_stride, size_t inlen, uint8_t *out, size_t outlen, size_t n);
+
+/* ---- samplers of the Kyber ring (pke/kyber/internal/common/sample.go) ---- */
+/* (*Poly).DeriveUniform  sample.go:192-236: polys[i] = 12-bit rejection sampling of SHAKE128(seed_i || x_i || y_i);
+ * seeds: 32 bytes each at seeds + i*seed_stride (0: one seed); xy: n x 2 bytes (x, y). */
+int cb200_kyber_derive_uniform(int16_t *polys, const uint8_t *seeds, size_t seed_stride, const uint8_t *xy, size_t n);
+/* (*Poly).DeriveNoise(2|3)  sample.go:31-95: polys[i] = CBD_eta(SHAKE256(seed_i || nonce_i)); seeds 32 bytes each. */
+int cb200_kyber_derive_noise(int16_t *polys, int eta, const uint8_t *seeds, size_t seed_stride, const uint8_t *nonces,
+                             size_t n);
+/* ---- serialisation of the Kyber ring (pke/kyber/internal/common/poly.go) ---- */
+/* Pack / Unpack  poly.go:106-129: 12 bits per coefficient, 384 bytes per polynomial (input normalised) */
+int cb200_kyber_pack(uint8_t *out, const int16_t *polys, size_t n);
+int cb200_kyber_unpack(int16_t *polys, const uint8_t *in, size_t n);
+/* CompressTo / Decompress  poly.go:170-328 for d in {4, 5, 10, 11} (32 d bytes per polynomial), and
+ * CompressMessageTo / DecompressMessage  poly.go:134-166 for d = 1 (32 bytes); compress expects normalised input */
+int cb200_kyber_compress(uint8_t *out, const int16_t *polys, int d, size_t n);
+int cb200_kyber_decompress(int16_t *polys, const uint8_t *in, int d, size_t n);
+
+/* ---- samplers and packers of the Dilithium ring; mode = 44, 65 or 87 picks the per-mode package
+ *      (sign/mldsa/mldsa{44,65,87}/internal/sample.go, sign/internal/dilithium/generic.go) ---- */
+/* PolyDeriveUniform  sample.go:92-123: 23-bit rejection sampling of SHAKE128(seed_i || le16(nonce_i)); seeds 32 bytes */
+int cb200_dil_derive_uniform(uint32_t *polys, const uint8_t *seeds, size_t seed_stride, const uint16_t *nonces, size_t n);
+/* PolyDeriveUniformLeqEta  sample.go:129-181: coefficients Q + eta - t, t from nibbles of SHAKE256(seed_i(64) || nonce) */
+int cb200_dil_derive_leq_eta(int mode, uint32_t *polys, const uint8_t *seeds, size_t seed_stride, const uint16_t *nonces,
+                             size_t n);
+/* PolyDeriveUniformLeGamma1  sample.go:197-209: gamma1 - (18|20-bit fields of SHAKE256(seed_i(64) || nonce)), mod q */
+int cb200_dil_derive_le_gamma1(int mode, uint32_t *polys, const uint8_t *seeds, size_t seed_stride,
+                               const uint16_t *nonces, size_t n);
+/* PolyDeriveUniformBall  sample.go:299-339: tau coefficients +-1 from SHAKE256(seed_i); seeds are c~ (32/48/64 bytes
+ * for mode 44/65/87) at seeds + i*seed_stride */
+int cb200_dil_derive_ball(int mode, uint32_t *polys, const uint8_t *seeds, size_t seed_stride, size_t n);
+/* (*Poly).Power2Round  generic.go:85 (poly.go:77-84): a0plusq[i] = Q + a0, a1[i] for normalised a */
+int cb200_dil_power2round(uint32_t *a0plusq, uint32_t *a1, const uint32_t *a, size_t n);
+/* (*Poly).PackLe16  generic.go:27 (pack.go:102-108): 4 bits per coefficient, 128 bytes per polynomial */
+int cb200_dil_pack_le16(uint8_t *out, const uint32_t *polys, size_t n);
 
 /* ---- ML-KEM ---- */
 /* scheme.UnmarshalBinaryPublicKey + EncapsulateDeterministically

@@ -87,6 +87,12 @@ def keccak_f1600(state25) -> list[int]:
     return list(a)
 
 
+def keccak_f1600_turbo(state25) -> list[int]:
+    a = (C.c_uint64 * 25)(*state25)
+    lib().orc_keccak_f1600_turbo(a)
+    return list(a)
+
+
 def _hash(fn, outlen: int, data: bytes) -> bytes:
     out = (C.c_uint8 * outlen)()
     if fn in ("orc_sha3_256", "orc_sha3_512"):
@@ -321,6 +327,37 @@ def dil_derive_legamma1(seed64, nonce):
 
 def dil_derive_ball(seed48):
     return _dil_sample("orc_dil_derive_ball", seed48)
+
+
+def mldsa_derive_leqeta(mode: int, seed64, nonce):
+    p = np.empty(256, dtype=np.uint32)
+    lib().orc_mldsa_derive_leqeta(C.c_int(mode), _ptr(p), _buf(seed64), C.c_uint16(nonce))
+    return p
+
+
+def mldsa_derive_legamma1(mode: int, seed64, nonce):
+    p = np.empty(256, dtype=np.uint32)
+    lib().orc_mldsa_derive_legamma1(C.c_int(mode), _ptr(p), _buf(seed64), C.c_uint16(nonce))
+    return p
+
+
+def mldsa_derive_ball(mode: int, ctilde):
+    p = np.empty(256, dtype=np.uint32)
+    lib().orc_mldsa_derive_ball(C.c_int(mode), _ptr(p), _buf(ctilde))
+    return p
+
+
+def dil_power2round(p):
+    p = np.ascontiguousarray(p, dtype=np.uint32)
+    a0, a1 = np.empty(256, dtype=np.uint32), np.empty(256, dtype=np.uint32)
+    lib().orc_dil_power2round(_ptr(p), _ptr(a0), _ptr(a1))
+    return a0, a1
+
+
+def dil_pack_le16(p) -> bytes:
+    out = (C.c_uint8 * 128)()
+    lib().orc_dil_pack_le16(out, _ptr(np.ascontiguousarray(p, dtype=np.uint32)))
+    return bytes(out)
 
 
 def mldsa65_keygen(seed32: bytes):

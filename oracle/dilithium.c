@@ -345,6 +345,15 @@ static void derive_ball(const dparams *P, uint32_t p[N], const uint8_t *seed) { 
 void orc_dil_derive_leqeta(uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { derive_leqeta(mode_of(65), p, seed, nonce); }
 void orc_dil_derive_legamma1(uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { derive_legamma1(mode_of(65), p, seed, nonce); }
 void orc_dil_derive_ball(uint32_t p[N], const uint8_t seed[48]) { derive_ball(mode_of(65), p, seed); }
+void orc_mldsa_derive_leqeta(int mode, uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { derive_leqeta(mode_of(mode), p, seed, nonce); }
+void orc_mldsa_derive_legamma1(int mode, uint32_t p[N], const uint8_t seed[64], uint16_t nonce) { derive_legamma1(mode_of(mode), p, seed, nonce); }
+void orc_mldsa_derive_ball(int mode, uint32_t p[N], const uint8_t *seed) { derive_ball(mode_of(mode), p, seed); }
+void orc_dil_power2round(const uint32_t *p, uint32_t *p0plusq, uint32_t *p1) { /* poly.go:77-84 */
+  for (int i = 0; i < N; i++) power2round(p[i], &p0plusq[i], &p1[i]);
+}
+void orc_dil_pack_le16(uint8_t buf[128], const uint32_t *p) { /* pack.go:102-108 */
+  for (int i = 0; i < 128; i++) buf[i] = (uint8_t)((uint8_t)p[2 * i] | (uint8_t)(p[2 * i + 1] << 4));
+}
 
 /* ---- rounding.go ---- */
 static void decompose(const dparams *P, uint32_t a, uint32_t *a0plusq, uint32_t *a1o) { /* rounding.go:13-43 */

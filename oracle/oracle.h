@@ -25,6 +25,7 @@ extern "C" {
 
 /* ---------------- Keccak (internal/sha3) ---------------- */
 void orc_keccak_f1600(uint64_t a[25]);                       /* keccakf.go:12 */
+void orc_keccak_f1600_turbo(uint64_t a[25]);                 /* keccakf.go:12, turbo = true: rounds 12..23 */
 typedef struct {
   uint64_t a[25];
   unsigned rate, pos;
@@ -119,6 +120,12 @@ void orc_dil_derive_uniform(uint32_t p[256], const uint8_t seed[32], uint16_t no
 void orc_dil_derive_leqeta(uint32_t p[256], const uint8_t seed[64], uint16_t nonce);    /* sample.go:129-181 */
 void orc_dil_derive_legamma1(uint32_t p[256], const uint8_t seed[64], uint16_t nonce);  /* sample.go:197-209 */
 void orc_dil_derive_ball(uint32_t p[256], const uint8_t seed[48]);                      /* sample.go:299-339 */
+/* per-mode samplers (mode = 44, 65, 87) and the remaining leaf methods of generic.go */
+void orc_mldsa_derive_leqeta(int mode, uint32_t p[256], const uint8_t seed[64], uint16_t nonce);
+void orc_mldsa_derive_legamma1(int mode, uint32_t p[256], const uint8_t seed[64], uint16_t nonce);
+void orc_mldsa_derive_ball(int mode, uint32_t p[256], const uint8_t *seed);     /* seed = c~: 32 / 48 / 64 bytes */
+void orc_dil_power2round(const uint32_t *p, uint32_t *p0plusq, uint32_t *p1);  /* poly.go:77-84 */
+void orc_dil_pack_le16(uint8_t buf[128], const uint32_t *p);                    /* pack.go:102-108 */
 void orc_mldsa65_keygen(uint8_t pk[1952], uint8_t sk[4032], const uint8_t seed[32]);    /* internal/dilithium.go:181-241 */
 /* returns the number of rejection-loop attempts (>= 1), or -1 after 576 (dilithium.go:372-377) */
 int orc_mldsa65_sign(uint8_t sig[3309], const uint8_t *sk, const uint8_t *msg, size_t msglen, const uint8_t *ctx,

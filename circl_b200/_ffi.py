@@ -24,6 +24,12 @@ SYMBOLS = {
     "cb200_release_stream": (C.c_int, [C.c_void_p]),
     "cb200_synchronize": (C.c_int, []),
     "cb200_bind_thread_to_device": (C.c_int, [C.c_int]),
+    "cb200_gather_alloc": (C.c_int, [C.c_size_t, C.c_void_p, C.c_void_p]),
+    "cb200_gather_free": (C.c_int, [C.c_void_p]),
+    "cb200_gather_open": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "cb200_gather_close": (C.c_int, [C.c_void_p]),
+    "cb200_gather_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
+    "cb200_gather_flush": (C.c_int, [C.c_void_p, C.c_int]),
     "cb200_host_alloc": (C.c_void_p, [C.c_size_t]),
     "cb200_host_free": (None, [C.c_void_p]),
     "cb200_launch_count": (C.c_uint64, []),

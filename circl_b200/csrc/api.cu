@@ -153,6 +153,8 @@ static int wset_create(WorkSet& w) {  // the owning device is current
     CB200_CUDA(cudaStreamCreateWithFlags(&w.lane[l], cudaStreamNonBlocking));
     CB200_CUDA(cudaEventCreateWithFlags(&w.ev_join[l], cudaEventDisableTiming));
   }
+  CB200_CUDA(cudaStreamCreateWithFlags(&w.copy, cudaStreamNonBlocking));
+  CB200_CUDA(cudaEventCreateWithFlags(&w.ev_copy, cudaEventDisableTiming));
   CB200_CUDA(cudaMalloc(&w.small, 256));
   CB200_CUDA(cudaHostAlloc(&w.pin, 64, cudaHostAllocDefault));
   return 0;
@@ -169,6 +171,10 @@ static void wset_destroy(WorkSet& w) {
   }
   if (w.ev_fork) cudaEventDestroy(w.ev_fork);
   w.ev_fork = nullptr;
+  if (w.copy) cudaStreamDestroy(w.copy);
+  if (w.ev_copy) cudaEventDestroy(w.ev_copy);
+  w.copy = nullptr;
+  w.ev_copy = nullptr;
   if (w.small) cudaFree(w.small);
   if (w.pin) cudaFreeHost(w.pin);
   w.small = w.pin = nullptr;

@@ -44,6 +44,8 @@ struct WorkSet {
   // sub-batch's kernels overlaps the head of the next (fork/join on events around them)
   cudaStream_t lane[2] = {nullptr, nullptr};
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
+  cudaStream_t copy = nullptr;  // result pushes (cb200_gather_push): copy-engine traffic beside the kernels
+  cudaEvent_t ev_copy = nullptr;
   void* small = nullptr;  // 256-byte device buffer (ML-DSA context string of a device-pointer call)
   void* pin = nullptr;    // 64 bytes of pinned host memory (per-round counters of the signing loop)
   std::mutex mu;          // callers sharing this set enqueue one after the other

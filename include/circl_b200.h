@@ -61,6 +61,21 @@ int cb200_synchronize(void);           /* waits for this thread's stream */
  * allocates and first touches afterwards is local to that GPU's NUMA node.  Returns the number of CPUs, 0 if the
  * topology is unknown (affinity unchanged).  The library's own worker threads do this themselves. */
 int cb200_bind_thread_to_device(int device);
+/* ---- result gather of the one-process-per-GPU launch ----
+ * Rank 0 allocates the destination of the gather (plain cudaMalloc memory on its GPU) and gets a 64-byte handle to
+ * publish over any transport (torch.distributed, a pipe); every other rank opens the handle and pushes its rows:
+ * cb200_gather_push(dst, src, bytes) is a cudaMemcpyAsync into the mapped peer memory over NVLink, issued on a copy
+ * stream of the library that first waits for everything the calling thread's stream has queued so far -- copy-engine
+ * traffic, no SM, no NCCL kernel beside the compute kernels.  dst may also be local (rank 0's own rows).
+ * cb200_gather_flush(row, wait_on_host): wait_on_host != 0 blocks until this rank's pushes have landed; otherwise the
+ * calling thread's stream is made to wait for them.  `row` is any device pointer of the pushing GPU. */
+#define CB200_GATHER_HANDLE_BYTES 64
+int cb200_gather_alloc(size_t bytes, void **dev_ptr, uint8_t *handle);
+int cb200_gather_free(void *dev_ptr);
+int cb200_gather_open(const uint8_t *handle, void **peer_ptr);
+int cb200_gather_close(void *peer_ptr);
+int cb200_gather_push(void *dst, const void *src, size_t bytes);
+int cb200_gather_flush(const void *any_local_row, int wait_on_host);
 /* Pinned host memory for large batches handed to Go via unsafe.Slice. */
 void *cb200_host_alloc(size_t bytes);
 void cb200_host_free(void *p);

@@ -261,6 +261,30 @@ def mlkem_encaps_batch(k: int, ek: np.ndarray, m: np.ndarray, nthreads: int = 1)
     return ct, ss, fails
 
 
+def mlkem_parse_keys(k: int, ek: np.ndarray) -> np.ndarray:
+    """UnmarshalBinaryPublicKey for every row of ek: the cached fields (th, aT, hpk) of each key, (n, parsed_size) uint8."""
+    L = lib()
+    L.orc_mlkem_parsed_size.restype = C.c_size_t
+    psz = int(L.orc_mlkem_parsed_size())
+    ek = np.ascontiguousarray(ek, dtype=np.uint8)
+    out = np.empty((ek.shape[0], psz), dtype=np.uint8)
+    for i in range(ek.shape[0]):
+        rc = L.orc_mlkem_pk_parse(C.c_int(k), C.c_void_p(out[i].ctypes.data), C.c_void_p(ek[i].ctypes.data))
+        assert rc == 0
+    return out
+
+
+def mlkem_encaps_parsed_batch(k: int, parsed: np.ndarray, m: np.ndarray, nthreads: int = 1):
+    """EncapsulateTo on pre-parsed keys (one per op)."""
+    _, _, ctsz = mlkem_sizes(k)
+    n = m.shape[0]
+    ct = np.empty((n, ctsz), dtype=np.uint8)
+    ss = np.empty((n, 32), dtype=np.uint8)
+    lib().orc_mlkem_encaps_parsed_batch(C.c_int(k), _ptr(ct), _ptr(ss), _ptr(parsed), C.c_size_t(parsed.shape[1]),
+                                        _ptr(np.ascontiguousarray(m)), C.c_size_t(n), C.c_int(nthreads))
+    return ct, ss
+
+
 # ------------------------------------------------------------------ Dilithium / ML-DSA-65
 def dil_zetas():
     L = lib()

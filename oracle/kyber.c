@@ -484,6 +484,50 @@ int orc_mlkem_encaps_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, s
   return fails;
 }
 
+/* ---- "pk pre-parsed" variant for BASELINE config 1: the reference's BenchmarkEncapsulate (kem/schemes/schemes_test.go)
+ * and the KAT loop (kem/kyber/kat_test.go:48-81) time EncapsulateTo on an already unmarshalled *PublicKey, whose cached
+ * fields are th, aT and hpk (kem/mlkem/mlkem768/kyber.go:39-43, cpapke.go:19-25).  parsed = th[4][256] | aT[16][256]
+ * (int16) | hpk[32]. */
+size_t orc_mlkem_parsed_size(void) { return 20 * N * sizeof(int16_t) + 32; }
+int orc_mlkem_pk_parse(int k, uint8_t *parsed, const uint8_t *ek) {
+  int16_t *th = (int16_t *)parsed, *aT = th + 4 * N;
+  int rc = pk_unpack(k, th, aT, ek);
+  orc_sha3_256(parsed + 20 * N * sizeof(int16_t), ek, orc_mlkem_ek_size(k));
+  return rc;
+}
+void orc_mlkem_encaps_parsed(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *parsed, const uint8_t m[32]) {
+  const int16_t *th = (const int16_t *)parsed, *aT = th + 4 * N;
+  uint8_t g_in[64], kr[64];
+  memcpy(g_in, m, 32);
+  memcpy(g_in + 32, parsed + 20 * N * sizeof(int16_t), 32);
+  orc_sha3_512(kr, g_in, 64);
+  cpapke_encrypt(k, ct, th, aT, m, kr + 32);
+  memcpy(ss, kr, 32);
+}
+typedef struct {
+  int k; uint8_t *ct, *ss; const uint8_t *parsed; size_t stride; const uint8_t *m; size_t lo, hi;
+} encp_job;
+static void *encp_worker(void *arg) {
+  encp_job *j = (encp_job *)arg;
+  size_t ctsz = orc_mlkem_ct_size(j->k);
+  for (size_t i = j->lo; i < j->hi; i++)
+    orc_mlkem_encaps_parsed(j->k, j->ct + i * ctsz, j->ss + i * 32, j->parsed + i * j->stride, j->m + i * 32);
+  return NULL;
+}
+void orc_mlkem_encaps_parsed_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *parsed, size_t stride, const uint8_t *m,
+                                   size_t n, int nthreads) {
+  if (nthreads < 1) nthreads = 1;
+  if ((size_t)nthreads > n) nthreads = n ? (int)n : 1;
+  pthread_t *th = (pthread_t *)malloc(sizeof(pthread_t) * nthreads);
+  encp_job *jobs = (encp_job *)malloc(sizeof(encp_job) * nthreads);
+  for (int t = 0; t < nthreads; t++) {
+    jobs[t] = (encp_job){k, ct, ss, parsed, stride, m, n * t / nthreads, n * (t + 1) / nthreads};
+    pthread_create(&th[t], NULL, encp_worker, &jobs[t]);
+  }
+  for (int t = 0; t < nthreads; t++) pthread_join(th[t], NULL);
+  free(th); free(jobs);
+}
+
 typedef struct { int16_t *p; size_t lo, hi; int inverse; } ntt_job;
 static void *ntt_worker(void *arg) {
   ntt_job *j = (ntt_job *)arg;

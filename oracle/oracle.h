@@ -97,6 +97,12 @@ void orc_hybrid_keygen(int id, uint8_t *pk, uint8_t *sk, const uint8_t seed[64])
 int orc_hybrid_encaps(int id, uint8_t *ct, uint8_t *ss, const uint8_t *pk, const uint8_t seed[32]);
 int orc_hybrid_decaps(int id, uint8_t *ss, const uint8_t *sk, const uint8_t *ct);
 
+/* EncapsulateTo on an already unmarshalled key (its cached th, aT, hpk): BASELINE config 1, "pk pre-parsed" */
+size_t orc_mlkem_parsed_size(void);
+int orc_mlkem_pk_parse(int k, uint8_t *parsed, const uint8_t *ek);
+void orc_mlkem_encaps_parsed(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *parsed, const uint8_t m[32]);
+void orc_mlkem_encaps_parsed_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *parsed, size_t stride, const uint8_t *m,
+                                   size_t n, int nthreads);
 int orc_mlkem_encaps_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, size_t ek_stride,
                            const uint8_t *m, size_t n, int nthreads);
 

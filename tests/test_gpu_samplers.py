@@ -99,8 +99,12 @@ def test_dilithium_sampler_vectors_of_the_reference(cb, sampler_vectors):
     seed32, seed64 = np.arange(32, dtype=np.uint8), np.arange(64, dtype=np.uint8)
     nonce = np.array([30000], dtype=np.uint16)
     assert dilithium.derive_uniform(seed32, nonce)[0].tolist() == sampler_vectors["dil_uniform_nonce30000"]
-    assert dilithium.derive_leq_eta(65, seed64, nonce)[0].tolist() == sampler_vectors["dil_leqeta4_nonce30000"]
-    assert dilithium.derive_le_gamma1(65, seed64, nonce)[0].tolist() == sampler_vectors["dil_legamma1_19_nonce30000"]
+    # the reference compares these two after p.Normalize() (mode3/internal/params_test.go:38-39, :99-100); so do we,
+    # with the Normalize of the same library
+    eta = dilithium.normalize(dilithium.derive_leq_eta(65, seed64, nonce))
+    assert eta[0].tolist() == sampler_vectors["dil_leqeta4_nonce30000"]
+    g1 = dilithium.normalize(dilithium.derive_le_gamma1(65, seed64, nonce))
+    assert g1[0].tolist() == sampler_vectors["dil_legamma1_19_nonce30000"]
 
 
 @pytest.mark.parametrize("mode", [44, 65, 87])

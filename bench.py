@@ -377,65 +377,6 @@ class Ctx:
                 for i in range(nk) if cnt[i]}
 
 
-class _RawCuda:
-    """A raw device pointer as a __cuda_array_interface__ object (torch.as_tensor views it without a copy)."""
-
-    def __init__(self, ptr: int, nbytes: int):
-        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
-
-
-class PeerGather:
-    """Rows of every rank into rank 0's buffer through CUDA IPC + copy engines (circl_b200/csrc/gather.cu);
-    torch.distributed only carries the 64-byte handle and the barriers."""
-
-    def __init__(self, cx: Ctx, n: int, widths):
-        import torch
-        self.cx, self.n, self.widths = cx, n, widths
-        L, check = cx.L, cx.check
-        self.offsets, total = [], 0
-        for w in widths:
-            self.offsets.append(total)
-            total += cx.world * n * w
-        self.total = total
-        handle = (ctypes.c_uint8 * 64)()
-        self.base = ctypes.c_void_p()
-        self.owner = cx.rank == 0
-        if self.owner:
-            check(L.cb200_gather_alloc(total, ctypes.byref(self.base), handle))
-        box = [bytes(handle)]
-        cx.dist.broadcast_object_list(box, src=0)
-        if not self.owner:
-            h = (ctypes.c_uint8 * 64).from_buffer_copy(box[0])
-            check(L.cb200_gather_open(h, ctypes.byref(self.base)))
-        self.view = torch.as_tensor(_RawCuda(self.base.value, total), device="cuda") if self.owner else None
-
-    def push(self, tensors, lo, hi):
-        """rows [lo, hi) of this rank's tensors -> their place in the global order on rank 0"""
-        L, check, r = self.cx.L, self.cx.check, self.cx.rank
-        for t, w, off in zip(tensors, self.widths, self.offsets):
-            dst = self.base.value + off + (r * self.n + lo) * w
-            check(L.cb200_gather_push(dst, t[lo:hi].data_ptr(), (hi - lo) * w))
-
-    def flush(self, any_tensor, on_host=False):
-        self.cx.check(self.cx.L.cb200_gather_flush(any_tensor.data_ptr(), 1 if on_host else 0))
-
-    def rows(self, which: int, idx):
-        """global rows `idx` of buffer `which` (rank 0) as a numpy array"""
-        import torch
-        w, off = self.widths[which], self.offsets[which]
-        v = self.view[off:off + self.cx.world * self.n * w].view(self.cx.world * self.n, w)
-        return v[torch.as_tensor(idx, device="cuda")].cpu().numpy()
-
-    def close(self):
-        L = self.cx.L
-        self.cx.barrier()
-        if self.owner:
-            self.view = None
-            L.cb200_gather_free(self.base)
-        else:
-            L.cb200_gather_close(self.base)
-
-
 # ---------------------------------------------------------------- ML-KEM encaps (configs 3 and 5)
 def bench_mlkem(cx: Ctx, wl_key: str, log2n: int, steps: int, warmup: int, with_profile=True, with_cpu=True,
                 e2e_steps=5, sampler=None):
@@ -463,7 +404,8 @@ def bench_mlkem(cx: Ctx, wl_key: str, log2n: int, steps: int, warmup: int, with_
     # N > 1: results are gathered to rank 0 in global index order (the one exchange of this path), chunk by chunk so that
     # the transfer of chunk c overlaps the kernels of chunk c+1; the transfers are peer copies by the copy engines.
     n_chunks = 16 if world > 1 else 1
-    pg = PeerGather(cx, n, [wl["ct"], 32]) if world > 1 else None
+    from circl_b200.shard import RowGather
+    pg = RowGather(n, [wl["ct"], 32], transport="ipc") if world > 1 else None
 
     def step_device(do_gather=True):
         if world == 1:
@@ -508,7 +450,8 @@ def bench_mlkem(cx: Ctx, wl_key: str, log2n: int, steps: int, warmup: int, with_
             rng = np.random.default_rng(2024)
             idx = sorted(set([0, world * n - 1] + [r * n + int(x) for r in range(world)
                                                     for x in list(rng.integers(0, n, size=14)) + [0, n - 1]]))
-            got_ct, got_ss = pg.rows(0, idx), pg.rows(1, idx)
+            sel = torch.as_tensor(idx, device="cuda")
+            got_ct, got_ss = pg.matrix(0)[sel].cpu().numpy(), pg.matrix(1)[sel].cpu().numpy()
             match = True
             for j, i in enumerate(idx):
                 wct, wss = oracle.mlkem_encaps(wl["k"], keys[i % 1024].tobytes(), op_seeds(0x01, i, 1)[0].tobytes())
@@ -613,6 +556,7 @@ def bench_mlkem(cx: Ctx, wl_key: str, log2n: int, steps: int, warmup: int, with_
             c1["gpu_outputs_match"] = bool(np.array_equal(gct, kct) and np.array_equal(gss, kss))
             cpu["config1"] = c1
     if pg is not None:
+        cx.barrier()
         pg.close()
     rec = {"metric": f"{wl['name']} encaps/sec", "value": world * n / (ms_step * 1e-3), "unit": "encaps/s",
            "per_gpu": n / (ms_step * 1e-3), "ms_per_step": ms_step, "config": mlkem_config(wl, n), "e2e": e2e,

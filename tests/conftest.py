@@ -44,3 +44,8 @@ def keccak_kats():
 @pytest.fixture(scope="session")
 def mldsa_other_acvp():
     return load_golden("mldsa_other_acvp.json.gz")
+
+
+@pytest.fixture(scope="session")
+def mldsa_wycheproof():
+    return load_golden("mldsa_wycheproof.json.gz")

@@ -11,6 +11,7 @@ only re-packages the reference's test DATA:
   * sampler vectors embedded as Go literals in *_test.go files
   * PQCgenKAT SHA-256 digests (kem/kyber/kat_test.go:25-33, sign/dilithium/kat_test.go:25-35)
   * Keccak ShortMsgKATs (internal/sha3/testdata/keccakKats.json.deflate), subsampled
+  * Wycheproof ML-DSA vectors (sign/schemes/testdata/wycheproof)
 """
 import gzip
 import json
@@ -99,15 +100,15 @@ def mldsa65():
 
 
 def mldsa_other():
-    """ML-DSA-44 and ML-DSA-87: a subset of the same ACVP files (the first vectors of every group)."""
-    out = {"source": "sign/mldsa/testdata (NIST ACVP FIPS 204), ML-DSA-44 / ML-DSA-87, first vectors of each group"}
+    """ML-DSA-44 and ML-DSA-87: every vector of their groups in the same ACVP files."""
+    out = {"source": "sign/mldsa/testdata (NIST ACVP FIPS 204), ML-DSA-44 / ML-DSA-87, all vectors of their groups"}
     for ps in ("ML-DSA-44", "ML-DSA-87"):
         o = {"siggen": [], "sigver": {}, "keygen": []}
         prompt, res = acvp("sign/mldsa/testdata/ML-DSA-sigGen-FIPS204")
         for g in prompt["testGroups"]:
             if g["parameterSet"] != ps:
                 continue
-            for t in g["tests"][:3]:
+            for t in g["tests"]:
                 o["siggen"].append({"tcId": t["tcId"], "deterministic": g["deterministic"], "sk": t["sk"],
                                     "message": t["message"], "rnd": t.get("rnd", "00" * 32),
                                     "signature": res[t["tcId"]]["signature"]})
@@ -116,16 +117,14 @@ def mldsa_other():
             if g["parameterSet"] != ps:
                 continue
             tests = g["tests"]
-            passed = [t for t in tests if res[t["tcId"]]["testPassed"]][:3]
-            failed = [t for t in tests if not res[t["tcId"]]["testPassed"]][:5]
             o["sigver"] = {"pk": g["pk"], "tests": [{"tcId": t["tcId"], "message": t["message"], "signature": t["signature"],
-                                                     "testPassed": res[t["tcId"]]["testPassed"]} for t in passed + failed]}
+                                                     "testPassed": res[t["tcId"]]["testPassed"]} for t in tests]}
         prompt, res = acvp("sign/mldsa/testdata/ML-DSA-keyGen-FIPS204")
         for g in prompt["testGroups"]:
             if g["parameterSet"] != ps:
                 continue
             o["keygen"] = [{"tcId": t["tcId"], "seed": t["seed"], "pk": res[t["tcId"]]["pk"], "sk": res[t["tcId"]]["sk"]}
-                           for t in g["tests"][:5]]
+                           for t in g["tests"]]
         out[ps] = o
     dump("mldsa_other_acvp.json.gz", out)
 
@@ -197,6 +196,27 @@ def x25519_vectors():
     dump("x25519_vectors.json.gz", out)
 
 
+def wycheproof():
+    """sign/schemes/testdata/wycheproof/mldsa_{44,65,87}_*: the vectors sign/schemes/wycheproof_test.go replays
+    (malformed keys and signatures, context strings, hint encodings, signatures that need many rejection rounds)."""
+    td = "sign/schemes/testdata/wycheproof"
+    out = {"source": td + " (all nine files, every group and test case; replayed as sign/schemes/wycheproof_test.go:40-150 does)"}
+    for f in sorted(os.listdir(os.path.join(REF, td))):
+        if not f.endswith(".json.gz"):
+            continue
+        ts = jgz(f"{td}/{f}")
+        groups = []
+        for g in ts["testGroups"]:
+            o = {"type": g["type"], "tests": [{k: t.get(k) for k in ("tcId", "msg", "ctx", "sig", "result", "comment", "flags")}
+                                              for t in g["tests"]]}
+            for k in ("privateKey", "privateSeed", "publicKey"):
+                if k in g:
+                    o[k] = g[k]
+            groups.append(o)
+        out[f.replace(".json.gz", "")] = {"algorithm": ts["algorithm"], "groups": groups}
+    dump("mldsa_wycheproof.json.gz", out)
+
+
 def keccak_kats():
     raw = open(os.path.join(REF, "internal/sha3/testdata/keccakKats.json.deflate"), "rb").read()
     kats = json.loads(zlib.decompress(raw, -15))["kats"]
@@ -219,3 +239,4 @@ if __name__ == "__main__":
     samplers()
     keccak_kats()
     x25519_vectors()
+    wycheproof()

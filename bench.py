@@ -401,23 +401,15 @@ def bench_mlkem(cx: Ctx, wl_key: str, log2n: int, steps: int, warmup: int, with_
     ct_d = torch.empty((n, wl["ct"]), dtype=torch.uint8, device="cuda")
     ss_d = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
 
-    # N > 1: results are gathered to rank 0 in global index order (the one exchange of this path), chunk by chunk so that
-    # the transfer of chunk c overlaps the kernels of chunk c+1; the transfers are peer copies by the copy engines.
-    n_chunks = 16 if world > 1 else 1
+    # N > 1: results are gathered to rank 0 in global index order (the one exchange of this path).  The flow pushes every
+    # sub-batch of 8192 results into rank 0's buffer as soon as it exists (cb200_mlkem_encaps_push: peer copies by the
+    # copy engines over NVLink) while the next sub-batches compute.
     from circl_b200.shard import RowGather
     pg = RowGather(n, [wl["ct"], 32], transport="ipc") if world > 1 else None
 
     def step_device(do_gather=True):
-        if world == 1:
-            scheme.EncapsulateBatch(eks_d, seeds_d, ct=ct_d, ss=ss_d)
-            return
-        for c in range(n_chunks):
-            lo, hi = c * n // n_chunks, (c + 1) * n // n_chunks
-            scheme.EncapsulateBatch(eks_d[lo:hi], seeds_d[lo:hi], ct=ct_d[lo:hi], ss=ss_d[lo:hi])
-            if do_gather:
-                pg.push([ct_d, ss_d], lo, hi)
-        if do_gather:
-            pg.flush(ct_d)  # the compute stream (and the event that ends the timed region) waits for this rank's pushes
+        push = (pg.dst_ptr(0), pg.dst_ptr(1)) if (pg is not None and do_gather) else None
+        scheme.EncapsulateBatch(eks_d, seeds_d, ct=ct_d, ss=ss_d, push=push)
 
     def step_host():
         check(L.cb200_mlkem_encaps(wl["k"], eks_h.data_ptr(), wl["ek"], seeds_h.data_ptr(), ct_h.data_ptr(),
@@ -471,14 +463,15 @@ def bench_mlkem(cx: Ctx, wl_key: str, log2n: int, steps: int, warmup: int, with_
         cx.barrier()
         ms_gather = cx.max_over_ranks(ev0.elapsed_time(ev1))
         nbytes = (world - 1) * n * (wl["ct"] + 32)
-        gather = {"to": "rank 0", "bytes_per_step": nbytes, "chunks": n_chunks, "ms_alone": ms_gather,
+        gather = {"to": "rank 0", "bytes_per_step": nbytes, "chunks": (n + 8191) // 8192, "ms_alone": ms_gather,
                   "rank0_ingress_GBps": nbytes / 1e9 / (ms_gather * 1e-3),
                   "ms_per_step_without_gather": ms_nogather, "exposed_ms": ms_step - ms_nogather,
                   "gathered_outputs_match": match, "checked_rows": (len(idx) if rank == 0 else None),
                   "transport": "CUDA IPC mapping of rank 0's buffer + cudaMemcpyAsync peer copies on a copy stream "
-                               "(copy engines over NVLink; no SM); torch.distributed/NCCL only for the handle and barriers",
-                  "note": "value includes the gather, overlapped chunk by chunk with the kernels; the strided sample of "
-                          "the gathered buffer on rank 0 is compared with the oracle"}
+                               "(copy engines over NVLink; no SM), issued by the encaps flow itself per sub-batch of 8192 "
+                               "results (cb200_mlkem_encaps_push); torch.distributed/NCCL only for the handle and barriers",
+                  "note": "value includes the gather, overlapped sub-batch by sub-batch with the kernels; the strided "
+                          "sample of the gathered buffer on rank 0 is compared with the oracle"}
 
     # ---- end to end through the C ABI with pinned host buffers
     e2e = None

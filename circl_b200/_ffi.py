@@ -62,6 +62,8 @@ SYMBOLS = {
     "cb200_dil_pack_le16": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "cb200_mlkem_encaps": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_size_t]),
+    "cb200_mlkem_encaps_push": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                          C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p]),
     "cb200_kyber_kem_keygen": (C.c_int, [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cb200_kyber_kem_encaps": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]),
     "cb200_kyber_kem_decaps": (C.c_int, [C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_size_t]),

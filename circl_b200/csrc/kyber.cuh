@@ -263,6 +263,9 @@ __device__ __forceinline__ void inv_pass_C(int32_t (&r)[32], const LaneTw& t) {
 // Inverse pass B on S layout: layers l = 16, 32, 64, 128 with the lazy Barrett
 // schedule of ntt.go:44-49 and the final multiplication by 1441 (ntt.go:187-192).
 // S layout: r[2s+b] = coefficient 16s + 2v + b.
+// SCALE = false leaves the last step out (for callers that folded the constant into an operand): the outputs are
+// then the int16-range values the reference holds right before it (|x| < 2^15), to be Barrett-reduced by the caller.
+template <bool SCALE = true>
 __device__ __forceinline__ void inv_pass_S(int32_t (&r)[32], int v) {
   static_for<0, 8>([&](auto hc) {  // l=16: pairs (s, s+1), k = 15 - (s>>1)
     constexpr int h = decltype(hc)::value;
@@ -304,8 +307,10 @@ __device__ __forceinline__ void inv_pass_S(int32_t (&r)[32], int v) {
 #pragma unroll
   for (int i = 0; i < 16; i++) gs_bfly(r[i], r[i + 16], Zeta<1>::z, Zeta<1>::zq);  // l=128, k=1
   // p[j] = montReduce(1441 * p[j])
+  if constexpr (SCALE) {
 #pragma unroll
-  for (int i = 0; i < 32; i++) r[i] = mont_mul_hi(r[i] >> 16, 1441, (int32_t)(((1441u * QINV) & 0xffffu) << 16));
+    for (int i = 0; i < 32; i++) r[i] = mont_mul_hi(r[i] >> 16, 1441, (int32_t)(((1441u * QINV) & 0xffffu) << 16));
+  }
 }
 
 // ---------------------------------------------------------------- S <-> C transposition

@@ -496,6 +496,238 @@ __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
 }
 
 
+// ------------------------------------------------------------------ 3b. K-PKE.Encrypt, inner products on packed pairs
+// The same function as encrypt_kernel with the matrix-vector products done differently.  What leaves the kernel is
+// Compress(Normalize(.)), so only residues mod q matter inside it, not the reference's Montgomery representatives:
+//
+//   * A^T and t-hat are used as they lie in memory: one 32-bit word = one degree-2 block (a0 | a1 << 16), plain
+//     residues in [0, 4096);
+//   * r-hat is prepared once per op as byte-split operands in shared memory, two words per block:
+//       W0 = [b0.lo, z b1.lo, b0.hi, z b1.hi]    W1 = [b1.lo, b0.lo, b1.hi, b0.hi]    (z = +-zeta of the block)
+//     (low bytes unsigned, high bytes signed), so that the two outputs of the block over all K columns,
+//       p0 = sum a0 b0 + a1 (z b1),   p1 = sum a0 b1 + a1 b0                         (poly.go:63-100 without the R^-1)
+//     are 4 IDP.2A (16-bit x 8-bit dot products with accumulate) per column and block, with no unpacking of A at all --
+//     against 5 Montgomery products, i.e. ~50 instructions, in the reference's formulation;
+//   * one Montgomery reduction per output coefficient then yields p R^-1 mod q, the residue MulHat would have
+//     produced; the constant of the inverse transform (ntt.go:187-192: x 1441 = R^2 / 128, Montgomery) is folded into
+//     the operands instead -- they carry r-hat R / 128 = 512 r-hat -- which costs a multiplication per coefficient of
+//     r-hat once instead of one per coefficient of every output row and doubles as their reduction.
+//
+// Bounds: |b| < q after the Montgomery multiplication, |z b1| < q, a < 4096 (a < q unless the key is not canonical): a
+// 32-bit sum p of 2 K products is below 8 . 4096 . q < 2^27, and |montReduce(p)| <= |p| / 2^16 + q / 2 <= q, which is the
+// input bound of the inverse transform's lazy-Barrett schedule (ntt.go:145-150).
+constexpr int kOpPad = 16;  // words between the operand areas of two ops: half-warps (two octets) hit disjoint banks
+template <int K>
+struct EncSmem {
+  static constexpr int op_words = K * 128 * 2 + kOpPad;
+  static constexpr int words = (kEncThreads / 8) * op_words + (kEncThreads / 8) * kyber::kPolyWords + 256;
+  static constexpr int bytes = words * 4;
+};
+
+__device__ __forceinline__ uint32_t dp2a_lo_uu(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d;
+  asm("dp2a.lo.u32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+__device__ __forceinline__ int32_t dp2a_hi_us(uint32_t a, uint32_t b, int32_t c) {
+  int32_t d;
+  asm("dp2a.hi.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+  return d;
+}
+// montReduce(p) << 16 for a 32-bit signed p (field.go:4-32)
+__device__ __forceinline__ int32_t mont_red_hi(int32_t p) {
+  const int32_t m = (int32_t)((uint32_t)p * (kyber::QINV << 16)) >> 16;
+  return p - m * Q;
+}
+// 12-bit unpack of 32 coefficients (48 bytes, 16-byte aligned) straight to packed pairs (poly.go:123-129);
+// returns nonzero if any coefficient is >= q (cpapke.go:45-55)
+__device__ __forceinline__ uint32_t unpack12_pairs(const uint8_t* __restrict__ src, uint32_t (&aw)[16]) {
+  const uint4* p = reinterpret_cast<const uint4*>(src);
+  uint32_t w[12];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    const uint4 q4 = __ldg(p + i);
+    w[4 * i] = q4.x;
+    w[4 * i + 1] = q4.y;
+    w[4 * i + 2] = q4.z;
+    w[4 * i + 3] = q4.w;
+  }
+  uint32_t bad = 0;
+#pragma unroll
+  for (int g = 0; g < 4; g++) {  // 3 words -> 8 coefficients -> 4 pairs
+    const uint32_t a = w[3 * g], b = w[3 * g + 1], c = w[3 * g + 2];
+    uint32_t t[8];
+    t[0] = a & 0xfff;
+    t[1] = (a >> 12) & 0xfff;
+    t[2] = ((a >> 24) | (b << 8)) & 0xfff;
+    t[3] = (b >> 4) & 0xfff;
+    t[4] = (b >> 16) & 0xfff;
+    t[5] = ((b >> 28) | (c << 4)) & 0xfff;
+    t[6] = (c >> 8) & 0xfff;
+    t[7] = c >> 20;
+#pragma unroll
+    for (int j = 0; j < 8; j++) bad |= (t[j] >= (uint32_t)Q);
+#pragma unroll
+    for (int j = 0; j < 4; j++) aw[4 * g + j] = t[2 * j] | (t[2 * j + 1] << 16);
+  }
+  return bad;
+}
+
+template <int K>
+__global__ void __launch_bounds__(kEncThreads, 3) encrypt_dp_kernel(
+    const uint8_t* __restrict__ ek, size_t ek_stride, const int16_t* __restrict__ A, int a_shared,
+    const int16_t* __restrict__ noise, const uint8_t* __restrict__ m, size_t n, uint8_t* __restrict__ ct,
+    uint8_t* __restrict__ ss, uint8_t* __restrict__ status, const kyber::TwPair* __restrict__ tw, int lenient) {
+  // lenient = 1: re-encryption inside Decapsulate (PublicKey.Unpack, cpapke.go:58-63: no modulus check; the
+  // Normalize of t-hat is immaterial here because only residues are used)
+  using P = Params<K>;
+  using S = EncSmem<K>;
+  using namespace kyber;
+  extern __shared__ __align__(16) uint32_t enc_smem[];
+  uint32_t* ops_all = enc_smem;
+  uint32_t* tiles = enc_smem + (kEncThreads / 8) * S::op_words;
+  TwPair* tws = reinterpret_cast<TwPair*>(tiles + (kEncThreads / 8) * kPolyWords);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
+  const unsigned octmask = 0xffu << (8 * oct);
+  uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
+  uint2* ops = reinterpret_cast<uint2*>(ops_all + (size_t)(warp * 4 + oct) * S::op_words) + v;  // [j][block][lane]
+
+  for (int i = threadIdx.x; i < 128; i += kEncThreads) tws[i] = tw[i];
+  __syncthreads();
+  const volatile TwPair* tab = tws;
+  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
+  if (base >= n) return;
+  const size_t op_raw = base + oct;
+  const bool active = op_raw < n;
+  const size_t op = active ? op_raw : n - 1;
+  const uint8_t* ekp = ek + op * ek_stride;
+  const uint32_t* Ap = reinterpret_cast<const uint32_t*>(A) + (a_shared ? 0 : op * K * K * (N / 2));
+  const uint32_t* np = reinterpret_cast<const uint32_t*>(noise) + op * P::n_noise * (N / 2);
+  uint8_t* ctp = ct + op * P::ct_bytes;
+
+  int32_t r[32];
+
+  // operands of rh = BarrettReduce(NTT(r))   (cpapke.go:142-144)
+#pragma unroll 1
+  for (int j = 0; j < K; j++) {
+    gload_S(np + j * (N / 2), v, r);
+    fwd_pass_S(r);
+    store_S(tile, v, r);
+    __syncwarp();
+    load_C(tile, v, r);
+    fwd_pass_C_smem(r, tab, v);
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < 8; q++) {  // quad q of this lane: zeta = Zetas[64 + 8 v + q], +zeta for its first block, -zeta for its second
+      const TwPair z = tw_at(tab, 64 + 8 * v + q);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        const int blk = 2 * q + h;
+        // x 512 = R / 128: mont_mul by 512 R mod q (|in| <= 7 q, |out| < q)
+        constexpr int32_t kS = (int32_t)((512ull * 65536ull) % Q), kSq = (int32_t)((((uint32_t)kS * QINV) & 0xffffu) << 16);
+        const int32_t b0 = mont_mul_hi(r[2 * blk] >> 16, kS, kSq), b1 = mont_mul_hi(r[2 * blk + 1] >> 16, kS, kSq);
+        int32_t zb1 = mont_mul_hi(b1 >> 16, z.z, z.zq);
+        if (h) zb1 = -zb1;
+        // bytes 2 (low, unsigned) and 3 (high, signed) of the high-half registers
+        ops[(j * 16 + blk) * 8] = make_uint2(__byte_perm((uint32_t)b0, (uint32_t)zb1, 0x7362),
+                                             __byte_perm((uint32_t)b1, (uint32_t)b0, 0x7362));
+      }
+    }
+  }
+  __syncwarp();
+
+  // u[i] = InvNTT(A^T[i] . rh) + e1[i]; v = InvNTT(t . rh) + e2 + m
+  uint32_t bad = 0;
+#pragma unroll 1
+  for (int i = 0; i <= K; i++) {
+    int32_t p0l[16], p0h[16], p1l[16], p1h[16];
+#pragma unroll
+    for (int c = 0; c < 16; c++) p0l[c] = p0h[c] = p1l[c] = p1h[c] = 0;
+#pragma unroll 1
+    for (int j = 0; j < K; j++) {
+      uint32_t aw[16];
+      if (i < K) {
+        load_words_C(Ap + (i * K + j) * (N / 2), v, aw);
+      } else {  // row K: t-hat from the encapsulation key, PolyDotHat(&v, &pk.th, &rh) (cpapke.go:167)
+        const uint32_t b = unpack12_pairs(ekp + 384 * j + 48 * v, aw);
+        if (!lenient) bad |= b;
+      }
+      const uint2* oj = ops + (size_t)j * 16 * 8;
+#pragma unroll
+      for (int c = 0; c < 16; c++) {
+        const uint2 w = oj[c * 8];
+        p0l[c] = (int32_t)dp2a_lo_uu(aw[c], w.x, (uint32_t)p0l[c]);
+        p0h[c] = dp2a_hi_us(aw[c], w.x, p0h[c]);
+        p1l[c] = (int32_t)dp2a_lo_uu(aw[c], w.y, (uint32_t)p1l[c]);
+        p1h[c] = dp2a_hi_us(aw[c], w.y, p1h[c]);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 16; c++) {
+      r[2 * c] = mont_red_hi(p0l[c] + p0h[c] * 256);
+      r[2 * c + 1] = mont_red_hi(p1l[c] + p1h[c] * 256);
+    }
+    inv_pass_C_smem(r, tab, v);
+    store_C(tile, v, r);
+    __syncwarp();
+    load_S(tile, v, r);
+    inv_pass_S<false>(r, v);
+    __syncwarp();
+    {  // + e1[i] / + e2 (+ Decompress_q(m, 1)), S layout
+      const uint32_t* e = np + (K + i) * (N / 2);
+      const uint32_t* mw = reinterpret_cast<const uint32_t*>(m + 32 * op);
+#pragma unroll
+      for (int s = 0; s < 16; s++) {
+        int32_t e0, e1;
+        unpack2(__ldg(e + 8 * s + v), e0, e1);
+        r[2 * s] += e0;
+        r[2 * s + 1] += e1;
+        if (i == K) {  // DecompressMessage, poly.go:134-147: coefficient idx = 16 s + 2 v + b <- bit idx of m
+          const uint32_t word = __ldg(mw + (s >> 1));
+          const uint32_t bits = (word >> (16 * (s & 1) + 2 * v)) & 3;
+          r[2 * s] += (bits & 1) ? ((Q + 1) / 2) << 16 : 0;
+          r[2 * s + 1] += (bits & 2) ? ((Q + 1) / 2) << 16 : 0;
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 32; c++) r[c] = csubq_hi(barrett_hi(r[c]));  // Normalize (cpapke.go:176-177)
+    store_S(tile, v, r);
+    __syncwarp();
+    load_C(tile, v, r);
+    __syncwarp();
+    bad = __any_sync(octmask, bad) ? 1u : 0u;  // after row K this holds the modulus check of the whole key
+    if (active) {
+      if (i < K)
+        compress_store_C<P::du>(r, reinterpret_cast<uint32_t*>(ctp + i * 32 * P::du) + v * P::du);
+      else if (!bad)
+        compress_store_C<P::dv>(r, reinterpret_cast<uint32_t*>(ctp + K * 32 * P::du) + v * P::dv);
+    }
+  }
+  // kem.ErrPubKey (cpapke.go:48-54): no output for a non-canonical key
+  if (active) {
+    if (bad) {
+      uint32_t* c32 = reinterpret_cast<uint32_t*>(ctp);
+      for (int w = v; w < P::ct_bytes / 4; w += 8) c32[w] = 0;
+      if (ss) reinterpret_cast<uint32_t*>(ss + 32 * op)[v] = 0;
+    }
+    if (status && v == 0 && !lenient) status[op] = (uint8_t)bad;
+  }
+}
+
+// the K-PKE.Encrypt launch of the three flows (Encapsulate, the re-encryption of Decapsulate, round-3 Kyber)
+template <int K>
+static int launch_encrypt(const uint8_t* ek, size_t ek_stride, const int16_t* A, int a_shared, const int16_t* noise,
+                          const uint8_t* m, size_t n, uint8_t* ct, uint8_t* ss, uint8_t* status, int lenient,
+                          cudaStream_t st) {
+  if (int arc = ensure_smem_attr((const void*)encrypt_dp_kernel<K>, EncSmem<K>::bytes)) return arc;
+  KernelScope ks(KID_MLKEM_ENCRYPT, st);
+  encrypt_dp_kernel<K><<<(unsigned)((n + 15) / 16), kEncThreads, EncSmem<K>::bytes, st>>>(
+      ek, ek_stride, A, a_shared, noise, m, n, ct, ss, status, (const kyber::TwPair*)ctx().kyber_tw, lenient);
+  return 0;
+}
+
+
 // ------------------------------------------------------------------ 4. Decapsulate
 // Decompress_q(x, d) (poly.go:170-243) of 32 coefficients (C layout) from D words
 template <int D>
@@ -734,12 +966,9 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
       sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
           ek + 384 * K + first * dk_stride, dk_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks, 1, P::n_noise, 4, K);
     }
-    {
-      KernelScope ks(KID_MLKEM_ENCRYPT, ls);
-      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
-          ek + first * dk_stride, dk_stride, A, 0, noise, mprime + 32 * first, cnt, ct2 + first * P::ct_bytes, nullptr,
-          nullptr, tw, 1);
-    }
+    if (int erc = launch_encrypt<K>(ek + first * dk_stride, dk_stride, A, 0, noise, mprime + 32 * first, cnt,
+                                    ct2 + first * P::ct_bytes, nullptr, nullptr, 1, ls))
+      return erc;
   }
   for (int q = 0; q < 2; q++) {
     CB200_CUDA(cudaEventRecord(ws.ev_join[q], ws.lane[q]));
@@ -1043,12 +1272,9 @@ static int r3_encrypt(const uint8_t* ek, size_t ek_stride, const uint8_t* h, siz
       sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
           ek + 384 * K + first * ek_stride, ek_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks, 1, P::n_noise, 4, K);
     }
-    {
-      KernelScope ks(KID_MLKEM_ENCRYPT, ls);
-      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
-          ek + first * ek_stride, ek_stride, A, 0, noise, m + 32 * first, cnt, ct + first * P::ct_bytes, nullptr, nullptr,
-          (const kyber::TwPair*)c.kyber_tw, 1);
-    }
+    if (int erc = launch_encrypt<K>(ek + first * ek_stride, ek_stride, A, 0, noise, m + 32 * first, cnt,
+                                    ct + first * P::ct_bytes, nullptr, nullptr, 1, ls))
+      return erc;
   }
   for (int q = 0; q < 2; q++) {
     CB200_CUDA(cudaEventRecord(ws.ev_join[q], ws.lane[q]));
@@ -1127,9 +1353,14 @@ struct Work {
 };
 
 
+// push_ct / push_ss (optional): where the rows of this call belong in a gather destination -- rank 0's buffer mapped
+// through CUDA IPC, or local memory.  Every sub-batch is copied there as soon as its encrypt kernel has run, by the copy
+// engines on the work set's copy stream, while the next sub-batches compute: the result gather of SURVEY.md 8(e)
+// overlapped inside the flow, with no SM taken from the (ALU-saturated) kernels.
 template <int K>
 static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
-                         uint8_t* status, size_t n, cudaStream_t st, int slot) {
+                         uint8_t* status, size_t n, cudaStream_t st, int slot, uint8_t* push_ct = nullptr,
+                         uint8_t* push_ss = nullptr) {
   using P = Params<K>;
   Dev& c = ctx();
   WorkSet& ws = wset(slot);
@@ -1190,13 +1421,22 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
           ek + 384 * K + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise,
           mat_blocks, 1, P::n_noise, 4, K);
     }
-    {
-      KernelScope ks(KID_MLKEM_ENCRYPT, ls);
-      encrypt_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
-          ek + (shared ? 0 : first * ek_stride), ek_stride, A, shared ? 1 : 0, noise, seeds + 32 * first, cnt,
-          ct + first * P::ct_bytes, ss + 32 * first, status ? status + first : nullptr,
-          (const kyber::TwPair*)c.kyber_tw, 0);
+    if (int erc = launch_encrypt<K>(ek + (shared ? 0 : first * ek_stride), ek_stride, A, shared ? 1 : 0, noise,
+                                    seeds + 32 * first, cnt, ct + first * P::ct_bytes, ss + 32 * first,
+                                    status ? status + first : nullptr, 0, ls))
+      return erc;
+    if (push_ct || push_ss) {
+      CB200_CUDA(cudaEventRecord(ws.ev_copy, ls));
+      CB200_CUDA(cudaStreamWaitEvent(ws.copy, ws.ev_copy, 0));
+      if (push_ct)
+        CB200_CUDA(cudaMemcpyAsync(push_ct + first * P::ct_bytes, ct + first * P::ct_bytes, cnt * (size_t)P::ct_bytes,
+                                   cudaMemcpyDefault, ws.copy));
+      if (push_ss) CB200_CUDA(cudaMemcpyAsync(push_ss + 32 * first, ss + 32 * first, cnt * 32, cudaMemcpyDefault, ws.copy));
     }
+  }
+  if (push_ct || push_ss) {  // the caller's stream covers the pushes too
+    CB200_CUDA(cudaEventRecord(ws.ev_copy, ws.copy));
+    CB200_CUDA(cudaStreamWaitEvent(st, ws.ev_copy, 0));
   }
   for (int q = 0; q < 2; q++) {
     CB200_CUDA(cudaEventRecord(ws.ev_join[q], ws.lane[q]));
@@ -1207,10 +1447,11 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
 }
 
 static int encaps_any(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
-                      uint8_t* status, size_t n, cudaStream_t st, int slot) {
-  return k == 2   ? encaps_device<2>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
-         : k == 3 ? encaps_device<3>(ek, ek_stride, seeds, ct, ss, status, n, st, slot)
-                  : encaps_device<4>(ek, ek_stride, seeds, ct, ss, status, n, st, slot);
+                      uint8_t* status, size_t n, cudaStream_t st, int slot, uint8_t* push_ct = nullptr,
+                      uint8_t* push_ss = nullptr) {
+  return k == 2   ? encaps_device<2>(ek, ek_stride, seeds, ct, ss, status, n, st, slot, push_ct, push_ss)
+         : k == 3 ? encaps_device<3>(ek, ek_stride, seeds, ct, ss, status, n, st, slot, push_ct, push_ss)
+                  : encaps_device<4>(ek, ek_stride, seeds, ct, ss, status, n, st, slot, push_ct, push_ss);
 }
 
 // ------------------------------------------------------------------ 7. the sampler and serialisation surface on its own
@@ -1582,8 +1823,22 @@ int cb200_mlkem_decaps(int k, const uint8_t* dk, size_t dk_stride, const uint8_t
 size_t cb200_mlkem_public_key_size(int k) { return (k >= 2 && k <= 4) ? 384u * k + 32 : 0; }
 size_t cb200_mlkem_ciphertext_size(int k) { return k == 3 ? 1088 : k == 4 ? 1568 : k == 2 ? 768 : 0; }
 
+static int mlkem_encaps_entry(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
+                              uint8_t* status, size_t n, uint8_t* push_ct, uint8_t* push_ss);
 int cb200_mlkem_encaps(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
                        uint8_t* status, size_t n) {
+  return mlkem_encaps_entry(k, ek, ek_stride, seeds, ct, ss, status, n, nullptr, nullptr);
+}
+int cb200_mlkem_encaps_push(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
+                            uint8_t* status, size_t n, uint8_t* push_ct, uint8_t* push_ss) {
+  if (!is_device_ptr(ct)) {
+    set_error("cb200_mlkem_encaps_push: device pointers only (host-pointer calls already end in the caller's buffers)");
+    return CB200_ERR_ARG;
+  }
+  return mlkem_encaps_entry(k, ek, ek_stride, seeds, ct, ss, status, n, push_ct, push_ss);
+}
+static int mlkem_encaps_entry(int k, const uint8_t* ek, size_t ek_stride, const uint8_t* seeds, uint8_t* ct, uint8_t* ss,
+                              uint8_t* status, size_t n, uint8_t* push_ct, uint8_t* push_ss) {
   int rc = require_ready();
   if (rc) return rc;
   if (k < 2 || k > 4) {
@@ -1610,7 +1865,7 @@ int cb200_mlkem_encaps(int k, const uint8_t* ek, size_t ek_stride, const uint8_t
     // status is needed to report kem.ErrPubKey; with device pointers the caller reads it asynchronously
     DeviceCall call(ct);
     if (call.rc) return call.rc;
-    return mlkem::encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, call.st, 3);
+    return mlkem::encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, call.st, 3, push_ct, push_ss);
   }
   // host pointers: one contiguous index range per GPU, each staged through HBM in chunks on three streams
   // (H2D | kernels | D2H overlap); the per-op status always comes back (it carries kem.ErrPubKey)

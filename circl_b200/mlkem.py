@@ -153,7 +153,7 @@ class Scheme:
         ct, ss = self.EncapsulateBatch(pk, np.frombuffer(seed, dtype=np.uint8).reshape(1, 32))
         return ct[0].tobytes(), ss[0].tobytes()
 
-    def EncapsulateBatch(self, pks, seeds, ct=None, ss=None):
+    def EncapsulateBatch(self, pks, seeds, ct=None, ss=None, push=None):
         """Batched EncapsulateDeterministically.
 
         pks:   one PublicKey (shared by all ops), or an (n, PublicKeySize) uint8
@@ -162,6 +162,8 @@ class Scheme:
         seeds: (n, 32) uint8 array or CUDA tensor.
         Returns (ct, ss): (n, CiphertextSize), (n, 32) in the same kind of memory.
         Raises ErrPubKey if any key is not canonical.
+        push:  (ct_ptr, ss_ptr) raw device addresses (CUDA tensors only): the rows are also copied there sub-batch by
+               sub-batch while the batch computes (cb200_mlkem_encaps_push; the gather to rank 0 of circl_b200.shard).
         """
         k, eksz, ctsz = self._k, self.PublicKeySize(), self.CiphertextSize()
         torch_mode = _is_torch(seeds)
@@ -180,8 +182,12 @@ class Scheme:
             ss = torch.empty((n, 32), dtype=torch.uint8, device=seeds.device) if ss is None else ss
             status = torch.zeros((n,), dtype=torch.uint8, device=seeds.device)
             check(lib().cb200_set_stream(torch.cuda.current_stream().cuda_stream))
-            check(self._c_encaps(ek.data_ptr(), stride, seeds.data_ptr(), ct.data_ptr(), ss.data_ptr(),
-                                 status.data_ptr(), n))
+            if push is None:
+                check(self._c_encaps(ek.data_ptr(), stride, seeds.data_ptr(), ct.data_ptr(), ss.data_ptr(),
+                                     status.data_ptr(), n))
+            else:
+                check(lib().cb200_mlkem_encaps_push(self._k, ek.data_ptr(), stride, seeds.data_ptr(), ct.data_ptr(),
+                                                    ss.data_ptr(), status.data_ptr(), n, push[0], push[1]))
             self._last_status = status  # read lazily: the call is asynchronous on the torch stream
             return ct, ss
         seeds = np.ascontiguousarray(seeds, dtype=np.uint8)

@@ -116,6 +116,10 @@ class RowGather:
             else:
                 self._pending.append(dist.isend(t[lo:hi].reshape(-1).contiguous(), dst=0, group=self.group))
 
+    def dst_ptr(self, which: int, lo: int = 0) -> int:
+        """ipc: raw address of this rank's row `lo` of matrix `which` in rank 0's buffer (for cb200_*_push entry points)"""
+        return self.base.value + self._dst_offset(which, self.rank, lo)
+
     def flush(self, any_tensor=None, on_host: bool = False):
         """ipc: make the caller's stream (or the host) wait for this rank's pushes; sendrecv: wait for the requests"""
         if self.transport == "ipc":

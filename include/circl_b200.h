@@ -180,6 +180,13 @@ int cb200_dil_pack_le16(uint8_t *out, const uint32_t *polys, size_t n);
  * (its ct/ss are zeroed).  Returns CB200_ERR_PUBKEY if any op failed. */
 int cb200_mlkem_encaps(int k, const uint8_t *ek, size_t ek_stride, const uint8_t *seeds, uint8_t *ct, uint8_t *ss,
                        uint8_t *status, size_t n);
+/* The same on device pointers, with the result gather of the one-process-per-GPU launch fused into the flow: the rows of
+ * every sub-batch (8192 operations) are also copied to push_ct + i*CiphertextSize / push_ss + i*32 -- typically this
+ * rank's place in rank 0's cb200_gather_alloc buffer, opened with cb200_gather_open -- as soon as they exist, by the
+ * copy engines over NVLink while the following sub-batches compute.  Either may be NULL.  The calling thread's stream
+ * is ordered after the pushes. */
+int cb200_mlkem_encaps_push(int k, const uint8_t *ek, size_t ek_stride, const uint8_t *seeds, uint8_t *ct, uint8_t *ss,
+                            uint8_t *status, size_t n, uint8_t *push_ct, uint8_t *push_ss);
 /* scheme.UnmarshalBinaryPrivateKey + Decapsulate
  *   kem/mlkem/mlkem768/kyber.go:398-407,376-388 -> PrivateKey.Unpack :203-229, DecapsulateTo :144-184
  *   (cpapke DecryptTo cpapke.go:113-130, re-encryption EncryptTo :137-181, implicit rejection with J = SHAKE256(z || ct)).

@@ -239,7 +239,8 @@ def config1_cpu(threads: int):
         ms.append(np.frombuffer(eseed, dtype=np.uint8))
     eks, ms = np.stack(eks), np.stack(ms)
     parsed = oracle.mlkem_parse_keys(3, eks)
-    out = {"ops": 1024, "inputs": "kem/kyber/kat_test.go:48-81 DRBG procedure, counts 0..1023", "unit": "encaps/s"}
+    out = {"ops": 1024, "inputs": "kem/kyber/kat_test.go:48-81 DRBG procedure, counts 0..1023", "unit": "encaps/s",
+           "arm": "generic restatement (oracle/kyber.c); including_unmarshal_avx2 = the same loop on the AVX2 arm"}
     ref = None
     for label, nt in (("1_thread", 1), ("all_threads", threads)):
         best_p = best_u = 1e9
@@ -252,7 +253,14 @@ def config1_cpu(threads: int):
             best_u = min(best_u, time.perf_counter() - t0)
             assert fails == 0 and np.array_equal(ct, ct2) and np.array_equal(ss, ss2)
         ref = (ct, ss)
-        out[label] = {"cores": nt, "pk_pre_parsed": 1024 / best_p, "including_unmarshal": 1024 / best_u}
+        best_a = 1e9
+        for _ in range(3):
+            t0 = time.perf_counter()
+            ct3, ss3, fails = oracle.mlkem_encaps_batch_avx2(3, eks, ms, nthreads=nt)
+            best_a = min(best_a, time.perf_counter() - t0)
+            assert fails == 0 and np.array_equal(ct, ct3) and np.array_equal(ss, ss3)
+        out[label] = {"cores": nt, "pk_pre_parsed": 1024 / best_p, "including_unmarshal": 1024 / best_u,
+                      "including_unmarshal_avx2": 1024 / best_a}
     return out, eks, ms, ref
 
 
@@ -270,19 +278,26 @@ def run_reference(args):
     idx = np.arange(sample) % 1024
     eks = np.ascontiguousarray(keys[idx])
     seeds = op_seeds(0x01, 0, sample)
-    times = []
-    for step in range(args.warmup + args.steps):
+    # Two CPU arms (both C restatements; CIRCL itself is Go and cannot be built here):
+    #   avx2     oracle/kyber_avx2.c  -- CIRCL's real amd64 path: f1600x4AVX2 for matrix A, nttAVX2 / invNttAVX2 / mulHatAVX2
+    #   generic  oracle/kyber.c       -- CIRCL's purego path
+    # The line's `value` (the denominator of the driver's ratio) is the FASTER, AVX2 one.
+    arms = {}
+    for arm, fn in (("avx2", oracle.mlkem_encaps_batch_avx2), ("generic", oracle.mlkem_encaps_batch)):
+        times = []
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            _, _, fails = fn(wl["k"], eks, seeds, nthreads=threads)
+            dt = time.perf_counter() - t0
+            assert fails == 0
+            if step >= args.warmup:
+                times.append(dt)
         t0 = time.perf_counter()
-        _, _, fails = oracle.mlkem_encaps_batch(wl["k"], eks, seeds, nthreads=threads)
-        dt = time.perf_counter() - t0
-        assert fails == 0
-        if step >= args.warmup:
-            times.append(dt)
-    ms = 1e3 * sum(times) / len(times)
+        fn(wl["k"], eks[:1 << 13], seeds[:1 << 13], nthreads=1)
+        arms[arm] = {"ms": 1e3 * sum(times) / len(times), "single_thread": (1 << 13) / (time.perf_counter() - t0)}
+    ms = arms["avx2"]["ms"]
     value = sample / (ms * 1e-3)
-    t0 = time.perf_counter()
-    oracle.mlkem_encaps_batch(wl["k"], eks[:1 << 13], seeds[:1 << 13], nthreads=1)
-    one = (1 << 13) / (time.perf_counter() - t0)
+    one = arms["avx2"]["single_thread"]
     c1, _, _, _ = config1_cpu(threads) if wl["k"] == 3 else (None, None, None, None)
     line = {
         "impl": "reference", "metric": f"{wl['name']} encaps/sec", "value": value, "unit": "encaps/s",
@@ -290,9 +305,14 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int16", "data": "synthetic",
         "config": mlkem_config(wl, n),
         "cpu_baseline": {"value": value, "unit": "encaps/s", "cores": threads, "kind": "port",
-                         "sample": f"{sample} ops per step (first 2^17 of the batch), C restatement of CIRCL's generic "
-                                   "Go path incl. per-op key parse; CIRCL itself is Go and no Go toolchain exists here",
-                         "single_thread": one, "config1": c1},
+                         "sample": f"{sample} ops per step (first 2^17 of the batch) incl. per-op key parse; C restatement "
+                                   "of CIRCL's amd64 fast path (4-way AVX2 Keccak for matrix A, 16-lane AVX2 NTT / InvNTT / "
+                                   "MulHat; oracle/kyber_avx2.c); CIRCL itself is Go and no Go toolchain exists here",
+                         "single_thread": one,
+                         "generic": {"value": sample / (arms["generic"]["ms"] * 1e-3),
+                                     "single_thread": arms["generic"]["single_thread"],
+                                     "what": "C restatement of CIRCL's purego path (oracle/kyber.c), same sample and threads"},
+                         "config1": c1},
         "e2e": {"value": value, "unit": "encaps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -538,10 +558,20 @@ def bench_mlkem(cx: Ctx, wl_key: str, log2n: int, steps: int, warmup: int, with_
         t0 = time.perf_counter()
         oracle.mlkem_encaps_batch(wl["k"], eks_s[:1 << 13], seeds_s[:1 << 13], nthreads=1)
         one = (1 << 13) / (time.perf_counter() - t0)
-        cpu = {"value": sample / dt, "unit": "encaps/s", "cores": threads, "kind": "port",
-               "sample": f"first {sample} ops of the batch, all {threads} host threads; C restatement of CIRCL's "
-                         "generic Go path (no Go toolchain on this image)",
-               "outputs_match_gpu": parity, "single_thread": one}
+        t0 = time.perf_counter()
+        act, ass, af = oracle.mlkem_encaps_batch_avx2(wl["k"], eks_s, seeds_s, nthreads=threads)
+        adt = time.perf_counter() - t0
+        parity &= bool(af == 0 and np.array_equal(act, wct) and np.array_equal(ass, wss))
+        t0 = time.perf_counter()
+        oracle.mlkem_encaps_batch_avx2(wl["k"], eks_s[:1 << 13], seeds_s[:1 << 13], nthreads=1)
+        aone = (1 << 13) / (time.perf_counter() - t0)
+        cpu = {"value": sample / adt, "unit": "encaps/s", "cores": threads, "kind": "port",
+               "sample": f"first {sample} ops of the batch, all {threads} host threads; C restatement of CIRCL's amd64 fast "
+                         "path (AVX2: 4-way Keccak for matrix A, 16-lane NTT / InvNTT / MulHat; oracle/kyber_avx2.c) -- "
+                         "no Go toolchain on this image",
+               "outputs_match_gpu": parity, "single_thread": aone,
+               "generic": {"value": sample / dt, "single_thread": one,
+                           "what": "C restatement of CIRCL's purego path (oracle/kyber.c), same sample and threads"}}
         if wl["k"] == 3:
             # BASELINE configs[0] beside it, and the same 1024 KAT operations through the GPU path
             c1, keks, kms, (kct, kss) = config1_cpu(threads)

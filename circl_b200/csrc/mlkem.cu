@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(128) g_kernel(const uint8_t* __restrict__ m, c
 // address of the next free int16 of this thread's row: every candidate is stored there (clamped to the slack entry
 // behind the row once 256 are in) and only the advance is predicated -- per candidate a shift/mask pair, a min, a
 // compare, one STS and one predicated add, all on 32-bit registers.  Returns the new address (>= end when full).
+template <bool CHECKED>
 __device__ __forceinline__ uint32_t reject_block(const uint64_t (&a)[25], uint32_t wp, uint32_t end) {
 #pragma unroll
   for (int f = 0; f < 112; f++) {
@@ -120,28 +121,45 @@ __device__ __forceinline__ uint32_t reject_block(const uint64_t (&a)[25], uint32
       const uint32_t hi = (uint32_t)(a[(wi + 1) >> 1] >> (32 * ((wi + 1) & 1)));
       d = __funnelshift_r(lo, hi, sh) & 0xfff;
     }
-    asm volatile("st.shared.u16 [%0], %1;" ::"r"(min(wp, end)), "h"((uint16_t)d) : "memory");
+    // the first two blocks hold 224 candidates: they cannot run past the 256-entry row, so only later blocks clamp
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(CHECKED ? min(wp, end) : wp), "h"((uint16_t)d) : "memory");
     wp += (d < (uint32_t)Q) ? 2u : 0u;
   }
   return wp;
 }
 
-// CBD_2 of 128 bytes (sample.go:80-93), written as 256 packed int16
+// CBD_2 of 128 bytes (sample.go:80-93), written as 256 packed int16.  Eight coefficients per 32-bit word t of the
+// PRF output: d = (t & 0x55..) + ((t >> 1) & 0x55..) holds, per nibble j, a_j in its low and b_j in its high two bits, and
+// coefficient j = a_j - b_j.  Bytewise: even coefficients sit in the low nibbles of the four bytes, odd ones in the
+// high nibbles; (0x80 | a) - b never borrows across bytes and ^ 0x80 turns it into the signed byte a - b; one PRMT per
+// output word then widens a byte pair to two int16 (selector bit 3 replicates the sign).  19 instructions per eight
+// coefficients instead of ~55 for the field-by-field form.
+// prmt.b32 with the full selector: bit 3 of a nibble replicates the sign of the selected byte (__byte_perm masks it off)
+__device__ __forceinline__ uint32_t prmt_sx(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ void cbd2_words(uint32_t t, uint32_t (&w)[4]) {
+  const uint32_t d = (t & 0x55555555u) + ((t >> 1) & 0x55555555u);
+  const uint32_t ae = d & 0x03030303u, be = (d >> 2) & 0x03030303u;
+  const uint32_t ao = (d >> 4) & 0x03030303u, bo = (d >> 6) & 0x03030303u;
+  const uint32_t ce = ((ae | 0x80808080u) - be) ^ 0x80808080u;  // signed bytes: coefficients 0, 2, 4, 6
+  const uint32_t co = ((ao | 0x80808080u) - bo) ^ 0x80808080u;  // coefficients 1, 3, 5, 7
+  w[0] = prmt_sx(ce, co, 0xc480);
+  w[1] = prmt_sx(ce, co, 0xd591);
+  w[2] = prmt_sx(ce, co, 0xe6a2);
+  w[3] = prmt_sx(ce, co, 0xf7b3);
+}
 __device__ __forceinline__ void cbd2_store(const uint64_t (&a)[25], int16_t* __restrict__ dst) {
   uint4* out = reinterpret_cast<uint4*>(dst);
 #pragma unroll
   for (int i = 0; i < 16; i++) {
-    const uint64_t t = a[i];
-    uint64_t d = (t & 0x5555555555555555ull) + ((t >> 1) & 0x5555555555555555ull);
-    uint32_t w[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-      const int c0 = (int)((d >> (8 * j)) & 3) - (int)((d >> (8 * j + 2)) & 3);
-      const int c1 = (int)((d >> (8 * j + 4)) & 3) - (int)((d >> (8 * j + 6)) & 3);
-      w[j] = ((uint32_t)c0 & 0xffffu) | ((uint32_t)c1 << 16);
-    }
-    out[2 * i] = make_uint4(w[0], w[1], w[2], w[3]);
-    out[2 * i + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    uint32_t lo[4], hi[4];
+    cbd2_words((uint32_t)a[i], lo);
+    cbd2_words((uint32_t)(a[i] >> 32), hi);
+    out[2 * i] = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+    out[2 * i + 1] = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   }
 }
 
@@ -185,9 +203,14 @@ __device__ __forceinline__ void uniform_stream(uint64_t (&a)[25], uint32_t* row_
   int16_t* row = reinterpret_cast<int16_t*>(row_words);
   uint32_t wp = smem_u32(row);
   const uint32_t wend = wp + 2 * N;
+#pragma unroll 1
+  for (int b = 0; b < 2; b++) {
+    keccak::f1600(a);
+    wp = reject_block<false>(a, wp, wend);
+  }
   do {
     keccak::f1600(a);
-    wp = reject_block(a, wp, wend);
+    wp = reject_block<true>(a, wp, wend);
   } while (wp < wend);
 }
 // One SHAKE256 PRF stream of DeriveNoise (sample.go:31-95): `a` holds the absorbed, padded block seed || nonce
@@ -517,10 +540,10 @@ __global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
 // 32-bit sum p of 2 K products is below 8 . 4096 . q < 2^27, and |montReduce(p)| <= |p| / 2^16 + q / 2 <= q, which is the
 // input bound of the inverse transform's lazy-Barrett schedule (ntt.go:145-150).
 constexpr int kOpPad = 16;  // words between the operand areas of two ops: half-warps (two octets) hit disjoint banks
-template <int K>
+template <int K, int THREADS>
 struct EncSmem {
   static constexpr int op_words = K * 128 * 2 + kOpPad;
-  static constexpr int words = (kEncThreads / 8) * op_words + (kEncThreads / 8) * kyber::kPolyWords + 256;
+  static constexpr int words = (THREADS / 8) * op_words + (THREADS / 8) * kyber::kPolyWords + 256;
   static constexpr int bytes = words * 4;
 };
 
@@ -539,6 +562,33 @@ __device__ __forceinline__ int32_t mont_red_hi(int32_t p) {
   const int32_t m = (int32_t)((uint32_t)p * (kyber::QINV << 16)) >> 16;
   return p - m * Q;
 }
+// Compress_q(x, d) (poly.go:248-328) from ANY representative x of the residue with |x| < 2^15, high-half register:
+// round(x 2^d / q) mod 2^d does not change when a multiple of q is added to x, so x + 10 q in [0, 2^16) is compressed
+// directly -- floor((x' 2^d + 1664) / q) as a 32 x 32 -> 64 multiplication by ceil(2^40 / q), exact below 2^28 -- and the
+// Normalize of cpapke.go:176-177 needs no instruction of its own.  Checked exhaustively against the reference's two
+// constant pairs for every 16-bit x' and d in {4, 5, 10, 11} (tests/test_compress_identity.py).
+template <int D>
+__device__ __forceinline__ uint32_t compress_any(int32_t x_hi) {
+  const uint32_t xp = ((uint32_t)x_hi + ((10u * Q) << 16)) >> 16;
+  const uint32_t v = (xp << D) + Q / 2;
+  return (__umulhi(v, 330282857u) >> 8) & ((1u << D) - 1);
+}
+template <int D>
+__device__ __forceinline__ void compress_any_store_C(const int32_t (&r)[32], uint32_t* __restrict__ dst) {
+  uint64_t acc = 0;
+  int bits = 0, o = 0;
+#pragma unroll
+  for (int i = 0; i < 32; i++) {
+    acc |= (uint64_t)compress_any<D>(r[i]) << bits;
+    bits += D;
+    if (bits >= 32) {
+      dst[o++] = (uint32_t)acc;
+      acc >>= 32;
+      bits -= 32;
+    }
+  }
+}
+
 // 12-bit unpack of 32 coefficients (48 bytes, 16-byte aligned) straight to packed pairs (poly.go:123-129);
 // returns nonzero if any coefficient is >= q (cpapke.go:45-55)
 __device__ __forceinline__ uint32_t unpack12_pairs(const uint8_t* __restrict__ src, uint32_t (&aw)[16]) {
@@ -573,29 +623,58 @@ __device__ __forceinline__ uint32_t unpack12_pairs(const uint8_t* __restrict__ s
   return bad;
 }
 
-template <int K>
-__global__ void __launch_bounds__(kEncThreads, 3) encrypt_dp_kernel(
+// 24 bytes (8-byte aligned) of a 12-bit packed polynomial -> 16 coefficients as 8 packed pairs (poly.go:123-129);
+// returns nonzero if any coefficient is >= q (cpapke.go:45-55)
+__device__ __forceinline__ uint32_t unpack12_half(const uint32_t (&w)[8], uint32_t (&aw)[8]) {
+  uint32_t bad = 0;
+#pragma unroll
+  for (int g = 0; g < 2; g++) {  // 3 words -> 8 coefficients -> 4 pairs
+    const uint32_t a = w[3 * g], b = w[3 * g + 1], c = w[3 * g + 2];
+    uint32_t t[8];
+    t[0] = a & 0xfff;
+    t[1] = (a >> 12) & 0xfff;
+    t[2] = ((a >> 24) | (b << 8)) & 0xfff;
+    t[3] = (b >> 4) & 0xfff;
+    t[4] = (b >> 16) & 0xfff;
+    t[5] = ((b >> 28) | (c << 4)) & 0xfff;
+    t[6] = (c >> 8) & 0xfff;
+    t[7] = c >> 20;
+#pragma unroll
+    for (int j = 0; j < 8; j++) bad |= (t[j] >= (uint32_t)Q);
+#pragma unroll
+    for (int j = 0; j < 4; j++) aw[4 * g + j] = t[2 * j] | (t[2 * j + 1] << 16);
+  }
+  return bad;
+}
+
+// THREADS / 8 operations per CTA.  Small CTAs (64 threads, 8 operations, ~31 KB of shared memory for K = 3) keep 7 CTAs
+// = 14 warps per SM resident; every global load is issued one step before its data is used (register double buffers),
+// because a warp walks 19 dependent load -> compute phases per operation and L2 latency, not the instruction count,
+// was what bounded the first version (ncu: long_scoreboard 1.3 per issue at 12-16 warps per SM).
+template <int K, int THREADS>
+__global__ void __launch_bounds__(THREADS, 448 / THREADS) encrypt_dp_kernel(
     const uint8_t* __restrict__ ek, size_t ek_stride, const int16_t* __restrict__ A, int a_shared,
     const int16_t* __restrict__ noise, const uint8_t* __restrict__ m, size_t n, uint8_t* __restrict__ ct,
     uint8_t* __restrict__ ss, uint8_t* __restrict__ status, const kyber::TwPair* __restrict__ tw, int lenient) {
   // lenient = 1: re-encryption inside Decapsulate (PublicKey.Unpack, cpapke.go:58-63: no modulus check; the
   // Normalize of t-hat is immaterial here because only residues are used)
   using P = Params<K>;
-  using S = EncSmem<K>;
+  using S = EncSmem<K, THREADS>;
   using namespace kyber;
+  constexpr int OCTS = THREADS / 8;
   extern __shared__ __align__(16) uint32_t enc_smem[];
   uint32_t* ops_all = enc_smem;
-  uint32_t* tiles = enc_smem + (kEncThreads / 8) * S::op_words;
-  TwPair* tws = reinterpret_cast<TwPair*>(tiles + (kEncThreads / 8) * kPolyWords);
+  uint32_t* tiles = enc_smem + OCTS * S::op_words;
+  TwPair* tws = reinterpret_cast<TwPair*>(tiles + OCTS * kPolyWords);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
   const unsigned octmask = 0xffu << (8 * oct);
   uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
   uint2* ops = reinterpret_cast<uint2*>(ops_all + (size_t)(warp * 4 + oct) * S::op_words) + v;  // [j][block][lane]
 
-  for (int i = threadIdx.x; i < 128; i += kEncThreads) tws[i] = tw[i];
+  for (int i = threadIdx.x; i < 128; i += THREADS) tws[i] = tw[i];
   __syncthreads();
   const volatile TwPair* tab = tws;
-  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
+  const size_t base = ((size_t)blockIdx.x * (THREADS / 32) + warp) * 4;
   if (base >= n) return;
   const size_t op_raw = base + oct;
   const bool active = op_raw < n;
@@ -607,65 +686,117 @@ __global__ void __launch_bounds__(kEncThreads, 3) encrypt_dp_kernel(
 
   int32_t r[32];
 
-  // operands of rh = BarrettReduce(NTT(r))   (cpapke.go:142-144)
+  // operands of rh = NTT(r) x 512  (cpapke.go:142-144; the reduction is the multiplication)
+  {
+    uint32_t nw[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) nw[q] = ldg_stream32(np + 8 * q + v);
 #pragma unroll 1
-  for (int j = 0; j < K; j++) {
-    gload_S(np + j * (N / 2), v, r);
-    fwd_pass_S(r);
-    store_S(tile, v, r);
-    __syncwarp();
-    load_C(tile, v, r);
-    fwd_pass_C_smem(r, tab, v);
-    __syncwarp();
+    for (int j = 0; j < K; j++) {
 #pragma unroll
-    for (int q = 0; q < 8; q++) {  // quad q of this lane: zeta = Zetas[64 + 8 v + q], +zeta for its first block, -zeta for its second
-      const TwPair z = tw_at(tab, 64 + 8 * v + q);
+      for (int q = 0; q < 16; q++) unpack2(nw[q], r[2 * q], r[2 * q + 1]);
+      if (j + 1 < K) {
 #pragma unroll
-      for (int h = 0; h < 2; h++) {
-        const int blk = 2 * q + h;
-        // x 512 = R / 128: mont_mul by 512 R mod q (|in| <= 7 q, |out| < q)
-        constexpr int32_t kS = (int32_t)((512ull * 65536ull) % Q), kSq = (int32_t)((((uint32_t)kS * QINV) & 0xffffu) << 16);
-        const int32_t b0 = mont_mul_hi(r[2 * blk] >> 16, kS, kSq), b1 = mont_mul_hi(r[2 * blk + 1] >> 16, kS, kSq);
-        int32_t zb1 = mont_mul_hi(b1 >> 16, z.z, z.zq);
-        if (h) zb1 = -zb1;
-        // bytes 2 (low, unsigned) and 3 (high, signed) of the high-half registers
-        ops[(j * 16 + blk) * 8] = make_uint2(__byte_perm((uint32_t)b0, (uint32_t)zb1, 0x7362),
-                                             __byte_perm((uint32_t)b1, (uint32_t)b0, 0x7362));
+        for (int q = 0; q < 16; q++) nw[q] = ldg_stream32(np + (j + 1) * (N / 2) + 8 * q + v);
+      }
+      fwd_pass_S(r);
+      store_S(tile, v, r);
+      __syncwarp();
+      load_C(tile, v, r);
+      fwd_pass_C_smem(r, tab, v);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; q++) {  // quad q of this lane: zeta = Zetas[64 + 8 v + q], +zeta for its first block, -zeta for its second
+        const TwPair z = tw_at(tab, 64 + 8 * v + q);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int blk = 2 * q + h;
+          // x 512 = R / 128: mont_mul by 512 R mod q (|in| <= 7 q, |out| < q)
+          constexpr int32_t kS = (int32_t)((512ull * 65536ull) % Q), kSq = (int32_t)((((uint32_t)kS * QINV) & 0xffffu) << 16);
+          const int32_t b0 = mont_mul_hi(r[2 * blk] >> 16, kS, kSq), b1 = mont_mul_hi(r[2 * blk + 1] >> 16, kS, kSq);
+          int32_t zb1 = mont_mul_hi(b1 >> 16, z.z, z.zq);
+          if (h) zb1 = -zb1;
+          // bytes 2 (low, unsigned) and 3 (high, signed) of the high-half registers
+          ops[(j * 16 + blk) * 8] = make_uint2(__byte_perm((uint32_t)b0, (uint32_t)zb1, 0x7362),
+                                               __byte_perm((uint32_t)b1, (uint32_t)b0, 0x7362));
+        }
       }
     }
   }
   __syncwarp();
 
-  // u[i] = InvNTT(A^T[i] . rh) + e1[i]; v = InvNTT(t . rh) + e2 + m
+  // u[i] = InvNTT(A^T[i] . rh) + e1[i]; v = InvNTT(t . rh) + e2 + m.  A row is accumulated in two halves of eight
+  // blocks (32 accumulators); step (i, h, j) loads the eight words of step + 1 before it multiplies its own.
+  auto fetch = [&](int i, int h, int j, uint32_t (&raw)[8]) {
+    if (i < K) {
+      const uint4* p = reinterpret_cast<const uint4*>(Ap + (i * K + j) * (N / 2) + 16 * v + 8 * h);
+      const uint4 x = __ldg(p), y = __ldg(p + 1);
+      raw[0] = x.x, raw[1] = x.y, raw[2] = x.z, raw[3] = x.w, raw[4] = y.x, raw[5] = y.y, raw[6] = y.z, raw[7] = y.w;
+    } else {  // row K: t-hat from the encapsulation key, PolyDotHat(&v, &pk.th, &rh) (cpapke.go:167)
+      const uint2* p = reinterpret_cast<const uint2*>(ekp + 384 * j + 48 * v + 24 * h);
+      const uint2 x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+      raw[0] = x.x, raw[1] = x.y, raw[2] = y.x, raw[3] = y.y, raw[4] = z.x, raw[5] = z.y;
+    }
+  };
   uint32_t bad = 0;
+  uint32_t raw[8];
+  fetch(0, 0, 0, raw);
 #pragma unroll 1
   for (int i = 0; i <= K; i++) {
-    int32_t p0l[16], p0h[16], p1l[16], p1h[16];
-#pragma unroll
-    for (int c = 0; c < 16; c++) p0l[c] = p0h[c] = p1l[c] = p1h[c] = 0;
+    uint32_t ew[16];
 #pragma unroll 1
-    for (int j = 0; j < K; j++) {
-      uint32_t aw[16];
-      if (i < K) {
-        load_words_C(Ap + (i * K + j) * (N / 2), v, aw);
-      } else {  // row K: t-hat from the encapsulation key, PolyDotHat(&v, &pk.th, &rh) (cpapke.go:167)
-        const uint32_t b = unpack12_pairs(ekp + 384 * j + 48 * v, aw);
-        if (!lenient) bad |= b;
-      }
-      const uint2* oj = ops + (size_t)j * 16 * 8;
+    for (int h = 0; h < 2; h++) {
+      int32_t p0l[8], p0h[8], p1l[8], p1h[8];
 #pragma unroll
-      for (int c = 0; c < 16; c++) {
-        const uint2 w = oj[c * 8];
-        p0l[c] = (int32_t)dp2a_lo_uu(aw[c], w.x, (uint32_t)p0l[c]);
-        p0h[c] = dp2a_hi_us(aw[c], w.x, p0h[c]);
-        p1l[c] = (int32_t)dp2a_lo_uu(aw[c], w.y, (uint32_t)p1l[c]);
-        p1h[c] = dp2a_hi_us(aw[c], w.y, p1h[c]);
-      }
-    }
+      for (int c = 0; c < 8; c++) p0l[c] = p0h[c] = p1l[c] = p1h[c] = 0;
+#pragma unroll 1
+      for (int j = 0; j < K; j++) {
+        uint32_t aw[8];
+        if (i < K) {
 #pragma unroll
-    for (int c = 0; c < 16; c++) {
-      r[2 * c] = mont_red_hi(p0l[c] + p0h[c] * 256);
-      r[2 * c + 1] = mont_red_hi(p1l[c] + p1h[c] * 256);
+          for (int c = 0; c < 8; c++) aw[c] = raw[c];
+        } else {
+          const uint32_t b = unpack12_half(raw, aw);
+          if (!lenient) bad |= b;
+        }
+        {  // the words of the next step
+          int ni = i, nh = h, nj = j + 1;
+          if (nj == K) {
+            nj = 0;
+            if (++nh == 2) {
+              nh = 0;
+              ni++;
+            }
+          }
+          if (ni <= K) fetch(ni, nh, nj, raw);
+        }
+        const uint2* oj = ops + (size_t)(j * 16 + 8 * h) * 8;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const uint2 w = oj[c * 8];
+          p0l[c] = (int32_t)dp2a_lo_uu(aw[c], w.x, (uint32_t)p0l[c]);
+          p0h[c] = dp2a_hi_us(aw[c], w.x, p0h[c]);
+          p1l[c] = (int32_t)dp2a_lo_uu(aw[c], w.y, (uint32_t)p1l[c]);
+          p1h[c] = dp2a_hi_us(aw[c], w.y, p1h[c]);
+        }
+      }
+      if (h == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          r[2 * c] = mont_red_hi(p0l[c] + p0h[c] * 256);
+          r[2 * c + 1] = mont_red_hi(p1l[c] + p1h[c] * 256);
+        }
+        // the noise polynomial this row ends with: in flight during the second half and the inverse transform
+        const uint32_t* e = np + (K + i) * (N / 2);
+#pragma unroll
+        for (int q = 0; q < 16; q++) ew[q] = __ldg(e + 8 * q + v);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          r[16 + 2 * c] = mont_red_hi(p0l[c] + p0h[c] * 256);
+          r[16 + 2 * c + 1] = mont_red_hi(p1l[c] + p1h[c] * 256);
+        }
+      }
     }
     inv_pass_C_smem(r, tab, v);
     store_C(tile, v, r);
@@ -673,13 +804,14 @@ __global__ void __launch_bounds__(kEncThreads, 3) encrypt_dp_kernel(
     load_S(tile, v, r);
     inv_pass_S<false>(r, v);
     __syncwarp();
+    // before the constant the reference bounds the values by 9 q (ntt.go:187-190), so adding e (<= 2) and the message
+    // term (1665) stays inside the int16 range of the high-half registers
     {  // + e1[i] / + e2 (+ Decompress_q(m, 1)), S layout
-      const uint32_t* e = np + (K + i) * (N / 2);
       const uint32_t* mw = reinterpret_cast<const uint32_t*>(m + 32 * op);
 #pragma unroll
       for (int s = 0; s < 16; s++) {
         int32_t e0, e1;
-        unpack2(__ldg(e + 8 * s + v), e0, e1);
+        unpack2(ew[s], e0, e1);
         r[2 * s] += e0;
         r[2 * s + 1] += e1;
         if (i == K) {  // DecompressMessage, poly.go:134-147: coefficient idx = 16 s + 2 v + b <- bit idx of m
@@ -690,18 +822,16 @@ __global__ void __launch_bounds__(kEncThreads, 3) encrypt_dp_kernel(
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < 32; c++) r[c] = csubq_hi(barrett_hi(r[c]));  // Normalize (cpapke.go:176-177)
-    store_S(tile, v, r);
+    store_S(tile, v, r);  // Normalize (cpapke.go:176-177) is absorbed by compress_any
     __syncwarp();
     load_C(tile, v, r);
     __syncwarp();
     bad = __any_sync(octmask, bad) ? 1u : 0u;  // after row K this holds the modulus check of the whole key
     if (active) {
       if (i < K)
-        compress_store_C<P::du>(r, reinterpret_cast<uint32_t*>(ctp + i * 32 * P::du) + v * P::du);
+        compress_any_store_C<P::du>(r, reinterpret_cast<uint32_t*>(ctp + i * 32 * P::du) + v * P::du);
       else if (!bad)
-        compress_store_C<P::dv>(r, reinterpret_cast<uint32_t*>(ctp + K * 32 * P::du) + v * P::dv);
+        compress_any_store_C<P::dv>(r, reinterpret_cast<uint32_t*>(ctp + K * 32 * P::du) + v * P::dv);
     }
   }
   // kem.ErrPubKey (cpapke.go:48-54): no output for a non-canonical key
@@ -716,13 +846,16 @@ __global__ void __launch_bounds__(kEncThreads, 3) encrypt_dp_kernel(
 }
 
 // the K-PKE.Encrypt launch of the three flows (Encapsulate, the re-encryption of Decapsulate, round-3 Kyber)
+constexpr int kEncDpThreads = 64;
 template <int K>
 static int launch_encrypt(const uint8_t* ek, size_t ek_stride, const int16_t* A, int a_shared, const int16_t* noise,
                           const uint8_t* m, size_t n, uint8_t* ct, uint8_t* ss, uint8_t* status, int lenient,
                           cudaStream_t st) {
-  if (int arc = ensure_smem_attr((const void*)encrypt_dp_kernel<K>, EncSmem<K>::bytes)) return arc;
+  using S = EncSmem<K, kEncDpThreads>;
+  if (int arc = ensure_smem_attr((const void*)encrypt_dp_kernel<K, kEncDpThreads>, S::bytes)) return arc;
   KernelScope ks(KID_MLKEM_ENCRYPT, st);
-  encrypt_dp_kernel<K><<<(unsigned)((n + 15) / 16), kEncThreads, EncSmem<K>::bytes, st>>>(
+  constexpr int per_cta = kEncDpThreads / 8;
+  encrypt_dp_kernel<K, kEncDpThreads><<<(unsigned)((n + per_cta - 1) / per_cta), kEncDpThreads, S::bytes, st>>>(
       ek, ek_stride, A, a_shared, noise, m, n, ct, ss, status, (const kyber::TwPair*)ctx().kyber_tw, lenient);
   return 0;
 }

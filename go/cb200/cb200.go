@@ -17,6 +17,7 @@ import "C"
 
 import (
 	"errors"
+	"runtime"
 	"sync"
 	"unsafe"
 )
@@ -31,16 +32,31 @@ var (
 var initOnce sync.Once
 var initErr error
 
-// Init binds the process to one GPU.  One process per GPU; safe to call many times.
-func Init(device int) error {
+// Init drives every visible GPU from this process (cb200_init_devices(0)): host-slice batches are cut into one
+// contiguous index range per GPU inside the library and the results land in the caller's slices in index order, so a
+// kem.Scheme / sign.Scheme caller never sees devices.  Safe to call many times and from any goroutine.
+func Init() error { return InitDevices(0) }
+
+// InitDevices restricts the library to GPUs 0..ndev-1 (ndev <= 0: all).
+func InitDevices(ndev int) error {
 	initOnce.Do(func() {
-		if rc := C.cb200_init(C.int(device)); rc != 0 {
-			initErr = errors.New(C.GoString(C.cb200_last_error()))
-		}
+		initErr = call(func() C.int { return C.cb200_init_devices(C.int(ndev)) })
 	})
 	return initErr
 }
 
+// ActiveDevices reports how many GPUs the library drives (0 before Init).
+func ActiveDevices() int { return int(C.cb200_active_devices()) }
+
+// call runs one C entry point and turns its return code into an error.  cb200_last_error() is per OS thread and a
+// goroutine may migrate between two cgo calls, so the call and the error fetch are pinned to one thread.
+func call(f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	return lastErr(f())
+}
+
+// lastErr must run on the OS thread that made the failing call (see call).
 func lastErr(rc C.int) error {
 	switch rc {
 	case 0:
@@ -69,7 +85,9 @@ func KyberNTT(polys [][256]int16, inverse bool) error {
 	if inverse {
 		inv = 1
 	}
-	return lastErr(C.cb200_kyber_ntt((*C.int16_t)(unsafe.Pointer(&polys[0])), C.size_t(len(polys)), inv))
+	return call(func() C.int {
+		return C.cb200_kyber_ntt((*C.int16_t)(unsafe.Pointer(&polys[0])), C.size_t(len(polys)), inv)
+	})
 }
 
 // KyberMulHat: p[i] = a[i] (*) b[i]  (mulHatAVX2, stubs_amd64.go:17).
@@ -80,8 +98,10 @@ func KyberMulHat(p, a, b [][256]int16) error {
 	if len(p) == 0 {
 		return nil
 	}
-	return lastErr(C.cb200_kyber_mulhat((*C.int16_t)(unsafe.Pointer(&p[0])), (*C.int16_t)(unsafe.Pointer(&a[0])),
-		(*C.int16_t)(unsafe.Pointer(&b[0])), C.size_t(len(p))))
+	return call(func() C.int {
+		return C.cb200_kyber_mulhat((*C.int16_t)(unsafe.Pointer(&p[0])), (*C.int16_t)(unsafe.Pointer(&a[0])),
+		(*C.int16_t)(unsafe.Pointer(&b[0])), C.size_t(len(p)))
+	})
 }
 
 // DilithiumNTT: (*Poly).NTT / InvNTT of sign/internal/dilithium over a batch, in place.
@@ -93,7 +113,9 @@ func DilithiumNTT(polys [][256]uint32, inverse bool) error {
 	if inverse {
 		inv = 1
 	}
-	return lastErr(C.cb200_dil_ntt((*C.uint32_t)(unsafe.Pointer(&polys[0])), C.size_t(len(polys)), inv))
+	return call(func() C.int {
+		return C.cb200_dil_ntt((*C.uint32_t)(unsafe.Pointer(&polys[0])), C.size_t(len(polys)), inv)
+	})
 }
 
 // MLKEMEncaps: batched UnmarshalBinaryPublicKey + EncapsulateDeterministically.
@@ -118,9 +140,11 @@ func MLKEMEncaps(k int, ek []byte, shared bool, seeds, ct, ss []byte) error {
 	if n == 0 {
 		return nil
 	}
-	return lastErr(C.cb200_mlkem_encaps(C.int(k), (*C.uint8_t)(unsafe.Pointer(&ek[0])), stride,
+	return call(func() C.int {
+		return C.cb200_mlkem_encaps(C.int(k), (*C.uint8_t)(unsafe.Pointer(&ek[0])), stride,
 		(*C.uint8_t)(unsafe.Pointer(&seeds[0])), (*C.uint8_t)(unsafe.Pointer(&ct[0])),
-		(*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n)))
+		(*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n))
+	})
 }
 
 // MLKEMDecaps: batched UnmarshalBinaryPrivateKey + Decapsulate (implicit rejection included).
@@ -138,8 +162,10 @@ func MLKEMDecaps(k int, dk []byte, shared bool, ct, ss []byte) error {
 	if n == 0 {
 		return nil
 	}
-	return lastErr(C.cb200_mlkem_decaps(C.int(k), (*C.uint8_t)(unsafe.Pointer(&dk[0])), stride,
-		(*C.uint8_t)(unsafe.Pointer(&ct[0])), (*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n)))
+	return call(func() C.int {
+		return C.cb200_mlkem_decaps(C.int(k), (*C.uint8_t)(unsafe.Pointer(&dk[0])), stride,
+		(*C.uint8_t)(unsafe.Pointer(&ct[0])), (*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n))
+	})
 }
 
 // MLDSA65Sign signs len(msgs) messages.  sk holds one packed 4032-byte key (shared) or one per message.
@@ -172,9 +198,11 @@ func MLDSA65Sign(sk []byte, shared bool, msgs [][]byte, ctx, rnd, sig []byte) er
 	if rnd != nil {
 		prnd = (*C.uint8_t)(unsafe.Pointer(&rnd[0]))
 	}
-	return lastErr(C.cb200_mldsa65_sign((*C.uint8_t)(unsafe.Pointer(&sk[0])), stride,
+	return call(func() C.int {
+		return C.cb200_mldsa65_sign((*C.uint8_t)(unsafe.Pointer(&sk[0])), stride,
 		(*C.uint8_t)(unsafe.Pointer(&blob[0])), (*C.uint64_t)(unsafe.Pointer(&off[0])), pctx, C.size_t(len(ctx)),
-		prnd, (*C.uint8_t)(unsafe.Pointer(&sig[0])), nil, C.size_t(n), 0, nil))
+		prnd, (*C.uint8_t)(unsafe.Pointer(&sig[0])), nil, C.size_t(n), 0, nil)
+	})
 }
 
 // Hybrid scheme identifiers of include/circl_b200.h (kem/hybrid/hybrid.go:34-62).
@@ -199,15 +227,19 @@ func X25519Batch(scalars, points, out []byte, ok []bool) error {
 	if points != nil {
 		pp = (*C.uint8_t)(unsafe.Pointer(&points[0]))
 	}
-	rc := C.cb200_x25519((*C.uint8_t)(unsafe.Pointer(&scalars[0])), pp, (*C.uint8_t)(unsafe.Pointer(&out[0])),
-		(*C.uint8_t)(unsafe.Pointer(&status[0])), C.size_t(n))
+	var rc C.int
+	err := call(func() C.int {
+		rc = C.cb200_x25519((*C.uint8_t)(unsafe.Pointer(&scalars[0])), pp, (*C.uint8_t)(unsafe.Pointer(&out[0])),
+			(*C.uint8_t)(unsafe.Pointer(&status[0])), C.size_t(n))
+		if rc == C.CB200_ERR_PUBKEY { // reported per operation through ok, like the bool of x25519.Shared
+			return 0
+		}
+		return rc
+	})
 	for i := range ok {
 		ok[i] = status[i] == 0
 	}
-	if rc == C.CB200_ERR_PUBKEY { // reported per operation through ok, like the bool of x25519.Shared
-		return nil
-	}
-	return lastErr(rc)
+	return err
 }
 
 // XWingEncaps: batched xwing.Encapsulate (kem/xwing/xwing.go:173-182).  pk: one packed 1216-byte key (shared) or n keys;
@@ -224,8 +256,10 @@ func XWingEncaps(pk []byte, shared bool, seeds, ct, ss []byte) error {
 	if n == 0 {
 		return nil
 	}
-	return lastErr(C.cb200_xwing_encaps((*C.uint8_t)(unsafe.Pointer(&pk[0])), stride, (*C.uint8_t)(unsafe.Pointer(&seeds[0])),
-		(*C.uint8_t)(unsafe.Pointer(&ct[0])), (*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n)))
+	return call(func() C.int {
+		return C.cb200_xwing_encaps((*C.uint8_t)(unsafe.Pointer(&pk[0])), stride, (*C.uint8_t)(unsafe.Pointer(&seeds[0])),
+		(*C.uint8_t)(unsafe.Pointer(&ct[0])), (*C.uint8_t)(unsafe.Pointer(&ss[0])), nil, C.size_t(n))
+	})
 }
 
 // HybridEncaps: batched hybrid.scheme.EncapsulateDeterministically (kem/hybrid/hybrid.go:233-261); id is one of the
@@ -244,17 +278,58 @@ func HybridEncaps(id int, pk []byte, shared bool, seeds, ct, ss []byte) error {
 	if n == 0 {
 		return nil
 	}
-	return lastErr(C.cb200_hybrid_encaps(C.int(id), (*C.uint8_t)(unsafe.Pointer(&pk[0])), stride,
+	return call(func() C.int {
+		return C.cb200_hybrid_encaps(C.int(id), (*C.uint8_t)(unsafe.Pointer(&pk[0])), stride,
 		(*C.uint8_t)(unsafe.Pointer(&seeds[0])), (*C.uint8_t)(unsafe.Pointer(&ct[0])), (*C.uint8_t)(unsafe.Pointer(&ss[0])),
-		nil, C.size_t(n)))
+		nil, C.size_t(n))
+	})
 }
 
 // PinnedBytes returns a Go slice over cudaHostAlloc'd memory: large batches should live
 // here so that host<->device copies run at full PCIe speed and overlap with the kernels.
 func PinnedBytes(n int) ([]byte, func()) {
+	runtime.LockOSThread()
 	p := C.cb200_host_alloc(C.size_t(n))
 	if p == nil {
-		panic(C.GoString(C.cb200_last_error()))
+		msg := C.GoString(C.cb200_last_error())
+		runtime.UnlockOSThread()
+		panic(msg)
 	}
+	runtime.UnlockOSThread()
 	return unsafe.Slice((*byte)(p), n), func() { C.cb200_host_free(p) }
+}
+
+// KeccakF1600 permutes every 25-lane state in place: the batched counterpart of (*keccakf1600.StateX4).Permute
+// (simd/keccakf1600/f1600x.go:115-121); turbo selects the 12-round variant.
+func KeccakF1600(states [][25]uint64, turbo bool) error {
+	if len(states) == 0 {
+		return nil
+	}
+	t := C.int(0)
+	if turbo {
+		t = 1
+	}
+	return call(func() C.int {
+		return C.cb200_keccak_f1600((*C.uint64_t)(unsafe.Pointer(&states[0])), C.size_t(len(states)), t)
+	})
+}
+
+// KyberDeriveUniform: (*Poly).DeriveUniform (pke/kyber/internal/common/sample.go:192-236) for len(polys) (seed, x, y)
+// triples; seeds holds one 32-byte seed (shared) or one per polynomial, xy two bytes per polynomial.
+func KyberDeriveUniform(polys [][256]int16, seeds []byte, xy []byte) error {
+	n := len(polys)
+	if len(xy) != 2*n || (len(seeds) != 32 && len(seeds) != 32*n) {
+		panic("cb200: KyberDeriveUniform buffers have the wrong length")
+	}
+	if n == 0 {
+		return nil
+	}
+	stride := C.size_t(32)
+	if len(seeds) == 32 {
+		stride = 0
+	}
+	return call(func() C.int {
+		return C.cb200_kyber_derive_uniform((*C.int16_t)(unsafe.Pointer(&polys[0])), (*C.uint8_t)(unsafe.Pointer(&seeds[0])),
+			stride, (*C.uint8_t)(unsafe.Pointer(&xy[0])), C.size_t(n))
+	})
 }

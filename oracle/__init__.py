@@ -261,6 +261,27 @@ def mlkem_encaps_batch(k: int, ek: np.ndarray, m: np.ndarray, nthreads: int = 1)
     return ct, ss, fails
 
 
+def mlkem_encaps_batch_avx2(k: int, ek: np.ndarray, m: np.ndarray, nthreads: int = 1):
+    """The AVX2 arm (kyber_avx2.c): same contract and same bytes as mlkem_encaps_batch."""
+    _, _, ctsz = mlkem_sizes(k)
+    n = m.shape[0]
+    ek = np.ascontiguousarray(ek, dtype=np.uint8)
+    ct = np.empty((n, ctsz), dtype=np.uint8)
+    ss = np.empty((n, 32), dtype=np.uint8)
+    L = lib()
+    L.orc_mlkem_encaps_batch_avx2.restype = C.c_int
+    fails = L.orc_mlkem_encaps_batch_avx2(C.c_int(k), _ptr(ct), _ptr(ss), _ptr(ek), C.c_size_t(ek.shape[1] if ek.ndim == 2 else 0),
+                                          _ptr(np.ascontiguousarray(m)), C.c_size_t(n), C.c_int(nthreads))
+    return ct, ss, int(fails)
+
+
+def keccak_f1600_x4(states4x25) -> np.ndarray:
+    """Four states (4, 25) uint64 -> permuted, through the interleaved StateX4 layout."""
+    a = np.ascontiguousarray(np.asarray(states4x25, dtype=np.uint64).T.reshape(100))
+    lib().orc_keccak_f1600_x4(_ptr(a))
+    return a.reshape(25, 4).T.copy()
+
+
 def mlkem_parse_keys(k: int, ek: np.ndarray) -> np.ndarray:
     """UnmarshalBinaryPublicKey for every row of ek: the cached fields (th, aT, hpk) of each key, (n, parsed_size) uint8."""
     L = lib()

@@ -106,6 +106,16 @@ void orc_mlkem_encaps_parsed_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_
 int orc_mlkem_encaps_batch(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, size_t ek_stride,
                            const uint8_t *m, size_t n, int nthreads);
 
+/* ---- kyber_avx2.c: the reference's amd64 fast path restated with intrinsics (second CPU arm of bench.py) ----
+ * f1600x4AVX2 (simd/keccakf1600/f1600x4_amd64.s:9), nttAVX2 / invNttAVX2 / mulHatAVX2 (pke/kyber/internal/common/amd64.s) */
+void orc_keccak_f1600_x4(uint64_t *a /* 100 words: lane i of instance j at a[4 i + j] */);
+void orc_kyber_ntt_avx2(int16_t p[256]);      /* == orc_kyber_ntt, coefficient for coefficient */
+void orc_kyber_invntt_avx2(int16_t p[256]);   /* == orc_kyber_invntt modulo q (other lazy-reduction points) */
+void orc_kyber_mulhat_avx2(int16_t p[256], const int16_t a[256], const int16_t b[256]); /* == orc_kyber_mulhat */
+int orc_mlkem_encaps_avx2(int k, uint8_t *ct, uint8_t ss[32], const uint8_t *ek, const uint8_t m[32]);
+int orc_mlkem_encaps_batch_avx2(int k, uint8_t *ct, uint8_t *ss, const uint8_t *ek, size_t ek_stride, const uint8_t *m,
+                                size_t n, int nthreads);
+
 /* ---------------- Dilithium / ML-DSA-65 (q = 8380417) ---------------- */
 #define ORC_MLDSA65_PK 1952
 #define ORC_MLDSA65_SK 4032

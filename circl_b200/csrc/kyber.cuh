@@ -103,6 +103,13 @@ __device__ __forceinline__ void unpack2(uint32_t w, int32_t& lo, int32_t& hi) {
   lo = (int32_t)(w << 16);
   hi = (int32_t)(w & 0xffff0000u);
 }
+// The same for values that only go through Cooley-Tukey butterflies, Barrett steps and pack2: there the low half of a
+// register is never read (b >> 16), and a +- t with a clean t neither carries into nor borrows from the high half,
+// so the upper coefficient may keep the lower one as garbage in its low half -- one LOP3 less per word.
+__device__ __forceinline__ void unpack2_ct(uint32_t w, int32_t& lo, int32_t& hi) {
+  lo = (int32_t)(w << 16);
+  hi = (int32_t)w;
+}
 __device__ __forceinline__ uint32_t pack2(int32_t lo, int32_t hi) {
   return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x7632);
 }
@@ -329,6 +336,18 @@ __device__ __forceinline__ void store_C(uint32_t* tile, int v, const int32_t (&r
   for (int c = 0; c < 4; c++)
     p[c] = make_uint4(pack2(r[8 * c], r[8 * c + 1]), pack2(r[8 * c + 2], r[8 * c + 3]), pack2(r[8 * c + 4], r[8 * c + 5]),
                       pack2(r[8 * c + 6], r[8 * c + 7]));
+}
+// load_C for the forward transform (see unpack2_ct)
+__device__ __forceinline__ void load_C_ct(const uint32_t* tile, int v, int32_t (&r)[32]) {
+  const uint4* p = reinterpret_cast<const uint4*>(tile + 16 * v + 4 * (v >> 1));
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    uint4 w = p[c];
+    unpack2_ct(w.x, r[8 * c], r[8 * c + 1]);
+    unpack2_ct(w.y, r[8 * c + 2], r[8 * c + 3]);
+    unpack2_ct(w.z, r[8 * c + 4], r[8 * c + 5]);
+    unpack2_ct(w.w, r[8 * c + 6], r[8 * c + 7]);
+  }
 }
 __device__ __forceinline__ void load_C(const uint32_t* tile, int v, int32_t (&r)[32]) {
   const uint4* p = reinterpret_cast<const uint4*>(tile + 16 * v + 4 * (v >> 1));

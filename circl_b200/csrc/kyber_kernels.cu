@@ -171,12 +171,12 @@ __global__ void __launch_bounds__(kThreads, 6) ntt_fwd_tma_kernel(uint32_t* __re
     mbar_wait(obar + (it & 1), (uint32_t)((it >> 1) & 1));
     int32_t r[32];
 #pragma unroll
-    for (int s = 0; s < 16; s++) unpack2(slot[8 * s + v], r[2 * s], r[2 * s + 1]);
+    for (int s = 0; s < 16; s++) unpack2_ct(slot[8 * s + v], r[2 * s], r[2 * s + 1]);
     __syncwarp();  // the raw polynomial is in registers: the slot becomes the transposition tile
     fwd_pass_S(r);
     store_S(slot, v, r);
     __syncwarp();
-    load_C(slot, v, r);
+    load_C_ct(slot, v, r);
     __syncwarp();  // every lane is done with the tile: it may be refilled
     if (v == 0 && it + 2 < n_it) {
       fence_proxy_async();  // order the generic-proxy accesses above before the asynchronous write into the slot

@@ -15,6 +15,7 @@
 //   2. sample_kernel  one thread per Keccak stream: K*K SHAKE128 matrix streams per key,
 //                     2K+1 SHAKE256 noise streams per op (warps are stream-homogeneous)
 //   3. encrypt_kernel one octet (8 lanes) per op: NTT(r), A^T o r, t o r, InvNTT, +e, compress
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -164,6 +165,7 @@ __device__ __forceinline__ void cbd2_store(const uint64_t (&a)[25], int16_t* __r
 }
 
 // sub-batch size: A^T + noise of one sub-batch (8 KiB / op for K=3, 12.5 KiB for K=4) stay L2-resident
+// (measured on a B200, profiles/r02_sweeps.txt: 8192 and 12288 are equally fast, 6144 is 1 % and 4096 is 7 % slower)
 constexpr size_t kSub = 8192;
 constexpr int kRowWords = 129;  // 256 int16 + 2 slack, odd word stride
 constexpr int kSampleSmem = 128 * kRowWords * 4;
@@ -395,133 +397,12 @@ __device__ __forceinline__ void load_words_C(const uint32_t* __restrict__ poly, 
   }
 }
 
-constexpr int kEncThreads = 128;  // 16 octets = 16 operations per CTA
+constexpr int kEncThreads = 128;  // 16 octets = 16 operations per CTA (decrypt / keygen kernels)
 
-template <int K>
-__global__ void __launch_bounds__(kEncThreads) encrypt_kernel(
-    const uint8_t* __restrict__ ek, size_t ek_stride, const int16_t* __restrict__ A, int a_shared,
-    const int16_t* __restrict__ noise, const uint8_t* __restrict__ m, size_t n, uint8_t* __restrict__ ct,
-    uint8_t* __restrict__ ss, uint8_t* __restrict__ status, const kyber::TwPair* __restrict__ tw, int lenient) {
-  // lenient = 1: re-encryption inside Decapsulate, where the key embedded in dk goes through
-  // PublicKey.Unpack (cpapke.go:58-63): t-hat is Normalized and there is no modulus check.
-  using P = Params<K>;
-  using namespace kyber;
-  __shared__ __align__(16) uint32_t tiles[(kEncThreads / 8) * kPolyWords];
-  __shared__ uint32_t rh_store[(kEncThreads / 8) * K * 128];  // NTT(r), lane-private words [oct][j][w][v]
-  __shared__ __align__(16) TwPair tws[128];                    // twiddle table, read at the point of use
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
-  const unsigned octmask = 0xffu << (8 * oct);
-  uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
-  uint32_t* rh = rh_store + (size_t)(warp * 4 + oct) * K * 128 + v;
-
-  for (int i = threadIdx.x; i < 128; i += kEncThreads) tws[i] = tw[i];
-  __syncthreads();
-  const volatile TwPair* tab = tws;
-  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
-  if (base >= n) return;
-  const size_t op_raw = base + oct;
-  const bool active = op_raw < n;
-  const size_t op = active ? op_raw : n - 1;
-  const uint8_t* ekp = ek + op * ek_stride;
-  const uint32_t* Ap = reinterpret_cast<const uint32_t*>(A) + (a_shared ? 0 : op * K * K * (N / 2));
-  const uint32_t* np = reinterpret_cast<const uint32_t*>(noise) + op * P::n_noise * (N / 2);
-  uint8_t* ctp = ct + op * P::ct_bytes;
-
-  int32_t r[32];
-
-  // rh = BarrettReduce(NTT(r))   (cpapke.go:142-144)
-#pragma unroll 1
-  for (int j = 0; j < K; j++) {
-    gload_S(np + j * (N / 2), v, r);
-    fwd_pass_S(r);
-    store_S(tile, v, r);
-    __syncwarp();
-    load_C(tile, v, r);
-    fwd_pass_C_smem(r, tab, v);
-    __syncwarp();
-#pragma unroll
-    for (int w = 0; w < 16; w++) rh[(j * 16 + w) * 8] = pack2(barrett_hi(r[2 * w]), barrett_hi(r[2 * w + 1]));
-  }
-
-  // u[i] = InvNTT(BarrettReduce(A^T[i] . rh)) + e1[i]; v = InvNTT(BarrettReduce(t . rh)) + e2 + m
-  uint32_t bad = 0;
-#pragma unroll 1
-  for (int i = 0; i <= K; i++) {
-#pragma unroll
-    for (int c = 0; c < 32; c++) r[c] = 0;
-#pragma unroll 1
-    for (int j = 0; j < K; j++) {
-      uint32_t aw[16];
-      if (i < K) {
-        load_words_C(Ap + (i * K + j) * (N / 2), v, aw);
-      } else {  // row K: t-hat from the encapsulation key, PolyDotHat(&v, &pk.th, &rh) (cpapke.go:167)
-        int32_t th[32];
-        const uint32_t b = unpack12_C(ekp + 384 * j + 48 * v, th);
-        if (lenient) {
-#pragma unroll
-          for (int c = 0; c < 32; c++) th[c] = csubq_hi(barrett_hi(th[c]));
-        } else {
-          bad |= b;
-        }
-#pragma unroll
-        for (int w = 0; w < 16; w++) aw[w] = pack2(th[2 * w], th[2 * w + 1]);
-      }
-      mulhat_acc_words(r, aw, rh + j * 128, tab, v);
-    }
-#pragma unroll
-    for (int c = 0; c < 32; c++) r[c] = barrett_hi(r[c]);
-    inv_pass_C_smem(r, tab, v);
-    store_C(tile, v, r);
-    __syncwarp();
-    load_S(tile, v, r);
-    inv_pass_S(r, v);
-    __syncwarp();
-    {  // + e1[i] / + e2 (+ Decompress_q(m, 1)), S layout
-      const uint32_t* e = np + (K + i) * (N / 2);
-      const uint32_t* mw = reinterpret_cast<const uint32_t*>(m + 32 * op);
-#pragma unroll
-      for (int s = 0; s < 16; s++) {
-        int32_t e0, e1;
-        unpack2(__ldg(e + 8 * s + v), e0, e1);
-        r[2 * s] += e0;
-        r[2 * s + 1] += e1;
-        if (i == K) {  // DecompressMessage, poly.go:134-147: coefficient idx = 16 s + 2 v + b <- bit idx of m
-          const uint32_t word = __ldg(mw + (s >> 1));
-          const uint32_t bits = (word >> (16 * (s & 1) + 2 * v)) & 3;
-          r[2 * s] += (bits & 1) ? ((Q + 1) / 2) << 16 : 0;
-          r[2 * s + 1] += (bits & 2) ? ((Q + 1) / 2) << 16 : 0;
-        }
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 32; c++) r[c] = csubq_hi(barrett_hi(r[c]));  // Normalize (cpapke.go:176-177)
-    store_S(tile, v, r);
-    __syncwarp();
-    load_C(tile, v, r);
-    __syncwarp();
-    bad = __any_sync(octmask, bad) ? 1u : 0u;  // after row K this holds the modulus check of the whole key
-    if (active) {
-      if (i < K)
-        compress_store_C<P::du>(r, reinterpret_cast<uint32_t*>(ctp + i * 32 * P::du) + v * P::du);
-      else if (!bad)
-        compress_store_C<P::dv>(r, reinterpret_cast<uint32_t*>(ctp + K * 32 * P::du) + v * P::dv);
-    }
-  }
-  // kem.ErrPubKey (cpapke.go:48-54): no output for a non-canonical key
-  if (active) {
-    if (bad) {
-      uint32_t* c32 = reinterpret_cast<uint32_t*>(ctp);
-      for (int w = v; w < P::ct_bytes / 4; w += 8) c32[w] = 0;
-      if (ss) reinterpret_cast<uint32_t*>(ss + 32 * op)[v] = 0;
-    }
-    if (status && v == 0 && !lenient) status[op] = (uint8_t)bad;
-  }
-}
-
-
-// ------------------------------------------------------------------ 3b. K-PKE.Encrypt, inner products on packed pairs
-// The same function as encrypt_kernel with the matrix-vector products done differently.  What leaves the kernel is
-// Compress(Normalize(.)), so only residues mod q matter inside it, not the reference's Montgomery representatives:
+// ------------------------------------------------------------------ 3. K-PKE.Encrypt (cpapke.go:137-181), one octet per op
+// u = InvNTT(A^T o NTT(r)) + e1, v = InvNTT(t o NTT(r)) + e2 + Decompress(m), ct = Compress(u) || Compress(v).  What leaves
+// the kernel is Compress(Normalize(.)), so only residues mod q matter inside it, not the reference's Montgomery
+// representatives, and the matrix-vector products are done differently from MulHat:
 //
 //   * A^T and t-hat are used as they lie in memory: one 32-bit word = one degree-2 block (a0 | a1 << 16), plain
 //     residues in [0, 4096);
@@ -651,8 +532,8 @@ __device__ __forceinline__ uint32_t unpack12_half(const uint32_t (&w)[8], uint32
 // = 14 warps per SM resident; every global load is issued one step before its data is used (register double buffers),
 // because a warp walks 19 dependent load -> compute phases per operation and L2 latency, not the instruction count,
 // was what bounded the first version (ncu: long_scoreboard 1.3 per issue at 12-16 warps per SM).
-template <int K, int THREADS>
-__global__ void __launch_bounds__(THREADS, 448 / THREADS) encrypt_dp_kernel(
+template <int K, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) encrypt_dp_kernel(
     const uint8_t* __restrict__ ek, size_t ek_stride, const int16_t* __restrict__ A, int a_shared,
     const int16_t* __restrict__ noise, const uint8_t* __restrict__ m, size_t n, uint8_t* __restrict__ ct,
     uint8_t* __restrict__ ss, uint8_t* __restrict__ status, const kyber::TwPair* __restrict__ tw, int lenient) {
@@ -726,7 +607,7 @@ __global__ void __launch_bounds__(THREADS, 448 / THREADS) encrypt_dp_kernel(
   __syncwarp();
 
   // u[i] = InvNTT(A^T[i] . rh) + e1[i]; v = InvNTT(t . rh) + e2 + m.  A row is accumulated in two halves of eight
-  // blocks (32 accumulators); step (i, h, j) loads the eight words of step + 1 before it multiplies its own.
+  // blocks (32 accumulators).
   auto fetch = [&](int i, int h, int j, uint32_t (&raw)[8]) {
     if (i < K) {
       const uint4* p = reinterpret_cast<const uint4*>(Ap + (i * K + j) * (N / 2) + 16 * v + 8 * h);
@@ -738,9 +619,12 @@ __global__ void __launch_bounds__(THREADS, 448 / THREADS) encrypt_dp_kernel(
       raw[0] = x.x, raw[1] = x.y, raw[2] = y.x, raw[3] = y.y, raw[4] = z.x, raw[5] = z.y;
     }
   };
+  // raw[j]: the eight words of column j of the half-row that comes next; refilled for the half-row after it as soon as they
+  // have been consumed, i.e. every load is K steps (~250 instructions of this warp) ahead of its use
   uint32_t bad = 0;
-  uint32_t raw[8];
-  fetch(0, 0, 0, raw);
+  uint32_t raw[K][8];
+#pragma unroll
+  for (int j = 0; j < K; j++) fetch(0, 0, j, raw[j]);
 #pragma unroll 1
   for (int i = 0; i <= K; i++) {
     uint32_t ew[16];
@@ -749,27 +633,18 @@ __global__ void __launch_bounds__(THREADS, 448 / THREADS) encrypt_dp_kernel(
       int32_t p0l[8], p0h[8], p1l[8], p1h[8];
 #pragma unroll
       for (int c = 0; c < 8; c++) p0l[c] = p0h[c] = p1l[c] = p1h[c] = 0;
-#pragma unroll 1
+      const int ni = h ? i + 1 : i, nh = h ^ 1;  // the half-row after this one
+#pragma unroll
       for (int j = 0; j < K; j++) {
         uint32_t aw[8];
         if (i < K) {
 #pragma unroll
-          for (int c = 0; c < 8; c++) aw[c] = raw[c];
+          for (int c = 0; c < 8; c++) aw[c] = raw[j][c];
         } else {
-          const uint32_t b = unpack12_half(raw, aw);
+          const uint32_t b = unpack12_half(raw[j], aw);
           if (!lenient) bad |= b;
         }
-        {  // the words of the next step
-          int ni = i, nh = h, nj = j + 1;
-          if (nj == K) {
-            nj = 0;
-            if (++nh == 2) {
-              nh = 0;
-              ni++;
-            }
-          }
-          if (ni <= K) fetch(ni, nh, nj, raw);
-        }
+        if (ni <= K) fetch(ni, nh, j, raw[j]);
         const uint2* oj = ops + (size_t)(j * 16 + 8 * h) * 8;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
@@ -847,17 +722,25 @@ __global__ void __launch_bounds__(THREADS, 448 / THREADS) encrypt_dp_kernel(
 
 // the K-PKE.Encrypt launch of the three flows (Encapsulate, the re-encryption of Decapsulate, round-3 Kyber)
 constexpr int kEncDpThreads = 64;
+template <int K, int MINB>
+static int launch_encrypt_v(const uint8_t* ek, size_t ek_stride, const int16_t* A, int a_shared, const int16_t* noise,
+                            const uint8_t* m, size_t n, uint8_t* ct, uint8_t* ss, uint8_t* status, int lenient,
+                            cudaStream_t st) {
+  using S = EncSmem<K, kEncDpThreads>;
+  if (int arc = ensure_smem_attr((const void*)encrypt_dp_kernel<K, kEncDpThreads, MINB>, S::bytes)) return arc;
+  KernelScope ks(KID_MLKEM_ENCRYPT, st);
+  constexpr int per_cta = kEncDpThreads / 8;
+  encrypt_dp_kernel<K, kEncDpThreads, MINB><<<(unsigned)((n + per_cta - 1) / per_cta), kEncDpThreads, S::bytes, st>>>(
+      ek, ek_stride, A, a_shared, noise, m, n, ct, ss, status, (const kyber::TwPair*)ctx().kyber_tw, lenient);
+  return 0;
+}
 template <int K>
 static int launch_encrypt(const uint8_t* ek, size_t ek_stride, const int16_t* A, int a_shared, const int16_t* noise,
                           const uint8_t* m, size_t n, uint8_t* ct, uint8_t* ss, uint8_t* status, int lenient,
                           cudaStream_t st) {
-  using S = EncSmem<K, kEncDpThreads>;
-  if (int arc = ensure_smem_attr((const void*)encrypt_dp_kernel<K, kEncDpThreads>, S::bytes)) return arc;
-  KernelScope ks(KID_MLKEM_ENCRYPT, st);
-  constexpr int per_cta = kEncDpThreads / 8;
-  encrypt_dp_kernel<K, kEncDpThreads><<<(unsigned)((n + per_cta - 1) / per_cta), kEncDpThreads, S::bytes, st>>>(
-      ek, ek_stride, A, a_shared, noise, m, n, ct, ss, status, (const kyber::TwPair*)ctx().kyber_tw, lenient);
-  return 0;
+  // 7 CTAs of 64 threads per SM (K = 4: 6, its operands and registers are larger); measured against 6 and 5:
+  // profiles/r02_sweeps.txt
+  return launch_encrypt_v<K, (K == 4 ? 6 : 7)>(ek, ek_stride, A, a_shared, noise, m, n, ct, ss, status, lenient, st);
 }
 
 

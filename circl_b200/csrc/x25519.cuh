@@ -433,16 +433,39 @@ CB200_XHD void scalarmult_base(uint32_t (&out)[8], const uint32_t (&kin)[8], con
   fe_set(h.Y, 1);
   fe_set(h.Z, 1);
   fe_set(h.T, 0);
+  // Constant-time use of the secret digit, as the reference's KeyGen keeps it (ladderJoye indexes its table by the loop
+  // counter only and uses cswap, dh/x25519/curve.go:7-37): all eight multiples of the row are read and the one wanted
+  // -- or the neutral element (1, 1, 0) for digit 0 -- is kept by masks; the sign is applied by a masked swap of
+  // y + x / y - x and a masked negation of 2dxy.  No branch and no address depends on the scalar.
   auto add_digit = [&](int i) {
     const int e = digit(i);
-    if (e != 0) {
-      const int m = e < 0 ? -e : e;
-      GePre q;
-      pre_from_words(q, table + ((i >> 1) * 8 + (m - 1)) * 32);
-      GeExt s;
-      ge_madd(s, h, q, e < 0);
-      h = s;
+    const uint32_t neg = (uint32_t)(e >> 31);             // all ones for a negative digit
+    const uint32_t m = ((uint32_t)e ^ neg) - neg;         // |e| in 0..8
+    GePre q;
+    fe_set(q.ypx, 1);
+    fe_set(q.ymx, 1);
+    fe_set(q.xy2d, 0);
+    const int32_t* row = table + (i >> 1) * 8 * 32;
+#pragma unroll 1
+    for (int j = 0; j < 8; j++) {
+      const uint32_t mask = (uint32_t)((int32_t)((m ^ (uint32_t)(j + 1)) - 1u) >> 31);  // all ones iff m == j + 1
+#pragma unroll
+      for (int c = 0; c < 10; c++) {
+        q.ypx.v[c] = (int32_t)(((uint32_t)q.ypx.v[c] & ~mask) | ((uint32_t)row[j * 32 + c] & mask));
+        q.ymx.v[c] = (int32_t)(((uint32_t)q.ymx.v[c] & ~mask) | ((uint32_t)row[j * 32 + 10 + c] & mask));
+        q.xy2d.v[c] = (int32_t)(((uint32_t)q.xy2d.v[c] & ~mask) | ((uint32_t)row[j * 32 + 20 + c] & mask));
+      }
     }
+#pragma unroll
+    for (int c = 0; c < 10; c++) {
+      const uint32_t t = neg & ((uint32_t)q.ypx.v[c] ^ (uint32_t)q.ymx.v[c]);
+      q.ypx.v[c] = (int32_t)((uint32_t)q.ypx.v[c] ^ t);
+      q.ymx.v[c] = (int32_t)((uint32_t)q.ymx.v[c] ^ t);
+      q.xy2d.v[c] = (int32_t)(((uint32_t)q.xy2d.v[c] ^ neg) - neg);
+    }
+    GeExt s;
+    ge_madd(s, h, q, false);
+    h = s;
   };
 #if defined(__CUDA_ARCH__)
 #pragma unroll 1

@@ -15,11 +15,13 @@
 #include <cstdint>
 #include <cstring>
 #include <memory>
-#include <random>
 #include <stdexcept>
+#include <cerrno>
 #include <string>
 #include <utility>
 #include <vector>
+
+#include <sys/random.h>
 
 #include "circl_b200.h"
 
@@ -33,9 +35,21 @@ struct Error : std::runtime_error {
 inline void init(int device = 0) {
   if (cb200_init(device) != 0) throw Error(cb200_last_error());
 }
-inline void fill_random(uint8_t* p, size_t n) {  // crypto/rand stand-in for the mirror (std::random_device)
-  std::random_device rd;
-  for (size_t i = 0; i < n; i++) p[i] = (uint8_t)rd();
+// one process, GPUs 0..ndev-1 (0: all): host-pointer batches are sharded by index inside the library
+inline void init_devices(int ndev = 0) {
+  if (cb200_init_devices(ndev) != 0) throw Error(cb200_last_error());
+}
+// crypto/rand of the mirror: the kernel's CSPRNG (getrandom(2)), as Go's crypto/rand reads it on Linux
+inline void fill_random(uint8_t* p, size_t n) {
+  size_t got = 0;
+  while (got < n) {
+    const ssize_t r = getrandom(p + got, n - got, 0);
+    if (r < 0) {
+      if (errno == EINTR) continue;
+      throw Error("getrandom failed");
+    }
+    got += (size_t)r;
+  }
 }
 
 namespace kem {

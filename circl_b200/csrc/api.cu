@@ -40,7 +40,7 @@ Dev& ctx() {
   return *t_dev;
 }
 WorkSet& wset(int slot) {
-  if (slot >= 0 && slot < 3) return ctx().staging[slot];
+  if (slot >= 0 && slot < Dev::kSlots) return ctx().staging[slot];
   if (!t_ws3) {
     fprintf(stderr, "cb200: internal error: no work set bound to this thread\n");
     abort();
@@ -109,8 +109,8 @@ int ensure_scratch(int slot, size_t bytes) {
 }
 
 int ensure_work(int slot, size_t bytes, void** out) {
-  const int level = slot >> 2;
-  WorkSet& w = wset(slot & 3);
+  const int level = slot / kLevel1;
+  WorkSet& w = wset(slot % kLevel1);
   if (w.work_bytes[level] < bytes) {
     // kernels of earlier calls on this set may still be running: the set is only ever used from one stream (and
     // the lanes joined to it), and cudaFree waits for the device
@@ -249,8 +249,13 @@ static int dev_create(int device, std::unique_ptr<Dev>* out) {
   std::unique_ptr<Dev> d(new Dev);
   d->device = device;
   d->sm_count = prop.multiProcessorCount;
-  for (int s = 0; s < 3; s++) {
+  CB200_CUDA(cudaStreamCreateWithFlags(&d->h2d, cudaStreamNonBlocking));
+  CB200_CUDA(cudaStreamCreateWithFlags(&d->d2h, cudaStreamNonBlocking));
+  for (int s = 0; s < Dev::kSlots; s++) {
     CB200_CUDA(cudaStreamCreateWithFlags(&d->pipe[s], cudaStreamNonBlocking));
+    CB200_CUDA(cudaEventCreateWithFlags(&d->ev_in[s], cudaEventDisableTiming));
+    CB200_CUDA(cudaEventCreateWithFlags(&d->ev_k[s], cudaEventDisableTiming));
+    CB200_CUDA(cudaEventCreateWithFlags(&d->ev_out[s], cudaEventDisableTiming));
     int rc = wset_create(d->staging[s]);
     if (rc) return rc;
   }
@@ -273,11 +278,16 @@ static void dev_destroy(Dev& d) {
   if (d.worker.joinable()) d.worker.join();
   cudaSetDevice(d.device);
   cudaDeviceSynchronize();
-  for (int s = 0; s < 3; s++) {
+  for (int s = 0; s < Dev::kSlots; s++) {
     if (d.scratch[s]) cudaFree(d.scratch[s]);
     if (d.pipe[s]) cudaStreamDestroy(d.pipe[s]);
+    if (d.ev_in[s]) cudaEventDestroy(d.ev_in[s]);
+    if (d.ev_k[s]) cudaEventDestroy(d.ev_k[s]);
+    if (d.ev_out[s]) cudaEventDestroy(d.ev_out[s]);
     wset_destroy(d.staging[s]);
   }
+  if (d.h2d) cudaStreamDestroy(d.h2d);
+  if (d.d2h) cudaStreamDestroy(d.d2h);
   for (auto& kv : d.sets) wset_destroy(*kv.second);
   d.sets.clear();
   if (d.pinned) cudaFreeHost(d.pinned);
@@ -396,14 +406,10 @@ int run_staged(std::vector<Buf>& bufs, size_t first0, size_t n, size_t chunk,
     size_t sz = bufs[i].shared ? bufs[i].unit : bufs[i].unit * chunk;
     off[i + 1] = off[i] + ((sz + 255) & ~(size_t)255);
   }
-  for (int s = 0; s < 3; s++) {
-    int rc = ensure_scratch(s, off[nb]);
-    if (rc) return rc;
-  }
+  std::vector<size_t> sched;
   // Chunk schedule: the first and the last chunks are short (1/4, 1/4, 1/2 of `chunk` on the way up, the mirror
   // image on the way down) so that the part of the pipeline that cannot overlap -- the first input copy and the last
   // kernels + output copy -- is a quarter of a chunk instead of a whole one.  Only worth it for long batches.
-  std::vector<size_t> sched;
   {
     const size_t ramp[3] = {chunk / 4, chunk / 4, chunk / 2};
     size_t left = n;
@@ -422,12 +428,24 @@ int run_staged(std::vector<Buf>& bufs, size_t first0, size_t n, size_t chunk,
     }
     for (size_t k = tail.size(); k-- > 0;) sched.push_back(tail[k]);
   }
+  constexpr int S = Dev::kSlots;
+  const int used = (int)std::min<size_t>(S, sched.size());
+  for (int s = 0; s < used; s++) {
+    int rc = ensure_scratch(s, off[nb]);
+    if (rc) return rc;
+  }
+  // a buffer that is copied in AND out (in-place ring ops) must not be refilled before its output copy is done
+  bool inout = false;
+  for (size_t i = 0; i < nb; i++) inout |= (bufs[i].host_in && bufs[i].host_out);
   std::vector<void*> dev(nb);
-  int slot = 0, rc = 0;
+  int rc = 0;
   size_t first = first0;
-  for (size_t ci = 0; ci < sched.size() && rc == 0; first += sched[ci], ci++, slot = (slot + 1) % 3) {
+  for (size_t ci = 0; ci < sched.size() && rc == 0; first += sched[ci], ci++) {
+    const int slot = (int)(ci % S);
     const size_t count = sched[ci];
     cudaStream_t st = c.pipe[slot];
+    // inputs: the slot's previous occupant (chunk ci - S) has finished reading them once its kernels are done
+    if (ci >= (size_t)S) CB200_CUDA(cudaStreamWaitEvent(c.h2d, inout ? c.ev_out[slot] : c.ev_k[slot], 0));
     for (size_t i = 0; i < nb; i++) {
       dev[i] = (char*)c.scratch[slot] + off[i];
       if (bufs[i].host_in) {
@@ -435,20 +453,30 @@ int run_staged(std::vector<Buf>& bufs, size_t first0, size_t n, size_t chunk,
         const char* src = (const char*)bufs[i].host_in + (bufs[i].shared ? 0 : first * hs);
         if (bufs[i].shared || hs == bufs[i].unit) {
           size_t sz = bufs[i].shared ? bufs[i].unit : count * bufs[i].unit;
-          CB200_CUDA(cudaMemcpyAsync(dev[i], src, sz, cudaMemcpyHostToDevice, st));
+          CB200_CUDA(cudaMemcpyAsync(dev[i], src, sz, cudaMemcpyHostToDevice, c.h2d));
         } else {
-          CB200_CUDA(cudaMemcpy2DAsync(dev[i], bufs[i].unit, src, hs, bufs[i].unit, count, cudaMemcpyHostToDevice, st));
+          CB200_CUDA(cudaMemcpy2DAsync(dev[i], bufs[i].unit, src, hs, bufs[i].unit, count, cudaMemcpyHostToDevice, c.h2d));
         }
       }
     }
+    CB200_CUDA(cudaEventRecord(c.ev_in[slot], c.h2d));
+    // kernels: after this chunk's inputs, and after the output copy of the slot's previous occupant
+    CB200_CUDA(cudaStreamWaitEvent(st, c.ev_in[slot], 0));
+    if (ci >= (size_t)S) CB200_CUDA(cudaStreamWaitEvent(st, c.ev_out[slot], 0));
     rc = body(dev.data(), count, first, st, slot);
     if (rc) break;
+    CB200_CUDA(cudaEventRecord(c.ev_k[slot], st));
+    // outputs
+    CB200_CUDA(cudaStreamWaitEvent(c.d2h, c.ev_k[slot], 0));
     for (size_t i = 0; i < nb; i++)
       if (bufs[i].host_out && !bufs[i].shared)
         CB200_CUDA(cudaMemcpyAsync((char*)bufs[i].host_out + first * bufs[i].unit, dev[i], count * bufs[i].unit,
-                                   cudaMemcpyDeviceToHost, st));
+                                   cudaMemcpyDeviceToHost, c.d2h));
+    CB200_CUDA(cudaEventRecord(c.ev_out[slot], c.d2h));
   }
-  for (int s = 0; s < 3; s++) CB200_CUDA(cudaStreamSynchronize(c.pipe[s]));
+  CB200_CUDA(cudaStreamSynchronize(c.h2d));
+  for (int s = 0; s < S; s++) CB200_CUDA(cudaStreamSynchronize(c.pipe[s]));
+  CB200_CUDA(cudaStreamSynchronize(c.d2h));
   return rc;
 }
 

@@ -57,11 +57,17 @@ struct Dev {
   void* kyber_tw = nullptr;     // 128 x {zeta, zetaq}
   void* dil_tw = nullptr;       // 256 x {zeta, invzeta}
   void* x25519_table = nullptr; // 32 KiB: multiples 1..8 of 256^i B for the fixed-base X25519 KeyGen (x25519.cuh)
-  // host staging pipeline (owned by the worker thread): H2D -> kernels -> D2H per chunk on three streams
-  cudaStream_t pipe[3] = {nullptr, nullptr, nullptr};
-  void* scratch[3] = {nullptr, nullptr, nullptr};
-  size_t scratch_bytes[3] = {0, 0, 0};
-  WorkSet staging[3];           // work sets of the three pipeline slots
+  // host staging pipeline (owned by the worker thread).  A chunk lives in one of kSlots slots (device images of its
+  // buffers + a work set); all input copies go down one stream, all output copies down another, the kernels of a
+  // slot down that slot's stream, tied by events: the input copy of chunk c + kSlots waits only for the KERNELS of
+  // chunk c (not for its output copy), so both copy engines stay busy across chunk boundaries.
+  static constexpr int kSlots = 4;
+  cudaStream_t pipe[kSlots] = {};
+  cudaStream_t h2d = nullptr, d2h = nullptr;
+  cudaEvent_t ev_in[kSlots] = {}, ev_k[kSlots] = {}, ev_out[kSlots] = {};
+  void* scratch[kSlots] = {};
+  size_t scratch_bytes[kSlots] = {};
+  WorkSet staging[kSlots];      // work sets of the pipeline slots
   void* pinned = nullptr;       // grow-only pinned host staging for small per-op outputs (status bytes)
   size_t pinned_bytes = 0;
   // device-pointer calls: one work set per caller stream
@@ -103,7 +109,9 @@ const char* kernel_name(int id);
 // The device the calling thread is working on: set by a DeviceCall (device-pointer entry points) or by the worker
 // thread of that device (host-pointer shards).  Flows only ever run inside one of the two.
 Dev& ctx();
-// Work set of `slot`: 0..2 = pipeline slots of ctx(), 3 = the set bound by the innermost DeviceCall.
+// Work set of `slot`: 0..kSlots-1 = pipeline slots of ctx(), kDevSlot = the set bound by the innermost DeviceCall.
+constexpr int kDevSlot = Dev::kSlots;
+constexpr int kLevel1 = 8;  // ensure_work(kLevel1 + slot, ...) = the level-1 area of that work set
 WorkSet& wset(int slot);
 bool profiling_on();
 
@@ -119,7 +127,7 @@ int require_ready();
 // true for device (or managed) memory; *device receives the ordinal that owns it
 bool is_device_ptr(const void* p, int* device = nullptr);
 int ensure_scratch(int slot, size_t bytes);
-// slot 0..3 = level-0 area of that work set, 4 + slot = its level-1 area
+// slot = level-0 area of that work set, kLevel1 + slot = its level-1 area
 int ensure_work(int slot, size_t bytes, void** out);
 int ensure_pinned(size_t bytes, void** out);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel)

@@ -157,7 +157,7 @@ struct Arena {  // bump allocator over the second-level work area of a slot
 };
 static int arena(int slot, size_t bytes, Arena* a) {
   void* p = nullptr;
-  int rc = ensure_work(4 + slot, bytes + 4096, &p);  // work areas 4..7 belong to this file, 0..3 to the lattice flows
+  int rc = ensure_work(kLevel1 + slot, bytes + 4096, &p);  // the level-1 areas belong to this file, level 0 to the lattice flows
   if (rc) return rc;
   a->base = (char*)p;
   a->off = 0;
@@ -424,7 +424,7 @@ int cb200_xwing_keygen(const uint8_t* seeds, uint8_t* pk, size_t n) {
     }
     DeviceCall call(pk);
     if (call.rc) return call.rc;
-    return xwing_keygen_dev(seeds, pk, n, call.st, 3);
+    return xwing_keygen_dev(seeds, pk, n, call.st, kDevSlot);
   }
   std::vector<Buf> bufs = {Buf{seeds, nullptr, 32, false, 0}, Buf{nullptr, pk, 1216, false, 0}};
   return run_host(bufs, n, 1u << 15, 1u << 13, [&](void** d, size_t cnt, size_t, cudaStream_t st, int slot) {
@@ -453,7 +453,7 @@ int cb200_xwing_encaps(const uint8_t* pk, size_t pk_stride, const uint8_t* eseed
     }
     DeviceCall call(ct);
     if (call.rc) return call.rc;
-    return xwing_encaps_dev(pk, pk_stride, eseeds, ct, ss, status, n, call.st, 3);
+    return xwing_encaps_dev(pk, pk_stride, eseeds, ct, ss, status, n, call.st, kDevSlot);
   }
   HostCall hc;
   hc.bufs = {Buf{pk, nullptr, 1216, pk_stride == 0, pk_stride}, Buf{eseeds, nullptr, 64, false, 0},
@@ -491,7 +491,7 @@ int cb200_xwing_decaps(const uint8_t* sk, size_t sk_stride, const uint8_t* ct, u
     }
     DeviceCall call(ss);
     if (call.rc) return call.rc;
-    return xwing_decaps_dev(sk, sk_stride, ct, ss, n, call.st, 3);
+    return xwing_decaps_dev(sk, sk_stride, ct, ss, n, call.st, kDevSlot);
   }
   std::vector<Buf> bufs = {Buf{sk, nullptr, 32, sk_stride == 0, sk_stride}, Buf{ct, nullptr, 1120, false, 0},
                            Buf{nullptr, ss, 32, false, 0}};
@@ -534,7 +534,7 @@ int cb200_hybrid_keygen(int id, const uint8_t* seeds, uint8_t* pk, uint8_t* sk, 
     }
     DeviceCall call(pk);
     if (call.rc) return call.rc;
-    return hybrid_keygen_dev(H, seeds, pk, sk, n, call.st, 3);
+    return hybrid_keygen_dev(H, seeds, pk, sk, n, call.st, kDevSlot);
   }
   std::vector<Buf> bufs = {Buf{seeds, nullptr, 64, false, 0}, Buf{nullptr, pk, H.ek + 32, false, 0},
                            Buf{nullptr, sk, H.dk + 32, false, 0}};
@@ -569,7 +569,7 @@ int cb200_hybrid_encaps(int id, const uint8_t* pk, size_t pk_stride, const uint8
     }
     DeviceCall call(ct);
     if (call.rc) return call.rc;
-    return hybrid_encaps_dev(H, pk, pk_stride, seeds, ct, ss, status, n, call.st, 3);
+    return hybrid_encaps_dev(H, pk, pk_stride, seeds, ct, ss, status, n, call.st, kDevSlot);
   }
   const size_t pks = H.ek + 32;
   HostCall hc;
@@ -613,7 +613,7 @@ int cb200_hybrid_decaps(int id, const uint8_t* sk, size_t sk_stride, const uint8
     }
     DeviceCall call(ss);
     if (call.rc) return call.rc;
-    return hybrid_decaps_dev(H, sk, sk_stride, ct, ss, status, n, call.st, 3);
+    return hybrid_decaps_dev(H, sk, sk_stride, ct, ss, status, n, call.st, kDevSlot);
   }
   const size_t sks = H.dk + 32;
   HostCall hc;

@@ -2000,7 +2000,7 @@ int cb200_mldsa_sign(int mode, const uint8_t* sk, size_t sk_stride, const uint8_
       CB200_CUDA(cudaMemcpyAsync(call.ws->small, context, ctxlen, cudaMemcpyHostToDevice, call.st));
       dctx = (const uint8_t*)call.ws->small;
     }
-    return dispatch_sign(mode, sk, sk_stride, msgs, msg_off, dctx, (int)ctxlen, rnd, sig, status, n, internal, call.st, 3,
+    return dispatch_sign(mode, sk, sk_stride, msgs, msg_off, dctx, (int)ctxlen, rnd, sig, status, n, internal, call.st, kDevSlot,
                          attempts, (volatile uint32_t*)call.ws->pin);
   }
   // host pointers: one contiguous range of the batch per GPU; on each GPU chunks of 2^16 signatures go through the three
@@ -2134,7 +2134,7 @@ int cb200_mldsa_verify(int mode, const uint8_t* pk, size_t pk_stride, const uint
       CB200_CUDA(cudaMemcpyAsync(call.ws->small, context, ctxlen, cudaMemcpyHostToDevice, call.st));
       dctx = (const uint8_t*)call.ws->small;
     }
-    return dispatch_verify(mode, pk, pk_stride, msgs, msg_off, dctx, (int)ctxlen, sig, ok, n, internal, call.st, 3);
+    return dispatch_verify(mode, pk, pk_stride, msgs, msg_off, dctx, (int)ctxlen, sig, ok, n, internal, call.st, kDevSlot);
   }
   // host pointers: one contiguous range per GPU, each in chunks of 2^15 signatures on the first staging slot
   return for_each_shard(n, 1u << 12, [&](size_t sh_first, size_t sh_n) -> int {
@@ -2205,7 +2205,7 @@ int cb200_mldsa_keygen(int mode, const uint8_t* seeds, uint8_t* pk, uint8_t* sk,
     }
     DeviceCall call(pk);
     if (call.rc) return call.rc;
-    return dispatch_keygen(mode, seeds, pk, sk, n, call.st, 3);
+    return dispatch_keygen(mode, seeds, pk, sk, n, call.st, kDevSlot);
   }
   std::vector<Buf> bufs(3);
   bufs[0] = Buf{seeds, nullptr, 32, false, 0};

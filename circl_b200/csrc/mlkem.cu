@@ -1700,7 +1700,7 @@ static int keygen_entry(const char* fn, int mlkem_flag, int k, const uint8_t* se
     }
     DeviceCall call(ek);
     if (call.rc) return call.rc;
-    return run(seeds, ek, dk, n, call.st, 3);
+    return run(seeds, ek, dk, n, call.st, kDevSlot);
   }
   std::vector<Buf> bufs(3);
   bufs[0] = Buf{seeds, nullptr, 64, false, 0};
@@ -1757,7 +1757,7 @@ static int kyber_kem_run(int decaps, int k, const uint8_t* key, size_t key_strid
     }
     DeviceCall call(ss);
     if (call.rc) return call.rc;
-    return run(key, key_stride, in, ct, ss, n, call.st, 3);
+    return run(key, key_stride, in, ct, ss, n, call.st, kDevSlot);
   }
   std::vector<Buf> bufs;
   bufs.push_back(Buf{key, nullptr, keysz, key_stride == 0, key_stride});
@@ -1811,7 +1811,7 @@ int cb200_mlkem_decaps(int k, const uint8_t* dk, size_t dk_stride, const uint8_t
     }
     DeviceCall call(ss);
     if (call.rc) return call.rc;
-    return run(dk, dk_stride, ct, ss, status, n, call.st, 3);
+    return run(dk, dk_stride, ct, ss, status, n, call.st, kDevSlot);
   }
   // a shared dk is replicated per op on the device inside each staged chunk (the decapsulation pipeline is per-op)
   HostCall hc;
@@ -1881,7 +1881,7 @@ static int mlkem_encaps_entry(int k, const uint8_t* ek, size_t ek_stride, const 
     // status is needed to report kem.ErrPubKey; with device pointers the caller reads it asynchronously
     DeviceCall call(ct);
     if (call.rc) return call.rc;
-    return mlkem::encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, call.st, 3, push_ct, push_ss);
+    return mlkem::encaps_any(k, ek, ek_stride, seeds, ct, ss, status, n, call.st, kDevSlot, push_ct, push_ss);
   }
   // host pointers: one contiguous index range per GPU, each staged through HBM in chunks on three streams
   // (H2D | kernels | D2H overlap); the per-op status always comes back (it carries kem.ErrPubKey)

@@ -1,8 +1,13 @@
 """Every kernel family of the library once, at small sizes, for compute-sanitizer (scripts/sanitize_r02.sh):
 memcheck / racecheck / synccheck / initcheck need short runs.  Results are still checked against the oracle."""
+import os
+import sys
+
 import numpy as np
 
-import circl_b200
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import circl_b200  # noqa: E402
 import oracle
 from circl_b200 import dilithium, hybrid, keccak, kyber, mldsa, mlkem
 

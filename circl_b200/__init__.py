@@ -10,5 +10,5 @@ of the reference's interfaces used by the tests and the bench:
   circl_b200.keccak  -- simd/keccakf1600 + internal/sha3 (batched permutation and one-shot sponges)
 """
 from ._ffi import Cb200Error, lib, check  # noqa: F401
-from .runtime import (init, init_devices, active_devices, bind_thread_to_device, release_stream, shutdown,  # noqa: F401
+from .runtime import (host_batch, host_free, init, init_devices, active_devices, bind_thread_to_device, release_stream, shutdown,  # noqa: F401
                       device_count, set_stream, synchronize, launch_count)

@@ -31,6 +31,7 @@ SYMBOLS = {
     "cb200_gather_push": (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     "cb200_gather_flush": (C.c_int, [C.c_void_p, C.c_int]),
     "cb200_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "cb200_host_alloc_batch": (C.c_void_p, [C.c_size_t, C.c_size_t]),
     "cb200_host_free": (None, [C.c_void_p]),
     "cb200_launch_count": (C.c_uint64, []),
     "cb200_profile_enable": (C.c_int, [C.c_int]),

@@ -12,6 +12,8 @@
 #include "common.cuh"
 #include "context.h"
 
+#include <sys/mman.h>
+
 namespace cb200 {
 
 static thread_local char g_err[512] = "";
@@ -54,7 +56,7 @@ static const char* kKernelNames[KID_COUNT] = {
     "mlkem_hash_ek", "mlkem_g", "mlkem_sample", "mlkem_encrypt",
     "dil_ntt", "dil_invntt", "dil_dot", "dil_elementwise",
     "mldsa_expand_key", "mldsa_mu_rhoprime", "mldsa_mask", "mldsa_w", "mldsa_challenge", "mldsa_response",
-    "mldsa_compact", "x25519", "hybrid_glue", "keccak_f1600", "sampler"};
+    "mldsa_compact", "x25519", "hybrid_glue", "keccak_f1600", "sampler", "mlkem_sample_fix"};
 const char* kernel_name(int id) { return (id >= 0 && id < KID_COUNT) ? kKernelNames[id] : "?"; }
 
 KernelScope::KernelScope(int id_, cudaStream_t st_) : st(st_), id(id_) {
@@ -124,6 +126,20 @@ int ensure_work(int slot, size_t bytes, void** out) {
   return 0;
 }
 
+int ensure_fix(int slot, int lane, size_t bytes, cudaStream_t st, void** out) {
+  WorkSet& w = wset(slot % kLevel1);
+  if (w.fix_bytes[lane] < bytes) {
+    if (w.fix[lane]) CB200_CUDA(cudaFree(w.fix[lane]));  // waits for the device: no kernel still uses the old area
+    w.fix[lane] = nullptr;
+    w.fix_bytes[lane] = 0;
+    CB200_CUDA(cudaMalloc(&w.fix[lane], bytes));
+    w.fix_bytes[lane] = bytes;
+    CB200_CUDA(cudaMemsetAsync(w.fix[lane], 0, 64, st));  // the counters in front of the list
+  }
+  *out = w.fix[lane];
+  return 0;
+}
+
 int ensure_pinned(size_t bytes, void** out) {
   Dev& c = ctx();
   if (c.pinned_bytes < bytes) {
@@ -161,6 +177,9 @@ static int wset_create(WorkSet& w) {  // the owning device is current
 }
 static void wset_destroy(WorkSet& w) {
   for (int l = 0; l < 2; l++) {
+    if (w.fix[l]) cudaFree(w.fix[l]);
+    w.fix[l] = nullptr;
+    w.fix_bytes[l] = 0;
     if (w.work[l]) cudaFree(w.work[l]);
     w.work[l] = nullptr;
     w.work_bytes[l] = 0;
@@ -667,8 +686,64 @@ void* cb200_host_alloc(size_t bytes) {
   }
   return p;
 }
+// One pinned buffer for a batch that cb200_* host-pointer calls will split over all active GPUs: the rows of shard s
+// (the split of for_each_shard) are first touched by the worker thread of the GPU that will copy them, which runs on
+// that GPU's NUMA node, so every GPU's copies stay on its own socket (profiles/r02_pcie_multi_probe.txt).
+static std::mutex g_map_mu;
+static std::map<void*, size_t> g_mapped;  // buffers of cb200_host_alloc_batch: mmap + cudaHostRegister
+
+void* cb200_host_alloc_batch(size_t n, size_t unit_bytes) {
+  if (require_ready()) return nullptr;
+  Runtime& r = rt();
+  const size_t nd = r.devs.size();
+  const size_t bytes = n * unit_bytes;
+  if (bytes == 0) return nullptr;
+  const size_t page = 4096, len = (bytes + page - 1) / page * page;
+  void* p = mmap(nullptr, len, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+  if (p == MAP_FAILED) {
+    set_error("cb200_host_alloc_batch(%zu x %zu): mmap failed", n, unit_bytes);
+    return nullptr;
+  }
+  std::mutex mu;
+  std::condition_variable cv;
+  size_t done = 0;
+  for (size_t s = 0; s < nd; s++) {
+    // page-rounded byte range of rows [n s / nd, n (s + 1) / nd)
+    size_t lo = (n * s / nd) * unit_bytes / page * page, hi = (n * (s + 1) / nd) * unit_bytes / page * page;
+    if (s + 1 == nd) hi = len;
+    post(*r.devs[s], [&, lo, hi] {
+      if (hi > lo) memset((char*)p + lo, 0, hi - lo);
+      std::lock_guard<std::mutex> lk(mu);
+      done++;
+      cv.notify_one();
+    });
+  }
+  {
+    std::unique_lock<std::mutex> lk(mu);
+    cv.wait(lk, [&] { return done == nd; });
+  }
+  if (cudaHostRegister(p, len, cudaHostRegisterPortable) != cudaSuccess) {
+    set_error("cb200_host_alloc_batch: cudaHostRegister(%zu) failed: %s", len, cudaGetErrorString(cudaGetLastError()));
+    munmap(p, len);
+    return nullptr;
+  }
+  std::lock_guard<std::mutex> lk(g_map_mu);
+  g_mapped[p] = len;
+  return p;
+}
 void cb200_host_free(void* p) {
-  if (p) cudaFreeHost(p);
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lk(g_map_mu);
+    auto it = g_mapped.find(p);
+    if (it != g_mapped.end()) {
+      cudaHostUnregister(p);
+      munmap(p, it->second);
+      g_mapped.erase(it);
+      return;
+    }
+  }
+  cudaFreeHost(p);
 }
 
 uint64_t cb200_launch_count(void) { return rt().launches.load(); }

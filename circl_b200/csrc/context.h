@@ -46,6 +46,8 @@ struct WorkSet {
   cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   cudaStream_t copy = nullptr;  // result pushes (cb200_gather_push): copy-engine traffic beside the kernels
   cudaEvent_t ev_copy = nullptr;
+  void* fix[2] = {nullptr, nullptr};  // per lane: streams a sampler kernel left unfinished (mlkem.cu, sample_fix_kernel)
+  size_t fix_bytes[2] = {0, 0};
   void* small = nullptr;  // 256-byte device buffer (ML-DSA context string of a device-pointer call)
   void* pin = nullptr;    // 64 bytes of pinned host memory (per-round counters of the signing loop)
   std::mutex mu;          // callers sharing this set enqueue one after the other
@@ -102,7 +104,7 @@ enum KernelId {
   KID_MLKEM_HASH_EK, KID_MLKEM_G, KID_MLKEM_SAMPLE, KID_MLKEM_ENCRYPT,
   KID_DIL_NTT, KID_DIL_INVNTT, KID_DIL_DOT, KID_DIL_EW,
   KID_MLDSA_EXPAND, KID_MLDSA_MU, KID_MLDSA_MASK, KID_MLDSA_W, KID_MLDSA_CHALLENGE, KID_MLDSA_RESPONSE,
-  KID_MLDSA_COMPACT, KID_X25519, KID_HYBRID_GLUE, KID_KECCAK, KID_SAMPLER, KID_COUNT
+  KID_MLDSA_COMPACT, KID_X25519, KID_HYBRID_GLUE, KID_KECCAK, KID_SAMPLER, KID_MLKEM_SAMPLE_FIX, KID_COUNT
 };
 const char* kernel_name(int id);
 
@@ -130,6 +132,8 @@ int ensure_scratch(int slot, size_t bytes);
 // slot = level-0 area of that work set, kLevel1 + slot = its level-1 area
 int ensure_work(int slot, size_t bytes, void** out);
 int ensure_pinned(size_t bytes, void** out);
+// grow-only per-lane list area of a work set; zero-filled (on `st`) whenever it is (re)allocated
+int ensure_fix(int slot, int lane, size_t bytes, cudaStream_t st, void** out);
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per (device, kernel)
 int ensure_smem_attr(const void* func, int bytes);
 inline void count_launch(uint64_t n = 1) { rt().launches.fetch_add(n, std::memory_order_relaxed); }

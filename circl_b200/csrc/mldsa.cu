@@ -549,7 +549,10 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
         acc[4 * q + 3] += mont_mul(x.w, z[q].w);
       }
       __syncwarp();  // every lane of the octet is done with the slot
-      if (v == 0 && c + kWSlots < n_chunks) issue(c + kWSlots);
+      if (v == 0 && c + kWSlots < n_chunks) {
+        fence_proxy_async();  // the reads above (generic proxy) before the asynchronous refill of the slot
+        issue(c + kWSlots);
+      }
     }
 #pragma unroll
     for (int q = 0; q < 32; q++) acc[q] = reduce_le2q(acc[q]);
@@ -993,7 +996,8 @@ __global__ void __launch_bounds__(128) finalize_kernel(const uint32_t* __restric
     if (lane < head) zd[lane] = zs[lane];
     uint32_t* dw = reinterpret_cast<uint32_t*>(zd + head);
     const int nw = (ZB - head) >> 2;
-    for (int j = lane; j < nw; j += 32) dw[j] = __funnelshift_r(zw[j], zw[j + 1], 8 * head);
+    // head == 0: the shift is 0 and word j + 1 of the last iteration would lie past the row
+    for (int j = lane; j < nw; j += 32) dw[j] = __funnelshift_r(zw[j], head ? zw[j + 1] : 0u, 8 * head);
     for (int i = head + 4 * nw + lane; i < ZB; i += 32) zd[i] = zs[i];
     if (lane == 0) {
       uint8_t* hb = sg + CTILDE + L * POLY_Z;  // PackHint (internal/pack.go:77-95)

@@ -215,6 +215,32 @@ __device__ __forceinline__ void uniform_stream(uint64_t (&a)[25], uint32_t* row_
     wp = reject_block<true>(a, wp, wend);
   } while (wp < wend);
 }
+// The same with exactly three blocks -- what 99 % of the streams need -- so that all lanes of a warp and
+// all warps of a CTA finish together; returns the number of coefficients accepted.  A stream that is short of 256 is
+// handed, with its sponge state, to sample_fix_kernel: a warp no longer squeezes a fourth block for all 32 lanes
+// because one of them needs it (27 % of the warps did), and no CTA waits at its barrier for such a warp.
+__device__ __forceinline__ int uniform_stream3(uint64_t (&a)[25], uint32_t* row_words) {
+  int16_t* row = reinterpret_cast<int16_t*>(row_words);
+  const uint32_t w0 = smem_u32(row);
+  uint32_t wp = w0;
+  const uint32_t wend = wp + 2 * N;
+#pragma unroll 1
+  for (int b = 0; b < 2; b++) {
+    keccak::f1600(a);
+    wp = reject_block<false>(a, wp, wend);
+  }
+  keccak::f1600(a);
+  wp = reject_block<true>(a, wp, wend);
+  return (int)((min(wp, wend) - w0) >> 1);
+}
+struct Pending {  // one unfinished SHAKE128 stream
+  uint32_t stream, count;
+  uint64_t a[25];
+};
+struct FixList {  // in front of the Pending array (64 bytes)
+  unsigned int n, done, pad[14];
+};
+
 // One SHAKE256 PRF stream of DeriveNoise (sample.go:31-95): `a` holds the absorbed, padded block seed || nonce
 template <int ETA>
 __device__ __forceinline__ void noise_stream(uint64_t (&a)[25], int16_t* __restrict__ dst) {
@@ -240,7 +266,7 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
                                                      const uint64_t* __restrict__ r, size_t n,
                                                      int16_t* __restrict__ A, int16_t* __restrict__ noise,
                                                      size_t mat_blocks, int transpose, int n_noise, int r_words,
-                                                     int n_eta1) {
+                                                     int n_eta1, FixList* __restrict__ fix) {
   // rho0 + key*ek_stride is rho of that key; transpose = 1 derives A^T (encryption), 0 derives A (key
   // generation, mat.go:13-29); n_noise PRF streams per op, seeded by r[op*r_words .. +4); the first n_eta1
   // nonces use eta1 (3 for ML-KEM-512), the others eta2 = 2
@@ -264,7 +290,15 @@ __global__ void __launch_bounds__(128) sample_kernel(const uint8_t* __restrict__
     // m[i][j] = XOF(rho, x, y) with (x, y) = (i, j) if transpose else (j, i)
     a[4] = (uint64_t)(transpose ? i : j) | ((uint64_t)(transpose ? j : i) << 8) | (0x1full << 16);
     a[20] = 0x8000000000000000ull;                               // rate 168
-    uniform_stream(a, rows + threadIdx.x * kRowWords);
+    const int got = uniform_stream3(a, rows + threadIdx.x * kRowWords);
+    if (live && got < N) {  // ~1 % of the streams: finished by sample_fix_kernel from this state
+      Pending* list = reinterpret_cast<Pending*>(fix + 1);
+      Pending& e = list[atomicAdd(&fix->n, 1u)];
+      e.stream = (uint32_t)s;
+      e.count = (uint32_t)got;
+#pragma unroll
+      for (int w = 0; w < 25; w++) e.a[w] = a[w];
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int p = warp; p < (int)blockDim.x; p += blockDim.x / 32) {
@@ -398,6 +432,69 @@ __device__ __forceinline__ void load_words_C(const uint32_t* __restrict__ poly, 
 }
 
 constexpr int kEncThreads = 128;  // 16 octets = 16 operations per CTA (decrypt / keygen kernels)
+
+// The streams sample_kernel left short of 256 coefficients: thread per stream, squeeze on from the saved state and
+// append to the polynomial in A (2-byte global stores; about 1 % of the streams, one or two dozen coefficients each).
+template <int K>
+__global__ void __launch_bounds__(64) sample_fix_kernel(FixList* __restrict__ fix, size_t nkeys, int16_t* __restrict__ A) {
+  __shared__ uint64_t sq[64][21];
+  const Pending* list = reinterpret_cast<const Pending*>(fix + 1);
+  const unsigned int total = fix->n;
+  for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    uint64_t a[25];
+#pragma unroll
+    for (int w = 0; w < 25; w++) a[w] = list[i].a[w];
+    const size_t sp = list[i].stream;
+    int16_t* dst = A + ((sp % nkeys) * K * K + sp / nkeys) * N;
+    int cnt = (int)list[i].count;
+    uint8_t* blk = reinterpret_cast<uint8_t*>(sq[threadIdx.x]);
+    while (cnt < N) {
+      keccak::f1600(a);
+#pragma unroll
+      for (int w = 0; w < 21; w++) sq[threadIdx.x][w] = a[w];
+#pragma unroll 1
+      for (int f = 0; f < 112 && cnt < N; f++) {  // sample.go:203-233: 12-bit candidates, low half of each 3 bytes first
+        const int byte = (3 * f) >> 1;
+        uint32_t d = (uint32_t)blk[byte] | ((uint32_t)blk[byte + 1] << 8);
+        d = ((f & 1) ? d >> 4 : d) & 0xfff;
+        if (d < (uint32_t)Q) dst[cnt++] = (int16_t)d;
+      }
+    }
+  }
+  // the last CTA to finish empties the list for the next launch on this lane
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    if (atomicAdd(&fix->done, 1u) == gridDim.x - 1) {
+      fix->n = 0;
+      fix->done = 0;
+    }
+  }
+}
+
+// sample_kernel + sample_fix_kernel on stream `ls`; `lane` picks the unfinished-stream list of the work set
+template <int K>
+static int launch_sample(int slot, int lane, cudaStream_t ls, const uint8_t* rho0, size_t ek_stride, size_t nkeys,
+                         const uint64_t* r, size_t n, int16_t* A, int16_t* noise, int transpose, int n_noise, int r_words,
+                         int n_eta1) {
+  if (int arc = ensure_smem_attr((const void*)sample_kernel<K>, kSampleSmem)) return arc;
+  const size_t streams = nkeys * K * K, mat_blocks = (streams + 127) / 128, noise_blocks = (n * n_noise + 127) / 128;
+  void* fix = nullptr;
+  if (int frc = ensure_fix(slot, lane, sizeof(FixList) + (streams ? streams : 1) * sizeof(Pending), ls, &fix)) return frc;
+  if (mat_blocks + noise_blocks == 0) return 0;
+  {
+    KernelScope ks(KID_MLKEM_SAMPLE, ls);
+    sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
+        rho0, ek_stride, nkeys, r, n, A, noise, mat_blocks, transpose, n_noise, r_words, n_eta1, (FixList*)fix);
+  }
+  if (streams) {
+    KernelScope ks(KID_MLKEM_SAMPLE_FIX, ls);
+    const unsigned grid = (unsigned)std::min<size_t>(64, (streams / 64 + 63) / 64 + 1);  // ~1 % of the streams, 64 per CTA
+    sample_fix_kernel<K><<<grid, 64, 0, ls>>>((FixList*)fix, nkeys, A);
+  }
+  CB200_CUDA(cudaGetLastError());
+  return 0;
+}
 
 // ------------------------------------------------------------------ 3. K-PKE.Encrypt (cpapke.go:137-181), one octet per op
 // u = InvNTT(A^T o NTT(r)) + e1, v = InvNTT(t o NTT(r)) + e2 + Decompress(m), ct = Compress(u) || Compress(v).  What leaves
@@ -976,12 +1073,9 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
     int16_t* A = (int16_t*)(b + o_A[l]);
     int16_t* noise = (int16_t*)(b + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
-    const size_t mat_blocks = (cnt * K * K + 127) / 128, noise_blocks = (cnt * P::n_noise + 127) / 128;
-    {
-      KernelScope ks(KID_MLKEM_SAMPLE, ls);
-      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
-          ek + 384 * K + first * dk_stride, dk_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks, 1, P::n_noise, 4, K);
-    }
+    if (int src = launch_sample<K>(slot, l, ls, ek + 384 * K + first * dk_stride, dk_stride, cnt, r + 4 * first, cnt, A, noise,
+                                   1, P::n_noise, 4, K))
+      return src;
     if (int erc = launch_encrypt<K>(ek + first * dk_stride, dk_stride, A, 0, noise, mprime + 32 * first, cnt,
                                     ct2 + first * P::ct_bytes, nullptr, nullptr, 1, ls))
       return erc;
@@ -1167,12 +1261,10 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
     int16_t* A = (int16_t*)(b + o_A[l]);
     int16_t* noise = (int16_t*)(b + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
-    const size_t mat_blocks = (cnt * K * K + 127) / 128, noise_blocks = (cnt * 2 * K + 127) / 128;
-    {  // A (not transposed) from rho = rs[0..4), s/e noise from sigma = rs[4..8)
-      KernelScope ks(KID_MLKEM_SAMPLE, ls);
-      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
-          (const uint8_t*)(rs + 8 * first), 64, cnt, rs + 8 * first + 4, cnt, A, noise, mat_blocks, 0, 2 * K, 8, 2 * K);
-    }
+    // A (not transposed) from rho = rs[0..4), s/e noise from sigma = rs[4..8)
+    if (int src = launch_sample<K>(slot, l, ls, (const uint8_t*)(rs + 8 * first), 64, cnt, rs + 8 * first + 4, cnt, A, noise, 0,
+                                   2 * K, 8, 2 * K))
+      return src;
     {
       KernelScope ks(KID_MLKEM_ENCRYPT, ls);
       keygen_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
@@ -1282,12 +1374,9 @@ static int r3_encrypt(const uint8_t* ek, size_t ek_stride, const uint8_t* h, siz
     int16_t* A = (int16_t*)(base + o_A[l]);
     int16_t* noise = (int16_t*)(base + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
-    const size_t mat_blocks = (cnt * K * K + 127) / 128, noise_blocks = (cnt * P::n_noise + 127) / 128;
-    {
-      KernelScope ks(KID_MLKEM_SAMPLE, ls);
-      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
-          ek + 384 * K + first * ek_stride, ek_stride, cnt, r + 4 * first, cnt, A, noise, mat_blocks, 1, P::n_noise, 4, K);
-    }
+    if (int src = launch_sample<K>(slot, l, ls, ek + 384 * K + first * ek_stride, ek_stride, cnt, r + 4 * first, cnt, A, noise,
+                                   1, P::n_noise, 4, K))
+      return src;
     if (int erc = launch_encrypt<K>(ek + first * ek_stride, ek_stride, A, 0, noise, m + 32 * first, cnt,
                                     ct + first * P::ct_bytes, nullptr, nullptr, 1, ls))
       return erc;
@@ -1411,12 +1500,10 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
     KernelScope ks(KID_MLKEM_G, st);
     g_kernel<<<(unsigned)((n + 127) / 128), 128, 0, st>>>(seeds, (const uint8_t*)h, shared ? 0 : 32, n, ss, r);
   }
-  if (shared) {  // one key: A^T is derived once, before the sub-batches fork
-    KernelScope ks(KID_MLKEM_SAMPLE, st);
-    sample_kernel<K><<<(unsigned)((K * K + 127) / 128), 128, kSampleSmem, st>>>(
-        ek + 384 * K, 0, 1, r, 0, (int16_t*)((char*)base + o_A[0]), (int16_t*)((char*)base + o_n[0]), (K * K + 127) / 128, 1,
-        P::n_noise, 4, K);
-  }
+  if (shared)  // one key: A^T is derived once, before the sub-batches fork
+    if (int src = launch_sample<K>(slot, 0, st, ek + 384 * K, 0, 1, r, 0, (int16_t*)((char*)base + o_A[0]),
+                                   (int16_t*)((char*)base + o_n[0]), 1, P::n_noise, 4, K))
+      return src;
   // Sub-batches alternate between two internal streams (fork/join on events): the tail wave of one
   // sub-batch's kernels overlaps the next sub-batch instead of idling SMs.
   CB200_CUDA(cudaEventRecord(ws.ev_fork, st));
@@ -1429,14 +1516,9 @@ static int encaps_device(const uint8_t* ek, size_t ek_stride, const uint8_t* see
     int16_t* noise = (int16_t*)((char*)base + o_n[l]);
     const size_t cnt = (n - first < sub) ? n - first : sub;
     const size_t keys_here = shared ? 0 : cnt;
-    const size_t mat_blocks = (keys_here * K * K + 127) / 128;
-    const size_t noise_blocks = (cnt * P::n_noise + 127) / 128;
-    {
-      KernelScope ks(KID_MLKEM_SAMPLE, ls);
-      sample_kernel<K><<<(unsigned)(mat_blocks + noise_blocks), 128, kSampleSmem, ls>>>(
-          ek + 384 * K + (shared ? 0 : first * ek_stride), ek_stride, keys_here, r + 4 * first, cnt, A, noise,
-          mat_blocks, 1, P::n_noise, 4, K);
-    }
+    if (int src = launch_sample<K>(slot, l, ls, ek + 384 * K + (shared ? 0 : first * ek_stride), ek_stride, keys_here,
+                                   r + 4 * first, cnt, A, noise, 1, P::n_noise, 4, K))
+      return src;
     if (int erc = launch_encrypt<K>(ek + (shared ? 0 : first * ek_stride), ek_stride, A, shared ? 1 : 0, noise,
                                     seeds + 32 * first, cnt, ct + first * P::ct_bytes, ss + 32 * first,
                                     status ? status + first : nullptr, 0, ls))

@@ -37,6 +37,29 @@ def release_stream(cuda_stream_handle: int | None) -> None:
     check(lib().cb200_release_stream(cuda_stream_handle))
 
 
+def host_batch(n: int, unit_bytes: int):
+    """(n, unit_bytes) uint8 numpy array in pinned memory for a batch that host-pointer calls split over all active GPUs:
+    each GPU's rows sit on that GPU's NUMA node (cb200_host_alloc_batch).  Release with host_free(array)."""
+    import ctypes as C
+
+    import numpy as np
+    p = lib().cb200_host_alloc_batch(n, unit_bytes)
+    if not p:
+        raise MemoryError(lib().cb200_last_error().decode())
+    a = np.frombuffer((C.c_uint8 * (n * unit_bytes)).from_address(p), dtype=np.uint8).reshape(n, unit_bytes)
+    _host_batches[a.ctypes.data] = p
+    return a
+
+
+def host_free(a) -> None:
+    p = _host_batches.pop(a.ctypes.data, None)
+    if p is not None:
+        lib().cb200_host_free(p)
+
+
+_host_batches: dict = {}
+
+
 def shutdown() -> None:
     lib().cb200_shutdown()
 

@@ -78,6 +78,10 @@ int cb200_gather_push(void *dst, const void *src, size_t bytes);
 int cb200_gather_flush(const void *any_local_row, int wait_on_host);
 /* Pinned host memory for large batches handed to Go via unsafe.Slice. */
 void *cb200_host_alloc(size_t bytes);
+/* The same for one array of a batch (n rows of unit_bytes) that host-pointer calls will split over all active GPUs
+ * (cb200_init_devices): the rows of each GPU's shard are placed on that GPU's NUMA node, so that all GPUs copy at link
+ * speed at the same time instead of sharing the socket interconnect.  Freed with cb200_host_free. */
+void *cb200_host_alloc_batch(size_t n, size_t unit_bytes);
 void cb200_host_free(void *p);
 /* number of kernels launched by this library since init (bench accounting) */
 uint64_t cb200_launch_count(void);

@@ -511,6 +511,29 @@ def bench_mlkem(cx: Ctx, wl_key: str, log2n: int, steps: int, warmup: int, with_
                "host_vs_device_outputs_equal": same,
                "numa": "rank thread and its pinned buffers bound to the %d CPUs next to its GPU" % cx.numa_cpus
                        if cx.numa_cpus else "topology unknown, unbound"}
+        # The floor of that number on this box: the same bytes of the same pinned buffers, copied in and out at the same
+        # time on two streams by every rank at once, and no kernel at all.
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+        def copies_only():
+            with torch.cuda.stream(s_in):
+                eks_d.copy_(eks_h, non_blocking=True)
+                seeds_d.copy_(seeds_h, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                ct_h.copy_(ct_d, non_blocking=True)
+                ss_h.copy_(ss_d, non_blocking=True)
+        copies_only()
+        torch.cuda.synchronize()
+        cx.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copies_only()
+        torch.cuda.synchronize()
+        copy_ms = cx.max_over_ranks(1e3 * (time.perf_counter() - t0) / e2e_steps)
+        cx.barrier()
+        e2e["copies_only_ms_per_step"] = copy_ms
+        e2e["copies_only_GBps_per_direction_all_ranks"] = world * n * (wl["ek"] + 32) / (copy_ms * 1e6)
+        e2e["share_of_copy_floor"] = copy_ms / e2e_ms
 
     # ---- per-kernel event timing (separate pass, not part of `value`)
     roofline = None

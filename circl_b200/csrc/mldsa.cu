@@ -485,24 +485,40 @@ __device__ __forceinline__ void decompose(uint32_t a, uint32_t& a0plusq, uint32_
 // each octet keeps kWSlots 1 KB bulk copies (TMA engine, one mbarrier per slot) in flight into the octet's ring in
 // shared memory, always kWSlots polynomials ahead of the arithmetic, also across the end of a row, so the DRAM
 // latency of the next row hides behind the inverse NTT and Decompose of the current one.
-constexpr int kWSlots = 3;
-constexpr int kWSmem = 16 * kWSlots * 1024 + 16 * kPolyWords * 4 + 16 * kWSlots * 8;
+// Measured on a B200 (profiles/r02_sweeps.txt, ML-DSA-65, 2^18 signatures): the kernel is bound by latency, not by a pipe
+// or by HBM, and resident warps are what it responds to.  Twiddles read from shared memory (154 -> 120 registers) and a
+// ring of two slots instead of three fit four CTAs per SM instead of three: 20.9 -> 18.7 ms per step.  Summing the L
+// products of a coefficient as 64-bit integers with one Montgomery reduction at the end saves a tenth of the
+// instructions but costs 32 registers (19.3 ms at three CTAs, 19.9 ms with spills at four); y-hat one polynomial ahead
+// in registers costs another 32 and is far slower at two CTAs per SM (33 ms).
+constexpr int kWSlots = 2;
+constexpr int kWCtas = 4;  // CTAs per SM the grid and the register allocation are sized for
+struct WSm {
+  static constexpr int ring = 16 * kWSlots * 1024, tiles = 16 * kPolyWords * 4, bars = 16 * kWSlots * 8;
+  static constexpr int bytes = ring + tiles + bars + 1024;  // + the inverse twiddles
+};
 template <class P>
-__global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
-                                                const uint32_t* __restrict__ A, const uint32_t* __restrict__ yh,
-                                                uint32_t* __restrict__ w0, uint8_t* __restrict__ w1u,
-                                                const uint32_t* __restrict__ owner, const uint32_t* __restrict__ zetas) {
+__global__ void __launch_bounds__(128, kWCtas) w_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
+                                                        const uint32_t* __restrict__ A, const uint32_t* __restrict__ yh,
+                                                        uint32_t* __restrict__ w0, uint8_t* __restrict__ w1u,
+                                                        const uint32_t* __restrict__ owner, const uint32_t* __restrict__ zetas) {
   MLDSA_USE(P);
+  using S = WSm;
+  constexpr int SLOTS = kWSlots;
   extern __shared__ __align__(128) uint8_t wsm[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7, ob = warp * 4 + oct;
-  uint32_t* ring = reinterpret_cast<uint32_t*>(wsm) + ob * (kWSlots * 256);
-  uint32_t* tile = reinterpret_cast<uint32_t*>(wsm + 16 * kWSlots * 1024) + ob * kPolyWords;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + 16 * kWSlots * 1024 + 16 * kPolyWords * 4) + ob * kWSlots;
+  uint32_t* ring = reinterpret_cast<uint32_t*>(wsm) + ob * (SLOTS * 256);
+  uint32_t* tile = reinterpret_cast<uint32_t*>(wsm + S::ring) + ob * kPolyWords;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(wsm + S::ring + S::tiles) + ob * SLOTS;
   if (v == 0) {
 #pragma unroll
-    for (int q = 0; q < kWSlots; q++) mbar_init(bars + q, 1);
+    for (int q = 0; q < SLOTS; q++) mbar_init(bars + q, 1);
     fence_barrier_init();
   }
+  // the per-lane twiddles of the inverse transform are read from shared memory where they are used: thirty registers
+  // less across the product loop
+  volatile uint32_t* izs = reinterpret_cast<volatile uint32_t*>(wsm + S::ring + S::tiles + S::bars);
+  for (int q = threadIdx.x; q < 256; q += blockDim.x) izs[q] = zetas[256 + q];
   __syncthreads();
   const size_t total = nact * K, G = (size_t)gridDim.x * 16, first = ((size_t)blockIdx.x * 4 + warp) * 4;
   if (first >= total) return;
@@ -512,18 +528,16 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
     const size_t u = first + it * G + oct;
     return u < total ? u : total - 1;  // octets past the end repeat the last unit and store nothing
   };
-  auto issue = [&](size_t c) {  // lane 0 of the octet: fetch polynomial c % L of row unit(c / L) into slot c % kWSlots
+  auto issue = [&](size_t c) {  // lane 0 of the octet: fetch polynomial c % L of row unit(c / L) into slot c % SLOTS
     const size_t u = unit(c / L);
     const size_t own = key_shared ? 0 : owner[act[u / K]];
     const uint32_t* src = A + (own * (size_t)(K * L) + (u % K) * L + c % L) * N;
-    uint64_t* bar = bars + c % kWSlots;
+    uint64_t* bar = bars + c % SLOTS;
     mbar_expect_tx(bar, 1024);
-    bulk_g2s(ring + (c % kWSlots) * 256, src, 1024, bar);
+    bulk_g2s(ring + (c % SLOTS) * 256, src, 1024, bar);
   };
   if (v == 0)
-    for (size_t c = 0; c < (size_t)kWSlots && c < n_chunks; c++) issue(c);
-  LaneTw t;
-  load_lane_tw_inv(t, zetas + 256, v);
+    for (size_t c = 0; c < (size_t)SLOTS && c < n_chunks; c++) issue(c);
   size_t c = 0;
   for (size_t it = 0; it < n_it; it++) {
     const size_t u = unit(it);
@@ -537,8 +551,8 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
     for (int j = 0; j < L; j++, c++) {
       uint4 z[8];
       gload_I(yh + (op * L + j) * N, v, z);  // issued before the wait: overlaps the tail of the bulk copy
-      const int slot = (int)(c % kWSlots);
-      mbar_wait(bars + slot, (uint32_t)((c / kWSlots) & 1));
+      const int slot = (int)(c % SLOTS);
+      mbar_wait(bars + slot, (uint32_t)((c / SLOTS) & 1));
       const uint4* xs = reinterpret_cast<const uint4*>(ring + slot * 256) + v;
 #pragma unroll
       for (int q = 0; q < 8; q++) {
@@ -549,15 +563,15 @@ __global__ void __launch_bounds__(128) w_kernel(const uint32_t* __restrict__ act
         acc[4 * q + 3] += mont_mul(x.w, z[q].w);
       }
       __syncwarp();  // every lane of the octet is done with the slot
-      if (v == 0 && c + kWSlots < n_chunks) {
+      if (v == 0 && c + SLOTS < n_chunks) {
         fence_proxy_async();  // the reads above (generic proxy) before the asynchronous refill of the slot
-        issue(c + kWSlots);
+        issue(c + SLOTS);
       }
     }
 #pragma unroll
     for (int q = 0; q < 32; q++) acc[q] = reduce_le2q(acc[q]);
     i_to_c(acc, tile, v);
-    invntt_octet(acc, tile, v, t);  // -> S layout: acc[2s+b] = coefficient 16s + 2v + b
+    invntt_octet_smem(acc, tile, v, izs);  // -> S layout: acc[2s+b] = coefficient 16s + 2v + b
     uint32_t* w0p = w0 + (op * K + i) * N;
     uint8_t* w1b = w1u + (op * K + i) * SignW1<P>::stride;
 #pragma unroll
@@ -1709,7 +1723,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
 
   if (int arc = ensure_smem_attr((const void*)expand_a_kernel<P>, kExpThreads * kExpRow * 4)) return arc;
   if (kChSmem) if (int arc = ensure_smem_attr((const void*)challenge_kernel<P>, kChSmem)) return arc;
-  if (int arc = ensure_smem_attr((const void*)w_kernel<P>, kWSmem)) return arc;
+  if (int arc = ensure_smem_attr((const void*)w_kernel<P>, WSm::bytes)) return arc;
   auto blocks = [](size_t units, size_t per) { return (unsigned)((units + per - 1) / per); };
   {
     KernelScope ks(KID_MLDSA_EXPAND, st);
@@ -1759,7 +1773,7 @@ static int sign_device(const uint8_t* sk, size_t sk_stride, const uint8_t* msgs,
     }
     {
       KernelScope ks(KID_MLDSA_W, st);
-      w_kernel<P><<<pgrid(ns * K, 3), 128, kWSmem, st>>>(sl, ns, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, w.owner, zetas);
+      w_kernel<P><<<pgrid(ns * K, kWCtas), 128, WSm::bytes, st>>>(sl, ns, shared ? 1 : 0, w.A, w.yh, w.w0, w.w1u, w.owner, zetas);
     }
     {
       KernelScope ks(KID_MLDSA_CHALLENGE, st);

@@ -25,8 +25,10 @@ void set_error(const char* fmt, ...) {
 }
 
 Runtime& rt() {
-  static Runtime r;
-  return r;
+  // never destroyed: a process that exits without cb200_shutdown() must not join worker threads or release CUDA
+  // objects from a static destructor (the CUDA runtime may already be gone by then)
+  static Runtime* r = new Runtime;
+  return *r;
 }
 
 // per-thread binding (see context.h)
@@ -278,7 +280,7 @@ static int dev_create(int device, std::unique_ptr<Dev>* out) {
     int rc = wset_create(d->staging[s]);
     if (rc) return rc;
   }
-  int32_t ktw[256];
+  int32_t ktw[512];
   kyber_fill_twiddles(ktw);
   CB200_CUDA(cudaMalloc(&d->kyber_tw, sizeof ktw));
   CB200_CUDA(cudaMemcpy(d->kyber_tw, ktw, sizeof ktw, cudaMemcpyHostToDevice));

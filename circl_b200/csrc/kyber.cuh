@@ -52,7 +52,7 @@ __host__ __device__ constexpr int32_t zetaq_of(int i) {
 }
 // compile-time loop: f(std::integral_constant<int, I>) for I in [B, E)
 template <int B, int E, class F>
-__device__ __forceinline__ void static_for(F&& f) {
+__host__ __device__ __forceinline__ void static_for(F&& f) {
   if constexpr (B < E) {
     f(std::integral_constant<int, B>{});
     static_for<B + 1, E>(f);
@@ -394,6 +394,246 @@ __device__ __forceinline__ void gstore_C(uint32_t* __restrict__ poly, int v, con
     stg_stream128(poly + 16 * v + 4 * c,
                   make_uint4(pack2(r[8 * c], r[8 * c + 1]), pack2(r[8 * c + 2], r[8 * c + 3]),
                              pack2(r[8 * c + 4], r[8 * c + 5]), pack2(r[8 * c + 6], r[8 * c + 7])));
+}
+
+// ---------------------------------------------------------------- "low" format fast path
+// A second register format for inputs inside the reference's contract.  A coefficient is a plain sign-extended
+// int32 ("low" format) and montReduce(zeta*b) (field.go:4-32) is evaluated in its Shoup form
+//     t = zp*b - q*n,   n = (kk*b + 32767) >> 16,
+// where zp = zeta * 2^-16 mod q (centred) and kk = (zp*2^16 - zeta) / q.  This is the same integer as the reference's
+// (zeta*b - m*q) / 2^16 with m = int16(zeta*b*q^-1) for EVERY int16 b: kk*q = -zeta (mod 2^16) gives kk*b = -m
+// (mod 2^16), hence kk*b + m = 2^16 n with n = floor((kk*b + 32767) / 2^16) because -32768 <= m <= 32767.
+// It costs 3 IMAD + 1 SHF instead of 3 IMAD + 2 SHF (no b >> 16: the operand already is sign-extended), i.e. a
+// 6-instruction butterfly -- but 32-bit adds no longer wrap where the reference's int16 adds would.  The kernels
+// therefore take this path only for polynomials whose coefficients are small enough that no intermediate value of
+// the reference can leave int16 (interval analysis of ntt.go:60-193 with |montReduce(zeta*b)| <= |b|*3328/2^16 +
+// 1665: |c| <= 13561 forward, |c| <= 3679 inverse; the reference's own contract is |c| <= q), checked on the packed
+// input words with one VIADDMNMX.U16x2 each; any other input runs through the high-half code above.  Both paths
+// return the reference's representatives bit for bit.
+constexpr int kFwdBound = 13561, kInvBound = 3679;
+
+__host__ __device__ constexpr int32_t zp_of(int i) {  // 17^brv7(i) mod q, centred
+  uint32_t z = 1, e = brv7((uint32_t)i);
+  for (uint32_t j = 0; j < e; j++) z = z * 17u % Q;
+  return (int32_t)z > Q / 2 ? (int32_t)z - Q : (int32_t)z;
+}
+__host__ __device__ constexpr int32_t kk_of(int i) { return (zp_of(i) * 65536 - zeta_of(i)) / Q; }
+template <int I>
+struct ZetaL {
+  static constexpr int32_t zp = zp_of(I);
+  static constexpr int32_t kk = kk_of(I);
+  static_assert(zp_of(I) * 65536 - zeta_of(I) == kk_of(I) * Q, "kk is an exact quotient");
+};
+// montReduce(1441 * x) (ntt.go:187-192): 1441 = 2^32/128 mod q, so zp = 2^16/128 = 512
+constexpr int32_t kScaleZp = 512, kScaleKk = (512 * 65536 - 1441) / Q;
+static_assert(512 * 65536 - 1441 == kScaleKk * Q, "scale constant");
+struct TwLow {
+  int32_t zp, kk;
+};
+
+__host__ __device__ __forceinline__ int32_t mont_mul_lo(int32_t b, int32_t zp, int32_t kk) {
+  const int32_t n = (kk * b + 32767) >> 16;
+  return zp * b - n * Q;
+}
+__host__ __device__ __forceinline__ int32_t barrett_lo(int32_t x) { return x - ((x * 20159) >> 26) * Q; }  // field.go:45-64
+// Cooley-Tukey butterfly (ntt.go:129-131) in five instructions: a + t = (zp*b + a) - q*n is two multiply-adds, and
+// a - t = 2a - (a + t) one three-input add
+__host__ __device__ __forceinline__ void ct_lo(int32_t& a, int32_t& b, int32_t zp, int32_t kk) {
+  const int32_t n = (kk * b + 32767) >> 16;
+  const int32_t ap = (zp * b + a) - n * Q;
+  b = 2 * a - ap;
+  a = ap;
+}
+__host__ __device__ __forceinline__ void gs_lo(int32_t& a, int32_t& b, int32_t zp, int32_t kk) {
+  const int32_t t = b - a;
+  a = a + b;
+  b = mont_mul_lo(t, zp, kk);
+}
+__host__ __device__ __forceinline__ void unpack2_lo(uint32_t w, int32_t& lo, int32_t& hi) {
+  lo = (int32_t)(int16_t)(w & 0xffffu);
+  hi = (int32_t)w >> 16;
+}
+__host__ __device__ __forceinline__ uint32_t pack2_lo(int32_t lo, int32_t hi) {
+#ifdef __CUDA_ARCH__
+  return __byte_perm((uint32_t)lo, (uint32_t)hi, 0x5410);
+#else
+  return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+#endif
+}
+// max over both halves of all 16 words of (coefficient + bound) as unsigned 16-bit numbers: <= 2*bound iff every
+// coefficient is in [-bound, bound]
+__host__ __device__ __forceinline__ bool words_in_range(const uint32_t (&w)[16], uint32_t bound) {
+#ifdef __CUDA_ARCH__
+  uint32_t acc = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) acc = __viaddmax_u16x2(w[i], bound * 0x10001u, acc);
+  return __vmaxu2(acc, 2 * bound * 0x10001u) == 2 * bound * 0x10001u;
+#else  // the same predicate spelled out (host-side check of the fast path, tests/cpp/test_kyber_low.cu)
+  uint32_t mx = 0;
+  for (int i = 0; i < 16; i++)
+    for (int h = 0; h < 2; h++) {
+      const uint32_t u = ((w[i] >> (16 * h)) + bound) & 0xffffu;
+      mx = u > mx ? u : mx;
+    }
+  return mx <= 2 * bound;
+#endif
+}
+
+struct LaneTwLow {
+  TwLow l8[2], l4[4], l2[8];
+};
+__host__ __device__ __forceinline__ void load_lane_tw_lo(LaneTwLow& t, const TwLow* tab, int v) {
+#pragma unroll
+  for (int i = 0; i < 2; i++) t.l8[i] = tab[16 + 2 * v + i];
+#pragma unroll
+  for (int i = 0; i < 4; i++) t.l4[i] = tab[32 + 4 * v + i];
+#pragma unroll
+  for (int i = 0; i < 8; i++) t.l2[i] = tab[64 + 8 * v + i];
+}
+__host__ __device__ __forceinline__ TwLow twl_at(const volatile TwLow* tab, int k) {
+  const volatile int2* p = reinterpret_cast<const volatile int2*>(tab + k);
+  TwLow t;
+  t.zp = p->x;
+  t.kk = p->y;
+  return t;
+}
+
+__host__ __device__ __forceinline__ void fwd_pass_S_lo(int32_t (&r)[32]) {
+#pragma unroll
+  for (int i = 0; i < 16; i++) ct_lo(r[i], r[i + 16], ZetaL<1>::zp, ZetaL<1>::kk);
+  static_for<0, 2>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 8; i++) ct_lo(r[16 * h + i], r[16 * h + i + 8], ZetaL<2 + h>::zp, ZetaL<2 + h>::kk);
+  });
+  static_for<0, 4>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 4; i++) ct_lo(r[8 * h + i], r[8 * h + i + 4], ZetaL<4 + h>::zp, ZetaL<4 + h>::kk);
+  });
+  static_for<0, 8>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 2; i++) ct_lo(r[4 * h + i], r[4 * h + i + 2], ZetaL<8 + h>::zp, ZetaL<8 + h>::kk);
+  });
+}
+__host__ __device__ __forceinline__ void fwd_pass_C_lo(int32_t (&r)[32], const LaneTwLow& t) {
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) ct_lo(r[16 * blk + j], r[16 * blk + j + 8], t.l8[blk].zp, t.l8[blk].kk);
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++)
+#pragma unroll
+    for (int j = 0; j < 4; j++) ct_lo(r[8 * blk + j], r[8 * blk + j + 4], t.l4[blk].zp, t.l4[blk].kk);
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++)
+#pragma unroll
+    for (int j = 0; j < 2; j++) ct_lo(r[4 * blk + j], r[4 * blk + j + 2], t.l2[blk].zp, t.l2[blk].kk);
+}
+__host__ __device__ __forceinline__ void inv_pass_C_lo(int32_t (&r)[32], const volatile TwLow* tab, int v) {
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++) {
+    const TwLow t = twl_at(tab, 127 - 8 * v - blk);
+#pragma unroll
+    for (int j = 0; j < 2; j++) gs_lo(r[4 * blk + j], r[4 * blk + j + 2], t.zp, t.kk);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++) {
+    const TwLow t = twl_at(tab, 63 - 4 * v - blk);
+#pragma unroll
+    for (int j = 0; j < 4; j++) gs_lo(r[8 * blk + j], r[8 * blk + j + 4], t.zp, t.kk);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++) {
+    const TwLow t = twl_at(tab, 31 - 2 * v - blk);
+#pragma unroll
+    for (int j = 0; j < 8; j++) gs_lo(r[16 * blk + j], r[16 * blk + j + 8], t.zp, t.kk);
+  }
+  r[16] = barrett_lo(r[16]);
+  r[17] = barrett_lo(r[17]);
+}
+// the lazy Barrett schedule of inv_pass_S, on low-format registers
+__host__ __device__ __forceinline__ void inv_pass_S_lo(int32_t (&r)[32], int v) {
+  static_for<0, 8>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 2; i++) gs_lo(r[4 * h + i], r[4 * h + i + 2], ZetaL<15 - h>::zp, ZetaL<15 - h>::kk);
+  });
+#pragma unroll
+  for (int s = 0; s < 16; s += 4)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      if (v == 0) r[2 * s + b] = barrett_lo(r[2 * s + b]);
+      if (v <= 1) r[2 * (s + 2) + b] = barrett_lo(r[2 * (s + 2) + b]);
+    }
+  static_for<0, 4>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 4; i++) gs_lo(r[8 * h + i], r[8 * h + i + 4], ZetaL<7 - h>::zp, ZetaL<7 - h>::kk);
+  });
+#pragma unroll
+  for (int s = 0; s < 16; s += 8)
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+      if (v == 1) r[2 * s + b] = barrett_lo(r[2 * s + b]);
+      if (v >= 1 && v <= 3) r[2 * (s + 4) + b] = barrett_lo(r[2 * (s + 4) + b]);
+    }
+  static_for<0, 2>([&](auto hc) {
+    constexpr int h = decltype(hc)::value;
+#pragma unroll
+    for (int i = 0; i < 8; i++) gs_lo(r[16 * h + i], r[16 * h + i + 8], ZetaL<3 - h>::zp, ZetaL<3 - h>::kk);
+  });
+#pragma unroll
+  for (int b = 0; b < 2; b++) {
+    if (v == 2 || v == 3) r[b] = barrett_lo(r[b]);
+    if (v >= 2) r[16 + b] = barrett_lo(r[16 + b]);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; i++) gs_lo(r[i], r[i + 16], ZetaL<1>::zp, ZetaL<1>::kk);
+#pragma unroll
+  for (int i = 0; i < 32; i++) r[i] = mont_mul_lo(r[i], kScaleZp, kScaleKk);
+}
+
+// Unpacked S <-> C transposition for the fast path: registers travel as 128-bit groups of four, one group per
+// (writer lane, reader lane) pair, in a tile of 8 rows x 9 groups (144-byte rows): the eight lanes of an octet -- one
+// quarter-warp, i.e. one shared-memory transaction of a 128-bit access -- hit eight different 16-byte bank groups both
+// when they write (row = own lane, group = reader) and when they read (row = writer, group = own lane).
+// 8 STS.128 + 8 LDS.128 per lane replace 16 PRMT + 16 STS.32 + 4 LDS.128 + 32 unpacking instructions.
+constexpr int kWideTileBytes = 8 * 144;
+__host__ __device__ __forceinline__ void wide_store_S(unsigned char* tile, int v, const int32_t (&r)[32]) {
+  // S layout r[2s+b] = coefficient 16s + 2v + b: group u = r[4u..4u+3] = coefficients 32u + {2v, 2v+1, 16+2v, 17+2v}
+  int4* wr = reinterpret_cast<int4*>(tile + v * 144);
+#pragma unroll
+  for (int u = 0; u < 8; u++) wr[u] = make_int4(r[4 * u], r[4 * u + 1], r[4 * u + 2], r[4 * u + 3]);
+}
+__host__ __device__ __forceinline__ void wide_load_C(const unsigned char* tile, int v, int32_t (&r)[32]) {
+  const int4* rd = reinterpret_cast<const int4*>(tile + v * 16);
+#pragma unroll
+  for (int w = 0; w < 8; w++) {  // from writer lane w: C registers 2w, 2w+1, 16+2w, 17+2w
+    const int4 g = rd[9 * w];
+    r[2 * w] = g.x;
+    r[2 * w + 1] = g.y;
+    r[16 + 2 * w] = g.z;
+    r[17 + 2 * w] = g.w;
+  }
+}
+__host__ __device__ __forceinline__ void wide_store_C(unsigned char* tile, int v, const int32_t (&r)[32]) {
+  // C layout r[i] = coefficient 32v + i: group u (for reader lane u) = r[2u], r[2u+1], r[16+2u], r[17+2u]
+  int4* wr = reinterpret_cast<int4*>(tile + v * 144);
+#pragma unroll
+  for (int u = 0; u < 8; u++) wr[u] = make_int4(r[2 * u], r[2 * u + 1], r[16 + 2 * u], r[17 + 2 * u]);
+}
+__host__ __device__ __forceinline__ void wide_load_S(const unsigned char* tile, int v, int32_t (&r)[32]) {
+  const int4* rd = reinterpret_cast<const int4*>(tile + v * 16);
+#pragma unroll
+  for (int w = 0; w < 8; w++) {  // from writer lane w: coefficients 32w + {2v, 2v+1, 16+2v, 17+2v} = S registers 4w..4w+3
+    const int4 g = rd[9 * w];
+    r[4 * w] = g.x;
+    r[4 * w + 1] = g.y;
+    r[4 * w + 2] = g.z;
+    r[4 * w + 3] = g.w;
+  }
 }
 
 // ---------------------------------------------------------------- MulHat on C layout

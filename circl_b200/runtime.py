@@ -1,9 +1,19 @@
 """Process-level runtime helpers: one process per GPU (init) or one process driving several (init_devices)."""
 from __future__ import annotations
 
+import atexit
 import os
 
 from ._ffi import check, lib
+
+_atexit_registered = False
+
+
+def _shutdown_at_exit() -> None:
+    global _atexit_registered
+    if not _atexit_registered:  # worker threads and streams are released before the interpreter tears CUDA down
+        atexit.register(shutdown)
+        _atexit_registered = True
 
 
 def device_count() -> int:
@@ -15,12 +25,14 @@ def init(device: int | None = None) -> int:
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
     check(lib().cb200_init(device))
+    _shutdown_at_exit()
     return device
 
 
 def init_devices(ndev: int = 0) -> int:
     """One process drives GPUs 0..ndev-1 (0: all visible); host-pointer batches are sharded by index inside the library."""
     check(lib().cb200_init_devices(ndev))
+    _shutdown_at_exit()
     return int(lib().cb200_active_devices())
 
 

@@ -74,3 +74,20 @@ def test_cpp_host_layer_matches_oracle():
         b = blocks[name]
         assert (b["pk"], b["sk"]) == oracle.hybrid_keygen(name, hseed64)
         assert (b["ct"], b["ss"], 0) == oracle.hybrid_encaps(name, b["pk"], e32)
+
+
+def test_kyber_low_format_fast_path_on_host(tmp_path):
+    """csrc/kyber.cuh's low-format fast path compiled as host code (nvcc, no GPU): the Shoup-form Montgomery product
+    against montReduce for every twiddle and every int16, barrett_lo on every int16, and an emulated octet (the
+    kernels' own pass and transposition functions, lane after lane) against nttGeneric / invNTTGeneric on inputs up
+    to the bounds of the fast range, plus the range predicate (tests/cpp/test_kyber_low.cu)."""
+    import oracle
+    oracle.build()
+    exe = str(tmp_path / "kyber_low")
+    odir = os.path.join(ROOT, "oracle")
+    r = subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-O2", "-std=c++17", "--expt-relaxed-constexpr", "-Wno-deprecated-gpu-targets",
+                        os.path.join(ROOT, "tests", "cpp", "test_kyber_low.cu"), "-o", exe, "-L", odir, "-loracle",
+                        "-Xlinker", "-rpath=" + odir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout[-2000:]

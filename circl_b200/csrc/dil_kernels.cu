@@ -15,18 +15,18 @@ namespace dil {
 constexpr int kThreads = 128;
 constexpr int kOctetsPerCta = kThreads / 8;
 
-// In-place NTT / InvNTT: 1 KiB read + 1 KiB written per polynomial.
+// In-place NTT / InvNTT: 1 KiB read + 1 KiB written per polynomial.  Twiddle pairs of the C-layout pass come from a
+// staged shared-memory copy (dilithium.cuh: stage_pairs), those of the S-layout pass are immediates.
 template <bool INV>
-__global__ void __launch_bounds__(kThreads) ntt_kernel(uint32_t* __restrict__ polys, size_t n,
-                                                       const uint32_t* __restrict__ zetas /* [256 fwd | 256 inv] */) {
+__global__ void __launch_bounds__(kThreads, 6) ntt_kernel(uint32_t* __restrict__ polys, size_t n,
+                                                          const uint32_t* __restrict__ zetas /* dil_fill_twiddles */) {
   __shared__ __align__(16) uint32_t tiles[kOctetsPerCta * kPolyWords];
+  __shared__ __align__(8) uint2 pairs[256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
   uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
-  LaneTw t;
-  if (INV)
-    load_lane_tw_inv(t, zetas + 256, v);
-  else
-    load_lane_tw_fwd(t, zetas, v);
+  stage_pairs<INV>(pairs, zetas);
+  __syncthreads();
+  const volatile uint2* zs = pairs;
   const size_t stride = (size_t)gridDim.x * kOctetsPerCta;
   for (size_t base = ((size_t)blockIdx.x * 4 + warp) * 4; base < n; base += stride) {
     const size_t p = base + oct;
@@ -35,11 +35,11 @@ __global__ void __launch_bounds__(kThreads) ntt_kernel(uint32_t* __restrict__ po
     uint32_t r[32];
     if (!INV) {
       gload_S(poly, v, r);
-      ntt_octet(r, tile, v, t);
+      ntt_octet_smem(r, tile, v, zs);
       if (active) gstore_C(poly, v, r);
     } else {
       gload_C(poly, v, r);
-      invntt_octet(r, tile, v, t);
+      invntt_octet_smem(r, tile, v, zs);
       if (active) gstore_S(poly, v, r);
     }
   }
@@ -213,10 +213,15 @@ int launch_dil_pack_le16(uint8_t* out, const uint32_t* a, size_t n, cudaStream_t
   return 0;
 }
 
-void dil_fill_twiddles(uint32_t* out /* 512: Zetas | InvZetas */) {
+void dil_fill_twiddles(uint32_t* out /* dil::kTwWords: Zetas | InvZetas | forward pairs | inverse pairs */) {
   for (int i = 0; i < 256; i++) {
-    out[i] = dil::zeta_of(i);
-    out[256 + i] = dil::inv_zeta_of(i);
+    const uint32_t z = dil::zeta_of(i), iz = dil::inv_zeta_of(i);
+    out[i] = z;
+    out[256 + i] = iz;
+    out[dil::kTwFwdPairs + 2 * i] = dil::shoup_p(z);
+    out[dil::kTwFwdPairs + 2 * i + 1] = dil::shoup_k(z);
+    out[dil::kTwInvPairs + 2 * i] = dil::shoup_p(iz);
+    out[dil::kTwInvPairs + 2 * i + 1] = dil::shoup_k(iz);
   }
 }
 

@@ -50,6 +50,21 @@ struct Zeta {
   static constexpr uint32_t z = zeta_of(I);
   static constexpr uint32_t iz = inv_zeta_of(I);
 };
+// Shoup form of a Montgomery multiplication by a CONSTANT c (a twiddle or ROver256): with cp = c * 2^-32 mod q and
+// ck = (cp * 2^32 - c) / q,
+//     montReduceLe2Q(c * b) = cp * b - q * hi32(ck * b)        (mod 2^32; the value is below 2q)
+// for every uint32 b: ck * q = -c (mod 2^32) makes ck * b the reference's m = c b (-q^-1) mod 2^32 (field.go:20-24), so
+// (c b + m q) / 2^32 = cp b - q (ck b - m) / 2^32 = cp b - q floor(ck b / 2^32).  One wide multiplication and two
+// 32-bit ones instead of two wide ones and a 32-bit one (IMAD.WIDE issues at half the rate of IMAD).
+__host__ __device__ constexpr uint32_t shoup_p(uint32_t c) {  // c * 2^-32 mod q
+  return (uint32_t)((uint64_t)c * powmod((uint32_t)((1ull << 32) % Q), Q - 2) % Q);
+}
+__host__ __device__ constexpr uint32_t shoup_k(uint32_t c) { return (uint32_t)((((uint64_t)shoup_p(c) << 32) - c) / Q); }
+template <uint32_t C>
+struct Shoup {
+  static constexpr uint32_t p = shoup_p(C), k = shoup_k(C);
+  static_assert(((uint64_t)p << 32) - C == (uint64_t)k * Q, "exact quotient");
+};
 
 template <int B, int E, class F>
 __device__ __forceinline__ void static_for(F&& f) {
@@ -65,6 +80,26 @@ __device__ __forceinline__ uint32_t mont_le2q(uint64_t x) {  // field.go:20-24
   return (uint32_t)((x + (uint64_t)m * Q) >> 32);
 }
 __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b) { return mont_le2q((uint64_t)a * b); }
+// hi32(k * b).  Written as a wide multiplication on purpose: IMAD.WIDE.U32 issues faster than IMAD.HI.U32 on this part
+// (0.24 against 0.18 warp instructions per clock and sub-partition, profiles/r01c_ubench_imad_wide.txt,
+// r01_ubench_pipes.txt), and the compiler turns the plain C expression into the latter.
+__host__ __device__ __forceinline__ uint32_t mulhi_wide(uint32_t k, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  uint32_t hi, lo;
+  asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%1, %0}, t; }" : "=r"(hi), "=r"(lo) : "r"(k), "r"(b));
+  (void)lo;
+  return hi;
+#else
+  return (uint32_t)(((uint64_t)k * b) >> 32);
+#endif
+}
+__host__ __device__ __forceinline__ uint32_t mont_mul_shoup(uint32_t b, uint32_t p, uint32_t k) {
+  return p * b - mulhi_wide(k, b) * Q;
+}
+template <uint32_t C>
+__device__ __forceinline__ uint32_t mont_mul_const(uint32_t b) {  // == mont_mul(C, b), see Shoup above
+  return mont_mul_shoup(b, Shoup<C>::p, Shoup<C>::k);
+}
 __device__ __forceinline__ uint32_t reduce_le2q(uint32_t x) {  // field.go:5-13
   const uint32_t x1 = x >> 23, x2 = x & 0x7FFFFF;
   return x2 + (x1 << 13) - x1;
@@ -83,62 +118,89 @@ __device__ __forceinline__ bool exceeds1(uint32_t c, uint32_t bound) {
 }
 
 // ---------------------------------------------------------------- butterflies
-__device__ __forceinline__ void ct_bfly(uint32_t& a, uint32_t& b, uint32_t z) {  // ntt.go:177-180
-  const uint32_t t = mont_mul(z, b);
+// A run-time twiddle is its Shoup pair {p, k} (see struct Shoup).
+__device__ __forceinline__ void ct_bfly(uint32_t& a, uint32_t& b, uint2 z) {  // ntt.go:177-180
+  const uint32_t t = mont_mul_shoup(b, z.x, z.y);
   b = a + (2 * Q - t);
   a = a + t;
 }
-__device__ __forceinline__ void gs_bfly(uint32_t& a, uint32_t& b, uint32_t z) {  // ntt.go:202-208
+__device__ __forceinline__ void gs_bfly(uint32_t& a, uint32_t& b, uint2 z) {  // ntt.go:202-208
   uint32_t t = a;
   a = t + b;
   t += 256 * Q - b;
-  b = mont_mul(z, t);
+  b = mont_mul_shoup(t, z.x, z.y);
+}
+template <uint32_t Z>
+__device__ __forceinline__ void ct_bfly_const(uint32_t& a, uint32_t& b) {  // ntt.go:177-180, immediate twiddle
+  const uint32_t t = mont_mul_const<Z>(b);
+  b = a + (2 * Q - t);
+  a = a + t;
+}
+template <uint32_t Z>
+__device__ __forceinline__ void gs_bfly_const(uint32_t& a, uint32_t& b) {  // ntt.go:202-208, immediate twiddle
+  uint32_t t = a;
+  a = t + b;
+  t += 256 * Q - b;
+  b = mont_mul_const<Z>(t);
 }
 
-struct LaneTw {  // per-lane twiddles of the C-layout pass: l = 8, 4, 2, 1
-  uint32_t l8[2], l4[4], l2[8], l1[16];
+// Twiddle table in global memory (dil_fill_twiddles): words [0, 256) Zetas, [256, 512) InvZetas, then 256 forward and 256
+// inverse Shoup pairs {p, k}.
+constexpr int kTwWords = 512 + 2 * 512, kTwFwdPairs = 512, kTwInvPairs = 1024;
+// Per-lane twiddles of the C-layout pass as pairs: l = 8, 4, 2 in registers (28); the sixteen of l = 1, each used for one
+// butterfly, are read through the read-only path where they are used.
+struct LaneTw {
+  uint2 l8[2], l4[4], l2[8];
+  const uint2* l1;
 };
+// read-only load of a pair that stays where it is written (volatile asm: not hoisted out of the polynomial loop, which
+// would turn the sixteen l = 1 pairs back into 32 live registers)
+__device__ __forceinline__ uint2 ldg_pair_here(const uint2* p) {
+  uint2 z;
+  asm volatile("ld.global.nc.v2.u32 {%0, %1}, [%2];" : "=r"(z.x), "=r"(z.y) : "l"(p));
+  return z;
+}
 // forward: Zetas[16+2v+i], [32+4v+i], [64+8v+i], [128+16v+i]
-__device__ __forceinline__ void load_lane_tw_fwd(LaneTw& t, const uint32_t* __restrict__ zetas, int v) {
+__device__ __forceinline__ void load_lane_tw_fwd(LaneTw& t, const uint32_t* __restrict__ tab, int v) {
+  const uint2* z = reinterpret_cast<const uint2*>(tab + kTwFwdPairs);
 #pragma unroll
-  for (int i = 0; i < 2; i++) t.l8[i] = zetas[16 + 2 * v + i];
+  for (int i = 0; i < 2; i++) t.l8[i] = __ldg(z + 16 + 2 * v + i);
 #pragma unroll
-  for (int i = 0; i < 4; i++) t.l4[i] = zetas[32 + 4 * v + i];
+  for (int i = 0; i < 4; i++) t.l4[i] = __ldg(z + 32 + 4 * v + i);
 #pragma unroll
-  for (int i = 0; i < 8; i++) t.l2[i] = zetas[64 + 8 * v + i];
-#pragma unroll
-  for (int i = 0; i < 16; i++) t.l1[i] = zetas[128 + 16 * v + i];
+  for (int i = 0; i < 8; i++) t.l2[i] = __ldg(z + 64 + 8 * v + i);
+  t.l1 = z + 128 + 16 * v;
 }
 // inverse (k counts up, ntt.go:191-217): l=1: InvZetas[16v+i], l=2: [128+8v+i], l=4: [192+4v+i], l=8: [224+2v+i]
-__device__ __forceinline__ void load_lane_tw_inv(LaneTw& t, const uint32_t* __restrict__ izetas, int v) {
+__device__ __forceinline__ void load_lane_tw_inv(LaneTw& t, const uint32_t* __restrict__ tab, int v) {
+  const uint2* iz = reinterpret_cast<const uint2*>(tab + kTwInvPairs);
+  t.l1 = iz + 16 * v;
 #pragma unroll
-  for (int i = 0; i < 16; i++) t.l1[i] = izetas[16 * v + i];
+  for (int i = 0; i < 8; i++) t.l2[i] = __ldg(iz + 128 + 8 * v + i);
 #pragma unroll
-  for (int i = 0; i < 8; i++) t.l2[i] = izetas[128 + 8 * v + i];
+  for (int i = 0; i < 4; i++) t.l4[i] = __ldg(iz + 192 + 4 * v + i);
 #pragma unroll
-  for (int i = 0; i < 4; i++) t.l4[i] = izetas[192 + 4 * v + i];
-#pragma unroll
-  for (int i = 0; i < 2; i++) t.l8[i] = izetas[224 + 2 * v + i];
+  for (int i = 0; i < 2; i++) t.l8[i] = __ldg(iz + 224 + 2 * v + i);
 }
 
 // forward pass 1, S layout: l = 128 (k=1), 64 (k=2+h), 32 (k=4+h), 16 (k=8+h)
 __device__ __forceinline__ void fwd_pass_S(uint32_t (&r)[32]) {
 #pragma unroll
-  for (int i = 0; i < 16; i++) ct_bfly(r[i], r[i + 16], Zeta<1>::z);
+  for (int i = 0; i < 16; i++) ct_bfly_const<Zeta<1>::z>(r[i], r[i + 16]);
   static_for<0, 2>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
-    for (int i = 0; i < 8; i++) ct_bfly(r[16 * h + i], r[16 * h + i + 8], Zeta<2 + h>::z);
+    for (int i = 0; i < 8; i++) ct_bfly_const<Zeta<2 + h>::z>(r[16 * h + i], r[16 * h + i + 8]);
   });
   static_for<0, 4>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
-    for (int i = 0; i < 4; i++) ct_bfly(r[8 * h + i], r[8 * h + i + 4], Zeta<4 + h>::z);
+    for (int i = 0; i < 4; i++) ct_bfly_const<Zeta<4 + h>::z>(r[8 * h + i], r[8 * h + i + 4]);
   });
   static_for<0, 8>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
-    for (int i = 0; i < 2; i++) ct_bfly(r[4 * h + i], r[4 * h + i + 2], Zeta<8 + h>::z);
+    for (int i = 0; i < 2; i++) ct_bfly_const<Zeta<8 + h>::z>(r[4 * h + i], r[4 * h + i + 2]);
   });
 }
 // forward pass 2, C layout: l = 8, 4, 2, 1
@@ -156,12 +218,12 @@ __device__ __forceinline__ void fwd_pass_C(uint32_t (&r)[32], const LaneTw& t) {
 #pragma unroll
     for (int j = 0; j < 2; j++) ct_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.l2[blk]);
 #pragma unroll
-  for (int blk = 0; blk < 16; blk++) ct_bfly(r[2 * blk], r[2 * blk + 1], t.l1[blk]);
+  for (int blk = 0; blk < 16; blk++) ct_bfly(r[2 * blk], r[2 * blk + 1], ldg_pair_here(t.l1 + blk));
 }
 // inverse pass A, C layout: l = 1, 2, 4, 8
 __device__ __forceinline__ void inv_pass_C(uint32_t (&r)[32], const LaneTw& t) {
 #pragma unroll
-  for (int blk = 0; blk < 16; blk++) gs_bfly(r[2 * blk], r[2 * blk + 1], t.l1[blk]);
+  for (int blk = 0; blk < 16; blk++) gs_bfly(r[2 * blk], r[2 * blk + 1], ldg_pair_here(t.l1 + blk));
 #pragma unroll
   for (int blk = 0; blk < 8; blk++)
 #pragma unroll
@@ -175,29 +237,94 @@ __device__ __forceinline__ void inv_pass_C(uint32_t (&r)[32], const LaneTw& t) {
 #pragma unroll
     for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.l8[blk]);
 }
-// inverse pass A with the twiddles read from a shared-memory copy of InvZetas at the point of use
-// (saves 30 registers in kernels that hold two polynomials)
-__device__ __forceinline__ void inv_pass_C_smem(uint32_t (&r)[32], const volatile uint32_t* iz, int v) {
+// The C-layout passes with the twiddle pairs read from a shared-memory copy at the point of use (30 registers less
+// than LaneTw).  The copy is lane-transposed: a pass reads "entry i of lane v" of a layer, which in table order sits at
+// base + c v + i (c = 16, 8, 4, 2 entries per lane for l = 1, 2, 4, 8) -- eight lanes 2c words apart, i.e. on one or two
+// banks; stage_pairs stores it at base + 8 i + v instead, so that the eight lanes of an octet read eight consecutive
+// pairs (the four octets of a warp read the same ones: a broadcast).
+__device__ __forceinline__ uint2 pair_at(const volatile uint2* tab, int i) {
+  uint2 z;
+  z.x = tab[i].x;
+  z.y = tab[i].y;
+  return z;
+}
+template <bool INV>
+__device__ __forceinline__ int staged_index(int p) {  // table index of a pair -> its place in the staged copy
+  int b, c;
+  if (!INV) {
+    if (p >= 128) b = 128, c = 16;
+    else if (p >= 64) b = 64, c = 8;
+    else if (p >= 32) b = 32, c = 4;
+    else if (p >= 16) b = 16, c = 2;
+    else return p;
+  } else {
+    if (p < 128) b = 0, c = 16;
+    else if (p < 192) b = 128, c = 8;
+    else if (p < 224) b = 192, c = 4;
+    else if (p < 240) b = 224, c = 2;
+    else return p;
+  }
+  const int v = (p - b) / c, i = (p - b) % c;
+  return b + 8 * i + v;
+}
+// fills the 2 KB staged copy of the forward or inverse pairs (all threads of the CTA; the caller synchronises)
+template <bool INV>
+__device__ __forceinline__ void stage_pairs(volatile uint2* dst, const uint32_t* __restrict__ tab) {
+  const uint2* src = reinterpret_cast<const uint2*>(tab + (INV ? kTwInvPairs : kTwFwdPairs));
+  for (int q = threadIdx.x; q < 256; q += blockDim.x) {
+    const uint2 z = __ldg(src + q);
+    const int d = staged_index<INV>(q);
+    dst[d].x = z.x;
+    dst[d].y = z.y;
+  }
+}
+__device__ __forceinline__ void fwd_pass_C_smem(uint32_t (&r)[32], const volatile uint2* zs, int v) {
 #pragma unroll
-  for (int blk = 0; blk < 16; blk++) gs_bfly(r[2 * blk], r[2 * blk + 1], iz[16 * v + blk]);
+  for (int blk = 0; blk < 2; blk++) {
+    const uint2 z = pair_at(zs, 16 + 8 * blk + v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) ct_bfly(r[16 * blk + j], r[16 * blk + j + 8], z);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++) {
+    const uint2 z = pair_at(zs, 32 + 8 * blk + v);
+#pragma unroll
+    for (int j = 0; j < 4; j++) ct_bfly(r[8 * blk + j], r[8 * blk + j + 4], z);
+  }
 #pragma unroll
   for (int blk = 0; blk < 8; blk++) {
-    const uint32_t z = iz[128 + 8 * v + blk];
+    const uint2 z = pair_at(zs, 64 + 8 * blk + v);
+#pragma unroll
+    for (int j = 0; j < 2; j++) ct_bfly(r[4 * blk + j], r[4 * blk + j + 2], z);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 16; blk++) ct_bfly(r[2 * blk], r[2 * blk + 1], pair_at(zs, 128 + 8 * blk + v));
+}
+__device__ __forceinline__ void inv_pass_C_smem(uint32_t (&r)[32], const volatile uint2* iz, int v) {
+#pragma unroll
+  for (int blk = 0; blk < 16; blk++) gs_bfly(r[2 * blk], r[2 * blk + 1], pair_at(iz, 8 * blk + v));
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++) {
+    const uint2 z = pair_at(iz, 128 + 8 * blk + v);
 #pragma unroll
     for (int j = 0; j < 2; j++) gs_bfly(r[4 * blk + j], r[4 * blk + j + 2], z);
   }
 #pragma unroll
   for (int blk = 0; blk < 4; blk++) {
-    const uint32_t z = iz[192 + 4 * v + blk];
+    const uint2 z = pair_at(iz, 192 + 8 * blk + v);
 #pragma unroll
     for (int j = 0; j < 4; j++) gs_bfly(r[8 * blk + j], r[8 * blk + j + 4], z);
   }
 #pragma unroll
   for (int blk = 0; blk < 2; blk++) {
-    const uint32_t z = iz[224 + 2 * v + blk];
+    const uint2 z = pair_at(iz, 224 + 8 * blk + v);
 #pragma unroll
     for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], z);
   }
+}
+// fills a 2 KB shared-memory copy of the inverse pairs for inv_pass_C_smem
+__device__ __forceinline__ void stage_inv_pairs(volatile uint2* dst, const uint32_t* __restrict__ tab) {
+  stage_pairs<true>(dst, tab);
 }
 
 // inverse pass B, S layout: l = 16 (k=240+h), 32 (248+h), 64 (252+h), 128 (254), then * ROver256
@@ -205,22 +332,22 @@ __device__ __forceinline__ void inv_pass_S(uint32_t (&r)[32]) {
   static_for<0, 8>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
-    for (int i = 0; i < 2; i++) gs_bfly(r[4 * h + i], r[4 * h + i + 2], Zeta<240 + h>::iz);
+    for (int i = 0; i < 2; i++) gs_bfly_const<Zeta<240 + h>::iz>(r[4 * h + i], r[4 * h + i + 2]);
   });
   static_for<0, 4>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
-    for (int i = 0; i < 4; i++) gs_bfly(r[8 * h + i], r[8 * h + i + 4], Zeta<248 + h>::iz);
+    for (int i = 0; i < 4; i++) gs_bfly_const<Zeta<248 + h>::iz>(r[8 * h + i], r[8 * h + i + 4]);
   });
   static_for<0, 2>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
-    for (int i = 0; i < 8; i++) gs_bfly(r[16 * h + i], r[16 * h + i + 8], Zeta<252 + h>::iz);
+    for (int i = 0; i < 8; i++) gs_bfly_const<Zeta<252 + h>::iz>(r[16 * h + i], r[16 * h + i + 8]);
   });
 #pragma unroll
-  for (int i = 0; i < 16; i++) gs_bfly(r[i], r[i + 16], Zeta<254>::iz);
+  for (int i = 0; i < 16; i++) gs_bfly_const<Zeta<254>::iz>(r[i], r[i + 16]);
 #pragma unroll
-  for (int i = 0; i < 32; i++) r[i] = mont_mul(ROVER256, r[i]);
+  for (int i = 0; i < 32; i++) r[i] = mont_mul_const<ROVER256>(r[i]);
 }
 
 // ---------------------------------------------------------------- shared-memory tile (S <-> C)
@@ -303,7 +430,15 @@ __device__ __forceinline__ void invntt_octet(uint32_t (&r)[32], uint32_t* tile, 
   __syncwarp();
   inv_pass_S(r);
 }
-__device__ __forceinline__ void invntt_octet_smem(uint32_t (&r)[32], uint32_t* tile, int v, const volatile uint32_t* iz) {
+__device__ __forceinline__ void ntt_octet_smem(uint32_t (&r)[32], uint32_t* tile, int v, const volatile uint2* zs) {
+  fwd_pass_S(r);
+  store_S(tile, v, r);
+  __syncwarp();
+  load_C(tile, v, r);
+  __syncwarp();
+  fwd_pass_C_smem(r, zs, v);
+}
+__device__ __forceinline__ void invntt_octet_smem(uint32_t (&r)[32], uint32_t* tile, int v, const volatile uint2* iz) {
   inv_pass_C_smem(r, iz, v);
   store_C(tile, v, r);
   __syncwarp();

@@ -495,7 +495,7 @@ constexpr int kWSlots = 2;
 constexpr int kWCtas = 4;  // CTAs per SM the grid and the register allocation are sized for
 struct WSm {
   static constexpr int ring = 16 * kWSlots * 1024, tiles = 16 * kPolyWords * 4, bars = 16 * kWSlots * 8;
-  static constexpr int bytes = ring + tiles + bars + 1024;  // + the inverse twiddles
+  static constexpr int bytes = ring + tiles + bars + 2048;  // + the inverse twiddle pairs
 };
 template <class P>
 __global__ void __launch_bounds__(128, kWCtas) w_kernel(const uint32_t* __restrict__ act, size_t nact, int key_shared,
@@ -517,8 +517,8 @@ __global__ void __launch_bounds__(128, kWCtas) w_kernel(const uint32_t* __restri
   }
   // the per-lane twiddles of the inverse transform are read from shared memory where they are used: thirty registers
   // less across the product loop
-  volatile uint32_t* izs = reinterpret_cast<volatile uint32_t*>(wsm + S::ring + S::tiles + S::bars);
-  for (int q = threadIdx.x; q < 256; q += blockDim.x) izs[q] = zetas[256 + q];
+  volatile uint2* izs = reinterpret_cast<volatile uint2*>(wsm + S::ring + S::tiles + S::bars);
+  stage_inv_pairs(izs, zetas);
   __syncthreads();
   const size_t total = nact * K, G = (size_t)gridDim.x * 16, first = ((size_t)blockIdx.x * 4 + warp) * 4;
   if (first >= total) return;
@@ -803,7 +803,7 @@ __global__ void __launch_bounds__(128) cntt_kernel(const uint32_t* __restrict__ 
 
 // InvNTT(c-hat . x-hat) on an octet: returns S layout
 __device__ __forceinline__ void c_times(uint32_t (&r)[32], const uint32_t* __restrict__ chat,
-                                        const uint32_t* __restrict__ xhat, const OctetCtx& o, const volatile uint32_t* iz) {
+                                        const uint32_t* __restrict__ xhat, const OctetCtx& o, const volatile uint2* iz) {
   uint4 x[8], z[8];
   gload_I(chat, o.v, x);
   gload_I_ro(xhat, o.v, z);
@@ -847,10 +847,10 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
                                                        const uint32_t* __restrict__ zetas) {
   MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
-  __shared__ uint32_t izs[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) izs[i] = zetas[256 + i];
+  __shared__ __align__(8) uint2 izs[256];
+  stage_inv_pairs(izs, zetas);
   __syncthreads();
-  const volatile uint32_t* ti = izs;
+  const volatile uint2* ti = izs;
   const OctetCtx o = octet_ctx(tiles);
   const unsigned octmask = 0xffu << (8 * o.oct);
   constexpr int ITEMS = STAGE == 1 ? L : K;
@@ -1204,8 +1204,8 @@ __global__ void __launch_bounds__(128) verify_w_kernel(const uint8_t* __restrict
                                                        uint8_t* __restrict__ w1u, const uint32_t* __restrict__ zetas) {
   MLDSA_USE(P);
   __shared__ __align__(16) uint32_t tiles[16 * kPolyWords];
-  __shared__ uint32_t izs[256];
-  for (int i = threadIdx.x; i < 256; i += blockDim.x) izs[i] = zetas[256 + i];
+  __shared__ __align__(8) uint2 izs[256];
+  stage_inv_pairs(izs, zetas);
   __syncthreads();
   const OctetCtx o = octet_ctx(tiles);
   const size_t total = n * K, base = ((size_t)blockIdx.x * 4 + o.warp) * 4;
@@ -1544,7 +1544,7 @@ __global__ void __launch_bounds__(128) kg_t_kernel(const uint32_t* __restrict__ 
 #pragma unroll
   for (int c = 0; c < 32; c++) r[c] = reduce_le2q(r[c]);
   LaneTw t;
-  load_lane_tw_inv(t, zetas + 256, o.v);
+  load_lane_tw_inv(t, zetas, o.v);
   invntt_octet(r, o.tile, o.v, t);  // S layout
   const uint32_t* s2 = spoly + (op * (L + K) + L + i) * N;
 #pragma unroll

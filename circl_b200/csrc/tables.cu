@@ -1,13 +1,14 @@
 // circl_b200/csrc/tables.cu -- device tables built at cb200_init time.
 #include "common.cuh"
 #include "context.h"
+#include "dilithium.cuh"
 #include "x25519.cuh"
 
 #include <vector>
 
 namespace cb200 {
 int init_extra_tables(Dev& c) {  // device c.device is current
-  uint32_t tw[512];
+  uint32_t tw[dil::kTwWords];
   dil_fill_twiddles(tw);
   if (c.dil_tw) cudaFree(c.dil_tw);
   CB200_CUDA(cudaMalloc(&c.dil_tw, sizeof tw));

@@ -91,3 +91,18 @@ def test_kyber_low_format_fast_path_on_host(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout[-2000:]
+
+
+def test_dilithium_shoup_constants_on_host(tmp_path):
+    """csrc/dilithium.cuh's Shoup-form multiplication by a constant (every forward / inverse twiddle and ROver256)
+    against the oracle's montReduceLe2Q, compiled as host code (tests/cpp/test_dil_shoup.cu)."""
+    import oracle
+    oracle.build()
+    exe = str(tmp_path / "dil_shoup")
+    odir = os.path.join(ROOT, "oracle")
+    r = subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-O2", "-std=c++17", "--expt-relaxed-constexpr",
+                        "-Wno-deprecated-gpu-targets", os.path.join(ROOT, "tests", "cpp", "test_dil_shoup.cu"), "-o", exe,
+                        "-L", odir, "-loracle", "-Xlinker", "-rpath=" + odir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout[-2000:]

@@ -126,3 +126,34 @@ def test_full_size_property_2_20(cb):
     kyber.normalize(d, out=d)
     want = (orig.to(torch.int64) * 65536) % Q
     assert torch.equal(d.to(torch.int64), want)
+
+
+@pytest.mark.parametrize("inverse,bound", [(False, 13561), (True, 3679)])
+def test_ntt_fast_and_general_path_agree_with_oracle(cb, inverse, bound):
+    """The NTT kernels choose per warp between the low-format fast path (all coefficients of the warp's four
+    polynomials inside [-bound, bound]: no int16 wrap-around can occur in ntt.go:60-193) and the general path.
+    Batches that sit at the edge of the range, one past it, and that interleave both kinds -- so that neighbouring
+    warps, and polynomials inside one warp, fall on different sides -- must all equal the oracle."""
+    import oracle
+    from circl_b200 import kyber
+    N = 256
+    rng = np.random.default_rng(99 + int(inverse))
+    n = 4 * 16 * 37 + 3  # ragged: the last warp has idle octets
+    cases = {
+        "at the bound": rng.integers(-bound, bound + 1, size=(n, N)),
+        "extremes of the range": rng.choice([-bound, bound], size=(n, N)),
+        "one past the bound": np.where(rng.random((n, N)) < 0.01, rng.choice([-bound - 1, bound + 1], size=(n, N)),
+                                       rng.integers(-bound, bound + 1, size=(n, N))),
+        "contract": rng.integers(-Q, Q + 1, size=(n, N)),
+    }
+    mixed = rng.integers(-bound, bound + 1, size=(n, N))
+    mixed[::5] = rng.integers(-32768, 32768, size=mixed[::5].shape)       # one polynomial in five anywhere in int16
+    mixed[3::64, 255] = bound + 1                                          # a single coefficient decides
+    mixed[7::64, 0] = -bound - 1
+    mixed[11::64] = -32768
+    cases["mixed"] = mixed
+    for name, x in cases.items():
+        p = x.astype(np.int16)
+        want = oracle.kyber_invntt(p) if inverse else oracle.kyber_ntt(p)
+        got = (kyber.inv_ntt_ if inverse else kyber.ntt_)(p.copy())
+        assert np.array_equal(got, want), name

@@ -479,16 +479,25 @@ __host__ __device__ __forceinline__ bool words_in_range(const uint32_t (&w)[16],
 #endif
 }
 
+// The low-format pairs of the C-layout passes are kept lane-transposed (in the device table and therefore in its
+// shared-memory copy): "entry i of lane v" of a layer, Zetas position base + c v + i (c = 2, 4, 8 entries per lane for
+// l = 8, 4, 2), is stored at base + 8 i + v, so the eight lanes of an octet read eight consecutive pairs instead of
+// pairs 2c words apart (a 4-way bank conflict per read in table order).
+__host__ __device__ constexpr int tw_slot(int k) {
+  if (k < 16) return k;
+  const int b = k >= 64 ? 64 : (k >= 32 ? 32 : 16), c = b / 8;
+  return b + 8 * ((k - b) % c) + (k - b) / c;
+}
 struct LaneTwLow {
   TwLow l8[2], l4[4], l2[8];
 };
 __host__ __device__ __forceinline__ void load_lane_tw_lo(LaneTwLow& t, const TwLow* tab, int v) {
 #pragma unroll
-  for (int i = 0; i < 2; i++) t.l8[i] = tab[16 + 2 * v + i];
+  for (int i = 0; i < 2; i++) t.l8[i] = tab[16 + 8 * i + v];
 #pragma unroll
-  for (int i = 0; i < 4; i++) t.l4[i] = tab[32 + 4 * v + i];
+  for (int i = 0; i < 4; i++) t.l4[i] = tab[32 + 8 * i + v];
 #pragma unroll
-  for (int i = 0; i < 8; i++) t.l2[i] = tab[64 + 8 * v + i];
+  for (int i = 0; i < 8; i++) t.l2[i] = tab[64 + 8 * i + v];
 }
 __host__ __device__ __forceinline__ TwLow twl_at(const volatile TwLow* tab, int k) {
   const volatile int2* p = reinterpret_cast<const volatile int2*>(tab + k);
@@ -531,22 +540,45 @@ __host__ __device__ __forceinline__ void fwd_pass_C_lo(int32_t (&r)[32], const L
 #pragma unroll
     for (int j = 0; j < 2; j++) ct_lo(r[4 * blk + j], r[4 * blk + j + 2], t.l2[blk].zp, t.l2[blk].kk);
 }
+// forward pass 2 with the pairs read from the shared-memory copy where they are used
+__host__ __device__ __forceinline__ void fwd_pass_C_lo_smem(int32_t (&r)[32], const volatile TwLow* tab, int v) {
+#pragma unroll
+  for (int blk = 0; blk < 2; blk++) {
+    const TwLow t = twl_at(tab, 16 + 8 * blk + v);
+#pragma unroll
+    for (int j = 0; j < 8; j++) ct_lo(r[16 * blk + j], r[16 * blk + j + 8], t.zp, t.kk);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 4; blk++) {
+    const TwLow t = twl_at(tab, 32 + 8 * blk + v);
+#pragma unroll
+    for (int j = 0; j < 4; j++) ct_lo(r[8 * blk + j], r[8 * blk + j + 4], t.zp, t.kk);
+  }
+#pragma unroll
+  for (int blk = 0; blk < 8; blk++) {
+    const TwLow t = twl_at(tab, 64 + 8 * blk + v);
+#pragma unroll
+    for (int j = 0; j < 2; j++) ct_lo(r[4 * blk + j], r[4 * blk + j + 2], t.zp, t.kk);
+  }
+}
+// inverse pass A: Zetas positions 127 - 8v - blk, 63 - 4v - blk, 31 - 2v - blk (ntt.go:152-160), i.e. entry 7 - blk
+// (3 - blk, 1 - blk) of lane 7 - v in the transposed table
 __host__ __device__ __forceinline__ void inv_pass_C_lo(int32_t (&r)[32], const volatile TwLow* tab, int v) {
 #pragma unroll
   for (int blk = 0; blk < 8; blk++) {
-    const TwLow t = twl_at(tab, 127 - 8 * v - blk);
+    const TwLow t = twl_at(tab, 64 + 8 * (7 - blk) + (7 - v));
 #pragma unroll
     for (int j = 0; j < 2; j++) gs_lo(r[4 * blk + j], r[4 * blk + j + 2], t.zp, t.kk);
   }
 #pragma unroll
   for (int blk = 0; blk < 4; blk++) {
-    const TwLow t = twl_at(tab, 63 - 4 * v - blk);
+    const TwLow t = twl_at(tab, 32 + 8 * (3 - blk) + (7 - v));
 #pragma unroll
     for (int j = 0; j < 4; j++) gs_lo(r[8 * blk + j], r[8 * blk + j + 4], t.zp, t.kk);
   }
 #pragma unroll
   for (int blk = 0; blk < 2; blk++) {
-    const TwLow t = twl_at(tab, 31 - 2 * v - blk);
+    const TwLow t = twl_at(tab, 16 + 8 * (1 - blk) + (7 - v));
 #pragma unroll
     for (int j = 0; j < 8; j++) gs_lo(r[16 * blk + j], r[16 * blk + j + 8], t.zp, t.kk);
   }

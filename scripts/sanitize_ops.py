@@ -15,10 +15,14 @@ circl_b200.init(0)
 rng = np.random.default_rng(7)
 Q = 3329
 
-# raw ring kernels: the forward NTT is the bulk-async (TMA) ring with one mbarrier per slot, the inverse the plain kernel
+# raw ring kernels: the forward NTT stages its input with bulk-async (TMA) copies, one mbarrier per octet; both
+# directions are run on in-contract inputs (fast path) and on arbitrary int16 (general path)
 p = rng.integers(-Q, Q, size=(203, 256), dtype=np.int64).astype(np.int16)
 assert np.array_equal(kyber.ntt_(p.copy()), oracle.kyber_ntt(p))
 assert np.array_equal(kyber.inv_ntt_(p.copy()), oracle.kyber_invntt(p))
+pa = rng.integers(-32768, 32768, size=(203, 256), dtype=np.int64).astype(np.int16)
+assert np.array_equal(kyber.ntt_(pa.copy()), oracle.kyber_ntt(pa))
+assert np.array_equal(kyber.inv_ntt_(pa.copy()), oracle.kyber_invntt(pa))
 a = rng.integers(-Q, Q, size=(40, 3, 256), dtype=np.int64).astype(np.int16)
 assert np.array_equal(kyber.poly_dot_hat(a, a, 3), oracle.kyber_dot(a, a, 3))
 d = rng.integers(0, 8380417, size=(77, 256), dtype=np.int64).astype(np.uint32)

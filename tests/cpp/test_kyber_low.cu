@@ -65,11 +65,11 @@ static void inv_fast(int16_t p[256], const TwLow* tab) {
 int main() {
   int bad = 0;
   TwLow tab[128];
-  for (int i = 0; i < 128; i++) tab[i] = TwLow{zp_of(i), kk_of(i)};
+  for (int i = 0; i < 128; i++) tab[tw_slot(i)] = TwLow{zp_of(i), kk_of(i)};  // the device table order
   const int16_t* zt = orc_kyber_zetas();
   // 1. every twiddle x every int16
   for (int i = 0; i <= 128; i++) {
-    const int32_t zeta = i < 128 ? zt[i] : 1441, zp = i < 128 ? tab[i].zp : kScaleZp, kk = i < 128 ? tab[i].kk : kScaleKk;
+    const int32_t zeta = i < 128 ? zt[i] : 1441, zp = i < 128 ? tab[tw_slot(i)].zp : kScaleZp, kk = i < 128 ? tab[tw_slot(i)].kk : kScaleKk;
     if (i < 128 && zeta != zeta_of(i)) { bad++; printf("zeta table %d\n", i); }
     for (int b = -32768; b <= 32767; b++)
       if (mont_mul_lo(b, zp, kk) != orc_kyber_mont_reduce(zeta * b)) { bad++; if (bad < 10) printf("mont %d %d\n", i, b); }

@@ -585,41 +585,50 @@ __host__ __device__ __forceinline__ void inv_pass_C_lo(int32_t (&r)[32], const v
   r[16] = barrett_lo(r[16]);
   r[17] = barrett_lo(r[17]);
 }
-// the lazy Barrett schedule of inv_pass_S, on low-format registers
+// the lazy Barrett schedule of inv_pass_S, on low-format registers.  The per-lane conditions of the schedule are folded
+// into the Barrett multiplier (20159 where the reference reduces, 0 elsewhere: x - ((x * 0) >> 26) q = x), so every
+// lane runs the same three instructions and the warp never diverges.
+__host__ __device__ __forceinline__ int32_t barrett_if(int32_t x, int32_t mul) { return x - ((x * mul) >> 26) * Q; }
 __host__ __device__ __forceinline__ void inv_pass_S_lo(int32_t (&r)[32], int v) {
+  constexpr int32_t B = 20159;
+  const int32_t m_v0 = v == 0 ? B : 0, m_v01 = v <= 1 ? B : 0, m_v1 = v == 1 ? B : 0, m_v13 = (v >= 1 && v <= 3) ? B : 0,
+                m_v23 = (v == 2 || v == 3) ? B : 0, m_v27 = v >= 2 ? B : 0;
   static_for<0, 8>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
     for (int i = 0; i < 2; i++) gs_lo(r[4 * h + i], r[4 * h + i + 2], ZetaL<15 - h>::zp, ZetaL<15 - h>::kk);
   });
+  // after layer 4: idx mod 64 in {0,1} -> (s&3)==0, v==0 ; {32..35} -> (s&3)==2, v<=1
 #pragma unroll
   for (int s = 0; s < 16; s += 4)
 #pragma unroll
     for (int b = 0; b < 2; b++) {
-      if (v == 0) r[2 * s + b] = barrett_lo(r[2 * s + b]);
-      if (v <= 1) r[2 * (s + 2) + b] = barrett_lo(r[2 * (s + 2) + b]);
+      r[2 * s + b] = barrett_if(r[2 * s + b], m_v0);
+      r[2 * (s + 2) + b] = barrett_if(r[2 * (s + 2) + b], m_v01);
     }
   static_for<0, 4>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
     for (int i = 0; i < 4; i++) gs_lo(r[8 * h + i], r[8 * h + i + 4], ZetaL<7 - h>::zp, ZetaL<7 - h>::kk);
   });
+  // after layer 5: idx mod 128 in {2,3} -> (s&7)==0, v==1 ; {66..71} -> (s&7)==4, v in 1..3
 #pragma unroll
   for (int s = 0; s < 16; s += 8)
 #pragma unroll
     for (int b = 0; b < 2; b++) {
-      if (v == 1) r[2 * s + b] = barrett_lo(r[2 * s + b]);
-      if (v >= 1 && v <= 3) r[2 * (s + 4) + b] = barrett_lo(r[2 * (s + 4) + b]);
+      r[2 * s + b] = barrett_if(r[2 * s + b], m_v1);
+      r[2 * (s + 4) + b] = barrett_if(r[2 * (s + 4) + b], m_v13);
     }
   static_for<0, 2>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
     for (int i = 0; i < 8; i++) gs_lo(r[16 * h + i], r[16 * h + i + 8], ZetaL<3 - h>::zp, ZetaL<3 - h>::kk);
   });
+  // after layer 6: idx in {4..7} -> s==0, v in {2,3} ; {132..143} -> s==8, v in 2..7
 #pragma unroll
   for (int b = 0; b < 2; b++) {
-    if (v == 2 || v == 3) r[b] = barrett_lo(r[b]);
-    if (v >= 2) r[16 + b] = barrett_lo(r[16 + b]);
+    r[b] = barrett_if(r[b], m_v23);
+    r[16 + b] = barrett_if(r[16 + b], m_v27);
   }
 #pragma unroll
   for (int i = 0; i < 16; i++) gs_lo(r[i], r[i + 16], ZetaL<1>::zp, ZetaL<1>::kk);

@@ -95,7 +95,9 @@ int cb200_profile_read(double *ms_total, uint64_t *launches, int n);
 
 /* ---- Kyber / ML-KEM ring, q = 3329, Poly = [256]int16 ---- */
 /* (*Poly).NTT / InvNTT   pke/kyber/internal/common/generic.go:24,36; stubs_amd64.go:8-14
- * in place over n contiguous polynomials. */
+ * in place over n contiguous polynomials.  Results equal nttGeneric / invNTTGeneric (ntt.go:60-193) bit for bit,
+ * unnormalised, for EVERY int16 input (the reference's int16 wrap-around included).  Inputs inside the reference's
+ * contract (|c| <= q; in fact |c| <= 13561 forward, <= 3679 inverse) run a faster kernel path. */
 int cb200_kyber_ntt(int16_t *polys, size_t n, int inverse);
 /* (*Poly).MulHat         generic.go:49; poly.go:63-100.  out may alias a or b. */
 int cb200_kyber_mulhat(int16_t *out, const int16_t *a, const int16_t *b, size_t n);

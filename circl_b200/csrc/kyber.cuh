@@ -589,6 +589,8 @@ __host__ __device__ __forceinline__ void inv_pass_C_lo(int32_t (&r)[32], const v
 // into the Barrett multiplier (20159 where the reference reduces, 0 elsewhere: x - ((x * 0) >> 26) q = x), so every
 // lane runs the same three instructions and the warp never diverges.
 __host__ __device__ __forceinline__ int32_t barrett_if(int32_t x, int32_t mul) { return x - ((x * mul) >> 26) * Q; }
+// SCALE = false leaves the multiplication by 1441 out (callers that folded the constant into an operand)
+template <bool SCALE = true>
 __host__ __device__ __forceinline__ void inv_pass_S_lo(int32_t (&r)[32], int v) {
   constexpr int32_t B = 20159;
   const int32_t m_v0 = v == 0 ? B : 0, m_v01 = v <= 1 ? B : 0, m_v1 = v == 1 ? B : 0, m_v13 = (v >= 1 && v <= 3) ? B : 0,
@@ -632,8 +634,39 @@ __host__ __device__ __forceinline__ void inv_pass_S_lo(int32_t (&r)[32], int v) 
   }
 #pragma unroll
   for (int i = 0; i < 16; i++) gs_lo(r[i], r[i + 16], ZetaL<1>::zp, ZetaL<1>::kk);
+  if constexpr (SCALE) {
 #pragma unroll
-  for (int i = 0; i < 32; i++) r[i] = mont_mul_lo(r[i], kScaleZp, kScaleKk);
+    for (int i = 0; i < 32; i++) r[i] = mont_mul_lo(r[i], kScaleZp, kScaleKk);
+  }
+}
+
+// Packed S <-> C transposition of low-format registers through the 608-byte tile of store_S / load_C (kernels whose
+// shared memory has no room for the wide tile below)
+__device__ __forceinline__ void store_S_lo(uint32_t* tile, int v, const int32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++) tile[8 * s + v + 4 * (s >> 2)] = pack2_lo(r[2 * s], r[2 * s + 1]);
+}
+__device__ __forceinline__ void load_S_lo(const uint32_t* tile, int v, int32_t (&r)[32]) {
+#pragma unroll
+  for (int s = 0; s < 16; s++) unpack2_lo(tile[8 * s + v + 4 * (s >> 2)], r[2 * s], r[2 * s + 1]);
+}
+__device__ __forceinline__ void store_C_lo(uint32_t* tile, int v, const int32_t (&r)[32]) {
+  uint4* p = reinterpret_cast<uint4*>(tile + 16 * v + 4 * (v >> 1));
+#pragma unroll
+  for (int c = 0; c < 4; c++)
+    p[c] = make_uint4(pack2_lo(r[8 * c], r[8 * c + 1]), pack2_lo(r[8 * c + 2], r[8 * c + 3]),
+                      pack2_lo(r[8 * c + 4], r[8 * c + 5]), pack2_lo(r[8 * c + 6], r[8 * c + 7]));
+}
+__device__ __forceinline__ void load_C_lo(const uint32_t* tile, int v, int32_t (&r)[32]) {
+  const uint4* p = reinterpret_cast<const uint4*>(tile + 16 * v + 4 * (v >> 1));
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const uint4 w = p[c];
+    unpack2_lo(w.x, r[8 * c], r[8 * c + 1]);
+    unpack2_lo(w.y, r[8 * c + 2], r[8 * c + 3]);
+    unpack2_lo(w.z, r[8 * c + 4], r[8 * c + 5]);
+    unpack2_lo(w.w, r[8 * c + 6], r[8 * c + 7]);
+  }
 }
 
 // Unpacked S <-> C transposition for the fast path: registers travel as 128-bit groups of four, one group per

@@ -540,6 +540,8 @@ __device__ __forceinline__ int32_t mont_red_hi(int32_t p) {
   const int32_t m = (int32_t)((uint32_t)p * (kyber::QINV << 16)) >> 16;
   return p - m * Q;
 }
+// montReduce(p) as a plain sign-extended value
+__device__ __forceinline__ int32_t mont_red_lo(int32_t p) { return mont_red_hi(p) >> 16; }
 // Compress_q(x, d) (poly.go:248-328) from ANY representative x of the residue with |x| < 2^15, high-half register:
 // round(x 2^d / q) mod 2^d does not change when a multiple of q is added to x, so x + 10 q in [0, 2^16) is compressed
 // directly -- floor((x' 2^d + 1664) / q) as a 32 x 32 -> 64 multiplication by ceil(2^40 / q), exact below 2^28 -- and the
@@ -551,13 +553,19 @@ __device__ __forceinline__ uint32_t compress_any(int32_t x_hi) {
   const uint32_t v = (xp << D) + Q / 2;
   return (__umulhi(v, 330282857u) >> 8) & ((1u << D) - 1);
 }
+// the same from a low-format register (plain sign-extended representative)
 template <int D>
+__device__ __forceinline__ uint32_t compress_any_lo(int32_t x) {
+  const uint32_t v = ((uint32_t)(x + 10 * Q) << D) + Q / 2;
+  return (__umulhi(v, 330282857u) >> 8) & ((1u << D) - 1);
+}
+template <int D, bool LOW = false>
 __device__ __forceinline__ void compress_any_store_C(const int32_t (&r)[32], uint32_t* __restrict__ dst) {
   uint64_t acc = 0;
   int bits = 0, o = 0;
 #pragma unroll
   for (int i = 0; i < 32; i++) {
-    acc |= (uint64_t)compress_any<D>(r[i]) << bits;
+    acc |= (uint64_t)(LOW ? compress_any_lo<D>(r[i]) : compress_any<D>(r[i])) << bits;
     bits += D;
     if (bits >= 32) {
       dst[o++] = (uint32_t)acc;
@@ -649,9 +657,11 @@ __global__ void __launch_bounds__(THREADS, MINB) encrypt_dp_kernel(
   uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
   uint2* ops = reinterpret_cast<uint2*>(ops_all + (size_t)(warp * 4 + oct) * S::op_words) + v;  // [j][block][lane]
 
-  for (int i = threadIdx.x; i < 128; i += THREADS) tws[i] = tw[i];
+  // every transform of this kernel runs on low-format registers (kyber.cuh): its inputs are bounded by construction
+  // (|noise| <= 3, |montReduce(.)| <= q), far inside the range where no int16 of the reference would wrap
+  for (int i = threadIdx.x; i < 128; i += THREADS) tws[i] = tw[128 + i];  // {zp, kk} pairs in tw_slot order
   __syncthreads();
-  const volatile TwPair* tab = tws;
+  const volatile TwLow* tabl = reinterpret_cast<const volatile TwLow*>(tws);
   const size_t base = ((size_t)blockIdx.x * (THREADS / 32) + warp) * 4;
   if (base >= n) return;
   const size_t op_raw = base + oct;
@@ -672,31 +682,31 @@ __global__ void __launch_bounds__(THREADS, MINB) encrypt_dp_kernel(
 #pragma unroll 1
     for (int j = 0; j < K; j++) {
 #pragma unroll
-      for (int q = 0; q < 16; q++) unpack2(nw[q], r[2 * q], r[2 * q + 1]);
+      for (int q = 0; q < 16; q++) unpack2_lo(nw[q], r[2 * q], r[2 * q + 1]);
       if (j + 1 < K) {
 #pragma unroll
         for (int q = 0; q < 16; q++) nw[q] = ldg_stream32(np + (j + 1) * (N / 2) + 8 * q + v);
       }
-      fwd_pass_S(r);
-      store_S(tile, v, r);
+      fwd_pass_S_lo(r);
+      store_S_lo(tile, v, r);
       __syncwarp();
-      load_C(tile, v, r);
-      fwd_pass_C_smem(r, tab, v);
+      load_C_lo(tile, v, r);
+      fwd_pass_C_lo_smem(r, tabl, v);
       __syncwarp();
 #pragma unroll
       for (int q = 0; q < 8; q++) {  // quad q of this lane: zeta = Zetas[64 + 8 v + q], +zeta for its first block, -zeta for its second
-        const TwPair z = tw_at(tab, 64 + 8 * v + q);
+        const TwLow z = twl_at(tabl, 64 + 8 * q + v);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int blk = 2 * q + h;
-          // x 512 = R / 128: mont_mul by 512 R mod q (|in| <= 7 q, |out| < q)
-          constexpr int32_t kS = (int32_t)((512ull * 65536ull) % Q), kSq = (int32_t)((((uint32_t)kS * QINV) & 0xffffu) << 16);
-          const int32_t b0 = mont_mul_hi(r[2 * blk] >> 16, kS, kSq), b1 = mont_mul_hi(r[2 * blk + 1] >> 16, kS, kSq);
-          int32_t zb1 = mont_mul_hi(b1 >> 16, z.z, z.zq);
+          // x 512 = R / 128: the Montgomery product by 512 R mod q = 1441, i.e. the pair (kScaleZp, kScaleKk) of the
+          // inverse transform (|in| <= 7 q, |out| < q)
+          const int32_t b0 = mont_mul_lo(r[2 * blk], kScaleZp, kScaleKk), b1 = mont_mul_lo(r[2 * blk + 1], kScaleZp, kScaleKk);
+          int32_t zb1 = mont_mul_lo(b1, z.zp, z.kk);
           if (h) zb1 = -zb1;
-          // bytes 2 (low, unsigned) and 3 (high, signed) of the high-half registers
-          ops[(j * 16 + blk) * 8] = make_uint2(__byte_perm((uint32_t)b0, (uint32_t)zb1, 0x7362),
-                                               __byte_perm((uint32_t)b1, (uint32_t)b0, 0x7362));
+          // bytes 0 (low, unsigned) and 1 (high, signed) of the registers
+          ops[(j * 16 + blk) * 8] = make_uint2(__byte_perm((uint32_t)b0, (uint32_t)zb1, 0x5140),
+                                               __byte_perm((uint32_t)b1, (uint32_t)b0, 0x5140));
         }
       }
     }
@@ -755,8 +765,8 @@ __global__ void __launch_bounds__(THREADS, MINB) encrypt_dp_kernel(
       if (h == 0) {
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-          r[2 * c] = mont_red_hi(p0l[c] + p0h[c] * 256);
-          r[2 * c + 1] = mont_red_hi(p1l[c] + p1h[c] * 256);
+          r[2 * c] = mont_red_lo(p0l[c] + p0h[c] * 256);
+          r[2 * c + 1] = mont_red_lo(p1l[c] + p1h[c] * 256);
         }
         // the noise polynomial this row ends with: in flight during the second half and the inverse transform
         const uint32_t* e = np + (K + i) * (N / 2);
@@ -765,45 +775,45 @@ __global__ void __launch_bounds__(THREADS, MINB) encrypt_dp_kernel(
       } else {
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-          r[16 + 2 * c] = mont_red_hi(p0l[c] + p0h[c] * 256);
-          r[16 + 2 * c + 1] = mont_red_hi(p1l[c] + p1h[c] * 256);
+          r[16 + 2 * c] = mont_red_lo(p0l[c] + p0h[c] * 256);
+          r[16 + 2 * c + 1] = mont_red_lo(p1l[c] + p1h[c] * 256);
         }
       }
     }
-    inv_pass_C_smem(r, tab, v);
-    store_C(tile, v, r);
+    inv_pass_C_lo(r, tabl, v);
+    store_C_lo(tile, v, r);
     __syncwarp();
-    load_S(tile, v, r);
-    inv_pass_S<false>(r, v);
+    load_S_lo(tile, v, r);
+    inv_pass_S_lo<false>(r, v);
     __syncwarp();
     // before the constant the reference bounds the values by 9 q (ntt.go:187-190), so adding e (<= 2) and the message
-    // term (1665) stays inside the int16 range of the high-half registers
+    // term (1665) stays inside the int16 range the packed tile below carries
     {  // + e1[i] / + e2 (+ Decompress_q(m, 1)), S layout
       const uint32_t* mw = reinterpret_cast<const uint32_t*>(m + 32 * op);
 #pragma unroll
       for (int s = 0; s < 16; s++) {
         int32_t e0, e1;
-        unpack2(ew[s], e0, e1);
+        unpack2_lo(ew[s], e0, e1);
         r[2 * s] += e0;
         r[2 * s + 1] += e1;
         if (i == K) {  // DecompressMessage, poly.go:134-147: coefficient idx = 16 s + 2 v + b <- bit idx of m
           const uint32_t word = __ldg(mw + (s >> 1));
           const uint32_t bits = (word >> (16 * (s & 1) + 2 * v)) & 3;
-          r[2 * s] += (bits & 1) ? ((Q + 1) / 2) << 16 : 0;
-          r[2 * s + 1] += (bits & 2) ? ((Q + 1) / 2) << 16 : 0;
+          r[2 * s] += (bits & 1) ? (Q + 1) / 2 : 0;
+          r[2 * s + 1] += (bits & 2) ? (Q + 1) / 2 : 0;
         }
       }
     }
-    store_S(tile, v, r);  // Normalize (cpapke.go:176-177) is absorbed by compress_any
+    store_S_lo(tile, v, r);  // Normalize (cpapke.go:176-177) is absorbed by compress_any
     __syncwarp();
-    load_C(tile, v, r);
+    load_C_lo(tile, v, r);
     __syncwarp();
     bad = __any_sync(octmask, bad) ? 1u : 0u;  // after row K this holds the modulus check of the whole key
     if (active) {
       if (i < K)
-        compress_any_store_C<P::du>(r, reinterpret_cast<uint32_t*>(ctp + i * 32 * P::du) + v * P::du);
+        compress_any_store_C<P::du, true>(r, reinterpret_cast<uint32_t*>(ctp + i * 32 * P::du) + v * P::du);
       else if (!bad)
-        compress_any_store_C<P::dv>(r, reinterpret_cast<uint32_t*>(ctp + K * 32 * P::du) + v * P::dv);
+        compress_any_store_C<P::dv, true>(r, reinterpret_cast<uint32_t*>(ctp + K * 32 * P::du) + v * P::dv);
     }
   }
   // kem.ErrPubKey (cpapke.go:48-54): no output for a non-canonical key

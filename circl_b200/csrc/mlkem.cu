@@ -547,17 +547,25 @@ __device__ __forceinline__ int32_t mont_red_lo(int32_t p) { return mont_red_hi(p
 // directly -- floor((x' 2^d + 1664) / q) as a 32 x 32 -> 64 multiplication by ceil(2^40 / q), exact below 2^28 -- and the
 // Normalize of cpapke.go:176-177 needs no instruction of its own.  Checked exhaustively against the reference's two
 // constant pairs for every 16-bit x' and d in {4, 5, 10, 11} (tests/test_compress_identity.py).
+// hi32(a * b) as a wide multiplication: IMAD.WIDE.U32 issues faster than the IMAD.HI.U32 __umulhi compiles to (0.24
+// against 0.18 per clock and sub-partition, profiles/r01c_ubench_imad_wide.txt)
+__device__ __forceinline__ uint32_t umulhi_wide(uint32_t a, uint32_t b) {
+  uint32_t hi, lo;
+  asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%1, %0}, t; }" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
+  (void)lo;
+  return hi;
+}
 template <int D>
 __device__ __forceinline__ uint32_t compress_any(int32_t x_hi) {
   const uint32_t xp = ((uint32_t)x_hi + ((10u * Q) << 16)) >> 16;
   const uint32_t v = (xp << D) + Q / 2;
-  return (__umulhi(v, 330282857u) >> 8) & ((1u << D) - 1);
+  return (umulhi_wide(v, 330282857u) >> 8) & ((1u << D) - 1);
 }
 // the same from a low-format register (plain sign-extended representative)
 template <int D>
 __device__ __forceinline__ uint32_t compress_any_lo(int32_t x) {
   const uint32_t v = ((uint32_t)(x + 10 * Q) << D) + Q / 2;
-  return (__umulhi(v, 330282857u) >> 8) & ((1u << D) - 1);
+  return (umulhi_wide(v, 330282857u) >> 8) & ((1u << D) - 1);
 }
 template <int D, bool LOW = false>
 __device__ __forceinline__ void compress_any_store_C(const int32_t (&r)[32], uint32_t* __restrict__ dst) {

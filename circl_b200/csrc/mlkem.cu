@@ -390,47 +390,6 @@ __device__ __forceinline__ uint32_t unpack12_C(const uint8_t* __restrict__ src, 
   return bad;
 }
 
-// acc += MulHat(a, b) on C layout, with a streamed from global memory as packed words and
-// b read from this lane's private copy in shared memory (word index w*8 + v, stride kept by caller)
-__device__ __forceinline__ void mulhat_acc_words(int32_t (&acc)[32], const uint32_t (&aw)[16],
-                                                 const uint32_t* __restrict__ bpriv, const volatile kyber::TwPair* tab,
-                                                 int v) {
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const kyber::TwPair z = kyber::tw_at(tab, 64 + 8 * v + j);
-    int32_t x0, x1, x2, x3, y0, y1, y2, y3;
-    kyber::unpack2(aw[2 * j], x0, x1);
-    kyber::unpack2(aw[2 * j + 1], x2, x3);
-    kyber::unpack2(bpriv[(2 * j) * 8], y0, y1);
-    kyber::unpack2(bpriv[(2 * j + 1) * 8], y2, y3);
-    const int32_t a0 = x0 >> 16, a1 = x1 >> 16, a2 = x2 >> 16, a3 = x3 >> 16;
-    const int32_t b0 = y0 >> 16, b1 = y1 >> 16, b2 = y2 >> 16, b3 = y3 >> 16;
-    int32_t p0 = kyber::mont_prod_hi(a1, b1);
-    p0 = kyber::mont_mul_hi(p0 >> 16, z.z, z.zq);
-    p0 += kyber::mont_prod_hi(a0, b0);
-    const int32_t p1 = kyber::mont_prod_hi(a0, b1) + kyber::mont_prod_hi(a1, b0);
-    int32_t p2 = kyber::mont_prod_hi(a3, b3);
-    p2 = -kyber::mont_mul_hi(p2 >> 16, z.z, z.zq);
-    p2 += kyber::mont_prod_hi(a2, b2);
-    const int32_t p3 = kyber::mont_prod_hi(a2, b3) + kyber::mont_prod_hi(a3, b2);
-    acc[4 * j] += p0;
-    acc[4 * j + 1] += p1;
-    acc[4 * j + 2] += p2;
-    acc[4 * j + 3] += p3;
-  }
-}
-
-__device__ __forceinline__ void load_words_C(const uint32_t* __restrict__ poly, int v, uint32_t (&w)[16]) {
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    uint4 q4 = __ldg(reinterpret_cast<const uint4*>(poly + 16 * v + 4 * c));
-    w[4 * c] = q4.x;
-    w[4 * c + 1] = q4.y;
-    w[4 * c + 2] = q4.z;
-    w[4 * c + 3] = q4.w;
-  }
-}
-
 constexpr int kEncThreads = 128;  // 16 octets = 16 operations per CTA (decrypt / keygen kernels)
 
 // The streams sample_kernel left short of 256 coefficients: thread per stream, squeeze on from the saved state and
@@ -1155,24 +1114,54 @@ __device__ __forceinline__ void pack12_C(const int32_t (&r)[32], uint32_t (&w)[1
   }
 }
 
+// 32 normalised coefficients (C layout, plain values in [0, q)) -> 12 words (poly.go:106-116)
+__device__ __forceinline__ void pack12_C_lo(const int32_t (&r)[32], uint32_t (&w)[12]) {
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    uint32_t t[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) t[j] = (uint32_t)r[8 * g + j];
+    w[3 * g] = t[0] | (t[1] << 12) | (t[2] << 24);
+    w[3 * g + 1] = (t[2] >> 8) | (t[3] << 4) | (t[4] << 16) | (t[5] << 28);
+    w[3 * g + 2] = (t[5] >> 4) | (t[6] << 8) | (t[7] << 20);
+  }
+}
+// Normalize (field.go:45-74) of a low-format register holding any int16 value: csubq(barrettReduce(x))
+__device__ __forceinline__ int32_t normalize_lo(int32_t x) {
+  x = kyber::barrett_lo(x) - Q;
+  return x + ((x >> 31) & Q);
+}
+
 // K-PKE.KeyGen arithmetic (cpapke.go:83-105): s-hat = Normalize(NTT(s)), e-hat = NTT(e),
 // t-hat[i] = Normalize(ToMont(A[i] . s-hat) + e-hat[i]); packs s-hat into dk and t-hat into ek and dk.  Octet per op.
-template <int K>
-__global__ void __launch_bounds__(kEncThreads) keygen_kernel(const int16_t* __restrict__ A, const int16_t* __restrict__ noise,
-                                                             size_t n, uint8_t* __restrict__ ek, uint8_t* __restrict__ dk,
-                                                             const kyber::TwPair* __restrict__ tw) {
+// What leaves the kernel is Normalize(.), so -- as in encrypt_dp_kernel -- only residues matter inside it and the same two
+// devices apply: the matrix-vector product runs as IDP.2A dot products of the packed words of A with byte-split
+// operands made once per op from s-hat, here carrying s-hat R (one Montgomery multiplication by R^2 = 1353, which is the
+// reference's ToMont moved onto the operand: montReduce(sum a . s-hat R) = sum a . s-hat), and every transform runs on
+// low-format registers (inputs |c| <= 3).
+template <int K, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) keygen_dp_kernel(const int16_t* __restrict__ A,
+                                                                  const int16_t* __restrict__ noise, size_t n,
+                                                                  uint8_t* __restrict__ ek, uint8_t* __restrict__ dk,
+                                                                  const kyber::TwPair* __restrict__ tw) {
   using P = Params<K>;
+  using S = EncSmem<K, THREADS>;
   using namespace kyber;
-  __shared__ __align__(16) uint32_t tiles[(kEncThreads / 8) * kPolyWords];
-  __shared__ uint32_t sh_store[(kEncThreads / 8) * K * 128];
-  __shared__ __align__(16) TwPair tws[128];
+  constexpr int OCTS = THREADS / 8;
+  // R^2 mod q = 1353 (field.go:35-39) as a Shoup pair: zp = R mod q = 2285 - q
+  constexpr int32_t kR2Zp = 2285 - Q, kR2Kk = (kR2Zp * 65536 - 1353) / Q;
+  static_assert(kR2Zp * 65536 - 1353 == kR2Kk * Q, "ToMont constant");
+  extern __shared__ __align__(16) uint32_t enc_smem[];
+  uint32_t* ops_all = enc_smem;
+  uint32_t* tiles = enc_smem + OCTS * S::op_words;
+  TwPair* tws = reinterpret_cast<TwPair*>(tiles + OCTS * kPolyWords);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
   uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
-  uint32_t* shp = sh_store + (size_t)(warp * 4 + oct) * K * 128 + v;
-  for (int i = threadIdx.x; i < 128; i += kEncThreads) tws[i] = tw[i];
+  uint2* ops = reinterpret_cast<uint2*>(ops_all + (size_t)(warp * 4 + oct) * S::op_words) + v;  // [j][block][lane]
+  for (int i = threadIdx.x; i < 128; i += THREADS) tws[i] = tw[128 + i];  // {zp, kk} pairs in tw_slot order
   __syncthreads();
-  const volatile TwPair* tab = tws;
-  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
+  const volatile TwLow* tabl = reinterpret_cast<const volatile TwLow*>(tws);
+  const size_t base = ((size_t)blockIdx.x * (THREADS / 32) + warp) * 4;
   if (base >= n) return;
   const bool active = base + oct < n;
   const size_t op = active ? base + oct : n - 1;
@@ -1180,54 +1169,117 @@ __global__ void __launch_bounds__(kEncThreads) keygen_kernel(const int16_t* __re
   const uint32_t* np = reinterpret_cast<const uint32_t*>(noise) + op * (2 * K) * (N / 2);
   uint8_t* ekp = ek + op * P::ek_bytes;
   uint8_t* dkp = dk + op * (768 * K + 96);
+
   int32_t r[32];
-#pragma unroll 1
-  for (int j = 0; j < K; j++) {  // s-hat
-    gload_S(np + j * (N / 2), v, r);
-    fwd_pass_S(r);
-    store_S(tile, v, r);
-    __syncwarp();
-    load_C(tile, v, r);
-    fwd_pass_C_smem(r, tab, v);
-    __syncwarp();
+  {  // s-hat[j]: packed into dk (normalised) and turned into the operands of the products
+    uint32_t nw[16];
 #pragma unroll
-    for (int c = 0; c < 32; c++) r[c] = csubq_hi(barrett_hi(r[c]));
-#pragma unroll
-    for (int w = 0; w < 16; w++) shp[(j * 16 + w) * 8] = pack2(r[2 * w], r[2 * w + 1]);
-    uint32_t pw[12];
-    pack12_C(r, pw);
-    if (active) {
-      uint32_t* dst = reinterpret_cast<uint32_t*>(dkp + 384 * j) + 12 * v;
-#pragma unroll
-      for (int w = 0; w < 12; w++) dst[w] = pw[w];
-    }
-  }
-#pragma unroll 1
-  for (int i = 0; i < K; i++) {
-    int32_t acc[32];
-#pragma unroll
-    for (int c = 0; c < 32; c++) acc[c] = 0;
+    for (int q = 0; q < 16; q++) nw[q] = ldg_stream32(np + 8 * q + v);
 #pragma unroll 1
     for (int j = 0; j < K; j++) {
-      uint32_t aw[16];
-      load_words_C(Ap + (i * K + j) * (N / 2), v, aw);
-      mulhat_acc_words(acc, aw, shp + j * 128, tab, v);
-    }
-    // e-hat[i] = NTT(e[i])
-    gload_S(np + (K + i) * (N / 2), v, r);
-    fwd_pass_S(r);
-    store_S(tile, v, r);
-    __syncwarp();
-    load_C(tile, v, r);
-    fwd_pass_C_smem(r, tab, v);
-    __syncwarp();
 #pragma unroll
-    for (int c = 0; c < 32; c++) {
-      const int32_t t = mont_mul_hi(acc[c] >> 16, 1353, (int32_t)(((1353u * QINV) & 0xffffu) << 16));  // ToMont
-      r[c] = csubq_hi(barrett_hi(t + r[c]));
+      for (int q = 0; q < 16; q++) unpack2_lo(nw[q], r[2 * q], r[2 * q + 1]);
+      if (j + 1 < K) {
+#pragma unroll
+        for (int q = 0; q < 16; q++) nw[q] = ldg_stream32(np + (j + 1) * (N / 2) + 8 * q + v);
+      }
+      fwd_pass_S_lo(r);
+      store_S_lo(tile, v, r);
+      __syncwarp();
+      load_C_lo(tile, v, r);
+      fwd_pass_C_lo_smem(r, tabl, v);
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < 8; q++) {  // quad q of this lane: zeta = Zetas[64 + 8 v + q], +zeta for its first block, -zeta for its second
+        const TwLow z = twl_at(tabl, 64 + 8 * q + v);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int blk = 2 * q + h;
+          const int32_t b0 = mont_mul_lo(r[2 * blk], kR2Zp, kR2Kk), b1 = mont_mul_lo(r[2 * blk + 1], kR2Zp, kR2Kk);
+          int32_t zb1 = mont_mul_lo(b1, z.zp, z.kk);
+          if (h) zb1 = -zb1;
+          ops[(j * 16 + blk) * 8] = make_uint2(__byte_perm((uint32_t)b0, (uint32_t)zb1, 0x5140),
+                                               __byte_perm((uint32_t)b1, (uint32_t)b0, 0x5140));
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 32; c++) r[c] = normalize_lo(r[c]);
+      uint32_t pw[12];
+      pack12_C_lo(r, pw);
+      if (active) {
+        uint32_t* dst = reinterpret_cast<uint32_t*>(dkp + 384 * j) + 12 * v;
+#pragma unroll
+        for (int w = 0; w < 12; w++) dst[w] = pw[w];
+      }
+    }
+  }
+  __syncwarp();
+
+  // t-hat[i] = Normalize(A[i] . s-hat + e-hat[i]); a row is accumulated in two halves of eight blocks, every load of A
+  // issued K steps before its use (as in encrypt_dp_kernel)
+  auto fetch = [&](int i, int h, int j, uint32_t (&raw)[8]) {
+    const uint4* p = reinterpret_cast<const uint4*>(Ap + (i * K + j) * (N / 2) + 16 * v + 8 * h);
+    const uint4 x = __ldg(p), y = __ldg(p + 1);
+    raw[0] = x.x, raw[1] = x.y, raw[2] = x.z, raw[3] = x.w, raw[4] = y.x, raw[5] = y.y, raw[6] = y.z, raw[7] = y.w;
+  };
+  uint32_t raw[K][8];
+#pragma unroll
+  for (int j = 0; j < K; j++) fetch(0, 0, j, raw[j]);
+  uint32_t ew[16];
+#pragma unroll
+  for (int q = 0; q < 16; q++) ew[q] = __ldg(np + K * (N / 2) + 8 * q + v);
+#pragma unroll 1
+  for (int i = 0; i < K; i++) {
+#pragma unroll
+    for (int q = 0; q < 16; q++) unpack2_lo(ew[q], r[2 * q], r[2 * q + 1]);  // e-hat[i] = NTT(e[i])
+    if (i + 1 < K) {
+#pragma unroll
+      for (int q = 0; q < 16; q++) ew[q] = __ldg(np + (K + i + 1) * (N / 2) + 8 * q + v);
+    }
+    fwd_pass_S_lo(r);
+    store_S_lo(tile, v, r);
+    __syncwarp();
+    load_C_lo(tile, v, r);
+    fwd_pass_C_lo_smem(r, tabl, v);
+    __syncwarp();
+#pragma unroll 1
+    for (int h = 0; h < 2; h++) {
+      int32_t p0l[8], p0h[8], p1l[8], p1h[8];
+#pragma unroll
+      for (int c = 0; c < 8; c++) p0l[c] = p0h[c] = p1l[c] = p1h[c] = 0;
+      const int ni = h ? i + 1 : i, nh = h ^ 1;  // the half-row after this one
+#pragma unroll
+      for (int j = 0; j < K; j++) {
+        uint32_t aw[8];
+#pragma unroll
+        for (int c = 0; c < 8; c++) aw[c] = raw[j][c];
+        if (ni < K) fetch(ni, nh, j, raw[j]);
+        const uint2* oj = ops + (size_t)(j * 16 + 8 * h) * 8;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const uint2 w = oj[c * 8];
+          p0l[c] = (int32_t)dp2a_lo_uu(aw[c], w.x, (uint32_t)p0l[c]);
+          p0h[c] = dp2a_hi_us(aw[c], w.x, p0h[c]);
+          p1l[c] = (int32_t)dp2a_lo_uu(aw[c], w.y, (uint32_t)p1l[c]);
+          p1h[c] = dp2a_hi_us(aw[c], w.y, p1h[c]);
+        }
+      }
+      if (h == 0) {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          r[2 * c] = normalize_lo(mont_red_lo(p0l[c] + p0h[c] * 256) + r[2 * c]);
+          r[2 * c + 1] = normalize_lo(mont_red_lo(p1l[c] + p1h[c] * 256) + r[2 * c + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          r[16 + 2 * c] = normalize_lo(mont_red_lo(p0l[c] + p0h[c] * 256) + r[16 + 2 * c]);
+          r[16 + 2 * c + 1] = normalize_lo(mont_red_lo(p1l[c] + p1h[c] * 256) + r[16 + 2 * c + 1]);
+        }
+      }
     }
     uint32_t pw[12];
-    pack12_C(r, pw);
+    pack12_C_lo(r, pw);
     if (active) {
       uint32_t* d1 = reinterpret_cast<uint32_t*>(ekp + 384 * i) + 12 * v;
       uint32_t* d2 = reinterpret_cast<uint32_t*>(dkp + 384 * K + 384 * i) + 12 * v;
@@ -1285,7 +1337,10 @@ static int keygen_device(const uint8_t* seeds, uint8_t* ek, uint8_t* dk, size_t 
       return src;
     {
       KernelScope ks(KID_MLKEM_ENCRYPT, ls);
-      keygen_kernel<K><<<(unsigned)((cnt + 15) / 16), kEncThreads, 0, ls>>>(
+      constexpr int MINB = K == 4 ? 6 : 7, per_cta = kEncDpThreads / 8;
+      using S = EncSmem<K, kEncDpThreads>;
+      if (int arc = ensure_smem_attr((const void*)keygen_dp_kernel<K, kEncDpThreads, MINB>, S::bytes)) return arc;
+      keygen_dp_kernel<K, kEncDpThreads, MINB><<<(unsigned)((cnt + per_cta - 1) / per_cta), kEncDpThreads, S::bytes, ls>>>(
           A, noise, cnt, ek + first * P::ek_bytes, dk + first * dksz, (const kyber::TwPair*)c.kyber_tw);
     }
   }

@@ -390,7 +390,6 @@ __device__ __forceinline__ uint32_t unpack12_C(const uint8_t* __restrict__ src, 
   return bad;
 }
 
-constexpr int kEncThreads = 128;  // 16 octets = 16 operations per CTA (decrypt / keygen kernels)
 
 // The streams sample_kernel left short of 256 coefficients: thread per stream, squeeze on from the saved state and
 // append to the polynomial in A (2-byte global stores; about 1 % of the streams, one or two dozen coefficients each).
@@ -540,6 +539,24 @@ __device__ __forceinline__ void compress_any_store_C(const int32_t (&r)[32], uin
       bits -= 32;
     }
   }
+}
+
+// 32 normalised coefficients (C layout, plain values in [0, q)) -> 12 words (poly.go:106-116)
+__device__ __forceinline__ void pack12_C_lo(const int32_t (&r)[32], uint32_t (&w)[12]) {
+#pragma unroll
+  for (int g = 0; g < 4; g++) {
+    uint32_t t[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) t[j] = (uint32_t)r[8 * g + j];
+    w[3 * g] = t[0] | (t[1] << 12) | (t[2] << 24);
+    w[3 * g + 1] = (t[2] >> 8) | (t[3] << 4) | (t[4] << 16) | (t[5] << 28);
+    w[3 * g + 2] = (t[5] >> 4) | (t[6] << 8) | (t[7] << 20);
+  }
+}
+// Normalize (field.go:45-74) of a low-format register holding any int16 value: csubq(barrettReduce(x))
+__device__ __forceinline__ int32_t normalize_lo(int32_t x) {
+  x = kyber::barrett_lo(x) - Q;
+  return x + ((x >> 31) & Q);
 }
 
 // 12-bit unpack of 32 coefficients (48 bytes, 16-byte aligned) straight to packed pairs (poly.go:123-129);
@@ -820,7 +837,7 @@ static int launch_encrypt(const uint8_t* ek, size_t ek_stride, const int16_t* A,
 
 // ------------------------------------------------------------------ 4. Decapsulate
 // Decompress_q(x, d) (poly.go:170-243) of 32 coefficients (C layout) from D words
-template <int D>
+template <int D, bool LOW = false>
 __device__ __forceinline__ void decompress_C(const uint32_t* __restrict__ src, int32_t (&r)[32]) {
   uint32_t w[D + 1];
 #pragma unroll
@@ -832,86 +849,120 @@ __device__ __forceinline__ void decompress_C(const uint32_t* __restrict__ src, i
     uint32_t t = w[wi] >> sh;
     if (sh + D > 32) t |= w[wi + 1] << (32 - sh);
     t &= (1u << D) - 1;
-    r[i] = (int32_t)((((1u << (D - 1)) + t * (uint32_t)Q) >> D) << 16);
+    const uint32_t x = ((1u << (D - 1)) + t * (uint32_t)Q) >> D;
+    r[i] = (int32_t)(LOW ? x : x << 16);
   }
 }
 
-// K-PKE.Decrypt (cpapke.go:113-130): m' = CompressMessage(v - InvNTT(s-hat . NTT(u))); one octet per op
-template <int K>
-__global__ void __launch_bounds__(kEncThreads) decrypt_kernel(const uint8_t* __restrict__ dk, size_t dk_stride,
-                                                              const uint8_t* __restrict__ ct, size_t n,
-                                                              uint8_t* __restrict__ mprime,
-                                                              const kyber::TwPair* __restrict__ tw) {
+// K-PKE.Decrypt (cpapke.go:113-130): m' = CompressMessage(v - InvNTT(s-hat . NTT(u))); one octet per op.
+// The message bits only depend on residues, so the kernel has the shape of the last row of encrypt_dp_kernel: the packed
+// 12-bit words of s-hat in dk are the 16-bit side of IDP.2A products (any 12-bit value will do: PrivateKey.Unpack's
+// Normalize, cpapke.go:32-36, does not change a residue), NTT(u[j]) x 512 are the byte-split operands, one Montgomery
+// reduction per coefficient feeds the inverse transform without its final constant; all transforms on low-format
+// registers (|Decompress(.)| < q).
+template <int K, int THREADS, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) decrypt_dp_kernel(const uint8_t* __restrict__ dk, size_t dk_stride,
+                                                                   const uint8_t* __restrict__ ct, size_t n,
+                                                                   uint8_t* __restrict__ mprime,
+                                                                   const kyber::TwPair* __restrict__ tw) {
   using P = Params<K>;
+  using S = EncSmem<K, THREADS>;
   using namespace kyber;
-  __shared__ __align__(16) uint32_t tiles[(kEncThreads / 8) * kPolyWords];
-  __shared__ __align__(16) TwPair tws[128];
+  constexpr int OCTS = THREADS / 8;
+  extern __shared__ __align__(16) uint32_t enc_smem[];
+  uint32_t* ops_all = enc_smem;
+  uint32_t* tiles = enc_smem + OCTS * S::op_words;
+  TwPair* tws = reinterpret_cast<TwPair*>(tiles + OCTS * kPolyWords);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, oct = lane >> 3, v = lane & 7;
   const unsigned octmask = 0xffu << (8 * oct);
   uint32_t* tile = tiles + (warp * 4 + oct) * kPolyWords;
-  for (int i = threadIdx.x; i < 128; i += kEncThreads) tws[i] = tw[i];
+  uint2* ops = reinterpret_cast<uint2*>(ops_all + (size_t)(warp * 4 + oct) * S::op_words) + v;  // [j][block][lane]
+  for (int i = threadIdx.x; i < 128; i += THREADS) tws[i] = tw[128 + i];  // {zp, kk} pairs in tw_slot order
   __syncthreads();
-  const volatile TwPair* tab = tws;
-  const size_t base = ((size_t)blockIdx.x * 4 + warp) * 4;
+  const volatile TwLow* tabl = reinterpret_cast<const volatile TwLow*>(tws);
+  const size_t base = ((size_t)blockIdx.x * (THREADS / 32) + warp) * 4;
   if (base >= n) return;
   const bool active = base + oct < n;
   const size_t op = active ? base + oct : n - 1;
   const uint8_t* dkp = dk + op * dk_stride;
   const uint8_t* ctp = ct + op * P::ct_bytes;
-  int32_t acc[32], r[32];
-#pragma unroll
-  for (int c = 0; c < 32; c++) acc[c] = 0;
+  int32_t r[32];
 #pragma unroll 1
-  for (int j = 0; j < K; j++) {
-    decompress_C<P::du>(reinterpret_cast<const uint32_t*>(ctp + j * 32 * P::du) + v * P::du, r);  // u[j]
-    store_C(tile, v, r);
+  for (int j = 0; j < K; j++) {  // operands of u-hat[j] = NTT(Decompress(u[j])) x 512
+    decompress_C<P::du, true>(reinterpret_cast<const uint32_t*>(ctp + j * 32 * P::du) + v * P::du, r);
+    store_C_lo(tile, v, r);
     __syncwarp();
-    load_S(tile, v, r);
+    load_S_lo(tile, v, r);
     __syncwarp();
-    fwd_pass_S(r);  // u.NTT()
-    store_S(tile, v, r);
+    fwd_pass_S_lo(r);
+    store_S_lo(tile, v, r);
     __syncwarp();
-    load_C(tile, v, r);
+    load_C_lo(tile, v, r);
+    fwd_pass_C_lo_smem(r, tabl, v);
     __syncwarp();
-    fwd_pass_C_smem(r, tab, v);
-    int32_t sh[32];
-    unpack12_C(dkp + 384 * j + 48 * v, sh);  // sk.sh.Unpack + Normalize (cpapke.go:32-36)
 #pragma unroll
-    for (int q = 0; q < 8; q++) {  // PolyDotHat(&m, &sk.sh, &u): MulHat(sh[j], u[j]) (poly.go:63-100)
-      const TwPair z = tw_at(tab, 64 + 8 * v + q);
-      int32_t a[4], b[4];
+    for (int q = 0; q < 8; q++) {
+      const TwLow z = twl_at(tabl, 64 + 8 * q + v);
 #pragma unroll
-      for (int e = 0; e < 4; e++) {
-        a[e] = csubq_hi(barrett_hi(sh[4 * q + e])) >> 16;
-        b[e] = r[4 * q + e] >> 16;
+      for (int h = 0; h < 2; h++) {
+        const int blk = 2 * q + h;
+        const int32_t b0 = mont_mul_lo(r[2 * blk], kScaleZp, kScaleKk), b1 = mont_mul_lo(r[2 * blk + 1], kScaleZp, kScaleKk);
+        int32_t zb1 = mont_mul_lo(b1, z.zp, z.kk);
+        if (h) zb1 = -zb1;
+        ops[(j * 16 + blk) * 8] = make_uint2(__byte_perm((uint32_t)b0, (uint32_t)zb1, 0x5140),
+                                             __byte_perm((uint32_t)b1, (uint32_t)b0, 0x5140));
       }
-      int32_t p0 = mont_prod_hi(a[1], b[1]);
-      p0 = mont_mul_hi(p0 >> 16, z.z, z.zq);
-      p0 += mont_prod_hi(a[0], b[0]);
-      const int32_t p1 = mont_prod_hi(a[0], b[1]) + mont_prod_hi(a[1], b[0]);
-      int32_t p2 = mont_prod_hi(a[3], b[3]);
-      p2 = -mont_mul_hi(p2 >> 16, z.z, z.zq);
-      p2 += mont_prod_hi(a[2], b[2]);
-      const int32_t p3 = mont_prod_hi(a[2], b[3]) + mont_prod_hi(a[3], b[2]);
-      acc[4 * q] += p0;
-      acc[4 * q + 1] += p1;
-      acc[4 * q + 2] += p2;
-      acc[4 * q + 3] += p3;
     }
   }
+  __syncwarp();
+  // PolyDotHat(&m, &sk.sh, &u) (cpapke.go:121): one row over the K columns, in two halves of eight blocks
+#pragma unroll 1
+  for (int h = 0; h < 2; h++) {
+    int32_t p0l[8], p0h[8], p1l[8], p1h[8];
 #pragma unroll
-  for (int c = 0; c < 32; c++) acc[c] = barrett_hi(acc[c]);
-  inv_pass_C_smem(acc, tab, v);
-  store_C(tile, v, acc);
+    for (int c = 0; c < 8; c++) p0l[c] = p0h[c] = p1l[c] = p1h[c] = 0;
+#pragma unroll
+    for (int j = 0; j < K; j++) {
+      const uint2* p = reinterpret_cast<const uint2*>(dkp + 384 * j + 48 * v + 24 * h);
+      const uint2 x = __ldg(p), y = __ldg(p + 1), zz = __ldg(p + 2);
+      uint32_t raw[8] = {x.x, x.y, y.x, y.y, zz.x, zz.y, 0, 0}, aw[8];
+      unpack12_half(raw, aw);
+      const uint2* oj = ops + (size_t)(j * 16 + 8 * h) * 8;
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        const uint2 w = oj[c * 8];
+        p0l[c] = (int32_t)dp2a_lo_uu(aw[c], w.x, (uint32_t)p0l[c]);
+        p0h[c] = dp2a_hi_us(aw[c], w.x, p0h[c]);
+        p1l[c] = (int32_t)dp2a_lo_uu(aw[c], w.y, (uint32_t)p1l[c]);
+        p1h[c] = dp2a_hi_us(aw[c], w.y, p1h[c]);
+      }
+    }
+    if (h == 0) {
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        r[2 * c] = mont_red_lo(p0l[c] + p0h[c] * 256);
+        r[2 * c + 1] = mont_red_lo(p1l[c] + p1h[c] * 256);
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 8; c++) {
+        r[16 + 2 * c] = mont_red_lo(p0l[c] + p0h[c] * 256);
+        r[16 + 2 * c + 1] = mont_red_lo(p1l[c] + p1h[c] * 256);
+      }
+    }
+  }
+  inv_pass_C_lo(r, tabl, v);
+  store_C_lo(tile, v, r);
   __syncwarp();
-  load_S(tile, v, acc);
+  load_S_lo(tile, v, r);
   __syncwarp();
-  inv_pass_S(acc, v);
+  inv_pass_S_lo<false>(r, v);
   // v polynomial: decompress in C layout, bring to S layout
-  decompress_C<P::dv>(reinterpret_cast<const uint32_t*>(ctp + K * 32 * P::du) + v * P::dv, r);
-  store_C(tile, v, r);
+  int32_t vv[32];
+  decompress_C<P::dv, true>(reinterpret_cast<const uint32_t*>(ctp + K * 32 * P::du) + v * P::dv, vv);
+  store_C_lo(tile, v, vv);
   __syncwarp();
-  load_S(tile, v, r);
+  load_S_lo(tile, v, vv);
   __syncwarp();
   // m = Normalize(v - m); CompressMessageTo (poly.go:150-166); coefficient 16 s + 2 v + b -> bit of m'
   uint32_t words[8];
@@ -921,11 +972,10 @@ __global__ void __launch_bounds__(kEncThreads) decrypt_kernel(const uint8_t* __r
   for (int s = 0; s < 16; s++) {
 #pragma unroll
     for (int b = 0; b < 2; b++) {
-      const int32_t d = csubq_hi(barrett_hi(r[2 * s + b] - acc[2 * s + b]));
-      int32_t x = (1664 << 16) - d;        // int16 arithmetic in the high half
+      const int32_t d = normalize_lo(vv[2 * s + b] - r[2 * s + b]);
+      int32_t x = 1664 - d;
       x = (x >> 31) ^ x;
-      x &= 0xffff0000;
-      x -= (832 << 16);
+      x -= 832;
       const uint32_t bit = (uint32_t)x >> 31;
       words[s >> 1] |= bit << (16 * (s & 1) + 2 * v + b);
     }
@@ -944,6 +994,16 @@ __global__ void __launch_bounds__(kEncThreads) decrypt_kernel(const uint8_t* __r
     for (int w = 0; w < 8; w++) mine = (v == w) ? words[w] : mine;
     reinterpret_cast<uint32_t*>(mprime + 32 * op)[v] = mine;
   }
+}
+template <int K>
+static int launch_decrypt(const uint8_t* dk, size_t dk_stride, const uint8_t* ct, size_t n, uint8_t* mprime,
+                          const kyber::TwPair* tw, cudaStream_t st) {
+  constexpr int MINB = K == 4 ? 6 : 7, per_cta = kEncDpThreads / 8;
+  using S = EncSmem<K, kEncDpThreads>;
+  if (int arc = ensure_smem_attr((const void*)decrypt_dp_kernel<K, kEncDpThreads, MINB>, S::bytes)) return arc;
+  decrypt_dp_kernel<K, kEncDpThreads, MINB><<<(unsigned)((n + per_cta - 1) / per_cta), kEncDpThreads, S::bytes, st>>>(
+      dk, dk_stride, ct, n, mprime, tw);
+  return 0;
 }
 
 // Implicit rejection (kyber.go:168-183): ss = (ct == ct2) ? K' : SHAKE256(z || ct)[:32]; also checks
@@ -1032,7 +1092,7 @@ static int decaps_device(const uint8_t* dk, size_t dk_stride, const uint8_t* ct,
   const kyber::TwPair* tw = (const kyber::TwPair*)c.kyber_tw;
   {
     KernelScope ks(KID_MLKEM_ENCRYPT, st);
-    decrypt_kernel<K><<<(unsigned)((n + 15) / 16), kEncThreads, 0, st>>>(dk, dk_stride, ct, n, mprime, tw);
+    if (int drc = launch_decrypt<K>(dk, dk_stride, ct, n, mprime, tw, st)) return drc;
   }
   {
     KernelScope ks(KID_MLKEM_HASH_EK, st);
@@ -1112,24 +1172,6 @@ __device__ __forceinline__ void pack12_C(const int32_t (&r)[32], uint32_t (&w)[1
     w[3 * g + 1] = (t[2] >> 8) | (t[3] << 4) | (t[4] << 16) | (t[5] << 28);
     w[3 * g + 2] = (t[5] >> 4) | (t[6] << 8) | (t[7] << 20);
   }
-}
-
-// 32 normalised coefficients (C layout, plain values in [0, q)) -> 12 words (poly.go:106-116)
-__device__ __forceinline__ void pack12_C_lo(const int32_t (&r)[32], uint32_t (&w)[12]) {
-#pragma unroll
-  for (int g = 0; g < 4; g++) {
-    uint32_t t[8];
-#pragma unroll
-    for (int j = 0; j < 8; j++) t[j] = (uint32_t)r[8 * g + j];
-    w[3 * g] = t[0] | (t[1] << 12) | (t[2] << 24);
-    w[3 * g + 1] = (t[2] >> 8) | (t[3] << 4) | (t[4] << 16) | (t[5] << 28);
-    w[3 * g + 2] = (t[5] >> 4) | (t[6] << 8) | (t[7] << 20);
-  }
-}
-// Normalize (field.go:45-74) of a low-format register holding any int16 value: csubq(barrettReduce(x))
-__device__ __forceinline__ int32_t normalize_lo(int32_t x) {
-  x = kyber::barrett_lo(x) - Q;
-  return x + ((x >> 31) & Q);
 }
 
 // K-PKE.KeyGen arithmetic (cpapke.go:83-105): s-hat = Normalize(NTT(s)), e-hat = NTT(e),
@@ -1510,7 +1552,7 @@ static int r3_device(int decaps, const uint8_t* key, size_t key_stride, const ui
     const uint8_t* ek = key + 384 * K;
     {
       KernelScope ks(KID_MLKEM_ENCRYPT, st);
-      decrypt_kernel<K><<<(unsigned)((n + 15) / 16), kEncThreads, 0, st>>>(key, key_stride, in, n, m, tw);
+      if (int drc = launch_decrypt<K>(key, key_stride, in, n, m, tw, st)) return drc;
     }
     rc = r3_encrypt<K>(ek, key_stride, key + 384 * K + P::ek_bytes, key_stride, m, ct2, kbar, r, b, o_A, o_n, n, st, slot);
     if (rc) return rc;

@@ -179,14 +179,53 @@ def synth_polys(first_poly: int, n: int, device="cpu"):
 
 # ---------------------------------------------------------------- clocks sampler
 class ClockSampler:
+    """SM clock and throttle reasons DURING the timed region.  The region is short (5 steps of ~18 ms), so the samples
+    come from NVML in a thread (one query ~ 0.1 ms, every 2 ms) -- the same counters `nvidia-smi --query-gpu=clocks.sm,
+    clocks.max.sm,clocks_event_reasons.*` prints (B200_PROFILING.md), which is the fallback when pynvml is missing:
+    nvidia-smi itself needs longer to start than the region lasts."""
     FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
               "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
               "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index: int):
         self.index, self.rows, self.proc = index, [], None
+        self.nvml, self.handle, self.thread, self.stop_flag, self.samples, self.mask, self.max_mhz = None, None, None, False, [], 0, None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # LOCAL_RANK indexes the visible devices; map through CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            ids = [x.strip() for x in vis.split(",")] if vis else []
+            if index < len(ids) and ids[index].startswith("GPU-"):
+                self.handle = pynvml.nvmlDeviceGetHandleByUUID(ids[index])
+            else:
+                phys = int(ids[index]) if index < len(ids) and ids[index].isdigit() else index
+                self.handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM)))
+                try:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def start(self):
+        if self.nvml is not None:
+            self.stop_flag, self.samples, self.mask = False, [], 0
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
@@ -200,6 +239,14 @@ class ClockSampler:
             self.rows.append([c.strip() for c in line.split(",")])
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=1.0)
+            sm = self.samples
+            load = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
+            return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": self.max_mhz,
+                    "reasons": sorted(name for name, bit in self.REASONS if self.mask & bit), "samples": len(sm),
+                    "source": "nvml, every 2 ms during the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -217,7 +264,7 @@ class ClockSampler:
         # "under load" = samples in the upper half of what was seen (idle samples bracket the region)
         load = [x for x in sm if x >= 0.5 * max(sm)] if sm else []
         return {"sm_mhz": statistics.median(load) if load else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------- reference arm (CPU restatement)

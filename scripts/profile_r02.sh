@@ -17,7 +17,7 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:"sam
     -o gpurun_out/r02z_prof_mlkem python bench.py --steps 1 --warmup 3 --batch-log2 16 --no-cpu-baseline --no-ntt --no-extras > gpurun_out/r02z_prof_mlkem.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:"ntt_fwd_kernel|ntt_inv_kernel" -s 1 -c 2 \
     -o gpurun_out/r02z_prof_ntt python scripts/ntt_once.py > gpurun_out/r02z_prof_ntt.log 2>&1
-timeout 600 ncu --set full --clock-control none -k regex:"dil.*ntt_kernel|f1600_kernel" -s 4 -c 3 \
+timeout 600 ncu --set full --clock-control none -k regex:"^ntt_kernel$" -s 12 -c 2 \
     -o gpurun_out/r02z_prof_ring python scripts/time_ring.py > gpurun_out/r02z_prof_ring.log 2>&1
 timeout 600 ncu --set full --clock-control none -k regex:"mask_kernel|yntt_kernel|w_kernel|challenge_kernel|response_kernel" -c 7 \
     -o gpurun_out/r02z_prof_sign python scripts/sign_once.py > gpurun_out/r02z_prof_sign.log 2>&1

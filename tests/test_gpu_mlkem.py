@@ -11,6 +11,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 KS = {"ML-KEM-512": 2, "ML-KEM-768": 3, "ML-KEM-1024": 4}
+Q = 3329
 
 
 @pytest.fixture(scope="module")
@@ -172,6 +173,41 @@ def test_encaps_decaps_roundtrip_and_rejection(cb, ps):
     with pytest.raises(mlkem.ErrPrivKey) as ei:
         scheme.DecapsulateBatch(broken, ct[:4])
     assert ei.value.status.tolist() == [0, 0, 2, 0]
+
+
+@pytest.mark.parametrize("ps", list(KS))
+def test_decaps_with_unnormalised_secret_key_coefficients(cb, ps):
+    """PrivateKey.Unpack normalises s-hat after the 12-bit unpack (cpapke.go:32-36), so a dk whose s-hat coefficients
+    carry an extra q (still 12 bits) decapsulates like the canonical one.  The decrypt kernel feeds the packed words
+    straight into its products (only residues matter): it must agree with the oracle, which follows the reference."""
+    import oracle
+    from circl_b200 import mlkem
+    k = KS[ps]
+    scheme = mlkem.ByName(ps)
+    ek, dk = oracle.mlkem_keygen(k, _h(7, k, 64))
+    dkb = bytearray(dk)
+    changed = 0
+    for i in range(0, 128 * k):  # pairs of coefficients, 3 bytes each
+        b0, b1, b2 = dkb[3 * i], dkb[3 * i + 1], dkb[3 * i + 2]
+        c0, c1 = b0 | ((b1 & 0xF) << 8), (b1 >> 4) | (b2 << 4)
+        if c0 + Q < 4096 and i % 3 == 0:
+            c0 += Q
+            changed += 1
+        if c1 + Q < 4096 and i % 5 == 0:
+            c1 += Q
+            changed += 1
+        dkb[3 * i], dkb[3 * i + 1], dkb[3 * i + 2] = c0 & 0xFF, (c0 >> 8) | ((c1 & 0xF) << 4), c1 >> 4
+    assert changed > 10
+    n = 40
+    ms = np.stack([np.frombuffer(_h(8, i, 32), dtype=np.uint8) for i in range(n)])
+    eks = np.stack([np.frombuffer(ek, dtype=np.uint8)] * n)
+    ct, ss = scheme.EncapsulateBatch(eks, ms)
+    ct[::4, 9] ^= 0x11                                                    # some implicit rejections as well
+    dks = np.stack([np.frombuffer(bytes(dkb), dtype=np.uint8)] * n)
+    got = scheme.DecapsulateBatch(dks, ct)
+    for i in range(n):
+        assert got[i].tobytes() == oracle.mlkem_decaps(k, bytes(dkb), ct[i].tobytes()), i
+    assert np.array_equal(got[1], ss[1])                                  # and it still is the key pair's secret
 
 
 # ---------------------------------------------------------------- KeyGen (SURVEY.md 8(f) row 2)

@@ -40,17 +40,7 @@ __global__ void __launch_bounds__(kThreads, 6) ntt_kernel(uint32_t* __restrict__
     if (!INV) {
       gload_S(poly, v, r);
       ntt_octet_smem(r, tile, v, zs);
-      store_C(tile, v, r);
-      __syncwarp();
-      uint4 w[8];
-#pragma unroll
-      for (int c = 0; c < 8; c++) w[c] = *reinterpret_cast<const uint4*>(tile + 36 * c + 4 * v);
-      __syncwarp();
-      if (active) {
-        uint4* dst = reinterpret_cast<uint4*>(poly) + v;
-#pragma unroll
-        for (int c = 0; c < 8; c++) dst[8 * c] = w[c];
-      }
+      gstore_C_via_tile(poly, tile, v, r, active);
     } else {
       uint4 w[8];
       gload_I(poly, v, w);

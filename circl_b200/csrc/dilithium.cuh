@@ -413,6 +413,24 @@ __device__ __forceinline__ void gstore_C(uint32_t* __restrict__ poly, int v, con
   for (int c = 0; c < 8; c++) p[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
 }
 
+// C-layout registers -> global memory in the interleaved order of gload_I through the octet's (free) tile: an octet
+// writes 128 contiguous bytes per instruction instead of eight 16-byte pieces 128 bytes apart.  Every lane of the warp
+// calls it; only active octets store.
+__device__ __forceinline__ void gstore_C_via_tile(uint32_t* __restrict__ poly, uint32_t* tile, int v,
+                                                  const uint32_t (&r)[32], bool active) {
+  store_C(tile, v, r);
+  __syncwarp();
+  uint4 w[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++) w[c] = *reinterpret_cast<const uint4*>(tile + 36 * c + 4 * v);
+  __syncwarp();
+  if (active) {
+    uint4* dst = reinterpret_cast<uint4*>(poly) + v;
+#pragma unroll
+    for (int c = 0; c < 8; c++) dst[8 * c] = w[c];
+  }
+}
+
 // Whole transforms on an octet.  fwd: in S layout -> out C layout; inv: in C layout -> out S layout.
 __device__ __forceinline__ void ntt_octet(uint32_t (&r)[32], uint32_t* tile, int v, const LaneTw& t) {
   fwd_pass_S(r);

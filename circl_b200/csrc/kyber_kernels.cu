@@ -90,7 +90,10 @@ constexpr int kFwdCtasPerSm = 5, kInvCtasPerSm = 6;
 //     input runs the general high-half code (int16 wrap-around exact) on the same words.
 // Measured on a B200 (profiles/r02y_*): 92 registers, 5 CTAs per SM; both integer pipes ~70 % busy, issue 78 %.
 // Slower in the same sweep (profiles/r02y_ntt_variants*.json): the pairs read from shared memory at 6 / 7 CTAs per SM,
-// two slots per octet, the whole shared-memory carve-out.
+// two slots per octet, the whole shared-memory carve-out.  Also measured and dropped (profiles/r02z4_bench.json): output /
+// input of the C-layout side in 128-byte-contiguous order through the tile, which takes the Dilithium kernels from 0.62 to
+// 0.89 of the HBM peak (their lanes are 128 bytes apart and the kernel waits on the memory pipeline) but costs these
+// pipe-bound kernels 1-2 % (eight more shared-memory instructions per polynomial, lanes only 64 bytes apart).
 __global__ void __launch_bounds__(kThreads, kFwdCtasPerSm) ntt_fwd_kernel(uint32_t* __restrict__ polys, size_t n,
                                                                           const TwPair* __restrict__ tw) {
   extern __shared__ __align__(16) unsigned char dsm[];

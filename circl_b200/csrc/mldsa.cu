@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(128) expand_s_kernel(const uint8_t* __restrict
   LaneTw t;
   load_lane_tw_fwd(t, zetas, v);
   ntt_octet(r, tile, v, t);
-  if (active) gstore_C(sh + (key * NKEYPOLY + p) * N, v, r);
+  gstore_C_via_tile(sh + (key * NKEYPOLY + p) * N, tile, v, r, active);
 }
 
 // ------------------------------------------------------------------ mu, rho'
@@ -459,7 +459,7 @@ __global__ void __launch_bounds__(128) yntt_kernel(const uint32_t* __restrict__ 
   LaneTw t;
   load_lane_tw_fwd(t, zetas, o.v);
   ntt_octet(r, o.tile, o.v, t);
-  if (active) gstore_C(yh + (op * L + j) * N, o.v, r);
+  gstore_C_via_tile(yh + (op * L + j) * N, o.tile, o.v, r, active);
 }
 
 // decompose (rounding.go:13-43): alpha = 523776 (gamma2 = (q-1)/32) or 190464 (gamma2 = (q-1)/88)
@@ -780,7 +780,7 @@ __global__ void __launch_bounds__(128) cntt_mask_kernel(const uint32_t* __restri
   load_lane_tw_fwd(t, zetas, o.v);
   ntt_octet(r, o.tile, o.v, t);
   __syncwarp();
-  if (active) gstore_C(cpoly + op * N, o.v, r);
+  gstore_C_via_tile(cpoly + op * N, o.tile, o.v, r, active);
 }
 
 // c-hat = NTT(c): octet per active op
@@ -798,7 +798,7 @@ __global__ void __launch_bounds__(128) cntt_kernel(const uint32_t* __restrict__ 
   load_lane_tw_fwd(t, zetas, o.v);
   ntt_octet(r, o.tile, o.v, t);
   __syncwarp();
-  if (active) gstore_C(cpoly + op * N, o.v, r);
+  gstore_C_via_tile(cpoly + op * N, o.tile, o.v, r, active);
 }
 
 // InvNTT(c-hat . x-hat) on an octet: returns S layout
@@ -1190,7 +1190,7 @@ __global__ void __launch_bounds__(128) verify_z_kernel(const uint8_t* __restrict
   LaneTw t;
   load_lane_tw_fwd(t, zetas, o.v);
   ntt_octet(r, o.tile, o.v, t);
-  if (active) gstore_C(zh + (op * L + j) * N, o.v, r);
+  gstore_C_via_tile(zh + (op * L + j) * N, o.tile, o.v, r, active);
   reject = __any_sync(octmask, reject);
   if (reject && active && o.v == 0) atomicOr(flags + op, 1u);
 }
@@ -1507,7 +1507,7 @@ __global__ void __launch_bounds__(128) kg_s1ntt_kernel(const uint32_t* __restric
   LaneTw t;
   load_lane_tw_fwd(t, zetas, o.v);
   ntt_octet(r, o.tile, o.v, t);
-  if (active) gstore_C(s1h + (op * L + j) * N, o.v, r);
+  gstore_C_via_tile(s1h + (op * L + j) * N, o.tile, o.v, r, active);
 }
 
 // t = Normalize(InvNTT(ReduceLe2Q(A[i] . s1h)) + s2[i]); Power2Round; PackT1 -> pk, PackT0 -> sk: octet per (op, i)

@@ -119,13 +119,6 @@ __device__ __forceinline__ uint32_t pack2(int32_t lo, int32_t hi) {
 // both access patterns below are bank-conflict free; octet stride 152 words
 // (== 24 mod 32) separates the four octets of a warp.
 constexpr int kPolyWords = 152;
-__device__ __forceinline__ int phys_word(int w) { return w + ((w >> 5) << 2); }
-
-// S-layout word s of lane v  <-> logical word 8s + v
-template <int S>
-__device__ __forceinline__ int s_word(int v) {
-  return 8 * S + v + 4 * (S >> 2);
-}
 
 // ---------------------------------------------------------------- butterflies
 // Cooley-Tukey, ntt.go:129-131
@@ -178,25 +171,9 @@ __device__ __forceinline__ void load_lane_tw(LaneTw& t, const TwPair* __restrict
   for (int i = 0; i < 8; i++) t.l2[i] = tab[64 + 8 * v + i];
 }
 
-// Forward pass 2 on C layout: layers l = 8, 4, 2.
-__device__ __forceinline__ void fwd_pass_C(int32_t (&r)[32], const LaneTw& t) {
-#pragma unroll
-  for (int blk = 0; blk < 2; blk++)
-#pragma unroll
-    for (int j = 0; j < 8; j++) ct_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.l8[blk].z, t.l8[blk].zq);
-#pragma unroll
-  for (int blk = 0; blk < 4; blk++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) ct_bfly(r[8 * blk + j], r[8 * blk + j + 4], t.l4[blk].z, t.l4[blk].zq);
-#pragma unroll
-  for (int blk = 0; blk < 8; blk++)
-#pragma unroll
-    for (int j = 0; j < 2; j++) ct_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.l2[blk].z, t.l2[blk].zq);
-}
-
-// The same pass with the twiddles read from a shared-memory copy of the table at the
-// point of use (keeps 28 registers free -> 8 CTAs of 128 threads per SM).  `tab` must be
-// volatile-qualified by the caller's cast so the loads stay inside the polynomial loop.
+// Forward pass 2 on C layout (layers l = 8, 4, 2) with the twiddles read from a shared-memory copy of the table at the
+// point of use (28 registers less than holding them).  `tab` must be volatile-qualified by the caller's cast so the
+// loads stay inside the polynomial loop.
 __device__ __forceinline__ TwPair tw_at(const volatile TwPair* tab, int k) {
   const volatile int2* p = reinterpret_cast<const volatile int2*>(tab + k);
   TwPair t;
@@ -243,26 +220,6 @@ __device__ __forceinline__ void inv_pass_C_smem(int32_t (&r)[32], const volatile
 #pragma unroll
     for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.z, t.zq);
   }
-  r[16] = barrett_hi(r[16]);
-  r[17] = barrett_hi(r[17]);
-}
-
-// Inverse pass A on C layout: layers l = 2, 4, 8 then the layer-3 Barrett set
-// (indices == 16,17 mod 32, ntt.go:42-43).  Zetas[k] with k = 127-(idx>>2),
-// 63-(idx>>3), 31-(idx>>4): i.e. the forward per-lane entries of lane 7-v, reversed.
-__device__ __forceinline__ void inv_pass_C(int32_t (&r)[32], const LaneTw& t) {
-#pragma unroll
-  for (int blk = 0; blk < 8; blk++)
-#pragma unroll
-    for (int j = 0; j < 2; j++) gs_bfly(r[4 * blk + j], r[4 * blk + j + 2], t.l2[7 - blk].z, t.l2[7 - blk].zq);
-#pragma unroll
-  for (int blk = 0; blk < 4; blk++)
-#pragma unroll
-    for (int j = 0; j < 4; j++) gs_bfly(r[8 * blk + j], r[8 * blk + j + 4], t.l4[3 - blk].z, t.l4[3 - blk].zq);
-#pragma unroll
-  for (int blk = 0; blk < 2; blk++)
-#pragma unroll
-    for (int j = 0; j < 8; j++) gs_bfly(r[16 * blk + j], r[16 * blk + j + 8], t.l8[1 - blk].z, t.l8[1 - blk].zq);
   r[16] = barrett_hi(r[16]);
   r[17] = barrett_hi(r[17]);
 }
@@ -349,28 +306,9 @@ __device__ __forceinline__ void load_C_ct(const uint32_t* tile, int v, int32_t (
     unpack2_ct(w.w, r[8 * c + 6], r[8 * c + 7]);
   }
 }
-__device__ __forceinline__ void load_C(const uint32_t* tile, int v, int32_t (&r)[32]) {
-  const uint4* p = reinterpret_cast<const uint4*>(tile + 16 * v + 4 * (v >> 1));
-#pragma unroll
-  for (int c = 0; c < 4; c++) {
-    uint4 w = p[c];
-    unpack2(w.x, r[8 * c], r[8 * c + 1]);
-    unpack2(w.y, r[8 * c + 2], r[8 * c + 3]);
-    unpack2(w.z, r[8 * c + 4], r[8 * c + 5]);
-    unpack2(w.w, r[8 * c + 6], r[8 * c + 7]);
-  }
-}
 
 // ---------------------------------------------------------------- global <-> registers
-// S layout straight from global memory: 16 x 32-bit, each octet reads one full
-// 32-byte sector per instruction.
-__device__ __forceinline__ void gload_S(const uint32_t* __restrict__ poly, int v, int32_t (&r)[32]) {
-  uint32_t w[16];
-#pragma unroll
-  for (int s = 0; s < 16; s++) w[s] = ldg_stream32(poly + 8 * s + v);
-#pragma unroll
-  for (int s = 0; s < 16; s++) unpack2(w[s], r[2 * s], r[2 * s + 1]);
-}
+// S layout: 16 x 32-bit per lane, each octet moves one full 32-byte sector per instruction
 __device__ __forceinline__ void gstore_S(uint32_t* __restrict__ poly, int v, const int32_t (&r)[32]) {
 #pragma unroll
   for (int s = 0; s < 16; s++) poly[8 * s + v] = pack2(r[2 * s], r[2 * s + 1]);

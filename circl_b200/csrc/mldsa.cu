@@ -866,11 +866,14 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
     bool reject = false;
     if constexpr (STAGE == 0) {
       const int i = item;
-      c_times(r, chat, keyp + (L + i) * N, o, ti);  // c s2[i]
       uint32_t* w0p = w0 + (op * K + i) * N;
+      uint2 aw[16];  // w0[i], requested before the product and the inverse transform instead of after them
+#pragma unroll
+      for (int s = 0; s < 16; s++) aw[s] = *reinterpret_cast<const uint2*>(w0p + 16 * s + 2 * o.v);
+      c_times(r, chat, keyp + (L + i) * N, o, ti);  // c s2[i]
 #pragma unroll
       for (int s = 0; s < 16; s++) {
-        const uint2 a = *reinterpret_cast<const uint2*>(w0p + 16 * s + 2 * o.v);
+        const uint2 a = aw[s];
         r[2 * s] = modq(a.x + (2 * Q - r[2 * s]));  // w0 - c s2, Normalize
         r[2 * s + 1] = modq(a.y + (2 * Q - r[2 * s + 1]));
         reject |= exceeds1(r[2 * s], GAMMA2 - BETA) | exceeds1(r[2 * s + 1], GAMMA2 - BETA);
@@ -878,11 +881,14 @@ __global__ void __launch_bounds__(128) response_kernel(const uint32_t* __restric
       }
     } else if constexpr (STAGE == 1) {
       const int j = item;
-      c_times(r, chat, keyp + j * N, o, ti);  // c s1[j]
       const uint32_t* yp = y + (op * L + j) * N;
+      uint2 aw[16];  // y[j], requested before the product and the inverse transform
+#pragma unroll
+      for (int s = 0; s < 16; s++) aw[s] = __ldg(reinterpret_cast<const uint2*>(yp + 16 * s + 2 * o.v));
+      c_times(r, chat, keyp + j * N, o, ti);  // c s1[j]
 #pragma unroll
       for (int s = 0; s < 16; s++) {
-        const uint2 a = *reinterpret_cast<const uint2*>(yp + 16 * s + 2 * o.v);
+        const uint2 a = aw[s];
         r[2 * s] = modq(r[2 * s] + a.x);
         r[2 * s + 1] = modq(r[2 * s + 1] + a.y);
         reject |= exceeds1(r[2 * s], GAMMA1 - BETA) | exceeds1(r[2 * s + 1], GAMMA1 - BETA);

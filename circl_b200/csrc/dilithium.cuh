@@ -249,7 +249,7 @@ __device__ __forceinline__ uint2 pair_at(const volatile uint2* tab, int i) {
   return z;
 }
 template <bool INV>
-__device__ __forceinline__ int staged_index(int p) {  // table index of a pair -> its place in the staged copy
+__host__ __device__ __forceinline__ int staged_index(int p) {  // table index of a pair -> its place in the staged copy
   int b, c;
   if (!INV) {
     if (p >= 128) b = 128, c = 16;

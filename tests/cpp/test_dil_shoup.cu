@@ -26,6 +26,24 @@ int main() {
       if (mont_mul_shoup(b, p, k) != orc_dil_mont_reduce_le2q((uint64_t)c * b)) { bad++; if (bad < 10) printf("rnd %d %u\n", i, b); }
     }
   }
+  // the lane-transposed shared-memory copy of the pair tables (stage_pairs): a permutation of 0..255 that puts "entry i
+  // of lane v" of a layer (table position base + c v + i) at base + 8 i + v, the index the C-layout passes read
+  for (int inv = 0; inv < 2; inv++) {
+    bool seen[256] = {false};
+    for (int p = 0; p < 256; p++) {
+      const int d = inv ? staged_index<true>(p) : staged_index<false>(p);
+      if (d < 0 || d > 255 || seen[d]) { bad++; printf("staged_index not a permutation (%d, %d)\n", inv, p); }
+      else seen[d] = true;
+    }
+    const int bases[4] = {inv ? 0 : 128, inv ? 128 : 64, inv ? 192 : 32, inv ? 224 : 16}, per_lane[4] = {16, 8, 4, 2};
+    for (int l = 0; l < 4; l++)
+      for (int v = 0; v < 8; v++)
+        for (int i = 0; i < per_lane[l]; i++) {
+          const int table = bases[l] + per_lane[l] * v + i, want = bases[l] + 8 * i + v;
+          const int got = inv ? staged_index<true>(table) : staged_index<false>(table);
+          if (got != want) { bad++; printf("staged_index(%d) = %d, want %d\n", table, got, want); }
+        }
+  }
   printf("bad=%d\n", bad);
   return bad != 0;
 }

@@ -14,7 +14,7 @@
 //   1. hash_kernel    one thread per op/key: h = SHA3-256(ek), (K', r) = SHA3-512(m || h)
 //   2. sample_kernel  one thread per Keccak stream: K*K SHAKE128 matrix streams per key,
 //                     2K+1 SHAKE256 noise streams per op (warps are stream-homogeneous)
-//   3. encrypt_kernel one octet (8 lanes) per op: NTT(r), A^T o r, t o r, InvNTT, +e, compress
+//   3. encrypt_dp_kernel one octet (8 lanes) per op: NTT(r), A^T o r, t o r, InvNTT, +e, compress
 #include <stdlib.h>
 #include <string.h>
 

@@ -67,7 +67,7 @@ struct Shoup {
 };
 
 template <int B, int E, class F>
-__device__ __forceinline__ void static_for(F&& f) {
+__host__ __device__ __forceinline__ void static_for(F&& f) {
   if constexpr (B < E) {
     f(std::integral_constant<int, B>{});
     static_for<B + 1, E>(f);
@@ -85,9 +85,8 @@ __device__ __forceinline__ uint32_t mont_mul(uint32_t a, uint32_t b) { return mo
 // r01_ubench_pipes.txt), and the compiler turns the plain C expression into the latter.
 __host__ __device__ __forceinline__ uint32_t mulhi_wide(uint32_t k, uint32_t b) {
 #ifdef __CUDA_ARCH__
-  uint32_t hi, lo;
-  asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%1, %0}, t; }" : "=r"(hi), "=r"(lo) : "r"(k), "r"(b));
-  (void)lo;
+  uint32_t hi;
+  asm("{ .reg .b64 t; mul.wide.u32 t, %1, %2; mov.b64 {_, %0}, t; }" : "=r"(hi) : "r"(k), "r"(b));
   return hi;
 #else
   return (uint32_t)(((uint64_t)k * b) >> 32);
@@ -97,7 +96,7 @@ __host__ __device__ __forceinline__ uint32_t mont_mul_shoup(uint32_t b, uint32_t
   return p * b - mulhi_wide(k, b) * Q;
 }
 template <uint32_t C>
-__device__ __forceinline__ uint32_t mont_mul_const(uint32_t b) {  // == mont_mul(C, b), see Shoup above
+__host__ __device__ __forceinline__ uint32_t mont_mul_const(uint32_t b) {  // == mont_mul(C, b), see Shoup above
   return mont_mul_shoup(b, Shoup<C>::p, Shoup<C>::k);
 }
 __device__ __forceinline__ uint32_t reduce_le2q(uint32_t x) {  // field.go:5-13
@@ -119,25 +118,25 @@ __device__ __forceinline__ bool exceeds1(uint32_t c, uint32_t bound) {
 
 // ---------------------------------------------------------------- butterflies
 // A run-time twiddle is its Shoup pair {p, k} (see struct Shoup).
-__device__ __forceinline__ void ct_bfly(uint32_t& a, uint32_t& b, uint2 z) {  // ntt.go:177-180
+__host__ __device__ __forceinline__ void ct_bfly(uint32_t& a, uint32_t& b, uint2 z) {  // ntt.go:177-180
   const uint32_t t = mont_mul_shoup(b, z.x, z.y);
   b = a + (2 * Q - t);
   a = a + t;
 }
-__device__ __forceinline__ void gs_bfly(uint32_t& a, uint32_t& b, uint2 z) {  // ntt.go:202-208
+__host__ __device__ __forceinline__ void gs_bfly(uint32_t& a, uint32_t& b, uint2 z) {  // ntt.go:202-208
   uint32_t t = a;
   a = t + b;
   t += 256 * Q - b;
   b = mont_mul_shoup(t, z.x, z.y);
 }
 template <uint32_t Z>
-__device__ __forceinline__ void ct_bfly_const(uint32_t& a, uint32_t& b) {  // ntt.go:177-180, immediate twiddle
+__host__ __device__ __forceinline__ void ct_bfly_const(uint32_t& a, uint32_t& b) {  // ntt.go:177-180, immediate twiddle
   const uint32_t t = mont_mul_const<Z>(b);
   b = a + (2 * Q - t);
   a = a + t;
 }
 template <uint32_t Z>
-__device__ __forceinline__ void gs_bfly_const(uint32_t& a, uint32_t& b) {  // ntt.go:202-208, immediate twiddle
+__host__ __device__ __forceinline__ void gs_bfly_const(uint32_t& a, uint32_t& b) {  // ntt.go:202-208, immediate twiddle
   uint32_t t = a;
   a = t + b;
   t += 256 * Q - b;
@@ -184,7 +183,7 @@ __device__ __forceinline__ void load_lane_tw_inv(LaneTw& t, const uint32_t* __re
 }
 
 // forward pass 1, S layout: l = 128 (k=1), 64 (k=2+h), 32 (k=4+h), 16 (k=8+h)
-__device__ __forceinline__ void fwd_pass_S(uint32_t (&r)[32]) {
+__host__ __device__ __forceinline__ void fwd_pass_S(uint32_t (&r)[32]) {
 #pragma unroll
   for (int i = 0; i < 16; i++) ct_bfly_const<Zeta<1>::z>(r[i], r[i + 16]);
   static_for<0, 2>([&](auto hc) {
@@ -242,7 +241,7 @@ __device__ __forceinline__ void inv_pass_C(uint32_t (&r)[32], const LaneTw& t) {
 // base + c v + i (c = 16, 8, 4, 2 entries per lane for l = 1, 2, 4, 8) -- eight lanes 2c words apart, i.e. on one or two
 // banks; stage_pairs stores it at base + 8 i + v instead, so that the eight lanes of an octet read eight consecutive
 // pairs (the four octets of a warp read the same ones: a broadcast).
-__device__ __forceinline__ uint2 pair_at(const volatile uint2* tab, int i) {
+__host__ __device__ __forceinline__ uint2 pair_at(const volatile uint2* tab, int i) {
   uint2 z;
   z.x = tab[i].x;
   z.y = tab[i].y;
@@ -278,7 +277,7 @@ __device__ __forceinline__ void stage_pairs(volatile uint2* dst, const uint32_t*
     dst[d].y = z.y;
   }
 }
-__device__ __forceinline__ void fwd_pass_C_smem(uint32_t (&r)[32], const volatile uint2* zs, int v) {
+__host__ __device__ __forceinline__ void fwd_pass_C_smem(uint32_t (&r)[32], const volatile uint2* zs, int v) {
 #pragma unroll
   for (int blk = 0; blk < 2; blk++) {
     const uint2 z = pair_at(zs, 16 + 8 * blk + v);
@@ -300,7 +299,7 @@ __device__ __forceinline__ void fwd_pass_C_smem(uint32_t (&r)[32], const volatil
 #pragma unroll
   for (int blk = 0; blk < 16; blk++) ct_bfly(r[2 * blk], r[2 * blk + 1], pair_at(zs, 128 + 8 * blk + v));
 }
-__device__ __forceinline__ void inv_pass_C_smem(uint32_t (&r)[32], const volatile uint2* iz, int v) {
+__host__ __device__ __forceinline__ void inv_pass_C_smem(uint32_t (&r)[32], const volatile uint2* iz, int v) {
 #pragma unroll
   for (int blk = 0; blk < 16; blk++) gs_bfly(r[2 * blk], r[2 * blk + 1], pair_at(iz, 8 * blk + v));
 #pragma unroll
@@ -328,7 +327,7 @@ __device__ __forceinline__ void stage_inv_pairs(volatile uint2* dst, const uint3
 }
 
 // inverse pass B, S layout: l = 16 (k=240+h), 32 (248+h), 64 (252+h), 128 (254), then * ROver256
-__device__ __forceinline__ void inv_pass_S(uint32_t (&r)[32]) {
+__host__ __device__ __forceinline__ void inv_pass_S(uint32_t (&r)[32]) {
   static_for<0, 8>([&](auto hc) {
     constexpr int h = decltype(hc)::value;
 #pragma unroll
@@ -353,12 +352,12 @@ __device__ __forceinline__ void inv_pass_S(uint32_t (&r)[32]) {
 // ---------------------------------------------------------------- shared-memory tile (S <-> C)
 // 256 words + 4 pad words after every 32; octet stride 304 words (== 16 mod 32).
 constexpr int kPolyWords = 304;
-__device__ __forceinline__ void store_S(uint32_t* tile, int v, const uint32_t (&r)[32]) {
+__host__ __device__ __forceinline__ void store_S(uint32_t* tile, int v, const uint32_t (&r)[32]) {
 #pragma unroll
   for (int s = 0; s < 16; s++)
     *reinterpret_cast<uint2*>(tile + 16 * s + 2 * v + 4 * (s >> 1)) = make_uint2(r[2 * s], r[2 * s + 1]);
 }
-__device__ __forceinline__ void load_S(const uint32_t* tile, int v, uint32_t (&r)[32]) {
+__host__ __device__ __forceinline__ void load_S(const uint32_t* tile, int v, uint32_t (&r)[32]) {
 #pragma unroll
   for (int s = 0; s < 16; s++) {
     const uint2 w = *reinterpret_cast<const uint2*>(tile + 16 * s + 2 * v + 4 * (s >> 1));
@@ -366,12 +365,12 @@ __device__ __forceinline__ void load_S(const uint32_t* tile, int v, uint32_t (&r
     r[2 * s + 1] = w.y;
   }
 }
-__device__ __forceinline__ void store_C(uint32_t* tile, int v, const uint32_t (&r)[32]) {
+__host__ __device__ __forceinline__ void store_C(uint32_t* tile, int v, const uint32_t (&r)[32]) {
   uint4* p = reinterpret_cast<uint4*>(tile + 36 * v);
 #pragma unroll
   for (int c = 0; c < 8; c++) p[c] = make_uint4(r[4 * c], r[4 * c + 1], r[4 * c + 2], r[4 * c + 3]);
 }
-__device__ __forceinline__ void load_C(const uint32_t* tile, int v, uint32_t (&r)[32]) {
+__host__ __device__ __forceinline__ void load_C(const uint32_t* tile, int v, uint32_t (&r)[32]) {
   const uint4* p = reinterpret_cast<const uint4*>(tile + 36 * v);
 #pragma unroll
   for (int c = 0; c < 8; c++) {

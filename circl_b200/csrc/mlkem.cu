@@ -508,9 +508,8 @@ __device__ __forceinline__ int32_t mont_red_lo(int32_t p) { return mont_red_hi(p
 // hi32(a * b) as a wide multiplication: IMAD.WIDE.U32 issues faster than the IMAD.HI.U32 __umulhi compiles to (0.24
 // against 0.18 per clock and sub-partition, profiles/r01c_ubench_imad_wide.txt)
 __device__ __forceinline__ uint32_t umulhi_wide(uint32_t a, uint32_t b) {
-  uint32_t hi, lo;
-  asm("{ .reg .b64 t; mul.wide.u32 t, %2, %3; mov.b64 {%1, %0}, t; }" : "=r"(hi), "=r"(lo) : "r"(a), "r"(b));
-  (void)lo;
+  uint32_t hi;
+  asm("{ .reg .b64 t; mul.wide.u32 t, %1, %2; mov.b64 {_, %0}, t; }" : "=r"(hi) : "r"(a), "r"(b));
   return hi;
 }
 template <int D>

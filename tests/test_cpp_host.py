@@ -106,3 +106,19 @@ def test_dilithium_shoup_constants_on_host(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout[-2000:]
+
+
+def test_dilithium_transform_passes_on_host(tmp_path):
+    """csrc/dilithium.cuh's transform passes compiled as host code: an emulated octet (S-layout pass with immediate
+    Shoup pairs, padded-tile transposition, C-layout pass reading the lane-transposed staged pairs) against the
+    oracle's NTT / InvNTT, unnormalised, on arbitrary uint32 inputs (tests/cpp/test_dil_passes.cu)."""
+    import oracle
+    oracle.build()
+    exe = str(tmp_path / "dil_passes")
+    odir = os.path.join(ROOT, "oracle")
+    r = subprocess.run([os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"), "-O2", "-std=c++17", "--expt-relaxed-constexpr",
+                        "-Wno-deprecated-gpu-targets", os.path.join(ROOT, "tests", "cpp", "test_dil_passes.cu"), "-o", exe,
+                        "-L", odir, "-loracle", "-Xlinker", "-rpath=" + odir], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "bad=0" in r.stdout, r.stdout[-2000:]
